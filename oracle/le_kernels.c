@@ -1,0 +1,512 @@
+/*
+ * oracle/le_kernels.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, no dependencies) of the arithmetic of IBAMR's
+ * Lagrangian-Eulerian interaction Fortran routines for the five in-scope
+ * kernels.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may call into this file; the product path
+ * (ibamr_b200/csrc) never does.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks this file against
+ * the reference's own golden files (copied fixtures under tests/golden/):
+ *   tests/interpolate/interpolate_01_{2d,3d}.{ib_4,ib_6,bspline_3,bspline_4,
+ *   piecewise_linear}.output, tests/IBTK/ghost_accumulation_01_*spread*.output,
+ *   tests/IBTK/index_utilities_{2d,3d}.output.
+ *
+ * Reference files followed (all under /root/reference/ibtk/src/lagrangian/fortran):
+ *   lagrangian_interaction3d.f.m4:24-86     fixed-width inner loops (bspline)
+ *   lagrangian_interaction3d.f.m4:493-730   piecewise_linear interp/spread
+ *   lagrangian_interaction3d.f.m4:1203-1475 ib_4 interp/spread
+ *   lagrangian_interaction3d.f.m4:2178-2582 ib_6 interp/spread
+ *   lagrangian_interaction3d.f.m4:2591-2805 bspline_3 interp/spread
+ *   lagrangian_interaction3d.f.m4:2814-3041 bspline_4 interp/spread
+ *   lagrangian_interaction2d.f.m4:469,587,1152,1273,1971,2136,2300,2410,2519,2634
+ *   lagrangian_delta.f.m4:243-288           bspline_3 / bspline_4 1-D functions
+ *
+ * Structure here is NOT the reference's: the Fortran has one hand-unrolled
+ * subroutine per (kernel, op, dim).  This file factors every routine into
+ *   (1) a per-dimension "stencil" (loop bounds + 1-D weights), and
+ *   (2) one of two accumulation styles:
+ *       TENSOR  (ib_4, ib_6): w3 = w0*(w1*wz), wz = w2 [/ (dx0*dx1*dx2) for spread]
+ *       INLINE  (bspline_3/4, piecewise_linear): ((w0*w1)*w2)*u, spread divides
+ *               the whole term by (dx0*dx1*dx2)
+ * keeping the reference's evaluation order so results agree to rounding.
+ * Build with -ffp-contract=off (no FMA contraction), see oracle/Makefile.
+ *
+ * Array conventions (Fortran, restated):
+ *   u(ilower0-g0:iupper0+g0, ilower1-g1:iupper1+g1[, ilower2-g2:iupper2+g2], 0:depth-1)
+ *   X(0:NDIM-1, 0:*), V(0:depth-1, 0:*), Xshift(0:NDIM-1, 0:nindices-1), indices(0:nindices-1)
+ */
+#include <math.h>
+#include <stddef.h>
+
+#define MAXW 6
+
+enum
+{
+    K_PIECEWISE_LINEAR = 0,
+    K_IB_4 = 1,
+    K_IB_6 = 2,
+    K_BSPLINE_3 = 3,
+    K_BSPLINE_4 = 4
+};
+
+typedef struct
+{
+    int lo, hi;     /* loop bounds in array index space (already clipped to the ghost box) */
+    int wbase;      /* weight j belongs to array index wbase + j                            */
+    double w[MAXW]; /* 1-D weights                                                          */
+} stencil1d;
+
+/* Fortran NINT: round half away from zero. */
+static inline int nint_f(double x)
+{
+    return (int)lround(x);
+}
+
+/* lagrangian_delta.f.m4:243-260 */
+static double bspline_3_delta(double x)
+{
+    const double modx = fabs(x);
+    const double r = modx + 1.5;
+    const double r2 = r * r;
+    if (modx <= 0.5) return 0.5 * (-2.0 * r2 + 6.0 * r - 3.0);
+    if (modx <= 1.5) return 0.5 * (r2 - 6.0 * r + 9.0);
+    return 0.0;
+}
+
+/* lagrangian_delta.f.m4:268-288 */
+static double bspline_4_delta(double x)
+{
+    const double modx = fabs(x);
+    const double r = modx + 2.0;
+    const double r2 = r * r;
+    const double r3 = r2 * r;
+    if (modx <= 1.0) return (1.0 / 6.0) * (3.0 * r3 - 24.0 * r2 + 60.0 * r - 44.0);
+    if (modx <= 2.0) return (1.0 / 6.0) * (-r3 + 12.0 * r2 - 48.0 * r + 64.0);
+    return 0.0;
+}
+
+/* 3d.f.m4:1265-1273, 1309-1310 (one dimension of ib_4). */
+static void stencil_ib_4(double Xs, double x_lower, double dx, int ilower, int iupper, int g, stencil1d* s)
+{
+    const double X_o_dx = (Xs - x_lower) / dx;
+    const int ic_lower = nint_f(X_o_dx) + ilower - 2;
+    const int ic_upper = ic_lower + 3;
+    const double r = X_o_dx - ((ic_lower + 1 - ilower) + 0.5);
+    const double q = sqrt(1.0 + 4.0 * r * (1.0 - r));
+    s->w[0] = 0.125 * (3.0 - 2.0 * r - q);
+    s->w[1] = 0.125 * (3.0 - 2.0 * r + q);
+    s->w[2] = 0.125 * (1.0 + 2.0 * r + q);
+    s->w[3] = 0.125 * (1.0 + 2.0 * r - q);
+    const int ig_lower = ilower - g, ig_upper = iupper + g;
+    const int istart = (ig_lower - ic_lower > 0) ? ig_lower - ic_lower : 0;
+    const int istop = 3 - ((ic_upper - ig_upper > 0) ? ic_upper - ig_upper : 0);
+    s->wbase = ic_lower;
+    s->lo = ic_lower + istart;
+    s->hi = ic_lower + istop;
+}
+
+/* 3d.f.m4:2220, 2243-2272, 2350-2351 (one dimension of ib_6). */
+static void stencil_ib_6(double Xs, double x_lower, double dx, int ilower, int iupper, int g, stencil1d* s)
+{
+    const double K = (59.0 / 60.0) * (1.0 - sqrt(1.0 - (3220.0 / 3481.0)));
+    const double X_o_dx = (Xs - x_lower) / dx;
+    const int ic_lower = nint_f(X_o_dx) + ilower - 3;
+    const int ic_upper = ic_lower + 5;
+    const double r = 1.0 - X_o_dx + ((ic_lower + 2 - ilower) + 0.5);
+    const double r2 = r * r;
+    const double r3 = r2 * r;
+    const double r4 = r2 * r2;
+    const double r6 = r4 * r2;
+    const double alpha = 28.0;
+    const double beta = (9.0 / 4.0) - (3.0 / 2.0) * (K + r2) + ((22.0 / 3.0) - 7.0 * K) * r - (7.0 / 3.0) * r3;
+    const double gamma = (1.0 / 4.0) * (((161.0 / 36.0) - (59.0 / 6.0) * K + 5.0 * (K * K)) * (1.0 / 2.0) * r2 +
+                                        (-(109.0 / 24.0) + 5.0 * K) * (1.0 / 3.0) * r4 + (5.0 / 18.0) * r6);
+    const double discr = beta * beta - 4.0 * alpha * gamma;
+    const double sgn = ((3.0 / 2.0) - K) >= 0.0 ? 1.0 : -1.0;
+    const double pm3 = (-beta + sgn * sqrt(discr)) / (2.0 * alpha);
+    const double pm2 =
+        -3.0 * pm3 - (1.0 / 16.0) + (1.0 / 8.0) * (K + r2) + (1.0 / 12.0) * (3.0 * K - 1.0) * r + (1.0 / 12.0) * r3;
+    const double pm1 = 2.0 * pm3 + (1.0 / 4.0) + (1.0 / 6.0) * (4.0 - 3.0 * K) * r - (1.0 / 6.0) * r3;
+    const double p = 2.0 * pm3 + (5.0 / 8.0) - (1.0 / 4.0) * (K + r2);
+    const double pp1 = -3.0 * pm3 + (1.0 / 4.0) - (1.0 / 6.0) * (4.0 - 3.0 * K) * r + (1.0 / 6.0) * r3;
+    const double pp2 =
+        pm3 - (1.0 / 16.0) + (1.0 / 8.0) * (K + r2) - (1.0 / 12.0) * (3.0 * K - 1.0) * r - (1.0 / 12.0) * r3;
+    s->w[0] = pm3;
+    s->w[1] = pm2;
+    s->w[2] = pm1;
+    s->w[3] = p;
+    s->w[4] = pp1;
+    s->w[5] = pp2;
+    const int ig_lower = ilower - g, ig_upper = iupper + g;
+    const int istart = (ig_lower - ic_lower > 0) ? ig_lower - ic_lower : 0;
+    const int istop = 5 - ((ic_upper - ig_upper > 0) ? ic_upper - ig_upper : 0);
+    s->wbase = ic_lower;
+    s->lo = ic_lower + istart;
+    s->hi = ic_lower + istop;
+}
+
+/* 3d.f.m4:2659-2678: weights are indexed from the CLAMPED lower bound. */
+static void stencil_bspline_3(double Xs, double x_lower, double dx, int ilower, int iupper, int g, stencil1d* s)
+{
+    const int ic_center = (int)floor((Xs - x_lower) / dx) + ilower;
+    int ic_lower = ic_center - 1;
+    int ic_upper = ic_center + 1;
+    if (ic_lower < ilower - g) ic_lower = ilower - g;
+    if (ic_upper > iupper + g) ic_upper = iupper + g;
+    for (int ic = ic_lower; ic <= ic_upper; ++ic)
+    {
+        const double X_cell = x_lower + ((double)(ic - ilower) + 0.5) * dx;
+        s->w[ic - ic_lower] = bspline_3_delta((Xs - X_cell) / dx);
+    }
+    s->wbase = ic_lower;
+    s->lo = ic_lower;
+    s->hi = ic_upper;
+}
+
+/* 3d.f.m4:2882-2908: the left/right choice compares the UNSHIFTED X with X_cell (:2891). */
+static void
+stencil_bspline_4(double Xs, double Xraw, double x_lower, double dx, int ilower, int iupper, int g, stencil1d* s)
+{
+    const int ic_center = (int)floor((Xs - x_lower) / dx) + ilower;
+    const double X_cell_c = x_lower + ((double)(ic_center - ilower) + 0.5) * dx;
+    int ic_lower, ic_upper;
+    if (Xraw < X_cell_c)
+    {
+        ic_lower = ic_center - 2;
+        ic_upper = ic_center + 1;
+    }
+    else
+    {
+        ic_lower = ic_center - 1;
+        ic_upper = ic_center + 2;
+    }
+    if (ic_lower < ilower - g) ic_lower = ilower - g;
+    if (ic_upper > iupper + g) ic_upper = iupper + g;
+    for (int ic = ic_lower; ic <= ic_upper; ++ic)
+    {
+        const double X_cell = x_lower + ((double)(ic - ilower) + 0.5) * dx;
+        s->w[ic - ic_lower] = bspline_4_delta((Xs - X_cell) / dx);
+    }
+    s->wbase = ic_lower;
+    s->lo = ic_lower;
+    s->hi = ic_upper;
+}
+
+/* 3d.f.m4:563-583: trimmed loop bounds, weights indexed from the UNTRIMMED lower bound. */
+static void stencil_piecewise_linear(double Xs, double x_lower, double dx, int ilower, int iupper, int g, stencil1d* s)
+{
+    const int ic_center = ilower + nint_f((Xs - x_lower) / dx - 0.5);
+    const double X_cell = x_lower + ((double)(ic_center - ilower) + 0.5) * dx;
+    int ic_lower, ic_upper;
+    if (Xs < X_cell)
+    {
+        ic_lower = ic_center - 1;
+        ic_upper = ic_center;
+        s->w[0] = (X_cell - Xs) / dx;
+        s->w[1] = 1.0 - s->w[0];
+    }
+    else
+    {
+        ic_lower = ic_center;
+        ic_upper = ic_center + 1;
+        s->w[0] = 1.0 + (X_cell - Xs) / dx;
+        s->w[1] = 1.0 - s->w[0];
+    }
+    s->wbase = ic_lower;
+    s->lo = (ic_lower > ilower - g) ? ic_lower : ilower - g;
+    s->hi = (ic_upper < iupper + g) ? ic_upper : iupper + g;
+}
+
+static void make_stencil(int kernel,
+                         double Xs,
+                         double Xraw,
+                         double x_lower,
+                         double dx,
+                         int ilower,
+                         int iupper,
+                         int g,
+                         stencil1d* s)
+{
+    switch (kernel)
+    {
+    case K_PIECEWISE_LINEAR:
+        stencil_piecewise_linear(Xs, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_IB_4:
+        stencil_ib_4(Xs, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_IB_6:
+        stencil_ib_6(Xs, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_BSPLINE_3:
+        stencil_bspline_3(Xs, x_lower, dx, ilower, iupper, g, s);
+        break;
+    default:
+        stencil_bspline_4(Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    }
+}
+
+static inline int is_tensor_style(int kernel)
+{
+    return kernel == K_IB_4 || kernel == K_IB_6;
+}
+
+/*
+ * Generic interpolate: V(d,s) = sum_stencil w * u(...,d) for every listed marker.
+ * ndim = 2 or 3; for ndim == 2 the third dimension is a single plane.
+ */
+void le_oracle_interp(int kernel,
+                      int ndim,
+                      const double* dx,
+                      const double* x_lower,
+                      int depth,
+                      const int* ilower,
+                      const int* iupper,
+                      const int* nugc,
+                      const double* u,
+                      const int* indices,
+                      const double* Xshift,
+                      int nindices,
+                      const double* X,
+                      double* V)
+{
+    ptrdiff_t n[3] = { 1, 1, 1 };
+    int iglo[3] = { 0, 0, 0 };
+    for (int d = 0; d < ndim; ++d)
+    {
+        n[d] = (ptrdiff_t)(iupper[d] - ilower[d] + 1 + 2 * nugc[d]);
+        iglo[d] = ilower[d] - nugc[d];
+    }
+    const ptrdiff_t comp_stride = n[0] * n[1] * n[2];
+    const int tensor = is_tensor_style(kernel);
+    for (int l = 0; l < nindices; ++l)
+    {
+        const int s = indices[l];
+        stencil1d st[3];
+        st[2].lo = st[2].hi = st[2].wbase = 0;
+        st[2].w[0] = 1.0;
+        for (int d = 0; d < ndim; ++d)
+        {
+            const double Xraw = X[(ptrdiff_t)ndim * s + d];
+            const double Xs = Xraw + Xshift[(ptrdiff_t)ndim * l + d];
+            make_stencil(kernel, Xs, Xraw, x_lower[d], dx[d], ilower[d], iupper[d], nugc[d], &st[d]);
+        }
+        for (int d = 0; d < depth; ++d)
+        {
+            const double* ud = u + comp_stride * d;
+            double acc = 0.0;
+            for (int ic2 = st[2].lo; ic2 <= st[2].hi; ++ic2)
+            {
+                const double w2 = st[2].w[ic2 - st[2].wbase];
+                for (int ic1 = st[1].lo; ic1 <= st[1].hi; ++ic1)
+                {
+                    const double w1 = st[1].w[ic1 - st[1].wbase];
+                    /* TENSOR: w(i0,i1,i2) = w0*(w1*w2) (3d.f.m4:1297-1305); 2D: w0*w1. */
+                    const double wyz = (ndim == 3) ? w1 * w2 : w1;
+                    const double* row = ud + ((ptrdiff_t)(ic2 - iglo[2]) * n[1] + (ic1 - iglo[1])) * n[0] - iglo[0];
+                    for (int ic0 = st[0].lo; ic0 <= st[0].hi; ++ic0)
+                    {
+                        const double w0 = st[0].w[ic0 - st[0].wbase];
+                        if (tensor)
+                            acc = acc + (w0 * wyz) * row[ic0];
+                        else if (ndim == 3)
+                            acc = acc + w0 * w1 * w2 * row[ic0]; /* 3d.f.m4:30-34 */
+                        else
+                            acc = acc + w0 * w1 * row[ic0]; /* 2d.f.m4:29-32 */
+                    }
+                }
+            }
+            V[(ptrdiff_t)depth * s + d] = acc;
+        }
+    }
+}
+
+/*
+ * Generic spread: u(...,d) += w * V(d,s) / prod(dx) for every listed marker,
+ * markers processed in list order (serial, as the Fortran does).
+ */
+void le_oracle_spread(int kernel,
+                      int ndim,
+                      const double* dx,
+                      const double* x_lower,
+                      int depth,
+                      const int* indices,
+                      const double* Xshift,
+                      int nindices,
+                      const double* X,
+                      const double* V,
+                      const int* ilower,
+                      const int* iupper,
+                      const int* nugc,
+                      double* u)
+{
+    ptrdiff_t n[3] = { 1, 1, 1 };
+    int iglo[3] = { 0, 0, 0 };
+    for (int d = 0; d < ndim; ++d)
+    {
+        n[d] = (ptrdiff_t)(iupper[d] - ilower[d] + 1 + 2 * nugc[d]);
+        iglo[d] = ilower[d] - nugc[d];
+    }
+    const ptrdiff_t comp_stride = n[0] * n[1] * n[2];
+    const int tensor = is_tensor_style(kernel);
+    const double dxprod = (ndim == 3) ? dx[0] * dx[1] * dx[2] : dx[0] * dx[1];
+    for (int l = 0; l < nindices; ++l)
+    {
+        const int s = indices[l];
+        stencil1d st[3];
+        st[2].lo = st[2].hi = st[2].wbase = 0;
+        st[2].w[0] = 1.0;
+        for (int d = 0; d < ndim; ++d)
+        {
+            const double Xraw = X[(ptrdiff_t)ndim * s + d];
+            const double Xs = Xraw + Xshift[(ptrdiff_t)ndim * l + d];
+            make_stencil(kernel, Xs, Xraw, x_lower[d], dx[d], ilower[d], iupper[d], nugc[d], &st[d]);
+        }
+        for (int d = 0; d < depth; ++d)
+        {
+            double* ud = u + comp_stride * d;
+            const double Vds = V[(ptrdiff_t)depth * s + d];
+            for (int ic2 = st[2].lo; ic2 <= st[2].hi; ++ic2)
+            {
+                const double w2 = st[2].w[ic2 - st[2].wbase];
+                /* TENSOR 3D: wz = w2/(dx0*dx1*dx2) (3d.f.m4:1439) */
+                const double wz = w2 / dxprod;
+                for (int ic1 = st[1].lo; ic1 <= st[1].hi; ++ic1)
+                {
+                    const double w1 = st[1].w[ic1 - st[1].wbase];
+                    /* TENSOR 2D: wy = w1/(dx0*dx1) (2d.f.m4:1356) */
+                    const double wyz = (ndim == 3) ? w1 * wz : w1 / dxprod;
+                    double* row = ud + ((ptrdiff_t)(ic2 - iglo[2]) * n[1] + (ic1 - iglo[1])) * n[0] - iglo[0];
+                    for (int ic0 = st[0].lo; ic0 <= st[0].hi; ++ic0)
+                    {
+                        const double w0 = st[0].w[ic0 - st[0].wbase];
+                        if (tensor)
+                            row[ic0] = row[ic0] + (w0 * wyz) * Vds;
+                        else if (ndim == 3)
+                            row[ic0] = row[ic0] + (w0 * w1 * w2 * Vds / dxprod); /* 3d.f.m4:61-65 */
+                        else
+                            row[ic0] = row[ic0] + (w0 * w1 * Vds / dxprod); /* 2d.f.m4:54-57 */
+                    }
+                }
+            }
+        }
+    }
+}
+
+/*
+ * Fortran-ABI entry points (seam B4): the exact symbol names and argument
+ * orders the reference declares at LEInteractor.cpp:237-1518 (mangling:
+ * lower case + trailing underscore, CMakeLists.txt:77-83), so this file could
+ * be link-substituted into a real IBAMR build for cross-checking.
+ */
+#define DEFINE_3D(NAME, KERNEL)                                                                                        \
+    void lagrangian_##NAME##_interp3d_(const double* dx,                                                               \
+                                       const double* x_lower,                                                          \
+                                       const double* x_upper,                                                          \
+                                       const int* depth,                                                               \
+                                       const int* ilower0,                                                             \
+                                       const int* iupper0,                                                             \
+                                       const int* ilower1,                                                             \
+                                       const int* iupper1,                                                             \
+                                       const int* ilower2,                                                             \
+                                       const int* iupper2,                                                             \
+                                       const int* nugc0,                                                               \
+                                       const int* nugc1,                                                               \
+                                       const int* nugc2,                                                               \
+                                       const double* u,                                                                \
+                                       const int* indices,                                                             \
+                                       const double* Xshift,                                                           \
+                                       const int* nindices,                                                            \
+                                       const double* X,                                                                \
+                                       double* V)                                                                      \
+    {                                                                                                                  \
+        (void)x_upper;                                                                                                 \
+        const int il[3] = { *ilower0, *ilower1, *ilower2 }, iu[3] = { *iupper0, *iupper1, *iupper2 };                  \
+        const int ng[3] = { *nugc0, *nugc1, *nugc2 };                                                                  \
+        le_oracle_interp(KERNEL, 3, dx, x_lower, *depth, il, iu, ng, u, indices, Xshift, *nindices, X, V);             \
+    }                                                                                                                  \
+    void lagrangian_##NAME##_spread3d_(const double* dx,                                                               \
+                                       const double* x_lower,                                                          \
+                                       const double* x_upper,                                                          \
+                                       const int* depth,                                                               \
+                                       const int* indices,                                                             \
+                                       const double* Xshift,                                                           \
+                                       const int* nindices,                                                            \
+                                       const double* X,                                                                \
+                                       const double* V,                                                                \
+                                       const int* ilower0,                                                             \
+                                       const int* iupper0,                                                             \
+                                       const int* ilower1,                                                             \
+                                       const int* iupper1,                                                             \
+                                       const int* ilower2,                                                             \
+                                       const int* iupper2,                                                             \
+                                       const int* nugc0,                                                               \
+                                       const int* nugc1,                                                               \
+                                       const int* nugc2,                                                               \
+                                       double* u)                                                                      \
+    {                                                                                                                  \
+        (void)x_upper;                                                                                                 \
+        const int il[3] = { *ilower0, *ilower1, *ilower2 }, iu[3] = { *iupper0, *iupper1, *iupper2 };                  \
+        const int ng[3] = { *nugc0, *nugc1, *nugc2 };                                                                  \
+        le_oracle_spread(KERNEL, 3, dx, x_lower, *depth, indices, Xshift, *nindices, X, V, il, iu, ng, u);             \
+    }
+
+#define DEFINE_2D(NAME, KERNEL)                                                                                        \
+    void lagrangian_##NAME##_interp2d_(const double* dx,                                                               \
+                                       const double* x_lower,                                                          \
+                                       const double* x_upper,                                                          \
+                                       const int* depth,                                                               \
+                                       const int* ilower0,                                                             \
+                                       const int* iupper0,                                                             \
+                                       const int* ilower1,                                                             \
+                                       const int* iupper1,                                                             \
+                                       const int* nugc0,                                                               \
+                                       const int* nugc1,                                                               \
+                                       const double* u,                                                                \
+                                       const int* indices,                                                             \
+                                       const double* Xshift,                                                           \
+                                       const int* nindices,                                                            \
+                                       const double* X,                                                                \
+                                       double* V)                                                                      \
+    {                                                                                                                  \
+        (void)x_upper;                                                                                                 \
+        const int il[2] = { *ilower0, *ilower1 }, iu[2] = { *iupper0, *iupper1 };                                      \
+        const int ng[2] = { *nugc0, *nugc1 };                                                                          \
+        le_oracle_interp(KERNEL, 2, dx, x_lower, *depth, il, iu, ng, u, indices, Xshift, *nindices, X, V);             \
+    }                                                                                                                  \
+    void lagrangian_##NAME##_spread2d_(const double* dx,                                                               \
+                                       const double* x_lower,                                                          \
+                                       const double* x_upper,                                                          \
+                                       const int* depth,                                                               \
+                                       const int* indices,                                                             \
+                                       const double* Xshift,                                                           \
+                                       const int* nindices,                                                            \
+                                       const double* X,                                                                \
+                                       const double* V,                                                                \
+                                       const int* ilower0,                                                             \
+                                       const int* iupper0,                                                             \
+                                       const int* ilower1,                                                             \
+                                       const int* iupper1,                                                             \
+                                       const int* nugc0,                                                               \
+                                       const int* nugc1,                                                               \
+                                       double* u)                                                                      \
+    {                                                                                                                  \
+        (void)x_upper;                                                                                                 \
+        const int il[2] = { *ilower0, *ilower1 }, iu[2] = { *iupper0, *iupper1 };                                      \
+        const int ng[2] = { *nugc0, *nugc1 };                                                                          \
+        le_oracle_spread(KERNEL, 2, dx, x_lower, *depth, indices, Xshift, *nindices, X, V, il, iu, ng, u);             \
+    }
+
+DEFINE_3D(piecewise_linear, K_PIECEWISE_LINEAR)
+DEFINE_3D(ib_4, K_IB_4)
+DEFINE_3D(ib_6, K_IB_6)
+DEFINE_3D(bspline_3, K_BSPLINE_3)
+DEFINE_3D(bspline_4, K_BSPLINE_4)
+DEFINE_2D(piecewise_linear, K_PIECEWISE_LINEAR)
+DEFINE_2D(ib_4, K_IB_4)
+DEFINE_2D(ib_6, K_IB_6)
+DEFINE_2D(bspline_3, K_BSPLINE_3)
+DEFINE_2D(bspline_4, K_BSPLINE_4)

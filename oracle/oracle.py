@@ -1,0 +1,402 @@
+"""ctypes front end of the CPU oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.  The arithmetic lives in oracle/le_kernels.c and oracle/le_driver.c
+(each function there cites the reference file:line it restates); this file adds the small
+numpy orchestration that the reference does with SAMRAI/PETSc objects:
+
+  * PatchGeom / level helpers                     (SAMRAI CartesianPatchGeometry role)
+  * side_* / cell_* position-only LEInteractor calls
+        ibtk/src/lagrangian/LEInteractor.cpp:2805-2863 (CellData), :3045-3127, :4188-4263 (SideData)
+  * ghost_accumulate                              SAMRAIGhostDataAccumulator::accumulateGhostData
+        ibtk/src/math/SAMRAIGhostDataAccumulator.cpp:295-353 (+ DOF sharing of faces,
+        ibtk/src/math/PETScVecUtilities.cpp:519-611)
+  * bin_level                                     LDataManager::beginDataRedistribution binning
+        ibtk/src/lagrangian/LDataManager.cpp:1397-1508, LIndexSetData.cpp:53-141
+
+Array convention: a Fortran array u(lo0-g:hi0+g, lo1-g:hi1+g[, lo2-g:hi2+g]) is held as a
+C-ordered numpy array of shape ([n2,] n1, n0), i.e. the same memory.
+
+Parity status: PINNED (tests/test_oracle_golden.py, fixtures under tests/golden/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KERNELS = {"PIECEWISE_LINEAR": 0, "IB_4": 1, "IB_6": 2, "BSPLINE_3": 3, "BSPLINE_4": 4}
+# LEInteractor::getStencilSize (LEInteractor.cpp:2052-2108) and getMinimumGhostWidth (:2110-2114)
+STENCIL_SIZE = {"PIECEWISE_LINEAR": 2, "IB_4": 4, "IB_6": 6, "BSPLINE_3": 4, "BSPLINE_4": 4}
+
+
+def min_ghost_width(kernel: str) -> int:
+    return int(np.floor(0.5 * STENCIL_SIZE[kernel])) + 1
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("le_kernels.c", "le_driver.c", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.le_oracle_baseline_create.restype = C.c_void_p
+        _LIB.le_oracle_baseline_f.restype = C.POINTER(C.c_double)
+        _LIB.le_oracle_baseline_u.restype = C.POINTER(C.c_double)
+        _LIB.le_oracle_baseline_array_size.restype = C.c_size_t
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+# ----------------------------------------------------------------------------------------------
+# raw funnel (seam B4): same argument meaning as the Fortran routines
+# ----------------------------------------------------------------------------------------------
+def interp_raw(kernel, ndim, dx, x_lower, depth, ilower, iupper, nugc, u, indices, Xshift, X, V=None):
+    X = _f64(X)
+    indices = _i32(indices)
+    Xshift = _f64(Xshift)
+    u = _f64(u)
+    if V is None:
+        V = np.zeros((X.size // ndim, depth))
+    lib().le_oracle_interp(
+        KERNELS[kernel], ndim, _dp(_f64(dx)), _dp(_f64(x_lower)), depth, _ip(_i32(ilower)), _ip(_i32(iupper)),
+        _ip(_i32(nugc)), _dp(u), _ip(indices), _dp(Xshift), int(indices.size), _dp(X), _dp(V))
+    return V
+
+
+def spread_raw(kernel, ndim, dx, x_lower, depth, indices, Xshift, X, V, ilower, iupper, nugc, u):
+    assert u.dtype == np.float64 and u.flags.c_contiguous
+    X = _f64(X)
+    V = _f64(V)
+    indices = _i32(indices)
+    Xshift = _f64(Xshift)
+    lib().le_oracle_spread(
+        KERNELS[kernel], ndim, _dp(_f64(dx)), _dp(_f64(x_lower)), depth, _ip(indices), _dp(Xshift),
+        int(indices.size), _dp(X), _dp(V), _ip(_i32(ilower)), _ip(_i32(iupper)), _ip(_i32(nugc)), _dp(u))
+    return u
+
+
+def get_cell_index(X, x_lower, x_upper, dx, ilower, iupper):
+    X = _f64(X)
+    ndim = len(dx)
+    n = X.size // ndim
+    out = np.zeros((n, ndim), dtype=np.int32)
+    lib().le_oracle_get_cell_index(ndim, n, _dp(X), _dp(_f64(x_lower)), _dp(_f64(x_upper)), _dp(_f64(dx)),
+                                   _ip(_i32(ilower)), _ip(_i32(iupper)), _ip(out))
+    return out
+
+
+def wrap_positions(X, x_lower, x_upper, periodic):
+    X = _f64(X).copy()
+    ndim = len(x_lower)
+    esc = lib().le_oracle_wrap_positions(ndim, X.size // ndim, _dp(X), _dp(_f64(x_lower)), _dp(_f64(x_upper)),
+                                         _ip(_i32(periodic)))
+    return X, esc
+
+
+# ----------------------------------------------------------------------------------------------
+# patch geometry stand-in
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class PatchGeom:
+    """What LEInteractor reads from SAMRAI's Patch/CartesianPatchGeometry."""
+    lower: tuple  # patch box lower cell index
+    upper: tuple  # patch box upper cell index (inclusive)
+    x_lower: tuple
+    x_upper: tuple
+    dx: tuple
+    gcw: tuple = ()
+
+    @property
+    def ndim(self):
+        return len(self.lower)
+
+    def side_shape(self, axis, gcw=None):
+        g = self.gcw if gcw is None else gcw
+        n = [self.upper[d] - self.lower[d] + 1 + (1 if d == axis else 0) + 2 * g[d] for d in range(self.ndim)]
+        return tuple(reversed(n))
+
+    def cell_shape(self, gcw=None):
+        g = self.gcw if gcw is None else gcw
+        n = [self.upper[d] - self.lower[d] + 1 + 2 * g[d] for d in range(self.ndim)]
+        return tuple(reversed(n))
+
+    def side_coords(self, axis, gcw=None):
+        """Physical coordinates of every side of `axis` (incl. ghosts), as ndim arrays."""
+        g = self.gcw if gcw is None else gcw
+        ax = []
+        for d in range(self.ndim):
+            n = self.upper[d] - self.lower[d] + 1 + (1 if d == axis else 0) + 2 * g[d]
+            i = np.arange(n) - g[d]
+            ax.append(self.x_lower[d] + self.dx[d] * (i + (0.0 if d == axis else 0.5)))
+        return np.meshgrid(*reversed(ax), indexing="ij")[::-1]
+
+    def cell_coords(self, gcw=None):
+        g = self.gcw if gcw is None else gcw
+        ax = []
+        for d in range(self.ndim):
+            n = self.upper[d] - self.lower[d] + 1 + 2 * g[d]
+            i = np.arange(n) - g[d]
+            ax.append(self.x_lower[d] + self.dx[d] * (i + 0.5))
+        return np.meshgrid(*reversed(ax), indexing="ij")[::-1]
+
+
+def indices_in_box(X, pg: PatchGeom, box_lower, box_upper):
+    """LEInteractor::buildLocalIndices, position form (LEInteractor.cpp:6088-6126)."""
+    X = _f64(X)
+    n = X.size // pg.ndim
+    out = np.zeros(max(n, 1), dtype=np.int32)
+    cnt = lib().le_oracle_indices_in_box(pg.ndim, n, _dp(X), _dp(_f64(pg.x_lower)), _dp(_f64(pg.x_upper)),
+                                         _dp(_f64(pg.dx)), _ip(_i32(pg.lower)), _ip(_i32(pg.upper)),
+                                         _ip(_i32(box_lower)), _ip(_i32(box_upper)), _ip(out))
+    return out[:cnt].copy()
+
+
+def _ptr_array(arrs):
+    P = (C.POINTER(C.c_double) * len(arrs))()
+    for i, a in enumerate(arrs):
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+        P[i] = _dp(a)
+    return P
+
+
+def side_interp(kernel, pg: PatchGeom, u_sides, X, indices, shifts=None, Q=None):
+    """SideData interpolate with an explicit index list (LEInteractor.cpp:2402-2489)."""
+    ndim = pg.ndim
+    X = _f64(X)
+    indices = _i32(indices)
+    shifts = np.zeros(indices.size * ndim) if shifts is None else _f64(shifts)
+    if Q is None:
+        Q = np.zeros((X.size // ndim, ndim))
+    lib().le_oracle_side_interp(KERNELS[kernel], ndim, _dp(_f64(pg.x_lower)), _dp(_f64(pg.dx)), _ip(_i32(pg.lower)),
+                                _ip(_i32(pg.upper)), _ip(_i32(pg.gcw)), _ptr_array(u_sides), _ip(indices), _dp(shifts),
+                                int(indices.size), _dp(X), _dp(Q))
+    return Q
+
+
+def side_spread(kernel, pg: PatchGeom, u_sides, X, Q, indices, shifts=None):
+    """SideData spread with an explicit index list (LEInteractor.cpp:3627-3714)."""
+    ndim = pg.ndim
+    X = _f64(X)
+    Q = _f64(Q)
+    indices = _i32(indices)
+    shifts = np.zeros(indices.size * ndim) if shifts is None else _f64(shifts)
+    lib().le_oracle_side_spread(KERNELS[kernel], ndim, _dp(_f64(pg.x_lower)), _dp(_f64(pg.dx)), _ip(_i32(pg.lower)),
+                                _ip(_i32(pg.upper)), _ip(_i32(pg.gcw)), _ptr_array(u_sides), _ip(indices), _dp(shifts),
+                                int(indices.size), _dp(X), _dp(Q))
+    return u_sides
+
+
+def side_interp_positions(kernel, pg, u_sides, X, box_lower=None, box_upper=None):
+    """Position-only SideData interpolate (LEInteractor.cpp:3045-3127)."""
+    idx = indices_in_box(X, pg, pg.lower if box_lower is None else box_lower, pg.upper if box_upper is None else box_upper)
+    return side_interp(kernel, pg, u_sides, X, idx)
+
+
+def side_spread_positions(kernel, pg, u_sides, X, Q, box_lower=None, box_upper=None):
+    """Position-only SideData spread (LEInteractor.cpp:4188-4263)."""
+    idx = indices_in_box(X, pg, pg.lower if box_lower is None else box_lower, pg.upper if box_upper is None else box_upper)
+    return side_spread(kernel, pg, u_sides, X, Q, idx)
+
+
+def cell_interp_positions(kernel, pg, u_cell, depth, X, box_lower=None, box_upper=None):
+    """Position-only CellData interpolate (LEInteractor.cpp:2805-2863); u_cell shape (depth, [n2,] n1, n0)."""
+    idx = indices_in_box(X, pg, pg.lower if box_lower is None else box_lower, pg.upper if box_upper is None else box_upper)
+    ndim = pg.ndim
+    V = np.full((np.asarray(X).size // ndim, depth), np.finfo(np.float64).max)
+    return interp_raw(kernel, ndim, pg.dx, pg.x_lower, depth, pg.lower, pg.upper, pg.gcw, u_cell, idx,
+                      np.zeros(idx.size * ndim), X, V)
+
+
+def cell_spread_positions(kernel, pg, u_cell, depth, X, Q, box_lower=None, box_upper=None):
+    """Position-only CellData spread (LEInteractor.cpp:3951-4009)."""
+    idx = indices_in_box(X, pg, pg.lower if box_lower is None else box_lower, pg.upper if box_upper is None else box_upper)
+    ndim = pg.ndim
+    return spread_raw(kernel, ndim, pg.dx, pg.x_lower, depth, idx, np.zeros(idx.size * ndim), X, Q, pg.lower, pg.upper,
+                      pg.gcw, u_cell)
+
+
+# ----------------------------------------------------------------------------------------------
+# level = set of patches on one refinement level of a Cartesian domain
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Level:
+    ndim: int
+    domain_lower: tuple  # level cell index of the domain's lower corner (normally 0)
+    domain_ncells: tuple  # cells of the (refined) physical domain per dimension
+    x_lower: tuple
+    x_upper: tuple
+    periodic: tuple
+    boxes: list  # [(lower tuple, upper tuple)] patch boxes on this level
+    gcw: tuple
+    dx: tuple = field(init=False)
+
+    def __post_init__(self):
+        self.dx = tuple((self.x_upper[d] - self.x_lower[d]) / self.domain_ncells[d] for d in range(self.ndim))
+
+    def patch_geom(self, p) -> PatchGeom:
+        lo, hi = self.boxes[p]
+        # SAMRAI computes patch x_lower/x_upper as x_lo + dx * (index - domain_lower)
+        xl = tuple(self.x_lower[d] + self.dx[d] * (lo[d] - self.domain_lower[d]) for d in range(self.ndim))
+        xu = tuple(self.x_lower[d] + self.dx[d] * (hi[d] + 1 - self.domain_lower[d]) for d in range(self.ndim))
+        return PatchGeom(tuple(lo), tuple(hi), xl, xu, self.dx, tuple(self.gcw))
+
+    def domain_upper(self):
+        return tuple(self.domain_lower[d] + self.domain_ncells[d] - 1 for d in range(self.ndim))
+
+
+def bin_level(level: Level, X):
+    """Marker -> (cell, owner patch) and the per-patch index lists.
+
+    cell   = getCellIndex(X, grid_geom, ratio)        LDataManager.cpp:1475
+    owner  = the patch whose box contains the cell    LDataManager.cpp:1476
+    lists  = LIndexSetData::cacheLocalIndices         LIndexSetData.cpp:53-141
+    Returns dict(cells, owner, patches=[dict(all_idx, all_shift, interior_mask)]).
+    """
+    ndim = level.ndim
+    X = _f64(X)
+    n = X.size // ndim
+    cells = get_cell_index(X, level.x_lower, level.x_upper, level.dx, level.domain_lower, level.domain_upper())
+    owner = np.full(n, -1, dtype=np.int32)
+    for p, (lo, hi) in enumerate(level.boxes):
+        m = np.ones(n, dtype=bool)
+        for d in range(ndim):
+            m &= (cells[:, d] >= lo[d]) & (cells[:, d] <= hi[d])
+        owner[m] = p
+    patches = []
+    for p, (lo, hi) in enumerate(level.boxes):
+        args = (ndim, n, _ip(cells), _ip(_i32(lo)), _ip(_i32(hi)), _ip(_i32(level.gcw)), _ip(_i32(level.domain_lower)),
+                _ip(_i32(level.domain_ncells)), _ip(_i32(level.periodic)), _dp(_f64(level.dx)))
+        cnt = lib().le_oracle_patch_lists(*args, None, None, None)
+        idx = np.zeros(max(cnt, 1), dtype=np.int32)
+        sh = np.zeros(max(cnt, 1) * ndim)
+        interior = np.zeros(max(cnt, 1), dtype=np.int32)
+        lib().le_oracle_patch_lists(*args, _ip(idx), _dp(sh), _ip(interior))
+        patches.append(dict(all_idx=idx[:cnt].copy(), all_shift=sh[:cnt * ndim].copy(),
+                            interior_mask=interior[:cnt].astype(bool)))
+    return dict(cells=cells, owner=owner, patches=patches)
+
+
+def ghost_accumulate(level: Level, arrays, centering="side"):
+    """SAMRAIGhostDataAccumulator::accumulateGhostData on one level.
+
+    arrays[p][axis] (side) or arrays[p][0] (cell): per-patch arrays including ghosts.  Every copy
+    of a DOF (interior copies of shared faces and all ghost copies, periodic images included) is
+    summed into one value, which is then written back to every copy
+    (SAMRAIGhostDataAccumulator.cpp:327-344).  Copies with no owner on this level (outside a
+    non-periodic domain, or under no patch) keep their values (DOF index -1, :114,231).
+    Modifies arrays in place.
+    """
+    ndim = level.ndim
+    ncomp = ndim if centering == "side" else 1
+    for axis in range(ncomp):
+        # global DOF space of this component
+        ext = [level.domain_ncells[d] + (1 if (centering == "side" and d == axis and not level.periodic[d]) else 0)
+               for d in range(ndim)]
+        total = np.zeros(tuple(reversed(ext)))
+        owned = np.zeros(tuple(reversed(ext)), dtype=bool)
+        maps = []
+        for p, (lo, hi) in enumerate(level.boxes):
+            a = arrays[p][axis]
+            gi = []
+            valid = []
+            for d in range(ndim):
+                n = hi[d] - lo[d] + 1 + (1 if (centering == "side" and d == axis) else 0) + 2 * level.gcw[d]
+                g = np.arange(n) + lo[d] - level.gcw[d] - level.domain_lower[d]
+                if level.periodic[d]:
+                    v = np.ones(n, dtype=bool)
+                    g = np.mod(g, level.domain_ncells[d])
+                else:
+                    v = (g >= 0) & (g < ext[d])
+                    g = np.clip(g, 0, ext[d] - 1)
+                gi.append(g)
+                valid.append(v)
+                # interior (owned) range of this patch
+            mesh = np.meshgrid(*reversed(gi), indexing="ij")
+            vmesh = np.meshgrid(*reversed(valid), indexing="ij")
+            vm = np.logical_and.reduce(vmesh)
+            maps.append((mesh, vm))
+            # mark DOFs owned by some patch interior
+            sl = []
+            for d in reversed(range(ndim)):
+                n_int = hi[d] - lo[d] + 1 + (1 if (centering == "side" and d == axis) else 0)
+                sl.append(slice(level.gcw[d], level.gcw[d] + n_int))
+            im = np.zeros(a.shape, dtype=bool)
+            im[tuple(sl)] = True
+            owned[tuple(m[im & vm] for m in mesh)] = True
+        for p in range(len(level.boxes)):
+            mesh, vm = maps[p]
+            a = arrays[p][axis]
+            ok = vm & owned[tuple(mesh)]
+            np.add.at(total, tuple(m[ok] for m in mesh), a[ok])
+        for p in range(len(level.boxes)):
+            mesh, vm = maps[p]
+            a = arrays[p][axis]
+            ok = vm & owned[tuple(mesh)]
+            a[ok] = total[tuple(m[ok] for m in mesh)]
+    return arrays
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline (reference parallel model on OpenMP threads); bench.py only
+# ----------------------------------------------------------------------------------------------
+class Baseline:
+    def __init__(self, ndim, N, npatch, gcw, x_lower, x_upper, X, field_seed=0):
+        self.ndim = ndim
+        self.X = _f64(X)
+        self.n = self.X.size // ndim
+        self._h = lib().le_oracle_baseline_create(ndim, _ip(_i32(N)), _ip(_i32(npatch)), int(gcw), _dp(_f64(x_lower)),
+                                                  _dp(_f64(x_upper)), self.n, _dp(self.X),
+                                                  C.c_ulonglong(field_seed))
+        self._h = C.c_void_p(self._h)
+
+    def step(self, kernel, F, U):
+        lib().le_oracle_baseline_step(self._h, KERNELS[kernel], _dp(self.X), _dp(F), _dp(U))
+
+    def zero_f(self):
+        lib().le_oracle_baseline_zero_f(self._h)
+
+    @staticmethod
+    def threads():
+        return lib().le_oracle_baseline_threads()
+
+    def close(self):
+        if self._h:
+            lib().le_oracle_baseline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,22 @@
+#!/bin/sh
+# Copies the reference's own golden OUTPUT files (data, not source) that pin the hot path
+#  into tests/golden/.  Run in the build container where /root/reference is
+# mounted; the GPU box has no /root/reference, so the copies are what the tests read.
+set -e
+REF=${1:-/root/reference}
+HERE=$(dirname "$0")
+for k in ib_4 ib_6 bspline_3 bspline_4 piecewise_linear; do
+  for d in 2d 3d; do
+    cp "$REF/tests/interpolate/interpolate_01_$d.$k.output" "$HERE/"
+  done
+done
+for d in 2d 3d; do
+  for c in cell side; do
+    for v in a b; do
+      cp "$REF/tests/IBTK/ghost_accumulation_01_$d.$c.spread.$v.output" "$HERE/"
+    done
+    cp "$REF/tests/IBTK/ghost_accumulation_01_$d.$c.spread.b.mpirun=4.output" "$HERE/ghost_accumulation_01_$d.$c.spread.b.mpirun4.output"
+  done
+  cp "$REF/tests/IBTK/index_utilities_$d.output" "$HERE/"
+done
+cp "$REF/examples/IB/explicit/ex1/curve2d_64.vertex" "$HERE/"

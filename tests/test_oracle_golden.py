@@ -1,0 +1,162 @@
+"""Pins the CPU oracle against the reference's own golden files.
+
+Fixtures under tests/golden/ are verbatim copies of reference test outputs
+(tests/golden/collect_fixtures.sh).  CPU only.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.util import (read_ghost_accumulation_golden, read_index_utilities_golden, read_interpolate_golden,
+                        std_uniform_stream)
+
+KERNELS = ["IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR"]
+
+
+def _interp_patch(ndim, N):
+    # tests/interpolate/interpolate_01_*.input: N coarse cells, ratio 4, level-1 patch = refined
+    # RefineBoxes [(N/4..), (N/2-1..)]  ->  fine box [N, 2N-1]^ndim, dx = 1/(4N), x in [0.25, 0.5]
+    lo = (N,) * ndim
+    hi = (2 * N - 1,) * ndim
+    dx = (1.0 / (4 * N),) * ndim
+    return lo, hi, dx
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_interpolate_01_3d(kernel, golden_dir):
+    """tests/interpolate/interpolate_01.cpp with interpolate_01_3d.<kernel>.input (multilinear field)."""
+    gold = read_interpolate_golden(os.path.join(golden_dir, f"interpolate_01_3d.{kernel.lower()}.output"))
+    ndim, N = 3, 8
+    lo, hi, dx = _interp_patch(ndim, N)
+    g = orc.min_ghost_width(kernel)
+    pg = orc.PatchGeom(lo, hi, (0.25,) * 3, (0.5,) * 3, dx, (g,) * 3)
+    x, y, z = pg.cell_coords()
+    f = 1 + 2 * x + 3 * y - z + 4 * x * y + 2 * x * z + 3 * x * y * z
+    u = np.ascontiguousarray(np.stack([f, f, f]))
+    X = std_uniform_stream(42, 300, 0.25, 0.5).reshape(100, 3)
+    # the RNG stream is reproduced (goldens print 16 significant digits, i.e. not round-trip exact)
+    np.testing.assert_allclose(X, gold[:, :3], rtol=1e-15, atol=0)
+    Q = orc.cell_interp_positions(kernel, pg, u, 3, X)
+    # reference regression tolerance is numdiff -r 1e-6 -a 1e-10 (attest:351); the multilinear
+    # field is reproduced exactly by every in-scope kernel, so 1e-12 (the .exact bound) holds.
+    np.testing.assert_allclose(Q, gold[:, 3:6], rtol=0, atol=2e-12)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_interpolate_01_2d(kernel, golden_dir):
+    """interpolate_01_2d.<kernel>.input: trigonometric field on the level-1 patch [16,31]^2.
+
+    Ghost cells of that patch come from coarse-level LINEAR_REFINE in the reference, which the
+    oracle does not model: compare only points whose stencil stays inside the patch interior
+    (SURVEY.md section 4), where the data is the analytic field at cell centres."""
+    gold = read_interpolate_golden(os.path.join(golden_dir, f"interpolate_01_2d.{kernel.lower()}.output"))
+    ndim, N = 2, 16
+    lo, hi, dx = _interp_patch(ndim, N)
+    g = orc.min_ghost_width(kernel)
+    pg = orc.PatchGeom(lo, hi, (0.25,) * 2, (0.5,) * 2, dx, (g,) * 2)
+    x, y = pg.cell_coords()
+    f = np.sin(2 * np.pi * (x - 0.1234)) * np.sin(2 * np.pi * (y - 0.1234))
+    u = np.ascontiguousarray(np.stack([f, f]))
+    X = std_uniform_stream(42, 200, 0.25, 0.5).reshape(100, 2)
+    np.testing.assert_allclose(X, gold[:, :2], rtol=1e-15, atol=0)
+    Q = orc.cell_interp_positions(kernel, pg, u, 2, X)
+    reach = {'IB_4': 2, 'IB_6': 3, 'BSPLINE_3': 2, 'BSPLINE_4': 2, 'PIECEWISE_LINEAR': 1}[kernel]
+    cell = np.floor((X - 0.25) / dx[0]).astype(int)  # 0..15 within the patch
+    inside = np.all((cell - reach >= 0) & (cell + reach <= N - 1), axis=1)
+    assert inside.sum() >= 30, inside.sum()
+    # BSPLINE_4's polynomial form amplifies compiler-dependent rounding to ~7e-15 relative
+    # (SURVEY.md appendix B), everything else agrees to ~1 ulp of the 16 printed digits.
+    np.testing.assert_allclose(Q[inside], gold[inside][:, 3:5], rtol=0, atol=5e-14)
+
+
+GA_CASES = {
+    # name: (ndim, centering, finest-level cells per dim, periodic, finest-level index of domain lower)
+    "2d.cell.spread.a": (2, "cell", 8, True),
+    "2d.cell.spread.b": (2, "cell", 8, True),
+    "2d.cell.spread.b.mpirun4": (2, "cell", 8, True),
+    "2d.side.spread.a": (2, "side", 8, True),
+    "2d.side.spread.b": (2, "side", 8, True),
+    "2d.side.spread.b.mpirun4": (2, "side", 8, True),
+    "3d.cell.spread.a": (3, "cell", 8, False),
+    "3d.cell.spread.b": (3, "cell", 8, False),  # N=4 coarse, finest level = ratio-2 patch [(2,0,0),(3,3,3)]
+    "3d.cell.spread.b.mpirun4": (3, "cell", 8, False),
+    "3d.side.spread.a": (3, "side", 8, False),
+    "3d.side.spread.b": (3, "side", 8, False),
+    "3d.side.spread.b.mpirun4": (3, "side", 8, False),
+}
+
+
+@pytest.mark.parametrize("case", sorted(GA_CASES))
+def test_ghost_accumulation_01_spread(case, golden_dir):
+    """tests/IBTK/ghost_accumulation_01.cpp, fill_test = "spread": owner-only PIECEWISE_LINEAR
+    spread of 100 points into every finest-level patch (ghost regions included), then
+    SAMRAIGhostDataAccumulator::accumulateGhostData, then a dump of the patch interiors."""
+    ndim, centering, n, periodic = GA_CASES[case]
+    gold = read_ghost_accumulation_golden(os.path.join(golden_dir, f"ghost_accumulation_01_{case}.output"), ndim)
+    dx = 1.0 / n
+    boxes = []
+    for p in gold:
+        lo = tuple(int(round(p["x_lower"][d] / dx)) for d in range(ndim))
+        hi = tuple(int(round(p["x_upper"][d] / dx)) - 1 for d in range(ndim))
+        boxes.append((lo, hi))
+    level = orc.Level(ndim, (0,) * ndim, (n,) * ndim, (0.0,) * ndim, (1.0,) * ndim, (int(periodic),) * ndim, boxes,
+                      (2,) * ndim)
+    q_depth = 1 if centering == "cell" else ndim
+    stream = std_uniform_stream(42, (q_depth + ndim) * 100)
+    Q = stream[:q_depth * 100].reshape(100, q_depth)  # ghost_accumulation_01.cpp:134
+    X = stream[q_depth * 100:].reshape(100, ndim)  # :135
+    arrays = []
+    for p in range(len(boxes)):
+        pg = level.patch_geom(p)
+        if centering == "side":
+            a = [np.zeros(pg.side_shape(ax)) for ax in range(ndim)]
+            orc.side_spread_positions("PIECEWISE_LINEAR", pg, a, X, Q)
+        else:
+            a = [np.zeros((1,) + pg.cell_shape())]
+            orc.cell_spread_positions("PIECEWISE_LINEAR", pg, a[0], 1, X, Q)
+            a = [a[0][0]]
+        arrays.append(a)
+    orc.ghost_accumulate(level, arrays, centering)
+    checked = 0
+    for p, gp in enumerate(gold):
+        lo, hi = boxes[p]
+        for axis, entries in gp["comps"].items():
+            a = arrays[p][axis]
+            for idx, val in entries.items():
+                loc = tuple(idx[d] - lo[d] + 2 for d in reversed(range(ndim)))
+                got = a[loc]
+                assert abs(got - val) <= 1e-12 * max(1.0, abs(val)), (case, p, axis, idx, got, val)
+                checked += 1
+    assert checked > 0
+
+
+# tests/IBTK/index_utilities.cpp:56-96 (exact source literals; the golden prints 6 digits only)
+IU_POINTS = [
+    (-0.35355339059327373086, -0.35355339059327373086, 0.0),
+    (-5.5511151231257827e-17, -0.49999999999999994, 0.0),
+    (-0.25, -0.25, 0.0),
+    (-2.7755575615628914e-17, -0.32322330470336308, 0.0),
+    (-4.163336342344337e-17, -0.41161165235168151, 0.0),
+]
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_index_utilities(ndim, golden_dir):
+    """tests/IBTK/index_utilities.cpp: IndexUtilities::getCellIndex(point, patch_geom, patch_box)
+    for five boundary-straddling points against every patch of a 32^ndim periodic [-1,1]^ndim grid."""
+    gold = read_index_utilities_golden(os.path.join(golden_dir, f"index_utilities_{ndim}d.output"), ndim)
+    assert len(gold) > 0
+    dx = 2.0 / 32
+    npatch = len(gold) // len(IU_POINTS)
+    for k, (pt_print, level, blo, bhi, idx, contains) in enumerate(gold):
+        assert level == 0
+        pt = IU_POINTS[k // npatch][:ndim]
+        assert all(abs(pt[d] - pt_print[d]) < 1e-6 for d in range(ndim))
+        xl = tuple(-1.0 + dx * blo[d] for d in range(ndim))
+        xu = tuple(-1.0 + dx * (bhi[d] + 1) for d in range(ndim))
+        got = orc.get_cell_index(np.array(pt), xl, xu, (dx,) * ndim, blo, bhi)[0]
+        assert tuple(int(v) for v in got) == idx, (pt, blo, bhi, got, idx)
+        inside = all(blo[d] <= got[d] <= bhi[d] for d in range(ndim))
+        assert int(inside) == contains
