@@ -1,0 +1,75 @@
+"""Builds libibk.so (the C-ABI shared library) in-tree with nvcc for sm_100a.
+
+nvcc cross-compiles without a GPU, so this runs in the CPU-only build container; the resulting
+ibamr_b200/libibk.so is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["ibk_api.cu", "ibk_level.cu", "ibk_bin.cu", "ibk_sort.cu", "ibk_interp.cu", "ibk_spread.cu", "ibk_halo.cu"]
+HEADERS = ["ibk_device.cuh", "ibk_engine.h", "ibk_ctx.h", os.path.join("..", "..", "include", "ibk.h")]
+LIB = os.path.join(HERE, "libibk.so")
+OBJDIR = os.path.join(HERE, "_obj")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False, extra_flags=()):
+    nvcc = _nvcc()
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    objs = []
+    procs = []
+    host_cc = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + hdrs):
+            cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-ccbin", host_cc] if host_cc else []) + ["-c", s, "-o", o]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"--- nvcc failed for {src}\n{out}\n")
+        elif verbose and out.strip():
+            print(out)
+    if failed:
+        raise RuntimeError("libibk.so: compilation failed")
+    if force or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + (["-ccbin", host_cc] if host_cc else []) + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("libibk.so: link failed\n" + r.stdout + r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True, extra_flags=[f for f in sys.argv[1:] if f.startswith("-X")]))

@@ -1,0 +1,96 @@
+// ibk_ctx.h -- the context object behind the C ABI (internal).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "ibk_engine.h"
+
+namespace ibk
+{
+// growable device buffer
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as()
+    {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+struct PatchState
+{
+    int lower[3], upper[3];
+    PatchBin pb;
+    // per axis: u and f arrays (pitched), extents incl. ghosts
+    double* u[3] = { nullptr, nullptr, nullptr };
+    double* f[3] = { nullptr, nullptr, nullptr };
+    int n[3][3];
+    long long pitch[3];
+    size_t elems[3];
+};
+
+struct LevelState
+{
+    bool valid = false;
+    int ndim = 0;
+    int domain_lower[3], domain_upper[3], periodic[3], gcw[3];
+    double x_lower[3], x_upper[3], dx[3];
+    int G = 0;
+    std::vector<PatchState> patches;
+    std::vector<PatchBin> h_bins;
+    PatchBin* d_bins = nullptr;
+    // markers (storage order; after a rebin: sorted order)
+    int n = 0;
+    long long stride = 0;
+    double* X = nullptr;
+    double* U = nullptr;
+    double* F = nullptr;
+    double* tmp = nullptr;    // [ndim][stride] permutation scratch
+    uint32_t* lag = nullptr;  // storage position -> Lagrangian index
+    uint32_t* lag_prev = nullptr; // the same map as it was when the binning products were written
+    int* cells = nullptr;     // [n][ndim], in lag_prev storage order
+    int* owner = nullptr;     // [n]
+    int* escaped = nullptr;   // device counter
+    Bins bins;
+    bool binned = false;
+    int n_owned = 0;
+};
+
+} // namespace ibk
+
+struct ibk_ctx
+{
+    int device = 0;
+    ibk::Launcher L;
+    std::string err;
+    // scratch for the raw / patch seams
+    ibk::Bins sbins;
+    ibk::DevBuf b_Xe, b_Xr, b_Xes, b_Xrs, b_src, b_patchbin;
+    ibk::DevBuf b_io[8]; // staging for *_host entry points
+    ibk::LevelState lv;
+    bool timing = false;
+    cudaEvent_t ev[3][2];
+    bool ev_valid[3] = { false, false, false };
+    bool ev_created = false;
+};

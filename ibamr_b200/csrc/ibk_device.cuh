@@ -1,0 +1,283 @@
+// ibk_device.cuh -- device-side building blocks shared by the sm_100a kernels:
+// delta-kernel stencils (origin + 1-D weights), geometry structs, small PTX wrappers.
+//
+// Arithmetic follows the reference Fortran (ibtk/src/lagrangian/fortran/
+// lagrangian_interaction3d.f.m4, lagrangian_delta.f.m4; line numbers at each function).
+// Everything that decides an INTEGER (cell index, stencil origin, left/right choice) is written
+// with explicit round-to-nearest intrinsics (__dsub_rn, __ddiv_rn, ...) so that nvcc cannot
+// contract it into FMAs: those integers must be bit-identical to the reference's.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ibk.h"
+
+namespace ibk
+{
+constexpr int BRICK = 4;       // cells per brick edge (binning granularity)
+constexpr int TILE_BRICKS = 4; // bricks per marker-tile edge
+constexpr int TILE = BRICK * TILE_BRICKS; // 16 cells / points per tile edge
+
+// ---------------------------------------------------------------------------------------------
+// kernel traits: W = points per dimension, M = reach (cells) of the stencil from the marker's cell
+// ---------------------------------------------------------------------------------------------
+template <int K>
+struct KTraits;
+template <>
+struct KTraits<IBK_PIECEWISE_LINEAR>
+{
+    static constexpr int W = 2, M = 1;
+};
+template <>
+struct KTraits<IBK_IB_4>
+{
+    static constexpr int W = 4, M = 2;
+};
+template <>
+struct KTraits<IBK_IB_6>
+{
+    static constexpr int W = 6, M = 3;
+};
+template <>
+struct KTraits<IBK_BSPLINE_3>
+{
+    static constexpr int W = 3, M = 2;
+};
+template <>
+struct KTraits<IBK_BSPLINE_4>
+{
+    static constexpr int W = 4, M = 2;
+};
+
+// Fortran NINT (round half away from zero).
+__device__ __forceinline__ int nint_f(double x)
+{
+    return (int)round(x);
+}
+
+// lagrangian_delta.f.m4:243-260
+__device__ __forceinline__ double bspline_3_delta(double x)
+{
+    const double modx = fabs(x);
+    const double r = modx + 1.5;
+    const double r2 = r * r;
+    if (modx <= 0.5) return 0.5 * (-2.0 * r2 + 6.0 * r - 3.0);
+    if (modx <= 1.5) return 0.5 * (r2 - 6.0 * r + 9.0);
+    return 0.0;
+}
+// lagrangian_delta.f.m4:268-288
+__device__ __forceinline__ double bspline_4_delta(double x)
+{
+    const double modx = fabs(x);
+    const double r = modx + 2.0;
+    const double r2 = r * r;
+    const double r3 = r2 * r;
+    if (modx <= 1.0) return (1.0 / 6.0) * (3.0 * r3 - 24.0 * r2 + 60.0 * r - 44.0);
+    if (modx <= 2.0) return (1.0 / 6.0) * (-r3 + 12.0 * r2 - 48.0 * r + 64.0);
+    return 0.0;
+}
+
+// One dimension of a stencil.  Inputs: Xs = X + Xshift, Xraw = X (BSPLINE_4 quirk), x_lower and
+// dx of the array, all exactly as the Fortran receives them.  Output: `lo` = first stencil index
+// RELATIVE to the array's ilower (ic_lower - ilower) and W weights; weight j belongs to index
+// lo + j.  Clipping to the ghost box is the caller's job: every in-scope kernel's weights depend
+// only on the point's own index, so "clamp the bounds, then weigh" (3d.f.m4:2666-2678) equals
+// "weigh, then skip the clipped points".
+template <int K>
+__device__ __forceinline__ void stencil_1d(double Xs, double Xraw, double x_lower, double dx, int& lo, double* w)
+{
+    // (X + Xshift - x_lower)/dx, 3d.f.m4:1265 / :2660 / :565
+    const double t = __ddiv_rn(__dsub_rn(Xs, x_lower), dx);
+    if constexpr (K == IBK_IB_4)
+    {
+        // 3d.f.m4:1266-1273
+        lo = nint_f(t) - 2;
+        const double r = __dsub_rn(t, __dadd_rn((double)(lo + 1), 0.5));
+        const double q = sqrt(1.0 + 4.0 * r * (1.0 - r));
+        w[0] = 0.125 * (3.0 - 2.0 * r - q);
+        w[1] = 0.125 * (3.0 - 2.0 * r + q);
+        w[2] = 0.125 * (1.0 + 2.0 * r + q);
+        w[3] = 0.125 * (1.0 + 2.0 * r - q);
+    }
+    else if constexpr (K == IBK_IB_6)
+    {
+        // 3d.f.m4:2220, 2244-2272
+        // K = (59/60)*(1 - sqrt(1 - 3220/3481)) evaluated in double precision
+        const double Kc = 0x1.6d9b402672048p-1; // 0.714075092976608
+        lo = nint_f(t) - 3;
+        const double r = (1.0 - t) + ((double)(lo + 2) + 0.5);
+        const double r2 = r * r, r3 = r2 * r, r4 = r2 * r2, r6 = r4 * r2;
+        const double alpha = 28.0;
+        const double beta = (9.0 / 4.0) - (3.0 / 2.0) * (Kc + r2) + ((22.0 / 3.0) - 7.0 * Kc) * r - (7.0 / 3.0) * r3;
+        const double gamma = (1.0 / 4.0) * (((161.0 / 36.0) - (59.0 / 6.0) * Kc + 5.0 * (Kc * Kc)) * (1.0 / 2.0) * r2 +
+                                            (-(109.0 / 24.0) + 5.0 * Kc) * (1.0 / 3.0) * r4 + (5.0 / 18.0) * r6);
+        const double discr = beta * beta - 4.0 * alpha * gamma;
+        // sign(1, 3/2 - K) = +1 since K ~ 0.714
+        const double pm3 = (-beta + sqrt(discr)) / (2.0 * alpha);
+        w[0] = pm3;
+        w[1] = -3.0 * pm3 - (1.0 / 16.0) + (1.0 / 8.0) * (Kc + r2) + (1.0 / 12.0) * (3.0 * Kc - 1.0) * r +
+               (1.0 / 12.0) * r3;
+        w[2] = 2.0 * pm3 + (1.0 / 4.0) + (1.0 / 6.0) * (4.0 - 3.0 * Kc) * r - (1.0 / 6.0) * r3;
+        w[3] = 2.0 * pm3 + (5.0 / 8.0) - (1.0 / 4.0) * (Kc + r2);
+        w[4] = -3.0 * pm3 + (1.0 / 4.0) - (1.0 / 6.0) * (4.0 - 3.0 * Kc) * r + (1.0 / 6.0) * r3;
+        w[5] = pm3 - (1.0 / 16.0) + (1.0 / 8.0) * (Kc + r2) - (1.0 / 12.0) * (3.0 * Kc - 1.0) * r - (1.0 / 12.0) * r3;
+    }
+    else if constexpr (K == IBK_BSPLINE_3)
+    {
+        // 3d.f.m4:2659-2678: centre cell floor(t); weight = delta((Xs - X_cell)/dx)
+        const int c = (int)floor(t);
+        lo = c - 1;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+        {
+            const double X_cell = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)(lo + j), 0.5), dx));
+            w[j] = bspline_3_delta(__ddiv_rn(__dsub_rn(Xs, X_cell), dx));
+        }
+    }
+    else if constexpr (K == IBK_BSPLINE_4)
+    {
+        // 3d.f.m4:2882-2908; the side choice compares the UNSHIFTED X with X_cell (:2891)
+        const int c = (int)floor(t);
+        const double X_cell_c = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)c, 0.5), dx));
+        lo = (Xraw < X_cell_c) ? c - 2 : c - 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const double X_cell = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)(lo + j), 0.5), dx));
+            w[j] = bspline_4_delta(__ddiv_rn(__dsub_rn(Xs, X_cell), dx));
+        }
+    }
+    else
+    {
+        // PIECEWISE_LINEAR, 3d.f.m4:563-579
+        const int c = nint_f(__dsub_rn(t, 0.5));
+        const double X_cell = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)c, 0.5), dx));
+        if (Xs < X_cell)
+        {
+            lo = c - 1;
+            w[0] = __ddiv_rn(__dsub_rn(X_cell, Xs), dx);
+        }
+        else
+        {
+            lo = c;
+            w[0] = 1.0 + __ddiv_rn(__dsub_rn(X_cell, Xs), dx);
+        }
+        w[1] = 1.0 - w[0];
+    }
+}
+
+// IndexUtilities::getCellIndex, one dimension (ibtk/include/ibtk/private/IndexUtilities-inl.h:62-73).
+__device__ __forceinline__ int cell_index_1d(double X, double x_lower, double x_upper, double dx, int ilower, int iupper)
+{
+    const double dX_lower = __dsub_rn(X, x_lower);
+    const double dX_upper = __dsub_rn(X, x_upper);
+    if (fabs(dX_lower) <= fabs(dX_upper)) return ilower + (int)floor(__ddiv_rn(dX_lower, dx));
+    return iupper + (int)floor(__ddiv_rn(dX_upper, dx)) + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry handed to the tile kernels
+// ---------------------------------------------------------------------------------------------
+// One scalar array (one SideData axis, or one depth slice of a CellData) in "pp" coordinates:
+// pp = array index - (patch_lower - G), the same origin the binning uses for cells.
+struct CompGeom
+{
+    double* ptr;           // element (0,0,0) of the array (first ghost)
+    long long pitch;       // elements between consecutive rows (>= n[0])
+    int n[3];              // extents incl. ghosts
+    int pp0[3];            // pp coordinate of element 0  (= G - nugc)
+    int var[3];            // which x_lower variant each dimension uses (see TileParams::xl)
+    int vcol;              // which marker value column this component reads / writes
+};
+
+struct TileParams
+{
+    int ndim;
+    int ncomp;
+    CompGeom comp[IBK_MAX_COMP];
+    double dx[3];
+    double xl[3][2];       // x_lower variants per dimension, RELATIVE indexing: the stencil's `lo`
+                           // is relative to the patch lower index; variant 0 = cell-centred,
+                           // 1 = shifted by -dx/2 (LEInteractor.cpp:2464)
+    int nvar[3];
+    int G;                 // binning margin: pp = (index - patch_lower) + G
+    int nb[3];             // bricks per dimension (padded to a multiple of TILE_BRICKS)
+    int nt[3];             // marker tiles per dimension
+    int brick_base;        // first brick id of this patch in brick_start[]
+    int ot_lo[3];          // first output tile index per dimension (spread)
+    int ot_n[3];           // number of output tiles per dimension (spread)
+    double inv_vol;        // 1 / (dx0*dx1[*dx2])  (spread scale, 3d.f.m4:1439)
+};
+
+// Hierarchical brick id: tiles (tz,ty,tx) row-major, then brick-in-tile (bz,by,bx).
+__host__ __device__ __forceinline__ int brick_id_3d(int bx, int by, int bz, const int* nt)
+{
+    const int tx = bx >> 2, ty = by >> 2, tz = bz >> 2;
+    return (((tz * nt[1] + ty) * nt[0] + tx) << 6) | ((bz & 3) << 4) | ((by & 3) << 2) | (bx & 3);
+}
+__host__ __device__ __forceinline__ int brick_id_2d(int bx, int by, const int* nt)
+{
+    const int tx = bx >> 2, ty = by >> 2;
+    return ((ty * nt[0] + tx) << 4) | ((by & 3) << 2) | (bx & 3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA (cp.async.bulk.tensor), sm_90+/sm_100a
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t phase)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    while (!mbar_try_wait(bar, phase))
+    {
+    }
+}
+// generic-proxy writes to shared memory -> later async-proxy (TMA) accesses of the same bytes
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+} // namespace ibk

@@ -1,0 +1,140 @@
+// ibk_engine.h -- host-side internal interfaces between the translation units of libibk.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "ibk_device.cuh"
+
+namespace ibk
+{
+// ---------------------------------------------------------------------------------------------
+// binning geometry of one patch (device-visible POD)
+// ---------------------------------------------------------------------------------------------
+struct PatchBin
+{
+    int ndim;
+    int lower[3], upper[3];   // patch box (level cell indices)
+    int accept_lo[3], accept_hi[3]; // a marker is binned into this patch iff its cell is in this box
+    int G;                    // margin: cc = cell - lower + G  (cc >= 0 for every accepted cell)
+    int nb[3], nt[3];         // bricks / marker tiles per dimension
+    int brick_base;           // first brick id of this patch
+    int nbricks;              // nt[0]*nt[1]*nt[2] * 4^ndim
+};
+
+// How cells are computed from positions.
+struct CellGeom
+{
+    int ndim;
+    double x_lower[3], x_upper[3], dx[3];
+    int ilower[3], iupper[3];
+    int two_branch; // 1: IndexUtilities::getCellIndex (two-branch), 0: floor((X - x_lower)/dx) + ilower
+};
+
+struct DomainGeom
+{
+    int ndim;
+    double x_lower[3], x_upper[3];
+    int periodic[3];
+};
+
+void fill_patch_bin(PatchBin& pb, int ndim, const int* lower, const int* upper, const int* accept_lo, const int* accept_hi,
+                    int G, int brick_base);
+
+// Sorted marker bins (device).  Capacity-managed by the owner.
+struct Bins
+{
+    int n_entries = 0;        // entries handed to the binning
+    int n_active = 0;         // entries accepted by some patch (sorted to the front); filled lazily
+    int total_bricks = 0;
+    uint64_t* keys[2] = { nullptr, nullptr }; // ping-pong
+    uint32_t* vals[2] = { nullptr, nullptr };
+    int sorted_in = 0;        // which ping-pong buffer holds the sorted result
+    int* brick_start = nullptr; // [total_bricks + 1]
+    int tie_bits = 32;        // low key bits holding the tie-break id
+    void* sort_temp = nullptr;
+    size_t sort_temp_bytes = 0;
+    int capacity = 0;
+    int brick_capacity = 0;
+};
+
+struct Launcher
+{
+    cudaStream_t stream = 0;
+    long long launches = 0;
+};
+
+// ibk_sort.cu
+size_t radix_sort_temp_bytes(int n);
+int radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int n, int begin_bit,
+                     int end_bit, void* temp, cudaStream_t stream, long long* launches);
+
+// ibk_bin.cu
+cudaError_t bins_reserve(Bins& b, int n_entries, int total_bricks);
+void bins_free(Bins& b);
+// X: SoA [ndim][stride].  tie[i] = tie-break id of entry i (Lagrangian index) or nullptr for i.
+// cells_out ([n][ndim], optional) and owner_out ([n], optional) receive the binning products.
+cudaError_t bins_build(Bins& b, Launcher& L, const CellGeom& cg, const PatchBin* d_patches, int n_patches,
+                       const PatchBin* h_patches, const double* d_X, long long x_stride, const uint32_t* d_tie,
+                       uint32_t tie_bound, int n_entries, int* d_cells_out, int* d_owner_out);
+cudaError_t wrap_positions(Launcher& L, const DomainGeom& dg, double* d_X, long long x_stride, int n, int* d_escaped);
+// out[c][i] = in[c][perm[i]] for c < ncols (SoA gather through the sort permutation)
+cudaError_t gather_columns(Launcher& L, const double* d_in, long long in_stride, double* d_out, long long out_stride,
+                           const uint32_t* d_perm, int n, int ncols);
+cudaError_t scatter_columns(Launcher& L, const double* d_in, long long in_stride, double* d_out, long long out_stride,
+                            const uint32_t* d_perm, int n, int ncols);
+cudaError_t extract_low32(Launcher& L, const uint64_t* d_keys, uint32_t* d_out, int n, int bits);
+
+// ibk_interp.cu / ibk_spread.cu
+// Marker data for the tile kernels, in SORTED order (entry i of the bins).
+struct MarkerView
+{
+    const double* X;      // SoA [ndim][x_stride]: X + Xshift
+    const double* Xraw;   // SoA, unshifted positions (BSPLINE_4 quirk) or nullptr (= X)
+    long long x_stride;
+    double* V;            // values: column c of entry i is V[c * v_cstride + src(i) * v_istride]
+    long long v_cstride;
+    long long v_istride;
+    const uint32_t* src;  // optional gather index (sorted position -> value row); nullptr = identity
+};
+
+struct TmaMaps; // opaque, ibk_interp.cu
+
+cudaError_t launch_interp(Launcher& L, int kernel, const TileParams& tp, const Bins& bins, const MarkerView& mv,
+                          std::string& err);
+cudaError_t launch_spread(Launcher& L, int kernel, const TileParams& tp, const Bins& bins, const MarkerView& mv,
+                          std::string& err);
+long long count_touched(Launcher& L, int kernel, const TileParams& tp, const Bins& bins, std::string& err);
+
+// ibk_halo.cu
+struct RegionCopy
+{
+    double* dst;
+    const double* src;
+    long long dst_pitch, src_pitch;
+    int dst_n1, src_n1;   // rows per plane
+    int dst_off[3], src_off[3];
+    int ext[3];
+};
+cudaError_t launch_region_ops(Launcher& L, const std::vector<RegionCopy>& ops, int mode /*0 copy, 1 add*/);
+cudaError_t launch_pack(Launcher& L, const double* arr, long long pitch, int n1, const int* off, const int* ext, double* buf,
+                        int ndim);
+cudaError_t launch_unpack(Launcher& L, double* arr, long long pitch, int n1, const int* off, const int* ext,
+                          const double* buf, int ndim, int mode);
+cudaError_t launch_fill(Launcher& L, double* ptr, size_t count, double value);
+// layout conversion: reference (dense Fortran) <-> pitched device array
+cudaError_t copy_dense_to_pitched(Launcher& L, const double* src_dense, double* dst, long long pitch, const int* n, int ndim,
+                                  cudaMemcpyKind kind);
+cudaError_t copy_pitched_to_dense(Launcher& L, const double* src, long long pitch, double* dst_dense, const int* n, int ndim,
+                                  cudaMemcpyKind kind);
+// AoS [n][depth] <-> SoA [depth][stride]
+cudaError_t aos_to_soa(Launcher& L, const double* d_aos, double* d_soa, long long stride, int n, int depth);
+cudaError_t soa_to_aos(Launcher& L, const double* d_soa, long long stride, double* d_aos, int n, int depth);
+// entries for the raw / indexed seams: Xe[d][l] = X[idx[l]][d] + shift[l][d], Xr[d][l] = X[idx[l]][d]
+cudaError_t build_entries(Launcher& L, const double* d_X_aos, const int* d_idx, const double* d_shift, int n, int ndim,
+                          double* d_Xe, double* d_Xr, long long stride);
+cudaError_t compose_index(Launcher& L, const int* d_idx, const uint32_t* d_perm, uint32_t* d_out, int n);
+
+} // namespace ibk

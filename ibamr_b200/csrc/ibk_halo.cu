@@ -1,0 +1,241 @@
+// ibk_halo.cu -- grid halo operations and layout conversions.
+//
+// Device replacements for the SAMRAI schedules around the hot path:
+//   region copy        u ghost fill, u_ghost_fill_scheds[ln]->fillData (LDataManager.cpp:744):
+//                      same-level copies incl. periodic images
+//   region add         ghost-region accumulation onto the owning DOFs,
+//                      SAMRAIGhostDataAccumulator::accumulateGhostData
+//                      (ibtk/src/math/SAMRAIGhostDataAccumulator.cpp:327-334, ADD_VALUES/SCATTER_REVERSE)
+//   pack / unpack      the same regions through a contiguous buffer, for the inter-process exchange
+// plus AoS<->SoA (LData seam) and dense<->pitched (SAMRAI ArrayData seam) conversions.
+// All of it is pure HBM streaming: one thread per element, x fastest so that warps touch
+// contiguous 256-byte runs.
+#include <cuda_runtime.h>
+
+#include "ibk_engine.h"
+
+namespace ibk
+{
+struct RegionBatch
+{
+    RegionCopy op[16];
+    int n;
+};
+
+template <int MODE>
+__global__ void region_ops_kernel(RegionBatch rb)
+{
+    const RegionCopy& r = rb.op[blockIdx.y];
+    const long long total = (long long)r.ext[0] * r.ext[1] * r.ext[2];
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int i = (int)(q % r.ext[0]);
+        const long long t = q / r.ext[0];
+        const int j = (int)(t % r.ext[1]);
+        const int k = (int)(t / r.ext[1]);
+        const double v = r.src[((long long)(r.src_off[2] + k) * r.src_n1 + (r.src_off[1] + j)) * r.src_pitch + r.src_off[0] + i];
+        double* p = r.dst + ((long long)(r.dst_off[2] + k) * r.dst_n1 + (r.dst_off[1] + j)) * r.dst_pitch + r.dst_off[0] + i;
+        if (MODE == 0)
+            *p = v;
+        else
+            *p += v;
+    }
+}
+
+cudaError_t launch_region_ops(Launcher& L, const std::vector<RegionCopy>& ops, int mode)
+{
+    // The caller orders `ops` so that no two ops of one call write the same element (adds into the
+    // same owner from different sources go into separate calls), which keeps the sums deterministic.
+    for (size_t base = 0; base < ops.size(); base += 16)
+    {
+        RegionBatch rb;
+        rb.n = (int)std::min<size_t>(16, ops.size() - base);
+        long long maxtotal = 1;
+        for (int i = 0; i < rb.n; ++i)
+        {
+            rb.op[i] = ops[base + i];
+            const long long t = (long long)rb.op[i].ext[0] * rb.op[i].ext[1] * rb.op[i].ext[2];
+            if (t > maxtotal) maxtotal = t;
+        }
+        const int T = 256;
+        long long nbx = (maxtotal + T - 1) / T;
+        if (nbx > 4096) nbx = 4096;
+        dim3 grid((unsigned)nbx, (unsigned)rb.n);
+        if (mode == 0)
+            region_ops_kernel<0><<<grid, T, 0, L.stream>>>(rb);
+        else
+            region_ops_kernel<1><<<grid, T, 0, L.stream>>>(rb);
+        L.launches++;
+    }
+    return cudaGetLastError();
+}
+
+__global__ void pack_kernel(const double* __restrict__ arr, long long pitch, int n1, int o0, int o1, int o2, int e0, int e1,
+                            int e2, double* __restrict__ buf)
+{
+    const long long total = (long long)e0 * e1 * e2;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int i = (int)(q % e0);
+        const long long t = q / e0;
+        const int j = (int)(t % e1);
+        const int k = (int)(t / e1);
+        buf[q] = arr[((long long)(o2 + k) * n1 + (o1 + j)) * pitch + o0 + i];
+    }
+}
+
+template <int MODE>
+__global__ void unpack_kernel(double* __restrict__ arr, long long pitch, int n1, int o0, int o1, int o2, int e0, int e1,
+                              int e2, const double* __restrict__ buf)
+{
+    const long long total = (long long)e0 * e1 * e2;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int i = (int)(q % e0);
+        const long long t = q / e0;
+        const int j = (int)(t % e1);
+        const int k = (int)(t / e1);
+        double* p = arr + ((long long)(o2 + k) * n1 + (o1 + j)) * pitch + o0 + i;
+        if (MODE == 0)
+            *p = buf[q];
+        else
+            *p += buf[q];
+    }
+}
+
+static unsigned grid_for(long long total, int T)
+{
+    long long nb = (total + T - 1) / T;
+    if (nb > 148 * 32) nb = 148 * 32;
+    if (nb < 1) nb = 1;
+    return (unsigned)nb;
+}
+
+cudaError_t launch_pack(Launcher& L, const double* arr, long long pitch, int n1, const int* off, const int* ext, double* buf,
+                        int ndim)
+{
+    const int o2 = ndim == 3 ? off[2] : 0, e2 = ndim == 3 ? ext[2] : 1;
+    const long long total = (long long)ext[0] * ext[1] * e2;
+    if (total <= 0) return cudaSuccess;
+    pack_kernel<<<grid_for(total, 256), 256, 0, L.stream>>>(arr, pitch, n1, off[0], off[1], o2, ext[0], ext[1], e2, buf);
+    L.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack(Launcher& L, double* arr, long long pitch, int n1, const int* off, const int* ext, const double* buf,
+                          int ndim, int mode)
+{
+    const int o2 = ndim == 3 ? off[2] : 0, e2 = ndim == 3 ? ext[2] : 1;
+    const long long total = (long long)ext[0] * ext[1] * e2;
+    if (total <= 0) return cudaSuccess;
+    if (mode == 0)
+        unpack_kernel<0><<<grid_for(total, 256), 256, 0, L.stream>>>(arr, pitch, n1, off[0], off[1], o2, ext[0], ext[1], e2, buf);
+    else
+        unpack_kernel<1><<<grid_for(total, 256), 256, 0, L.stream>>>(arr, pitch, n1, off[0], off[1], o2, ext[0], ext[1], e2, buf);
+    L.launches++;
+    return cudaGetLastError();
+}
+
+__global__ void fill_kernel(double* __restrict__ p, size_t n, double v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+cudaError_t launch_fill(Launcher& L, double* ptr, size_t count, double value)
+{
+    if (count == 0) return cudaSuccess;
+    if (value == 0.0) return cudaMemsetAsync(ptr, 0, count * sizeof(double), L.stream);
+    fill_kernel<<<grid_for((long long)count, 256), 256, 0, L.stream>>>(ptr, count, value);
+    L.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t copy_dense_to_pitched(Launcher& L, const double* src_dense, double* dst, long long pitch, const int* n, int ndim,
+                                  cudaMemcpyKind kind)
+{
+    const size_t rows = (size_t)n[1] * (ndim == 3 ? n[2] : 1);
+    return cudaMemcpy2DAsync(dst, (size_t)pitch * sizeof(double), src_dense, (size_t)n[0] * sizeof(double),
+                             (size_t)n[0] * sizeof(double), rows, kind, L.stream);
+}
+
+cudaError_t copy_pitched_to_dense(Launcher& L, const double* src, long long pitch, double* dst_dense, const int* n, int ndim,
+                                  cudaMemcpyKind kind)
+{
+    const size_t rows = (size_t)n[1] * (ndim == 3 ? n[2] : 1);
+    return cudaMemcpy2DAsync(dst_dense, (size_t)n[0] * sizeof(double), src, (size_t)pitch * sizeof(double),
+                             (size_t)n[0] * sizeof(double), rows, kind, L.stream);
+}
+
+__global__ void aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ soa, long long stride, int n, int depth)
+{
+    const long long total = (long long)n * depth;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int i = (int)(q / depth), d = (int)(q % depth);
+        soa[d * stride + i] = aos[q];
+    }
+}
+__global__ void soa_to_aos_kernel(const double* __restrict__ soa, long long stride, double* __restrict__ aos, int n, int depth)
+{
+    const long long total = (long long)n * depth;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int i = (int)(q / depth), d = (int)(q % depth);
+        aos[q] = soa[d * stride + i];
+    }
+}
+
+cudaError_t aos_to_soa(Launcher& L, const double* d_aos, double* d_soa, long long stride, int n, int depth)
+{
+    if (n <= 0) return cudaSuccess;
+    aos_to_soa_kernel<<<grid_for((long long)n * depth, 256), 256, 0, L.stream>>>(d_aos, d_soa, stride, n, depth);
+    L.launches++;
+    return cudaGetLastError();
+}
+cudaError_t soa_to_aos(Launcher& L, const double* d_soa, long long stride, double* d_aos, int n, int depth)
+{
+    if (n <= 0) return cudaSuccess;
+    soa_to_aos_kernel<<<grid_for((long long)n * depth, 256), 256, 0, L.stream>>>(d_soa, stride, d_aos, n, depth);
+    L.launches++;
+    return cudaGetLastError();
+}
+
+__global__ void build_entries_kernel(const double* __restrict__ X, const int* __restrict__ idx, const double* __restrict__ shift,
+                                     int n, int ndim, double* __restrict__ Xe, double* __restrict__ Xr, long long stride)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    const long long s = idx ? idx[l] : l;
+    for (int d = 0; d < ndim; ++d)
+    {
+        const double x = X[s * ndim + d];
+        const double sh = shift ? shift[(long long)l * ndim + d] : 0.0;
+        Xe[d * stride + l] = __dadd_rn(x, sh); // X(d,s)+Xshift(d,l), 3d.f.m4:1265
+        if (Xr) Xr[d * stride + l] = x;
+    }
+}
+
+cudaError_t build_entries(Launcher& L, const double* d_X_aos, const int* d_idx, const double* d_shift, int n, int ndim,
+                          double* d_Xe, double* d_Xr, long long stride)
+{
+    if (n <= 0) return cudaSuccess;
+    build_entries_kernel<<<(n + 255) / 256, 256, 0, L.stream>>>(d_X_aos, d_idx, d_shift, n, ndim, d_Xe, d_Xr, stride);
+    L.launches++;
+    return cudaGetLastError();
+}
+
+__global__ void compose_index_kernel(const int* __restrict__ idx, const uint32_t* __restrict__ perm, uint32_t* __restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = idx ? (uint32_t)idx[perm[i]] : perm[i];
+}
+
+cudaError_t compose_index(Launcher& L, const int* d_idx, const uint32_t* d_perm, uint32_t* d_out, int n)
+{
+    if (n <= 0) return cudaSuccess;
+    compose_index_kernel<<<(n + 255) / 256, 256, 0, L.stream>>>(d_idx, d_perm, d_out, n);
+    L.launches++;
+    return cudaGetLastError();
+}
+
+} // namespace ibk

@@ -1,0 +1,301 @@
+// ibk_interp.cu -- velocity interpolation (grid -> markers) for sm_100a.
+//
+// Replaces lagrangian_<kernel>_interp{2,3}d (ibtk/src/lagrangian/fortran/
+// lagrangian_interaction3d.f.m4:1203-1334 ib_4, :2178-2375 ib_6, :2591-2693 bspline_3,
+// :2814-2923 bspline_4, :493-607 piecewise_linear; 2D twins in lagrangian_interaction2d.f.m4) and
+// the per-axis loop LEInteractor wraps around them (LEInteractor.cpp:2454-2486).
+//
+// One CTA per marker tile (16^ndim cells; its markers are one contiguous range of the sorted
+// storage).  For every component the CTA stages the tile's grid neighbourhood
+// (16 + 2M)^ndim points, M = kernel reach, into shared memory with ONE TMA box copy
+// (cp.async.bulk.tensor, out-of-bounds elements are zero-filled, which is exactly the reference's
+// "clip the stencil to the ghost box"), waits on an mbarrier, and then each thread gathers the
+// tensor-product stencil of one marker from shared memory.  A marker whose stencil is not inside
+// the staged box (only possible when its binning cell and its stencil origin disagree by a
+// rounding) takes a clipped global-memory path, so results never depend on the staging.
+// Arrays that do not satisfy TMA's 16-byte pitch/base alignment (the raw B4 seam on dense
+// reference-layout arrays) are staged with ordinary coalesced loads instead.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "ibk_engine.h"
+
+namespace ibk
+{
+struct alignas(64) TmaMapSet
+{
+    CUtensorMap m[IBK_MAX_COMP];
+};
+
+struct InterpArgs
+{
+    const int* brick_start;
+    const double* X;
+    const double* Xraw;
+    long long x_stride;
+    double* V;
+    long long v_cstride, v_istride;
+    const uint32_t* src;
+    unsigned tma_mask; // bit a set: component a is staged by TMA
+};
+
+constexpr int INTERP_THREADS = 256;
+
+template <int NDIM, int K>
+__global__ void __launch_bounds__(INTERP_THREADS)
+    interp_tile_kernel(const __grid_constant__ TileParams tp, const __grid_constant__ TmaMapSet maps, InterpArgs args)
+{
+    constexpr int W = KTraits<K>::W;
+    constexpr int M = KTraits<K>::M;
+    constexpr int S = TILE + 2 * M;
+    constexpr int BRICKS_PER_TILE = (NDIM == 3) ? 64 : 16;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* su = reinterpret_cast<double*>(smem_raw);
+    __shared__ uint64_t bar;
+
+    const int tile = blockIdx.x;
+    const int b0 = tp.brick_base + tile * BRICKS_PER_TILE;
+    const int s0 = args.brick_start[b0];
+    const int s1 = args.brick_start[b0 + BRICKS_PER_TILE];
+    if (s0 >= s1) return;
+
+    int t[3];
+    {
+        int r = tile;
+        t[0] = r % tp.nt[0];
+        r /= tp.nt[0];
+        t[1] = r % tp.nt[1];
+        t[2] = r / tp.nt[1];
+    }
+    // pp coordinate of the first staged point per dimension
+    int sp0[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) sp0[d] = TILE * t[d] - M;
+
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+
+    for (int a = 0; a < tp.ncomp; ++a)
+    {
+        const CompGeom& cg = tp.comp[a];
+        // element coordinates of the staged box's first point
+        int e0[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) e0[d] = sp0[d] - cg.pp0[d];
+        const bool use_tma = (args.tma_mask >> a) & 1u;
+        if (use_tma)
+        {
+            if (threadIdx.x == 0)
+            {
+                constexpr uint32_t bytes = (NDIM == 3 ? S * S * S : S * S) * sizeof(double);
+                fence_proxy_async_smem();
+                mbar_expect_tx(&bar, bytes);
+                if constexpr (NDIM == 3)
+                    tma_load_3d(su, &maps.m[a], &bar, e0[0], e0[1], e0[2]);
+                else
+                    tma_load_2d(su, &maps.m[a], &bar, e0[0], e0[1]);
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1;
+        }
+        else
+        {
+            constexpr int NPTS = (NDIM == 3) ? S * S * S : S * S;
+            for (int q = threadIdx.x; q < NPTS; q += INTERP_THREADS)
+            {
+                const int i = q % S;
+                const int j = (q / S) % S;
+                const int k = (NDIM == 3) ? q / (S * S) : 0;
+                const int gi = e0[0] + i, gj = e0[1] + j, gk = (NDIM == 3) ? e0[2] + k : 0;
+                double v = 0.0;
+                if (gi >= 0 && gi < cg.n[0] && gj >= 0 && gj < cg.n[1] && gk >= 0 && gk < cg.n[2])
+                    v = cg.ptr[((long long)gk * cg.n[1] + gj) * cg.pitch + gi];
+                su[q] = v;
+            }
+            __syncthreads();
+        }
+
+        for (int i = s0 + threadIdx.x; i < s1; i += INTERP_THREADS)
+        {
+            double w[NDIM][W];
+            int lo[NDIM]; // stencil origin in pp coordinates
+            bool staged = true;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d)
+            {
+                const double xs = args.X[d * args.x_stride + i];
+                const double xr = args.Xraw ? args.Xraw[d * args.x_stride + i] : xs;
+                int l;
+                stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w[d]);
+                lo[d] = l + tp.G;
+                staged = staged && (lo[d] >= sp0[d]) && (lo[d] + W <= sp0[d] + S);
+            }
+            double acc = 0.0;
+            if (staged)
+            {
+                if constexpr (NDIM == 3)
+                {
+                    const double* base = su + ((lo[2] - sp0[2]) * S + (lo[1] - sp0[1])) * S + (lo[0] - sp0[0]);
+#pragma unroll
+                    for (int k = 0; k < W; ++k)
+#pragma unroll
+                        for (int j = 0; j < W; ++j)
+                        {
+                            const double wyz = w[1][j] * w[2][k];
+#pragma unroll
+                            for (int ii = 0; ii < W; ++ii) acc += (w[0][ii] * wyz) * base[(k * S + j) * S + ii];
+                        }
+                }
+                else
+                {
+                    const double* base = su + (lo[1] - sp0[1]) * S + (lo[0] - sp0[0]);
+#pragma unroll
+                    for (int j = 0; j < W; ++j)
+#pragma unroll
+                        for (int ii = 0; ii < W; ++ii) acc += (w[0][ii] * w[1][j]) * base[j * S + ii];
+                }
+            }
+            else
+            {
+                // clipped global path (3d.f.m4:1309-1327)
+                constexpr int KW = (NDIM == 3) ? W : 1;
+#pragma unroll
+                for (int k = 0; k < KW; ++k)
+                {
+                    const int gk = (NDIM == 3) ? lo[NDIM - 1] + k - cg.pp0[2] : 0;
+                    if (gk < 0 || gk >= cg.n[2]) continue;
+#pragma unroll
+                    for (int j = 0; j < W; ++j)
+                    {
+                        const int gj = lo[1] + j - cg.pp0[1];
+                        if (gj < 0 || gj >= cg.n[1]) continue;
+                        const double wyz = (NDIM == 3) ? w[1][j] * w[NDIM - 1][k] : w[1][j];
+#pragma unroll
+                        for (int ii = 0; ii < W; ++ii)
+                        {
+                            const int gi = lo[0] + ii - cg.pp0[0];
+                            if (gi < 0 || gi >= cg.n[0]) continue;
+                            acc += (w[0][ii] * wyz) * cg.ptr[((long long)gk * cg.n[1] + gj) * cg.pitch + gi];
+                        }
+                    }
+                }
+            }
+            const long long row = args.src ? (long long)args.src[i] : (long long)i;
+            args.V[cg.vcol * args.v_cstride + row * args.v_istride] = acc;
+        }
+        __syncthreads(); // everyone is done with su before the next component overwrites it
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn)
+    {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+static bool tma_eligible(const CompGeom& cg)
+{
+    return ((uintptr_t)cg.ptr % 16 == 0) && ((cg.pitch * 8) % 16 == 0);
+}
+
+static bool make_map(CUtensorMap* m, const CompGeom& cg, int ndim, int S)
+{
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = { (cuuint64_t)cg.n[0], (cuuint64_t)cg.n[1], (cuuint64_t)cg.n[2] };
+    cuuint64_t strides[2] = { (cuuint64_t)cg.pitch * 8ull, (cuuint64_t)cg.pitch * 8ull * (cuuint64_t)cg.n[1] };
+    cuuint32_t box[3] = { (cuuint32_t)S, (cuuint32_t)S, (cuuint32_t)S };
+    cuuint32_t estr[3] = { 1, 1, 1 };
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)ndim, (void*)cg.ptr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int NDIM, int K>
+static cudaError_t launch_interp_t(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err)
+{
+    constexpr int M = KTraits<K>::M;
+    constexpr int S = TILE + 2 * M;
+    const size_t smem = sizeof(double) * (size_t)(NDIM == 3 ? S * S * S : S * S);
+    TmaMapSet maps;
+    std::memset(&maps, 0, sizeof(maps));
+    InterpArgs args;
+    args.brick_start = bins.brick_start;
+    args.X = mv.X;
+    args.Xraw = mv.Xraw;
+    args.x_stride = mv.x_stride;
+    args.V = mv.V;
+    args.v_cstride = mv.v_cstride;
+    args.v_istride = mv.v_istride;
+    args.src = mv.src;
+    args.tma_mask = 0;
+    for (int a = 0; a < tp.ncomp; ++a)
+        if (tma_eligible(tp.comp[a]) && make_map(&maps.m[a], tp.comp[a], NDIM, S)) args.tma_mask |= (1u << a);
+    auto kfn = interp_tile_kernel<NDIM, K>;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+    {
+        err = "cudaFuncSetAttribute(interp) failed";
+        return e;
+    }
+    const int ntiles = tp.nt[0] * tp.nt[1] * tp.nt[2];
+    if (ntiles <= 0) return cudaSuccess;
+    kfn<<<ntiles, INTERP_THREADS, smem, L.stream>>>(tp, maps, args);
+    L.launches++;
+    return cudaGetLastError();
+}
+
+template <int NDIM>
+static cudaError_t launch_interp_k(Launcher& L, int kernel, const TileParams& tp, const Bins& bins, const MarkerView& mv,
+                                   std::string& err)
+{
+    switch (kernel)
+    {
+    case IBK_PIECEWISE_LINEAR:
+        return launch_interp_t<NDIM, IBK_PIECEWISE_LINEAR>(L, tp, bins, mv, err);
+    case IBK_IB_4:
+        return launch_interp_t<NDIM, IBK_IB_4>(L, tp, bins, mv, err);
+    case IBK_IB_6:
+        return launch_interp_t<NDIM, IBK_IB_6>(L, tp, bins, mv, err);
+    case IBK_BSPLINE_3:
+        return launch_interp_t<NDIM, IBK_BSPLINE_3>(L, tp, bins, mv, err);
+    case IBK_BSPLINE_4:
+        return launch_interp_t<NDIM, IBK_BSPLINE_4>(L, tp, bins, mv, err);
+    default:
+        err = "unknown kernel";
+        return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_interp(Launcher& L, int kernel, const TileParams& tp, const Bins& bins, const MarkerView& mv,
+                          std::string& err)
+{
+    if (tp.ndim == 3) return launch_interp_k<3>(L, kernel, tp, bins, mv, err);
+    return launch_interp_k<2>(L, kernel, tp, bins, mv, err);
+}
+
+} // namespace ibk

@@ -1,0 +1,975 @@
+// ibk_level.cu -- the device-resident level behind seams B1/B2 (include/ibk.h): side-centred u / f
+// for the patches this process owns, SoA fp64 marker columns (LData role), rebin
+// (LDataManager::begin/endDataRedistribution role), spreadForce / interpolateVelocity
+// (IBMethod.cpp:972-995 / :672-694 over LDataManager.cpp:551-667 / :698-813) and the halo ops
+// that replace the SAMRAI schedules around them.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "ibk_ctx.h"
+
+using namespace ibk;
+
+namespace ibk
+{
+int fail(ibk_ctx* ctx, int code, const std::string& msg);
+int cuda_fail(ibk_ctx* ctx, cudaError_t e, const char* what);
+int kernel_reach(int kernel);
+long long round_pitch(int n0);
+struct ArrayComp
+{
+    double* ptr;
+    long long pitch;
+    int n[3];
+    int nugc[3];
+    int var[3];
+    int vcol;
+};
+void make_tile_params(TileParams& tp, int ndim, const double* dx, const double xl[3][2], const int* nvar, const PatchBin& pb,
+                      int ncomp, const ArrayComp* comps);
+
+// ---------------------------------------------------------------------------------------------
+// halo kernels
+// ---------------------------------------------------------------------------------------------
+constexpr int HALO_MAXSRC = 64;
+struct HaloSrc
+{
+    const double* ptr;
+    long long pitch;
+    int n1;
+    int alo[3], ahi[3]; // array box of the source, already shifted into the destination's index space
+    int ilo[3], ihi[3]; // interior (side) box of the source, shifted likewise
+};
+struct HaloArgs
+{
+    double* dst;
+    long long pitch;
+    int n1;
+    int ndim;
+    int alo[3], ahi[3]; // array box of the destination
+    int ilo[3], ihi[3]; // interior (side) box of the destination
+    int rim;            // ghost width (thickness of the interior rim that ghosts of others can reach)
+    int nsrc;
+    HaloSrc src[HALO_MAXSRC];
+};
+
+// Enumerates `outer \ inner` as up to 6 slabs (blockIdx.y selects the slab).
+__device__ __forceinline__ bool slab_box(int ndim, int slab, const int* olo, const int* ohi, const int* ilo, const int* ihi,
+                                         int* lo, int* hi)
+{
+    // slab order: (dim ndim-1 low, high), ..., (dim 0 low, high); dims above the slab's dim are
+    // restricted to the inner range so the slabs are disjoint
+    const int d = ndim - 1 - slab / 2;
+    const int side = slab & 1;
+    if (d < 0) return false;
+    for (int e = 0; e < 3; ++e)
+    {
+        if (e >= ndim)
+        {
+            lo[e] = hi[e] = 0;
+        }
+        else if (e > d)
+        {
+            lo[e] = max(olo[e], ilo[e]);
+            hi[e] = min(ohi[e], ihi[e]);
+        }
+        else if (e == d)
+        {
+            if (side == 0)
+            {
+                lo[e] = olo[e];
+                hi[e] = min(ohi[e], ilo[e] - 1);
+            }
+            else
+            {
+                lo[e] = max(olo[e], ihi[e] + 1);
+                hi[e] = ohi[e];
+            }
+        }
+        else
+        {
+            lo[e] = olo[e];
+            hi[e] = ohi[e];
+        }
+        if (hi[e] < lo[e]) return false;
+    }
+    return true;
+}
+
+// u ghost fill: every ghost element of dst takes the value of the first source whose INTERIOR holds it.
+__global__ void halo_fill_kernel(const HaloArgs* __restrict__ argp)
+{
+    const HaloArgs& A = *argp;
+    int lo[3], hi[3];
+    if (!slab_box(A.ndim, blockIdx.y, A.alo, A.ahi, A.ilo, A.ihi, lo, hi)) return;
+    const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
+    const long long total = (long long)e0 * e1 * e2;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int I0 = lo[0] + (int)(q % e0);
+        const long long t = q / e0;
+        const int I1 = lo[1] + (int)(t % e1), I2 = lo[2] + (int)(t / e1);
+        for (int s = 0; s < A.nsrc; ++s)
+        {
+            const HaloSrc& S = A.src[s];
+            if (I0 >= S.ilo[0] && I0 <= S.ihi[0] && I1 >= S.ilo[1] && I1 <= S.ihi[1] && I2 >= S.ilo[2] && I2 <= S.ihi[2])
+            {
+                const double v = S.ptr[((long long)(I2 - S.alo[2]) * S.n1 + (I1 - S.alo[1])) * S.pitch + (I0 - S.alo[0])];
+                A.dst[((long long)(I2 - A.alo[2]) * A.n1 + (I1 - A.alo[1])) * A.pitch + (I0 - A.alo[0])] = v;
+                break;
+            }
+        }
+    }
+}
+
+// f ghost accumulation: every interior element of dst within `rim` of the interior boundary adds the
+// GHOST copies other arrays (or periodic images of itself) hold of it, sources in canonical order.
+__global__ void halo_accum_kernel(const HaloArgs* __restrict__ argp)
+{
+    const HaloArgs& A = *argp;
+    int inlo[3], inhi[3], lo[3], hi[3];
+    for (int d = 0; d < 3; ++d)
+    {
+        inlo[d] = A.ilo[d] + (d < A.ndim ? A.rim : 0);
+        inhi[d] = A.ihi[d] - (d < A.ndim ? A.rim : 0);
+        if (d < A.ndim && inhi[d] < inlo[d])
+        {
+            // interior thinner than two rims: the whole interior is rim; make the inner box empty
+            inlo[d] = A.ihi[d] + 1;
+            inhi[d] = A.ihi[d];
+        }
+    }
+    // when the inner box is empty along some dim, slab "low" of that dim covers everything
+    if (!slab_box(A.ndim, blockIdx.y, A.ilo, A.ihi, inlo, inhi, lo, hi)) return;
+    const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
+    const long long total = (long long)e0 * e1 * e2;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int I0 = lo[0] + (int)(q % e0);
+        const long long t = q / e0;
+        const int I1 = lo[1] + (int)(t % e1), I2 = lo[2] + (int)(t / e1);
+        double* p = A.dst + ((long long)(I2 - A.alo[2]) * A.n1 + (I1 - A.alo[1])) * A.pitch + (I0 - A.alo[0]);
+        double acc = *p;
+        bool any = false;
+        for (int s = 0; s < A.nsrc; ++s)
+        {
+            const HaloSrc& S = A.src[s];
+            const bool in_arr = I0 >= S.alo[0] && I0 <= S.ahi[0] && I1 >= S.alo[1] && I1 <= S.ahi[1] && I2 >= S.alo[2] && I2 <= S.ahi[2];
+            if (!in_arr) continue;
+            const bool in_int = I0 >= S.ilo[0] && I0 <= S.ihi[0] && I1 >= S.ilo[1] && I1 <= S.ihi[1] && I2 >= S.ilo[2] && I2 <= S.ihi[2];
+            if (in_int) continue; // interior copies of shared faces are summed by face_sync_kernel
+            acc += S.ptr[((long long)(I2 - S.alo[2]) * S.n1 + (I1 - S.alo[1])) * S.pitch + (I0 - S.alo[0])];
+            any = true;
+        }
+        if (any) *p = acc;
+    }
+}
+
+struct FacePair
+{
+    double* a;
+    double* b;
+    long long a_pitch, b_pitch;
+    int a_n1, b_n1;
+    int a_off[3], b_off[3];
+    int ext[3];
+};
+// Shared faces of the axis-normal component exist in two interiors (or twice in one periodic
+// patch): both copies become a + b (PETScVecUtilities.cpp:519-611 gives them one DOF).
+__global__ void face_sync_kernel(const FacePair* __restrict__ pairs)
+{
+    const FacePair& P = pairs[blockIdx.y];
+    const long long total = (long long)P.ext[0] * P.ext[1] * P.ext[2];
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int i = (int)(q % P.ext[0]);
+        const long long t = q / P.ext[0];
+        const int j = (int)(t % P.ext[1]), k = (int)(t / P.ext[1]);
+        double* pa = P.a + ((long long)(P.a_off[2] + k) * P.a_n1 + (P.a_off[1] + j)) * P.a_pitch + P.a_off[0] + i;
+        double* pb = P.b + ((long long)(P.b_off[2] + k) * P.b_n1 + (P.b_off[1] + j)) * P.b_pitch + P.b_off[0] + i;
+        const double s = *pa + *pb;
+        *pa = s;
+        *pb = s;
+    }
+}
+
+__global__ void count_nonzero_kernel(const double* __restrict__ p, long long pitch, int n0, long long rows,
+                                     unsigned long long* __restrict__ out)
+{
+    unsigned long long c = 0;
+    const long long total = rows * n0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const long long r = q / n0;
+        const int i = (int)(q % n0);
+        if (p[r * pitch + i] != 0.0) ++c;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+__global__ void iota_kernel(uint32_t* p, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm, uint32_t* __restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
+}
+} // namespace ibk
+
+#define CK(call)                                                                                                       \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call);                                                     \
+    } while (0)
+#define NEED_LEVEL()                                                                                                   \
+    if (!ctx) return IBK_ERR_INVALID;                                                                                  \
+    if (!ctx->lv.valid) return fail(ctx, IBK_ERR_STATE, "no level registered (ibk_level_create)")
+
+// host-side halo plans live next to the level (file-local registry keyed by ctx)
+namespace
+{
+struct HaloPlan
+{
+    // [which][patch][axis]
+    std::vector<HaloArgs*> d_args[2];
+    std::vector<FacePair*> d_pairs; // per axis (f only)
+    std::vector<int> n_pairs;
+    std::vector<void*> allocs;
+};
+struct LevelExtra
+{
+    HaloPlan halo;
+    std::vector<TileParams> tp; // per patch: [u params, f params] interleaved: tp[2*p + which]
+};
+static std::vector<std::pair<ibk_ctx*, LevelExtra*>> g_extra;
+LevelExtra* extra_of(ibk_ctx* ctx, bool create)
+{
+    for (auto& kv : g_extra)
+        if (kv.first == ctx) return kv.second;
+    if (!create) return nullptr;
+    g_extra.push_back({ ctx, new LevelExtra() });
+    return g_extra.back().second;
+}
+void extra_drop(ibk_ctx* ctx)
+{
+    for (size_t i = 0; i < g_extra.size(); ++i)
+        if (g_extra[i].first == ctx)
+        {
+            for (void* p : g_extra[i].second->halo.allocs) cudaFree(p);
+            delete g_extra[i].second;
+            g_extra.erase(g_extra.begin() + i);
+            return;
+        }
+}
+} // namespace
+
+static void side_geom(const LevelState& lv, const PatchState& ps, int axis, int* alo, int* ahi, int* ilo, int* ihi)
+{
+    for (int d = 0; d < 3; ++d)
+    {
+        if (d < lv.ndim)
+        {
+            ilo[d] = ps.lower[d];
+            ihi[d] = ps.upper[d] + (d == axis ? 1 : 0);
+            alo[d] = ilo[d] - lv.gcw[d];
+            ahi[d] = ihi[d] + lv.gcw[d];
+        }
+        else
+        {
+            alo[d] = ahi[d] = ilo[d] = ihi[d] = 0;
+        }
+    }
+}
+
+static int build_halo_plan(ibk_ctx* ctx)
+{
+    LevelState& lv = ctx->lv;
+    LevelExtra* ex = extra_of(ctx, true);
+    HaloPlan& hp = ex->halo;
+    const int ndim = lv.ndim, P = (int)lv.patches.size();
+    int N[3] = { 1, 1, 1 };
+    for (int d = 0; d < ndim; ++d) N[d] = lv.domain_upper[d] - lv.domain_lower[d] + 1;
+    for (int which = 0; which < 2; ++which) hp.d_args[which].assign((size_t)P * ndim, nullptr);
+    hp.d_pairs.assign(ndim, nullptr);
+    hp.n_pairs.assign(ndim, 0);
+    for (int axis = 0; axis < ndim; ++axis)
+    {
+        std::vector<FacePair> pairs;
+        for (int p = 0; p < P; ++p)
+        {
+            const PatchState& ps = lv.patches[p];
+            int alo[3], ahi[3], ilo[3], ihi[3];
+            side_geom(lv, ps, axis, alo, ahi, ilo, ihi);
+            for (int which = 0; which < 2; ++which)
+            {
+                HaloArgs A;
+                std::memset(&A, 0, sizeof(A));
+                A.dst = which == 0 ? ps.u[axis] : ps.f[axis];
+                A.pitch = ps.pitch[axis];
+                A.n1 = ps.n[axis][1];
+                A.ndim = ndim;
+                A.rim = 0;
+                for (int d = 0; d < 3; ++d)
+                {
+                    A.alo[d] = alo[d];
+                    A.ahi[d] = ahi[d];
+                    A.ilo[d] = ilo[d];
+                    A.ihi[d] = ihi[d];
+                    if (d < ndim) A.rim = std::max(A.rim, lv.gcw[d]);
+                }
+                // canonical source order: patch number, then periodic offset (o2, o1, o0)
+                for (int q = 0; q < P; ++q)
+                {
+                    const PatchState& qs = lv.patches[q];
+                    int qalo[3], qahi[3], qilo[3], qihi[3];
+                    side_geom(lv, qs, axis, qalo, qahi, qilo, qihi);
+                    int omin[3] = { 0, 0, 0 }, omax[3] = { 0, 0, 0 };
+                    for (int d = 0; d < ndim; ++d)
+                        if (lv.periodic[d])
+                        {
+                            omin[d] = -1;
+                            omax[d] = 1;
+                        }
+                    for (int o2 = omin[2]; o2 <= omax[2]; ++o2)
+                        for (int o1 = omin[1]; o1 <= omax[1]; ++o1)
+                            for (int o0 = omin[0]; o0 <= omax[0]; ++o0)
+                            {
+                                if (q == p && o0 == 0 && o1 == 0 && o2 == 0) continue;
+                                const int o[3] = { o0 * N[0], o1 * N[1], o2 * N[2] };
+                                // does the shifted source array intersect the destination array at all?
+                                bool hit = true;
+                                for (int d = 0; d < ndim; ++d)
+                                    hit = hit && (qalo[d] + o[d] <= ahi[d]) && (qahi[d] + o[d] >= alo[d]);
+                                if (!hit) continue;
+                                if (A.nsrc >= HALO_MAXSRC) return fail(ctx, IBK_ERR_INVALID, "too many halo sources for one patch");
+                                HaloSrc& S = A.src[A.nsrc++];
+                                S.ptr = which == 0 ? qs.u[axis] : qs.f[axis];
+                                S.pitch = qs.pitch[axis];
+                                S.n1 = qs.n[axis][1];
+                                for (int d = 0; d < 3; ++d)
+                                {
+                                    S.alo[d] = qalo[d] + (d < ndim ? o[d] : 0);
+                                    S.ahi[d] = qahi[d] + (d < ndim ? o[d] : 0);
+                                    S.ilo[d] = qilo[d] + (d < ndim ? o[d] : 0);
+                                    S.ihi[d] = qihi[d] + (d < ndim ? o[d] : 0);
+                                }
+                                // shared faces (f only, found once per unordered pair): q's LOWER face == p's UPPER face
+                                if (which == 1 && qilo[axis] + o[axis] == ihi[axis])
+                                {
+                                    FacePair fp;
+                                    std::memset(&fp, 0, sizeof(fp));
+                                    bool ok = true;
+                                    int lo[3], hi[3];
+                                    for (int d = 0; d < 3; ++d)
+                                    {
+                                        if (d >= ndim)
+                                        {
+                                            lo[d] = hi[d] = 0;
+                                            continue;
+                                        }
+                                        if (d == axis)
+                                        {
+                                            lo[d] = hi[d] = ihi[axis];
+                                        }
+                                        else
+                                        {
+                                            lo[d] = std::max(ilo[d], qilo[d] + o[d]);
+                                            hi[d] = std::min(ihi[d], qihi[d] + o[d]);
+                                        }
+                                        ok = ok && hi[d] >= lo[d];
+                                    }
+                                    if (ok)
+                                    {
+                                        fp.a = ps.f[axis];
+                                        fp.b = qs.f[axis];
+                                        fp.a_pitch = ps.pitch[axis];
+                                        fp.b_pitch = qs.pitch[axis];
+                                        fp.a_n1 = ps.n[axis][1];
+                                        fp.b_n1 = qs.n[axis][1];
+                                        for (int d = 0; d < 3; ++d)
+                                        {
+                                            fp.a_off[d] = lo[d] - alo[d];
+                                            fp.b_off[d] = lo[d] - (qalo[d] + (d < ndim ? o[d] : 0));
+                                            fp.ext[d] = hi[d] - lo[d] + 1;
+                                        }
+                                        pairs.push_back(fp);
+                                    }
+                                }
+                            }
+                }
+                HaloArgs* d_A = nullptr;
+                CK(cudaMalloc(&d_A, sizeof(HaloArgs)));
+                hp.allocs.push_back(d_A);
+                CK(cudaMemcpy(d_A, &A, sizeof(HaloArgs), cudaMemcpyHostToDevice));
+                hp.d_args[which][(size_t)p * ndim + axis] = d_A;
+            }
+        }
+        hp.n_pairs[axis] = (int)pairs.size();
+        if (!pairs.empty())
+        {
+            FacePair* d_p = nullptr;
+            CK(cudaMalloc(&d_p, sizeof(FacePair) * pairs.size()));
+            hp.allocs.push_back(d_p);
+            CK(cudaMemcpy(d_p, pairs.data(), sizeof(FacePair) * pairs.size(), cudaMemcpyHostToDevice));
+            hp.d_pairs[axis] = d_p;
+        }
+    }
+    return IBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// level
+// ---------------------------------------------------------------------------------------------
+extern "C" int ibk_level_destroy(ibk_ctx* ctx)
+{
+    if (!ctx) return IBK_ERR_INVALID;
+    LevelState& lv = ctx->lv;
+    if (!lv.valid) return IBK_OK;
+    cudaStreamSynchronize(ctx->L.stream);
+    for (auto& ps : lv.patches)
+        for (int a = 0; a < 3; ++a)
+        {
+            if (ps.u[a]) cudaFree(ps.u[a]);
+            if (ps.f[a]) cudaFree(ps.f[a]);
+        }
+    if (lv.d_bins) cudaFree(lv.d_bins);
+    for (void* p : { (void*)lv.X, (void*)lv.U, (void*)lv.F, (void*)lv.tmp, (void*)lv.lag, (void*)lv.lag_prev,
+                     (void*)lv.cells, (void*)lv.owner, (void*)lv.escaped })
+        if (p) cudaFree(p);
+    bins_free(lv.bins);
+    extra_drop(ctx);
+    lv = LevelState();
+    return IBK_OK;
+}
+
+extern "C" int ibk_level_create(ibk_ctx* ctx, const ibk_level_desc* desc)
+{
+    if (!ctx || !desc) return IBK_ERR_INVALID;
+    if (desc->ndim != 2 && desc->ndim != 3) return fail(ctx, IBK_ERR_INVALID, "ndim must be 2 or 3");
+    if (desc->n_patches < 0 || (desc->n_patches > 0 && (!desc->patch_lower || !desc->patch_upper)))
+        return fail(ctx, IBK_ERR_INVALID, "patch boxes missing");
+    ibk_level_destroy(ctx);
+    LevelState& lv = ctx->lv;
+    const int ndim = desc->ndim;
+    lv.ndim = ndim;
+    int gmax = 0;
+    for (int d = 0; d < 3; ++d)
+    {
+        lv.domain_lower[d] = d < ndim ? desc->domain_lower[d] : 0;
+        lv.domain_upper[d] = d < ndim ? desc->domain_upper[d] : 0;
+        lv.periodic[d] = d < ndim ? desc->periodic[d] : 0;
+        lv.gcw[d] = d < ndim ? desc->gcw[d] : 0;
+        lv.x_lower[d] = d < ndim ? desc->x_lower[d] : 0.0;
+        lv.x_upper[d] = d < ndim ? desc->x_upper[d] : 1.0;
+        const int ncell = lv.domain_upper[d] - lv.domain_lower[d] + 1;
+        // level dx as IndexUtilities::getCellIndex(X, grid_geom, ratio) forms it (dx0/ratio);
+        // the caller passes the level's own domain box so dx = L / n_cells
+        lv.dx[d] = d < ndim ? (lv.x_upper[d] - lv.x_lower[d]) / (double)ncell : 1.0;
+        gmax = std::max(gmax, lv.gcw[d]);
+    }
+    lv.G = gmax + 4;
+    int brick_base = 0;
+    for (int p = 0; p < desc->n_patches; ++p)
+    {
+        PatchState ps;
+        std::memset(&ps, 0, sizeof(ps));
+        for (int d = 0; d < 3; ++d)
+        {
+            ps.lower[d] = d < ndim ? desc->patch_lower[p * ndim + d] : 0;
+            ps.upper[d] = d < ndim ? desc->patch_upper[p * ndim + d] : 0;
+        }
+        fill_patch_bin(ps.pb, ndim, ps.lower, ps.upper, ps.lower, ps.upper, lv.G, brick_base);
+        brick_base += ps.pb.nbricks;
+        for (int a = 0; a < ndim; ++a)
+        {
+            for (int d = 0; d < 3; ++d)
+                ps.n[a][d] = d < ndim ? ps.upper[d] - ps.lower[d] + 1 + 2 * lv.gcw[d] + (d == a ? 1 : 0) : 1;
+            ps.pitch[a] = round_pitch(ps.n[a][0]);
+            ps.elems[a] = (size_t)ps.pitch[a] * ps.n[a][1] * ps.n[a][2];
+            CK(cudaMalloc(&ps.u[a], sizeof(double) * ps.elems[a]));
+            CK(cudaMalloc(&ps.f[a], sizeof(double) * ps.elems[a]));
+            CK(cudaMemsetAsync(ps.u[a], 0, sizeof(double) * ps.elems[a], ctx->L.stream));
+            CK(cudaMemsetAsync(ps.f[a], 0, sizeof(double) * ps.elems[a], ctx->L.stream));
+        }
+        lv.patches.push_back(ps);
+        lv.h_bins.push_back(ps.pb);
+    }
+    if (!lv.h_bins.empty())
+    {
+        CK(cudaMalloc(&lv.d_bins, sizeof(PatchBin) * lv.h_bins.size()));
+        CK(cudaMemcpy(lv.d_bins, lv.h_bins.data(), sizeof(PatchBin) * lv.h_bins.size(), cudaMemcpyHostToDevice));
+    }
+    CK(cudaMalloc(&lv.escaped, sizeof(int)));
+    lv.valid = true;
+    // tile parameters per patch
+    LevelExtra* ex = extra_of(ctx, true);
+    ex->tp.resize(2 * lv.patches.size());
+    for (size_t p = 0; p < lv.patches.size(); ++p)
+    {
+        const PatchState& ps = lv.patches[p];
+        double xl[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
+        int nvar[3] = { 1, 1, 1 };
+        for (int d = 0; d < ndim; ++d)
+        {
+            // patch x_lower as SAMRAI's CartesianPatchGeometry holds it: x_lo + dx * (lower - domain_lower)
+            const double pxl = lv.x_lower[d] + lv.dx[d] * (double)(ps.lower[d] - lv.domain_lower[d]);
+            xl[d][0] = pxl;
+            xl[d][1] = pxl - 0.5 * lv.dx[d];
+            nvar[d] = 2;
+        }
+        for (int which = 0; which < 2; ++which)
+        {
+            ArrayComp comps[3];
+            for (int a = 0; a < ndim; ++a)
+            {
+                comps[a].ptr = which == 0 ? ps.u[a] : ps.f[a];
+                comps[a].pitch = ps.pitch[a];
+                comps[a].vcol = a;
+                for (int d = 0; d < 3; ++d)
+                {
+                    comps[a].n[d] = ps.n[a][d];
+                    comps[a].nugc[d] = d < ndim ? lv.gcw[d] : 0;
+                    comps[a].var[d] = (d == a) ? 1 : 0;
+                }
+            }
+            make_tile_params(ex->tp[2 * p + which], ndim, lv.dx, xl, nvar, ps.pb, ndim, comps);
+        }
+    }
+    int rc = build_halo_plan(ctx);
+    if (rc != IBK_OK) return rc;
+    return IBK_OK;
+}
+
+static int check_patch_axis(ibk_ctx* ctx, int which, int patch, int axis)
+{
+    if (which < 0 || which > 1 || patch < 0 || patch >= (int)ctx->lv.patches.size() || axis < 0 || axis >= ctx->lv.ndim)
+        return fail(ctx, IBK_ERR_INVALID, "bad (which, patch, axis)");
+    return IBK_OK;
+}
+
+extern "C" int ibk_grid_upload(ibk_ctx* ctx, int which, int patch, int axis, const double* h_data)
+{
+    NEED_LEVEL();
+    if (int rc = check_patch_axis(ctx, which, patch, axis)) return rc;
+    PatchState& ps = ctx->lv.patches[patch];
+    CK(copy_dense_to_pitched(ctx->L, h_data, which == 0 ? ps.u[axis] : ps.f[axis], ps.pitch[axis], ps.n[axis], ctx->lv.ndim,
+                             cudaMemcpyHostToDevice));
+    return IBK_OK;
+}
+extern "C" int ibk_grid_download(ibk_ctx* ctx, int which, int patch, int axis, double* h_data)
+{
+    NEED_LEVEL();
+    if (int rc = check_patch_axis(ctx, which, patch, axis)) return rc;
+    PatchState& ps = ctx->lv.patches[patch];
+    CK(copy_pitched_to_dense(ctx->L, which == 0 ? ps.u[axis] : ps.f[axis], ps.pitch[axis], h_data, ps.n[axis], ctx->lv.ndim,
+                             cudaMemcpyDeviceToHost));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    return IBK_OK;
+}
+extern "C" int ibk_grid_fill(ibk_ctx* ctx, int which, double value)
+{
+    NEED_LEVEL();
+    if (which < 0 || which > 1) return fail(ctx, IBK_ERR_INVALID, "which must be 0 (u) or 1 (f)");
+    for (auto& ps : ctx->lv.patches)
+        for (int a = 0; a < ctx->lv.ndim; ++a) CK(launch_fill(ctx->L, which == 0 ? ps.u[a] : ps.f[a], ps.elems[a], value));
+    return IBK_OK;
+}
+extern "C" int ibk_grid_device_ptr(ibk_ctx* ctx, int which, int patch, int axis, double** d_ptr, long long* pitch, int* dims)
+{
+    NEED_LEVEL();
+    if (int rc = check_patch_axis(ctx, which, patch, axis)) return rc;
+    PatchState& ps = ctx->lv.patches[patch];
+    if (d_ptr) *d_ptr = which == 0 ? ps.u[axis] : ps.f[axis];
+    if (pitch) *pitch = ps.pitch[axis];
+    if (dims)
+        for (int d = 0; d < ctx->lv.ndim; ++d) dims[d] = ps.n[axis][d];
+    return IBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// markers
+// ---------------------------------------------------------------------------------------------
+static int reserve_markers(ibk_ctx* ctx, int n)
+{
+    LevelState& lv = ctx->lv;
+    if ((long long)n <= lv.stride) return IBK_OK;
+    const long long stride = ((long long)std::max(n, 1024) + 31) / 32 * 32;
+    for (double** pp : { &lv.X, &lv.U, &lv.F, &lv.tmp })
+    {
+        if (*pp) cudaFree(*pp);
+        *pp = nullptr;
+        CK(cudaMalloc(pp, sizeof(double) * (size_t)stride * lv.ndim));
+        CK(cudaMemsetAsync(*pp, 0, sizeof(double) * (size_t)stride * lv.ndim, ctx->L.stream));
+    }
+    for (uint32_t** pp : { &lv.lag, &lv.lag_prev })
+    {
+        if (*pp) cudaFree(*pp);
+        *pp = nullptr;
+        CK(cudaMalloc(pp, sizeof(uint32_t) * (size_t)stride));
+    }
+    if (lv.cells) cudaFree(lv.cells);
+    if (lv.owner) cudaFree(lv.owner);
+    CK(cudaMalloc(&lv.cells, sizeof(int) * (size_t)stride * lv.ndim));
+    CK(cudaMalloc(&lv.owner, sizeof(int) * (size_t)stride));
+    lv.stride = stride;
+    return IBK_OK;
+}
+
+static double* column_of(LevelState& lv, int which)
+{
+    return which == 0 ? lv.X : which == 1 ? lv.U : lv.F;
+}
+
+extern "C" int ibk_markers_upload(ibk_ctx* ctx, int which, const double* h_data)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (which < 0 || which > 2 || !h_data) return fail(ctx, IBK_ERR_INVALID, "bad marker column");
+    if (lv.n <= 0) return IBK_OK;
+    const size_t bytes = sizeof(double) * (size_t)lv.n * lv.ndim;
+    CK(ctx->b_io[5].reserve(bytes));
+    CK(cudaMemcpyAsync(ctx->b_io[5].p, h_data, bytes, cudaMemcpyHostToDevice, ctx->L.stream));
+    // AoS (Lagrangian order) -> SoA (Lagrangian order) -> storage order: col[i] = lagcol[lag[i]]
+    CK(aos_to_soa(ctx->L, ctx->b_io[5].as<double>(), lv.tmp, lv.stride, lv.n, lv.ndim));
+    CK(gather_columns(ctx->L, lv.tmp, lv.stride, column_of(lv, which), lv.stride, lv.lag, lv.n, lv.ndim));
+    if (which == 0) lv.binned = false;
+    return IBK_OK;
+}
+extern "C" int ibk_markers_download(ibk_ctx* ctx, int which, double* h_data)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (which < 0 || which > 2 || !h_data) return fail(ctx, IBK_ERR_INVALID, "bad marker column");
+    if (lv.n <= 0) return IBK_OK;
+    const size_t bytes = sizeof(double) * (size_t)lv.n * lv.ndim;
+    CK(ctx->b_io[5].reserve(bytes));
+    CK(scatter_columns(ctx->L, column_of(lv, which), lv.stride, lv.tmp, lv.stride, lv.lag, lv.n, lv.ndim));
+    CK(soa_to_aos(ctx->L, lv.tmp, lv.stride, ctx->b_io[5].as<double>(), lv.n, lv.ndim));
+    CK(cudaMemcpyAsync(h_data, ctx->b_io[5].p, bytes, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    return IBK_OK;
+}
+extern "C" int ibk_markers_set_positions(ibk_ctx* ctx, const double* h_X, int n_markers)
+{
+    NEED_LEVEL();
+    if (n_markers < 0 || (n_markers > 0 && !h_X)) return fail(ctx, IBK_ERR_INVALID, "bad marker positions");
+    LevelState& lv = ctx->lv;
+    if (int rc = reserve_markers(ctx, n_markers)) return rc;
+    lv.n = n_markers;
+    lv.binned = false;
+    if (n_markers == 0) return IBK_OK;
+    iota_kernel<<<(n_markers + 255) / 256, 256, 0, ctx->L.stream>>>(lv.lag, n_markers);
+    ctx->L.launches++;
+    return ibk_markers_upload(ctx, 0, h_X);
+}
+extern "C" int ibk_markers_count(const ibk_ctx* ctx)
+{
+    return (ctx && ctx->lv.valid) ? ctx->lv.n : 0;
+}
+extern "C" int ibk_markers_device_ptr(ibk_ctx* ctx, int which, double** d_ptr, long long* stride)
+{
+    NEED_LEVEL();
+    if (which < 0 || which > 2) return fail(ctx, IBK_ERR_INVALID, "bad marker column");
+    if (d_ptr) *d_ptr = column_of(ctx->lv, which);
+    if (stride) *stride = ctx->lv.stride;
+    return IBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rebin
+// ---------------------------------------------------------------------------------------------
+extern "C" int ibk_rebin(ibk_ctx* ctx, int error_if_points_leave_domain)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    const int ndim = lv.ndim, n = lv.n;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[2][0], ctx->L.stream));
+    DomainGeom dg;
+    std::memset(&dg, 0, sizeof(dg));
+    dg.ndim = ndim;
+    CellGeom cg;
+    std::memset(&cg, 0, sizeof(cg));
+    cg.ndim = ndim;
+    cg.two_branch = 1; // IndexUtilities::getCellIndex(X, grid_geom, ratio), IndexUtilities-inl.h:225-242
+    for (int d = 0; d < ndim; ++d)
+    {
+        dg.x_lower[d] = cg.x_lower[d] = lv.x_lower[d];
+        dg.x_upper[d] = cg.x_upper[d] = lv.x_upper[d];
+        dg.periodic[d] = lv.periodic[d];
+        cg.dx[d] = lv.dx[d];
+        cg.ilower[d] = lv.domain_lower[d];
+        cg.iupper[d] = lv.domain_upper[d];
+    }
+    CK(cudaMemsetAsync(lv.escaped, 0, sizeof(int), ctx->L.stream));
+    CK(wrap_positions(ctx->L, dg, lv.X, lv.stride, n, lv.escaped));
+    if (error_if_points_leave_domain)
+    {
+        int esc = 0;
+        CK(cudaMemcpyAsync(&esc, lv.escaped, sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
+        CK(cudaStreamSynchronize(ctx->L.stream));
+        if (esc > 0) return fail(ctx, IBK_ERR_ESCAPED, "IB point has escaped from the computational domain!");
+    }
+    if (n > 0) CK(cudaMemcpyAsync(lv.lag_prev, lv.lag, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    CK(bins_build(lv.bins, ctx->L, cg, lv.d_bins, (int)lv.h_bins.size(), lv.h_bins.data(), lv.X, lv.stride, lv.lag,
+                  (uint32_t)std::max(n, 1), n, lv.cells, lv.owner));
+    if (n > 0)
+    {
+        const uint32_t* perm = lv.bins.vals[lv.bins.sorted_in];
+        for (double** col : { &lv.X, &lv.U, &lv.F })
+        {
+            // permute into the scratch column, then swap roles (no copy back)
+            CK(gather_columns(ctx->L, *col, lv.stride, lv.tmp, lv.stride, perm, n, ndim));
+            std::swap(*col, lv.tmp);
+        }
+        CK(extract_low32(ctx->L, lv.bins.keys[lv.bins.sorted_in], lv.lag, n, lv.bins.tie_bits));
+    }
+    lv.binned = true;
+    if (ctx->timing)
+    {
+        CK(cudaEventRecord(ctx->ev[2][1], ctx->L.stream));
+        ctx->ev_valid[2] = true;
+    }
+    return IBK_OK;
+}
+
+extern "C" int ibk_bin_get_cells(ibk_ctx* ctx, int* h_cells, int* h_owner)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (!lv.binned) return fail(ctx, IBK_ERR_STATE, "ibk_rebin has not run");
+    const int n = lv.n, ndim = lv.ndim;
+    if (n == 0) return IBK_OK;
+    std::vector<int> cells((size_t)n * ndim), owner(n);
+    std::vector<uint32_t> lagp(n);
+    CK(cudaMemcpyAsync(cells.data(), lv.cells, sizeof(int) * cells.size(), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaMemcpyAsync(owner.data(), lv.owner, sizeof(int) * owner.size(), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaMemcpyAsync(lagp.data(), lv.lag_prev, sizeof(uint32_t) * lagp.size(), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    for (int i = 0; i < n; ++i)
+    {
+        const uint32_t l = lagp[i];
+        if (h_cells)
+            for (int d = 0; d < ndim; ++d) h_cells[(size_t)l * ndim + d] = cells[(size_t)i * ndim + d];
+        if (h_owner) h_owner[l] = owner[i];
+    }
+    return IBK_OK;
+}
+extern "C" int ibk_bin_get_order(ibk_ctx* ctx, int* h_lag_idx)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (!lv.binned) return fail(ctx, IBK_ERR_STATE, "ibk_rebin has not run");
+    if (lv.n == 0 || !h_lag_idx) return IBK_OK;
+    CK(cudaMemcpyAsync(h_lag_idx, lv.lag, sizeof(uint32_t) * (size_t)lv.n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    return IBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// halo
+// ---------------------------------------------------------------------------------------------
+static unsigned halo_blocks(const LevelState& lv, const PatchState& ps, int axis)
+{
+    // enough CTAs to cover the largest slab (a face of the array times the ghost width) a few times over
+    long long face = 1;
+    for (int d = 0; d < lv.ndim; ++d) face = std::max(face, (long long)ps.n[axis][(d + 1) % lv.ndim] * ps.n[axis][(d + 2) % lv.ndim]);
+    long long nb = (face * 4 + 255) / 256;
+    return (unsigned)std::min<long long>(std::max<long long>(nb, 1), 148 * 8);
+}
+
+extern "C" int ibk_halo_local(ibk_ctx* ctx, int which)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    LevelExtra* ex = extra_of(ctx, false);
+    if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
+    if (which < 0 || which > 1) return fail(ctx, IBK_ERR_INVALID, "which must be 0 (u: fill) or 1 (f: accumulate)");
+    const int ndim = lv.ndim, P = (int)lv.patches.size();
+    const unsigned nslab = 2 * ndim;
+    if (which == 1)
+    {
+        for (int axis = 0; axis < ndim; ++axis)
+            if (ex->halo.n_pairs[axis] > 0)
+            {
+                dim3 grid(64, ex->halo.n_pairs[axis]);
+                face_sync_kernel<<<grid, 256, 0, ctx->L.stream>>>(ex->halo.d_pairs[axis]);
+                ctx->L.launches++;
+            }
+    }
+    for (int p = 0; p < P; ++p)
+        for (int axis = 0; axis < ndim; ++axis)
+        {
+            dim3 grid(halo_blocks(lv, lv.patches[p], axis), nslab);
+            const HaloArgs* A = ex->halo.d_args[which][(size_t)p * ndim + axis];
+            if (which == 0)
+                halo_fill_kernel<<<grid, 256, 0, ctx->L.stream>>>(A);
+            else
+                halo_accum_kernel<<<grid, 256, 0, ctx->L.stream>>>(A);
+            ctx->L.launches++;
+        }
+    CK(cudaGetLastError());
+    return IBK_OK;
+}
+
+static int region_args(ibk_ctx* ctx, int which, int patch, int axis, const int* lower, const int* upper, int* off, int* ext)
+{
+    if (int rc = check_patch_axis(ctx, which, patch, axis)) return rc;
+    const LevelState& lv = ctx->lv;
+    const PatchState& ps = lv.patches[patch];
+    for (int d = 0; d < 3; ++d)
+    {
+        if (d < lv.ndim)
+        {
+            off[d] = lower[d] - (ps.lower[d] - lv.gcw[d]);
+            ext[d] = upper[d] - lower[d] + 1;
+            if (off[d] < 0 || ext[d] < 0 || off[d] + ext[d] > ps.n[axis][d]) return fail(ctx, IBK_ERR_INVALID, "region outside the array");
+        }
+        else
+        {
+            off[d] = 0;
+            ext[d] = 1;
+        }
+    }
+    return IBK_OK;
+}
+extern "C" int ibk_halo_pack(ibk_ctx* ctx, int which, int patch, int axis, const int* lower, const int* upper, double* d_buf)
+{
+    NEED_LEVEL();
+    int off[3], ext[3];
+    if (int rc = region_args(ctx, which, patch, axis, lower, upper, off, ext)) return rc;
+    PatchState& ps = ctx->lv.patches[patch];
+    CK(launch_pack(ctx->L, which == 0 ? ps.u[axis] : ps.f[axis], ps.pitch[axis], ps.n[axis][1], off, ext, d_buf, ctx->lv.ndim));
+    return IBK_OK;
+}
+extern "C" int ibk_halo_unpack(ibk_ctx* ctx, int which, int patch, int axis, const int* lower, const int* upper,
+                               const double* d_buf, int mode)
+{
+    NEED_LEVEL();
+    int off[3], ext[3];
+    if (int rc = region_args(ctx, which, patch, axis, lower, upper, off, ext)) return rc;
+    PatchState& ps = ctx->lv.patches[patch];
+    CK(launch_unpack(ctx->L, which == 0 ? ps.u[axis] : ps.f[axis], ps.pitch[axis], ps.n[axis][1], off, ext, d_buf, ctx->lv.ndim,
+                     mode));
+    return IBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// spreadForce / interpolateVelocity
+// ---------------------------------------------------------------------------------------------
+static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (!lv.binned) return fail(ctx, IBK_ERR_STATE, "markers are not binned: call ibk_rebin first");
+    const int kernel = ibk_kernel_from_string(fcn);
+    if (kernel < 0) return fail(ctx, IBK_ERR_UNKNOWN_KERNEL, std::string("unknown kernel function ") + (fcn ? fcn : "(null)"));
+    const int min_ghosts = ibk_get_minimum_ghost_width(fcn);
+    for (int d = 0; d < lv.ndim; ++d)
+        if (lv.gcw[d] < min_ghosts) return fail(ctx, IBK_ERR_GHOST_WIDTH, "insufficient ghost cells for the kernel function");
+    LevelExtra* ex = extra_of(ctx, false);
+    if (!ex) return fail(ctx, IBK_ERR_STATE, "level parameters missing");
+    const int which_ev = op == 1 ? 0 : 1;
+    if (op == 0 && halo)
+        if (int rc = ibk_halo_local(ctx, 0)) return rc;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[which_ev][0], ctx->L.stream));
+    MarkerView mv;
+    mv.X = lv.X;
+    mv.Xraw = nullptr;
+    mv.x_stride = lv.stride;
+    mv.V = op == 0 ? lv.U : lv.F;
+    mv.v_cstride = lv.stride;
+    mv.v_istride = 1;
+    mv.src = nullptr;
+    for (size_t p = 0; p < lv.patches.size(); ++p)
+    {
+        std::string err;
+        cudaError_t e = (op == 0) ? launch_interp(ctx->L, kernel, ex->tp[2 * p + 0], lv.bins, mv, err) :
+                                    launch_spread(ctx->L, kernel, ex->tp[2 * p + 1], lv.bins, mv, err);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, err.empty() ? "tile kernel launch" : err.c_str());
+    }
+    if (ctx->timing)
+    {
+        CK(cudaEventRecord(ctx->ev[which_ev][1], ctx->L.stream));
+        ctx->ev_valid[which_ev] = true;
+    }
+    if (op == 1 && halo)
+        if (int rc = ibk_halo_local(ctx, 1)) return rc;
+    return IBK_OK;
+}
+
+extern "C" int ibk_spread_force(ibk_ctx* ctx, const char* spread_fcn, int accumulate_halo)
+{
+    return level_op(ctx, 1, spread_fcn, accumulate_halo);
+}
+extern "C" int ibk_interpolate_velocity(ibk_ctx* ctx, const char* interp_fcn, int fill_halo)
+{
+    return level_op(ctx, 0, interp_fcn, fill_halo);
+}
+
+extern "C" int ibk_count_touched_dofs(ibk_ctx* ctx, const char* kernel_fcn, long long* touched)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (!lv.binned) return fail(ctx, IBK_ERR_STATE, "markers are not binned: call ibk_rebin first");
+    const int kernel = ibk_kernel_from_string(kernel_fcn);
+    if (kernel < 0 || !touched) return fail(ctx, IBK_ERR_UNKNOWN_KERNEL, "unknown kernel function");
+    LevelExtra* ex = extra_of(ctx, false);
+    // spread a field of ones into scratch copies of f and count the nonzeros
+    DevBuf ones, cnt;
+    CK(ones.reserve(sizeof(double) * (size_t)lv.stride * lv.ndim));
+    CK(cnt.reserve(sizeof(unsigned long long)));
+    CK(launch_fill(ctx->L, ones.as<double>(), (size_t)lv.stride * lv.ndim, 1.0));
+    CK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), ctx->L.stream));
+    MarkerView mv;
+    mv.X = lv.X;
+    mv.Xraw = nullptr;
+    mv.x_stride = lv.stride;
+    mv.V = ones.as<double>();
+    mv.v_cstride = lv.stride;
+    mv.v_istride = 1;
+    mv.src = nullptr;
+    int rc = IBK_OK;
+    for (size_t p = 0; p < lv.patches.size() && rc == IBK_OK; ++p)
+    {
+        const PatchState& ps = lv.patches[p];
+        TileParams tp = ex->tp[2 * p + 1];
+        DevBuf scratch[3];
+        for (int a = 0; a < lv.ndim; ++a)
+        {
+            CK(scratch[a].reserve(sizeof(double) * ps.elems[a]));
+            CK(cudaMemsetAsync(scratch[a].p, 0, sizeof(double) * ps.elems[a], ctx->L.stream));
+            tp.comp[a].ptr = scratch[a].as<double>();
+        }
+        std::string err;
+        cudaError_t e = launch_spread(ctx->L, kernel, tp, lv.bins, mv, err);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "count_touched spread");
+        for (int a = 0; a < lv.ndim && rc == IBK_OK; ++a)
+        {
+            count_nonzero_kernel<<<148 * 8, 256, 0, ctx->L.stream>>>(scratch[a].as<double>(), ps.pitch[a], ps.n[a][0],
+                                                                     (long long)ps.n[a][1] * ps.n[a][2],
+                                                                     cnt.as<unsigned long long>());
+            ctx->L.launches++;
+        }
+        cudaStreamSynchronize(ctx->L.stream);
+        for (int a = 0; a < 3; ++a) scratch[a].release();
+    }
+    unsigned long long h = 0;
+    if (rc == IBK_OK)
+    {
+        CK(cudaMemcpyAsync(&h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->L.stream));
+        CK(cudaStreamSynchronize(ctx->L.stream));
+        *touched = (long long)h;
+    }
+    ones.release();
+    cnt.release();
+    return rc;
+}

@@ -1,0 +1,453 @@
+// ibk_spread.cu -- force spreading (markers -> grid) for sm_100a, deterministic, no
+// floating-point atomics anywhere.
+//
+// Replaces lagrangian_<kernel>_spread{2,3}d (ibtk/src/lagrangian/fortran/
+// lagrangian_interaction3d.f.m4:1344-1475 ib_4, :2384-2582 ib_6, :2703-2805 bspline_3,
+// :2933-3041 bspline_4, :617-730 piecewise_linear; 2D twins in lagrangian_interaction2d.f.m4) and
+// the per-axis loop of LEInteractor (LEInteractor.cpp:3676-3711).  The reference is serial over
+// markers, so it has no write conflicts; here the work is organised so that none can occur:
+//
+//  * OWNER-COMPUTES TILES.  One CTA owns a 16^ndim block of grid points of every component and is
+//    the only writer of those points: it accumulates in shared memory and finishes with one
+//    coalesced `f += tile` pass (the contract of LDataManager::spread, LDataManager.cpp:662-663).
+//    The CTA visits every marker whose stencil can reach its points: the markers binned in the
+//    (16 + 2M)^ndim cells around the tile, i.e. NBR^ndim bricks of 4^ndim cells, each a contiguous
+//    segment of the sorted marker storage.  Stencils are clipped to the tile.
+//  * BRICK COLOURING.  Inside the CTA one warp takes one brick at a time and walks its markers in
+//    storage order; the 32 lanes cover the stencil points.  Two bricks whose index differs by a
+//    multiple of NC in every dimension have disjoint footprints (4*NC >= 4 + 2M), so the CTA runs
+//    NC^ndim phases separated by __syncthreads and inside a phase no two warps touch the same
+//    shared-memory word.  The summation order at every grid point is therefore fixed by the
+//    sorted marker order alone: results are bit-reproducible run to run.
+//  * Stencil weights are evaluated lane-per-(marker, dimension) for a batch of 8 markers and
+//    parked in a small per-warp scratch, so the sqrt/div work is not repeated by the 32 lanes.
+//
+// Contributions to points farther than M cells from the marker's binning cell (possible only if
+// binning cell and stencil origin disagree by a rounding) are excluded here by the margin mask and
+// added by spread_fixup_kernel in a fixed order.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "ibk_engine.h"
+
+namespace ibk
+{
+constexpr int SPREAD_THREADS = 256;
+constexpr int SPREAD_WARPS = SPREAD_THREADS / 32;
+constexpr int SPREAD_BATCH = 8;
+constexpr int SPREAD_MAXC = 3; // components accumulated per launch
+
+struct SpreadArgs
+{
+    const int* brick_start;
+    const uint64_t* keys; // sorted keys (cell-in-brick bits)
+    int tie_bits;
+    const double* X;
+    const double* Xraw;
+    long long x_stride;
+    const double* V;
+    long long v_cstride, v_istride;
+    const uint32_t* src;
+    int comp0; // first component handled by this launch
+    int ncomp; // number of components handled by this launch (<= SPREAD_MAXC)
+    // exceptions (stencil beyond the margin box): appended here, processed by spread_fixup_kernel
+    int* exc_count;
+    int* exc_list;
+    int exc_capacity;
+};
+
+template <int NDIM>
+__device__ __forceinline__ int acc_index(int x, int y, int z)
+{
+    // 16-double rows; XOR-swizzle the 4-double group with the row so that the 4x4 (x,y) footprint of
+    // a stencil plane hits 16 distinct 8-byte banks.
+    const int xs = x ^ ((y & 3) << 2);
+    if constexpr (NDIM == 3)
+        return ((z << 4) + y) * 16 + xs;
+    else
+        return y * 16 + xs;
+}
+
+template <int NDIM, int K>
+__global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __grid_constant__ TileParams tp, SpreadArgs args)
+{
+    constexpr int W = KTraits<K>::W;
+    constexpr int M = KTraits<K>::M;
+    constexpr int NBR = TILE_BRICKS + (2 * M + BRICK - 1) / BRICK; // bricks per dimension around the tile
+    constexpr int NC = (BRICK + 2 * M + BRICK - 1) / BRICK;        // colours per dimension
+    constexpr int NPTS = (NDIM == 3) ? W * W * W : W * W;
+    constexpr int NSLOT = (NPTS + 31) / 32;
+    constexpr int TILE_PTS = (NDIM == 3) ? TILE * TILE * TILE : TILE * TILE;
+    constexpr int NBRICKS = (NDIM == 3) ? NBR * NBR * NBR : NBR * NBR;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* acc = reinterpret_cast<double*>(smem_raw);                                   // [ncomp][TILE_PTS]
+    double* wgt_all = acc + (size_t)args.ncomp * TILE_PTS;                               // [warp][BATCH][NDIM][2][W]
+    double* fs_all = wgt_all + SPREAD_WARPS * SPREAD_BATCH * NDIM * 2 * W;               // [warp][BATCH][MAXC]
+    int* lom_all = reinterpret_cast<int*>(fs_all + SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC); // [warp][BATCH][NDIM][2]
+    int* brng = lom_all + SPREAD_WARPS * SPREAD_BATCH * NDIM * 2;                        // [NBRICKS][2]
+    __shared__ int any_markers;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* wgt = wgt_all + warp * (SPREAD_BATCH * NDIM * 2 * W);
+    double* fs = fs_all + warp * (SPREAD_BATCH * SPREAD_MAXC);
+    int* lom = lom_all + warp * (SPREAD_BATCH * NDIM * 2);
+
+    // which output tile
+    int ot[3];
+    {
+        int r = blockIdx.x;
+        ot[0] = tp.ot_lo[0] + r % tp.ot_n[0];
+        r /= tp.ot_n[0];
+        ot[1] = tp.ot_lo[1] + r % tp.ot_n[1];
+        ot[2] = (NDIM == 3) ? tp.ot_lo[2] + r / tp.ot_n[1] : 0;
+    }
+    int tlo[3]; // pp coordinate of the tile's first point
+#pragma unroll
+    for (int d = 0; d < 3; ++d) tlo[d] = TILE * ot[d] + M;
+
+    // brick ranges of the neighbourhood + emptiness test
+    if (threadIdx.x == 0) any_markers = 0;
+    __syncthreads();
+    for (int q = threadIdx.x; q < NBRICKS; q += SPREAD_THREADS)
+    {
+        const int lx = q % NBR, ly = (q / NBR) % NBR, lz = (NDIM == 3) ? q / (NBR * NBR) : 0;
+        const int bx = TILE_BRICKS * ot[0] + lx, by = TILE_BRICKS * ot[1] + ly, bz = (NDIM == 3) ? TILE_BRICKS * ot[2] + lz : 0;
+        int s = 0, e = 0;
+        if (bx < tp.nb[0] && by < tp.nb[1] && bz < tp.nb[2])
+        {
+            const int id = tp.brick_base + ((NDIM == 3) ? brick_id_3d(bx, by, bz, tp.nt) : brick_id_2d(bx, by, tp.nt));
+            s = args.brick_start[id];
+            e = args.brick_start[id + 1];
+        }
+        brng[2 * q] = s;
+        brng[2 * q + 1] = e;
+        if (e > s) any_markers = 1;
+    }
+    __syncthreads();
+    if (!any_markers) return;
+
+    for (int q = threadIdx.x; q < args.ncomp * TILE_PTS; q += SPREAD_THREADS) acc[q] = 0.0;
+
+    // per-lane stencil point(s)
+    int pix[NSLOT], piy[NSLOT], piz[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s)
+    {
+        const int q = lane + 32 * s;
+        pix[s] = q % W;
+        piy[s] = (q / W) % W;
+        piz[s] = (NDIM == 3) ? q / (W * W) : 0;
+    }
+    __syncthreads();
+
+    constexpr int NCOL = (NDIM == 3) ? NC * NC * NC : NC * NC;
+    for (int col = 0; col < NCOL; ++col)
+    {
+        const int c0 = col % NC, c1 = (col / NC) % NC, c2 = (NDIM == 3) ? col / (NC * NC) : 0;
+        const int n0 = (NBR - c0 + NC - 1) / NC, n1 = (NBR - c1 + NC - 1) / NC, n2 = (NDIM == 3) ? (NBR - c2 + NC - 1) / NC : 1;
+        const int nbr_col = n0 * n1 * n2;
+        for (int bi = warp; bi < nbr_col; bi += SPREAD_WARPS)
+        {
+            const int lx = c0 + NC * (bi % n0), ly = c1 + NC * ((bi / n0) % n1), lz = (NDIM == 3) ? c2 + NC * (bi / (n0 * n1)) : 0;
+            const int q = (lz * NBR + ly) * NBR + lx;
+            const int bs = brng[2 * q], be = brng[2 * q + 1];
+            if (bs >= be) continue;
+            const int gb[3] = { TILE_BRICKS * ot[0] + lx, TILE_BRICKS * ot[1] + ly, TILE_BRICKS * ot[2] + lz };
+            for (int batch = bs; batch < be; batch += SPREAD_BATCH)
+            {
+                const int nb = min(SPREAD_BATCH, be - batch);
+                // ---- phase A: lane (m, d) evaluates the stencil(s) of marker m along dimension d ----
+                {
+                    const int m = lane / NDIM, d = lane % NDIM;
+                    if (m < nb)
+                    {
+                        const int i = batch + m;
+                        const double xs = args.X[d * args.x_stride + i];
+                        const double xr = args.Xraw ? args.Xraw[d * args.x_stride + i] : xs;
+                        const int cin = (int)((args.keys[i] >> (args.tie_bits + 2 * d)) & 3ull);
+                        const int cc = BRICK * gb[d] + cin; // marker's binning cell (pp coordinates)
+                        bool beyond = false;
+                        for (int v = 0; v < tp.nvar[d]; ++v)
+                        {
+                            double w[W];
+                            int l;
+                            stencil_1d<K>(xs, xr, tp.xl[d][v], tp.dx[d], l, w);
+                            const int lo_pp = l + tp.G;
+                            unsigned mask = 0;
+#pragma unroll
+                            for (int j = 0; j < W; ++j)
+                            {
+                                const int pp = lo_pp + j;
+                                const bool in_margin = (pp >= cc - M) && (pp <= cc + M);
+                                beyond = beyond || !in_margin;
+                                if (in_margin && pp >= tlo[d] && pp < tlo[d] + TILE) mask |= (1u << j);
+                                wgt[((m * NDIM + d) * 2 + v) * W + j] = w[j];
+                            }
+                            lom[(m * NDIM + d) * 2 + v] = ((lo_pp - tlo[d]) & 0xFFFF) | (mask << 16);
+                        }
+                        if (beyond && args.exc_list)
+                        {
+                            // record once: by the CTA whose tile holds the marker's cell, dimension 0 lane
+                            // (exceptions are re-derived in full by the fix-up kernel)
+                            bool mine = true;
+#pragma unroll
+                            for (int dd = 0; dd < NDIM; ++dd)
+                            {
+                                const int cind = (int)((args.keys[i] >> (args.tie_bits + 2 * dd)) & 3ull);
+                                const int ccd = BRICK * gb[dd] + cind;
+                                mine = mine && ccd >= tlo[dd] && ccd < tlo[dd] + TILE;
+                            }
+                            if (mine)
+                            {
+                                const int slot = atomicAdd(args.exc_count, 1);
+                                if (slot < args.exc_capacity) args.exc_list[slot] = i;
+                            }
+                        }
+                        if (d == 0)
+                        {
+                            const long long row = args.src ? (long long)args.src[i] : (long long)i;
+                            for (int a = 0; a < args.ncomp; ++a)
+                                fs[m * SPREAD_MAXC + a] =
+                                    args.V[tp.comp[args.comp0 + a].vcol * args.v_cstride + row * args.v_istride] * tp.inv_vol;
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- phase B: markers one after another, lanes over the stencil points ----
+                for (int m = 0; m < nb; ++m)
+                {
+                    for (int a = 0; a < args.ncomp; ++a)
+                    {
+                        const CompGeom& cg = tp.comp[args.comp0 + a];
+                        const int v0 = cg.var[0], v1 = cg.var[1], v2 = (NDIM == 3) ? cg.var[2] : 0;
+                        const int L0 = lom[(m * NDIM + 0) * 2 + v0];
+                        const int L1 = lom[(m * NDIM + 1) * 2 + v1];
+                        const int L2 = (NDIM == 3) ? lom[(m * NDIM + (NDIM - 1)) * 2 + v2] : 0;
+                        // whole marker clipped away along some dimension?  (warp-uniform)
+                        if ((L0 >> 16) == 0 || (L1 >> 16) == 0 || ((NDIM == 3) && (L2 >> 16) == 0)) continue;
+                        const double f = fs[m * SPREAD_MAXC + a];
+                        const double* w0 = &wgt[((m * NDIM + 0) * 2 + v0) * W];
+                        const double* w1 = &wgt[((m * NDIM + 1) * 2 + v1) * W];
+                        const double* w2 = &wgt[((m * NDIM + (NDIM - 1)) * 2 + v2) * W];
+                        const int x0 = (int)(short)(L0 & 0xFFFF), y0 = (int)(short)(L1 & 0xFFFF),
+                                  z0 = (NDIM == 3) ? (int)(short)(L2 & 0xFFFF) : 0;
+                        double* acc_a = acc + a * TILE_PTS;
+#pragma unroll
+                        for (int s = 0; s < NSLOT; ++s)
+                        {
+                            if (NPTS % 32 != 0 && lane + 32 * s >= NPTS) continue;
+                            bool ok = ((L0 >> (16 + pix[s])) & 1) && ((L1 >> (16 + piy[s])) & 1);
+                            if (NDIM == 3) ok = ok && ((L2 >> (16 + piz[s])) & 1);
+                            if (ok)
+                            {
+                                double wv = w0[pix[s]] * w1[piy[s]];
+                                if (NDIM == 3) wv *= w2[piz[s]];
+                                const int idx = acc_index<NDIM>(x0 + pix[s], y0 + piy[s], z0 + piz[s]);
+                                acc_a[idx] += wv * f;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- write-out: f += tile (coalesced along x), dropping points outside the array ----
+    for (int a = 0; a < args.ncomp; ++a)
+    {
+        const CompGeom& cg = tp.comp[args.comp0 + a];
+        const double* acc_a = acc + a * TILE_PTS;
+        for (int q = threadIdx.x; q < TILE_PTS; q += SPREAD_THREADS)
+        {
+            const int x = q & 15, y = (q >> 4) & 15, z = (NDIM == 3) ? q >> 8 : 0;
+            const int gi = tlo[0] + x - cg.pp0[0], gj = tlo[1] + y - cg.pp0[1], gk = (NDIM == 3) ? tlo[2] + z - cg.pp0[2] : 0;
+            if (gi >= 0 && gi < cg.n[0] && gj >= 0 && gj < cg.n[1] && gk >= 0 && gk < cg.n[2])
+            {
+                const double v = acc_a[acc_index<NDIM>(x, y, z)];
+                if (v != 0.0)
+                {
+                    double* p = cg.ptr + ((long long)gk * cg.n[1] + gj) * cg.pitch + gi;
+                    *p += v;
+                }
+            }
+        }
+    }
+}
+
+// Fix-up for the (practically never occurring) markers whose stencil reaches beyond M cells from
+// their binning cell: one thread, sorted-position order, only the points OUTSIDE the margin box
+// (the tile kernel did the ones inside).  Deterministic by construction.
+template <int NDIM, int K>
+__global__ void spread_fixup_kernel(const __grid_constant__ TileParams tp, SpreadArgs args)
+{
+    constexpr int W = KTraits<K>::W;
+    constexpr int M = KTraits<K>::M;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n = *args.exc_count;
+    if (n <= 0) return;
+    if (n > args.exc_capacity) n = args.exc_capacity;
+    // insertion sort of the exception list by sorted position (tiny)
+    for (int a = 1; a < n; ++a)
+    {
+        const int v = args.exc_list[a];
+        int b = a - 1;
+        while (b >= 0 && args.exc_list[b] > v)
+        {
+            args.exc_list[b + 1] = args.exc_list[b];
+            --b;
+        }
+        args.exc_list[b + 1] = v;
+    }
+    for (int e = 0; e < n; ++e)
+    {
+        const int i = args.exc_list[e];
+        if (e > 0 && args.exc_list[e - 1] == i) continue;
+        const uint64_t key = args.keys[i];
+        const long long brick_global = (long long)(key >> (args.tie_bits + 2 * NDIM));
+        const int brick = (int)(brick_global - tp.brick_base);
+        // decode hierarchical brick id -> brick coordinates
+        int gb[3] = { 0, 0, 0 };
+        if (NDIM == 3)
+        {
+            const int tile = brick >> 6;
+            const int tx = tile % tp.nt[0], ty = (tile / tp.nt[0]) % tp.nt[1], tz = tile / (tp.nt[0] * tp.nt[1]);
+            gb[0] = 4 * tx + (brick & 3);
+            gb[1] = 4 * ty + ((brick >> 2) & 3);
+            gb[2] = 4 * tz + ((brick >> 4) & 3);
+        }
+        else
+        {
+            const int tile = brick >> 4;
+            const int tx = tile % tp.nt[0], ty = tile / tp.nt[0];
+            gb[0] = 4 * tx + (brick & 3);
+            gb[1] = 4 * ty + ((brick >> 2) & 3);
+        }
+        const long long row = args.src ? (long long)args.src[i] : (long long)i;
+        for (int a = 0; a < args.ncomp; ++a)
+        {
+            const CompGeom& cg = tp.comp[args.comp0 + a];
+            double w[3][W];
+            int lo[3] = { 0, 0, 0 }, cc[3] = { 0, 0, 0 };
+            for (int d = 0; d < NDIM; ++d)
+            {
+                const double xs = args.X[d * args.x_stride + i];
+                const double xr = args.Xraw ? args.Xraw[d * args.x_stride + i] : xs;
+                int l;
+                stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w[d]);
+                lo[d] = l + tp.G;
+                cc[d] = BRICK * gb[d] + (int)((key >> (args.tie_bits + 2 * d)) & 3ull);
+            }
+            const double f = args.V[cg.vcol * args.v_cstride + row * args.v_istride] * tp.inv_vol;
+            const int KW = (NDIM == 3) ? W : 1;
+            for (int k = 0; k < KW; ++k)
+                for (int j = 0; j < W; ++j)
+                    for (int ii = 0; ii < W; ++ii)
+                    {
+                        const int px = lo[0] + ii, py = lo[1] + j, pz = (NDIM == 3) ? lo[2] + k : 0;
+                        bool inside = (px >= cc[0] - M && px <= cc[0] + M) && (py >= cc[1] - M && py <= cc[1] + M);
+                        if (NDIM == 3) inside = inside && (pz >= cc[2] - M && pz <= cc[2] + M);
+                        if (inside) continue; // done by the tile kernel
+                        const int gi = px - cg.pp0[0], gj = py - cg.pp0[1], gk = (NDIM == 3) ? pz - cg.pp0[2] : 0;
+                        if (gi < 0 || gi >= cg.n[0] || gj < 0 || gj >= cg.n[1] || gk < 0 || gk >= cg.n[2]) continue;
+                        double wv = w[0][ii] * w[1][j];
+                        if (NDIM == 3) wv *= w[2][k];
+                        cg.ptr[((long long)gk * cg.n[1] + gj) * cg.pitch + gi] += wv * f;
+                    }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int* g_exc_buf = nullptr; // [1 + capacity] per process (device); tiny
+constexpr int EXC_CAPACITY = 4096;
+
+template <int NDIM, int K>
+static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err)
+{
+    constexpr int W = KTraits<K>::W;
+    constexpr int M = KTraits<K>::M;
+    constexpr int NBR = TILE_BRICKS + (2 * M + BRICK - 1) / BRICK;
+    constexpr int TILE_PTS = (NDIM == 3) ? TILE * TILE * TILE : TILE * TILE;
+    constexpr int NBRICKS = (NDIM == 3) ? NBR * NBR * NBR : NBR * NBR;
+    cudaError_t e;
+    if (!g_exc_buf)
+    {
+        if ((e = cudaMalloc(&g_exc_buf, sizeof(int) * (1 + EXC_CAPACITY))) != cudaSuccess) return e;
+    }
+    if ((e = cudaMemsetAsync(g_exc_buf, 0, sizeof(int), L.stream)) != cudaSuccess) return e;
+    SpreadArgs args;
+    args.brick_start = bins.brick_start;
+    args.keys = bins.keys[bins.sorted_in];
+    args.tie_bits = bins.tie_bits;
+    args.X = mv.X;
+    args.Xraw = mv.Xraw;
+    args.x_stride = mv.x_stride;
+    args.V = mv.V;
+    args.v_cstride = mv.v_cstride;
+    args.v_istride = mv.v_istride;
+    args.src = mv.src;
+    args.exc_count = g_exc_buf;
+    args.exc_list = g_exc_buf + 1;
+    args.exc_capacity = EXC_CAPACITY;
+    const int ntiles = tp.ot_n[0] * tp.ot_n[1] * tp.ot_n[2];
+    if (ntiles <= 0) return cudaSuccess;
+    auto kfn = spread_tile_kernel<NDIM, K>;
+    auto ffn = spread_fixup_kernel<NDIM, K>;
+    for (int c0 = 0; c0 < tp.ncomp; c0 += SPREAD_MAXC)
+    {
+        args.comp0 = c0;
+        args.ncomp = (tp.ncomp - c0 < SPREAD_MAXC) ? tp.ncomp - c0 : SPREAD_MAXC;
+        const size_t smem = sizeof(double) * ((size_t)args.ncomp * TILE_PTS + SPREAD_WARPS * SPREAD_BATCH * NDIM * 2 * W +
+                                              SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC) +
+                            sizeof(int) * (SPREAD_WARPS * SPREAD_BATCH * NDIM * 2 + 2 * NBRICKS);
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+        {
+            err = "cudaFuncSetAttribute(spread) failed";
+            return e;
+        }
+        kfn<<<ntiles, SPREAD_THREADS, smem, L.stream>>>(tp, args);
+        ffn<<<1, 32, 0, L.stream>>>(tp, args);
+        L.launches += 2;
+        if (c0 + SPREAD_MAXC < tp.ncomp)
+            if ((e = cudaMemsetAsync(g_exc_buf, 0, sizeof(int), L.stream)) != cudaSuccess) return e;
+    }
+    return cudaGetLastError();
+}
+
+template <int NDIM>
+static cudaError_t launch_spread_k(Launcher& L, int kernel, const TileParams& tp, const Bins& bins, const MarkerView& mv,
+                                   std::string& err)
+{
+    switch (kernel)
+    {
+    case IBK_PIECEWISE_LINEAR:
+        return launch_spread_t<NDIM, IBK_PIECEWISE_LINEAR>(L, tp, bins, mv, err);
+    case IBK_IB_4:
+        return launch_spread_t<NDIM, IBK_IB_4>(L, tp, bins, mv, err);
+    case IBK_IB_6:
+        return launch_spread_t<NDIM, IBK_IB_6>(L, tp, bins, mv, err);
+    case IBK_BSPLINE_3:
+        return launch_spread_t<NDIM, IBK_BSPLINE_3>(L, tp, bins, mv, err);
+    case IBK_BSPLINE_4:
+        return launch_spread_t<NDIM, IBK_BSPLINE_4>(L, tp, bins, mv, err);
+    default:
+        err = "unknown kernel";
+        return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_spread(Launcher& L, int kernel, const TileParams& tp, const Bins& bins, const MarkerView& mv,
+                          std::string& err)
+{
+    if (tp.ndim == 3) return launch_spread_k<3>(L, kernel, tp, bins, mv, err);
+    return launch_spread_k<2>(L, kernel, tp, bins, mv, err);
+}
+
+} // namespace ibk

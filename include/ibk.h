@@ -1,0 +1,327 @@
+/*
+ * ibk.h -- C ABI of the B200-native Lagrangian-Eulerian interaction library (libibk.so).
+ *
+ * This is the drop-in boundary for IBAMR's IB spread / interpolate hot path.  Every entry
+ * point names the reference interface it replaces (file:line under the IBAMR tree); the
+ * reference-side bindings a maintainer would add are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns int: IBK_OK (0) or a negative ibk_status; nothing throws across
+ *     the boundary; ibk_last_error(ctx) holds the message of the last failure (the reference
+ *     aborts through TBOX_ERROR instead, e.g. LEInteractor.cpp:2425-2429, 4491-4498);
+ *   - an ibk_ctx belongs to one (process, CUDA device) pair and is not thread-safe, like the
+ *     reference (single-threaded MPI ranks);
+ *   - all device work is enqueued on the ctx stream (ibk_ctx_set_stream); *_host entry points
+ *     copy in/out on that stream and return after the results are in the caller's buffers;
+ *   - "h_" pointers are host memory (borrowed for the call), "d_" pointers are device memory;
+ *   - grid arrays at the *_host / raw seams use the reference layout: Fortran order,
+ *     u(ilower0-g0:iupper0+g0, ilower1-g1:iupper1+g1[, ilower2-g2:iupper2+g2], 0:depth-1)
+ *     (SAMRAI ArrayData), marker arrays are AoS [marker][depth] (LData / PETSc block Vec,
+ *     ibtk/include/ibtk/LData.h:351-367);
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     IBK_ERR_CUDA.
+ */
+#ifndef IBK_H
+#define IBK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define IBK_MAX_DIM 3
+#define IBK_MAX_COMP 8
+
+typedef struct ibk_ctx ibk_ctx;
+
+typedef enum ibk_status
+{
+    IBK_OK = 0,
+    IBK_ERR_INVALID = -1,        /* bad argument                                               */
+    IBK_ERR_CUDA = -2,           /* CUDA runtime / driver failure (incl. "no device")          */
+    IBK_ERR_UNKNOWN_KERNEL = -3, /* LEInteractor.cpp:2100-2104                                  */
+    IBK_ERR_GHOST_WIDTH = -4,    /* "insufficient ghost cells", LEInteractor.cpp:4488-4498      */
+    IBK_ERR_DEPTH = -5,          /* "side-centered ... requires vector-valued data", :2425-2429 */
+    IBK_ERR_STATE = -6,          /* call order violated (e.g. spread before rebin)              */
+    IBK_ERR_ESCAPED = -7         /* "IB point has escaped ...", LDataManager.cpp:1410-1416      */
+} ibk_status;
+
+/* The five in-scope delta kernels (names as LEInteractor::string_to_kernel accepts them,
+ * LEInteractor.cpp:1923-2016). */
+typedef enum ibk_kernel
+{
+    IBK_PIECEWISE_LINEAR = 0,
+    IBK_IB_4 = 1,
+    IBK_IB_6 = 2,
+    IBK_BSPLINE_3 = 3,
+    IBK_BSPLINE_4 = 4
+} ibk_kernel;
+
+/* ---- LEInteractor static queries (ibtk/include/ibtk/LEInteractor.h:99-117) ------------------ */
+/* string_to_kernel: returns the ibk_kernel value or IBK_ERR_UNKNOWN_KERNEL. */
+int ibk_kernel_from_string(const char* kernel_fcn);
+/* LEInteractor::isKnownKernel restricted to the in-scope kernels (LEInteractor.cpp:2038-2050). */
+int ibk_is_known_kernel(const char* kernel_fcn);
+/* LEInteractor::getStencilSize (LEInteractor.cpp:2052-2108). */
+int ibk_get_stencil_size(const char* kernel_fcn);
+/* LEInteractor::getMinimumGhostWidth (LEInteractor.cpp:2110-2114). */
+int ibk_get_minimum_ghost_width(const char* kernel_fcn);
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int ibk_ctx_create(int device, ibk_ctx** ctx);
+int ibk_ctx_destroy(ibk_ctx* ctx);
+const char* ibk_last_error(const ibk_ctx* ctx);
+int ibk_ctx_set_stream(ibk_ctx* ctx, void* cuda_stream); /* cudaStream_t */
+int ibk_ctx_synchronize(ibk_ctx* ctx);
+/* Number of kernels this library launched on the ctx since creation (bench.py's gpu_launches). */
+long long ibk_ctx_launch_count(const ibk_ctx* ctx);
+/* Device-time (ms) of the last spread / interp / rebin kernel groups, measured with CUDA events
+ * on the ctx stream (valid after ibk_ctx_synchronize). which: 0 spread, 1 interp, 2 rebin. */
+int ibk_ctx_enable_timing(ibk_ctx* ctx, int enable);
+int ibk_ctx_last_ms(ibk_ctx* ctx, int which, float* ms);
+
+/* ---- seam B4: the raw funnel ------------------------------------------------------------------
+ * Replaces the Fortran routines lagrangian_<kernel>_{interp,spread}{2,3}d_
+ * (ibtk/src/lagrangian/fortran/lagrangian_interaction3d.f.m4:1203-1209, 1344-1350; C++
+ * declarations LEInteractor.cpp:237-1518) as called from LEInteractor's private
+ * interpolate/spread (LEInteractor.cpp:4470-5230, 5232-6006).  One call handles one array
+ * (one SideData axis, or a CellData of `depth` components). */
+typedef struct ibk_array_desc
+{
+    int ndim;                      /* 2 or 3                                                     */
+    int depth;                     /* components stored one after another (Fortran last index)   */
+    double dx[IBK_MAX_DIM];
+    double x_lower[IBK_MAX_DIM];   /* already shifted by -dx/2 on the side axis (LEInteractor.cpp:2464) */
+    double x_upper[IBK_MAX_DIM];   /* unused by the in-scope kernels, kept for signature parity  */
+    int ilower[IBK_MAX_DIM];       /* data box (toSideBox'ed for SideData)                       */
+    int iupper[IBK_MAX_DIM];
+    int nugc[IBK_MAX_DIM];         /* ghost width of the array                                   */
+} ibk_array_desc;
+
+/* V(d, indices[l]) = sum_stencil w * u(..., d); markers not listed are left untouched. */
+int ibk_raw_interp(ibk_ctx* ctx,
+                   int kernel,
+                   const ibk_array_desc* desc,
+                   const double* d_u,
+                   const int* d_indices,
+                   const double* d_Xshift, /* [nindices][ndim] or NULL for zeros */
+                   int nindices,
+                   const double* d_X,      /* AoS [*][ndim] */
+                   int n_markers,          /* extent of X / V (max index + 1) */
+                   double* d_V);           /* AoS [*][depth] */
+/* u(..., d) += w * V(d, indices[l]) / prod(dx), deterministic (no floating-point atomics). */
+int ibk_raw_spread(ibk_ctx* ctx,
+                   int kernel,
+                   const ibk_array_desc* desc,
+                   const int* d_indices,
+                   const double* d_Xshift,
+                   int nindices,
+                   const double* d_X,
+                   int n_markers,
+                   const double* d_V,
+                   double* d_u);
+/* Same with host buffers (H2D/D2H inside): the signature a Fortran-level shim would bind. */
+int ibk_raw_interp_host(ibk_ctx* ctx,
+                        int kernel,
+                        const ibk_array_desc* desc,
+                        const double* h_u,
+                        const int* h_indices,
+                        const double* h_Xshift,
+                        int nindices,
+                        const double* h_X,
+                        int n_markers,
+                        double* h_V);
+int ibk_raw_spread_host(ibk_ctx* ctx,
+                        int kernel,
+                        const ibk_array_desc* desc,
+                        const int* h_indices,
+                        const double* h_Xshift,
+                        int nindices,
+                        const double* h_X,
+                        int n_markers,
+                        const double* h_V,
+                        double* h_u);
+
+/* ---- seam B3: patch-level LEInteractor calls --------------------------------------------------
+ * What LEInteractor reads from SAMRAI's Patch / CartesianPatchGeometry / SideData. */
+typedef struct ibk_patch_desc
+{
+    int ndim;
+    int lower[IBK_MAX_DIM]; /* patch box (cell indices, inclusive)                               */
+    int upper[IBK_MAX_DIM];
+    int gcw[IBK_MAX_DIM];   /* ghost cell width of the Eulerian data                             */
+    double x_lower[IBK_MAX_DIM];
+    double x_upper[IBK_MAX_DIM];
+    double dx[IBK_MAX_DIM];
+    int touches_physical_bdry; /* any getTouchesRegularBoundary() (LEInteractor.cpp:5253-5258)   */
+} ibk_patch_desc;
+
+/* Position-only SideData interpolate:
+ *   LEInteractor::interpolate(double* Q, int Q_size, int Q_depth, const double* X, int X_size,
+ *                             int X_depth, Pointer<SideData> q, Pointer<Patch>, const Box& box,
+ *                             const std::string& fcn)     LEInteractor.h:566-575, .cpp:3045-3127
+ * h_q[axis] is SideData::getPointer(axis).  Only markers whose cell (getCellIndex) lies in
+ * `box` are interpolated; the others keep their Q. */
+int ibk_side_interpolate_host(ibk_ctx* ctx,
+                              const char* interp_fcn,
+                              const ibk_patch_desc* patch,
+                              const double* const* h_q,
+                              int q_depth,
+                              const int* box_lower,
+                              const int* box_upper,
+                              const double* h_X,
+                              int X_size,
+                              int X_depth,
+                              double* h_Q,
+                              int Q_size,
+                              int Q_depth);
+/* Position-only SideData spread (LEInteractor.h:1132-1141, .cpp:4188-4263): q += S[Q]. */
+int ibk_side_spread_host(ibk_ctx* ctx,
+                         const char* spread_fcn,
+                         const ibk_patch_desc* patch,
+                         double* const* h_q,
+                         int q_depth,
+                         const int* box_lower,
+                         const int* box_upper,
+                         const double* h_X,
+                         int X_size,
+                         int X_depth,
+                         const double* h_Q,
+                         int Q_size,
+                         int Q_depth);
+/* Position-only CellData forms (LEInteractor.cpp:2805-2863, 3951-4009); q has q_depth comps. */
+int ibk_cell_interpolate_host(ibk_ctx* ctx,
+                              const char* interp_fcn,
+                              const ibk_patch_desc* patch,
+                              const double* h_q,
+                              int q_depth,
+                              const int* box_lower,
+                              const int* box_upper,
+                              const double* h_X,
+                              int X_size,
+                              int X_depth,
+                              double* h_Q,
+                              int Q_size,
+                              int Q_depth);
+int ibk_cell_spread_host(ibk_ctx* ctx,
+                         const char* spread_fcn,
+                         const ibk_patch_desc* patch,
+                         double* h_q,
+                         int q_depth,
+                         const int* box_lower,
+                         const int* box_upper,
+                         const double* h_X,
+                         int X_size,
+                         int X_depth,
+                         const double* h_Q,
+                         int Q_size,
+                         int Q_depth);
+/* Index-set SideData forms (LEInteractor.h:184-192, 704-712; .cpp:2402-2489, 3627-3714): the
+ * caller passes the flat lists LIndexSetData caches (local PETSc indices + periodic shifts). */
+int ibk_side_interpolate_indexed_host(ibk_ctx* ctx,
+                                      const char* interp_fcn,
+                                      const ibk_patch_desc* patch,
+                                      const double* const* h_q,
+                                      const int* h_local_indices,
+                                      const double* h_periodic_shifts,
+                                      int n_indices,
+                                      const double* h_X,
+                                      int n_markers,
+                                      double* h_Q);
+int ibk_side_spread_indexed_host(ibk_ctx* ctx,
+                                 const char* spread_fcn,
+                                 const ibk_patch_desc* patch,
+                                 double* const* h_q,
+                                 const int* h_local_indices,
+                                 const double* h_periodic_shifts,
+                                 int n_indices,
+                                 const double* h_X,
+                                 int n_markers,
+                                 const double* h_Q);
+
+/* ---- seams B1/B2: device-resident level (LDataManager + LData + LIndexSetData roles) --------- */
+typedef struct ibk_level_desc
+{
+    int ndim;
+    int n_patches;                      /* patches owned by THIS process on this level           */
+    int domain_lower[IBK_MAX_DIM];      /* level index space of the physical domain              */
+    int domain_upper[IBK_MAX_DIM];
+    double x_lower[IBK_MAX_DIM];        /* physical domain (CartesianGridGeometry)               */
+    double x_upper[IBK_MAX_DIM];
+    int periodic[IBK_MAX_DIM];          /* periodic_shift != 0                                   */
+    int gcw[IBK_MAX_DIM];               /* ghost width of u / f ("ib_ghosts",
+                                           src/IB/IBHierarchyIntegrator.cpp:297-303)             */
+    const int* patch_lower;             /* [n_patches][ndim]                                     */
+    const int* patch_upper;             /* [n_patches][ndim]                                     */
+} ibk_level_desc;
+
+/* Registers the level and allocates device-resident side-centred u and f (all patches, with
+ * ghosts; device layout is pitched).  Replaces the SAMRAI patch data the
+ * integrator allocates for d_u_idx / d_f_idx. */
+int ibk_level_create(ibk_ctx* ctx, const ibk_level_desc* desc);
+int ibk_level_destroy(ibk_ctx* ctx);
+
+/* Grid data movement (SideData::getPointer(axis) layout on the host side).  which: 0 = u, 1 = f. */
+int ibk_grid_upload(ibk_ctx* ctx, int which, int patch, int axis, const double* h_data);
+int ibk_grid_download(ibk_ctx* ctx, int which, int patch, int axis, double* h_data);
+int ibk_grid_fill(ibk_ctx* ctx, int which, double value); /* HierarchyDataOpsReal::setToScalar */
+
+/* LData role: marker columns, AoS on the host side, SoA fp64 on the device.
+ * ibk_markers_set_positions replaces LData("X") setup (LDataManager.cpp:2187-2197) and resets
+ * the Lagrangian numbering to 0..n-1. */
+int ibk_markers_set_positions(ibk_ctx* ctx, const double* h_X, int n_markers);
+/* which: 0 = X, 1 = U, 2 = F; AoS [n][ndim] in LAGRANGIAN index order. */
+int ibk_markers_upload(ibk_ctx* ctx, int which, const double* h_data);
+int ibk_markers_download(ibk_ctx* ctx, int which, double* h_data);
+int ibk_markers_count(const ibk_ctx* ctx);
+
+/* LDataManager::beginDataRedistribution + endDataRedistribution (LDataManager.cpp:1348-1959):
+ * wrap/clamp X into the domain, cell = getCellIndex(X, grid_geom, ratio), owner patch, stable
+ * device radix sort by (patch, brick, cell) with the Lagrangian index as tie-break, permute all
+ * marker columns.  error_if_points_leave_domain follows IBMethod's flag (IBMethod.cpp:2060). */
+int ibk_rebin(ibk_ctx* ctx, int error_if_points_leave_domain);
+
+/* Binning products for parity checks (LIndexSetData role), in LAGRANGIAN index order:
+ * cells [n][ndim] (level cell index), owner [n] (local patch number or -1). */
+int ibk_bin_get_cells(ibk_ctx* ctx, int* h_cells, int* h_owner);
+/* Sorted order: h_lag_idx[i] = Lagrangian index of the marker stored at sorted position i
+ * (the "local PETSc index -> Lagrangian index" map, LDataManager.cpp:2897-2911). */
+int ibk_bin_get_order(ibk_ctx* ctx, int* h_lag_idx);
+
+/* LDataManager::spread core (LDataManager.cpp:551-667) as IBMethod::spreadForce calls it
+ * (src/IB/IBMethod.cpp:972-995): f += S[F] from the markers each patch OWNS into interior and
+ * ghost cells, followed (accumulate_halo != 0) by the ghost-region sum onto the owning DOFs
+ * among this process's patches incl. periodic wrap (SAMRAIGhostDataAccumulator semantics,
+ * ibtk/src/math/SAMRAIGhostDataAccumulator.cpp:295-353). */
+int ibk_spread_force(ibk_ctx* ctx, const char* spread_fcn, int accumulate_halo);
+/* LDataManager::interp core (LDataManager.cpp:698-813) as IBMethod::interpolateVelocity calls it
+ * (IBMethod.cpp:672-694): (fill_halo != 0) ghost fill of u among this process's patches incl.
+ * periodic wrap (replaces u_ghost_fill_scheds[ln]->fillData, :744), then U = J[u]. */
+int ibk_interpolate_velocity(ibk_ctx* ctx, const char* interp_fcn, int fill_halo);
+
+/* Halo ops on their own (device pack/unpack around an external exchange; multi-process runs
+ * move the packed buffers with NCCL, see ibamr_b200/halo.py).  which: 0 = u (copy), 1 = f (add). */
+int ibk_halo_local(ibk_ctx* ctx, int which);
+/* Region pack/unpack for inter-process exchange.  Regions are given in the array index space
+ * of (patch, axis): lower/upper inclusive.  mode for unpack: 0 = copy, 1 = add. */
+int ibk_halo_pack(ibk_ctx* ctx, int which, int patch, int axis, const int* lower, const int* upper, double* d_buf);
+int ibk_halo_unpack(ibk_ctx* ctx, int which, int patch, int axis, const int* lower, const int* upper,
+                    const double* d_buf, int mode);
+
+/* Device pointers for zero-copy callers (torch tensors, NCCL): SoA marker columns in SORTED
+ * order ([ndim][capacity] with the given stride) and pitched grid arrays. */
+int ibk_markers_device_ptr(ibk_ctx* ctx, int which, double** d_ptr, long long* stride);
+int ibk_grid_device_ptr(ibk_ctx* ctx, int which, int patch, int axis, double** d_ptr, long long* pitch,
+                        int* dims /* [ndim] incl. ghosts */);
+
+/* Algorithmic-byte accounting of SURVEY.md 8(d): number of distinct side DOFs (all axes) in the
+ * stencil support of >= 1 marker, computed on the device from the sorted keys. */
+int ibk_count_touched_dofs(ibk_ctx* ctx, const char* kernel_fcn, long long* touched);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBK_H */
