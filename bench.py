@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- IB_4 spread + interpolate throughput (markers/s) on B200, one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (weak scaling, BASELINE.json config 5's per-GPU shard): every GPU owns one 512^3 patch of a
+periodic staggered grid and 2^23 markers uniformly distributed inside it; N GPUs form a
+(2,1,1) / (2,2,1) / (2,2,2) process grid, i.e. 8 GPUs = 64M markers on 1024^3.  Kernel IB_4, fp64.
+A step = one pass of the hot path on pre-binned markers:
+    spreadForce         zero f ghosts, f += S[F] (owner-only, deterministic), halo accumulate
+    interpolateVelocity halo fill of u, U = J[u]
+`value` times the steps with inputs resident in HBM; `e2e` times the same step through the
+C ABI with HOST buffers (X, F, u in; U, f out over PCIe, pinned memory) -- the drop-in situation where
+the fluid solver stays on the CPU.  Inputs (2 x 3.3 GB of grid data per GPU) are far larger than the
+126 MB L2, so no explicit L2 flush is needed between iterations.
+
+--impl reference times the reference's own CPU path: the oracle's restatement of the Fortran kernels
+driven the way the reference parallelises (one worker per patch with private arrays, redundant
+ghost-region spreading), on all host cores (OpenMP threads; MPI is not in this image), on a bounded
+density-preserving sample (256^3 cells, 2^20 markers per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+KERNEL = "IB_4"
+METRIC = "IB_4 spread+interp markers/sec"
+UNIT = "markers/s"
+
+
+def splitmix_unit(seed, idx):
+    x = (np.asarray(idx, dtype=np.uint64) ^ np.uint64(seed)) + np.uint64(0x9E3779B97F4A7C15)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    x = x ^ (x >> np.uint64(31))
+    return (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def process_grid(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# --------------------------------------------------------------------------------------------------
+def cpu_baseline(steps=2, warmup=1, n=256, log2_markers=20):
+    """The reference's CPU path (oracle port) on all host cores, on a density-preserving sample."""
+    from oracle import oracle as orc
+    threads = orc.Baseline.threads()
+    # one patch per worker, SAMRAI-style box decomposition of the n^3 sample
+    np3 = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2), 16: (4, 2, 2), 32: (4, 4, 2), 64: (4, 4, 4)}
+    t = 1
+    while t * 2 <= threads and t * 2 in np3:
+        t *= 2
+    npatch = np3[t]
+    N = 1 << log2_markers
+    X = np.stack([splitmix_unit(7 + d, np.arange(N)) for d in range(3)], axis=1).copy()
+    F = np.stack([2.0 * splitmix_unit(1 + d, np.arange(N)) - 1.0 for d in range(3)], axis=1).copy()
+    U = np.zeros((N, 3))
+    b = orc.Baseline(3, (n, n, n), npatch, 3, (0.0,) * 3, (1.0,) * 3, X, field_seed=0)
+    for _ in range(warmup):
+        b.step(KERNEL, F, U)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        b.step(KERNEL, F, U)
+    dt = (time.perf_counter() - t0) / steps
+    b.close()
+    return {"value": N / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n}^3 periodic staggered grid cut into {npatch[0]}x{npatch[1]}x{npatch[2]} patches (one worker each, "
+                      f"gcw 3, redundant ghost-region spreading), 2^{log2_markers} uniform markers, IB_4 spread+interp, "
+                      f"{steps} timed passes; oracle/_ref unbuildable here (needs m4+gfortran+SAMRAI+PETSc+MPI)",
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(steps=max(args.steps, 1), warmup=max(min(args.warmup, 2), 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, args),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, args):
+    pg = process_grid(n_gpus)
+    n = args.cells
+    return {"workload": f"C5 shard (weak scaling): per GPU one {n}^3 patch of a periodic staggered grid + 2^{args.log2_markers} "
+                        f"uniform markers, IB_4, fp64; process grid {pg[0]}x{pg[1]}x{pg[2]} "
+                        f"(global {n * pg[0]}x{n * pg[1]}x{n * pg[2]}, {n_gpus * (1 << args.log2_markers)} markers)",
+            "kernel": KERNEL, "cells_per_gpu": [n, n, n], "markers_per_gpu": 1 << args.log2_markers,
+            "step": "spreadForce (ghost zero + spread + halo accumulate) + interpolateVelocity (halo fill + interp), markers pre-binned",
+            "l2": "inputs larger than L2 (2 x 3.3 GB grid data per GPU vs 126 MB)"}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from ibamr_b200 import api, halo
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = api.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    n, N = args.cells, 1 << args.log2_markers
+    pg = process_grid(world)
+    patches = halo.cartesian_patches(3, pg, (n, n, n))
+    me = patches[rank]
+    dom = tuple(n * pg[d] for d in range(3))
+    ib = api.IBMethodB200(3, (0, 0, 0), tuple(d - 1 for d in dom), (0.0,) * 3, tuple(float(p) for p in pg), (1, 1, 1),
+                          [(me.lower, me.upper)], kernel_fcn=KERNEL, ctx=ctx)
+    g = ib.gcw[0]
+    hx = None
+    if world > 1:
+        plan = halo.HaloPlan(patches, dom, (1, 1, 1), ib.gcw, rank)
+        hx = halo.HaloExchange(plan, halo.IbkBackend(ib, dist, torch))
+
+    # ---- synthetic inputs: uniform markers in the rank's patch, smooth + noisy velocity
+    h = 1.0 / n
+    idx = np.arange(N, dtype=np.uint64) + np.uint64(rank) * np.uint64(N)
+    X = np.stack([(me.lower[d] + n * splitmix_unit(7 + d, idx)) * h for d in range(3)], axis=1)
+    F = np.stack([2.0 * splitmix_unit(1 + d, idx) - 1.0 for d in range(3)], axis=1)
+    # pinned host buffers for the e2e leg
+    hX = torch.from_numpy(X).pin_memory()
+    hF = torch.from_numpy(F).pin_memory()
+    hU = torch.zeros((N, 3), dtype=torch.float64).pin_memory()
+    hu, hf = [], []
+    for a in range(3):
+        shp = ib.side_shape(0, a)
+        lin = [np.arange(shp[2 - d], dtype=np.float64) for d in range(3)]  # index along dim d
+        coords = []
+        for d in range(3):
+            c = (me.lower[d] - g + lin[d] + (0.0 if d == a else 0.5)) * h
+            coords.append(c)
+        ua = (np.sin(2 * np.pi * coords[a]).reshape([-1 if d == a else 1 for d in (2, 1, 0)]) *
+              np.cos(2 * np.pi * coords[(a + 1) % 3]).reshape([-1 if d == (a + 1) % 3 else 1 for d in (2, 1, 0)]))
+        ua = np.broadcast_to(ua, shp).copy()
+        t = torch.from_numpy(ua).pin_memory()
+        hu.append(t)
+        hf.append(torch.zeros(shp, dtype=torch.float64).pin_memory())
+        ib.grid_upload("u", 0, a, t.numpy())
+    ib.setPositions(hX.numpy())
+    ib.setLData("F", hF.numpy())
+    ctx.enable_timing(True)
+    ib.beginDataRedistribution()
+    ctx.synchronize()
+    rebin_ms = ctx.last_ms(2)
+    touched = ib.count_touched_dofs(KERNEL)
+
+    def step():
+        if hx is None:
+            ib.spreadForce(accumulate_halo=True)
+            ib.interpolateVelocity(fill_halo=True)
+        else:
+            lib, hnd = ctx.lib, ctx.h
+            ctx.check(lib.ibk_spread_begin(hnd))
+            ib.spreadForce(accumulate_halo=False)
+            hx.accumulate_begin()
+            ib.halo("f")
+            hx.accumulate_end()
+            ctx.check(lib.ibk_spread_end(hnd))
+            ib.halo("u")
+            hx.fill()
+            ib.interpolateVelocity(fill_halo=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    spread_ms, interp_ms = [], []
+    launches0 = ctx.launch_count()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    launches = ctx.launch_count() - launches0
+    total_ms = ev0.elapsed_time(ev1)
+    # per-kernel-group device times (CUDA events on the ctx stream inside libibk): a few extra steps,
+    # read back one by one so the events of each step are still the "last" ones
+    for _ in range(min(args.steps, 5)):
+        step()
+        ctx.synchronize()
+        spread_ms.append(ctx.last_ms(0))
+        interp_ms.append(ctx.last_ms(1))
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    ms_per_step = total_ms / args.steps
+
+    # ---- e2e: the same step through host buffers (pinned): X, F, u in; U, f out
+    def e2e_step():
+        ib.setLData("X", hX.numpy())  # new positions from the host ...
+        ib.beginDataRedistribution()  # ... are re-binned on the device (wrap, cell, radix sort, permute)
+        ib.setLData("F", hF.numpy())
+        for a in range(3):
+            ib.grid_upload("u", 0, a, hu[a].numpy())
+        ib.grid_fill("f", 0.0)
+        step()
+        C = __import__("ctypes")
+        ctx.check(ctx.lib.ibk_markers_download(ctx.h, 1, hU.numpy().ctypes.data_as(C.POINTER(C.c_double))))
+        for a in range(3):
+            ctx.check(ctx.lib.ibk_grid_download(ctx.h, 1, 0, a, hf[a].numpy().ctypes.data_as(C.POINTER(C.c_double))))
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    grid_bytes = sum(int(np.prod(ib.side_shape(0, a))) for a in range(3)) * 8
+    h2d = 2 * N * 3 * 8 + grid_bytes
+    d2h = N * 3 * 8 + grid_bytes
+
+    # ---- reduce over ranks (max time)
+    if world > 1:
+        t = torch.tensor([ms_per_step, e2e_s, float(np.mean(spread_ms)), float(np.mean(interp_ms))], device="cuda",
+                         dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step, e2e_s, sp_ms, in_ms = [float(v) for v in t.tolist()]
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    else:
+        sp_ms, in_ms = float(np.mean(spread_ms)), float(np.mean(interp_ms))
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        peak = float(peaks["hbm_gbs"])
+        total_markers = N * world
+        spread_bytes = 8 * (3 * N + 3 * N) + 16 * touched
+        interp_bytes = 8 * (3 * N + 3 * N) + 8 * touched
+        ach = spread_bytes / (sp_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": total_markers / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world, args),
+            "e2e": {"value": total_markers / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                    "what": "host X, F, u (pinned) -> device, step, U and f -> host; all copies inside the timed region"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "spread_tile_kernel<3,IB_4> (+ fix-up)", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": spread_bytes, "launch_ms": sp_ms,
+                         "interp": {"kernel": "interp_tile_kernel<3,IB_4>", "achieved": interp_bytes / (in_ms * 1e-3) / 1e9,
+                                    "frac": interp_bytes / (in_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": interp_bytes,
+                                    "launch_ms": in_ms},
+                         "touched_side_dofs": touched},
+            "clocks": sampler.result(),
+            "phases_ms": {"spread_kernels": sp_ms, "interp_kernels": in_ms, "step": ms_per_step, "rebin": rebin_ms},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline()
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    ib.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=512, help="cells per dimension per GPU")
+    ap.add_argument("--log2-markers", type=int, default=23, help="log2 of the markers per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,8 @@ SYMBOLS = {
     "ibk_bin_get_cells": (_i, [_vp, _pi, _pi]),
     "ibk_bin_get_order": (_i, [_vp, _pi]),
     "ibk_spread_force": (_i, [_vp, _s, _i]),
+    "ibk_spread_begin": (_i, [_vp]),
+    "ibk_spread_end": (_i, [_vp]),
     "ibk_interpolate_velocity": (_i, [_vp, _s, _i]),
     "ibk_halo_local": (_i, [_vp, _i]),
     "ibk_halo_pack": (_i, [_vp, _i, _i, _i, _pi, _pi, _vp]),

@@ -266,6 +266,9 @@ int run_entries_op(ibk_ctx* ctx, int op, int kernel, TileParams& tp, const CellG
     mv.v_istride = v_istride;
     mv.src = ctx->b_src.as<uint32_t>();
     std::string err;
+    if (op == 0)
+        CK(zero_discarded(ctx->L, ctx->sbins.brick_start, ctx->sbins.total_bricks, n_entries, mv.src, d_V, v_cstride, v_istride,
+                          tp.ncomp));
     cudaError_t e = (op == 0) ? launch_interp(ctx->L, kernel, tp, ctx->sbins, mv, err) :
                                 launch_spread(ctx->L, kernel, tp, ctx->sbins, mv, err);
     if (e != cudaSuccess) return cuda_fail(ctx, e, err.empty() ? "tile kernel launch" : err.c_str());
@@ -388,8 +391,6 @@ static int raw_host(ibk_ctx* ctx, int op, int kernel, const ibk_array_desc* desc
     CK(ctx->b_io[3].reserve(sizeof(double) * (size_t)n_markers * ndim));
     CK(ctx->b_io[4].reserve(sizeof(double) * (size_t)n_markers * depth));
     double* d_u = ctx->b_io[0].as<double>();
-    int nn[3] = { n[0], n[1] * depth, n[2] }; // depth slices are stacked planes: treat as extra rows
-    if (ndim == 2) nn[1] = n[1] * depth;
     // dense -> pitched, all depth slices at once (rows = n1*n2*depth)
     CK(cudaMemcpy2DAsync(d_u, (size_t)pitch * 8, h_u, (size_t)n[0] * 8, (size_t)n[0] * 8, rows, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->b_io[1].p, h_indices, sizeof(int) * (size_t)nindices, cudaMemcpyHostToDevice, st));

@@ -135,6 +135,8 @@ cudaError_t soa_to_aos(Launcher& L, const double* d_soa, long long stride, doubl
 // entries for the raw / indexed seams: Xe[d][l] = X[idx[l]][d] + shift[l][d], Xr[d][l] = X[idx[l]][d]
 cudaError_t build_entries(Launcher& L, const double* d_X_aos, const int* d_idx, const double* d_shift, int n, int ndim,
                           double* d_Xe, double* d_Xr, long long stride);
+cudaError_t zero_discarded(Launcher& L, const int* brick_start, int total_bricks, int n, const uint32_t* src, double* V,
+                           long long v_cstride, long long v_istride, int ncol);
 cudaError_t compose_index(Launcher& L, const int* d_idx, const uint32_t* d_perm, uint32_t* d_out, int n);
 
 } // namespace ibk

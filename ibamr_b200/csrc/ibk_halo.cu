@@ -224,6 +224,28 @@ cudaError_t build_entries(Launcher& L, const double* d_X_aos, const int* d_idx, 
     return cudaGetLastError();
 }
 
+// Listed markers that no tile can reach (binned into the discard bucket) get V = 0, as the Fortran
+// does for a fully clipped stencil (V(d,s) = 0.d0 before the empty loops, 3d.f.m4:1316).
+__global__ void zero_discarded_kernel(const int* __restrict__ brick_start, int total_bricks, int n, const uint32_t* __restrict__ src,
+                                      double* __restrict__ V, long long v_cstride, long long v_istride, int ncol)
+{
+    const int first = brick_start[total_bricks];
+    for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const long long row = src ? (long long)src[i] : (long long)i;
+        for (int c = 0; c < ncol; ++c) V[c * v_cstride + row * v_istride] = 0.0;
+    }
+}
+
+cudaError_t zero_discarded(Launcher& L, const int* brick_start, int total_bricks, int n, const uint32_t* src, double* V,
+                           long long v_cstride, long long v_istride, int ncol)
+{
+    if (n <= 0) return cudaSuccess;
+    zero_discarded_kernel<<<64, 256, 0, L.stream>>>(brick_start, total_bricks, n, src, V, v_cstride, v_istride, ncol);
+    L.launches++;
+    return cudaGetLastError();
+}
+
 __global__ void compose_index_kernel(const int* __restrict__ idx, const uint32_t* __restrict__ perm, uint32_t* __restrict__ out, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ibk_engine.h"
@@ -51,6 +52,10 @@ __global__ void __launch_bounds__(INTERP_THREADS)
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
     constexpr int S = TILE + 2 * M;
+    // TMA needs the box to start on a 16-byte boundary: with 8-byte elements the innermost start
+    // coordinate must be even.  The box is therefore SX = S + 2 wide in x and starts at the even
+    // coordinate at or below the first needed point (measured on B200: an odd start traps).
+    constexpr int SX = S + 2;
     constexpr int BRICKS_PER_TILE = (NDIM == 3) ? 64 : 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* su = reinterpret_cast<double*>(smem_raw);
@@ -90,12 +95,15 @@ __global__ void __launch_bounds__(INTERP_THREADS)
         int e0[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) e0[d] = sp0[d] - cg.pp0[d];
+        const int xodd = e0[0] & 1; // two's complement: also right for negative coordinates
+        e0[0] -= xodd;
+        const int sx0 = sp0[0] - xodd; // pp coordinate of the first staged column
         const bool use_tma = (args.tma_mask >> a) & 1u;
         if (use_tma)
         {
             if (threadIdx.x == 0)
             {
-                constexpr uint32_t bytes = (NDIM == 3 ? S * S * S : S * S) * sizeof(double);
+                constexpr uint32_t bytes = (NDIM == 3 ? SX * S * S : SX * S) * sizeof(double);
                 fence_proxy_async_smem();
                 mbar_expect_tx(&bar, bytes);
                 if constexpr (NDIM == 3)
@@ -108,12 +116,12 @@ __global__ void __launch_bounds__(INTERP_THREADS)
         }
         else
         {
-            constexpr int NPTS = (NDIM == 3) ? S * S * S : S * S;
+            constexpr int NPTS = (NDIM == 3) ? SX * S * S : SX * S;
             for (int q = threadIdx.x; q < NPTS; q += INTERP_THREADS)
             {
-                const int i = q % S;
-                const int j = (q / S) % S;
-                const int k = (NDIM == 3) ? q / (S * S) : 0;
+                const int i = q % SX;
+                const int j = (q / SX) % S;
+                const int k = (NDIM == 3) ? q / (SX * S) : 0;
                 const int gi = e0[0] + i, gj = e0[1] + j, gk = (NDIM == 3) ? e0[2] + k : 0;
                 double v = 0.0;
                 if (gi >= 0 && gi < cg.n[0] && gj >= 0 && gj < cg.n[1] && gk >= 0 && gk < cg.n[2])
@@ -143,7 +151,7 @@ __global__ void __launch_bounds__(INTERP_THREADS)
             {
                 if constexpr (NDIM == 3)
                 {
-                    const double* base = su + ((lo[2] - sp0[2]) * S + (lo[1] - sp0[1])) * S + (lo[0] - sp0[0]);
+                    const double* base = su + ((lo[2] - sp0[2]) * S + (lo[1] - sp0[1])) * SX + (lo[0] - sx0);
 #pragma unroll
                     for (int k = 0; k < W; ++k)
 #pragma unroll
@@ -151,16 +159,16 @@ __global__ void __launch_bounds__(INTERP_THREADS)
                         {
                             const double wyz = w[1][j] * w[2][k];
 #pragma unroll
-                            for (int ii = 0; ii < W; ++ii) acc += (w[0][ii] * wyz) * base[(k * S + j) * S + ii];
+                            for (int ii = 0; ii < W; ++ii) acc += (w[0][ii] * wyz) * base[(k * S + j) * SX + ii];
                         }
                 }
                 else
                 {
-                    const double* base = su + (lo[1] - sp0[1]) * S + (lo[0] - sp0[0]);
+                    const double* base = su + (lo[1] - sp0[1]) * SX + (lo[0] - sx0);
 #pragma unroll
                     for (int j = 0; j < W; ++j)
 #pragma unroll
-                        for (int ii = 0; ii < W; ++ii) acc += (w[0][ii] * w[1][j]) * base[j * S + ii];
+                        for (int ii = 0; ii < W; ++ii) acc += (w[0][ii] * w[1][j]) * base[j * SX + ii];
                 }
             }
             else
@@ -227,7 +235,7 @@ static bool make_map(CUtensorMap* m, const CompGeom& cg, int ndim, int S)
     if (!enc) return false;
     cuuint64_t dims[3] = { (cuuint64_t)cg.n[0], (cuuint64_t)cg.n[1], (cuuint64_t)cg.n[2] };
     cuuint64_t strides[2] = { (cuuint64_t)cg.pitch * 8ull, (cuuint64_t)cg.pitch * 8ull * (cuuint64_t)cg.n[1] };
-    cuuint32_t box[3] = { (cuuint32_t)S, (cuuint32_t)S, (cuuint32_t)S };
+    cuuint32_t box[3] = { (cuuint32_t)(S + 2), (cuuint32_t)S, (cuuint32_t)S };
     cuuint32_t estr[3] = { 1, 1, 1 };
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)ndim, (void*)cg.ptr, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -240,7 +248,7 @@ static cudaError_t launch_interp_t(Launcher& L, const TileParams& tp, const Bins
 {
     constexpr int M = KTraits<K>::M;
     constexpr int S = TILE + 2 * M;
-    const size_t smem = sizeof(double) * (size_t)(NDIM == 3 ? S * S * S : S * S);
+    const size_t smem = sizeof(double) * (size_t)(NDIM == 3 ? (S + 2) * S * S : (S + 2) * S);
     TmaMapSet maps;
     std::memset(&maps, 0, sizeof(maps));
     InterpArgs args;
@@ -253,8 +261,14 @@ static cudaError_t launch_interp_t(Launcher& L, const TileParams& tp, const Bins
     args.v_istride = mv.v_istride;
     args.src = mv.src;
     args.tma_mask = 0;
+    static const bool no_tma = getenv("IBK_NO_TMA") != nullptr;
+    static const bool dbg = getenv("IBK_DEBUG") != nullptr;
     for (int a = 0; a < tp.ncomp; ++a)
-        if (tma_eligible(tp.comp[a]) && make_map(&maps.m[a], tp.comp[a], NDIM, S)) args.tma_mask |= (1u << a);
+        if (!no_tma && tma_eligible(tp.comp[a]) && make_map(&maps.m[a], tp.comp[a], NDIM, S)) args.tma_mask |= (1u << a);
+    if (dbg)
+        fprintf(stderr, "[ibk] interp<%d,%d> ncomp=%d tma_mask=%x ntiles=%d n=(%d,%d,%d) pitch=%lld ptr=%p sizeof(tp)=%zu\n", NDIM, K,
+                tp.ncomp, args.tma_mask, tp.nt[0] * tp.nt[1] * tp.nt[2], tp.comp[0].n[0], tp.comp[0].n[1], tp.comp[0].n[2],
+                tp.comp[0].pitch, (void*)tp.comp[0].ptr, sizeof(TileParams));
     auto kfn = interp_tile_kernel<NDIM, K>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)

@@ -169,6 +169,24 @@ __global__ void halo_accum_kernel(const HaloArgs* __restrict__ argp)
     }
 }
 
+// f ghosts are scratch for the spread: LDataManager::spread zeroes them (setToScalar(f, 0,
+// interior_only = false), LDataManager.cpp:594) before anything is spread into them.
+__global__ void halo_zero_ghost_kernel(const HaloArgs* __restrict__ argp)
+{
+    const HaloArgs& A = *argp;
+    int lo[3], hi[3];
+    if (!slab_box(A.ndim, blockIdx.y, A.alo, A.ahi, A.ilo, A.ihi, lo, hi)) return;
+    const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
+    const long long total = (long long)e0 * e1 * e2;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int I0 = lo[0] + (int)(q % e0);
+        const long long t = q / e0;
+        const int I1 = lo[1] + (int)(t % e1), I2 = lo[2] + (int)(t / e1);
+        A.dst[((long long)(I2 - A.alo[2]) * A.n1 + (I1 - A.alo[1])) * A.pitch + (I0 - A.alo[0])] = 0.0;
+    }
+}
+
 struct FacePair
 {
     double* a;
@@ -194,6 +212,39 @@ __global__ void face_sync_kernel(const FacePair* __restrict__ pairs)
         const double s = *pa + *pb;
         *pa = s;
         *pb = s;
+    }
+}
+
+// Pre-existing content of f on the two boundary face layers of the axis-normal component must not
+// take part in the face/ghost sums (the reference spreads into a zeroed f and adds the old f to the
+// interiors afterwards, LDataManager.cpp:589-594, 662-663): park it, zero the layers, restore-add later.
+// mode 0: save + zero, mode 1: layer += saved.
+__global__ void face_layers_kernel(const HaloArgs* __restrict__ argp, int axis, double* __restrict__ save, int mode)
+{
+    const HaloArgs& A = *argp;
+    int ext[3];
+    for (int d = 0; d < 3; ++d) ext[d] = (d == axis) ? 1 : (A.ihi[d] - A.ilo[d] + 1);
+    const long long per = (long long)ext[0] * ext[1] * ext[2];
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < 2 * per; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int side = (int)(q / per);
+        long long r = q % per;
+        int I[3];
+        I[0] = A.ilo[0] + (int)(r % ext[0]);
+        r /= ext[0];
+        I[1] = A.ilo[1] + (int)(r % ext[1]);
+        I[2] = A.ilo[2] + (int)(r / ext[1]);
+        I[axis] = side ? A.ihi[axis] : A.ilo[axis];
+        double* p = A.dst + ((long long)(I[2] - A.alo[2]) * A.n1 + (I[1] - A.alo[1])) * A.pitch + (I[0] - A.alo[0]);
+        if (mode == 0)
+        {
+            save[q] = *p;
+            *p = 0.0;
+        }
+        else
+        {
+            *p += save[q];
+        }
     }
 }
 
@@ -243,6 +294,7 @@ struct HaloPlan
     std::vector<HaloArgs*> d_args[2];
     std::vector<FacePair*> d_pairs; // per axis (f only)
     std::vector<int> n_pairs;
+    std::vector<double*> d_face_save; // [patch][axis]: 2 boundary layers of f's axis-normal component
     std::vector<void*> allocs;
 };
 struct LevelExtra
@@ -299,6 +351,7 @@ static int build_halo_plan(ibk_ctx* ctx)
     int N[3] = { 1, 1, 1 };
     for (int d = 0; d < ndim; ++d) N[d] = lv.domain_upper[d] - lv.domain_lower[d] + 1;
     for (int which = 0; which < 2; ++which) hp.d_args[which].assign((size_t)P * ndim, nullptr);
+    hp.d_face_save.assign((size_t)P * ndim, nullptr);
     hp.d_pairs.assign(ndim, nullptr);
     hp.n_pairs.assign(ndim, 0);
     for (int axis = 0; axis < ndim; ++axis)
@@ -409,6 +462,15 @@ static int build_halo_plan(ibk_ctx* ctx)
                 HaloArgs* d_A = nullptr;
                 CK(cudaMalloc(&d_A, sizeof(HaloArgs)));
                 hp.allocs.push_back(d_A);
+                if (which == 1)
+                {
+                    long long per = 1;
+                    for (int d = 0; d < ndim; ++d) per *= (d == axis) ? 1 : (ihi[d] - ilo[d] + 1);
+                    double* d_save = nullptr;
+                    CK(cudaMalloc(&d_save, sizeof(double) * 2 * (size_t)per));
+                    hp.allocs.push_back(d_save);
+                    hp.d_face_save[(size_t)p * ndim + axis] = d_save;
+                }
                 CK(cudaMemcpy(d_A, &A, sizeof(HaloArgs), cudaMemcpyHostToDevice));
                 hp.d_args[which][(size_t)p * ndim + axis] = d_A;
             }
@@ -865,6 +927,45 @@ extern "C" int ibk_halo_unpack(ibk_ctx* ctx, int which, int patch, int axis, con
 // ---------------------------------------------------------------------------------------------
 // spreadForce / interpolateVelocity
 // ---------------------------------------------------------------------------------------------
+static int face_layers(ibk_ctx* ctx, int mode)
+{
+    LevelState& lv = ctx->lv;
+    LevelExtra* ex = extra_of(ctx, false);
+    if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
+    for (size_t p = 0; p < lv.patches.size(); ++p)
+        for (int axis = 0; axis < lv.ndim; ++axis)
+        {
+            face_layers_kernel<<<halo_blocks(lv, lv.patches[p], axis), 256, 0, ctx->L.stream>>>(
+                ex->halo.d_args[1][p * lv.ndim + axis], axis, ex->halo.d_face_save[p * lv.ndim + axis], mode);
+            ctx->L.launches++;
+        }
+    CK(cudaGetLastError());
+    return IBK_OK;
+}
+
+extern "C" int ibk_spread_begin(ibk_ctx* ctx)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    LevelExtra* ex = extra_of(ctx, false);
+    if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
+    // the ghost regions of f receive fresh spread values only (LDataManager.cpp:594)
+    const unsigned nslab = 2 * lv.ndim;
+    for (size_t p = 0; p < lv.patches.size(); ++p)
+        for (int axis = 0; axis < lv.ndim; ++axis)
+        {
+            dim3 grid(halo_blocks(lv, lv.patches[p], axis), nslab);
+            halo_zero_ghost_kernel<<<grid, 256, 0, ctx->L.stream>>>(ex->halo.d_args[1][p * lv.ndim + axis]);
+            ctx->L.launches++;
+        }
+    return face_layers(ctx, 0);
+}
+extern "C" int ibk_spread_end(ibk_ctx* ctx)
+{
+    NEED_LEVEL();
+    return face_layers(ctx, 1);
+}
+
 static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo)
 {
     NEED_LEVEL();
@@ -880,6 +981,8 @@ static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo)
     const int which_ev = op == 1 ? 0 : 1;
     if (op == 0 && halo)
         if (int rc = ibk_halo_local(ctx, 0)) return rc;
+    if (op == 1 && halo)
+        if (int rc = ibk_spread_begin(ctx)) return rc;
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[which_ev][0], ctx->L.stream));
     MarkerView mv;
     mv.X = lv.X;
@@ -902,7 +1005,10 @@ static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo)
         ctx->ev_valid[which_ev] = true;
     }
     if (op == 1 && halo)
+    {
         if (int rc = ibk_halo_local(ctx, 1)) return rc;
+        if (int rc = ibk_spread_end(ctx)) return rc;
+    }
     return IBK_OK;
 }
 

@@ -27,6 +27,7 @@
 // added by spread_fixup_kernel in a fixed order.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 
 #include "ibk_engine.h"
@@ -395,7 +396,26 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     args.exc_count = g_exc_buf;
     args.exc_list = g_exc_buf + 1;
     args.exc_capacity = EXC_CAPACITY;
-    const int ntiles = tp.ot_n[0] * tp.ot_n[1] * tp.ot_n[2];
+    // output tiles: tile a covers the points pp in [16a + M, 16a + M + 16); cover every array point
+    TileParams tpl = tp;
+    for (int d = 0; d < 3; ++d)
+    {
+        tpl.ot_lo[d] = 0;
+        tpl.ot_n[d] = 1;
+        if (d >= NDIM) continue;
+        int ppmin = 1 << 30, ppmax = -(1 << 30);
+        for (int a = 0; a < tp.ncomp; ++a)
+        {
+            ppmin = std::min(ppmin, tp.comp[a].pp0[d]);
+            ppmax = std::max(ppmax, tp.comp[a].pp0[d] + tp.comp[a].n[d] - 1);
+        }
+        auto fdiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
+        const int alo = std::max(0, fdiv(ppmin - M, TILE));
+        const int ahi = fdiv(ppmax - M, TILE);
+        tpl.ot_lo[d] = alo;
+        tpl.ot_n[d] = std::max(0, ahi - alo + 1);
+    }
+    const int ntiles = tpl.ot_n[0] * tpl.ot_n[1] * tpl.ot_n[2];
     if (ntiles <= 0) return cudaSuccess;
     auto kfn = spread_tile_kernel<NDIM, K>;
     auto ffn = spread_fixup_kernel<NDIM, K>;
@@ -412,8 +432,8 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
             err = "cudaFuncSetAttribute(spread) failed";
             return e;
         }
-        kfn<<<ntiles, SPREAD_THREADS, smem, L.stream>>>(tp, args);
-        ffn<<<1, 32, 0, L.stream>>>(tp, args);
+        kfn<<<ntiles, SPREAD_THREADS, smem, L.stream>>>(tpl, args);
+        ffn<<<1, 32, 0, L.stream>>>(tpl, args);
         L.launches += 2;
         if (c0 + SPREAD_MAXC < tp.ncomp)
             if ((e = cudaMemsetAsync(g_exc_buf, 0, sizeof(int), L.stream)) != cudaSuccess) return e;

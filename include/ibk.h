@@ -297,6 +297,14 @@ int ibk_bin_get_order(ibk_ctx* ctx, int* h_lag_idx);
  * among this process's patches incl. periodic wrap (SAMRAIGhostDataAccumulator semantics,
  * ibtk/src/math/SAMRAIGhostDataAccumulator.cpp:295-353). */
 int ibk_spread_force(ibk_ctx* ctx, const char* spread_fcn, int accumulate_halo);
+/* The pieces of accumulate_halo != 0, for callers that interleave an inter-process exchange
+ * (ibamr_b200/halo.py): ibk_spread_begin zeroes the ghost regions of f and parks + zeroes the
+ * pre-existing content of the shared boundary face layers (the reference spreads into a zeroed f and
+ * adds the old f afterwards, LDataManager.cpp:589-594, 662-663); then ibk_spread_force(.., 0),
+ * pack for remote ranks, ibk_halo_local(ctx, 1), remote unpack-adds; ibk_spread_end restores the
+ * parked face content. */
+int ibk_spread_begin(ibk_ctx* ctx);
+int ibk_spread_end(ibk_ctx* ctx);
 /* LDataManager::interp core (LDataManager.cpp:698-813) as IBMethod::interpolateVelocity calls it
  * (IBMethod.cpp:672-694): (fill_halo != 0) ghost fill of u among this process's patches incl.
  * periodic wrap (replaces u_ghost_fill_scheds[ln]->fillData, :744), then U = J[u]. */
