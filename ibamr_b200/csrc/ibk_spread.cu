@@ -36,8 +36,8 @@ namespace ibk
 {
 constexpr int SPREAD_THREADS = 256;
 constexpr int SPREAD_WARPS = SPREAD_THREADS / 32;
-constexpr int SPREAD_BATCH = 8;
-constexpr int SPREAD_MAXC = 3; // components accumulated per launch
+constexpr int SPREAD_BATCH = 4; // markers per phase-A batch (per warp)
+constexpr int SPREAD_MAXC = 3;  // components accumulated per launch
 
 struct SpreadArgs
 {
@@ -58,16 +58,18 @@ struct SpreadArgs
     int exc_capacity;
 };
 
+// Accumulator tile layout: 16-double rows, row y rotated by 4*y (mod 16).  The 4x4 (x, y) footprint
+// of a stencil plane then hits 16 distinct 8-byte banks, and -- unlike an XOR swizzle -- the rotation
+// is additive: (x + 4y) & 15 = (R0 + lane constant) & 15 with R0 = x0 + 4*y0 of the stencil origin, so
+// a lane needs three integer operations per marker to find its word.
 template <int NDIM>
 __device__ __forceinline__ int acc_index(int x, int y, int z)
 {
-    // 16-double rows; XOR-swizzle the 4-double group with the row so that the 4x4 (x,y) footprint of
-    // a stencil plane hits 16 distinct 8-byte banks.
-    const int xs = x ^ ((y & 3) << 2);
+    const int xs = (x + 4 * y) & 15;
     if constexpr (NDIM == 3)
-        return ((z << 4) + y) * 16 + xs;
+        return (z << 8) + (y << 4) + xs;
     else
-        return y * 16 + xs;
+        return (y << 4) + xs;
 }
 
 template <int NDIM, int K>
@@ -81,19 +83,28 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
     constexpr int NSLOT = (NPTS + 31) / 32;
     constexpr int TILE_PTS = (NDIM == 3) ? TILE * TILE * TILE : TILE * TILE;
     constexpr int NBRICKS = (NDIM == 3) ? NBR * NBR * NBR : NBR * NBR;
+    constexpr int NCOL = (NDIM == 3) ? NC * NC * NC : NC * NC;
+    constexpr bool FAST4 = (NDIM == 3) && (W == 4); // lane = (ix, iy, half): two adjacent z points per lane
+    constexpr int LD = NDIM - 1;                    // the "last" dimension carries the force factor
+    constexpr int NTASK = SPREAD_BATCH * NDIM * 2;  // phase-A tasks per batch: (marker, dimension, variant)
+    static_assert(NTASK <= 32, "one phase-A round per batch");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* acc = reinterpret_cast<double*>(smem_raw);                                   // [ncomp][TILE_PTS]
-    double* wgt_all = acc + (size_t)args.ncomp * TILE_PTS;                               // [warp][BATCH][NDIM][2][W]
-    double* fs_all = wgt_all + SPREAD_WARPS * SPREAD_BATCH * NDIM * 2 * W;               // [warp][BATCH][MAXC]
-    int* lom_all = reinterpret_cast<int*>(fs_all + SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC); // [warp][BATCH][NDIM][2]
-    int* brng = lom_all + SPREAD_WARPS * SPREAD_BATCH * NDIM * 2;                        // [NBRICKS][2]
+    double* acc = reinterpret_cast<double*>(smem_raw);                          // [ncomp][TILE_PTS]
+    double* wgt_all = acc + (size_t)args.ncomp * TILE_PTS;                      // [warp][BATCH][NDIM][2][W]
+    double* wlf_all = wgt_all + SPREAD_WARPS * SPREAD_BATCH * NDIM * 2 * W;     // [warp][BATCH][MAXC][W]  last-dim weights * force
+    int* lom_all = reinterpret_cast<int*>(wlf_all + SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * W); // [warp][BATCH][NDIM][2]
+    int* rec_all = lom_all + SPREAD_WARPS * SPREAD_BATCH * NDIM * 2;            // [warp][BATCH][MAXC][2]
+    int* brng = rec_all + SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * 2;        // [NBRICKS][2]
+    unsigned char* order = reinterpret_cast<unsigned char*>(brng + 2 * NBRICKS); // [NBRICKS] bricks sorted by colour
     __shared__ int any_markers;
+    __shared__ int col_start[NCOL + 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* wgt = wgt_all + warp * (SPREAD_BATCH * NDIM * 2 * W);
-    double* fs = fs_all + warp * (SPREAD_BATCH * SPREAD_MAXC);
+    double* wlf = wlf_all + warp * (SPREAD_BATCH * SPREAD_MAXC * W);
     int* lom = lom_all + warp * (SPREAD_BATCH * NDIM * 2);
+    int* rec = rec_all + warp * (SPREAD_BATCH * SPREAD_MAXC * 2);
 
     // which output tile
     int ot[3];
@@ -108,8 +119,18 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
 #pragma unroll
     for (int d = 0; d < 3; ++d) tlo[d] = TILE * ot[d] + M;
 
-    // brick ranges of the neighbourhood + emptiness test
+    // brick ranges of the neighbourhood, colour-sorted brick order, emptiness test
     if (threadIdx.x == 0) any_markers = 0;
+    if (threadIdx.x <= NCOL)
+    {
+        int s = 0; // bricks with colour < threadIdx.x (NBR, NC are compile-time)
+        for (int c = 0; c < (int)threadIdx.x; ++c)
+        {
+            const int c0 = c % NC, c1 = (c / NC) % NC, c2 = (NDIM == 3) ? c / (NC * NC) : 0;
+            s += ((NBR - c0 + NC - 1) / NC) * ((NBR - c1 + NC - 1) / NC) * ((NDIM == 3) ? (NBR - c2 + NC - 1) / NC : 1);
+        }
+        col_start[threadIdx.x] = s;
+    }
     __syncthreads();
     for (int q = threadIdx.x; q < NBRICKS; q += SPREAD_THREADS)
     {
@@ -125,13 +146,47 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
         brng[2 * q] = s;
         brng[2 * q + 1] = e;
         if (e > s) any_markers = 1;
+        const int c0 = lx % NC, c1 = ly % NC, c2 = lz % NC;
+        const int col = (c2 * NC + c1) * NC + c0;
+        const int n0 = (NBR - c0 + NC - 1) / NC, n1 = (NBR - c1 + NC - 1) / NC;
+        const int pos = ((lz / NC) * n1 + ly / NC) * n0 + lx / NC;
+        order[col_start[col] + pos] = (unsigned char)q;
     }
     __syncthreads();
     if (!any_markers) return;
 
     for (int q = threadIdx.x; q < args.ncomp * TILE_PTS; q += SPREAD_THREADS) acc[q] = 0.0;
 
+    const int ncomp = args.ncomp;
+    const double inv_vol = tp.inv_vol;
+    const int G = tp.G;
+    // phase-A role of this lane: (marker, dimension, variant) and, for A2, (marker, component)
+    const int a_m = lane / (NDIM * 2), a_d = (lane >> 1) % NDIM, a_v = lane & 1;
+    const bool a_on = lane < NTASK && a_v < tp.nvar[a_d];
+    const double a_xl = tp.xl[a_d][a_v], a_dx = tp.dx[a_d];
+    const int a_tlo = tlo[a_d];
+    const int b_m = lane / SPREAD_MAXC, b_a = lane % SPREAD_MAXC;
+    const bool b_on = lane < SPREAD_BATCH * SPREAD_MAXC && b_a < ncomp;
+    int b_v[3] = { 0, 0, 0 }, b_vcol = 0;
+    if (b_on)
+    {
+        const CompGeom& cg = tp.comp[args.comp0 + b_a];
+        b_v[0] = cg.var[0];
+        b_v[1] = cg.var[1];
+        b_v[2] = cg.var[2];
+        b_vcol = cg.vcol;
+    }
+    // phase-B role: weight offsets of each component (which x_lower variant per dimension)
+    int wo0[SPREAD_MAXC], wo1[SPREAD_MAXC];
+#pragma unroll
+    for (int a = 0; a < SPREAD_MAXC; ++a)
+    {
+        const CompGeom& cg = tp.comp[args.comp0 + (a < ncomp ? a : 0)];
+        wo0[a] = (0 * 2 + cg.var[0]) * W;
+        wo1[a] = (1 * 2 + cg.var[1]) * W;
+    }
     // per-lane stencil point(s)
+    const int l15 = lane & 15, half = lane >> 4;
     int pix[NSLOT], piy[NSLOT], piz[NSLOT];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s)
@@ -143,110 +198,146 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
     }
     __syncthreads();
 
-    constexpr int NCOL = (NDIM == 3) ? NC * NC * NC : NC * NC;
     for (int col = 0; col < NCOL; ++col)
     {
-        const int c0 = col % NC, c1 = (col / NC) % NC, c2 = (NDIM == 3) ? col / (NC * NC) : 0;
-        const int n0 = (NBR - c0 + NC - 1) / NC, n1 = (NBR - c1 + NC - 1) / NC, n2 = (NDIM == 3) ? (NBR - c2 + NC - 1) / NC : 1;
-        const int nbr_col = n0 * n1 * n2;
-        for (int bi = warp; bi < nbr_col; bi += SPREAD_WARPS)
+        const int cbeg = col_start[col], cend = col_start[col + 1];
+        for (int bi = cbeg + warp; bi < cend; bi += SPREAD_WARPS)
         {
-            const int lx = c0 + NC * (bi % n0), ly = c1 + NC * ((bi / n0) % n1), lz = (NDIM == 3) ? c2 + NC * (bi / (n0 * n1)) : 0;
-            const int q = (lz * NBR + ly) * NBR + lx;
+            const int q = order[bi];
             const int bs = brng[2 * q], be = brng[2 * q + 1];
             if (bs >= be) continue;
+            const int lx = q % NBR, ly = (q / NBR) % NBR, lz = (NDIM == 3) ? q / (NBR * NBR) : 0;
             const int gb[3] = { TILE_BRICKS * ot[0] + lx, TILE_BRICKS * ot[1] + ly, TILE_BRICKS * ot[2] + lz };
+            const int a_gb = BRICK * gb[a_d];
             for (int batch = bs; batch < be; batch += SPREAD_BATCH)
             {
                 const int nb = min(SPREAD_BATCH, be - batch);
-                // ---- phase A: lane (m, d) evaluates the stencil(s) of marker m along dimension d ----
+                // ---- phase A1: one lane per (marker, dimension, variant): stencil origin, weights, masks ----
+                if (a_on && a_m < nb)
                 {
-                    const int m = lane / NDIM, d = lane % NDIM;
-                    if (m < nb)
+                    const int i = batch + a_m;
+                    const double xs = __ldg(&args.X[a_d * args.x_stride + i]);
+                    const double xr = args.Xraw ? __ldg(&args.Xraw[a_d * args.x_stride + i]) : xs;
+                    const unsigned long long key = __ldg(&args.keys[i]);
+                    const int cc = a_gb + (int)((key >> (args.tie_bits + 2 * a_d)) & 3ull); // binning cell (pp)
+                    double w[W];
+                    int l;
+                    stencil_1d<K>(xs, xr, a_xl, a_dx, l, w);
+                    const int lo_pp = l + G;
+                    unsigned mask = 0;
+                    bool beyond = false;
+#pragma unroll
+                    for (int j = 0; j < W; ++j)
                     {
-                        const int i = batch + m;
-                        const double xs = args.X[d * args.x_stride + i];
-                        const double xr = args.Xraw ? args.Xraw[d * args.x_stride + i] : xs;
-                        const int cin = (int)((args.keys[i] >> (args.tie_bits + 2 * d)) & 3ull);
-                        const int cc = BRICK * gb[d] + cin; // marker's binning cell (pp coordinates)
-                        bool beyond = false;
-                        for (int v = 0; v < tp.nvar[d]; ++v)
-                        {
-                            double w[W];
-                            int l;
-                            stencil_1d<K>(xs, xr, tp.xl[d][v], tp.dx[d], l, w);
-                            const int lo_pp = l + tp.G;
-                            unsigned mask = 0;
+                        const int pp = lo_pp + j;
+                        const bool in_margin = (pp >= cc - M) && (pp <= cc + M);
+                        beyond = beyond || !in_margin;
+                        if (in_margin && pp >= a_tlo && pp < a_tlo + TILE) mask |= (1u << j);
+                        wgt[((a_m * NDIM + a_d) * 2 + a_v) * W + j] = w[j];
+                    }
+                    lom[(a_m * NDIM + a_d) * 2 + a_v] = ((lo_pp - a_tlo) & 0xFFFF) | (mask << 16);
+                    if (beyond && args.exc_list)
+                    {
+                        // recorded by the CTA whose tile holds the marker's cell (the fix-up kernel re-derives
+                        // everything and removes duplicates)
+                        bool mine = true;
 #pragma unroll
-                            for (int j = 0; j < W; ++j)
-                            {
-                                const int pp = lo_pp + j;
-                                const bool in_margin = (pp >= cc - M) && (pp <= cc + M);
-                                beyond = beyond || !in_margin;
-                                if (in_margin && pp >= tlo[d] && pp < tlo[d] + TILE) mask |= (1u << j);
-                                wgt[((m * NDIM + d) * 2 + v) * W + j] = w[j];
-                            }
-                            lom[(m * NDIM + d) * 2 + v] = ((lo_pp - tlo[d]) & 0xFFFF) | (mask << 16);
-                        }
-                        if (beyond && args.exc_list)
+                        for (int dd = 0; dd < NDIM; ++dd)
                         {
-                            // record once: by the CTA whose tile holds the marker's cell, dimension 0 lane
-                            // (exceptions are re-derived in full by the fix-up kernel)
-                            bool mine = true;
-#pragma unroll
-                            for (int dd = 0; dd < NDIM; ++dd)
-                            {
-                                const int cind = (int)((args.keys[i] >> (args.tie_bits + 2 * dd)) & 3ull);
-                                const int ccd = BRICK * gb[dd] + cind;
-                                mine = mine && ccd >= tlo[dd] && ccd < tlo[dd] + TILE;
-                            }
-                            if (mine)
-                            {
-                                const int slot = atomicAdd(args.exc_count, 1);
-                                if (slot < args.exc_capacity) args.exc_list[slot] = i;
-                            }
+                            const int ccd = BRICK * gb[dd] + (int)((key >> (args.tie_bits + 2 * dd)) & 3ull);
+                            mine = mine && ccd >= tlo[dd] && ccd < tlo[dd] + TILE;
                         }
-                        if (d == 0)
+                        if (mine)
                         {
-                            const long long row = args.src ? (long long)args.src[i] : (long long)i;
-                            for (int a = 0; a < args.ncomp; ++a)
-                                fs[m * SPREAD_MAXC + a] =
-                                    args.V[tp.comp[args.comp0 + a].vcol * args.v_cstride + row * args.v_istride] * tp.inv_vol;
+                            const int slot = atomicAdd(args.exc_count, 1);
+                            if (slot < args.exc_capacity) args.exc_list[slot] = i;
                         }
                     }
+                }
+                // the force value of (marker, component) is fetched while A1 computes
+                double b_f = 0.0;
+                if (b_on && b_m < nb)
+                {
+                    const int i = batch + b_m;
+                    const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
+                    b_f = __ldg(&args.V[b_vcol * args.v_cstride + row * args.v_istride]) * inv_vol;
+                }
+                __syncwarp();
+                // ---- phase A2: one lane per (marker, component): packed record + last-dim weights * force ----
+                if (b_on && b_m < nb)
+                {
+                    const int L0 = lom[(b_m * NDIM + 0) * 2 + b_v[0]];
+                    const int L1 = lom[(b_m * NDIM + 1) * 2 + b_v[1]];
+                    const int L2 = (NDIM == 3) ? lom[(b_m * NDIM + LD) * 2 + b_v[LD]] : (1 << 16);
+                    const int x0 = (int)(short)(L0 & 0xFFFF), y0 = (int)(short)(L1 & 0xFFFF),
+                              z0 = (NDIM == 3) ? (int)(short)(L2 & 0xFFFF) : 0;
+                    const unsigned mx = (unsigned)L0 >> 16, my = (unsigned)L1 >> 16, mz = (unsigned)L2 >> 16;
+                    unsigned w0r;
+                    if constexpr (FAST4)
+                    {
+                        unsigned mxy = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mxy |= ((my >> j) & 1u) ? (mx << (4 * j)) : 0u;
+                        w0r = mxy | (mz << 16);
+                    }
+                    else
+                    {
+                        w0r = mx | (my << 8) | (mz << 16);
+                    }
+                    const bool empty = (mx == 0) || (my == 0) || (mz == 0);
+                    w0r = empty ? 0u : (w0r | ((unsigned)((x0 + 4 * y0) & 15) << 24) | 0x80000000u);
+                    rec[(b_m * SPREAD_MAXC + b_a) * 2 + 0] = (int)w0r;
+                    rec[(b_m * SPREAD_MAXC + b_a) * 2 + 1] = (NDIM == 3) ? (z0 * 256 + y0 * 16) : (y0 * 16);
+                    const double* wl = &wgt[((b_m * NDIM + LD) * 2 + b_v[LD]) * W];
+#pragma unroll
+                    for (int j = 0; j < W; ++j) wlf[(b_m * SPREAD_MAXC + b_a) * W + j] = wl[j] * b_f;
                 }
                 __syncwarp();
                 // ---- phase B: markers one after another, lanes over the stencil points ----
                 for (int m = 0; m < nb; ++m)
                 {
-                    for (int a = 0; a < args.ncomp; ++a)
-                    {
-                        const CompGeom& cg = tp.comp[args.comp0 + a];
-                        const int v0 = cg.var[0], v1 = cg.var[1], v2 = (NDIM == 3) ? cg.var[2] : 0;
-                        const int L0 = lom[(m * NDIM + 0) * 2 + v0];
-                        const int L1 = lom[(m * NDIM + 1) * 2 + v1];
-                        const int L2 = (NDIM == 3) ? lom[(m * NDIM + (NDIM - 1)) * 2 + v2] : 0;
-                        // whole marker clipped away along some dimension?  (warp-uniform)
-                        if ((L0 >> 16) == 0 || (L1 >> 16) == 0 || ((NDIM == 3) && (L2 >> 16) == 0)) continue;
-                        const double f = fs[m * SPREAD_MAXC + a];
-                        const double* w0 = &wgt[((m * NDIM + 0) * 2 + v0) * W];
-                        const double* w1 = &wgt[((m * NDIM + 1) * 2 + v1) * W];
-                        const double* w2 = &wgt[((m * NDIM + (NDIM - 1)) * 2 + v2) * W];
-                        const int x0 = (int)(short)(L0 & 0xFFFF), y0 = (int)(short)(L1 & 0xFFFF),
-                                  z0 = (NDIM == 3) ? (int)(short)(L2 & 0xFFFF) : 0;
-                        double* acc_a = acc + a * TILE_PTS;
+                    const double* wm = wgt + m * (NDIM * 2 * W);
 #pragma unroll
-                        for (int s = 0; s < NSLOT; ++s)
+                    for (int a = 0; a < SPREAD_MAXC; ++a)
+                    {
+                        if (a >= ncomp) break;
+                        const int2 r = *reinterpret_cast<const int2*>(&rec[(m * SPREAD_MAXC + a) * 2]);
+                        if (r.x >= 0) continue; // nothing of this marker lands in the tile (warp-uniform)
+                        double* acc_a = acc + a * TILE_PTS;
+                        const int rot = (r.x >> 24) & 15;
+                        if constexpr (FAST4)
                         {
-                            if (NPTS % 32 != 0 && lane + 32 * s >= NPTS) continue;
-                            bool ok = ((L0 >> (16 + pix[s])) & 1) && ((L1 >> (16 + piy[s])) & 1);
-                            if (NDIM == 3) ok = ok && ((L2 >> (16 + piz[s])) & 1);
-                            if (ok)
+                            // lane = (ix, iy) = l15, z points 2*half and 2*half + 1
+                            const int idx = r.y + (half << 9) + ((l15 >> 2) << 4) + ((rot + l15) & 15);
+                            const double wxy = wm[wo0[a] + (l15 & 3)] * wm[wo1[a] + (l15 >> 2)];
+                            const double2 wz = *reinterpret_cast<const double2*>(&wlf[(m * SPREAD_MAXC + a) * W + 2 * half]);
+                            const bool okxy = (r.x >> l15) & 1;
+                            const bool ok0 = okxy && ((r.x >> (16 + 2 * half)) & 1);
+                            const bool ok1 = okxy && ((r.x >> (17 + 2 * half)) & 1);
+                            if (ok0) acc_a[idx] += wxy * wz.x;
+                            if (ok1) acc_a[idx + 256] += wxy * wz.y;
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int s = 0; s < NSLOT; ++s)
                             {
-                                double wv = w0[pix[s]] * w1[piy[s]];
-                                if (NDIM == 3) wv *= w2[piz[s]];
-                                const int idx = acc_index<NDIM>(x0 + pix[s], y0 + piy[s], z0 + piz[s]);
-                                acc_a[idx] += wv * f;
+                                const bool active = (NPTS % 32 == 0) || (lane + 32 * s < NPTS);
+                                if (!active) continue;
+                                bool ok = ((r.x >> pix[s]) & (r.x >> (8 + piy[s])) & 1) != 0;
+                                double wv = wm[wo0[a] + pix[s]];
+                                int idx = r.y + (piy[s] << 4) + ((rot + pix[s] + 4 * piy[s]) & 15);
+                                if constexpr (NDIM == 3)
+                                {
+                                    ok = ok && ((r.x >> (16 + piz[s])) & 1);
+                                    wv *= wm[wo1[a] + piy[s]] * wlf[(m * SPREAD_MAXC + a) * W + piz[s]];
+                                    idx += piz[s] << 8;
+                                }
+                                else
+                                {
+                                    wv *= wlf[(m * SPREAD_MAXC + a) * W + piy[s]];
+                                }
+                                if (ok) acc_a[idx] += wv;
                             }
                         }
                     }
@@ -258,23 +349,38 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
     }
 
     // ---- write-out: f += tile (coalesced along x), dropping points outside the array ----
-    for (int a = 0; a < args.ncomp; ++a)
+    for (int a = 0; a < ncomp; ++a)
     {
         const CompGeom& cg = tp.comp[args.comp0 + a];
         const double* acc_a = acc + a * TILE_PTS;
-        for (int q = threadIdx.x; q < TILE_PTS; q += SPREAD_THREADS)
+        const int x = threadIdx.x & 15, y0t = threadIdx.x >> 4; // 16 rows of 16 points per pass
+        const int gi = tlo[0] + x - cg.pp0[0];
+        const bool okx = gi >= 0 && gi < cg.n[0];
+        constexpr int ROWS = (NDIM == 3) ? TILE * TILE : TILE; // rows (y, z) in the tile
+        constexpr int PASSES = ROWS / (SPREAD_THREADS / 16);
+#pragma unroll
+        for (int r0 = 0; r0 < PASSES; r0 += 8)
         {
-            const int x = q & 15, y = (q >> 4) & 15, z = (NDIM == 3) ? q >> 8 : 0;
-            const int gi = tlo[0] + x - cg.pp0[0], gj = tlo[1] + y - cg.pp0[1], gk = (NDIM == 3) ? tlo[2] + z - cg.pp0[2] : 0;
-            if (gi >= 0 && gi < cg.n[0] && gj >= 0 && gj < cg.n[1] && gk >= 0 && gk < cg.n[2])
+            double vals[8], old[8];
+            double* ptrs[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
             {
+                ptrs[r] = nullptr;
+                if (r0 + r >= PASSES) continue;
+                const int row = y0t + (r0 + r) * (SPREAD_THREADS / 16);
+                const int y = row & 15, z = (NDIM == 3) ? row >> 4 : 0;
+                const int gj = tlo[1] + y - cg.pp0[1], gk = (NDIM == 3) ? tlo[2] + z - cg.pp0[2] : 0;
                 const double v = acc_a[acc_index<NDIM>(x, y, z)];
-                if (v != 0.0)
-                {
-                    double* p = cg.ptr + ((long long)gk * cg.n[1] + gj) * cg.pitch + gi;
-                    *p += v;
-                }
+                const bool ok = okx && gj >= 0 && gj < cg.n[1] && gk >= 0 && gk < cg.n[2] && v != 0.0;
+                ptrs[r] = ok ? cg.ptr + ((long long)gk * cg.n[1] + gj) * cg.pitch + gi : nullptr;
+                vals[r] = v;
             }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) old[r] = ptrs[r] ? *ptrs[r] : 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (ptrs[r]) *ptrs[r] = old[r] + vals[r];
         }
     }
 }
@@ -424,8 +530,10 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
         args.comp0 = c0;
         args.ncomp = (tp.ncomp - c0 < SPREAD_MAXC) ? tp.ncomp - c0 : SPREAD_MAXC;
         const size_t smem = sizeof(double) * ((size_t)args.ncomp * TILE_PTS + SPREAD_WARPS * SPREAD_BATCH * NDIM * 2 * W +
-                                              SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC) +
-                            sizeof(int) * (SPREAD_WARPS * SPREAD_BATCH * NDIM * 2 + 2 * NBRICKS);
+                                              SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * W) +
+                            sizeof(int) * (SPREAD_WARPS * SPREAD_BATCH * NDIM * 2 + SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * 2 +
+                                           2 * NBRICKS) +
+                            ((NBRICKS + 15) / 16) * 16;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
         {
