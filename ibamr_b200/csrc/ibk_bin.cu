@@ -275,7 +275,22 @@ cudaError_t bins_build(Bins& b, Launcher& L, const CellGeom& cg, const PatchBin*
     brick_offsets_kernel<<<(n_entries + 1 + T - 1) / T, T, 0, L.stream>>>(b.keys[b.sorted_in], n_entries, tie_bits + cshift,
                                                                          total_bricks, b.brick_start);
     L.launches++;
-    return cudaGetLastError();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // marker range of every patch (its bricks are one contiguous id range)
+    b.range_base.assign(n_patches, 0);
+    b.range_first.assign(n_patches, 0);
+    b.range_last.assign(n_patches, 0);
+    for (int p = 0; p < n_patches; ++p)
+    {
+        b.range_base[p] = h_patches[p].brick_base;
+        if ((e = cudaMemcpyAsync(&b.range_first[p], b.brick_start + h_patches[p].brick_base, sizeof(int), cudaMemcpyDeviceToHost,
+                                 L.stream)) != cudaSuccess)
+            return e;
+        if ((e = cudaMemcpyAsync(&b.range_last[p], b.brick_start + h_patches[p].brick_base + h_patches[p].nbricks, sizeof(int),
+                                 cudaMemcpyDeviceToHost, L.stream)) != cudaSuccess)
+            return e;
+    }
+    return cudaStreamSynchronize(L.stream);
 }
 
 cudaError_t wrap_positions(Launcher& L, const DomainGeom& dg, double* d_X, long long x_stride, int n, int* d_escaped)

@@ -58,6 +58,9 @@ struct Bins
     size_t sort_temp_bytes = 0;
     int capacity = 0;
     int brick_capacity = 0;
+    // per patch (keyed by its first brick id): sorted positions [first, last) of its markers, read
+    // back once per binning so that launches need no device->host round trip
+    std::vector<int> range_base, range_first, range_last;
 };
 
 struct Launcher

@@ -7,20 +7,22 @@
 // the per-axis loop of LEInteractor (LEInteractor.cpp:3676-3711).  The reference is serial over
 // markers, so it has no write conflicts; here the work is organised so that none can occur:
 //
-//  * OWNER-COMPUTES TILES.  One CTA owns a 16^ndim block of grid points of every component and is
-//    the only writer of those points: it accumulates in shared memory and finishes with one
-//    coalesced `f += tile` pass (the contract of LDataManager::spread, LDataManager.cpp:662-663).
-//    The CTA visits every marker whose stencil can reach its points: the markers binned in the
-//    (16 + 2M)^ndim cells around the tile, i.e. NBR^ndim bricks of 4^ndim cells, each a contiguous
-//    segment of the sorted marker storage.  Stencils are clipped to the tile.
+//  * STENCIL RECORDS (spread_records_kernel).  One thread per (marker, dimension, x_lower variant)
+//    evaluates the stencil origin and the 1-D weights once per marker and stores them, with the
+//    scaled force, as one 16-byte-aligned record per marker in sorted-marker order.  The sqrt/div
+//    chains run at full occupancy here instead of inside the latency-critical tile kernel.
+//  * OWNER-COMPUTES TILES (spread_tile_kernel).  One CTA owns a 16^ndim block of grid points of
+//    every component and is the only writer of those points: it accumulates in shared memory and
+//    finishes with one coalesced `f += tile` pass (the contract of LDataManager::spread,
+//    LDataManager.cpp:662-663).  The CTA visits every marker whose stencil can reach its points: the
+//    markers binned in the (16 + 2M)^ndim cells around the tile, i.e. NBR^ndim bricks of 4^ndim
+//    cells, each a contiguous run of records.  Stencils are clipped to the tile.
 //  * BRICK COLOURING.  Inside the CTA one warp takes one brick at a time and walks its markers in
 //    storage order; the 32 lanes cover the stencil points.  Two bricks whose index differs by a
 //    multiple of NC in every dimension have disjoint footprints (4*NC >= 4 + 2M), so the CTA runs
 //    NC^ndim phases separated by __syncthreads and inside a phase no two warps touch the same
 //    shared-memory word.  The summation order at every grid point is therefore fixed by the
 //    sorted marker order alone: results are bit-reproducible run to run.
-//  * Stencil weights are evaluated lane-per-(marker, dimension) for a batch of 8 markers and
-//    parked in a small per-warp scratch, so the sqrt/div work is not repeated by the 32 lanes.
 //
 // Contributions to points farther than M cells from the marker's binning cell (possible only if
 // binning cell and stencil origin disagree by a rounding) are excluded here by the margin mask and
@@ -36,13 +38,24 @@ namespace ibk
 {
 constexpr int SPREAD_THREADS = 256;
 constexpr int SPREAD_WARPS = SPREAD_THREADS / 32;
-constexpr int SPREAD_BATCH = 4; // markers per phase-A batch (per warp)
+constexpr int SPREAD_BATCH = 4; // markers per batch (per warp)
 constexpr int SPREAD_MAXC = 3;  // components accumulated per launch
+constexpr int REC_INTS = 10;    // lo[d][v] (6), binning cell cc[d] (3), spare
+
+// doubles per marker record: weights [d][v][j], scaled force per component, integer section
+template <int NDIM, int W>
+struct RecLayout
+{
+    static constexpr int WGT = NDIM * 2 * W;
+    static constexpr int FRC = WGT;
+    static constexpr int INTS = WGT + SPREAD_MAXC; // offset (in doubles) of the integer section
+    static constexpr int DOUBLES = ((INTS + REC_INTS / 2) + 1) / 2 * 2;
+};
 
 struct SpreadArgs
 {
     const int* brick_start;
-    const uint64_t* keys; // sorted keys (cell-in-brick bits)
+    const uint64_t* keys; // sorted keys (brick id, cell-in-brick bits)
     int tie_bits;
     const double* X;
     const double* Xraw;
@@ -52,6 +65,8 @@ struct SpreadArgs
     const uint32_t* src;
     int comp0; // first component handled by this launch
     int ncomp; // number of components handled by this launch (<= SPREAD_MAXC)
+    double* records; // [n_entries][RecLayout::DOUBLES]
+    int first, last; // sorted positions of this patch's markers
     // exceptions (stencil beyond the margin box): appended here, processed by spread_fixup_kernel
     int* exc_count;
     int* exc_list;
@@ -72,11 +87,91 @@ __device__ __forceinline__ int acc_index(int x, int y, int z)
         return (y << 4) + xs;
 }
 
+// brick coordinates from the hierarchical brick id (tile-major, then brick-in-tile)
+template <int NDIM>
+__device__ __forceinline__ void brick_coords(int brick, const int* nt, int* gb)
+{
+    if constexpr (NDIM == 3)
+    {
+        const int tile = brick >> 6;
+        const int tx = tile % nt[0], ty = (tile / nt[0]) % nt[1], tz = tile / (nt[0] * nt[1]);
+        gb[0] = 4 * tx + (brick & 3);
+        gb[1] = 4 * ty + ((brick >> 2) & 3);
+        gb[2] = 4 * tz + ((brick >> 4) & 3);
+    }
+    else
+    {
+        const int tile = brick >> 4;
+        const int tx = tile % nt[0], ty = tile / nt[0];
+        gb[0] = 4 * tx + (brick & 3);
+        gb[1] = 4 * ty + ((brick >> 2) & 3);
+        gb[2] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 1: stencil records, one thread per (marker, dimension, variant)
+// ---------------------------------------------------------------------------------------------
+template <int NDIM, int K>
+__global__ void __launch_bounds__(256) spread_records_kernel(const __grid_constant__ TileParams tp, SpreadArgs args)
+{
+    constexpr int W = KTraits<K>::W;
+    constexpr int M = KTraits<K>::M;
+    using RL = RecLayout<NDIM, W>;
+    constexpr int TASKS = NDIM * 2;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = args.first + (int)(gid / TASKS);
+    const int t = (int)(gid % TASKS);
+    if (i >= args.last) return;
+    const int d = t >> 1, v = t & 1;
+    double* rec = args.records + (long long)i * RL::DOUBLES;
+    int* ri = reinterpret_cast<int*>(rec + RL::INTS);
+    const unsigned long long key = __ldg(&args.keys[i]);
+    int gb[3];
+    brick_coords<NDIM>((int)(key >> (args.tie_bits + 2 * NDIM)) - tp.brick_base, tp.nt, gb);
+    const int cc = BRICK * gb[d] + (int)((key >> (args.tie_bits + 2 * d)) & 3ull); // binning cell (pp)
+    if (v < tp.nvar[d])
+    {
+        const double xs = __ldg(&args.X[d * args.x_stride + i]);
+        const double xr = args.Xraw ? __ldg(&args.Xraw[d * args.x_stride + i]) : xs;
+        double w[W];
+        int l;
+        stencil_1d<K>(xs, xr, tp.xl[d][v], tp.dx[d], l, w);
+        const int lo_pp = l + tp.G;
+#pragma unroll
+        for (int j = 0; j < W; ++j) rec[(d * 2 + v) * W + j] = w[j];
+        ri[d * 2 + v] = lo_pp;
+        if ((lo_pp < cc - M || lo_pp + W - 1 > cc + M) && args.exc_list)
+        {
+            const int slot = atomicAdd(args.exc_count, 1);
+            if (slot < args.exc_capacity) args.exc_list[slot] = i;
+        }
+    }
+    else
+    {
+        ri[d * 2 + v] = -(1 << 20);
+    }
+    if (v == 0) ri[6 + d] = cc;
+    if (t == 0)
+    {
+        const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
+        for (int a = 0; a < SPREAD_MAXC; ++a)
+            rec[RL::FRC + a] = (a < args.ncomp) ? __ldg(&args.V[tp.comp[args.comp0 + a].vcol * args.v_cstride + row * args.v_istride]) * tp.inv_vol : 0.0;
+        if (NDIM == 2) ri[8] = 0;
+        ri[9] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 2: owner-computes tiles
+// ---------------------------------------------------------------------------------------------
 template <int NDIM, int K>
 __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __grid_constant__ TileParams tp, SpreadArgs args)
 {
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
+    using RL = RecLayout<NDIM, W>;
+    constexpr int RECD = RL::DOUBLES;
     constexpr int NBR = TILE_BRICKS + (2 * M + BRICK - 1) / BRICK; // bricks per dimension around the tile
     constexpr int NC = (BRICK + 2 * M + BRICK - 1) / BRICK;        // colours per dimension
     constexpr int NPTS = (NDIM == 3) ? W * W * W : W * W;
@@ -86,24 +181,21 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
     constexpr int NCOL = (NDIM == 3) ? NC * NC * NC : NC * NC;
     constexpr bool FAST4 = (NDIM == 3) && (W == 4); // lane = (ix, iy, half): two adjacent z points per lane
     constexpr int LD = NDIM - 1;                    // the "last" dimension carries the force factor
-    constexpr int NTASK = SPREAD_BATCH * NDIM * 2;  // phase-A tasks per batch: (marker, dimension, variant)
-    static_assert(NTASK <= 32, "one phase-A round per batch");
+    constexpr int PF = (SPREAD_BATCH * RECD / 2 + 31) / 32; // 16-byte words per lane per batch
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* acc = reinterpret_cast<double*>(smem_raw);                          // [ncomp][TILE_PTS]
-    double* wgt_all = acc + (size_t)args.ncomp * TILE_PTS;                      // [warp][BATCH][NDIM][2][W]
-    double* wlf_all = wgt_all + SPREAD_WARPS * SPREAD_BATCH * NDIM * 2 * W;     // [warp][BATCH][MAXC][W]  last-dim weights * force
-    int* lom_all = reinterpret_cast<int*>(wlf_all + SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * W); // [warp][BATCH][NDIM][2]
-    int* rec_all = lom_all + SPREAD_WARPS * SPREAD_BATCH * NDIM * 2;            // [warp][BATCH][MAXC][2]
+    double* rbuf_all = acc + (size_t)args.ncomp * TILE_PTS;                     // [warp][BATCH][RECD] marker records
+    double* wlf_all = rbuf_all + SPREAD_WARPS * SPREAD_BATCH * RECD;            // [warp][BATCH][MAXC][W]  last-dim weights * force
+    int* rec_all = reinterpret_cast<int*>(wlf_all + SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * W); // [warp][BATCH][MAXC][2]
     int* brng = rec_all + SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * 2;        // [NBRICKS][2]
     unsigned char* order = reinterpret_cast<unsigned char*>(brng + 2 * NBRICKS); // [NBRICKS] bricks sorted by colour
     __shared__ int any_markers;
     __shared__ int col_start[NCOL + 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* wgt = wgt_all + warp * (SPREAD_BATCH * NDIM * 2 * W);
+    double* rbuf = rbuf_all + warp * (SPREAD_BATCH * RECD);
     double* wlf = wlf_all + warp * (SPREAD_BATCH * SPREAD_MAXC * W);
-    int* lom = lom_all + warp * (SPREAD_BATCH * NDIM * 2);
     int* rec = rec_all + warp * (SPREAD_BATCH * SPREAD_MAXC * 2);
 
     // which output tile
@@ -143,14 +235,14 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
             s = args.brick_start[id];
             e = args.brick_start[id + 1];
         }
-        brng[2 * q] = s;
-        brng[2 * q + 1] = e;
-        if (e > s) any_markers = 1;
         const int c0 = lx % NC, c1 = ly % NC, c2 = lz % NC;
         const int col = (c2 * NC + c1) * NC + c0;
         const int n0 = (NBR - c0 + NC - 1) / NC, n1 = (NBR - c1 + NC - 1) / NC;
-        const int pos = ((lz / NC) * n1 + ly / NC) * n0 + lx / NC;
-        order[col_start[col] + pos] = (unsigned char)q;
+        const int pos = col_start[col] + ((lz / NC) * n1 + ly / NC) * n0 + lx / NC;
+        brng[2 * pos] = s; // stored in colour order
+        brng[2 * pos + 1] = e;
+        order[pos] = (unsigned char)q;
+        if (e > s) any_markers = 1;
     }
     __syncthreads();
     if (!any_markers) return;
@@ -158,23 +250,16 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
     for (int q = threadIdx.x; q < args.ncomp * TILE_PTS; q += SPREAD_THREADS) acc[q] = 0.0;
 
     const int ncomp = args.ncomp;
-    const double inv_vol = tp.inv_vol;
-    const int G = tp.G;
-    // phase-A role of this lane: (marker, dimension, variant) and, for A2, (marker, component)
-    const int a_m = lane / (NDIM * 2), a_d = (lane >> 1) % NDIM, a_v = lane & 1;
-    const bool a_on = lane < NTASK && a_v < tp.nvar[a_d];
-    const double a_xl = tp.xl[a_d][a_v], a_dx = tp.dx[a_d];
-    const int a_tlo = tlo[a_d];
+    // A2 role of this lane: (marker, component)
     const int b_m = lane / SPREAD_MAXC, b_a = lane % SPREAD_MAXC;
     const bool b_on = lane < SPREAD_BATCH * SPREAD_MAXC && b_a < ncomp;
-    int b_v[3] = { 0, 0, 0 }, b_vcol = 0;
+    int b_v[3] = { 0, 0, 0 };
     if (b_on)
     {
         const CompGeom& cg = tp.comp[args.comp0 + b_a];
         b_v[0] = cg.var[0];
         b_v[1] = cg.var[1];
         b_v[2] = cg.var[2];
-        b_vcol = cg.vcol;
     }
     // phase-B role: weight offsets of each component (which x_lower variant per dimension)
     int wo0[SPREAD_MAXC], wo1[SPREAD_MAXC];
@@ -185,7 +270,6 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
         wo0[a] = (0 * 2 + cg.var[0]) * W;
         wo1[a] = (1 * 2 + cg.var[1]) * W;
     }
-    // per-lane stencil point(s)
     const int l15 = lane & 15, half = lane >> 4;
     int pix[NSLOT], piy[NSLOT], piz[NSLOT];
 #pragma unroll
@@ -196,154 +280,155 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
         piy[s] = (q / W) % W;
         piz[s] = (NDIM == 3) ? q / (W * W) : 0;
     }
+    const double2* recs2 = reinterpret_cast<const double2*>(args.records);
     __syncthreads();
 
     for (int col = 0; col < NCOL; ++col)
     {
-        const int cbeg = col_start[col], cend = col_start[col + 1];
-        for (int bi = cbeg + warp; bi < cend; bi += SPREAD_WARPS)
+        const int cend = col_start[col + 1];
+        // this warp's bricks of the colour: cbeg + warp, + 8, ...; skip the empty ones
+        int bi = col_start[col] + warp;
+        int bs = 0, be = 0;
+        while (bi < cend)
         {
-            const int q = order[bi];
-            const int bs = brng[2 * q], be = brng[2 * q + 1];
-            if (bs >= be) continue;
-            const int lx = q % NBR, ly = (q / NBR) % NBR, lz = (NDIM == 3) ? q / (NBR * NBR) : 0;
-            const int gb[3] = { TILE_BRICKS * ot[0] + lx, TILE_BRICKS * ot[1] + ly, TILE_BRICKS * ot[2] + lz };
-            const int a_gb = BRICK * gb[a_d];
-            for (int batch = bs; batch < be; batch += SPREAD_BATCH)
+            bs = brng[2 * bi];
+            be = brng[2 * bi + 1];
+            if (be > bs) break;
+            bi += SPREAD_WARPS;
+        }
+        double2 pre[PF];
+        int batch = bs;
+        if (bi < cend)
+        {
+            const int nv = min(SPREAD_BATCH, be - batch) * (RECD / 2);
+            const double2* src = recs2 + (long long)batch * (RECD / 2);
+#pragma unroll
+            for (int p = 0; p < PF; ++p)
+                if (lane + 32 * p < nv) pre[p] = __ldg(&src[lane + 32 * p]);
+        }
+        while (bi < cend)
+        {
+            const int nb = min(SPREAD_BATCH, be - batch);
             {
-                const int nb = min(SPREAD_BATCH, be - batch);
-                // ---- phase A1: one lane per (marker, dimension, variant): stencil origin, weights, masks ----
-                if (a_on && a_m < nb)
-                {
-                    const int i = batch + a_m;
-                    const double xs = __ldg(&args.X[a_d * args.x_stride + i]);
-                    const double xr = args.Xraw ? __ldg(&args.Xraw[a_d * args.x_stride + i]) : xs;
-                    const unsigned long long key = __ldg(&args.keys[i]);
-                    const int cc = a_gb + (int)((key >> (args.tie_bits + 2 * a_d)) & 3ull); // binning cell (pp)
-                    double w[W];
-                    int l;
-                    stencil_1d<K>(xs, xr, a_xl, a_dx, l, w);
-                    const int lo_pp = l + G;
-                    unsigned mask = 0;
-                    bool beyond = false;
+                const int nv = nb * (RECD / 2);
+                double2* dst = reinterpret_cast<double2*>(rbuf);
 #pragma unroll
-                    for (int j = 0; j < W; ++j)
-                    {
-                        const int pp = lo_pp + j;
-                        const bool in_margin = (pp >= cc - M) && (pp <= cc + M);
-                        beyond = beyond || !in_margin;
-                        if (in_margin && pp >= a_tlo && pp < a_tlo + TILE) mask |= (1u << j);
-                        wgt[((a_m * NDIM + a_d) * 2 + a_v) * W + j] = w[j];
-                    }
-                    lom[(a_m * NDIM + a_d) * 2 + a_v] = ((lo_pp - a_tlo) & 0xFFFF) | (mask << 16);
-                    if (beyond && args.exc_list)
-                    {
-                        // recorded by the CTA whose tile holds the marker's cell (the fix-up kernel re-derives
-                        // everything and removes duplicates)
-                        bool mine = true;
+                for (int p = 0; p < PF; ++p)
+                    if (lane + 32 * p < nv) dst[lane + 32 * p] = pre[p];
+            }
+            __syncwarp();
+            // next batch of this warp (same brick, or the next non-empty brick of the colour): prefetch its records
+            int nbatch = batch + SPREAD_BATCH, nbi = bi, nbe = be;
+            if (nbatch >= be)
+            {
+                nbi = bi + SPREAD_WARPS;
+                while (nbi < cend)
+                {
+                    nbatch = brng[2 * nbi];
+                    nbe = brng[2 * nbi + 1];
+                    if (nbe > nbatch) break;
+                    nbi += SPREAD_WARPS;
+                }
+            }
+            if (nbi < cend)
+            {
+                const int nv = min(SPREAD_BATCH, nbe - nbatch) * (RECD / 2);
+                const double2* src = recs2 + (long long)nbatch * (RECD / 2);
 #pragma unroll
-                        for (int dd = 0; dd < NDIM; ++dd)
-                        {
-                            const int ccd = BRICK * gb[dd] + (int)((key >> (args.tie_bits + 2 * dd)) & 3ull);
-                            mine = mine && ccd >= tlo[dd] && ccd < tlo[dd] + TILE;
-                        }
-                        if (mine)
-                        {
-                            const int slot = atomicAdd(args.exc_count, 1);
-                            if (slot < args.exc_capacity) args.exc_list[slot] = i;
-                        }
-                    }
-                }
-                // the force value of (marker, component) is fetched while A1 computes
-                double b_f = 0.0;
-                if (b_on && b_m < nb)
+                for (int p = 0; p < PF; ++p)
+                    if (lane + 32 * p < nv) pre[p] = __ldg(&src[lane + 32 * p]);
+            }
+            // ---- A2: one lane per (marker, component): packed record + last-dim weights * force ----
+            if (b_on && b_m < nb)
+            {
+                const double* rm = rbuf + b_m * RECD;
+                const int* ri = reinterpret_cast<const int*>(rm + RL::INTS);
+                int o[3] = { 0, 0, 0 };
+                unsigned mk[3] = { 1u, 1u, 1u };
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d)
                 {
-                    const int i = batch + b_m;
-                    const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
-                    b_f = __ldg(&args.V[b_vcol * args.v_cstride + row * args.v_istride]) * inv_vol;
+                    const int lo = ri[d * 2 + b_v[d]], cc = ri[6 + d];
+                    const int jlo = max(max(cc - M, tlo[d]) - lo, 0);
+                    const int jhi = min(min(cc + M, tlo[d] + TILE - 1) - lo, W - 1);
+                    mk[d] = (jhi >= jlo) ? (((1u << (jhi + 1)) - 1u) & ~((1u << jlo) - 1u)) : 0u;
+                    o[d] = lo - tlo[d];
                 }
-                __syncwarp();
-                // ---- phase A2: one lane per (marker, component): packed record + last-dim weights * force ----
-                if (b_on && b_m < nb)
+                unsigned w0r;
+                if constexpr (FAST4)
                 {
-                    const int L0 = lom[(b_m * NDIM + 0) * 2 + b_v[0]];
-                    const int L1 = lom[(b_m * NDIM + 1) * 2 + b_v[1]];
-                    const int L2 = (NDIM == 3) ? lom[(b_m * NDIM + LD) * 2 + b_v[LD]] : (1 << 16);
-                    const int x0 = (int)(short)(L0 & 0xFFFF), y0 = (int)(short)(L1 & 0xFFFF),
-                              z0 = (NDIM == 3) ? (int)(short)(L2 & 0xFFFF) : 0;
-                    const unsigned mx = (unsigned)L0 >> 16, my = (unsigned)L1 >> 16, mz = (unsigned)L2 >> 16;
-                    unsigned w0r;
+                    unsigned mxy = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mxy |= ((mk[1] >> j) & 1u) ? (mk[0] << (4 * j)) : 0u;
+                    w0r = mxy | (mk[2] << 16);
+                }
+                else
+                {
+                    w0r = mk[0] | (mk[1] << 8) | (mk[2] << 16);
+                }
+                const bool empty = (mk[0] == 0) || (mk[1] == 0) || (mk[2] == 0);
+                w0r = empty ? 0u : (w0r | ((unsigned)((o[0] + 4 * o[1]) & 15) << 24) | 0x80000000u);
+                rec[(b_m * SPREAD_MAXC + b_a) * 2 + 0] = (int)w0r;
+                rec[(b_m * SPREAD_MAXC + b_a) * 2 + 1] = (NDIM == 3) ? (o[2] * 256 + o[1] * 16) : (o[1] * 16);
+                const double f = rm[RL::FRC + b_a];
+                const double* wl = rm + (LD * 2 + b_v[LD]) * W;
+#pragma unroll
+                for (int j = 0; j < W; ++j) wlf[(b_m * SPREAD_MAXC + b_a) * W + j] = wl[j] * f;
+            }
+            __syncwarp();
+            // ---- phase B: markers one after another, lanes over the stencil points ----
+            for (int m = 0; m < nb; ++m)
+            {
+                const double* wm = rbuf + m * RECD;
+#pragma unroll
+                for (int a = 0; a < SPREAD_MAXC; ++a)
+                {
+                    if (a >= ncomp) break;
+                    const int2 r = *reinterpret_cast<const int2*>(&rec[(m * SPREAD_MAXC + a) * 2]);
+                    if (r.x >= 0) continue; // nothing of this marker lands in the tile (warp-uniform)
+                    double* acc_a = acc + a * TILE_PTS;
+                    const int rot = (r.x >> 24) & 15;
                     if constexpr (FAST4)
                     {
-                        unsigned mxy = 0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) mxy |= ((my >> j) & 1u) ? (mx << (4 * j)) : 0u;
-                        w0r = mxy | (mz << 16);
+                        // lane = (ix, iy) = l15, z points 2*half and 2*half + 1
+                        const int idx = r.y + (half << 9) + ((l15 >> 2) << 4) + ((rot + l15) & 15);
+                        const double wxy = wm[wo0[a] + (l15 & 3)] * wm[wo1[a] + (l15 >> 2)];
+                        const double2 wz = *reinterpret_cast<const double2*>(&wlf[(m * SPREAD_MAXC + a) * W + 2 * half]);
+                        const bool okxy = (r.x >> l15) & 1;
+                        const bool ok0 = okxy && ((r.x >> (16 + 2 * half)) & 1);
+                        const bool ok1 = okxy && ((r.x >> (17 + 2 * half)) & 1);
+                        if (ok0) acc_a[idx] += wxy * wz.x;
+                        if (ok1) acc_a[idx + 256] += wxy * wz.y;
                     }
                     else
                     {
-                        w0r = mx | (my << 8) | (mz << 16);
-                    }
-                    const bool empty = (mx == 0) || (my == 0) || (mz == 0);
-                    w0r = empty ? 0u : (w0r | ((unsigned)((x0 + 4 * y0) & 15) << 24) | 0x80000000u);
-                    rec[(b_m * SPREAD_MAXC + b_a) * 2 + 0] = (int)w0r;
-                    rec[(b_m * SPREAD_MAXC + b_a) * 2 + 1] = (NDIM == 3) ? (z0 * 256 + y0 * 16) : (y0 * 16);
-                    const double* wl = &wgt[((b_m * NDIM + LD) * 2 + b_v[LD]) * W];
 #pragma unroll
-                    for (int j = 0; j < W; ++j) wlf[(b_m * SPREAD_MAXC + b_a) * W + j] = wl[j] * b_f;
+                        for (int s = 0; s < NSLOT; ++s)
+                        {
+                            const bool active = (NPTS % 32 == 0) || (lane + 32 * s < NPTS);
+                            if (!active) continue;
+                            bool ok = ((r.x >> pix[s]) & (r.x >> (8 + piy[s])) & 1) != 0;
+                            double wv = wm[wo0[a] + pix[s]];
+                            int idx = r.y + (piy[s] << 4) + ((rot + pix[s] + 4 * piy[s]) & 15);
+                            if constexpr (NDIM == 3)
+                            {
+                                ok = ok && ((r.x >> (16 + piz[s])) & 1);
+                                wv *= wm[wo1[a] + piy[s]] * wlf[(m * SPREAD_MAXC + a) * W + piz[s]];
+                                idx += piz[s] << 8;
+                            }
+                            else
+                            {
+                                wv *= wlf[(m * SPREAD_MAXC + a) * W + piy[s]];
+                            }
+                            if (ok) acc_a[idx] += wv;
+                        }
+                    }
                 }
                 __syncwarp();
-                // ---- phase B: markers one after another, lanes over the stencil points ----
-                for (int m = 0; m < nb; ++m)
-                {
-                    const double* wm = wgt + m * (NDIM * 2 * W);
-#pragma unroll
-                    for (int a = 0; a < SPREAD_MAXC; ++a)
-                    {
-                        if (a >= ncomp) break;
-                        const int2 r = *reinterpret_cast<const int2*>(&rec[(m * SPREAD_MAXC + a) * 2]);
-                        if (r.x >= 0) continue; // nothing of this marker lands in the tile (warp-uniform)
-                        double* acc_a = acc + a * TILE_PTS;
-                        const int rot = (r.x >> 24) & 15;
-                        if constexpr (FAST4)
-                        {
-                            // lane = (ix, iy) = l15, z points 2*half and 2*half + 1
-                            const int idx = r.y + (half << 9) + ((l15 >> 2) << 4) + ((rot + l15) & 15);
-                            const double wxy = wm[wo0[a] + (l15 & 3)] * wm[wo1[a] + (l15 >> 2)];
-                            const double2 wz = *reinterpret_cast<const double2*>(&wlf[(m * SPREAD_MAXC + a) * W + 2 * half]);
-                            const bool okxy = (r.x >> l15) & 1;
-                            const bool ok0 = okxy && ((r.x >> (16 + 2 * half)) & 1);
-                            const bool ok1 = okxy && ((r.x >> (17 + 2 * half)) & 1);
-                            if (ok0) acc_a[idx] += wxy * wz.x;
-                            if (ok1) acc_a[idx + 256] += wxy * wz.y;
-                        }
-                        else
-                        {
-#pragma unroll
-                            for (int s = 0; s < NSLOT; ++s)
-                            {
-                                const bool active = (NPTS % 32 == 0) || (lane + 32 * s < NPTS);
-                                if (!active) continue;
-                                bool ok = ((r.x >> pix[s]) & (r.x >> (8 + piy[s])) & 1) != 0;
-                                double wv = wm[wo0[a] + pix[s]];
-                                int idx = r.y + (piy[s] << 4) + ((rot + pix[s] + 4 * piy[s]) & 15);
-                                if constexpr (NDIM == 3)
-                                {
-                                    ok = ok && ((r.x >> (16 + piz[s])) & 1);
-                                    wv *= wm[wo1[a] + piy[s]] * wlf[(m * SPREAD_MAXC + a) * W + piz[s]];
-                                    idx += piz[s] << 8;
-                                }
-                                else
-                                {
-                                    wv *= wlf[(m * SPREAD_MAXC + a) * W + piy[s]];
-                                }
-                                if (ok) acc_a[idx] += wv;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
             }
+            batch = nbatch;
+            bi = nbi;
+            be = nbe;
         }
         __syncthreads();
     }
@@ -473,12 +558,15 @@ __global__ void spread_fixup_kernel(const __grid_constant__ TileParams tp, Sprea
 // ---------------------------------------------------------------------------------------------
 static int* g_exc_buf = nullptr; // [1 + capacity] per process (device); tiny
 constexpr int EXC_CAPACITY = 4096;
+static double* g_rec_buf = nullptr; // marker records, grown on demand
+static size_t g_rec_cap = 0;
 
 template <int NDIM, int K>
 static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err)
 {
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
+    using RL = RecLayout<NDIM, W>;
     constexpr int NBR = TILE_BRICKS + (2 * M + BRICK - 1) / BRICK;
     constexpr int TILE_PTS = (NDIM == 3) ? TILE * TILE * TILE : TILE * TILE;
     constexpr int NBRICKS = (NDIM == 3) ? NBR * NBR * NBR : NBR * NBR;
@@ -486,6 +574,19 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     if (!g_exc_buf)
     {
         if ((e = cudaMalloc(&g_exc_buf, sizeof(int) * (1 + EXC_CAPACITY))) != cudaSuccess) return e;
+    }
+    const size_t need = (size_t)std::max(bins.n_entries, 1) * RL::DOUBLES * sizeof(double);
+    if (need > g_rec_cap)
+    {
+        if (g_rec_buf) cudaFree(g_rec_buf);
+        g_rec_buf = nullptr;
+        g_rec_cap = 0;
+        if ((e = cudaMalloc(&g_rec_buf, need + need / 8)) != cudaSuccess)
+        {
+            err = "cudaMalloc(marker records) failed";
+            return e;
+        }
+        g_rec_cap = need + need / 8;
     }
     if ((e = cudaMemsetAsync(g_exc_buf, 0, sizeof(int), L.stream)) != cudaSuccess) return e;
     SpreadArgs args;
@@ -499,9 +600,19 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     args.v_cstride = mv.v_cstride;
     args.v_istride = mv.v_istride;
     args.src = mv.src;
+    args.records = g_rec_buf;
     args.exc_count = g_exc_buf;
     args.exc_list = g_exc_buf + 1;
     args.exc_capacity = EXC_CAPACITY;
+    // sorted positions of this patch's markers (read back when the bins were built)
+    args.first = args.last = 0;
+    for (size_t p = 0; p < bins.range_base.size(); ++p)
+        if (bins.range_base[p] == tp.brick_base)
+        {
+            args.first = bins.range_first[p];
+            args.last = bins.range_last[p];
+        }
+    if (args.last <= args.first) return cudaSuccess;
     // output tiles: tile a covers the points pp in [16a + M, 16a + M + 16); cover every array point
     TileParams tpl = tp;
     for (int d = 0; d < 3; ++d)
@@ -523,26 +634,27 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     }
     const int ntiles = tpl.ot_n[0] * tpl.ot_n[1] * tpl.ot_n[2];
     if (ntiles <= 0) return cudaSuccess;
+    auto rfn = spread_records_kernel<NDIM, K>;
     auto kfn = spread_tile_kernel<NDIM, K>;
     auto ffn = spread_fixup_kernel<NDIM, K>;
     for (int c0 = 0; c0 < tp.ncomp; c0 += SPREAD_MAXC)
     {
         args.comp0 = c0;
         args.ncomp = (tp.ncomp - c0 < SPREAD_MAXC) ? tp.ncomp - c0 : SPREAD_MAXC;
-        const size_t smem = sizeof(double) * ((size_t)args.ncomp * TILE_PTS + SPREAD_WARPS * SPREAD_BATCH * NDIM * 2 * W +
+        const size_t smem = sizeof(double) * ((size_t)args.ncomp * TILE_PTS + SPREAD_WARPS * SPREAD_BATCH * RL::DOUBLES +
                                               SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * W) +
-                            sizeof(int) * (SPREAD_WARPS * SPREAD_BATCH * NDIM * 2 + SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * 2 +
-                                           2 * NBRICKS) +
-                            ((NBRICKS + 15) / 16) * 16;
+                            sizeof(int) * (SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * 2 + 2 * NBRICKS) + ((NBRICKS + 15) / 16) * 16;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
         {
             err = "cudaFuncSetAttribute(spread) failed";
             return e;
         }
+        const long long ntask = (long long)(args.last - args.first) * NDIM * 2;
+        rfn<<<(unsigned)((ntask + 255) / 256), 256, 0, L.stream>>>(tpl, args);
         kfn<<<ntiles, SPREAD_THREADS, smem, L.stream>>>(tpl, args);
         ffn<<<1, 32, 0, L.stream>>>(tpl, args);
-        L.launches += 2;
+        L.launches += 3;
         if (c0 + SPREAD_MAXC < tp.ncomp)
             if ((e = cudaMemsetAsync(g_exc_buf, 0, sizeof(int), L.stream)) != cudaSuccess) return e;
     }
