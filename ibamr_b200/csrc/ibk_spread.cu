@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
     unsigned char* order = reinterpret_cast<unsigned char*>(brng + 2 * NBRICKS); // [NBRICKS] bricks sorted by colour
     __shared__ int any_markers;
     __shared__ int col_start[NCOL + 1];
+    __shared__ int claim;                  // next brick (colour-major order) to hand out
+    __shared__ unsigned char done[NBRICKS]; // per brick: all its markers have been accumulated
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* rbuf = rbuf_all + warp * (SPREAD_BATCH * RECD);
@@ -242,12 +244,41 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
         brng[2 * pos] = s; // stored in colour order
         brng[2 * pos + 1] = e;
         order[pos] = (unsigned char)q;
+        done[q] = (e > s) ? 0 : 1;
         if (e > s) any_markers = 1;
     }
     __syncthreads();
     if (!any_markers) return;
 
     for (int q = threadIdx.x; q < args.ncomp * TILE_PTS; q += SPREAD_THREADS) acc[q] = 0.0;
+
+    // Everything this tile will read later -- the records of all its bricks and the f rows of the final
+    // `f += tile` -- is requested into L2 now, so that the per-colour stages and the write-out pay an
+    // L2 hit instead of a DRAM round trip each (the stages are short and latency-bound).
+    for (int q = warp; q < NBRICKS; q += SPREAD_WARPS)
+    {
+        const int s = brng[2 * q], e = brng[2 * q + 1];
+        const char* p0 = reinterpret_cast<const char*>(args.records + (long long)s * RECD);
+        const long long bytes = (long long)(e - s) * RECD * 8;
+        for (long long o = 128ll * lane; o < bytes; o += 128ll * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+    }
+    for (int a = 0; a < args.ncomp; ++a)
+    {
+        const CompGeom& cg = tp.comp[args.comp0 + a];
+        constexpr int ROWS = (NDIM == 3) ? TILE * TILE : TILE;
+        for (int row = threadIdx.x; row < ROWS; row += SPREAD_THREADS)
+        {
+            const int y = row & 15, z = (NDIM == 3) ? row >> 4 : 0;
+            const int gi = max(tlo[0] - cg.pp0[0], 0);
+            const int gj = tlo[1] + y - cg.pp0[1], gk = (NDIM == 3) ? tlo[2] + z - cg.pp0[2] : 0;
+            if (gi < cg.n[0] && gj >= 0 && gj < cg.n[1] && gk >= 0 && gk < cg.n[2])
+            {
+                const double* p0 = cg.ptr + ((long long)gk * cg.n[1] + gj) * cg.pitch + gi;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + 15)); // the 16-point row may straddle two lines
+            }
+        }
+    }
 
     const int ncomp = args.ncomp;
     // A2 role of this lane: (marker, component)
@@ -281,157 +312,176 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
         piz[s] = (NDIM == 3) ? q / (W * W) : 0;
     }
     const double2* recs2 = reinterpret_cast<const double2*>(args.records);
+    if (threadIdx.x == 0) claim = 0;
     __syncthreads();
 
-    for (int col = 0; col < NCOL; ++col)
+    // Bricks are claimed in colour-major order.  Instead of a CTA barrier between colours, a brick waits
+    // only for ITS lower-coloured neighbours (the only bricks whose footprint overlaps its own and that
+    // precede it in the fixed summation order): a flag per brick, set when its last marker is done.
+    // Claims are handed out in order, so every brick a warp waits for is already owned by a running warp.
+    while (true)
     {
-        const int cend = col_start[col + 1];
-        // this warp's bricks of the colour: cbeg + warp, + 8, ...; skip the empty ones
-        int bi = col_start[col] + warp;
-        int bs = 0, be = 0;
-        while (bi < cend)
-        {
-            bs = brng[2 * bi];
-            be = brng[2 * bi + 1];
-            if (be > bs) break;
-            bi += SPREAD_WARPS;
-        }
+        int p = 0;
+        if (lane == 0) p = atomicAdd(&claim, 1);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= NBRICKS) break;
+        const int bs = brng[2 * p], be = brng[2 * p + 1];
+        if (be <= bs) continue; // empty bricks were flagged done at set-up
+        const int q = order[p];
         double2 pre[PF];
-        int batch = bs;
-        if (bi < cend)
         {
-            const int nv = min(SPREAD_BATCH, be - batch) * (RECD / 2);
-            const double2* src = recs2 + (long long)batch * (RECD / 2);
+            const int nv = min(SPREAD_BATCH, be - bs) * (RECD / 2);
+            const double2* src = recs2 + (long long)bs * (RECD / 2);
 #pragma unroll
-            for (int p = 0; p < PF; ++p)
-                if (lane + 32 * p < nv) pre[p] = __ldg(&src[lane + 32 * p]);
+            for (int pp = 0; pp < PF; ++pp)
+                if (lane + 32 * pp < nv) pre[pp] = __ldg(&src[lane + 32 * pp]);
         }
-        while (bi < cend)
         {
-            const int nb = min(SPREAD_BATCH, be - batch);
+            const int lx = q % NBR, ly = (q / NBR) % NBR, lz = (NDIM == 3) ? q / (NBR * NBR) : 0;
+            const int mycol = ((lz % NC) * NC + ly % NC) * NC + lx % NC;
+            // neighbours whose footprint can overlap: index distance <= NC - 1 per dimension
+            constexpr int RN = 2 * (NC - 1) + 1;
+            constexpr int NNB = (NDIM == 3) ? RN * RN * RN : RN * RN;
+            const volatile unsigned char* vd = done;
+            for (int n0 = 0; n0 < NNB; n0 += 32)
             {
-                const int nv = nb * (RECD / 2);
-                double2* dst = reinterpret_cast<double2*>(rbuf);
-#pragma unroll
-                for (int p = 0; p < PF; ++p)
-                    if (lane + 32 * p < nv) dst[lane + 32 * p] = pre[p];
-            }
-            __syncwarp();
-            // next batch of this warp (same brick, or the next non-empty brick of the colour): prefetch its records
-            int nbatch = batch + SPREAD_BATCH, nbi = bi, nbe = be;
-            if (nbatch >= be)
-            {
-                nbi = bi + SPREAD_WARPS;
-                while (nbi < cend)
+                const int n = n0 + lane;
+                bool need = false;
+                int nq = 0;
+                if (n < NNB)
                 {
-                    nbatch = brng[2 * nbi];
-                    nbe = brng[2 * nbi + 1];
-                    if (nbe > nbatch) break;
-                    nbi += SPREAD_WARPS;
+                    const int nx = lx + n % RN - (NC - 1), ny = ly + (n / RN) % RN - (NC - 1),
+                              nz = (NDIM == 3) ? lz + n / (RN * RN) - (NC - 1) : 0;
+                    if (nx >= 0 && nx < NBR && ny >= 0 && ny < NBR && nz >= 0 && nz < ((NDIM == 3) ? NBR : 1))
+                    {
+                        nq = (nz * NBR + ny) * NBR + nx;
+                        need = (((nz % NC) * NC + ny % NC) * NC + nx % NC) < mycol;
+                    }
+                }
+                while (!__all_sync(0xffffffffu, !need || vd[nq] != 0))
+                {
                 }
             }
-            if (nbi < cend)
-            {
-                const int nv = min(SPREAD_BATCH, nbe - nbatch) * (RECD / 2);
-                const double2* src = recs2 + (long long)nbatch * (RECD / 2);
-#pragma unroll
-                for (int p = 0; p < PF; ++p)
-                    if (lane + 32 * p < nv) pre[p] = __ldg(&src[lane + 32 * p]);
-            }
-            // ---- A2: one lane per (marker, component): packed record + last-dim weights * force ----
-            if (b_on && b_m < nb)
-            {
-                const double* rm = rbuf + b_m * RECD;
-                const int* ri = reinterpret_cast<const int*>(rm + RL::INTS);
-                int o[3] = { 0, 0, 0 };
-                unsigned mk[3] = { 1u, 1u, 1u };
-#pragma unroll
-                for (int d = 0; d < NDIM; ++d)
+            __threadfence_block();
+        }
+        for (int batch = bs; batch < be; batch += SPREAD_BATCH)
+        {
+                const int nb = min(SPREAD_BATCH, be - batch);
                 {
-                    const int lo = ri[d * 2 + b_v[d]], cc = ri[6 + d];
-                    const int jlo = max(max(cc - M, tlo[d]) - lo, 0);
-                    const int jhi = min(min(cc + M, tlo[d] + TILE - 1) - lo, W - 1);
-                    mk[d] = (jhi >= jlo) ? (((1u << (jhi + 1)) - 1u) & ~((1u << jlo) - 1u)) : 0u;
-                    o[d] = lo - tlo[d];
+                    const int nv = nb * (RECD / 2);
+                    double2* dst = reinterpret_cast<double2*>(rbuf);
+#pragma unroll
+                    for (int p = 0; p < PF; ++p)
+                        if (lane + 32 * p < nv) dst[lane + 32 * p] = pre[p];
                 }
-                unsigned w0r;
-                if constexpr (FAST4)
+                __syncwarp();
+                if (batch + SPREAD_BATCH < be)
                 {
-                    unsigned mxy = 0;
+                    // dense brick: keep one batch in flight
+                    const int nv = min(SPREAD_BATCH, be - batch - SPREAD_BATCH) * (RECD / 2);
+                    const double2* src = recs2 + (long long)(batch + SPREAD_BATCH) * (RECD / 2);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) mxy |= ((mk[1] >> j) & 1u) ? (mk[0] << (4 * j)) : 0u;
-                    w0r = mxy | (mk[2] << 16);
+                    for (int p = 0; p < PF; ++p)
+                        if (lane + 32 * p < nv) pre[p] = __ldg(&src[lane + 32 * p]);
                 }
-                else
+                // ---- A2: one lane per (marker, component): packed record + last-dim weights * force ----
+                if (b_on && b_m < nb)
                 {
-                    w0r = mk[0] | (mk[1] << 8) | (mk[2] << 16);
-                }
-                const bool empty = (mk[0] == 0) || (mk[1] == 0) || (mk[2] == 0);
-                w0r = empty ? 0u : (w0r | ((unsigned)((o[0] + 4 * o[1]) & 15) << 24) | 0x80000000u);
-                rec[(b_m * SPREAD_MAXC + b_a) * 2 + 0] = (int)w0r;
-                rec[(b_m * SPREAD_MAXC + b_a) * 2 + 1] = (NDIM == 3) ? (o[2] * 256 + o[1] * 16) : (o[1] * 16);
-                const double f = rm[RL::FRC + b_a];
-                const double* wl = rm + (LD * 2 + b_v[LD]) * W;
+                    const double* rm = rbuf + b_m * RECD;
+                    const int* ri = reinterpret_cast<const int*>(rm + RL::INTS);
+                    int o[3] = { 0, 0, 0 };
+                    unsigned mk[3] = { 1u, 1u, 1u };
 #pragma unroll
-                for (int j = 0; j < W; ++j) wlf[(b_m * SPREAD_MAXC + b_a) * W + j] = wl[j] * f;
-            }
-            __syncwarp();
-            // ---- phase B: markers one after another, lanes over the stencil points ----
-            for (int m = 0; m < nb; ++m)
-            {
-                const double* wm = rbuf + m * RECD;
-#pragma unroll
-                for (int a = 0; a < SPREAD_MAXC; ++a)
-                {
-                    if (a >= ncomp) break;
-                    const int2 r = *reinterpret_cast<const int2*>(&rec[(m * SPREAD_MAXC + a) * 2]);
-                    if (r.x >= 0) continue; // nothing of this marker lands in the tile (warp-uniform)
-                    double* acc_a = acc + a * TILE_PTS;
-                    const int rot = (r.x >> 24) & 15;
+                    for (int d = 0; d < NDIM; ++d)
+                    {
+                        const int lo = ri[d * 2 + b_v[d]], cc = ri[6 + d];
+                        const int jlo = max(max(cc - M, tlo[d]) - lo, 0);
+                        const int jhi = min(min(cc + M, tlo[d] + TILE - 1) - lo, W - 1);
+                        mk[d] = (jhi >= jlo) ? (((1u << (jhi + 1)) - 1u) & ~((1u << jlo) - 1u)) : 0u;
+                        o[d] = lo - tlo[d];
+                    }
+                    unsigned w0r;
                     if constexpr (FAST4)
                     {
-                        // lane = (ix, iy) = l15, z points 2*half and 2*half + 1
-                        const int idx = r.y + (half << 9) + ((l15 >> 2) << 4) + ((rot + l15) & 15);
-                        const double wxy = wm[wo0[a] + (l15 & 3)] * wm[wo1[a] + (l15 >> 2)];
-                        const double2 wz = *reinterpret_cast<const double2*>(&wlf[(m * SPREAD_MAXC + a) * W + 2 * half]);
-                        const bool okxy = (r.x >> l15) & 1;
-                        const bool ok0 = okxy && ((r.x >> (16 + 2 * half)) & 1);
-                        const bool ok1 = okxy && ((r.x >> (17 + 2 * half)) & 1);
-                        if (ok0) acc_a[idx] += wxy * wz.x;
-                        if (ok1) acc_a[idx + 256] += wxy * wz.y;
+                        unsigned mxy = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mxy |= ((mk[1] >> j) & 1u) ? (mk[0] << (4 * j)) : 0u;
+                        w0r = mxy | (mk[2] << 16);
                     }
                     else
                     {
-#pragma unroll
-                        for (int s = 0; s < NSLOT; ++s)
-                        {
-                            const bool active = (NPTS % 32 == 0) || (lane + 32 * s < NPTS);
-                            if (!active) continue;
-                            bool ok = ((r.x >> pix[s]) & (r.x >> (8 + piy[s])) & 1) != 0;
-                            double wv = wm[wo0[a] + pix[s]];
-                            int idx = r.y + (piy[s] << 4) + ((rot + pix[s] + 4 * piy[s]) & 15);
-                            if constexpr (NDIM == 3)
-                            {
-                                ok = ok && ((r.x >> (16 + piz[s])) & 1);
-                                wv *= wm[wo1[a] + piy[s]] * wlf[(m * SPREAD_MAXC + a) * W + piz[s]];
-                                idx += piz[s] << 8;
-                            }
-                            else
-                            {
-                                wv *= wlf[(m * SPREAD_MAXC + a) * W + piy[s]];
-                            }
-                            if (ok) acc_a[idx] += wv;
-                        }
+                        w0r = mk[0] | (mk[1] << 8) | (mk[2] << 16);
                     }
+                    const bool empty = (mk[0] == 0) || (mk[1] == 0) || (mk[2] == 0);
+                    w0r = empty ? 0u : (w0r | ((unsigned)((o[0] + 4 * o[1]) & 15) << 24) | 0x80000000u);
+                    rec[(b_m * SPREAD_MAXC + b_a) * 2 + 0] = (int)w0r;
+                    rec[(b_m * SPREAD_MAXC + b_a) * 2 + 1] = (NDIM == 3) ? (o[2] * 256 + o[1] * 16) : (o[1] * 16);
+                    const double f = rm[RL::FRC + b_a];
+                    const double* wl = rm + (LD * 2 + b_v[LD]) * W;
+#pragma unroll
+                    for (int j = 0; j < W; ++j) wlf[(b_m * SPREAD_MAXC + b_a) * W + j] = wl[j] * f;
                 }
                 __syncwarp();
-            }
-            batch = nbatch;
-            bi = nbi;
-            be = nbe;
+                // ---- phase B: markers one after another, lanes over the stencil points ----
+                for (int m = 0; m < nb; ++m)
+                {
+                    const double* wm = rbuf + m * RECD;
+#pragma unroll
+                    for (int a = 0; a < SPREAD_MAXC; ++a)
+                    {
+                        if (a >= ncomp) break;
+                        const int2 r = *reinterpret_cast<const int2*>(&rec[(m * SPREAD_MAXC + a) * 2]);
+                        if (r.x >= 0) continue; // nothing of this marker lands in the tile (warp-uniform)
+                        double* acc_a = acc + a * TILE_PTS;
+                        const int rot = (r.x >> 24) & 15;
+                        if constexpr (FAST4)
+                        {
+                            // lane = (ix, iy) = l15, z points 2*half and 2*half + 1
+                            const int idx = r.y + (half << 9) + ((l15 >> 2) << 4) + ((rot + l15) & 15);
+                            const double wxy = wm[wo0[a] + (l15 & 3)] * wm[wo1[a] + (l15 >> 2)];
+                            const double2 wz = *reinterpret_cast<const double2*>(&wlf[(m * SPREAD_MAXC + a) * W + 2 * half]);
+                            const bool okxy = (r.x >> l15) & 1;
+                            const bool ok0 = okxy && ((r.x >> (16 + 2 * half)) & 1);
+                            const bool ok1 = okxy && ((r.x >> (17 + 2 * half)) & 1);
+                            if (ok0) acc_a[idx] += wxy * wz.x;
+                            if (ok1) acc_a[idx + 256] += wxy * wz.y;
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int s = 0; s < NSLOT; ++s)
+                            {
+                                const bool active = (NPTS % 32 == 0) || (lane + 32 * s < NPTS);
+                                if (!active) continue;
+                                bool ok = ((r.x >> pix[s]) & (r.x >> (8 + piy[s])) & 1) != 0;
+                                double wv = wm[wo0[a] + pix[s]];
+                                int idx = r.y + (piy[s] << 4) + ((rot + pix[s] + 4 * piy[s]) & 15);
+                                if constexpr (NDIM == 3)
+                                {
+                                    ok = ok && ((r.x >> (16 + piz[s])) & 1);
+                                    wv *= wm[wo1[a] + piy[s]] * wlf[(m * SPREAD_MAXC + a) * W + piz[s]];
+                                    idx += piz[s] << 8;
+                                }
+                                else
+                                {
+                                    wv *= wlf[(m * SPREAD_MAXC + a) * W + piy[s]];
+                                }
+                                if (ok) acc_a[idx] += wv;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0)
+        {
+            __threadfence_block();
+            done[q] = 1;
+        }
     }
+    __syncthreads();
+
 
     // ---- write-out: f += tile (coalesced along x), dropping points outside the array ----
     for (int a = 0; a < ncomp; ++a)
