@@ -1,0 +1,117 @@
+// Test driver for the C++ host mirror (ibamr_b200/host): reads one case from a binary file, runs it
+// through IBTK_B200::LEInteractor (seam B3) and IBAMR_B200::IBMethodB200 (seam B1), writes the results.
+//   driver --static                 : LEInteractor static queries + "no GPU -> refuse" check, prints lines
+//   driver case.bin out.bin         : GPU run
+// case.bin: int32 n (cells per dim), int32 g (ghost width), int32 N (markers), char[32] kernel,
+//           double X[N][3], double F[N][3], then per axis the side array of u (Fortran order, ghosts incl.)
+// out.bin : double Q[N][3] (LEInteractor::interpolate), per-axis f arrays (LEInteractor::spread into zero),
+//           double U[N][3] (IBMethodB200::interpolateVelocity), per-axis f arrays (IBMethodB200::spreadForce)
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#define NDIM 3
+#include "../../ibamr_b200/host/IBMethodB200.h"
+#include "../../ibamr_b200/host/LEInteractorB200.h"
+
+using namespace SAMRAI_standin;
+using IBTK_B200::LEInteractor;
+
+static int run_static()
+{
+    const char* names[] = { "IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR" };
+    for (const char* n : names)
+        std::printf("%s known=%d stencil=%d ghosts=%d\n", n, (int)LEInteractor::isKnownKernel(n), LEInteractor::getStencilSize(n),
+                    LEInteractor::getMinimumGhostWidth(n));
+    std::printf("IB_7 known=%d\n", (int)LEInteractor::isKnownKernel("IB_7"));
+    try
+    {
+        LEInteractor::getStencilSize("IB_7");
+        std::printf("unknown kernel: no error\n");
+    }
+    catch (const std::exception& e)
+    {
+        std::printf("unknown kernel: error raised\n");
+    }
+    ibk_ctx* c = nullptr;
+    const int rc = ibk_ctx_create(0, &c);
+    std::printf("ctx_create rc=%d\n", rc);
+    if (c) ibk_ctx_destroy(c);
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc >= 2 && !std::strcmp(argv[1], "--static")) return run_static();
+    if (argc < 3) return 2;
+    FILE* fi = std::fopen(argv[1], "rb");
+    if (!fi) return 3;
+    int n, g, N;
+    char kernel[32];
+    if (std::fread(&n, 4, 1, fi) != 1 || std::fread(&g, 4, 1, fi) != 1 || std::fread(&N, 4, 1, fi) != 1 ||
+        std::fread(kernel, 1, 32, fi) != 32)
+        return 4;
+    std::vector<double> X((size_t)N * 3), F((size_t)N * 3);
+    if (std::fread(X.data(), 8, X.size(), fi) != X.size() || std::fread(F.data(), 8, F.size(), fi) != F.size()) return 4;
+    Box box(Index(0), Index(n - 1));
+    auto u = std::make_shared<SideData>(box, 1, IntVector(g));
+    for (int a = 0; a < 3; ++a)
+        if (std::fread(u->getPointer(a), 8, u->data[a].size(), fi) != u->data[a].size()) return 4;
+    std::fclose(fi);
+
+    auto geom = std::make_shared<CartesianPatchGeometry>();
+    for (int d = 0; d < 3; ++d)
+    {
+        geom->x_lower[d] = 0.0;
+        geom->x_upper[d] = 1.0;
+        geom->dx[d] = 1.0 / n;
+    }
+    auto patch = std::make_shared<Patch>();
+    patch->box = box;
+    patch->geom = geom;
+
+    FILE* fo = std::fopen(argv[2], "wb");
+    try
+    {
+        // seam B3
+        std::vector<double> Q((size_t)N * 3, 0.0);
+        LEInteractor::interpolate(Q, 3, X, 3, u, patch, box, kernel);
+        std::fwrite(Q.data(), 8, Q.size(), fo);
+        auto f = std::make_shared<SideData>(box, 1, IntVector(g));
+        LEInteractor::spread(f, F, 3, X, 3, patch, box, kernel);
+        for (int a = 0; a < 3; ++a) std::fwrite(f->getPointer(a), 8, f->data[a].size(), fo);
+        // seam B1
+        IBAMR_B200::IBMethodB200::LevelSpec lv;
+        lv.domain_box = box;
+        for (int d = 0; d < 3; ++d)
+        {
+            lv.x_lower[d] = 0.0;
+            lv.x_upper[d] = 1.0;
+            lv.periodic[d] = 1;
+        }
+        lv.patch_boxes.push_back(box);
+        IBAMR_B200::IBMethodB200 ib(lv, kernel, 0, g);
+        ib.setPositions(X);
+        ib.setForce(F);
+        ib.setEulerianVelocity(0, *u);
+        ib.beginDataRedistribution();
+        ib.endDataRedistribution();
+        ib.interpolateVelocity();
+        std::vector<double> U;
+        ib.getVelocity(U);
+        std::fwrite(U.data(), 8, U.size(), fo);
+        ib.spreadForce();
+        SideData f2(box, 1, IntVector(g));
+        ib.getEulerianForce(0, f2);
+        for (int a = 0; a < 3; ++a) std::fwrite(f2.getPointer(a), 8, f2.data[a].size(), fo);
+    }
+    catch (const std::exception& e)
+    {
+        std::fprintf(stderr, "driver: %s\n", e.what());
+        std::fclose(fo);
+        return 5;
+    }
+    std::fclose(fo);
+    return 0;
+}

@@ -519,3 +519,21 @@ def test_adjointness_and_moments_large(api, kernel):
     ib.interpolateVelocity(fill_halo=False)
     assert np.max(np.abs(ib.getLData("U") - 3.25)) <= 1e-12
     ib.close()
+
+
+def test_multi_gpu_parity_two_ranks():
+    """Patch-partitioned level on 2 GPUs with the NCCL halo exchange (tests/mgpu_worker.py) against the
+    oracle; needs >= 2 visible GPUs (the driver's single-GPU tier skips it)."""
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for kernel in ("IB_4", "IB_6"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                            "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "mgpu_worker.py"), kernel],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "MGPU_PARITY" in r.stdout

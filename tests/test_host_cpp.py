@@ -1,0 +1,113 @@
+"""The C++ host mirror (ibamr_b200/host/*.h + the Fortran link-substitution shim) compiles against the
+C ABI, answers the LEInteractor static queries, refuses to compute without a GPU (CPU test), and reproduces
+the oracle through LEInteractor::interpolate/spread and IBMethodB200 (GPU test)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "host_cpp", "_build")
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+@pytest.fixture(scope="module")
+def driver():
+    from ibamr_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "driver")
+    src = os.path.join(ROOT, "tests", "host_cpp", "driver.cpp")
+    libdir = os.path.join(ROOT, "ibamr_b200")
+    deps = [src, _lib.LIB_PATH] + [os.path.join(libdir, "host", f) for f in os.listdir(os.path.join(libdir, "host"))]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.run([CXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-o", exe, src, "-L" + libdir, "-libk",
+                        "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+        # the Fortran-symbol shim must compile and define all 20 in-scope entry points
+        obj = os.path.join(BUILD, "shim.o")
+        subprocess.run([CXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-c", "-o", obj,
+                        os.path.join(libdir, "host", "ibk_fortran_shim.cpp")], check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_cpp_static_queries_and_refusal(driver):
+    out = subprocess.run([driver, "--static"], capture_output=True, text=True, check=True).stdout
+    assert "IB_4 known=1 stencil=4 ghosts=3" in out
+    assert "IB_6 known=1 stencil=6 ghosts=4" in out
+    assert "BSPLINE_3 known=1 stencil=4 ghosts=3" in out
+    assert "PIECEWISE_LINEAR known=1 stencil=2 ghosts=2" in out
+    assert "IB_7 known=0" in out and "unknown kernel: error raised" in out
+    import torch
+    if not torch.cuda.is_available():
+        assert "ctx_create rc=-2" in out  # IBK_ERR_CUDA: no CPU fallback
+
+
+def test_fortran_shim_exports_all_symbols(driver):
+    out = subprocess.run(["nm", os.path.join(BUILD, "shim.o")], capture_output=True, text=True, check=True).stdout
+    for k in ("piecewise_linear", "ib_4", "ib_6", "bspline_3", "bspline_4"):
+        for op in ("interp", "spread"):
+            for d in ("2d", "3d"):
+                assert f" T lagrangian_{k}_{op}{d}_" in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["IB_4", "BSPLINE_3"])
+def test_cpp_host_mirror_vs_oracle(driver, kernel, tmp_path):
+    from oracle import oracle as orc
+    from tests.util import splitmix64_unit
+    n, N = 24, 3000
+    g = orc.min_ghost_width(kernel)
+    level = orc.Level(3, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), [((0,) * 3, (n - 1,) * 3)], (g,) * 3)
+    pg = level.patch_geom(0)
+    X = np.stack([splitmix64_unit(5 + d, np.arange(N)) for d in range(3)], axis=1)
+    F = np.stack([2 * splitmix64_unit(9 + d, np.arange(N)) - 1 for d in range(3)], axis=1)
+    u = []
+    ncell = (n,) * 3
+    for a in range(3):
+        c = pg.side_coords(a)
+        u.append(np.ascontiguousarray(np.sin(2 * np.pi * c[a]) * np.cos(2 * np.pi * c[(a + 1) % 3])))
+    case, outp = tmp_path / "case.bin", tmp_path / "out.bin"
+    with open(case, "wb") as f:
+        f.write(struct.pack("iii", n, g, N))
+        f.write(kernel.encode().ljust(32, b"\0"))
+        f.write(X.tobytes())
+        f.write(F.tobytes())
+        for a in range(3):
+            f.write(u[a].tobytes())
+    r = subprocess.run([driver, str(case), str(outp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = np.fromfile(outp, dtype=np.float64)
+    sizes = [u[a].size for a in range(3)]
+    off = 0
+    Q = raw[off:off + 3 * N].reshape(N, 3); off += 3 * N
+    fB3 = []
+    for a in range(3):
+        fB3.append(raw[off:off + sizes[a]].reshape(u[a].shape)); off += sizes[a]
+    U = raw[off:off + 3 * N].reshape(N, 3); off += 3 * N
+    fB1 = []
+    for a in range(3):
+        fB1.append(raw[off:off + sizes[a]].reshape(u[a].shape)); off += sizes[a]
+
+    def rel(a, b):
+        return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+    # seam B3: position-only LEInteractor calls (no periodic images)
+    Qo = orc.side_interp_positions(kernel, pg, u, X)
+    assert rel(Q, Qo) <= 1e-12
+    fo = [np.zeros_like(a) for a in u]
+    orc.side_spread_positions(kernel, pg, fo, X, F)
+    for a in range(3):
+        assert rel(fB3[a], fo[a]) <= 1e-12
+    # seam B1: the periodic level against the reference model (ghost-box lists with periodic shifts)
+    ref = orc.bin_level(level, X)
+    lst = ref["patches"][0]
+    fr = [np.zeros_like(a) for a in u]
+    orc.side_spread(kernel, pg, fr, X, F, lst["all_idx"], lst["all_shift"])
+    for a in range(3):
+        sl = tuple(slice(g, s - g) for s in fr[a].shape)
+        assert rel(fB1[a][sl], fr[a][sl]) <= 1e-12
+    # u given to the level has analytic (periodic) ghosts already, so U must equal the position-only result
+    assert rel(U, Qo) <= 1e-12
