@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "ibk_engine.h"
 
@@ -42,13 +43,14 @@ constexpr int SPREAD_BATCH = 4; // markers per batch (per warp)
 constexpr int SPREAD_MAXC = 3;  // components accumulated per launch
 constexpr int REC_INTS = 10;    // lo[d][v] (6), binning cell cc[d] (3), spare
 
-// doubles per marker record: weights [d][v][j], scaled force per component, integer section
+// doubles per marker record: weights [d < NDIM-1][v][j], last-dim weights * scaled force per component
+// [a][j], integer section
 template <int NDIM, int W>
 struct RecLayout
 {
-    static constexpr int WGT = NDIM * 2 * W;
-    static constexpr int FRC = WGT;
-    static constexpr int INTS = WGT + SPREAD_MAXC; // offset (in doubles) of the integer section
+    static constexpr int WGT = (NDIM - 1) * 2 * W;
+    static constexpr int WLF = WGT;                      // offset of wlf[a][j]
+    static constexpr int INTS = WGT + SPREAD_MAXC * W;   // offset (in doubles) of the integer section
     static constexpr int DOUBLES = ((INTS + REC_INTS / 2) + 1) / 2 * 2;
 };
 
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(256) spread_records_kernel(const __grid_consta
     constexpr int M = KTraits<K>::M;
     using RL = RecLayout<NDIM, W>;
     constexpr int TASKS = NDIM * 2;
+    constexpr int LD = NDIM - 1;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int i = args.first + (int)(gid / TASKS);
     const int t = (int)(gid % TASKS);
@@ -138,8 +141,24 @@ __global__ void __launch_bounds__(256) spread_records_kernel(const __grid_consta
         int l;
         stencil_1d<K>(xs, xr, tp.xl[d][v], tp.dx[d], l, w);
         const int lo_pp = l + tp.G;
+        if (d < LD)
+        {
 #pragma unroll
-        for (int j = 0; j < W; ++j) rec[(d * 2 + v) * W + j] = w[j];
+            for (int j = 0; j < W; ++j) rec[(d * 2 + v) * W + j] = w[j];
+        }
+        else
+        {
+            // last dimension: fold the scaled force of every component that uses this variant
+            const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
+            for (int a = 0; a < args.ncomp; ++a)
+            {
+                const CompGeom& cg = tp.comp[args.comp0 + a];
+                if (cg.var[LD] != v) continue;
+                const double f = __ldg(&args.V[cg.vcol * args.v_cstride + row * args.v_istride]) * tp.inv_vol;
+#pragma unroll
+                for (int j = 0; j < W; ++j) rec[RL::WLF + a * W + j] = w[j] * f;
+            }
+        }
         ri[d * 2 + v] = lo_pp;
         if ((lo_pp < cc - M || lo_pp + W - 1 > cc + M) && args.exc_list)
         {
@@ -154,9 +173,6 @@ __global__ void __launch_bounds__(256) spread_records_kernel(const __grid_consta
     if (v == 0) ri[6 + d] = cc;
     if (t == 0)
     {
-        const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
-        for (int a = 0; a < SPREAD_MAXC; ++a)
-            rec[RL::FRC + a] = (a < args.ncomp) ? __ldg(&args.V[tp.comp[args.comp0 + a].vcol * args.v_cstride + row * args.v_istride]) * tp.inv_vol : 0.0;
         if (NDIM == 2) ri[8] = 0;
         ri[9] = 0;
     }
@@ -165,19 +181,20 @@ __global__ void __launch_bounds__(256) spread_records_kernel(const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // stage 2: owner-computes tiles
 // ---------------------------------------------------------------------------------------------
-template <int NDIM, int K>
-__global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __grid_constant__ TileParams tp, SpreadArgs args)
+template <int NDIM, int K, int TZ>
+__global__ void __launch_bounds__(SPREAD_THREADS, (NDIM == 3 && TZ <= 8) ? 3 : 2) spread_tile_kernel(const __grid_constant__ TileParams tp, SpreadArgs args)
 {
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
     using RL = RecLayout<NDIM, W>;
     constexpr int RECD = RL::DOUBLES;
-    constexpr int NBR = TILE_BRICKS + (2 * M + BRICK - 1) / BRICK; // bricks per dimension around the tile
+    constexpr int NBR = TILE_BRICKS + (2 * M + BRICK - 1) / BRICK; // bricks per dimension around the tile (x, y)
+    constexpr int NBRZ = (NDIM == 3) ? TZ / BRICK + (2 * M + BRICK - 1) / BRICK : 1; // ... and along z (tile is TZ deep)
     constexpr int NC = (BRICK + 2 * M + BRICK - 1) / BRICK;        // colours per dimension
     constexpr int NPTS = (NDIM == 3) ? W * W * W : W * W;
     constexpr int NSLOT = (NPTS + 31) / 32;
-    constexpr int TILE_PTS = (NDIM == 3) ? TILE * TILE * TILE : TILE * TILE;
-    constexpr int NBRICKS = (NDIM == 3) ? NBR * NBR * NBR : NBR * NBR;
+    constexpr int TILE_PTS = (NDIM == 3) ? TILE * TILE * TZ : TILE * TILE;
+    constexpr int NBRICKS = (NDIM == 3) ? NBR * NBR * NBRZ : NBR * NBR;
     constexpr int NCOL = (NDIM == 3) ? NC * NC * NC : NC * NC;
     constexpr bool FAST4 = (NDIM == 3) && (W == 4); // lane = (ix, iy, half): two adjacent z points per lane
     constexpr int LD = NDIM - 1;                    // the "last" dimension carries the force factor
@@ -186,8 +203,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* acc = reinterpret_cast<double*>(smem_raw);                          // [ncomp][TILE_PTS]
     double* rbuf_all = acc + (size_t)args.ncomp * TILE_PTS;                     // [warp][BATCH][RECD] marker records
-    double* wlf_all = rbuf_all + SPREAD_WARPS * SPREAD_BATCH * RECD;            // [warp][BATCH][MAXC][W]  last-dim weights * force
-    int* rec_all = reinterpret_cast<int*>(wlf_all + SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * W); // [warp][BATCH][MAXC][2]
+    int* rec_all = reinterpret_cast<int*>(rbuf_all + SPREAD_WARPS * SPREAD_BATCH * RECD); // [warp][BATCH][MAXC][2]
     int* brng = rec_all + SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * 2;        // [NBRICKS][2]
     unsigned char* order = reinterpret_cast<unsigned char*>(brng + 2 * NBRICKS); // [NBRICKS] bricks sorted by colour
     __shared__ int any_markers;
@@ -197,7 +213,6 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* rbuf = rbuf_all + warp * (SPREAD_BATCH * RECD);
-    double* wlf = wlf_all + warp * (SPREAD_BATCH * SPREAD_MAXC * W);
     int* rec = rec_all + warp * (SPREAD_BATCH * SPREAD_MAXC * 2);
 
     // which output tile
@@ -211,7 +226,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
     }
     int tlo[3]; // pp coordinate of the tile's first point
 #pragma unroll
-    for (int d = 0; d < 3; ++d) tlo[d] = TILE * ot[d] + M;
+    for (int d = 0; d < 3; ++d) tlo[d] = ((d == 2) ? TZ : TILE) * ot[d] + M;
 
     // brick ranges of the neighbourhood, colour-sorted brick order, emptiness test
     if (threadIdx.x == 0) any_markers = 0;
@@ -221,7 +236,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
         for (int c = 0; c < (int)threadIdx.x; ++c)
         {
             const int c0 = c % NC, c1 = (c / NC) % NC, c2 = (NDIM == 3) ? c / (NC * NC) : 0;
-            s += ((NBR - c0 + NC - 1) / NC) * ((NBR - c1 + NC - 1) / NC) * ((NDIM == 3) ? (NBR - c2 + NC - 1) / NC : 1);
+            s += ((NBR - c0 + NC - 1) / NC) * ((NBR - c1 + NC - 1) / NC) * ((NDIM == 3) ? max((NBRZ - c2 + NC - 1) / NC, 0) : 1);
         }
         col_start[threadIdx.x] = s;
     }
@@ -229,7 +244,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
     for (int q = threadIdx.x; q < NBRICKS; q += SPREAD_THREADS)
     {
         const int lx = q % NBR, ly = (q / NBR) % NBR, lz = (NDIM == 3) ? q / (NBR * NBR) : 0;
-        const int bx = TILE_BRICKS * ot[0] + lx, by = TILE_BRICKS * ot[1] + ly, bz = (NDIM == 3) ? TILE_BRICKS * ot[2] + lz : 0;
+        const int bx = TILE_BRICKS * ot[0] + lx, by = TILE_BRICKS * ot[1] + ly, bz = (NDIM == 3) ? (TZ / BRICK) * ot[2] + lz : 0;
         int s = 0, e = 0;
         if (bx < tp.nb[0] && by < tp.nb[1] && bz < tp.nb[2])
         {
@@ -265,7 +280,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
     for (int a = 0; a < args.ncomp; ++a)
     {
         const CompGeom& cg = tp.comp[args.comp0 + a];
-        constexpr int ROWS = (NDIM == 3) ? TILE * TILE : TILE;
+        constexpr int ROWS = (NDIM == 3) ? TILE * TZ : TILE;
         for (int row = threadIdx.x; row < ROWS; row += SPREAD_THREADS)
         {
             const int y = row & 15, z = (NDIM == 3) ? row >> 4 : 0;
@@ -352,7 +367,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
                 {
                     const int nx = lx + n % RN - (NC - 1), ny = ly + (n / RN) % RN - (NC - 1),
                               nz = (NDIM == 3) ? lz + n / (RN * RN) - (NC - 1) : 0;
-                    if (nx >= 0 && nx < NBR && ny >= 0 && ny < NBR && nz >= 0 && nz < ((NDIM == 3) ? NBR : 1))
+                    if (nx >= 0 && nx < NBR && ny >= 0 && ny < NBR && nz >= 0 && nz < NBRZ)
                     {
                         nq = (nz * NBR + ny) * NBR + nx;
                         need = (((nz % NC) * NC + ny % NC) * NC + nx % NC) < mycol;
@@ -396,7 +411,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
                     {
                         const int lo = ri[d * 2 + b_v[d]], cc = ri[6 + d];
                         const int jlo = max(max(cc - M, tlo[d]) - lo, 0);
-                        const int jhi = min(min(cc + M, tlo[d] + TILE - 1) - lo, W - 1);
+                        const int jhi = min(min(cc + M, tlo[d] + ((d == 2) ? TZ : TILE) - 1) - lo, W - 1);
                         mk[d] = (jhi >= jlo) ? (((1u << (jhi + 1)) - 1u) & ~((1u << jlo) - 1u)) : 0u;
                         o[d] = lo - tlo[d];
                     }
@@ -416,10 +431,6 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
                     w0r = empty ? 0u : (w0r | ((unsigned)((o[0] + 4 * o[1]) & 15) << 24) | 0x80000000u);
                     rec[(b_m * SPREAD_MAXC + b_a) * 2 + 0] = (int)w0r;
                     rec[(b_m * SPREAD_MAXC + b_a) * 2 + 1] = (NDIM == 3) ? (o[2] * 256 + o[1] * 16) : (o[1] * 16);
-                    const double f = rm[RL::FRC + b_a];
-                    const double* wl = rm + (LD * 2 + b_v[LD]) * W;
-#pragma unroll
-                    for (int j = 0; j < W; ++j) wlf[(b_m * SPREAD_MAXC + b_a) * W + j] = wl[j] * f;
                 }
                 __syncwarp();
                 // ---- phase B: markers one after another, lanes over the stencil points ----
@@ -439,7 +450,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
                             // lane = (ix, iy) = l15, z points 2*half and 2*half + 1
                             const int idx = r.y + (half << 9) + ((l15 >> 2) << 4) + ((rot + l15) & 15);
                             const double wxy = wm[wo0[a] + (l15 & 3)] * wm[wo1[a] + (l15 >> 2)];
-                            const double2 wz = *reinterpret_cast<const double2*>(&wlf[(m * SPREAD_MAXC + a) * W + 2 * half]);
+                            const double2 wz = *reinterpret_cast<const double2*>(&wm[RL::WLF + a * W + 2 * half]);
                             const bool okxy = (r.x >> l15) & 1;
                             const bool ok0 = okxy && ((r.x >> (16 + 2 * half)) & 1);
                             const bool ok1 = okxy && ((r.x >> (17 + 2 * half)) & 1);
@@ -459,12 +470,12 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
                                 if constexpr (NDIM == 3)
                                 {
                                     ok = ok && ((r.x >> (16 + piz[s])) & 1);
-                                    wv *= wm[wo1[a] + piy[s]] * wlf[(m * SPREAD_MAXC + a) * W + piz[s]];
+                                    wv *= wm[wo1[a] + piy[s]] * wm[RL::WLF + a * W + piz[s]];
                                     idx += piz[s] << 8;
                                 }
                                 else
                                 {
-                                    wv *= wlf[(m * SPREAD_MAXC + a) * W + piy[s]];
+                                    wv *= wm[RL::WLF + a * W + piy[s]];
                                 }
                                 if (ok) acc_a[idx] += wv;
                             }
@@ -484,38 +495,38 @@ __global__ void __launch_bounds__(SPREAD_THREADS, 2) spread_tile_kernel(const __
 
 
     // ---- write-out: f += tile (coalesced along x), dropping points outside the array ----
-    for (int a = 0; a < ncomp; ++a)
+    // thread = (x, y); it walks the z column (3D) with a constant pointer / index stride
     {
-        const CompGeom& cg = tp.comp[args.comp0 + a];
-        const double* acc_a = acc + a * TILE_PTS;
-        const int x = threadIdx.x & 15, y0t = threadIdx.x >> 4; // 16 rows of 16 points per pass
-        const int gi = tlo[0] + x - cg.pp0[0];
-        const bool okx = gi >= 0 && gi < cg.n[0];
-        constexpr int ROWS = (NDIM == 3) ? TILE * TILE : TILE; // rows (y, z) in the tile
-        constexpr int PASSES = ROWS / (SPREAD_THREADS / 16);
-#pragma unroll
-        for (int r0 = 0; r0 < PASSES; r0 += 8)
+        const int x = threadIdx.x & 15, y = threadIdx.x >> 4;
+        constexpr int NZ = (NDIM == 3) ? TZ : 1;
+        const int sbase = (y << 4) + ((x + 4 * y) & 15);
+        for (int a = 0; a < ncomp; ++a)
         {
-            double vals[8], old[8];
-            double* ptrs[8];
+            const CompGeom& cg = tp.comp[args.comp0 + a];
+            const double* acc_a = acc + a * TILE_PTS + sbase;
+            const int gi = tlo[0] + x - cg.pp0[0], gj = tlo[1] + y - cg.pp0[1];
+            const int gk0 = (NDIM == 3) ? tlo[2] - cg.pp0[2] : 0;
+            const bool okxy = gi >= 0 && gi < cg.n[0] && gj >= 0 && gj < cg.n[1];
+            const long long zstride = (long long)cg.n[1] * cg.pitch;
+            double* p0 = cg.ptr + ((long long)gk0 * cg.n[1] + gj) * cg.pitch + gi;
+            const int zlo = max(0, -gk0), zhi = min(NZ, cg.n[2] - gk0); // valid z range of this tile
+            if (!okxy) continue;
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+            for (int z0 = 0; z0 < NZ; z0 += 8)
             {
-                ptrs[r] = nullptr;
-                if (r0 + r >= PASSES) continue;
-                const int row = y0t + (r0 + r) * (SPREAD_THREADS / 16);
-                const int y = row & 15, z = (NDIM == 3) ? row >> 4 : 0;
-                const int gj = tlo[1] + y - cg.pp0[1], gk = (NDIM == 3) ? tlo[2] + z - cg.pp0[2] : 0;
-                const double v = acc_a[acc_index<NDIM>(x, y, z)];
-                const bool ok = okx && gj >= 0 && gj < cg.n[1] && gk >= 0 && gk < cg.n[2] && v != 0.0;
-                ptrs[r] = ok ? cg.ptr + ((long long)gk * cg.n[1] + gj) * cg.pitch + gi : nullptr;
-                vals[r] = v;
+                double v[8], old[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                {
+                    const int z = z0 + r;
+                    v[r] = (z < NZ && z >= zlo && z < zhi) ? acc_a[z << 8] : 0.0;
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) old[r] = (v[r] != 0.0) ? p0[(z0 + r) * zstride] : 0.0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (v[r] != 0.0) p0[(z0 + r) * zstride] = old[r] + v[r];
             }
-#pragma unroll
-            for (int r = 0; r < 8; ++r) old[r] = ptrs[r] ? *ptrs[r] : 0.0;
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (ptrs[r]) *ptrs[r] = old[r] + vals[r];
         }
     }
 }
@@ -611,15 +622,16 @@ constexpr int EXC_CAPACITY = 4096;
 static double* g_rec_buf = nullptr; // marker records, grown on demand
 static size_t g_rec_cap = 0;
 
-template <int NDIM, int K>
-static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err)
+template <int NDIM, int K, int TZ>
+static cudaError_t launch_spread_tz(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err)
 {
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
     using RL = RecLayout<NDIM, W>;
     constexpr int NBR = TILE_BRICKS + (2 * M + BRICK - 1) / BRICK;
-    constexpr int TILE_PTS = (NDIM == 3) ? TILE * TILE * TILE : TILE * TILE;
-    constexpr int NBRICKS = (NDIM == 3) ? NBR * NBR * NBR : NBR * NBR;
+    constexpr int NBRZ = (NDIM == 3) ? TZ / BRICK + (2 * M + BRICK - 1) / BRICK : 1;
+    constexpr int TILE_PTS = (NDIM == 3) ? TILE * TILE * TZ : TILE * TILE;
+    constexpr int NBRICKS = (NDIM == 3) ? NBR * NBR * NBRZ : NBR * NBR;
     cudaError_t e;
     if (!g_exc_buf)
     {
@@ -677,22 +689,22 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
             ppmax = std::max(ppmax, tp.comp[a].pp0[d] + tp.comp[a].n[d] - 1);
         }
         auto fdiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
-        const int alo = std::max(0, fdiv(ppmin - M, TILE));
-        const int ahi = fdiv(ppmax - M, TILE);
+        const int td = (d == 2) ? TZ : TILE;
+        const int alo = std::max(0, fdiv(ppmin - M, td));
+        const int ahi = fdiv(ppmax - M, td);
         tpl.ot_lo[d] = alo;
         tpl.ot_n[d] = std::max(0, ahi - alo + 1);
     }
     const int ntiles = tpl.ot_n[0] * tpl.ot_n[1] * tpl.ot_n[2];
     if (ntiles <= 0) return cudaSuccess;
     auto rfn = spread_records_kernel<NDIM, K>;
-    auto kfn = spread_tile_kernel<NDIM, K>;
+    auto kfn = spread_tile_kernel<NDIM, K, TZ>;
     auto ffn = spread_fixup_kernel<NDIM, K>;
     for (int c0 = 0; c0 < tp.ncomp; c0 += SPREAD_MAXC)
     {
         args.comp0 = c0;
         args.ncomp = (tp.ncomp - c0 < SPREAD_MAXC) ? tp.ncomp - c0 : SPREAD_MAXC;
-        const size_t smem = sizeof(double) * ((size_t)args.ncomp * TILE_PTS + SPREAD_WARPS * SPREAD_BATCH * RL::DOUBLES +
-                                              SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * W) +
+        const size_t smem = sizeof(double) * ((size_t)args.ncomp * TILE_PTS + SPREAD_WARPS * SPREAD_BATCH * RL::DOUBLES) +
                             sizeof(int) * (SPREAD_WARPS * SPREAD_BATCH * SPREAD_MAXC * 2 + 2 * NBRICKS) + ((NBRICKS + 15) / 16) * 16;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
@@ -709,6 +721,17 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
             if ((e = cudaMemsetAsync(g_exc_buf, 0, sizeof(int), L.stream)) != cudaSuccess) return e;
     }
     return cudaGetLastError();
+}
+
+// z depth of the output tile: 8 keeps three CTAs (24 warps) resident per SM for the 4-point kernels; the
+// kernel is latency-bound, so the extra resident warps outweigh the larger marker neighbourhood
+template <int NDIM, int K>
+static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err)
+{
+    static const char* env = getenv("IBK_SPREAD_TZ");
+    const int tz = env ? atoi(env) : ((NDIM == 3 && KTraits<K>::W <= 4) ? 8 : 16);
+    if (NDIM == 3 && tz == 8) return launch_spread_tz<NDIM, K, 8>(L, tp, bins, mv, err);
+    return launch_spread_tz<NDIM, K, 16>(L, tp, bins, mv, err);
 }
 
 template <int NDIM>

@@ -550,6 +550,15 @@ int le_oracle_baseline_npatch(baseline_t* b)
 {
     return b->npatch;
 }
+/* torchrun exports OMP_NUM_THREADS=1; the baseline must use the cores the process may run on. */
+void le_oracle_baseline_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int le_oracle_baseline_threads(void)
 {
 #ifdef _OPENMP

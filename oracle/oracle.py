@@ -388,6 +388,12 @@ class Baseline:
 
     @staticmethod
     def threads():
+        """All cores this process may run on (torchrun's OMP_NUM_THREADS=1 default is overridden)."""
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        lib().le_oracle_baseline_set_threads(int(n))
         return lib().le_oracle_baseline_threads()
 
     def close(self):
