@@ -1,0 +1,175 @@
+"""BASELINE.json's configurations as GPU parity cases (reduced sizes where the oracle would take minutes):
+C1  examples/IB/explicit/ex1: 2D elastic ellipse (curve2d_64.vertex), IB_4, 64^2 periodic grid, one patch
+C2  3D spherical shell (Fibonacci lattice), IB_4, one periodic patch: many markers per cell
+C3  IB_6, uniform + clustered shell with radial jitter, 2x2x1 patches
+C4  two-level AMR: markers on the finest level whose patches do not cover the domain; ghost cells with no
+    same-level owner are dropped
+Each compares spreadForce / interpolateVelocity on the resident level with the oracle's model of the reference
+path (redundant ghost-box spreading with periodic shifts, interiors kept; interpolation at interior lists)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.util import splitmix64_unit
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def api():
+    from ibamr_b200 import api as _api
+    _api.default_context()
+    return _api
+
+
+def relerr(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300)
+
+
+def _side_field(pg, ncell, x_lower, L, seed, ndim):
+    out = []
+    for axis in range(ndim):
+        c = pg.side_coords(axis)
+        f = np.sin(2 * np.pi * (c[axis] - x_lower[axis]) / L[axis]) * np.cos(2 * np.pi * (c[(axis + 1) % ndim] - x_lower[(axis + 1) % ndim]) / L[(axis + 1) % ndim])
+        gi = []
+        for d in range(ndim):
+            cnt = pg.upper[d] - pg.lower[d] + 1 + (1 if d == axis else 0) + 2 * pg.gcw[d]
+            gi.append(np.mod(np.arange(cnt) + pg.lower[d] - pg.gcw[d], ncell[d]))
+        mesh = np.meshgrid(*reversed(gi), indexing="ij")[::-1]
+        lin = np.zeros(f.shape, dtype=np.int64)
+        mul = 1
+        for d in range(ndim):
+            lin += mesh[d] * mul
+            mul *= ncell[d]
+        out.append(np.ascontiguousarray(f + 1e-3 * splitmix64_unit(seed + axis, lin.reshape(-1)).reshape(f.shape)))
+    return out
+
+
+def _run_level_case(api, level, kernel, X, F, periodic_fill=True, check_ghost_fill=True):
+    """Runs the resident level and the reference model; returns the max relative errors."""
+    ndim = level.ndim
+    g = level.gcw[0]
+    N = X.shape[0]
+    L = tuple(level.x_upper[d] - level.x_lower[d] for d in range(ndim))
+    Xw, _ = orc.wrap_positions(X, level.x_lower, level.x_upper, level.periodic)
+    Xw = Xw.reshape(-1, ndim)
+    ref = orc.bin_level(level, Xw)
+    ib = api.IBMethodB200(ndim, level.domain_lower, level.domain_upper(), level.x_lower, level.x_upper, level.periodic, level.boxes,
+                          gcw=g, kernel_fcn=kernel)
+    ib.setPositions(X)
+    ib.setLData("F", F)
+    ib.beginDataRedistribution()
+    cells, owner = ib.getCellsAndOwners()
+    assert np.array_equal(cells, ref["cells"]) and np.array_equal(owner, ref["owner"])
+    U_ref = np.zeros((N, ndim))
+    f_ref = []
+    for p in range(len(level.boxes)):
+        pg = level.patch_geom(p)
+        u = _side_field(pg, level.domain_ncells, level.x_lower, L, 500, ndim)
+        lst = ref["patches"][p]
+        ii = lst["all_idx"][lst["interior_mask"]]
+        sh = lst["all_shift"].reshape(-1, ndim)[lst["interior_mask"]]
+        orc.side_interp(kernel, pg, u, Xw, ii, sh.reshape(-1), U_ref)
+        fo = [np.zeros(pg.side_shape(a)) for a in range(ndim)]
+        orc.side_spread(kernel, pg, fo, Xw, F, lst["all_idx"], lst["all_shift"])
+        f_ref.append(fo)
+        for a in range(ndim):
+            ib.grid_upload("u", p, a, u[a])  # analytic values everywhere (ghosts included)
+    ib.interpolateVelocity(fill_halo=periodic_fill)
+    U = ib.getLData("U")
+    owned = ref["owner"] >= 0
+    eu = relerr(U[owned], U_ref[owned])
+    ib.spreadForce(accumulate_halo=True)
+    ef = 0.0
+    for p in range(len(level.boxes)):
+        for a in range(ndim):
+            got = ib.grid_download("f", p, a)
+            sl = tuple(slice(g, s - g) for s in got.shape)
+            ef = max(ef, np.max(np.abs(got[sl] - f_ref[p][a][sl])) / max(max(np.max(np.abs(x)) for x in f_ref[p]), 1e-300))
+    ib.close()
+    return eu, ef
+
+
+def test_c1_ex1_ellipse_2d(api, golden_dir):
+    """C1: the 304 vertices of examples/IB/explicit/ex1/curve2d_64.vertex on the 64^2 periodic unit square."""
+    with open(os.path.join(golden_dir, "curve2d_64.vertex")) as f:
+        n = int(f.readline().split()[0])
+        X = np.array([[float(t) for t in f.readline().split()[:2]] for _ in range(n)])
+    assert X.shape == (304, 2)
+    F = np.stack([2 * splitmix64_unit(1 + d, np.arange(n)) - 1 for d in range(2)], axis=1)
+    level = orc.Level(2, (0, 0), (64, 64), (0.0, 0.0), (1.0, 1.0), (1, 1), [((0, 0), (63, 63))], (3, 3))
+    eu, ef = _run_level_case(api, level, "IB_4", X, F)
+    assert eu <= TOL and ef <= TOL
+
+
+def test_c2_spherical_shell_dense(api):
+    """C2 (reduced): Fibonacci-lattice shell R = 0.25 about the centre, 60k markers on 64^3 (tens of markers per cell)."""
+    N, n = 60000, 64
+    k = np.arange(N) + 0.5
+    phi = np.arccos(1 - 2 * k / N)
+    th = np.pi * (1 + 5 ** 0.5) * k
+    X = 0.5 + 0.25 * np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1)
+    F = np.stack([2 * splitmix64_unit(1 + d, np.arange(N)) - 1 for d in range(3)], axis=1)
+    level = orc.Level(3, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), [((0,) * 3, (n - 1,) * 3)], (3,) * 3)
+    eu, ef = _run_level_case(api, level, "IB_4", X, F)
+    assert eu <= TOL and ef <= TOL
+
+
+def test_c3_ib6_uniform_plus_jittered_shell(api):
+    """C3 (reduced): IB_6, uniform markers + shell R = 0.3 with radial jitter N(0, h), 2x2x1 patches of a 48^3 grid."""
+    n, N = 48, 30000
+    h = 1.0 / n
+    Xu = np.stack([splitmix64_unit(3 + 10 * d, np.arange(N // 2)) for d in range(3)], axis=1)
+    u1, u2 = splitmix64_unit(4, np.arange(N // 2)), splitmix64_unit(5, np.arange(N // 2))
+    jitter = np.sqrt(-2 * np.log(np.maximum(u1, 1e-300))) * np.cos(2 * np.pi * u2) * h  # Box-Muller
+    k = np.arange(N // 2) + 0.5
+    phi = np.arccos(1 - 2 * k / (N // 2))
+    th = np.pi * (1 + 5 ** 0.5) * k
+    Xs = 0.5 + (0.3 + jitter)[:, None] * np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1)
+    X = np.concatenate([Xu, Xs])
+    F = np.stack([2 * splitmix64_unit(1 + d, np.arange(N)) - 1 for d in range(3)], axis=1)
+    boxes = [((0, 0, 0), (23, 23, 47)), ((24, 0, 0), (47, 23, 47)), ((0, 24, 0), (23, 47, 47)), ((24, 24, 0), (47, 47, 47))]
+    level = orc.Level(3, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), boxes, (4,) * 3)
+    eu, ef = _run_level_case(api, level, "IB_6", X, F)
+    assert eu <= TOL and ef <= TOL
+
+
+def test_c4_two_level_amr_fine_patches(api):
+    """C4 (reduced): the finest level (ratio 4 of a 16^3 coarse grid -> 64^3 index space) exists only over the
+    central region, 2x2x2 patches of 16^3; markers on a sphere at least gcw fine cells inside it
+    (IBMethod::setupTagBuffer, IBMethod.cpp:272-293).  Ghost cells facing the coarse level have no same-level
+    owner: what is spread there is dropped, and u there is whatever the CF interpolation put (here: analytic)."""
+    nfine, N = 64, 20000
+    boxes = []
+    for kz in range(2):
+        for ky in range(2):
+            for kx in range(2):
+                lo = (16 + 16 * kx, 16 + 16 * ky, 16 + 16 * kz)
+                boxes.append((lo, tuple(l + 15 for l in lo)))
+    level = orc.Level(3, (0,) * 3, (nfine,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), boxes, (3,) * 3)
+    k = np.arange(N) + 0.5
+    phi = np.arccos(1 - 2 * k / N)
+    th = np.pi * (1 + 5 ** 0.5) * k
+    X = 0.5 + 0.18 * np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1)
+    F = np.stack([2 * splitmix64_unit(1 + d, np.arange(N)) - 1 for d in range(3)], axis=1)
+    # fill_halo=True copies same-level neighbours into ghosts; CF-facing ghosts keep the uploaded analytic values
+    eu, ef = _run_level_case(api, level, "IB_4", X, F)
+    assert eu <= TOL and ef <= TOL
+
+
+@pytest.mark.parametrize("kernel", ["BSPLINE_4", "PIECEWISE_LINEAR"])
+def test_nonperiodic_walls(api, kernel):
+    """Wall-bounded domain: markers close to the walls spread into ghost cells outside the domain, which have no
+    owner and are dropped (the physical-boundary fold-back, CartSideRobinPhysBdryOp.cpp:552-617, is out of scope);
+    interiors must still equal the reference's."""
+    n, N = 24, 8000
+    g = orc.min_ghost_width(kernel)
+    boxes = [((0, 0, 0), (11, 23, 23)), ((12, 0, 0), (23, 23, 23))]
+    level = orc.Level(3, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (0, 0, 0), boxes, (g,) * 3)
+    X = np.stack([0.01 + 0.98 * splitmix64_unit(20 + d, np.arange(N)) for d in range(3)], axis=1)
+    F = np.stack([2 * splitmix64_unit(1 + d, np.arange(N)) - 1 for d in range(3)], axis=1)
+    eu, ef = _run_level_case(api, level, kernel, X, F)
+    assert eu <= TOL and ef <= TOL
