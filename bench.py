@@ -233,10 +233,9 @@ def run_gpu(args):
     rebin_ms = ctx.last_ms(2)
     touched = ib.count_touched_dofs(KERNEL)
 
-    def step():
+    def spread_part():
         if hx is None:
             ib.spreadForce(accumulate_halo=True)
-            ib.interpolateVelocity(fill_halo=True)
         else:
             lib, hnd = ctx.lib, ctx.h
             ctx.check(lib.ibk_spread_begin(hnd))
@@ -245,9 +244,18 @@ def run_gpu(args):
             ib.halo("f")
             hx.accumulate_end()
             ctx.check(lib.ibk_spread_end(hnd))
+
+    def interp_part():
+        if hx is None:
+            ib.interpolateVelocity(fill_halo=True)
+        else:
             ib.halo("u")
             hx.fill()
             ib.interpolateVelocity(fill_halo=False)
+
+    def step():
+        spread_part()
+        interp_part()
 
     def barrier():
         torch.cuda.synchronize()
@@ -282,18 +290,45 @@ def run_gpu(args):
     ms_per_step = total_ms / args.steps
 
     # ---- e2e: the same step through host buffers (pinned): X, F, u in; U, f out
+    # The u upload and the f download run on the library's copy streams (ibk_grid_*_async): u is not needed
+    # before the interpolation, so its upload overlaps the re-binning, the spread and the f download.
+    C = __import__("ctypes")
+
     def e2e_step():
         ib.setLData("X", hX.numpy())  # new positions from the host ...
-        ib.beginDataRedistribution()  # ... are re-binned on the device (wrap, cell, radix sort, permute)
         ib.setLData("F", hF.numpy())
         for a in range(3):
-            ib.grid_upload("u", 0, a, hu[a].numpy())
+            ib.grid_upload_async("u", 0, a, hu[a].numpy())
+        ib.beginDataRedistribution()  # ... are re-binned on the device (wrap, cell, radix sort, permute)
         ib.grid_fill("f", 0.0)
-        step()
-        C = __import__("ctypes")
-        ctx.check(ctx.lib.ibk_markers_download(ctx.h, 1, hU.numpy().ctypes.data_as(C.POINTER(C.c_double))))
+        spread_part()
         for a in range(3):
-            ctx.check(ctx.lib.ibk_grid_download(ctx.h, 1, 0, a, hf[a].numpy().ctypes.data_as(C.POINTER(C.c_double))))
+            ib.grid_download_async("f", 0, a, hf[a].numpy())
+        interp_part()
+        ctx.check(ctx.lib.ibk_markers_download(ctx.h, 1, hU.numpy().ctypes.data_as(C.POINTER(C.c_double))))
+        ib.transfers_wait()
+
+    if args.e2e_breakdown and rank == 0:  # diagnostic: every phase alone, synchronised (stderr)
+        def timed(label, fn):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            fn()
+            ctx.synchronize()
+            torch.cuda.synchronize()
+            print(f"[e2e breakdown] {label:28s} {(time.perf_counter() - t) * 1e3:8.2f} ms", file=sys.stderr)
+        for _ in range(2):
+            timed("X upload", lambda: ib.setLData("X", hX.numpy()))
+            timed("F upload", lambda: ib.setLData("F", hF.numpy()))
+            timed("u upload (sync api)", lambda: [ib.grid_upload("u", 0, a, hu[a].numpy()) for a in range(3)])
+            timed("u upload (async api)", lambda: [ib.grid_upload_async("u", 0, a, hu[a].numpy()) for a in range(3)])
+            timed("rebin", ib.beginDataRedistribution)
+            timed("f fill", lambda: ib.grid_fill("f", 0.0))
+            timed("spread", spread_part)
+            timed("f download (async api)", lambda: [ib.grid_download_async("f", 0, a, hf[a].numpy()) for a in range(3)])
+            timed("interp", interp_part)
+            timed("U download", lambda: ctx.check(ctx.lib.ibk_markers_download(
+                ctx.h, 1, hU.numpy().ctypes.data_as(C.POINTER(C.c_double)))))
+            timed("whole e2e step", e2e_step)
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_step()
@@ -333,7 +368,7 @@ def run_gpu(args):
             "config": workload_config(world, args),
             "e2e": {"value": total_markers / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                    "what": "host X, F, u (pinned) -> device, step, U and f -> host; all copies inside the timed region"},
+                    "what": "host X, F, u (pinned) -> device, re-bin, step, U and f -> host; all copies inside the timed region, u upload / f download on copy streams overlapping the kernels"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "spread_tile_kernel<3,IB_4> (+ fix-up)", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
@@ -364,6 +399,7 @@ def main():
     ap.add_argument("--cells", type=int, default=512, help="cells per dimension per GPU")
     ap.add_argument("--log2-markers", type=int, default=23, help="log2 of the markers per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-breakdown", action="store_true", help="print the e2e phases, each synchronised, to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

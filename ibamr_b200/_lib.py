@@ -89,6 +89,9 @@ SYMBOLS = {
     "ibk_grid_upload": (_i, [_vp, _i, _i, _i, _pd]),
     "ibk_grid_download": (_i, [_vp, _i, _i, _i, _pd]),
     "ibk_grid_fill": (_i, [_vp, _i, _d]),
+    "ibk_grid_upload_async": (_i, [_vp, _i, _i, _i, _pd]),
+    "ibk_grid_download_async": (_i, [_vp, _i, _i, _i, _pd]),
+    "ibk_transfers_wait": (_i, [_vp]),
     "ibk_markers_set_positions": (_i, [_vp, _pd, _i]),
     "ibk_markers_upload": (_i, [_vp, _i, _pd]),
     "ibk_markers_download": (_i, [_vp, _i, _pd]),

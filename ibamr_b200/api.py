@@ -398,6 +398,23 @@ class IBMethodB200:
         self.ctx.check(self.ctx.lib.ibk_grid_download(self.ctx.h, {"u": 0, "f": 1}[which], patch, axis, _dp(a)))
         return a
 
+    def grid_upload_async(self, which, patch, axis, array):
+        """Upload on the library's copy-in stream (ibk_grid_upload_async).  `array` must stay alive and
+        unmodified until transfers_wait(); page-locked memory is needed for the copy to be asynchronous."""
+        a = array
+        assert isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous
+        assert a.shape == self.side_shape(patch, axis), (a.shape, self.side_shape(patch, axis))
+        self.ctx.check(self.ctx.lib.ibk_grid_upload_async(self.ctx.h, {"u": 0, "f": 1}[which], patch, axis, _dp(a)))
+
+    def grid_download_async(self, which, patch, axis, out):
+        """Download into `out` on the copy-out stream (ibk_grid_download_async); valid after transfers_wait()."""
+        assert isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous
+        assert out.shape == self.side_shape(patch, axis), (out.shape, self.side_shape(patch, axis))
+        self.ctx.check(self.ctx.lib.ibk_grid_download_async(self.ctx.h, {"u": 0, "f": 1}[which], patch, axis, _dp(out)))
+
+    def transfers_wait(self):
+        self.ctx.check(self.ctx.lib.ibk_transfers_wait(self.ctx.h))
+
     def grid_fill(self, which, value):
         self.ctx.check(self.ctx.lib.ibk_grid_fill(self.ctx.h, {"u": 0, "f": 1}[which], float(value)))
 

@@ -127,12 +127,26 @@ extern "C" int ibk_ctx_destroy(ibk_ctx* ctx)
     ctx->b_src.release();
     ctx->b_patchbin.release();
     for (auto& b : ctx->b_io) b.release();
+    for (auto& b : ctx->b_stage) b.release();
     if (ctx->ev_created)
         for (int i = 0; i < 3; ++i)
         {
             cudaEventDestroy(ctx->ev[i][0]);
             cudaEventDestroy(ctx->ev[i][1]);
         }
+    if (ctx->xfer_created)
+    {
+        cudaStreamSynchronize(ctx->s_in);
+        cudaStreamSynchronize(ctx->s_out);
+        for (int w = 0; w < 2; ++w)
+        {
+            cudaEventDestroy(ctx->ev_in[w]);
+            cudaEventDestroy(ctx->ev_out[w]);
+        }
+        cudaEventDestroy(ctx->ev_order);
+        cudaStreamDestroy(ctx->s_in);
+        cudaStreamDestroy(ctx->s_out);
+    }
     delete ctx;
     return IBK_OK;
 }
@@ -150,6 +164,12 @@ extern "C" int ibk_ctx_synchronize(ibk_ctx* ctx)
 {
     if (!ctx) return IBK_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->L.stream));
+    if (ctx->xfer_created)
+    {
+        CK(cudaStreamSynchronize(ctx->s_in));
+        CK(cudaStreamSynchronize(ctx->s_out));
+        for (int w = 0; w < 2; ++w) ctx->pend_in[w] = ctx->pend_out[w] = false;
+    }
     return IBK_OK;
 }
 extern "C" long long ibk_ctx_launch_count(const ibk_ctx* ctx)

@@ -93,4 +93,11 @@ struct ibk_ctx
     cudaEvent_t ev[3][2];
     bool ev_valid[3] = { false, false, false };
     bool ev_created = false;
+    // asynchronous grid transfers (ibk_grid_upload_async / ibk_grid_download_async): one stream per direction,
+    // one event per (direction, array) that the compute stream waits on before it touches the array again
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2], ev_out[2], ev_order;
+    bool xfer_created = false;
+    bool pend_in[2] = { false, false }, pend_out[2] = { false, false };
+    ibk::DevBuf b_stage[3]; // staging blocks of the grid transfers: compute stream, copy-in stream, copy-out stream
 };

@@ -128,10 +128,11 @@ cudaError_t launch_unpack(Launcher& L, double* arr, long long pitch, int n1, con
                           const double* buf, int ndim, int mode);
 cudaError_t launch_fill(Launcher& L, double* ptr, size_t count, double value);
 // layout conversion: reference (dense Fortran) <-> pitched device array
+// `stage` (device, `stage_bytes`): optional staging block; with it the bytes cross the link as flat copies
 cudaError_t copy_dense_to_pitched(Launcher& L, const double* src_dense, double* dst, long long pitch, const int* n, int ndim,
-                                  cudaMemcpyKind kind);
+                                  cudaMemcpyKind kind, void* stage = nullptr, size_t stage_bytes = 0);
 cudaError_t copy_pitched_to_dense(Launcher& L, const double* src, long long pitch, double* dst_dense, const int* n, int ndim,
-                                  cudaMemcpyKind kind);
+                                  cudaMemcpyKind kind, void* stage = nullptr, size_t stage_bytes = 0);
 // AoS [n][depth] <-> SoA [depth][stride]
 cudaError_t aos_to_soa(Launcher& L, const double* d_aos, double* d_soa, long long stride, int n, int depth);
 cudaError_t soa_to_aos(Launcher& L, const double* d_soa, long long stride, double* d_aos, int n, int depth);

@@ -12,6 +12,8 @@
 // contiguous 256-byte runs.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "ibk_engine.h"
 
 namespace ibk
@@ -150,20 +152,72 @@ cudaError_t launch_fill(Launcher& L, double* ptr, size_t count, double value)
     return cudaGetLastError();
 }
 
+// Host <-> pitched device array.  cudaMemcpy2DAsync moves host->device rows of a few KB at about half the
+// link rate (measured: 30 GB/s against 55 GB/s for a flat copy of the same bytes; scripts/pcie_probe.py), so
+// with a staging buffer the bytes cross the link as flat copies of dense row blocks and a small kernel moves
+// them between the dense block and the pitched array (on the same stream: in order, no extra events).
+__global__ void repitch_kernel(const double* __restrict__ src, double* __restrict__ dst, int n0, long long src_pitch,
+                               long long dst_pitch, long long rows)
+{
+    const long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+    if (row >= rows) return;
+    const double* s = src + row * src_pitch;
+    double* d = dst + row * dst_pitch;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+static cudaError_t launch_repitch(Launcher& L, const double* src, double* dst, int n0, long long src_pitch, long long dst_pitch,
+                                  long long rows)
+{
+    const dim3 block(128, 2);
+    const long long by = (rows + block.y - 1) / block.y;
+    for (long long r0 = 0; r0 < by; r0 += 65535) // gridDim.y limit
+    {
+        const long long nby = std::min<long long>(65535, by - r0);
+        const long long row0 = r0 * block.y;
+        repitch_kernel<<<dim3((unsigned)std::max(1, std::min(8, (n0 + 127) / 128)), (unsigned)nby), block, 0, L.stream>>>(
+            src + row0 * src_pitch, dst + row0 * dst_pitch, n0, src_pitch, dst_pitch, std::min<long long>(rows - row0, nby * block.y));
+        L.launches++;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t copy_dense_to_pitched(Launcher& L, const double* src_dense, double* dst, long long pitch, const int* n, int ndim,
-                                  cudaMemcpyKind kind)
+                                  cudaMemcpyKind kind, void* stage, size_t stage_bytes)
 {
     const size_t rows = (size_t)n[1] * (ndim == 3 ? n[2] : 1);
-    return cudaMemcpy2DAsync(dst, (size_t)pitch * sizeof(double), src_dense, (size_t)n[0] * sizeof(double),
-                             (size_t)n[0] * sizeof(double), rows, kind, L.stream);
+    const size_t row_bytes = (size_t)n[0] * sizeof(double);
+    if (pitch == n[0]) return cudaMemcpyAsync(dst, src_dense, rows * row_bytes, kind, L.stream);
+    if (!stage || stage_bytes < row_bytes)
+        return cudaMemcpy2DAsync(dst, (size_t)pitch * sizeof(double), src_dense, row_bytes, row_bytes, rows, kind, L.stream);
+    const size_t rows_per_chunk = stage_bytes / row_bytes;
+    cudaError_t e;
+    for (size_t r = 0; r < rows; r += rows_per_chunk)
+    {
+        const size_t nr = std::min(rows_per_chunk, rows - r);
+        if ((e = cudaMemcpyAsync(stage, src_dense + r * n[0], nr * row_bytes, kind, L.stream)) != cudaSuccess) return e;
+        if ((e = launch_repitch(L, (const double*)stage, dst + r * pitch, n[0], n[0], pitch, (long long)nr)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t copy_pitched_to_dense(Launcher& L, const double* src, long long pitch, double* dst_dense, const int* n, int ndim,
-                                  cudaMemcpyKind kind)
+                                  cudaMemcpyKind kind, void* stage, size_t stage_bytes)
 {
     const size_t rows = (size_t)n[1] * (ndim == 3 ? n[2] : 1);
-    return cudaMemcpy2DAsync(dst_dense, (size_t)n[0] * sizeof(double), src, (size_t)pitch * sizeof(double),
-                             (size_t)n[0] * sizeof(double), rows, kind, L.stream);
+    const size_t row_bytes = (size_t)n[0] * sizeof(double);
+    if (pitch == n[0]) return cudaMemcpyAsync(dst_dense, src, rows * row_bytes, kind, L.stream);
+    if (!stage || stage_bytes < row_bytes)
+        return cudaMemcpy2DAsync(dst_dense, row_bytes, src, (size_t)pitch * sizeof(double), row_bytes, rows, kind, L.stream);
+    const size_t rows_per_chunk = stage_bytes / row_bytes;
+    cudaError_t e;
+    for (size_t r = 0; r < rows; r += rows_per_chunk)
+    {
+        const size_t nr = std::min(rows_per_chunk, rows - r);
+        if ((e = launch_repitch(L, src + r * pitch, (double*)stage, n[0], pitch, n[0], (long long)nr)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(dst_dense + r * n[0], stage, nr * row_bytes, kind, L.stream)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 __global__ void aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ soa, long long stride, int n, int depth)

@@ -497,6 +497,12 @@ extern "C" int ibk_level_destroy(ibk_ctx* ctx)
     LevelState& lv = ctx->lv;
     if (!lv.valid) return IBK_OK;
     cudaStreamSynchronize(ctx->L.stream);
+    if (ctx->xfer_created)
+    {
+        cudaStreamSynchronize(ctx->s_in);
+        cudaStreamSynchronize(ctx->s_out);
+        for (int w = 0; w < 2; ++w) ctx->pend_in[w] = ctx->pend_out[w] = false;
+    }
     for (auto& ps : lv.patches)
         for (int a = 0; a < 3; ++a)
         {
@@ -618,29 +624,118 @@ static int check_patch_axis(ibk_ctx* ctx, int which, int patch, int axis)
     return IBK_OK;
 }
 
+constexpr size_t STAGE_BYTES = 64u << 20; // dense row blocks of the grid transfers (see copy_dense_to_pitched)
+
+// ---- asynchronous transfers: uploads and downloads of grid data on their own streams, so that the PCIe
+// traffic of one array overlaps the kernels (and the opposite-direction traffic) of another.
+static cudaError_t xfer_init(ibk_ctx* ctx)
+{
+    if (ctx->xfer_created) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (int w = 0; w < 2; ++w)
+    {
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_in[w], cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_out[w], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming)) != cudaSuccess) return e;
+    ctx->xfer_created = true;
+    return cudaSuccess;
+}
+// `stream` waits for the asynchronous transfers in flight that touch array `which` (0 = u, 1 = f)
+static cudaError_t grid_deps(ibk_ctx* ctx, int which, cudaStream_t stream)
+{
+    cudaError_t e;
+    if (ctx->pend_in[which] && stream != ctx->s_in)
+        if ((e = cudaStreamWaitEvent(stream, ctx->ev_in[which], 0)) != cudaSuccess) return e;
+    if (ctx->pend_out[which] && stream != ctx->s_out)
+        if ((e = cudaStreamWaitEvent(stream, ctx->ev_out[which], 0)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+#define GRID_DEPS(which) CK(grid_deps(ctx, (which), ctx->L.stream))
+
 extern "C" int ibk_grid_upload(ibk_ctx* ctx, int which, int patch, int axis, const double* h_data)
 {
     NEED_LEVEL();
     if (int rc = check_patch_axis(ctx, which, patch, axis)) return rc;
+    GRID_DEPS(which);
     PatchState& ps = ctx->lv.patches[patch];
+    CK(ctx->b_stage[0].reserve(STAGE_BYTES));
     CK(copy_dense_to_pitched(ctx->L, h_data, which == 0 ? ps.u[axis] : ps.f[axis], ps.pitch[axis], ps.n[axis], ctx->lv.ndim,
-                             cudaMemcpyHostToDevice));
+                             cudaMemcpyHostToDevice, ctx->b_stage[0].p, STAGE_BYTES));
     return IBK_OK;
 }
 extern "C" int ibk_grid_download(ibk_ctx* ctx, int which, int patch, int axis, double* h_data)
 {
     NEED_LEVEL();
     if (int rc = check_patch_axis(ctx, which, patch, axis)) return rc;
+    GRID_DEPS(which);
     PatchState& ps = ctx->lv.patches[patch];
+    CK(ctx->b_stage[0].reserve(STAGE_BYTES));
     CK(copy_pitched_to_dense(ctx->L, which == 0 ? ps.u[axis] : ps.f[axis], ps.pitch[axis], h_data, ps.n[axis], ctx->lv.ndim,
-                             cudaMemcpyDeviceToHost));
+                             cudaMemcpyDeviceToHost, ctx->b_stage[0].p, STAGE_BYTES));
     CK(cudaStreamSynchronize(ctx->L.stream));
+    return IBK_OK;
+}
+extern "C" int ibk_grid_upload_async(ibk_ctx* ctx, int which, int patch, int axis, const double* h_data)
+{
+    NEED_LEVEL();
+    if (int rc = check_patch_axis(ctx, which, patch, axis)) return rc;
+    if (!h_data) return fail(ctx, IBK_ERR_INVALID, "null host pointer");
+    CK(xfer_init(ctx));
+    // the copy is ordered after the work already queued on the compute stream (which may still read the
+    // array) and after a download of the same array that is in flight
+    CK(cudaEventRecord(ctx->ev_order, ctx->L.stream));
+    CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_order, 0));
+    CK(grid_deps(ctx, which, ctx->s_in));
+    PatchState& ps = ctx->lv.patches[patch];
+    Launcher Lin = ctx->L;
+    Lin.stream = ctx->s_in;
+    CK(ctx->b_stage[1].reserve(STAGE_BYTES));
+    CK(copy_dense_to_pitched(Lin, h_data, which == 0 ? ps.u[axis] : ps.f[axis], ps.pitch[axis], ps.n[axis], ctx->lv.ndim,
+                             cudaMemcpyHostToDevice, ctx->b_stage[1].p, STAGE_BYTES));
+    ctx->L.launches += Lin.launches - ctx->L.launches;
+    CK(cudaEventRecord(ctx->ev_in[which], ctx->s_in));
+    ctx->pend_in[which] = true;
+    return IBK_OK;
+}
+extern "C" int ibk_grid_download_async(ibk_ctx* ctx, int which, int patch, int axis, double* h_data)
+{
+    NEED_LEVEL();
+    if (int rc = check_patch_axis(ctx, which, patch, axis)) return rc;
+    if (!h_data) return fail(ctx, IBK_ERR_INVALID, "null host pointer");
+    CK(xfer_init(ctx));
+    CK(cudaEventRecord(ctx->ev_order, ctx->L.stream));
+    CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_order, 0));
+    CK(grid_deps(ctx, which, ctx->s_out));
+    PatchState& ps = ctx->lv.patches[patch];
+    Launcher Lout = ctx->L;
+    Lout.stream = ctx->s_out;
+    CK(ctx->b_stage[2].reserve(STAGE_BYTES));
+    CK(copy_pitched_to_dense(Lout, which == 0 ? ps.u[axis] : ps.f[axis], ps.pitch[axis], h_data, ps.n[axis], ctx->lv.ndim,
+                             cudaMemcpyDeviceToHost, ctx->b_stage[2].p, STAGE_BYTES));
+    ctx->L.launches += Lout.launches - ctx->L.launches;
+    CK(cudaEventRecord(ctx->ev_out[which], ctx->s_out));
+    ctx->pend_out[which] = true;
+    return IBK_OK;
+}
+extern "C" int ibk_transfers_wait(ibk_ctx* ctx)
+{
+    if (!ctx) return IBK_ERR_INVALID;
+    if (ctx->xfer_created)
+    {
+        CK(cudaStreamSynchronize(ctx->s_in));
+        CK(cudaStreamSynchronize(ctx->s_out));
+    }
+    for (int w = 0; w < 2; ++w) ctx->pend_in[w] = ctx->pend_out[w] = false;
     return IBK_OK;
 }
 extern "C" int ibk_grid_fill(ibk_ctx* ctx, int which, double value)
 {
     NEED_LEVEL();
     if (which < 0 || which > 1) return fail(ctx, IBK_ERR_INVALID, "which must be 0 (u) or 1 (f)");
+    GRID_DEPS(which);
     for (auto& ps : ctx->lv.patches)
         for (int a = 0; a < ctx->lv.ndim; ++a) CK(launch_fill(ctx->L, which == 0 ? ps.u[a] : ps.f[a], ps.elems[a], value));
     return IBK_OK;
@@ -649,6 +744,7 @@ extern "C" int ibk_grid_device_ptr(ibk_ctx* ctx, int which, int patch, int axis,
 {
     NEED_LEVEL();
     if (int rc = check_patch_axis(ctx, which, patch, axis)) return rc;
+    GRID_DEPS(which);
     PatchState& ps = ctx->lv.patches[patch];
     if (d_ptr) *d_ptr = which == 0 ? ps.u[axis] : ps.f[axis];
     if (pitch) *pitch = ps.pitch[axis];
@@ -855,6 +951,7 @@ extern "C" int ibk_halo_local(ibk_ctx* ctx, int which)
     LevelExtra* ex = extra_of(ctx, false);
     if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
     if (which < 0 || which > 1) return fail(ctx, IBK_ERR_INVALID, "which must be 0 (u: fill) or 1 (f: accumulate)");
+    GRID_DEPS(which);
     const int ndim = lv.ndim, P = (int)lv.patches.size();
     const unsigned nslab = 2 * ndim;
     if (which == 1)
@@ -908,6 +1005,7 @@ extern "C" int ibk_halo_pack(ibk_ctx* ctx, int which, int patch, int axis, const
     NEED_LEVEL();
     int off[3], ext[3];
     if (int rc = region_args(ctx, which, patch, axis, lower, upper, off, ext)) return rc;
+    GRID_DEPS(which);
     PatchState& ps = ctx->lv.patches[patch];
     CK(launch_pack(ctx->L, which == 0 ? ps.u[axis] : ps.f[axis], ps.pitch[axis], ps.n[axis][1], off, ext, d_buf, ctx->lv.ndim));
     return IBK_OK;
@@ -918,6 +1016,7 @@ extern "C" int ibk_halo_unpack(ibk_ctx* ctx, int which, int patch, int axis, con
     NEED_LEVEL();
     int off[3], ext[3];
     if (int rc = region_args(ctx, which, patch, axis, lower, upper, off, ext)) return rc;
+    GRID_DEPS(which);
     PatchState& ps = ctx->lv.patches[patch];
     CK(launch_unpack(ctx->L, which == 0 ? ps.u[axis] : ps.f[axis], ps.pitch[axis], ps.n[axis][1], off, ext, d_buf, ctx->lv.ndim,
                      mode));
@@ -946,6 +1045,7 @@ static int face_layers(ibk_ctx* ctx, int mode)
 extern "C" int ibk_spread_begin(ibk_ctx* ctx)
 {
     NEED_LEVEL();
+    GRID_DEPS(1);
     LevelState& lv = ctx->lv;
     LevelExtra* ex = extra_of(ctx, false);
     if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
@@ -963,12 +1063,14 @@ extern "C" int ibk_spread_begin(ibk_ctx* ctx)
 extern "C" int ibk_spread_end(ibk_ctx* ctx)
 {
     NEED_LEVEL();
+    GRID_DEPS(1);
     return face_layers(ctx, 1);
 }
 
 static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo)
 {
     NEED_LEVEL();
+    GRID_DEPS(op == 1 ? 1 : 0);
     LevelState& lv = ctx->lv;
     if (!lv.binned) return fail(ctx, IBK_ERR_STATE, "markers are not binned: call ibk_rebin first");
     const int kernel = ibk_kernel_from_string(fcn);

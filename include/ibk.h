@@ -268,6 +268,17 @@ int ibk_level_destroy(ibk_ctx* ctx);
 int ibk_grid_upload(ibk_ctx* ctx, int which, int patch, int axis, const double* h_data);
 int ibk_grid_download(ibk_ctx* ctx, int which, int patch, int axis, double* h_data);
 int ibk_grid_fill(ibk_ctx* ctx, int which, double value); /* HierarchyDataOpsReal::setToScalar */
+/* The same transfers on the library's own copy streams (one per direction), so the PCIe traffic of one
+ * array overlaps the kernels working on another and the traffic in the opposite direction.  h_data should be
+ * page-locked (cudaHostRegister / cudaHostAlloc) or the copy degrades to a synchronous one.  Ordering is kept
+ * by the library: an upload starts after the kernels already queued that read the array; every later call
+ * that touches the array waits (on the device) for its transfers in flight.  The HOST may read a downloaded
+ * array, or reuse an uploaded one, only after ibk_transfers_wait.  These replace the copies SAMRAI's
+ * schedules make between the integrator's u/f patch data and the IB scratch data
+ * (src/IB/IBHierarchyIntegrator.cpp:300-303 registers d_u_idx / d_f_idx, :366-377 their fill schedules). */
+int ibk_grid_upload_async(ibk_ctx* ctx, int which, int patch, int axis, const double* h_data);
+int ibk_grid_download_async(ibk_ctx* ctx, int which, int patch, int axis, double* h_data);
+int ibk_transfers_wait(ibk_ctx* ctx);
 
 /* LData role: marker columns, AoS on the host side, SoA fp64 on the device.
  * ibk_markers_set_positions replaces LData("X") setup (LDataManager.cpp:2187-2197) and resets

@@ -482,6 +482,58 @@ def test_spread_is_bit_reproducible(api):
         assert np.array_equal(runs[0][a], runs[2][a])
 
 
+def test_async_transfers_match_synchronous_ones(api):
+    """ibk_grid_upload_async / ibk_grid_download_async (copy streams, device-side ordering) give the bits of
+    the synchronous path: u uploaded while the spread runs, f downloaded while the interpolation runs."""
+    import torch
+    ndim, n, kernel = 3, 64, "IB_4"
+    level = _level_case(ndim, n, (2, 1, 1), kernel)
+    N = 60000
+    X = np.stack([_uniform(181 + d, N, 0.0, 1.0) for d in range(3)], axis=1)
+    F = np.stack([_uniform(191 + d, N, -1.0, 1.0) for d in range(3)], axis=1)
+
+    def make():
+        ib = api.IBMethodB200(3, (0,) * 3, (n - 1,) * 3, (0.0,) * 3, (1.0,) * 3, (1,) * 3, level.boxes, kernel_fcn=kernel)
+        ib.setPositions(X)
+        ib.setLData("F", F)
+        ib.beginDataRedistribution()
+        return ib
+
+    P = len(level.boxes)
+    ref = make()
+    u = [[np.ascontiguousarray(_uniform(7 + 10 * p + a, int(np.prod(ref.side_shape(p, a))), -1.0, 1.0)
+                               .reshape(ref.side_shape(p, a))) for a in range(3)] for p in range(P)]
+    for p in range(P):
+        for a in range(3):
+            ref.grid_upload("u", p, a, u[p][a])
+    ref.spreadForce(accumulate_halo=True)
+    ref.interpolateVelocity(fill_halo=True)
+    f_ref = [[ref.grid_download("f", p, a) for a in range(3)] for p in range(P)]
+    U_ref = ref.getLData("U")
+    ref.close()
+
+    ib = make()
+    for rep in range(2):  # the second pass re-uses the arrays while transfers of the first could still be in flight
+        hu = [[torch.from_numpy(u[p][a]).pin_memory() for a in range(3)] for p in range(P)]
+        hf = [[torch.zeros(ib.side_shape(p, a), dtype=torch.float64).pin_memory() for a in range(3)] for p in range(P)]
+        for p in range(P):
+            for a in range(3):
+                ib.grid_upload_async("u", p, a, hu[p][a].numpy())
+        ib.grid_fill("f", 0.0)
+        ib.spreadForce(accumulate_halo=True)
+        for p in range(P):
+            for a in range(3):
+                ib.grid_download_async("f", p, a, hf[p][a].numpy())
+        ib.interpolateVelocity(fill_halo=True)
+        U = ib.getLData("U")
+        ib.transfers_wait()
+        assert np.array_equal(U, U_ref)
+        for p in range(P):
+            for a in range(3):
+                assert np.array_equal(hf[p][a].numpy(), f_ref[p][a])
+    ib.close()
+
+
 @pytest.mark.parametrize("kernel", ["IB_4", "IB_6"])
 def test_adjointness_and_moments_large(api, kernel):
     """Size-independent properties on a larger case (oracle not needed):
