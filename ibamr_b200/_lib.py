@@ -97,6 +97,11 @@ SYMBOLS = {
     "ibk_markers_download": (_i, [_vp, _i, _pd]),
     "ibk_markers_count": (_i, [_vp]),
     "ibk_rebin": (_i, [_vp, _i]),
+    "ibk_markers_set_ids": (_i, [_vp, C.POINTER(C.c_uint), C.c_uint]),
+    "ibk_markers_get_ids": (_i, [_vp, C.POINTER(C.c_uint)]),
+    "ibk_migrate_plan": (_i, [_vp, _i, _pi, _pi, _pi, _i, _i, _pi]),
+    "ibk_migrate_pack": (_i, [_vp, _vp]),
+    "ibk_migrate_unpack": (_i, [_vp, _vp, _i, C.c_uint]),
     "ibk_bin_get_cells": (_i, [_vp, _pi, _pi]),
     "ibk_bin_get_order": (_i, [_vp, _pi]),
     "ibk_spread_force": (_i, [_vp, _s, _i]),

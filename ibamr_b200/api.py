@@ -449,6 +449,34 @@ class IBMethodB200:
             self.ctx.check(self.ctx.lib.ibk_bin_get_cells(self.ctx.h, _ip(cells), _ip(owner)))
         return cells, owner
 
+    # -- several processes: global Lagrangian indices, marker migration (LDataManager.cpp:1519-1959) --
+    def setIds(self, ids, id_bound):
+        """Global Lagrangian index of every host row (ibk_markers_set_ids)."""
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        assert a.shape == (self.n_markers,)
+        self.ctx.check(self.ctx.lib.ibk_markers_set_ids(self.ctx.h, a.ctypes.data_as(C.POINTER(C.c_uint)), int(id_bound)))
+
+    def getIds(self):
+        a = np.zeros(self.n_markers, dtype=np.uint32)
+        if self.n_markers:
+            self.ctx.check(self.ctx.lib.ibk_markers_get_ids(self.ctx.h, a.ctypes.data_as(C.POINTER(C.c_uint))))
+        return a
+
+    def migrate_plan(self, patch_lower, patch_upper, patch_rank, n_ranks, my_rank):
+        """Send counts per destination rank for the markers no local patch accepted (ibk_migrate_plan)."""
+        lo, hi, rk = _i32(patch_lower).reshape(-1), _i32(patch_upper).reshape(-1), _i32(patch_rank).reshape(-1)
+        counts = np.zeros(n_ranks, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.ibk_migrate_plan(self.ctx.h, len(rk), _ip(lo), _ip(hi), _ip(rk), int(n_ranks), int(my_rank),
+                                                     _ip(counts)))
+        return counts
+
+    def migrate_pack(self, device_ptr):
+        self.ctx.check(self.ctx.lib.ibk_migrate_pack(self.ctx.h, C.c_void_p(device_ptr)))
+
+    def migrate_unpack(self, device_ptr, n_recv, id_bound):
+        self.ctx.check(self.ctx.lib.ibk_migrate_unpack(self.ctx.h, C.c_void_p(device_ptr), int(n_recv), int(id_bound)))
+        self.n_markers = int(self.ctx.lib.ibk_markers_count(self.ctx.h))
+
     def getSortedLagrangianIndices(self):
         lag = np.zeros(self.n_markers, dtype=np.int32)
         if self.n_markers:

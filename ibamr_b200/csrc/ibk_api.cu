@@ -128,6 +128,7 @@ extern "C" int ibk_ctx_destroy(ibk_ctx* ctx)
     ctx->b_patchbin.release();
     for (auto& b : ctx->b_io) b.release();
     for (auto& b : ctx->b_stage) b.release();
+    for (auto& b : ctx->b_mig) b.release();
     if (ctx->ev_created)
         for (int i = 0; i < 3; ++i)
         {

@@ -67,7 +67,12 @@ struct LevelState
     double* U = nullptr;
     double* F = nullptr;
     double* tmp = nullptr;    // [ndim][stride] permutation scratch
-    uint32_t* lag = nullptr;  // storage position -> Lagrangian index
+    uint32_t* lag = nullptr;  // storage position -> row of the host AoS arrays (= Lagrangian index unless gid is set)
+    uint32_t* gid = nullptr;  // optional: storage position -> global Lagrangian index (multi-rank; ibk_markers_set_ids)
+    uint32_t id_bound = 0;    // exclusive upper bound of the global indices (sizes the tie bits of the sort key)
+    // migration state between ibk_migrate_plan and ibk_migrate_unpack
+    const uint32_t* mig_order = nullptr; // tail markers grouped by destination rank
+    int mig_n = -1;
     uint32_t* lag_prev = nullptr; // the same map as it was when the binning products were written
     int* cells = nullptr;     // [n][ndim], in lag_prev storage order
     int* owner = nullptr;     // [n]
@@ -99,5 +104,6 @@ struct ibk_ctx
     cudaEvent_t ev_in[2], ev_out[2], ev_order;
     bool xfer_created = false;
     bool pend_in[2] = { false, false }, pend_out[2] = { false, false };
+    ibk::DevBuf b_mig[8];   // marker migration scratch (keys/vals ping-pong, sort temp, box list, offsets)
     ibk::DevBuf b_stage[3]; // staging blocks of the grid transfers: compute stream, copy-in stream, copy-out stream
 };

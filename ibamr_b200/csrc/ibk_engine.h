@@ -90,6 +90,18 @@ cudaError_t scatter_columns(Launcher& L, const double* d_in, long long in_stride
                             const uint32_t* d_perm, int n, int ncols);
 cudaError_t extract_low32(Launcher& L, const uint64_t* d_keys, uint32_t* d_out, int n, int bits);
 
+// ibk_migrate.cu
+cudaError_t migrate_dest(Launcher& L, const CellGeom& cg, const int* d_plo, const int* d_phi, const int* d_prank, int n_patches,
+                         int n_ranks, const double* X, long long stride, int first, int n_tail, uint64_t* keys, uint32_t* vals);
+cudaError_t bucket_offsets(Launcher& L, const uint64_t* keys_sorted, int n, int n_buckets, int* d_start);
+cudaError_t migrate_pack(Launcher& L, const uint32_t* order, int n_send, const double* X, const double* U, const double* F,
+                         long long stride, int ndim, const uint32_t* gid, double* buf);
+cudaError_t migrate_append(Launcher& L, const double* buf, int n_recv, int at, double* X, double* U, double* F, long long stride,
+                           int ndim, uint32_t* gid);
+cudaError_t id_keys(Launcher& L, const uint32_t* gid, int n, uint64_t* keys, uint32_t* vals);
+cudaError_t rank_scatter(Launcher& L, const uint32_t* sorted_pos, int n, uint32_t* row);
+cudaError_t gather_u32(Launcher& L, const uint32_t* in, const uint32_t* perm, int n, uint32_t* out);
+
 // ibk_interp.cu / ibk_spread.cu
 // Marker data for the tile kernels, in SORTED order (entry i of the bins).
 struct MarkerView

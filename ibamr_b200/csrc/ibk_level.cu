@@ -511,7 +511,7 @@ extern "C" int ibk_level_destroy(ibk_ctx* ctx)
         }
     if (lv.d_bins) cudaFree(lv.d_bins);
     for (void* p : { (void*)lv.X, (void*)lv.U, (void*)lv.F, (void*)lv.tmp, (void*)lv.lag, (void*)lv.lag_prev,
-                     (void*)lv.cells, (void*)lv.owner, (void*)lv.escaped })
+                     (void*)lv.gid, (void*)lv.cells, (void*)lv.owner, (void*)lv.escaped })
         if (p) cudaFree(p);
     bins_free(lv.bins);
     extra_drop(ctx);
@@ -756,27 +756,45 @@ extern "C" int ibk_grid_device_ptr(ibk_ctx* ctx, int which, int patch, int axis,
 // ---------------------------------------------------------------------------------------------
 // markers
 // ---------------------------------------------------------------------------------------------
-static int reserve_markers(ibk_ctx* ctx, int n)
+// Capacity for n markers; the first n_keep entries of every column survive a reallocation.
+static int reserve_markers(ibk_ctx* ctx, int n, int n_keep = 0)
 {
     LevelState& lv = ctx->lv;
     if ((long long)n <= lv.stride) return IBK_OK;
     const long long stride = ((long long)std::max(n, 1024) + 31) / 32 * 32;
+    const int ndim = lv.ndim;
     for (double** pp : { &lv.X, &lv.U, &lv.F, &lv.tmp })
     {
-        if (*pp) cudaFree(*pp);
-        *pp = nullptr;
-        CK(cudaMalloc(pp, sizeof(double) * (size_t)stride * lv.ndim));
-        CK(cudaMemsetAsync(*pp, 0, sizeof(double) * (size_t)stride * lv.ndim, ctx->L.stream));
+        double* fresh = nullptr;
+        CK(cudaMalloc(&fresh, sizeof(double) * (size_t)stride * ndim));
+        CK(cudaMemsetAsync(fresh, 0, sizeof(double) * (size_t)stride * ndim, ctx->L.stream));
+        if (*pp && n_keep > 0 && pp != &lv.tmp)
+            CK(cudaMemcpy2DAsync(fresh, sizeof(double) * (size_t)stride, *pp, sizeof(double) * (size_t)lv.stride,
+                                 sizeof(double) * (size_t)n_keep, ndim, cudaMemcpyDeviceToDevice, ctx->L.stream));
+        if (*pp)
+        {
+            CK(cudaStreamSynchronize(ctx->L.stream));
+            cudaFree(*pp);
+        }
+        *pp = fresh;
     }
-    for (uint32_t** pp : { &lv.lag, &lv.lag_prev })
+    for (uint32_t** pp : { &lv.lag, &lv.lag_prev, &lv.gid })
     {
-        if (*pp) cudaFree(*pp);
-        *pp = nullptr;
-        CK(cudaMalloc(pp, sizeof(uint32_t) * (size_t)stride));
+        if (pp == &lv.gid && !lv.gid) continue; // global ids only once they were set
+        uint32_t* fresh = nullptr;
+        CK(cudaMalloc(&fresh, sizeof(uint32_t) * (size_t)stride));
+        if (*pp && n_keep > 0)
+            CK(cudaMemcpyAsync(fresh, *pp, sizeof(uint32_t) * (size_t)n_keep, cudaMemcpyDeviceToDevice, ctx->L.stream));
+        if (*pp)
+        {
+            CK(cudaStreamSynchronize(ctx->L.stream));
+            cudaFree(*pp);
+        }
+        *pp = fresh;
     }
     if (lv.cells) cudaFree(lv.cells);
     if (lv.owner) cudaFree(lv.owner);
-    CK(cudaMalloc(&lv.cells, sizeof(int) * (size_t)stride * lv.ndim));
+    CK(cudaMalloc(&lv.cells, sizeof(int) * (size_t)stride * ndim));
     CK(cudaMalloc(&lv.owner, sizeof(int) * (size_t)stride));
     lv.stride = stride;
     return IBK_OK;
@@ -824,6 +842,10 @@ extern "C" int ibk_markers_set_positions(ibk_ctx* ctx, const double* h_X, int n_
     if (int rc = reserve_markers(ctx, n_markers)) return rc;
     lv.n = n_markers;
     lv.binned = false;
+    if (lv.gid) cudaFree(lv.gid); // the numbering is reset to 0..n-1 (host rows = Lagrangian indices)
+    lv.gid = nullptr;
+    lv.id_bound = 0;
+    lv.mig_n = -1;
     if (n_markers == 0) return IBK_OK;
     iota_kernel<<<(n_markers + 255) / 256, 256, 0, ctx->L.stream>>>(lv.lag, n_markers);
     ctx->L.launches++;
@@ -877,8 +899,11 @@ extern "C" int ibk_rebin(ibk_ctx* ctx, int error_if_points_leave_domain)
         if (esc > 0) return fail(ctx, IBK_ERR_ESCAPED, "IB point has escaped from the computational domain!");
     }
     if (n > 0) CK(cudaMemcpyAsync(lv.lag_prev, lv.lag, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->L.stream));
-    CK(bins_build(lv.bins, ctx->L, cg, lv.d_bins, (int)lv.h_bins.size(), lv.h_bins.data(), lv.X, lv.stride, lv.lag,
-                  (uint32_t)std::max(n, 1), n, lv.cells, lv.owner));
+    // in-cell order = ascending Lagrangian index (LDataManager.cpp:1505): the global one when it is known
+    CK(bins_build(lv.bins, ctx->L, cg, lv.d_bins, (int)lv.h_bins.size(), lv.h_bins.data(), lv.X, lv.stride,
+                  lv.gid ? lv.gid : lv.lag, lv.gid ? std::max(lv.id_bound, 1u) : (uint32_t)std::max(n, 1), n, lv.cells,
+                  lv.owner));
+    lv.mig_n = -1;
     if (n > 0)
     {
         const uint32_t* perm = lv.bins.vals[lv.bins.sorted_in];
@@ -888,7 +913,13 @@ extern "C" int ibk_rebin(ibk_ctx* ctx, int error_if_points_leave_domain)
             CK(gather_columns(ctx->L, *col, lv.stride, lv.tmp, lv.stride, perm, n, ndim));
             std::swap(*col, lv.tmp);
         }
-        CK(extract_low32(ctx->L, lv.bins.keys[lv.bins.sorted_in], lv.lag, n, lv.bins.tie_bits));
+        if (lv.gid)
+        {
+            CK(extract_low32(ctx->L, lv.bins.keys[lv.bins.sorted_in], lv.gid, n, lv.bins.tie_bits));
+            CK(gather_u32(ctx->L, lv.lag_prev, perm, n, lv.lag));
+        }
+        else
+            CK(extract_low32(ctx->L, lv.bins.keys[lv.bins.sorted_in], lv.lag, n, lv.bins.tie_bits));
     }
     lv.binned = true;
     if (ctx->timing)
@@ -927,8 +958,160 @@ extern "C" int ibk_bin_get_order(ibk_ctx* ctx, int* h_lag_idx)
     LevelState& lv = ctx->lv;
     if (!lv.binned) return fail(ctx, IBK_ERR_STATE, "ibk_rebin has not run");
     if (lv.n == 0 || !h_lag_idx) return IBK_OK;
-    CK(cudaMemcpyAsync(h_lag_idx, lv.lag, sizeof(uint32_t) * (size_t)lv.n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaMemcpyAsync(h_lag_idx, lv.gid ? lv.gid : lv.lag, sizeof(uint32_t) * (size_t)lv.n, cudaMemcpyDeviceToHost,
+                       ctx->L.stream));
     CK(cudaStreamSynchronize(ctx->L.stream));
+    return IBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// marker migration between ranks (LDataManager::endDataRedistribution's scatter, LDataManager.cpp:1824-1837)
+// ---------------------------------------------------------------------------------------------
+static int n_active_of(const LevelState& lv)
+{
+    int n_active = 0;
+    for (int v : lv.bins.range_last) n_active = std::max(n_active, v);
+    return n_active;
+}
+static int ceil_log2_u(uint32_t v)
+{
+    int b = 1;
+    while (b < 32 && (1ull << b) < (unsigned long long)v) ++b;
+    return b;
+}
+
+extern "C" int ibk_markers_set_ids(ibk_ctx* ctx, const unsigned* h_ids, unsigned id_bound)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (!h_ids && lv.n > 0) return fail(ctx, IBK_ERR_INVALID, "null id array");
+    if (lv.n == 0)
+    {
+        lv.id_bound = id_bound;
+        return IBK_OK;
+    }
+    if (!lv.gid) CK(cudaMalloc(&lv.gid, sizeof(uint32_t) * (size_t)lv.stride));
+    CK(ctx->b_mig[1].reserve(sizeof(uint32_t) * (size_t)lv.n));
+    CK(cudaMemcpyAsync(ctx->b_mig[1].p, h_ids, sizeof(uint32_t) * (size_t)lv.n, cudaMemcpyHostToDevice, ctx->L.stream));
+    CK(gather_u32(ctx->L, ctx->b_mig[1].as<uint32_t>(), lv.lag, lv.n, lv.gid)); // host rows -> storage order
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    lv.id_bound = id_bound;
+    lv.binned = false;
+    return IBK_OK;
+}
+extern "C" int ibk_markers_get_ids(ibk_ctx* ctx, unsigned* h_ids)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (lv.n == 0) return IBK_OK;
+    if (!h_ids) return fail(ctx, IBK_ERR_INVALID, "null id array");
+    std::vector<uint32_t> row(lv.n), id(lv.n);
+    CK(cudaMemcpyAsync(row.data(), lv.lag, sizeof(uint32_t) * (size_t)lv.n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaMemcpyAsync(id.data(), lv.gid ? lv.gid : lv.lag, sizeof(uint32_t) * (size_t)lv.n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    for (int i = 0; i < lv.n; ++i) h_ids[row[i]] = id[i];
+    return IBK_OK;
+}
+
+extern "C" int ibk_migrate_plan(ibk_ctx* ctx, int n_patches, const int* patch_lower, const int* patch_upper, const int* patch_rank,
+                                int n_ranks, int my_rank, int* h_send_counts)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (!lv.binned) return fail(ctx, IBK_ERR_STATE, "ibk_rebin has not run");
+    if (n_patches <= 0 || !patch_lower || !patch_upper || !patch_rank || n_ranks <= 0 || my_rank < 0 || my_rank >= n_ranks ||
+        !h_send_counts)
+        return fail(ctx, IBK_ERR_INVALID, "bad migration arguments");
+    const int ndim = lv.ndim;
+    const int n_active = n_active_of(lv), n_tail = lv.n - n_active;
+    for (int r = 0; r < n_ranks; ++r) h_send_counts[r] = 0;
+    lv.mig_n = 0;
+    lv.mig_order = nullptr;
+    if (n_tail <= 0) return IBK_OK;
+    if (!lv.gid) return fail(ctx, IBK_ERR_STATE, "markers leave this rank but no global indices were set (ibk_markers_set_ids)");
+    DevBuf* B = ctx->b_mig;
+    CK(B[0].reserve(sizeof(uint64_t) * (size_t)n_tail));
+    CK(B[1].reserve(sizeof(uint32_t) * (size_t)n_tail));
+    CK(B[2].reserve(sizeof(uint64_t) * (size_t)n_tail));
+    CK(B[3].reserve(sizeof(uint32_t) * (size_t)n_tail));
+    CK(B[4].reserve(radix_sort_temp_bytes(n_tail)));
+    CK(B[5].reserve(sizeof(int) * (size_t)n_patches * (2 * ndim + 1)));
+    CK(B[6].reserve(sizeof(int) * (size_t)(n_ranks + 2)));
+    int* d_plo = B[5].as<int>();
+    int* d_phi = d_plo + (size_t)n_patches * ndim;
+    int* d_prank = d_phi + (size_t)n_patches * ndim;
+    CK(cudaMemcpyAsync(d_plo, patch_lower, sizeof(int) * (size_t)n_patches * ndim, cudaMemcpyHostToDevice, ctx->L.stream));
+    CK(cudaMemcpyAsync(d_phi, patch_upper, sizeof(int) * (size_t)n_patches * ndim, cudaMemcpyHostToDevice, ctx->L.stream));
+    CK(cudaMemcpyAsync(d_prank, patch_rank, sizeof(int) * (size_t)n_patches, cudaMemcpyHostToDevice, ctx->L.stream));
+    CellGeom cg;
+    std::memset(&cg, 0, sizeof(cg));
+    cg.ndim = ndim;
+    cg.two_branch = 1;
+    for (int d = 0; d < ndim; ++d)
+    {
+        cg.x_lower[d] = lv.x_lower[d];
+        cg.x_upper[d] = lv.x_upper[d];
+        cg.dx[d] = lv.dx[d];
+        cg.ilower[d] = lv.domain_lower[d];
+        cg.iupper[d] = lv.domain_upper[d];
+    }
+    CK(migrate_dest(ctx->L, cg, d_plo, d_phi, d_prank, n_patches, n_ranks, lv.X, lv.stride, n_active, n_tail, B[0].as<uint64_t>(),
+                    B[1].as<uint32_t>()));
+    const int which = radix_sort_pairs(B[0].as<uint64_t>(), B[1].as<uint32_t>(), B[2].as<uint64_t>(), B[3].as<uint32_t>(), n_tail, 0,
+                                       ceil_log2_u((uint32_t)n_ranks + 1), B[4].p, ctx->L.stream, &ctx->L.launches);
+    const uint64_t* keys_sorted = which ? B[2].as<uint64_t>() : B[0].as<uint64_t>();
+    lv.mig_order = which ? B[3].as<uint32_t>() : B[1].as<uint32_t>();
+    CK(bucket_offsets(ctx->L, keys_sorted, n_tail, n_ranks + 1, B[6].as<int>()));
+    std::vector<int> start(n_ranks + 2);
+    CK(cudaMemcpyAsync(start.data(), B[6].p, sizeof(int) * start.size(), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    for (int r = 0; r < n_ranks; ++r) h_send_counts[r] = start[r + 1] - start[r];
+    if (start[n_ranks + 1] - start[n_ranks] > 0)
+        return fail(ctx, IBK_ERR_ESCAPED, "a marker lies in no patch of the level (markers must stay on the finest level)");
+    if (h_send_counts[my_rank] > 0) return fail(ctx, IBK_ERR_STATE, "a marker of a local patch was not binned locally");
+    lv.mig_n = start[n_ranks];
+    return IBK_OK;
+}
+extern "C" int ibk_migrate_pack(ibk_ctx* ctx, double* d_buf)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (lv.mig_n < 0) return fail(ctx, IBK_ERR_STATE, "ibk_migrate_plan has not run");
+    if (lv.mig_n == 0) return IBK_OK;
+    if (!d_buf) return fail(ctx, IBK_ERR_INVALID, "null buffer");
+    CK(migrate_pack(ctx->L, lv.mig_order, lv.mig_n, lv.X, lv.U, lv.F, lv.stride, lv.ndim, lv.gid, d_buf));
+    return IBK_OK;
+}
+extern "C" int ibk_migrate_unpack(ibk_ctx* ctx, const double* d_buf, int n_recv, unsigned id_bound)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (lv.mig_n < 0) return fail(ctx, IBK_ERR_STATE, "ibk_migrate_plan has not run");
+    if (n_recv < 0 || (n_recv > 0 && !d_buf)) return fail(ctx, IBK_ERR_INVALID, "bad receive buffer");
+    const int n_active = n_active_of(lv);
+    const int n_new = n_active + n_recv;
+    lv.mig_n = -1;
+    if (n_new == lv.n && n_recv == 0) return IBK_OK; // nothing left, nothing arrived
+    if (n_recv > 0 && !lv.gid) return fail(ctx, IBK_ERR_STATE, "markers arrive but no global indices were set (ibk_markers_set_ids)");
+    if (int rc = reserve_markers(ctx, n_new, n_active)) return rc;
+    if (n_recv > 0) CK(migrate_append(ctx->L, d_buf, n_recv, n_active, lv.X, lv.U, lv.F, lv.stride, lv.ndim, lv.gid));
+    lv.n = n_new;
+    lv.id_bound = std::max(lv.id_bound, id_bound);
+    lv.binned = false;
+    if (n_new > 0 && lv.gid)
+    {
+        // host rows := ascending global index among the markers now held (identity numbering for one rank)
+        DevBuf* B = ctx->b_mig;
+        CK(B[0].reserve(sizeof(uint64_t) * (size_t)n_new));
+        CK(B[1].reserve(sizeof(uint32_t) * (size_t)n_new));
+        CK(B[2].reserve(sizeof(uint64_t) * (size_t)n_new));
+        CK(B[3].reserve(sizeof(uint32_t) * (size_t)n_new));
+        CK(B[4].reserve(radix_sort_temp_bytes(n_new)));
+        CK(id_keys(ctx->L, lv.gid, n_new, B[0].as<uint64_t>(), B[1].as<uint32_t>()));
+        const int which = radix_sort_pairs(B[0].as<uint64_t>(), B[1].as<uint32_t>(), B[2].as<uint64_t>(), B[3].as<uint32_t>(), n_new,
+                                           0, ceil_log2_u(std::max(lv.id_bound, 2u)), B[4].p, ctx->L.stream, &ctx->L.launches);
+        CK(rank_scatter(ctx->L, which ? B[3].as<uint32_t>() : B[1].as<uint32_t>(), n_new, lv.lag));
+    }
     return IBK_OK;
 }
 

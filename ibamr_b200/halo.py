@@ -231,6 +231,19 @@ class IbkBackend:
         ctx.check(ctx.lib.ibk_halo_unpack(ctx.h, which, patch, axis, l.ctypes.data_as(C.POINTER(C.c_int)),
                                           h.ctypes.data_as(C.POINTER(C.c_int)), C.c_void_p(buf.data_ptr()), mode))
 
+    def migrate_plan(self, lower, upper, ranks, world, rank):
+        return self.ib.migrate_plan(lower, upper, ranks, world, rank)
+
+    def migrate_pack(self, buf):
+        self.ib.ctx.synchronize()  # the buffer was created on torch's stream
+        self.ib.migrate_pack(buf.data_ptr())
+        self.ib.ctx.synchronize()
+
+    def migrate_unpack(self, buf, n_recv, id_bound):
+        self.torch.cuda.synchronize()
+        self.ib.migrate_unpack(buf.data_ptr(), n_recv, id_bound)
+        self.ib.ctx.synchronize()
+
     def isend(self, buf, dst):
         return self.dist.P2POp(self.dist.isend, buf, dst)
 
@@ -241,6 +254,54 @@ class IbkBackend:
         if ops:
             for r in self.dist.batch_isend_irecv(ops):
                 r.wait()
+
+
+class MarkerMigration:
+    """Moves the markers whose cell now lies in another rank's patch to that rank: the scatter of
+    LDataManager::endDataRedistribution (LDataManager.cpp:1519-1959, VecScatter :1824-1837; node counts are
+    exchanged like computeNodeOffsets' allGather, :3058).  The backend plans / packs / unpacks (libibk.so's
+    ibk_migrate_* on the device, a numpy stand-in in the CPU tests); this class does the messaging: one count
+    message and one row message per peer.  Call after a re-bin; re-bin again afterwards."""
+
+    def __init__(self, patches: list, rank: int, world: int, backend, id_bound: int):
+        self.rank, self.world, self.backend, self.id_bound = rank, world, backend, int(id_bound)
+        self.lower = [list(p.lower) for p in patches]
+        self.upper = [list(p.upper) for p in patches]
+        self.ranks = [p.rank for p in patches]
+        self.ndim = len(patches[0].lower)
+        self.width = 3 * self.ndim + 1
+
+    def migrate(self):
+        """Returns (markers sent, markers received)."""
+        b = self.backend
+        send_counts = [int(c) for c in b.migrate_plan(self.lower, self.upper, self.ranks, self.world, self.rank)]
+        peers = [r for r in range(self.world) if r != self.rank]
+        # counts
+        cs = {r: b.alloc(1) for r in peers}
+        cr = {r: b.alloc(1) for r in peers}
+        for r in peers:
+            cs[r].fill_(float(send_counts[r]))
+        b.run([b.irecv(cr[r], r) for r in peers] + [b.isend(cs[r], r) for r in peers])
+        recv_counts = [0] * self.world
+        for r in peers:
+            recv_counts[r] = int(round(float(cr[r][0].item())))
+        n_send, n_recv = sum(send_counts), sum(recv_counts)
+        # rows
+        sbuf = b.alloc(n_send * self.width)
+        rbuf = b.alloc(n_recv * self.width)
+        b.migrate_pack(sbuf)
+        ops, so, ro = [], 0, 0
+        for r in range(self.world):
+            if recv_counts[r]:
+                ops.append(b.irecv(b.view(rbuf, ro * self.width, recv_counts[r] * self.width), r))
+            ro += recv_counts[r]
+        for r in range(self.world):
+            if send_counts[r]:
+                ops.append(b.isend(b.view(sbuf, so * self.width, send_counts[r] * self.width), r))
+            so += send_counts[r]
+        b.run(ops)
+        b.migrate_unpack(rbuf, n_recv, self.id_bound)
+        return n_send, n_recv
 
 
 def cartesian_patches(ndim, ranks_per_dim, cells_per_rank):

@@ -295,6 +295,31 @@ int ibk_markers_count(const ibk_ctx* ctx);
  * marker columns.  error_if_points_leave_domain follows IBMethod's flag (IBMethod.cpp:2060). */
 int ibk_rebin(ibk_ctx* ctx, int error_if_points_leave_domain);
 
+/* ---- more than one process: global Lagrangian indices and marker migration ------------------------------
+ * With one process the host rows of ibk_markers_upload/download ARE the Lagrangian indices 0..n-1.  With
+ * several, each process holds a subset: ibk_markers_set_ids attaches the global Lagrangian index of every
+ * host row (h_ids[n], all < id_bound); the in-cell order of the binning then follows the global index
+ * (LDataManager.cpp:1505).  ibk_markers_get_ids returns them in host-row order.
+ *
+ * Migration = LDataManager::endDataRedistribution's scatter of every LData row to the process that owns the
+ * marker's new cell (LDataManager.cpp:1519-1959, VecScatter :1824-1837).  After ibk_rebin the markers that no
+ * local patch accepts sit behind the binned ones; then
+ *   ibk_migrate_plan    finds their destination rank from the level's global box list (patch_lower/upper:
+ *                       [n_patches][ndim] cell boxes, patch_rank[n_patches]) and fills h_send_counts[n_ranks];
+ *                       IBK_ERR_ESCAPED if a marker lies in no patch of the level;
+ *   ibk_migrate_pack    writes sum(h_send_counts) rows of 3*ndim+1 doubles [X, U, F, index] into the DEVICE
+ *                       buffer d_buf, grouped by destination rank in ascending order (the send buffer of an
+ *                       all-to-all: MPI_Alltoallv / ncclSend+ncclRecv; ibamr_b200/halo.py::MarkerMigration);
+ *   ibk_migrate_unpack  drops the markers that left, appends the n_recv rows that arrived, and renumbers the
+ *                       host rows: ascending global index among the markers now held.  ibk_rebin must follow. */
+int ibk_markers_set_ids(ibk_ctx* ctx, const unsigned* h_ids, unsigned id_bound);
+int ibk_markers_get_ids(ibk_ctx* ctx, unsigned* h_ids);
+int ibk_migrate_plan(ibk_ctx* ctx, int n_patches, const int* patch_lower, const int* patch_upper, const int* patch_rank,
+                     int n_ranks, int my_rank, int* h_send_counts);
+int ibk_migrate_pack(ibk_ctx* ctx, double* d_buf);
+int ibk_migrate_unpack(ibk_ctx* ctx, const double* d_buf, int n_recv, unsigned id_bound);
+
+
 /* Binning products for parity checks (LIndexSetData role), in LAGRANGIAN index order:
  * cells [n][ndim] (level cell index), owner [n] (local patch number or -1). */
 int ibk_bin_get_cells(ibk_ctx* ctx, int* h_cells, int* h_owner);

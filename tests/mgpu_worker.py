@@ -3,7 +3,10 @@ markers owned by the rank whose patch holds their cell, spreadForce / interpolat
 NCCL halo exchange, gathered and compared on rank 0 with the oracle's model of the reference path
 (redundant ghost-region spreading, interiors kept; interpolation after a ghost fill).
 
-    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_worker.py IB_4
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_worker.py IB_4 [migrate]
+
+With `migrate` the markers start on arbitrary ranks and are moved to their owners first
+(halo.MarkerMigration over ibk_migrate_*; LDataManager.cpp:1824-1837).
 """
 import os
 import sys
@@ -34,6 +37,7 @@ def periodic_side_field(pg, axis, ncell, seed):
 
 def main():
     kernel = sys.argv[1] if len(sys.argv) > 1 else "IB_4"
+    migrate = len(sys.argv) > 2 and sys.argv[2] == "migrate"
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -67,9 +71,25 @@ def main():
         garbage[mask] = 1e30
         ib.grid_upload("u", 0, a, garbage)
         ib.grid_upload("f", 0, a, np.full(pg.side_shape(a), 0.25))
-    ib.setPositions(X[mine])
-    ib.setLData("F", F[mine])
-    ib.beginDataRedistribution()
+    if migrate:
+        # start from an arbitrary distribution (index mod world) and let the markers find their owners
+        start = np.arange(rank, N, world)
+        ib.setPositions(X[start])
+        ib.setLData("F", F[start])
+        ib.setIds(start, N)
+        ib.beginDataRedistribution()
+        mig = halo.MarkerMigration(patches, rank, world, halo.IbkBackend(ib, dist, torch), N)
+        n_sent, n_recv = mig.migrate()
+        ib.beginDataRedistribution()
+        assert n_sent > 0 and n_recv > 0
+        assert np.array_equal(ib.getIds(), mine), "after the migration a rank holds exactly the markers of its patch"
+        assert np.array_equal(ib.getLData("X"), X[mine]) and np.array_equal(ib.getLData("F"), F[mine])
+        assert mig.migrate() == (0, 0)
+        ib.beginDataRedistribution()
+    else:
+        ib.setPositions(X[mine])
+        ib.setLData("F", F[mine])
+        ib.beginDataRedistribution()
     # spreadForce with the inter-rank exchange interleaved (see include/ibk.h, ibk_spread_begin)
     ctx.check(ctx.lib.ibk_spread_begin(ctx.h))
     ib.spreadForce(accumulate_halo=False)
@@ -99,7 +119,7 @@ def main():
     t = torch.tensor([err_u, err_f], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"MGPU_PARITY kernel={kernel} world={world} interp_rel_err={t[0].item():.3e} spread_rel_err={t[1].item():.3e} "
+        print(f"MGPU_PARITY kernel={kernel} world={world} migrate={int(migrate)} interp_rel_err={t[0].item():.3e} spread_rel_err={t[1].item():.3e} "
               f"fill_bytes={plan.bytes_per_exchange(plan.fill)} accum_bytes={plan.bytes_per_exchange(plan.accum)}", flush=True)
         assert t[0].item() <= 1e-12 and t[1].item() <= 1e-12
     ib.close()

@@ -482,6 +482,70 @@ def test_spread_is_bit_reproducible(api):
         assert np.array_equal(runs[0][a], runs[2][a])
 
 
+def test_marker_migration_between_two_contexts(api):
+    """ibk_markers_set_ids / ibk_migrate_plan / _pack / _unpack with two contexts on one device standing for two
+    ranks (the all-to-all is a pair of device copies): afterwards each side holds exactly the markers whose cell
+    lies in its patch, rows in ascending global index, X/U/F intact, and the binning agrees with the oracle
+    (LDataManager.cpp:1475-1476 ownership, :1824-1837 scatter)."""
+    import torch
+    from ibamr_b200 import halo
+    ndim, n = 3, 16
+    patches = halo.cartesian_patches(3, (2, 1, 1), (n, n, n))
+    dom, xup = (2 * n, n, n), (2.0, 1.0, 1.0)
+    level = orc.Level(3, (0,) * 3, dom, (0.0,) * 3, xup, (1, 1, 1), [(p.lower, p.upper) for p in patches], (3,) * 3)
+    N = 30000
+    ids = np.arange(N)
+    X = np.stack([xup[d] * _uniform(141 + d, N, 0.0, 1.0) for d in range(3)], axis=1)
+    U = np.stack([_uniform(151 + d, N, -1.0, 1.0) for d in range(3)], axis=1)
+    F = np.stack([_uniform(161 + d, N, -1.0, 1.0) for d in range(3)], axis=1)
+    ref = orc.bin_level(level, X)
+    ibs, start = [], []
+    for r in range(2):
+        ib = api.IBMethodB200(3, (0,) * 3, tuple(d - 1 for d in dom), (0.0,) * 3, xup, (1, 1, 1),
+                              [(patches[r].lower, patches[r].upper)], kernel_fcn="IB_4", ctx=api.Context(0))  # one ctx per "rank"
+        st = ids[r::2] if r == 0 else ids[1::2][::-1].copy()  # rank 1 starts in descending index order
+        ib.setPositions(X[st])
+        ib.setLData("U", U[st])
+        ib.setLData("F", F[st])
+        ib.setIds(st, N)
+        ib.beginDataRedistribution()
+        ibs.append(ib)
+        start.append(st)
+    lo = [p.lower for p in patches]
+    hi = [p.upper for p in patches]
+    # a marker that lies in no patch of the level is reported like an escaped point
+    with pytest.raises(api.IBKError) as e:
+        ibs[0].migrate_plan([lo[0]], [hi[0]], [0], 1, 0)
+    assert e.value.code == api.IBK_ERR_ESCAPED
+    counts = [ibs[r].migrate_plan(lo, hi, [0, 1], 2, r) for r in range(2)]
+    assert counts[0][0] == 0 and counts[1][1] == 0 and counts[0][1] > 0 and counts[1][0] > 0
+    bufs = [torch.zeros(max(int(counts[r].sum()), 1) * 10, dtype=torch.float64, device="cuda") for r in range(2)]
+    torch.cuda.synchronize()
+    for r in range(2):
+        ibs[r].migrate_pack(bufs[r].data_ptr())
+        ibs[r].ctx.synchronize()
+    for r in range(2):
+        ibs[r].migrate_unpack(bufs[1 - r].data_ptr(), int(counts[1 - r][r]), N)
+        ibs[r].beginDataRedistribution()
+    for r in range(2):
+        mine = np.nonzero(ref["owner"] == r)[0]
+        assert ibs[r].n_markers == len(mine)
+        assert np.array_equal(ibs[r].getIds(), mine)
+        assert np.array_equal(ibs[r].getLData("X"), X[mine])
+        assert np.array_equal(ibs[r].getLData("U"), U[mine])
+        assert np.array_equal(ibs[r].getLData("F"), F[mine])
+        cells, owner = ibs[r].getCellsAndOwners()
+        assert np.array_equal(cells, ref["cells"][mine]) and np.all(owner == 0)
+        # sorted order: (cell in canonical order, then global index), as the oracle lists the patch
+        order = ibs[r].getSortedLagrangianIndices()
+        assert sorted(order.tolist()) == mine.tolist()
+        # nothing more to move
+        assert ibs[r].migrate_plan(lo, hi, [0, 1], 2, r).sum() == 0
+        ibs[r].migrate_unpack(0, 0, N)
+    for ib in ibs:
+        ib.close()
+
+
 def test_async_transfers_match_synchronous_ones(api):
     """ibk_grid_upload_async / ibk_grid_download_async (copy streams, device-side ordering) give the bits of
     the synchronous path: u uploaded while the spread runs, f downloaded while the interpolation runs."""
@@ -589,3 +653,9 @@ def test_multi_gpu_parity_two_ranks():
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert "MGPU_PARITY" in r.stdout
+    # the same with the markers starting on arbitrary ranks: marker migration first (halo.MarkerMigration)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29518", os.path.join(root, "tests", "mgpu_worker.py"), "IB_4", "migrate"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MGPU_PARITY" in r.stdout and "migrate=1" in r.stdout
