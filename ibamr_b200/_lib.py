@@ -102,6 +102,19 @@ SYMBOLS = {
     "ibk_migrate_plan": (_i, [_vp, _i, _pi, _pi, _pi, _i, _i, _pi]),
     "ibk_migrate_pack": (_i, [_vp, _vp]),
     "ibk_migrate_unpack": (_i, [_vp, _vp, _i, C.c_uint]),
+    "ibk_markers_lincomb": (_i, [_vp, _i, _d, _i, _d, _i]),
+    "ibk_markers_zero_rows": (_i, [_vp, _i, _pi, _i]),
+    "ibk_force_set_springs": (_i, [_vp, _i, _pi, _pi, _pd, _pd]),
+    "ibk_force_set_beams": (_i, [_vp, _i, _pi, _pi, _pi, _pd, _pd]),
+    "ibk_force_set_target_points": (_i, [_vp, _i, _pi, _pd, _pd, _pd]),
+    "ibk_force_clear": (_i, [_vp]),
+    "ibk_compute_lagrangian_force": (_i, [_vp, _i, _i, _i]),
+    "ibk_io_last_error": (_s, []),
+    "ibk_io_read_vertex_file": (_i, [_s, _i, _pd, _i, _pi]),
+    "ibk_io_read_spring_file": (_i, [_s, _i, _i, _pi, _pi, _pd, _pd, _pi, _i, _pi]),
+    "ibk_io_read_beam_file": (_i, [_s, _i, _i, _i, _pi, _pi, _pi, _pd, _pd, _i, _pi]),
+    "ibk_io_read_target_file": (_i, [_s, _i, _i, _pi, _pd, _pd, _i, _pi]),
+    "ibk_io_read_anchor_file": (_i, [_s, _i, _i, _pi, _i, _pi]),
     "ibk_bin_get_cells": (_i, [_vp, _pi, _pi]),
     "ibk_bin_get_order": (_i, [_vp, _pi]),
     "ibk_spread_force": (_i, [_vp, _s, _i]),

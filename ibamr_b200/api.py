@@ -24,6 +24,10 @@ from . import _lib
 from ._lib import ArrayDesc, LevelDesc, PatchDesc
 
 
+# marker columns (include/ibk.h IBK_COL_*): X is the one spread / interpolate / re-bin work on
+COLUMNS = {"X": 0, "U": 1, "F": 2, "X_current": 3, "X_new": 4, "aux": 5}
+
+
 class IBKError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"ibk error {code}: {msg}")
@@ -427,12 +431,12 @@ class IBMethodB200:
     def setLData(self, name, data):
         a = _f64(data).reshape(-1, self.ndim)
         assert a.shape[0] == self.n_markers
-        self.ctx.check(self.ctx.lib.ibk_markers_upload(self.ctx.h, {"X": 0, "U": 1, "F": 2}[name], _dp(a)))
+        self.ctx.check(self.ctx.lib.ibk_markers_upload(self.ctx.h, COLUMNS[name], _dp(a)))
 
     def getLData(self, name):
         a = np.zeros((self.n_markers, self.ndim))
         if self.n_markers:
-            self.ctx.check(self.ctx.lib.ibk_markers_download(self.ctx.h, {"X": 0, "U": 1, "F": 2}[name], _dp(a)))
+            self.ctx.check(self.ctx.lib.ibk_markers_download(self.ctx.h, COLUMNS[name], _dp(a)))
         return a
 
     # -- IBStrategy::beginDataRedistribution / endDataRedistribution (IBStrategy.h:455,464) ----------
@@ -448,6 +452,60 @@ class IBMethodB200:
         if self.n_markers:
             self.ctx.check(self.ctx.lib.ibk_bin_get_cells(self.ctx.h, _ip(cells), _ip(owner)))
         return cells, owner
+
+    # -- N1: Lagrangian force + position updates on the device (IBStandardForceGen, IBMethod steps) ----
+    def lincomb(self, dst, alpha, a, beta, b):
+        """dst = alpha * a + beta * b on marker columns (VecWAXPY / VecAXPBYPCZ of IBMethod.cpp:714-826)."""
+        self.ctx.check(self.ctx.lib.ibk_markers_lincomb(self.ctx.h, COLUMNS[dst], float(alpha), COLUMNS[a], float(beta), COLUMNS[b]))
+
+    def setSprings(self, master, slave, kappa, rest_length):
+        m, s_ = _i32(master), _i32(slave)
+        k, r = _f64(kappa), _f64(rest_length)
+        self.ctx.check(self.ctx.lib.ibk_force_set_springs(self.ctx.h, len(m), _ip(m), _ip(s_), _dp(k), _dp(r)))
+
+    def setBeams(self, curr, next_, prev, rigidity, curvature=None):
+        c, n, p = _i32(curr), _i32(next_), _i32(prev)
+        k = _f64(rigidity)
+        cv = _f64(curvature) if curvature is not None else None
+        self.ctx.check(self.ctx.lib.ibk_force_set_beams(self.ctx.h, len(c), _ip(c), _ip(n), _ip(p), _dp(k),
+                                                        _dp(cv) if cv is not None else None))
+
+    def setTargetPoints(self, idx, kappa, eta, X0):
+        i, k, x0 = _i32(idx), _f64(kappa), _f64(X0)
+        e = _f64(eta) if eta is not None else None
+        self.ctx.check(self.ctx.lib.ibk_force_set_target_points(self.ctx.h, len(i), _ip(i), _dp(k), _dp(e) if e is not None else None,
+                                                                _dp(x0)))
+
+    def clearForces(self):
+        self.ctx.check(self.ctx.lib.ibk_force_clear(self.ctx.h))
+
+    def computeLagrangianForce(self, x="X", u="U", f="F"):
+        """IBMethod::computeLagrangianForce (IBMethod.cpp:834-858): F = springs + beams + target points."""
+        self.ctx.check(self.ctx.lib.ibk_compute_lagrangian_force(self.ctx.h, COLUMNS[x], COLUMNS[u], COLUMNS[f]))
+
+    def resetAnchorPointValues(self, name, anchor_idx):
+        """IBMethod::resetAnchorPointValues (IBMethod.cpp:1915-1943): zero the rows of the anchored nodes."""
+        a = _i32(anchor_idx)
+        self.ctx.check(self.ctx.lib.ibk_markers_zero_rows(self.ctx.h, COLUMNS[name], _ip(a), len(a)))
+
+    def preprocessIntegrateData(self):
+        """Start of a step: X_current := the working positions (IBMethod::preprocessIntegrateData keeps X_current)."""
+        self.lincomb("X_current", 1.0, "X", 0.0, "X")
+
+    def forwardEulerStep(self, dt):
+        """IBMethod::forwardEulerStep (IBMethod.cpp:714-738): X_new = X_current + dt U, then the midpoint data
+        X := (X_current + X_new) / 2 (reinitMidpointData, :1900-1912) become the working positions."""
+        self.lincomb("X_new", 1.0, "X_current", dt, "U")
+        self.lincomb("X", 0.5, "X_current", 0.5, "X_new")
+
+    def midpointStep(self, dt):
+        """IBMethod::midpointStep (IBMethod.cpp:768-792): X_new = X_current + dt U_half; midpoint data refreshed."""
+        self.lincomb("X_new", 1.0, "X_current", dt, "U")
+        self.lincomb("X", 0.5, "X_current", 0.5, "X_new")
+
+    def postprocessIntegrateData(self):
+        """End of a step: the new positions become the working and the current ones."""
+        self.lincomb("X", 1.0, "X_new", 0.0, "X_new")
 
     # -- several processes: global Lagrangian indices, marker migration (LDataManager.cpp:1519-1959) --
     def setIds(self, ids, id_bound):
@@ -516,3 +574,92 @@ class IBMethodB200:
     def close(self):
         if self.ctx and self.ctx.h:
             self.ctx.lib.ibk_level_destroy(self.ctx.h)
+
+
+# ------------------------------------------------------------------------------------------------
+# N2: IBStandardInitializer's ASCII structure files (src/IB/IBStandardInitializer.cpp), via libibk.so
+# ------------------------------------------------------------------------------------------------
+class IBStandardInitializer:
+    """Reads <base>.vertex / .spring / .beam / .target / .anchor the way IBStandardInitializer::init does
+    (IBStandardInitializer.cpp:131-182) for a list of structures on one level; vertex numbers of structure j
+    are offset by the vertex counts of the structures before it (:203-210)."""
+
+    def __init__(self, ndim, base_filenames):
+        from . import _lib
+        lib = _lib.load()
+        self.ndim = ndim
+        self.X, self.springs, self.beams, self.targets, self.anchors = [], [], [], [], []
+        offset = 0
+
+        def check(rc):
+            if rc != 0:
+                raise IBKError(rc, lib.ibk_io_last_error().decode())
+
+        cnt = C.c_int(0)
+        for base in base_filenames:
+            path = lambda ext: (base + ext).encode()
+            check(lib.ibk_io_read_vertex_file(path(".vertex"), ndim, None, 0, C.byref(cnt)))
+            nv = cnt.value
+            X = np.zeros((nv, ndim))
+            check(lib.ibk_io_read_vertex_file(path(".vertex"), ndim, _dp(X), nv, C.byref(cnt)))
+            self.X.append(X)
+            # springs
+            check(lib.ibk_io_read_spring_file(path(".spring"), nv, offset, None, None, None, None, None, 0, C.byref(cnt)))
+            ns = cnt.value
+            m, s_, f = np.zeros(ns, np.int32), np.zeros(ns, np.int32), np.zeros(ns, np.int32)
+            k, r = np.zeros(ns), np.zeros(ns)
+            if ns:
+                check(lib.ibk_io_read_spring_file(path(".spring"), nv, offset, _ip(m), _ip(s_), _dp(k), _dp(r), _ip(f), ns, C.byref(cnt)))
+            self.springs.append((m, s_, k, r, f))
+            # beams
+            check(lib.ibk_io_read_beam_file(path(".beam"), nv, offset, ndim, None, None, None, None, None, 0, C.byref(cnt)))
+            nb = cnt.value
+            pv, cu, nx = np.zeros(nb, np.int32), np.zeros(nb, np.int32), np.zeros(nb, np.int32)
+            bend, curv = np.zeros(nb), np.zeros((nb, ndim))
+            if nb:
+                check(lib.ibk_io_read_beam_file(path(".beam"), nv, offset, ndim, _ip(pv), _ip(cu), _ip(nx), _dp(bend), _dp(curv), nb,
+                                                C.byref(cnt)))
+            self.beams.append((pv, cu, nx, bend, curv))
+            # target points
+            check(lib.ibk_io_read_target_file(path(".target"), nv, offset, None, None, None, 0, C.byref(cnt)))
+            nt = cnt.value
+            ti, tk, te = np.zeros(nt, np.int32), np.zeros(nt), np.zeros(nt)
+            if nt:
+                check(lib.ibk_io_read_target_file(path(".target"), nv, offset, _ip(ti), _dp(tk), _dp(te), nt, C.byref(cnt)))
+            self.targets.append((ti, tk, te))
+            # anchors
+            check(lib.ibk_io_read_anchor_file(path(".anchor"), nv, offset, None, 0, C.byref(cnt)))
+            na = cnt.value
+            ai = np.zeros(na, np.int32)
+            if na:
+                check(lib.ibk_io_read_anchor_file(path(".anchor"), nv, offset, _ip(ai), na, C.byref(cnt)))
+            self.anchors.append(ai)
+            offset += nv
+        self.n_vertices = offset
+
+    def positions(self):
+        return np.concatenate(self.X, axis=0)
+
+    def register(self, ib: "IBMethodB200"):
+        """Positions, force elements and target positions of all structures into the device-resident method
+        (IBMethod::initializeLevelData + IBStandardForceGen::initializeLevelData roles).  Target positions
+        are the initial vertex positions (IBTargetPointForceSpec X0 = initial position)."""
+        X = self.positions()
+        ib.setPositions(X)
+        cat = lambda parts, dtype: np.concatenate(parts).astype(dtype) if parts else np.zeros(0, dtype)
+        m = cat([s[0] for s in self.springs], np.int32)
+        if len(m):
+            for s in self.springs:
+                if np.any(s[4] != 0):
+                    raise IBKError(IBK_ERR_INVALID, "only the default spring force function (index 0) is on the device")
+            ib.setSprings(m, cat([s[1] for s in self.springs], np.int32), cat([s[2] for s in self.springs], np.float64),
+                          cat([s[3] for s in self.springs], np.float64))
+        c = cat([b[1] for b in self.beams], np.int32)
+        if len(c):
+            ib.setBeams(c, cat([b[2] for b in self.beams], np.int32), cat([b[0] for b in self.beams], np.int32),
+                        cat([b[3] for b in self.beams], np.float64), np.concatenate([b[4] for b in self.beams], axis=0))
+        t = cat([tt[0] for tt in self.targets], np.int32)
+        if len(t):
+            ib.setTargetPoints(t, cat([tt[1] for tt in self.targets], np.float64), cat([tt[2] for tt in self.targets], np.float64),
+                               X[t])
+        return X

@@ -67,6 +67,14 @@ struct LevelState
     double* U = nullptr;
     double* F = nullptr;
     double* tmp = nullptr;    // [ndim][stride] permutation scratch
+    double* extra[3] = { nullptr, nullptr, nullptr }; // optional columns 3..5 (X_current, X_new, auxiliary), lazily allocated
+    // Lagrangian force elements (ibk_force_set_*), device tables + the inverse of the storage order
+    ForceTables force;
+    std::vector<void*> force_allocs; // every device array behind `force`
+    int* pos_of_id = nullptr;        // [pos_cap] Lagrangian index -> storage position (-1: not here)
+    int pos_cap = 0;
+    bool pos_valid = false;
+    int* d_missing = nullptr;        // device counter: force elements with an endpoint that is not on this rank
     uint32_t* lag = nullptr;  // storage position -> row of the host AoS arrays (= Lagrangian index unless gid is set)
     uint32_t* gid = nullptr;  // optional: storage position -> global Lagrangian index (multi-rank; ibk_markers_set_ids)
     uint32_t id_bound = 0;    // exclusive upper bound of the global indices (sizes the tie bits of the sort key)

@@ -90,6 +90,41 @@ cudaError_t scatter_columns(Launcher& L, const double* d_in, long long in_stride
                             const uint32_t* d_perm, int n, int ncols);
 cudaError_t extract_low32(Launcher& L, const uint64_t* d_keys, uint32_t* d_out, int n, int bits);
 
+// ibk_force.cu
+// Force elements by Lagrangian index plus, per node, the elements it takes part in (CSR), all on the device.
+struct ForceTables
+{
+    int n_nodes = 0; // the CSR pointers cover Lagrangian indices [0, n_nodes)
+    // springs
+    const int* spring_ptr = nullptr;   // [n_nodes + 1]
+    const int* spring_items = nullptr; // spring k * 2 + (0: node is the master, 1: the slave), ascending k per node
+    const int* spring_mastr = nullptr;
+    const int* spring_slave = nullptr;
+    const double* spring_kappa = nullptr;
+    const double* spring_rest = nullptr;
+    // beams
+    const int* beam_ptr = nullptr;
+    const int* beam_items = nullptr; // beam k * 4 + (0: master, 1: next, 2: prev)
+    const int* beam_mastr = nullptr;
+    const int* beam_next = nullptr;
+    const int* beam_prev = nullptr;
+    const double* beam_rigidity = nullptr;
+    const double* beam_curvature = nullptr; // [n_beams][ndim]
+    // target points
+    const int* target_ptr = nullptr;
+    const int* target_items = nullptr; // target k
+    const double* target_kappa = nullptr;
+    const double* target_eta = nullptr;
+    const double* target_X0 = nullptr; // [n_targets][ndim]
+};
+cudaError_t launch_lagrangian_force(Launcher& L, int ndim, const ForceTables& t, const double* X, const double* U, double* F,
+                                    long long stride, const uint32_t* id_of_pos, const int* pos_of_id, int n, int* d_missing);
+cudaError_t launch_pos_of_id(Launcher& L, const uint32_t* id_of_pos, int n, int* pos_of_id, int id_bound);
+cudaError_t launch_lincomb(Launcher& L, double* dst, double alpha, const double* a, double beta, const double* b, long long stride,
+                           int n, int ndim);
+cudaError_t launch_zero_rows(Launcher& L, double* col, long long stride, int ndim, const int* d_ids, int n_ids, const int* pos_of_id,
+                             int id_bound);
+
 // ibk_migrate.cu
 cudaError_t migrate_dest(Launcher& L, const CellGeom& cg, const int* d_plo, const int* d_phi, const int* d_prank, int n_patches,
                          int n_ranks, const double* X, long long stride, int first, int n_tail, uint64_t* keys, uint32_t* vals);

@@ -513,6 +513,11 @@ extern "C" int ibk_level_destroy(ibk_ctx* ctx)
     for (void* p : { (void*)lv.X, (void*)lv.U, (void*)lv.F, (void*)lv.tmp, (void*)lv.lag, (void*)lv.lag_prev,
                      (void*)lv.gid, (void*)lv.cells, (void*)lv.owner, (void*)lv.escaped })
         if (p) cudaFree(p);
+    for (double* p : lv.extra)
+        if (p) cudaFree(p);
+    for (void* p : lv.force_allocs) cudaFree(p);
+    if (lv.pos_of_id) cudaFree(lv.pos_of_id);
+    if (lv.d_missing) cudaFree(lv.d_missing);
     bins_free(lv.bins);
     extra_drop(ctx);
     lv = LevelState();
@@ -763,8 +768,9 @@ static int reserve_markers(ibk_ctx* ctx, int n, int n_keep = 0)
     if ((long long)n <= lv.stride) return IBK_OK;
     const long long stride = ((long long)std::max(n, 1024) + 31) / 32 * 32;
     const int ndim = lv.ndim;
-    for (double** pp : { &lv.X, &lv.U, &lv.F, &lv.tmp })
+    for (double** pp : { &lv.X, &lv.U, &lv.F, &lv.tmp, &lv.extra[0], &lv.extra[1], &lv.extra[2] })
     {
+        if (!*pp && (pp == &lv.extra[0] || pp == &lv.extra[1] || pp == &lv.extra[2])) continue; // allocated on first use
         double* fresh = nullptr;
         CK(cudaMalloc(&fresh, sizeof(double) * (size_t)stride * ndim));
         CK(cudaMemsetAsync(fresh, 0, sizeof(double) * (size_t)stride * ndim, ctx->L.stream));
@@ -797,20 +803,33 @@ static int reserve_markers(ibk_ctx* ctx, int n, int n_keep = 0)
     CK(cudaMalloc(&lv.cells, sizeof(int) * (size_t)stride * ndim));
     CK(cudaMalloc(&lv.owner, sizeof(int) * (size_t)stride));
     lv.stride = stride;
+    lv.pos_valid = false;
     return IBK_OK;
 }
 
+constexpr int IBK_NCOLS = 6; // X, U, F, X_current, X_new, auxiliary
 static double* column_of(LevelState& lv, int which)
 {
-    return which == 0 ? lv.X : which == 1 ? lv.U : lv.F;
+    return which == 0 ? lv.X : which == 1 ? lv.U : which == 2 ? lv.F : lv.extra[which - 3];
+}
+// columns 3..5 exist once they are used
+static int ensure_column(ibk_ctx* ctx, int which)
+{
+    LevelState& lv = ctx->lv;
+    if (which < 0 || which >= IBK_NCOLS) return fail(ctx, IBK_ERR_INVALID, "bad marker column");
+    if (which < 3 || lv.extra[which - 3] || lv.stride == 0) return IBK_OK;
+    CK(cudaMalloc(&lv.extra[which - 3], sizeof(double) * (size_t)lv.stride * lv.ndim));
+    CK(cudaMemsetAsync(lv.extra[which - 3], 0, sizeof(double) * (size_t)lv.stride * lv.ndim, ctx->L.stream));
+    return IBK_OK;
 }
 
 extern "C" int ibk_markers_upload(ibk_ctx* ctx, int which, const double* h_data)
 {
     NEED_LEVEL();
     LevelState& lv = ctx->lv;
-    if (which < 0 || which > 2 || !h_data) return fail(ctx, IBK_ERR_INVALID, "bad marker column");
+    if (which < 0 || which >= IBK_NCOLS || !h_data) return fail(ctx, IBK_ERR_INVALID, "bad marker column");
     if (lv.n <= 0) return IBK_OK;
+    if (int rc = ensure_column(ctx, which)) return rc;
     const size_t bytes = sizeof(double) * (size_t)lv.n * lv.ndim;
     CK(ctx->b_io[5].reserve(bytes));
     CK(cudaMemcpyAsync(ctx->b_io[5].p, h_data, bytes, cudaMemcpyHostToDevice, ctx->L.stream));
@@ -824,8 +843,9 @@ extern "C" int ibk_markers_download(ibk_ctx* ctx, int which, double* h_data)
 {
     NEED_LEVEL();
     LevelState& lv = ctx->lv;
-    if (which < 0 || which > 2 || !h_data) return fail(ctx, IBK_ERR_INVALID, "bad marker column");
+    if (which < 0 || which >= IBK_NCOLS || !h_data) return fail(ctx, IBK_ERR_INVALID, "bad marker column");
     if (lv.n <= 0) return IBK_OK;
+    if (int rc = ensure_column(ctx, which)) return rc;
     const size_t bytes = sizeof(double) * (size_t)lv.n * lv.ndim;
     CK(ctx->b_io[5].reserve(bytes));
     CK(scatter_columns(ctx->L, column_of(lv, which), lv.stride, lv.tmp, lv.stride, lv.lag, lv.n, lv.ndim));
@@ -846,6 +866,7 @@ extern "C" int ibk_markers_set_positions(ibk_ctx* ctx, const double* h_X, int n_
     lv.gid = nullptr;
     lv.id_bound = 0;
     lv.mig_n = -1;
+    lv.pos_valid = false;
     if (n_markers == 0) return IBK_OK;
     iota_kernel<<<(n_markers + 255) / 256, 256, 0, ctx->L.stream>>>(lv.lag, n_markers);
     ctx->L.launches++;
@@ -858,7 +879,8 @@ extern "C" int ibk_markers_count(const ibk_ctx* ctx)
 extern "C" int ibk_markers_device_ptr(ibk_ctx* ctx, int which, double** d_ptr, long long* stride)
 {
     NEED_LEVEL();
-    if (which < 0 || which > 2) return fail(ctx, IBK_ERR_INVALID, "bad marker column");
+    if (which < 0 || which >= IBK_NCOLS) return fail(ctx, IBK_ERR_INVALID, "bad marker column");
+    if (int rc = ensure_column(ctx, which)) return rc;
     if (d_ptr) *d_ptr = column_of(ctx->lv, which);
     if (stride) *stride = ctx->lv.stride;
     return IBK_OK;
@@ -907,8 +929,9 @@ extern "C" int ibk_rebin(ibk_ctx* ctx, int error_if_points_leave_domain)
     if (n > 0)
     {
         const uint32_t* perm = lv.bins.vals[lv.bins.sorted_in];
-        for (double** col : { &lv.X, &lv.U, &lv.F })
+        for (double** col : { &lv.X, &lv.U, &lv.F, &lv.extra[0], &lv.extra[1], &lv.extra[2] })
         {
+            if (!*col) continue;
             // permute into the scratch column, then swap roles (no copy back)
             CK(gather_columns(ctx->L, *col, lv.stride, lv.tmp, lv.stride, perm, n, ndim));
             std::swap(*col, lv.tmp);
@@ -922,6 +945,7 @@ extern "C" int ibk_rebin(ibk_ctx* ctx, int error_if_points_leave_domain)
             CK(extract_low32(ctx->L, lv.bins.keys[lv.bins.sorted_in], lv.lag, n, lv.bins.tie_bits));
     }
     lv.binned = true;
+    lv.pos_valid = false;
     if (ctx->timing)
     {
         CK(cudaEventRecord(ctx->ev[2][1], ctx->L.stream));
@@ -997,6 +1021,7 @@ extern "C" int ibk_markers_set_ids(ibk_ctx* ctx, const unsigned* h_ids, unsigned
     CK(cudaStreamSynchronize(ctx->L.stream));
     lv.id_bound = id_bound;
     lv.binned = false;
+    lv.pos_valid = false;
     return IBK_OK;
 }
 extern "C" int ibk_markers_get_ids(ibk_ctx* ctx, unsigned* h_ids)
@@ -1029,6 +1054,8 @@ extern "C" int ibk_migrate_plan(ibk_ctx* ctx, int n_patches, const int* patch_lo
     lv.mig_order = nullptr;
     if (n_tail <= 0) return IBK_OK;
     if (!lv.gid) return fail(ctx, IBK_ERR_STATE, "markers leave this rank but no global indices were set (ibk_markers_set_ids)");
+    if (lv.extra[0] || lv.extra[1] || lv.extra[2])
+        return fail(ctx, IBK_ERR_STATE, "marker migration carries the columns X, U, F only (columns 3..5 are in use)");
     DevBuf* B = ctx->b_mig;
     CK(B[0].reserve(sizeof(uint64_t) * (size_t)n_tail));
     CK(B[1].reserve(sizeof(uint32_t) * (size_t)n_tail));
@@ -1098,6 +1125,7 @@ extern "C" int ibk_migrate_unpack(ibk_ctx* ctx, const double* d_buf, int n_recv,
     lv.n = n_new;
     lv.id_bound = std::max(lv.id_bound, id_bound);
     lv.binned = false;
+    lv.pos_valid = false;
     if (n_new > 0 && lv.gid)
     {
         // host rows := ascending global index among the markers now held (identity numbering for one rank)
@@ -1112,6 +1140,218 @@ extern "C" int ibk_migrate_unpack(ibk_ctx* ctx, const double* d_buf, int n_recv,
                                            0, ceil_log2_u(std::max(lv.id_bound, 2u)), B[4].p, ctx->L.stream, &ctx->L.launches);
         CK(rank_scatter(ctx->L, which ? B[3].as<uint32_t>() : B[1].as<uint32_t>(), n_new, lv.lag));
     }
+    return IBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// N1: Lagrangian forces and marker-column algebra on the device (IBStandardForceGen, IBMethod steps)
+// ---------------------------------------------------------------------------------------------
+template <class T>
+static cudaError_t force_upload(LevelState& lv, const std::vector<T>& h, const T** d_out)
+{
+    *d_out = nullptr;
+    if (h.empty()) return cudaSuccess;
+    T* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(T) * h.size());
+    if (e != cudaSuccess) return e;
+    lv.force_allocs.push_back(d);
+    *d_out = d;
+    return cudaMemcpy(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice);
+}
+// node -> items CSR; items of one node ascend with the element number (the order the reference's loop meets them)
+static void build_csr(int n_nodes, const std::vector<std::pair<int, int>>& node_item, std::vector<int>& ptr, std::vector<int>& items)
+{
+    ptr.assign((size_t)n_nodes + 1, 0);
+    for (const auto& ni : node_item) ptr[(size_t)ni.first + 1]++;
+    for (int l = 0; l < n_nodes; ++l) ptr[(size_t)l + 1] += ptr[l];
+    items.resize(node_item.size());
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (const auto& ni : node_item) items[(size_t)fill[ni.first]++] = ni.second; // node_item is in element order
+}
+static int force_node_bound(const LevelState& lv)
+{
+    return lv.gid ? (int)lv.id_bound : lv.n;
+}
+static int check_nodes(ibk_ctx* ctx, int n, std::initializer_list<const int*> arrays, const char* what)
+{
+    const int bound = force_node_bound(ctx->lv);
+    for (const int* a : arrays)
+    {
+        if (!a) return fail(ctx, IBK_ERR_INVALID, std::string("null index array for ") + what);
+        for (int k = 0; k < n; ++k)
+            if (a[k] < 0 || a[k] >= bound) return fail(ctx, IBK_ERR_INVALID, std::string(what) + ": node index out of range");
+    }
+    return IBK_OK;
+}
+// The CSR pointer arrays of the three groups must agree on n_nodes: rebuilt whenever a group is (re)set.
+static int force_commit(ibk_ctx* ctx)
+{
+    ctx->lv.force.n_nodes = force_node_bound(ctx->lv);
+    return IBK_OK;
+}
+
+extern "C" int ibk_force_clear(ibk_ctx* ctx)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    for (void* p : lv.force_allocs) cudaFree(p);
+    lv.force_allocs.clear();
+    lv.force = ForceTables();
+    return IBK_OK;
+}
+
+extern "C" int ibk_force_set_springs(ibk_ctx* ctx, int n, const int* master, const int* slave, const double* kappa,
+                                     const double* rest_length)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (n < 0 || (n > 0 && (!kappa || !rest_length))) return fail(ctx, IBK_ERR_INVALID, "bad spring arrays");
+    if (int rc = check_nodes(ctx, n, { master, slave }, "springs")) return rc;
+    for (int k = 0; k < n; ++k)
+        if (master[k] == slave[k]) return fail(ctx, IBK_ERR_INVALID, "spring connects a node to itself"); // TBOX_ASSERT :852
+    const int nn = force_node_bound(lv);
+    std::vector<std::pair<int, int>> node_item;
+    node_item.reserve(2 * (size_t)n);
+    for (int k = 0; k < n; ++k)
+    {
+        node_item.push_back({ master[k], 2 * k });
+        node_item.push_back({ slave[k], 2 * k + 1 });
+    }
+    std::vector<int> ptr, items;
+    build_csr(nn, node_item, ptr, items);
+    CK(force_upload(lv, ptr, &lv.force.spring_ptr));
+    CK(force_upload(lv, items, &lv.force.spring_items));
+    CK(force_upload(lv, std::vector<int>(master, master + n), &lv.force.spring_mastr));
+    CK(force_upload(lv, std::vector<int>(slave, slave + n), &lv.force.spring_slave));
+    CK(force_upload(lv, std::vector<double>(kappa, kappa + n), &lv.force.spring_kappa));
+    CK(force_upload(lv, std::vector<double>(rest_length, rest_length + n), &lv.force.spring_rest));
+    return force_commit(ctx);
+}
+
+extern "C" int ibk_force_set_beams(ibk_ctx* ctx, int n, const int* curr, const int* next, const int* prev, const double* rigidity,
+                                   const double* curvature)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (n < 0 || (n > 0 && !rigidity)) return fail(ctx, IBK_ERR_INVALID, "bad beam arrays");
+    if (int rc = check_nodes(ctx, n, { curr, next, prev }, "beams")) return rc;
+    for (int k = 0; k < n; ++k)
+        if (curr[k] == next[k] || curr[k] == prev[k]) return fail(ctx, IBK_ERR_INVALID, "beam repeats its master node"); // :1075-1076
+    const int nn = force_node_bound(lv);
+    std::vector<std::pair<int, int>> node_item;
+    node_item.reserve(3 * (size_t)n);
+    for (int k = 0; k < n; ++k)
+    {
+        node_item.push_back({ curr[k], 4 * k });
+        node_item.push_back({ next[k], 4 * k + 1 });
+        node_item.push_back({ prev[k], 4 * k + 2 });
+    }
+    std::vector<int> ptr, items;
+    build_csr(nn, node_item, ptr, items);
+    std::vector<double> curv((size_t)n * lv.ndim, 0.0);
+    if (curvature) curv.assign(curvature, curvature + (size_t)n * lv.ndim);
+    CK(force_upload(lv, ptr, &lv.force.beam_ptr));
+    CK(force_upload(lv, items, &lv.force.beam_items));
+    CK(force_upload(lv, std::vector<int>(curr, curr + n), &lv.force.beam_mastr));
+    CK(force_upload(lv, std::vector<int>(next, next + n), &lv.force.beam_next));
+    CK(force_upload(lv, std::vector<int>(prev, prev + n), &lv.force.beam_prev));
+    CK(force_upload(lv, std::vector<double>(rigidity, rigidity + n), &lv.force.beam_rigidity));
+    CK(force_upload(lv, curv, &lv.force.beam_curvature));
+    return force_commit(ctx);
+}
+
+extern "C" int ibk_force_set_target_points(ibk_ctx* ctx, int n, const int* idx, const double* kappa, const double* eta,
+                                           const double* X0)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (n < 0 || (n > 0 && (!kappa || !X0))) return fail(ctx, IBK_ERR_INVALID, "bad target point arrays");
+    if (int rc = check_nodes(ctx, n, { idx }, "target points")) return rc;
+    const int nn = force_node_bound(lv);
+    std::vector<std::pair<int, int>> node_item;
+    for (int k = 0; k < n; ++k) node_item.push_back({ idx[k], k });
+    std::vector<int> ptr, items;
+    build_csr(nn, node_item, ptr, items);
+    std::vector<double> e((size_t)n, 0.0);
+    if (eta) e.assign(eta, eta + n);
+    CK(force_upload(lv, ptr, &lv.force.target_ptr));
+    CK(force_upload(lv, items, &lv.force.target_items));
+    CK(force_upload(lv, std::vector<double>(kappa, kappa + n), &lv.force.target_kappa));
+    CK(force_upload(lv, e, &lv.force.target_eta));
+    CK(force_upload(lv, std::vector<double>(X0, X0 + (size_t)n * lv.ndim), &lv.force.target_X0));
+    return force_commit(ctx);
+}
+
+// Lagrangian index -> storage position, rebuilt after the storage order changed
+static int refresh_pos_of_id(ibk_ctx* ctx)
+{
+    LevelState& lv = ctx->lv;
+    const int bound = std::max(force_node_bound(lv), 1);
+    if (lv.pos_valid && lv.pos_cap >= bound) return IBK_OK;
+    if (lv.pos_cap < bound)
+    {
+        if (lv.pos_of_id) cudaFree(lv.pos_of_id);
+        lv.pos_of_id = nullptr;
+        CK(cudaMalloc(&lv.pos_of_id, sizeof(int) * (size_t)bound));
+        lv.pos_cap = bound;
+    }
+    CK(launch_pos_of_id(ctx->L, lv.gid ? lv.gid : lv.lag, lv.n, lv.pos_of_id, bound));
+    lv.pos_valid = true;
+    return IBK_OK;
+}
+
+extern "C" int ibk_compute_lagrangian_force(ibk_ctx* ctx, int x_col, int u_col, int f_col)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    for (int c : { x_col, u_col, f_col })
+        if (int rc = ensure_column(ctx, c)) return rc;
+    if (f_col == x_col || f_col == u_col) return fail(ctx, IBK_ERR_INVALID, "the force column must differ from its inputs");
+    if (lv.n == 0) return IBK_OK;
+    if (lv.force.n_nodes != force_node_bound(lv) && (lv.force.spring_ptr || lv.force.beam_ptr || lv.force.target_ptr))
+        return fail(ctx, IBK_ERR_STATE, "the force elements were set for a different marker numbering (set them after the markers)");
+    if (int rc = refresh_pos_of_id(ctx)) return rc;
+    if (!lv.d_missing) CK(cudaMalloc(&lv.d_missing, sizeof(int)));
+    CK(cudaMemsetAsync(lv.d_missing, 0, sizeof(int), ctx->L.stream));
+    CK(launch_lagrangian_force(ctx->L, lv.ndim, lv.force, column_of(lv, x_col), column_of(lv, u_col), column_of(lv, f_col), lv.stride,
+                               lv.gid ? lv.gid : lv.lag, lv.pos_of_id, lv.n, lv.d_missing));
+    if (lv.gid) // several processes: an element may reach a node that lives elsewhere (the reference's ghost nodes)
+    {
+        int missing = 0;
+        CK(cudaMemcpyAsync(&missing, lv.d_missing, sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
+        CK(cudaStreamSynchronize(ctx->L.stream));
+        if (missing > 0)
+            return fail(ctx, IBK_ERR_STATE, "a force element reaches a node held by another process (structures must not straddle ranks)");
+    }
+    return IBK_OK;
+}
+
+extern "C" int ibk_markers_lincomb(ibk_ctx* ctx, int dst, double alpha, int a, double beta, int b)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    for (int c : { dst, a, b })
+        if (int rc = ensure_column(ctx, c)) return rc;
+    if (lv.n == 0) return IBK_OK;
+    CK(launch_lincomb(ctx->L, column_of(lv, dst), alpha, column_of(lv, a), beta, column_of(lv, b), lv.stride, lv.n, lv.ndim));
+    if (dst == 0) lv.binned = false; // the working positions moved: ibk_rebin before the next spread / interpolation
+    return IBK_OK;
+}
+
+extern "C" int ibk_markers_zero_rows(ibk_ctx* ctx, int which, const int* lag_idx, int n)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (int rc = ensure_column(ctx, which)) return rc;
+    if (n < 0 || (n > 0 && !lag_idx)) return fail(ctx, IBK_ERR_INVALID, "bad index list");
+    if (n == 0 || lv.n == 0) return IBK_OK;
+    if (int rc = refresh_pos_of_id(ctx)) return rc;
+    CK(ctx->b_io[6].reserve(sizeof(int) * (size_t)n));
+    CK(cudaMemcpyAsync(ctx->b_io[6].p, lag_idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->L.stream));
+    CK(launch_zero_rows(ctx->L, column_of(lv, which), lv.stride, lv.ndim, ctx->b_io[6].as<int>(), n, lv.pos_of_id,
+                        std::max(force_node_bound(lv), 1)));
+    CK(cudaStreamSynchronize(ctx->L.stream)); // lag_idx is the caller's (pageable) memory
     return IBK_OK;
 }
 

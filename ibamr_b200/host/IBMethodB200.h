@@ -118,6 +118,63 @@ public:
         check(ibk_spread_force(d_ctx, d_spread_kernel_fcn.c_str(), /*accumulate_halo*/ 1));
     }
 
+    // ---- N1: the steps either side of the path, with X, U, F resident on the device ----------------------
+    // IBMethod::preprocessIntegrateData keeps X_current; the working column IBK_COL_X plays X_LE / half data.
+    void preprocessIntegrateData()
+    {
+        check(ibk_markers_lincomb(d_ctx, IBK_COL_X_CURRENT, 1.0, IBK_COL_X, 0.0, IBK_COL_X));
+    }
+    // IBMethod::forwardEulerStep (IBMethod.cpp:714-738) + reinitMidpointData (:1900-1912)
+    void forwardEulerStep(double current_time, double new_time)
+    {
+        const double dt = new_time - current_time;
+        check(ibk_markers_lincomb(d_ctx, IBK_COL_X_NEW, 1.0, IBK_COL_X_CURRENT, dt, IBK_COL_U));
+        check(ibk_markers_lincomb(d_ctx, IBK_COL_X, 0.5, IBK_COL_X_CURRENT, 0.5, IBK_COL_X_NEW));
+    }
+    // IBMethod::midpointStep (IBMethod.cpp:768-792): U holds the half-time velocity
+    void midpointStep(double current_time, double new_time)
+    {
+        forwardEulerStep(current_time, new_time);
+    }
+    // IBMethod::postprocessIntegrateData: X_new becomes the working (and, at the next preprocess, the current) data
+    void postprocessIntegrateData()
+    {
+        check(ibk_markers_lincomb(d_ctx, IBK_COL_X, 1.0, IBK_COL_X_NEW, 0.0, IBK_COL_X_NEW));
+    }
+    // IBStandardForceGen::initializeLevelData roles (IBStandardForceGen.cpp:715-811, 933-1035, 1150-1199)
+    void registerSprings(const std::vector<int>& master, const std::vector<int>& slave, const std::vector<double>& kappa,
+                         const std::vector<double>& rest_length)
+    {
+        check(ibk_force_set_springs(d_ctx, (int)master.size(), master.data(), slave.data(), kappa.data(), rest_length.data()));
+    }
+    void registerBeams(const std::vector<int>& curr, const std::vector<int>& next, const std::vector<int>& prev,
+                       const std::vector<double>& rigidity, const std::vector<double>& curvature)
+    {
+        check(ibk_force_set_beams(d_ctx, (int)curr.size(), curr.data(), next.data(), prev.data(), rigidity.data(),
+                                  curvature.empty() ? nullptr : curvature.data()));
+    }
+    void registerTargetPoints(const std::vector<int>& idx, const std::vector<double>& kappa, const std::vector<double>& eta,
+                              const std::vector<double>& X0)
+    {
+        check(ibk_force_set_target_points(d_ctx, (int)idx.size(), idx.data(), kappa.data(), eta.empty() ? nullptr : eta.data(),
+                                          X0.data()));
+    }
+    // IBMethod::computeLagrangianForce(data_time) (IBMethod.cpp:834-858)
+    void computeLagrangianForce(double /*data_time*/ = 0.0)
+    {
+        check(ibk_compute_lagrangian_force(d_ctx, IBK_COL_X, IBK_COL_U, IBK_COL_F));
+    }
+    // IBMethod::resetAnchorPointValues (IBMethod.cpp:1915-1943)
+    void resetAnchorPointValues(int column, const std::vector<int>& anchor_idx)
+    {
+        check(ibk_markers_zero_rows(d_ctx, column, anchor_idx.data(), (int)anchor_idx.size()));
+    }
+    void getColumn(int column, std::vector<double>& out)
+    {
+        out.assign((size_t)ibk_markers_count(d_ctx) * NDIM, 0.0);
+        check(ibk_markers_download(d_ctx, column, out.data()));
+    }
+
     ibk_ctx* ctx()
     {
         return d_ctx;

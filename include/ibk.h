@@ -284,7 +284,8 @@ int ibk_transfers_wait(ibk_ctx* ctx);
  * ibk_markers_set_positions replaces LData("X") setup (LDataManager.cpp:2187-2197) and resets
  * the Lagrangian numbering to 0..n-1. */
 int ibk_markers_set_positions(ibk_ctx* ctx, const double* h_X, int n_markers);
-/* which: 0 = X, 1 = U, 2 = F; AoS [n][ndim] in LAGRANGIAN index order. */
+/* which: 0 = X, 1 = U, 2 = F (and the optional columns 3 = X_current, 4 = X_new, 5 = auxiliary of the N1
+ * section below, allocated on first use); AoS [n][ndim] in LAGRANGIAN index order. */
 int ibk_markers_upload(ibk_ctx* ctx, int which, const double* h_data);
 int ibk_markers_download(ibk_ctx* ctx, int which, double* h_data);
 int ibk_markers_count(const ibk_ctx* ctx);
@@ -318,6 +319,59 @@ int ibk_migrate_plan(ibk_ctx* ctx, int n_patches, const int* patch_lower, const 
                      int n_ranks, int my_rank, int* h_send_counts);
 int ibk_migrate_pack(ibk_ctx* ctx, double* d_buf);
 int ibk_migrate_unpack(ibk_ctx* ctx, const double* d_buf, int n_recv, unsigned id_bound);
+
+/* ---- N1: Lagrangian forces and position updates with the markers resident -------------
+ * Marker columns: IBK_COL_X is the one spread / interpolate / re-bin work on (IBMethod's X_LE / half-time data).
+ *
+ * ibk_markers_lincomb   dst = alpha * a + beta * b on whole columns: the VecWAXPY / VecAXPBYPCZ calls of
+ *                       IBMethod::forwardEulerStep / midpointStep / trapezoidalStep / reinitMidpointData
+ *                       (src/IB/IBMethod.cpp:714-826, 1900-1912).  Writing IBK_COL_X un-bins the markers.
+ * ibk_markers_zero_rows zeroes the rows of the listed Lagrangian indices: IBMethod::resetAnchorPointValues
+ *                       (IBMethod.cpp:1915-1943).
+ * ibk_force_set_*       the force elements IBStandardForceGen gathers from the node specs
+ *                       (IBStandardForceGen.cpp:715-811 springs, 933-1035 beams, 1150-1199 target points), by
+ *                       Lagrangian index; springs use the default force function kappa * (R - rest_length)
+ *                       (IBSpringForceFunctions.h:99-103); eta / curvature may be NULL (zero).  Set them after
+ *                       the markers (and after ibk_markers_set_ids, if used); ibk_force_clear drops them all.
+ * ibk_compute_lagrangian_force  F(f_col) = springs + beams + target points at positions x_col, velocities u_col:
+ *                       IBMethod::computeLagrangianForce (IBMethod.cpp:834-858) over
+ *                       IBStandardForceGen::computeLagrangianForce (IBStandardForceGen.cpp:253-303).  Every node
+ *                       gathers its elements in the reference's order: no atomics, bit-reproducible.  With
+ *                       several processes every element's nodes must be on one rank (IBK_ERR_STATE otherwise). */
+enum
+{
+    IBK_COL_X = 0,
+    IBK_COL_U = 1,
+    IBK_COL_F = 2,
+    IBK_COL_X_CURRENT = 3,
+    IBK_COL_X_NEW = 4,
+    IBK_COL_AUX = 5
+};
+int ibk_markers_lincomb(ibk_ctx* ctx, int dst, double alpha, int a, double beta, int b);
+int ibk_markers_zero_rows(ibk_ctx* ctx, int which, const int* lag_idx, int n);
+int ibk_force_set_springs(ibk_ctx* ctx, int n, const int* master, const int* slave, const double* kappa, const double* rest_length);
+int ibk_force_set_beams(ibk_ctx* ctx, int n, const int* curr, const int* next, const int* prev, const double* rigidity,
+                        const double* curvature);
+int ibk_force_set_target_points(ibk_ctx* ctx, int n, const int* idx, const double* kappa, const double* eta, const double* X0);
+int ibk_force_clear(ibk_ctx* ctx);
+int ibk_compute_lagrangian_force(ibk_ctx* ctx, int x_col, int u_col, int f_col);
+
+/* ---- N2: the ASCII structure files of IBStandardInitializer (host only, no context) -----
+ * Grammar and validity rules of src/IB/IBStandardInitializer.cpp (readVertexFiles :184-294, readSpringFiles
+ * :297-528, readBeamFiles :766-1002, readTargetPointFiles :1322-1517, readAnchorPointFiles :1520-1643): comments
+ * after '!', '#', '%'; line 1 = number of entries; indices in [0, n_vertices) and returned with vertex_offset
+ * added; duplicates skipped; springs stored smaller index first.  Output arrays may be NULL (count only) and hold
+ * at most `capacity` entries; *n_* receives the number of entries kept.  A missing .vertex file is an error, the
+ * other files are optional (count 0).  Errors: IBK_ERR_INVALID with the text in ibk_io_last_error(). */
+const char* ibk_io_last_error(void);
+int ibk_io_read_vertex_file(const char* path, int ndim, double* X, int capacity, int* n_vertices);
+int ibk_io_read_spring_file(const char* path, int n_vertices, int vertex_offset, int* master, int* slave, double* kappa,
+                            double* rest_length, int* force_fcn_idx, int capacity, int* n_springs);
+int ibk_io_read_beam_file(const char* path, int n_vertices, int vertex_offset, int ndim, int* prev, int* curr, int* next,
+                          double* rigidity, double* curvature, int capacity, int* n_beams);
+int ibk_io_read_target_file(const char* path, int n_vertices, int vertex_offset, int* idx, double* kappa, double* eta, int capacity,
+                            int* n_targets);
+int ibk_io_read_anchor_file(const char* path, int n_vertices, int vertex_offset, int* idx, int capacity, int* n_anchors);
 
 
 /* Binning products for parity checks (LIndexSetData role), in LAGRANGIAN index order:

@@ -42,7 +42,7 @@ def min_ghost_width(kernel: str) -> int:
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("le_kernels.c", "le_driver.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("le_kernels.c", "le_driver.c", "le_force.c", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, capture_output=True)
     return so
@@ -406,3 +406,104 @@ class Baseline:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------------
+# N1: Lagrangian forces (oracle/le_force.c) and N2: the structure files of IBStandardInitializer
+# ------------------------------------------------------------------------------------------------
+def lagrangian_force(ndim, X, U, springs=None, beams=None, targets=None):
+    """IBMethod::computeLagrangianForce + IBStandardForceGen::computeLagrangianForce
+    (IBMethod.cpp:834-858, IBStandardForceGen.cpp:253-303): F = 0, then springs, beams, target points.
+    springs = (mastr, slave, kappa, rest); beams = (mastr, next, prev, rigidity, curvature[n][ndim]);
+    targets = (idx, kappa, eta, X0[n][ndim]).  Node arrays are AoS [n][ndim]."""
+    X, U = _f64(X), _f64(U)
+    F = np.zeros_like(X)
+    if springs is not None and len(springs[0]):
+        m, s, k, r = springs
+        lib().le_oracle_spring_force(ndim, len(m), _ip(_i32(m)), _ip(_i32(s)), _dp(_f64(k)), _dp(_f64(r)), _dp(X), _dp(F))
+    if beams is not None and len(beams[0]):
+        m, nx, pv, k, c = beams
+        lib().le_oracle_beam_force(ndim, len(m), _ip(_i32(m)), _ip(_i32(nx)), _ip(_i32(pv)), _dp(_f64(k)), _dp(_f64(c)), _dp(X),
+                                   _dp(F))
+    if targets is not None and len(targets[0]):
+        i, k, e, x0 = targets
+        lib().le_oracle_target_force(ndim, len(i), _ip(_i32(i)), _dp(_f64(k)), _dp(_f64(e)), _dp(_f64(x0)), _dp(X), _dp(U), _dp(F))
+    return F
+
+
+def _discard_comments(line):
+    """IBStandardInitializer.cpp:65-87: drop everything after '!', '#' or '%'."""
+    for ch in "!#%":
+        line = line.split(ch, 1)[0]
+    return line
+
+
+def _structure_lines(path):
+    with open(path) as f:
+        lines = f.read().split("\n")
+    count = int(_discard_comments(lines[0]).split()[0])
+    if count <= 0:
+        raise ValueError("invalid count on line 1")
+    rows = [_discard_comments(l).split() for l in lines[1:1 + count]]
+    if len(rows) < count or any(len(r) == 0 for r in rows):
+        raise ValueError("premature end of file")
+    return count, rows
+
+
+def read_vertex_file(path, ndim):
+    """IBStandardInitializer::readVertexFiles (IBStandardInitializer.cpp:184-294); no shift / scale."""
+    n, rows = _structure_lines(path)
+    return np.array([[float(v) for v in r[:ndim]] for r in rows], dtype=np.float64).reshape(n, ndim)
+
+
+def read_spring_file(path, n_vertices, offset=0):
+    """readSpringFiles (IBStandardInitializer.cpp:297-528): 'mastr slave kappa rest [fcn_idx ...]'; the edge is
+    stored with the smaller index first (:478-481), duplicates are skipped (:482-499)."""
+    _, rows = _structure_lines(path)
+    seen, out = set(), []
+    for r in rows:
+        a, b, k, rest = int(r[0]), int(r[1]), float(r[2]), float(r[3])
+        if not (0 <= a < n_vertices and 0 <= b < n_vertices) or k < 0.0 or rest < 0.0:
+            raise ValueError("invalid spring entry")
+        fcn = int(r[4]) if len(r) > 4 else 0
+        a, b = a + offset, b + offset
+        if a > b:
+            a, b = b, a
+        if (a, b) in seen:
+            continue
+        seen.add((a, b))
+        out.append((a, b, k, rest, fcn))
+    return (np.array([o[0] for o in out], dtype=np.int32), np.array([o[1] for o in out], dtype=np.int32),
+            np.array([o[2] for o in out]), np.array([o[3] for o in out]), np.array([o[4] for o in out], dtype=np.int32))
+
+
+def read_beam_file(path, n_vertices, ndim, offset=0):
+    """readBeamFiles (IBStandardInitializer.cpp:766-1002): 'prev curr next bend [curvature x ndim]'."""
+    _, rows = _structure_lines(path)
+    prev, curr, nxt, bend, curv = [], [], [], [], []
+    seen = set()
+    for r in rows:
+        p, c, n, b = int(r[0]), int(r[1]), int(r[2]), float(r[3])
+        if not all(0 <= v < n_vertices for v in (p, c, n)) or b < 0.0:
+            raise ValueError("invalid beam entry")
+        cv = [float(v) for v in r[4:4 + ndim]] if len(r) >= 4 + ndim else [0.0] * ndim
+        key = (c + offset, n + offset, p + offset)
+        if key in seen:
+            continue
+        seen.add(key)
+        prev.append(p + offset), curr.append(c + offset), nxt.append(n + offset), bend.append(b), curv.append(cv)
+    return (np.array(prev, dtype=np.int32), np.array(curr, dtype=np.int32), np.array(nxt, dtype=np.int32), np.array(bend),
+            np.array(curv, dtype=np.float64).reshape(-1, ndim))
+
+
+def read_target_file(path, n_vertices, offset=0):
+    """readTargetPointFiles (IBStandardInitializer.cpp:1322-1517): 'idx kappa [eta]'."""
+    _, rows = _structure_lines(path)
+    idx, kappa, eta = [], [], []
+    for r in rows:
+        i, k = int(r[0]), float(r[1])
+        e = float(r[2]) if len(r) > 2 else 0.0
+        if not 0 <= i < n_vertices or k < 0.0 or e < 0.0:
+            raise ValueError("invalid target point entry")
+        idx.append(i + offset), kappa.append(k), eta.append(e)
+    return np.array(idx, dtype=np.int32), np.array(kappa), np.array(eta)

@@ -20,3 +20,8 @@ for d in 2d 3d; do
   cp "$REF/tests/IBTK/index_utilities_$d.output" "$HERE/"
 done
 cp "$REF/examples/IB/explicit/ex1/curve2d_64.vertex" "$HERE/"
+# sample structure files (inputs of the reference's own examples) for the reader / force tests (N1, N2)
+cp "$REF/examples/IB/explicit/ex1/curve2d_64.spring" "$HERE/"
+for e in vertex spring beam target; do
+  cp "$REF/examples/IB/explicit/ex3/fila_256.$e" "$HERE/"
+done

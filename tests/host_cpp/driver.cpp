@@ -1,18 +1,23 @@
 // Test driver for the C++ host mirror (ibamr_b200/host): reads one case from a binary file, runs it
 // through IBTK_B200::LEInteractor (seam B3) and IBAMR_B200::IBMethodB200 (seam B1), writes the results.
 //   driver --static                 : LEInteractor static queries + "no GPU -> refuse" check, prints lines
+//   driver --structure base ndim    : IBStandardInitializerB200 on <base>.vertex/.spring/.beam/.target/.anchor (no GPU)
 //   driver case.bin out.bin         : GPU run
 // case.bin: int32 n (cells per dim), int32 g (ghost width), int32 N (markers), char[32] kernel,
 //           double X[N][3], double F[N][3], then per axis the side array of u (Fortran order, ghosts incl.)
 // out.bin : double Q[N][3] (LEInteractor::interpolate), per-axis f arrays (LEInteractor::spread into zero),
-//           double U[N][3] (IBMethodB200::interpolateVelocity), per-axis f arrays (IBMethodB200::spreadForce)
+//           double U[N][3] (IBMethodB200::interpolateVelocity), per-axis f arrays (IBMethodB200::spreadForce),
+//           double Fl[N][3] (computeLagrangianForce for a closed ring of springs i -> i+1, kappa 1.5, rest 0.01, and
+//           target points on every 7th marker), double Xnew[N][3] (forwardEulerStep with dt = 0.01)
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <vector>
 
 #define NDIM 3
 #include "../../ibamr_b200/host/IBMethodB200.h"
+#include "../../ibamr_b200/host/IBStandardInitializerB200.h"
 #include "../../ibamr_b200/host/LEInteractorB200.h"
 
 using namespace SAMRAI_standin;
@@ -41,9 +46,30 @@ static int run_static()
     return 0;
 }
 
+static int run_structure(const char* base, int ndim)
+{
+    try
+    {
+        IBAMR_B200::IBStandardInitializerB200 init(ndim, { std::string(base) });
+        std::printf("vertices=%d springs=%zu beams=%zu targets=%zu anchors=%zu\n", init.num_vertices, init.spring_master.size(),
+                    init.beam_curr.size(), init.target_idx.size(), init.anchor_idx.size());
+        std::printf("X0=%.17g,%.17g\n", init.X[0], init.X[1]);
+        if (!init.spring_master.empty())
+            std::printf("last spring=%d,%d,%.17g,%.17g\n", init.spring_master.back(), init.spring_slave.back(), init.spring_kappa.back(),
+                        init.spring_rest.back());
+    }
+    catch (const std::exception& e)
+    {
+        std::printf("error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc >= 2 && !std::strcmp(argv[1], "--static")) return run_static();
+    if (argc >= 4 && !std::strcmp(argv[1], "--structure")) return run_structure(argv[2], std::atoi(argv[3]));
     if (argc < 3) return 2;
     FILE* fi = std::fopen(argv[1], "rb");
     if (!fi) return 3;
@@ -105,6 +131,31 @@ int main(int argc, char** argv)
         SideData f2(box, 1, IntVector(g));
         ib.getEulerianForce(0, f2);
         for (int a = 0; a < 3; ++a) std::fwrite(f2.getPointer(a), 8, f2.data[a].size(), fo);
+        // N1: force generation and a forward-Euler step on the device
+        std::vector<int> m(N), sl(N), ti;
+        std::vector<double> kap(N, 1.5), rest(N, 0.01), tk, te, tx0;
+        for (int i = 0; i < N; ++i)
+        {
+            m[i] = i;
+            sl[i] = (i + 1) % N;
+            if (i % 7 == 0)
+            {
+                ti.push_back(i);
+                tk.push_back(2.0);
+                te.push_back(0.25);
+                for (int d = 0; d < 3; ++d) tx0.push_back(0.5);
+            }
+        }
+        ib.registerSprings(m, sl, kap, rest);
+        ib.registerTargetPoints(ti, tk, te, tx0);
+        ib.computeLagrangianForce();
+        std::vector<double> Fl, Xnew;
+        ib.getColumn(IBK_COL_F, Fl);
+        std::fwrite(Fl.data(), 8, Fl.size(), fo);
+        ib.preprocessIntegrateData();
+        ib.forwardEulerStep(0.0, 0.01);
+        ib.getColumn(IBK_COL_X_NEW, Xnew);
+        std::fwrite(Xnew.data(), 8, Xnew.size(), fo);
     }
     catch (const std::exception& e)
     {

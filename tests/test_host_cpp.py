@@ -111,3 +111,26 @@ def test_cpp_host_mirror_vs_oracle(driver, kernel, tmp_path):
         assert rel(fB1[a][sl], fr[a][sl]) <= 1e-12
     # u given to the level has analytic (periodic) ghosts already, so U must equal the position-only result
     assert rel(U, Qo) <= 1e-12
+    # N1 through the C++ mirror: computeLagrangianForce (ring of springs + target points) and forwardEulerStep
+    Fl = raw[off:off + 3 * N].reshape(N, 3); off += 3 * N
+    Xnew = raw[off:off + 3 * N].reshape(N, 3); off += 3 * N
+    assert off == raw.size
+    Xw, _ = orc.wrap_positions(X, level.x_lower, level.x_upper, level.periodic)
+    Xw = Xw.reshape(N, 3)
+    ti = np.arange(0, N, 7)
+    Fo = orc.lagrangian_force(3, Xw, U, springs=(np.arange(N), (np.arange(N) + 1) % N, np.full(N, 1.5), np.full(N, 0.01)),
+                              targets=(ti, np.full(len(ti), 2.0), np.full(len(ti), 0.25), np.full((len(ti), 3), 0.5)))
+    assert rel(Fl, Fo) <= 1e-14
+    assert np.array_equal(Xnew, Xw + 0.01 * U)
+
+
+def test_cpp_structure_reader(driver):
+    """IBStandardInitializerB200 (host C++, no GPU) on the reference's sample structure files."""
+    gold = os.path.join(ROOT, "tests", "golden")
+    out = subprocess.run([driver, "--structure", os.path.join(gold, "curve2d_64"), "2"], capture_output=True, text=True, check=True).stdout
+    assert "vertices=304 springs=304 beams=0 targets=0 anchors=0" in out
+    assert "last spring=0,303,193.53241079974475,0" in out
+    out = subprocess.run([driver, "--structure", os.path.join(gold, "fila_256"), "2"], capture_output=True, text=True, check=True).stdout
+    assert "vertices=201 springs=200 beams=199 targets=1 anchors=0" in out and "X0=4.5,14.75" in out
+    r = subprocess.run([driver, "--structure", os.path.join(gold, "no_such_structure"), "2"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Cannot find required vertex file" in r.stdout
