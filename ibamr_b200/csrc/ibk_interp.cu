@@ -23,14 +23,10 @@
 #include <cstring>
 
 #include "ibk_engine.h"
+#include "ibk_tma.h"
 
 namespace ibk
 {
-struct alignas(64) TmaMapSet
-{
-    CUtensorMap m[IBK_MAX_COMP];
-};
-
 struct InterpArgs
 {
     const int* brick_start;
@@ -251,18 +247,14 @@ static PFN_encodeTiled get_encode_fn()
     return fn;
 }
 
-static bool tma_eligible(const CompGeom& cg)
+bool make_tensor_map(CUtensorMap* m, const CompGeom& cg, int ndim, unsigned bx, unsigned by, unsigned bz)
 {
-    return ((uintptr_t)cg.ptr % 16 == 0) && ((cg.pitch * 8) % 16 == 0);
-}
-
-static bool make_map(CUtensorMap* m, const CompGeom& cg, int ndim, int S)
-{
+    if (((uintptr_t)cg.ptr % 16 != 0) || ((cg.pitch * 8) % 16 != 0)) return false;
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return false;
     cuuint64_t dims[3] = { (cuuint64_t)cg.n[0], (cuuint64_t)cg.n[1], (cuuint64_t)cg.n[2] };
     cuuint64_t strides[2] = { (cuuint64_t)cg.pitch * 8ull, (cuuint64_t)cg.pitch * 8ull * (cuuint64_t)cg.n[1] };
-    cuuint32_t box[3] = { (cuuint32_t)(S + 2), (cuuint32_t)S, (cuuint32_t)S };
+    cuuint32_t box[3] = { (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz };
     cuuint32_t estr[3] = { 1, 1, 1 };
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)ndim, (void*)cg.ptr, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -291,7 +283,7 @@ static cudaError_t launch_interp_t(Launcher& L, const TileParams& tp, const Bins
     static const bool no_tma = getenv("IBK_NO_TMA") != nullptr;
     static const bool dbg = getenv("IBK_DEBUG") != nullptr;
     for (int a = 0; a < tp.ncomp; ++a)
-        if (!no_tma && tma_eligible(tp.comp[a]) && make_map(&maps.m[a], tp.comp[a], NDIM, S)) args.tma_mask |= (1u << a);
+        if (!no_tma && make_tensor_map(&maps.m[a], tp.comp[a], NDIM, S + 2, S, S)) args.tma_mask |= (1u << a);
     if (dbg)
         fprintf(stderr, "[ibk] interp<%d,%d> ncomp=%d tma_mask=%x ntiles=%d n=(%d,%d,%d) pitch=%lld ptr=%p sizeof(tp)=%zu\n", NDIM, K,
                 tp.ncomp, args.tma_mask, tp.nt[0] * tp.nt[1] * tp.nt[2], tp.comp[0].n[0], tp.comp[0].n[1], tp.comp[0].n[2],

@@ -31,8 +31,10 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "ibk_engine.h"
+#include "ibk_tma.h"
 
 namespace ibk
 {
@@ -55,6 +57,7 @@ struct SpreadArgs
     int* exc_list;
     int exc_capacity;
     int cap; // markers whose stencil weights are staged at a time (sizes the dynamic shared memory)
+    unsigned tma_mask; // bit a: the block of component a is loaded / stored by TMA (else zero-fill + red write-out)
 };
 
 // Brick colouring of a tile, worked out at compile time: the bricks of a tile in colour-major order
@@ -94,12 +97,16 @@ __constant__ BrickColouring<NDIM, NC> c_colouring = BrickColouring<NDIM, NC>();
 
 template <int NDIM, int K>
 __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
-    spread_tile_kernel(const __grid_constant__ TileParams tp, SpreadArgs args)
+    spread_tile_kernel(const __grid_constant__ TileParams tp, const __grid_constant__ TmaMapSet maps, SpreadArgs args)
 {
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
     constexpr int R = TILE + 2 * M; // haloed block edge
-    constexpr int RPTS = (NDIM == 3) ? R * R * R : R * R;
+    // TMA boxes of 8-byte elements must start on an even x coordinate and have an even x extent (16 bytes):
+    // the block gets XO spare columns on the left and is RX wide in x.
+    constexpr int XO = M & 1;
+    constexpr int RX = (R + XO + 1) & ~1;
+    constexpr int RPTS = (NDIM == 3) ? R * R * RX : R * RX;
     constexpr int NC = (BRICK + 2 * M + BRICK - 1) / BRICK; // brick colours per dimension
     using Colouring = BrickColouring<NDIM, NC>;
     constexpr int NBRICKS = Colouring::NB;
@@ -109,14 +116,15 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     static_assert(R <= 24 && R < 128, "write-out covers a row with 8 lanes x 3 points; origins are kept in bytes");
     const Colouring& bc = c_colouring<NDIM, NC>;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* acc = reinterpret_cast<double*>(smem_raw);            // [RPTS]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* acc = reinterpret_cast<double*>(smem_raw);            // [R][R][RX] (z, y, x)
     double* wgt = acc + RPTS;                                     // [cap][NDIM][W]  1-D weights (force folded in)
     int* rel = reinterpret_cast<int*>(wgt + args.cap * NDIM * W); // [cap]  stencil origin in the block, a byte per dim
     __shared__ int bfirst[NBRICKS];   // first marker of the brick at colour-order position p
     __shared__ int bpre[NBRICKS + 1]; // markers in the bricks before colour-order position p
     __shared__ int wsum[2];
     __shared__ int wcol[2]; // first / last colour present in the current window
+    __shared__ __align__(8) uint64_t tma_bar;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -140,6 +148,18 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     int blo[3]; // pp coordinate of the block's first point
 #pragma unroll
     for (int d = 0; d < 3; ++d) blo[d] = TILE * t[d] - M;
+    // With TMA the block starts as a copy of f (out-of-array points read as zero) and is stored back at the end
+    // (out-of-array points dropped): `f += S[F]` without a separate zero / add pass and without atomics.
+    // (Measured on B200: a TMA tensor STORE with a negative start coordinate traps, loads do not; the blocks of the
+    // first tile per dimension therefore take the fallback.  The store also writes whole 16-byte units, i.e. one
+    // element of the row padding when n[0] is odd: harmless, nothing reads the padding.)
+    const bool use_tma = ((args.tma_mask >> a) & 1u) && (blo[0] - XO - cg.pp0[0] >= 0) && (blo[1] - cg.pp0[1] >= 0) &&
+                         (NDIM == 2 || blo[2] - cg.pp0[2] >= 0);
+    if (use_tma && threadIdx.x == 0)
+    {
+        mbar_init(&tma_bar, 1);
+        mbar_fence_init();
+    }
 
     // marker ranges of the bricks in colour-major order, and their running count (two-warp scan)
     int my_cnt = 0, my_incl = 0;
@@ -161,8 +181,17 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
         }
         if (lane == 31) wsum[warp] = my_incl;
     }
-    for (int q = threadIdx.x; q < RPTS; q += SPREAD_THREADS) acc[q] = 0.0;
+    if (!use_tma)
+        for (int q = threadIdx.x; q < RPTS; q += SPREAD_THREADS) acc[q] = 0.0;
     __syncthreads();
+    if (use_tma && threadIdx.x == 0)
+    {
+        mbar_expect_tx(&tma_bar, (uint32_t)(RPTS * sizeof(double)));
+        if (NDIM == 3)
+            tma_load_3d(acc, &maps.m[a], &tma_bar, blo[0] - XO - cg.pp0[0], blo[1] - cg.pp0[1], blo[2] - cg.pp0[2]);
+        else
+            tma_load_2d(acc, &maps.m[a], &tma_bar, blo[0] - XO - cg.pp0[0], blo[1] - cg.pp0[1]);
+    }
     if (threadIdx.x < NBRICKS)
     {
         const int before = (warp == 1) ? wsum[0] : 0;
@@ -188,7 +217,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     {
         const int q = lane + 32 * s;
         const int ix = q % W, iy = (q / W) % W, iz = (NDIM == 3) ? q / (W * W) : 0;
-        poff[s] = (iz * R + iy) * R + ix;
+        poff[s] = (iz * R + iy) * RX + ix + XO;
         pw0[s] = ix;
         pw1[s] = W + iy;
         pw2[s] = 2 * W + iz;
@@ -233,6 +262,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
             if (NDIM == 2 && d == 0) reinterpret_cast<signed char*>(rel)[m * 4 + 2] = 0;
         }
         __syncthreads();
+        if (use_tma && off == 0) mbar_wait(&tma_bar, 0); // the block holds f now
         // ---- phase B, colour by colour (only the colours this window holds)
         const int col_lo = wcol[0], col_hi = wcol[1];
         for (int col = col_lo; col <= col_hi; ++col)
@@ -247,7 +277,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
                     const int rr = rel[m];
                     if ((rr & 0x00808080) == 0) // else: does not fit the block, left to the fix-up (warp-uniform)
                     {
-                        const int base = (((rr >> 16) & 0xff) * R + ((rr >> 8) & 0xff)) * R + (rr & 0xff);
+                        const int base = (((rr >> 16) & 0xff) * R + ((rr >> 8) & 0xff)) * RX + (rr & 0xff);
                         const double* wm = wgt + m * (NDIM * W);
 #pragma unroll
                         for (int s = 0; s < NSLOT; ++s)
@@ -270,10 +300,24 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
         }
     }
 
-    // ---- write-out: f += block (rows along x), dropping points outside the array.  Inside one launch a grid
-    // point belongs to at most one CTA, so the add is a fire-and-forget `red.global.add.f64`: one per point and
-    // launch, the launches are ordered by the stream, hence the order of the additions is fixed and the result
-    // bit-reproducible.
+    // ---- write-out.  TMA: the block (= old f + the spread values) is stored back, clipped to the array.
+    if (use_tma)
+    {
+        fence_proxy_async_smem(); // this thread's generic-proxy writes to the block -> visible to the async proxy
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            if (NDIM == 3)
+                tma_store_3d(&maps.m[a], acc, blo[0] - XO - cg.pp0[0], blo[1] - cg.pp0[1], blo[2] - cg.pp0[2]);
+            else
+                tma_store_2d(&maps.m[a], acc, blo[0] - XO - cg.pp0[0], blo[1] - cg.pp0[1]);
+            tma_store_commit_and_wait_read(); // shared memory must stay alive until it has been read
+        }
+        return;
+    }
+    // Fallback (array not addressable by TMA): f += block with `red.global.add.f64`, rows along x, dropping points
+    // outside the array.  Inside one launch a grid point belongs to at most one CTA and the launches are ordered by
+    // the stream, so the order of the additions is fixed and the result bit-reproducible.
     {
         constexpr int ROWS = (NDIM == 3) ? R * R : R;
         constexpr int RSTEP = SPREAD_THREADS / 8; // rows per sweep: a group of 8 lanes takes one row at a time,
@@ -284,8 +328,8 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
         for (int k = 0; k < 3; ++k) okx[k] = (l8 + 8 * k < R) && (gx0 + 8 * k >= 0) && (gx0 + 8 * k < cg.n[0]);
         int y = g8 % R, z = g8 / R;
         const int gy0 = blo[1] - cg.pp0[1], gz0 = (NDIM == 3) ? blo[2] - cg.pp0[2] : 0;
-        const double* arow = acc + g8 * R + l8;
-        for (int row = g8; row < ROWS; row += RSTEP, arow += RSTEP * R)
+        const double* arow = acc + g8 * RX + XO + l8;
+        for (int row = g8; row < ROWS; row += RSTEP, arow += RSTEP * RX)
         {
             const int gj = gy0 + y, gk = gz0 + z;
             y += RSTEP % R;
@@ -374,7 +418,9 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
     constexpr int R = TILE + 2 * M;
-    constexpr int RPTS = (NDIM == 3) ? R * R * R : R * R;
+    constexpr int XO = M & 1;
+    constexpr int RX = (R + XO + 1) & ~1;
+    constexpr int RPTS = (NDIM == 3) ? R * R * RX : R * RX;
     cudaError_t e;
     if (!g_exc_buf)
     {
@@ -406,6 +452,20 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     constexpr int cap_fit = (int)(budget / per_marker);
     args.cap = (cap_env >= 8 && cap_env <= 1024) ? cap_env : std::max(32, std::min(256, cap_fit));
     const size_t smem = sizeof(double) * ((size_t)RPTS + (size_t)args.cap * NDIM * W) + sizeof(int) * (size_t)args.cap;
+    // TMA moves the block when it can address the array and the block starts on an even x coordinate
+    TmaMapSet maps;
+    std::memset(&maps, 0, sizeof(maps));
+    args.tma_mask = 0;
+    static const bool no_tma = getenv("IBK_NO_TMA") != nullptr;
+    for (int a = 0; a < tp.ncomp; ++a)
+        if (!no_tma && ((tp.comp[a].pp0[0] + M + XO) % 2 == 0) && make_tensor_map(&maps.m[a], tp.comp[a], NDIM, RX, R, R))
+            args.tma_mask |= (1u << a);
+    static const bool dbg = getenv("IBK_DEBUG") != nullptr;
+    if (dbg)
+        for (int a = 0; a < tp.ncomp; ++a)
+            fprintf(stderr, "[ibk] spread<%d,%d> comp %d tma=%u n=(%d,%d,%d) pitch=%lld pp0=(%d,%d,%d) ptr=%p nt=(%d,%d,%d) box=(%d,%d)\n", NDIM,
+                    K, a, (args.tma_mask >> a) & 1u, tp.comp[a].n[0], tp.comp[a].n[1], tp.comp[a].n[2], tp.comp[a].pitch,
+                    tp.comp[a].pp0[0], tp.comp[a].pp0[1], tp.comp[a].pp0[2], (void*)tp.comp[a].ptr, tp.nt[0], tp.nt[1], tp.nt[2], RX, R);
     auto kfn = spread_tile_kernel<NDIM, K>;
     auto ffn = spread_fixup_kernel<NDIM, K>;
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -427,7 +487,7 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
         }
         if (ntiles <= 0) continue;
         dim3 grid((unsigned)ntiles, (unsigned)tp.ncomp);
-        kfn<<<grid, SPREAD_THREADS, smem, L.stream>>>(tp, args);
+        kfn<<<grid, SPREAD_THREADS, smem, L.stream>>>(tp, maps, args);
         L.launches++;
     }
     ffn<<<1, 32, 0, L.stream>>>(tp, args);
