@@ -361,6 +361,16 @@ def run_gpu(args):
         spread_bytes = 8 * (3 * N + 3 * N) + 16 * touched
         interp_bytes = 8 * (3 * N + 3 * N) + 8 * touched
         ach = spread_bytes / (sp_ms * 1e-3) / 1e9
+        # DRAM traffic of the same kernels from the committed ncu pass (profiles/, not measured in this run)
+        traffic, traffic_interp, traffic_src = None, None, None
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_step_kernels_dram.json")) as f:
+                prof = json.load(f)["per_kernel"]
+            traffic = sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in prof.items() if k.startswith("spread_"))
+            traffic_interp = sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in prof.items() if k.startswith("interp_"))
+            traffic_src = "profiles/r01_step_kernels_dram.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, same workload, 1 GPU)"
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": total_markers / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -371,10 +381,11 @@ def run_gpu(args):
                     "what": "host X, F, u (pinned) -> device, re-bin, step, U and f -> host; all copies inside the timed region, u upload / f download on copy streams overlapping the kernels"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "spread_tile_kernel<3,IB_4> (+ fix-up)", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes": spread_bytes, "launch_ms": sp_ms,
                          "interp": {"kernel": "interp_tile_kernel<3,IB_4>", "achieved": interp_bytes / (in_ms * 1e-3) / 1e9,
                                     "frac": interp_bytes / (in_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": interp_bytes,
+                                    "traffic": traffic_interp,
                                     "launch_ms": in_ms},
                          "touched_side_dofs": touched},
             "clocks": sampler.result(),
