@@ -38,7 +38,20 @@
 
 namespace ibk
 {
+// -DIBK_TIMELINE: thread 0 of a few CTAs records clock64() at the phase boundaries (printed by the launcher)
+#ifdef IBK_TIMELINE
+__device__ long long g_tl[64][16];
+__device__ int g_tl_n;
+#define TL(k)                                             \
+    do                                                    \
+    {                                                     \
+        if (threadIdx.x == 0 && tl_on) tl[k] = clock64(); \
+    } while (0)
+#else
+#define TL(k)
+#endif
 constexpr int SPREAD_THREADS = 256;
+constexpr int SPREAD_TASKS = 2; // (marker, dimension) stencil evaluations per thread and window
 constexpr int SPREAD_WARPS = SPREAD_THREADS / 32;
 
 struct SpreadArgs
@@ -93,7 +106,9 @@ struct BrickColouring
     }
 };
 template <int NDIM, int NC>
-__constant__ BrickColouring<NDIM, NC> c_colouring = BrickColouring<NDIM, NC>();
+__constant__ BrickColouring<NDIM, NC> c_colouring = BrickColouring<NDIM, NC>(); // uniform reads (start[], one colour[])
+template <int NDIM, int NC>
+__device__ const BrickColouring<NDIM, NC> d_colouring = BrickColouring<NDIM, NC>(); // per-lane reads (order[])
 
 template <int NDIM, int K>
 __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
@@ -123,7 +138,8 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     __shared__ int bfirst[NBRICKS];   // first marker of the brick at colour-order position p
     __shared__ int bpre[NBRICKS + 1]; // markers in the bricks before colour-order position p
     __shared__ int wsum[2];
-    __shared__ int wcol[2]; // first / last colour present in the current window
+    __shared__ int wcol[2][2];       // first / last colour present in the window (double-buffered by window parity)
+    __shared__ int sbs[NBRICKS + 1]; // the tile's slice of brick_start
     __shared__ __align__(8) uint64_t tma_bar;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -141,9 +157,20 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     const CompGeom& cg = tp.comp[a];
     const int tile = (NDIM == 3) ? (t[2] * tp.nt[1] + t[1]) * tp.nt[0] + t[0] : t[1] * tp.nt[0] + t[0];
     const int b0 = tp.brick_base + tile * NBRICKS;
-    const int s0 = __ldg(&args.brick_start[b0]);
-    const int s1 = __ldg(&args.brick_start[b0 + NBRICKS]);
+    // one coalesced read of the tile's NBRICKS + 1 segment offsets, and (independent of it) the colour order
+    int my_q = 0;
+    if (threadIdx.x <= NBRICKS) sbs[threadIdx.x] = __ldg(&args.brick_start[b0 + threadIdx.x]);
+    if (threadIdx.x < NBRICKS) my_q = __ldg(&d_colouring<NDIM, NC>.order[threadIdx.x]);
+#ifdef IBK_TIMELINE
+    long long tl[16];
+    for (int k = 0; k < 16; ++k) tl[k] = 0;
+    const bool tl_on = threadIdx.x == 0 && blockIdx.y == 0 && (blockIdx.x % 97) == 5;
+    TL(0);
+#endif
+    __syncthreads();
+    const int s0 = sbs[0], s1 = sbs[NBRICKS];
     if (s0 >= s1) return;
+    TL(1);
 
     int blo[3]; // pp coordinate of the block's first point
 #pragma unroll
@@ -165,8 +192,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     int my_cnt = 0, my_incl = 0;
     if (threadIdx.x < NBRICKS)
     {
-        const int q = bc.order[threadIdx.x];
-        const int s = __ldg(&args.brick_start[b0 + q]), e = __ldg(&args.brick_start[b0 + q + 1]);
+        const int s = sbs[my_q], e = sbs[my_q + 1];
         bfirst[threadIdx.x] = s;
         my_cnt = e - s;
     }
@@ -184,6 +210,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     if (!use_tma)
         for (int q = threadIdx.x; q < RPTS; q += SPREAD_THREADS) acc[q] = 0.0;
     __syncthreads();
+    TL(2);
     if (use_tma && threadIdx.x == 0)
     {
         mbar_expect_tx(&tma_bar, (uint32_t)(RPTS * sizeof(double)));
@@ -223,48 +250,79 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
         pw2[s] = 2 * W + iz;
     }
     __syncthreads();
+    TL(3);
     const int total = s1 - s0;
 
-    for (int off = 0; off < total; off += cap)
-    {
+    // stencil-evaluation tasks of this thread for a window: the global loads are issued by fetch() -- for window
+    // w + 1 before the accumulation of window w starts, so their latency hides behind it -- and consumed by
+    // evaluate() at the top of the window.
+    int t_i[SPREAD_TASKS];
+    double t_xs[SPREAD_TASKS], t_xr[SPREAD_TASKS], t_v[SPREAD_TASKS];
+    auto fetch = [&](int off, int par) {
         const int cnt = min(cap, total - off);
-        // ---- phase A
-        for (int tix = threadIdx.x; tix < cnt * NDIM; tix += SPREAD_THREADS)
+#pragma unroll
+        for (int k = 0; k < SPREAD_TASKS; ++k)
         {
+            const int tix = threadIdx.x + k * SPREAD_THREADS;
+            t_i[k] = -1;
+            if (tix >= cnt * NDIM) continue;
             const int m = tix / NDIM, d = tix - m * NDIM;
             const int lp = off + m; // position in the tile's colour-major marker list
             int p = 0;              // its brick (colour-order position): last p with bpre[p] <= lp
 #pragma unroll
             for (int step = NBRICKS / 2; step >= 1; step >>= 1)
                 if (bpre[p + step] <= lp) p += step;
-            if (d == 0 && m == 0) wcol[0] = bc.colour[p];
-            if (d == 0 && m == cnt - 1) wcol[1] = bc.colour[p];
+            if (d == 0 && m == 0) wcol[par][0] = bc.colour[p];
+            if (d == 0 && m == cnt - 1) wcol[par][1] = bc.colour[p];
             const int i = bfirst[p] + (lp - bpre[p]);
-            const double xs = __ldg(&Xp[d * args.x_stride + i]);
-            const double xr = Xr ? __ldg(&Xr[d * args.x_stride + i]) : xs;
+            t_i[k] = i;
+            t_xs[k] = __ldg(&Xp[d * args.x_stride + i]);
+            t_xr[k] = Xr ? __ldg(&Xr[d * args.x_stride + i]) : 0.0;
+            t_v[k] = 1.0;
+            if (d == LD)
+            {
+                const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
+                t_v[k] = __ldg(&args.V[vcol * args.v_cstride + row * args.v_istride]);
+            }
+        }
+    };
+    auto evaluate = [&]() {
+#pragma unroll
+        for (int k = 0; k < SPREAD_TASKS; ++k)
+        {
+            if (t_i[k] < 0) continue;
+            const int tix = threadIdx.x + k * SPREAD_THREADS;
+            const int m = tix / NDIM, d = tix - m * NDIM;
             const double xl_s = tp.xl[d][cg.var[d]];
             const double dx_s = tp.dx[d];
             const int blo_s = (d == 0) ? blo[0] : (d == 1) ? blo[1] : blo[2];
             double w[W];
             int l;
-            stencil_1d<K>(xs, xr, xl_s, dx_s, l, w);
+            stencil_1d<K>(t_xs[k], Xr ? t_xr[k] : t_xs[k], xl_s, dx_s, l, w);
             const int r0 = l + G - blo_s; // first stencil point relative to the block
             const bool fits = r0 >= 0 && r0 + W <= R;
-            double scale = 1.0;
-            if (d == LD)
-            {
-                const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
-                scale = __ldg(&args.V[vcol * args.v_cstride + row * args.v_istride]) * inv_vol;
-            }
+            const double scale = (d == LD) ? t_v[k] * inv_vol : 1.0;
 #pragma unroll
             for (int j = 0; j < W; ++j) wgt[(m * NDIM + d) * W + j] = w[j] * scale;
             reinterpret_cast<signed char*>(rel)[m * 4 + d] = fits ? (signed char)r0 : (signed char)-1;
             if (NDIM == 2 && d == 0) reinterpret_cast<signed char*>(rel)[m * 4 + 2] = 0;
         }
+    };
+
+    fetch(0, 0);
+    int par = 0;
+    for (int off = 0; off < total; off += cap, par ^= 1)
+    {
+        const int cnt = min(cap, total - off);
+        // ---- phase A
+        evaluate();
         __syncthreads();
+        if (off == 0) TL(4);
         if (use_tma && off == 0) mbar_wait(&tma_bar, 0); // the block holds f now
+        if (off == 0) TL(5);
+        const int col_lo = wcol[par][0], col_hi = wcol[par][1];
+        if (off + cap < total) fetch(off + cap, par ^ 1);
         // ---- phase B, colour by colour (only the colours this window holds)
-        const int col_lo = wcol[0], col_hi = wcol[1];
         for (int col = col_lo; col <= col_hi; ++col)
         {
             const int cend = bc.start[col + 1];
@@ -298,7 +356,10 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
             }
             __syncthreads();
         }
+        if (off == 0) TL(6);
+        if (off == cap) TL(7);
     }
+    TL(8);
 
     // ---- write-out.  TMA: the block (= old f + the spread values) is stored back, clipped to the array.
     if (use_tma)
@@ -312,6 +373,15 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
             else
                 tma_store_2d(&maps.m[a], acc, blo[0] - XO - cg.pp0[0], blo[1] - cg.pp0[1]);
             tma_store_commit_and_wait_read(); // shared memory must stay alive until it has been read
+#ifdef IBK_TIMELINE
+            TL(9);
+            if (tl_on)
+            {
+                const int slot = atomicAdd(&g_tl_n, 1);
+                if (slot < 64)
+                    for (int k = 0; k < 16; ++k) g_tl[slot][k] = tl[k];
+            }
+#endif
         }
         return;
     }
@@ -447,10 +517,11 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     // window size: as many markers as the shared memory left by the block allows at the target residency
     static const int cap_env = getenv("IBK_SPREAD_CAP") ? atoi(getenv("IBK_SPREAD_CAP")) : 0;
     constexpr int target_ctas = (M <= 2) ? 3 : 2;
-    constexpr long long budget = 233472 / target_ctas - 1024 - 2048 - (long long)sizeof(double) * RPTS;
+    constexpr long long budget = 233472 / target_ctas - 1024 - 2304 - (long long)sizeof(double) * RPTS;
     constexpr int per_marker = (int)sizeof(double) * NDIM * W + (int)sizeof(int);
     constexpr int cap_fit = (int)(budget / per_marker);
     args.cap = (cap_env >= 8 && cap_env <= 1024) ? cap_env : std::max(32, std::min(256, cap_fit));
+    args.cap = std::min(args.cap, SPREAD_TASKS * SPREAD_THREADS / NDIM); // fetch()/evaluate() hold SPREAD_TASKS tasks per thread
     const size_t smem = sizeof(double) * ((size_t)RPTS + (size_t)args.cap * NDIM * W) + sizeof(int) * (size_t)args.cap;
     // TMA moves the block when it can address the array and the block starts on an even x coordinate
     TmaMapSet maps;
@@ -492,6 +563,28 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     }
     ffn<<<1, 32, 0, L.stream>>>(tp, args);
     L.launches++;
+#ifdef IBK_TIMELINE
+    {
+        static int calls = 0;
+        if (++calls == 6)
+        {
+            cudaStreamSynchronize(L.stream);
+            static long long h[64][16];
+            int n = 0;
+            cudaMemcpyFromSymbol(&n, g_tl_n, sizeof(int));
+            cudaMemcpyFromSymbol(h, g_tl, sizeof(h));
+            n = std::min(n, 64);
+            double avg[16] = { 0 };
+            int used = 0;
+            for (int i = n / 2; i < n; ++i, ++used)
+                for (int k = 1; k < 10; ++k) avg[k] += (double)(h[i][k] - h[i][0]);
+            fprintf(stderr, "[timeline] %d samples; cycles since CTA start:", used);
+            const char* nm[10] = { "start", "offsets", "bricks", "scan", "phaseA0", "tma_wait", "phaseB0", "window1", "allB", "stored" };
+            for (int k = 1; k < 10; ++k) fprintf(stderr, " %s=%.0f", nm[k], avg[k] / std::max(used, 1));
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     return cudaGetLastError();
 }
 
