@@ -134,7 +134,9 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* acc = reinterpret_cast<double*>(smem_raw);            // [R][R][RX] (z, y, x)
     double* wgt = acc + RPTS;                                     // [cap][NDIM][W]  1-D weights (force folded in)
-    int* rel = reinterpret_cast<int*>(wgt + args.cap * NDIM * W); // [cap]  stencil origin in the block, a byte per dim
+    // [2][cap] byte offset of the stencil origin inside the block (negative: the stencil does not fit), summed over the
+    // dimensions by shared-memory atomics; double-buffered by window parity
+    int* relb = reinterpret_cast<int*>(wgt + args.cap * NDIM * W);
     __shared__ int bfirst[NBRICKS];   // first marker of the brick at colour-order position p
     __shared__ int bpre[NBRICKS + 1]; // markers in the bricks before colour-order position p
     __shared__ int wsum[2];
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     int my_q = 0;
     if (threadIdx.x <= NBRICKS) sbs[threadIdx.x] = __ldg(&args.brick_start[b0 + threadIdx.x]);
     if (threadIdx.x < NBRICKS) my_q = __ldg(&d_colouring<NDIM, NC>.order[threadIdx.x]);
+    for (int q = threadIdx.x; q < args.cap; q += SPREAD_THREADS) relb[q] = 0;
 #ifdef IBK_TIMELINE
     long long tl[16];
     for (int k = 0; k < 16; ++k) tl[k] = 0;
@@ -238,13 +241,13 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     const int vcol = cg.vcol;
     const int cap = args.cap;
     // phase-B role: this lane's stencil point(s), as offsets into the block and into the weight scratch
-    int poff[NSLOT], pw0[NSLOT], pw1[NSLOT], pw2[NSLOT];
+    int poffb[NSLOT], pw0[NSLOT], pw1[NSLOT], pw2[NSLOT];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s)
     {
         const int q = lane + 32 * s;
         const int ix = q % W, iy = (q / W) % W, iz = (NDIM == 3) ? q / (W * W) : 0;
-        poff[s] = (iz * R + iy) * RX + ix + XO;
+        poffb[s] = 8 * ((iz * R + iy) * RX + ix + XO);
         pw0[s] = ix;
         pw1[s] = W + iy;
         pw2[s] = 2 * W + iz;
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
             if (d == 0 && m == 0) wcol[par][0] = bc.colour[p];
             if (d == 0 && m == cnt - 1) wcol[par][1] = bc.colour[p];
             const int i = bfirst[p] + (lp - bpre[p]);
+            if (d == 0 && off > 0) relb[par * cap + m] = 0;
             t_i[k] = i;
             t_xs[k] = __ldg(&Xp[d * args.x_stride + i]);
             t_xr[k] = Xr ? __ldg(&Xr[d * args.x_stride + i]) : 0.0;
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
             }
         }
     };
-    auto evaluate = [&]() {
+    auto evaluate = [&](int par) {
 #pragma unroll
         for (int k = 0; k < SPREAD_TASKS; ++k)
         {
@@ -304,8 +308,8 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
             const double scale = (d == LD) ? t_v[k] * inv_vol : 1.0;
 #pragma unroll
             for (int j = 0; j < W; ++j) wgt[(m * NDIM + d) * W + j] = w[j] * scale;
-            reinterpret_cast<signed char*>(rel)[m * 4 + d] = fits ? (signed char)r0 : (signed char)-1;
-            if (NDIM == 2 && d == 0) reinterpret_cast<signed char*>(rel)[m * 4 + 2] = 0;
+            const int stride_b = (d == 0) ? 8 : (d == 1) ? 8 * RX : 8 * RX * R; // bytes per point along d in the block
+            atomicAdd(&relb[par * cap + m], fits ? r0 * stride_b : -(1 << 29));
         }
     };
 
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     {
         const int cnt = min(cap, total - off);
         // ---- phase A
-        evaluate();
+        evaluate(par);
         __syncthreads();
         if (off == 0) TL(4);
         if (use_tma && off == 0) mbar_wait(&tma_bar, 0); // the block holds f now
@@ -330,21 +334,45 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
             {
                 const int p0 = bpre[p], p1 = bpre[p + 1];
                 const int m0 = max(p0, off) - off, m1 = min(p1, off + cnt) - off;
-                for (int m = m0; m < m1; ++m)
+                if (m0 >= m1) continue;
+                // Per marker only the block's read-modify-write is serial: the origin of marker m + 1 is read ahead,
+                // the weights are addressed by running pointers, all loads of a marker precede its stores.
+                constexpr int NW = NDIM * W;
+                const int* rp = relb + par * cap;
+                const double* w0p = wgt + m0 * NW + pw0[0];
+                const double* w1p = wgt + m0 * NW + pw1[0];
+                char* const accb = reinterpret_cast<char*>(acc);
+                int ab_next = rp[m0];
+                for (int m = m0; m < m1; ++m, w0p += NW, w1p += NW)
                 {
-                    const int rr = rel[m];
-                    if ((rr & 0x00808080) == 0) // else: does not fit the block, left to the fix-up (warp-uniform)
+                    const int ab = ab_next;
+                    if (m + 1 < m1) ab_next = rp[m + 1];
+                    if (ab >= 0) // else: does not fit the block, left to the fix-up (warp-uniform)
                     {
-                        const int base = (((rr >> 16) & 0xff) * R + ((rr >> 8) & 0xff)) * RX + (rr & 0xff);
-                        const double* wm = wgt + m * (NDIM * W);
+                        double wv[NSLOT], av[NSLOT];
+                        if constexpr (NDIM == 3 && (32 % (W * W)) == 0)
+                        {
+                            // the lane's (ix, iy) is the same in every slot: one xy product, one z weight per slot
+                            const double wxy = w0p[0] * w1p[0];
+#pragma unroll
+                            for (int s = 0; s < NSLOT; ++s) wv[s] = wxy * w0p[pw2[s] - pw0[0]];
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int s = 0; s < NSLOT; ++s)
+                            {
+                                if (NPTS % 32 != 0 && lane + 32 * s >= NPTS) continue;
+                                wv[s] = w0p[pw0[s] - pw0[0]] * w0p[pw1[s] - pw0[0]];
+                                if (NDIM == 3) wv[s] *= w0p[pw2[s] - pw0[0]];
+                            }
+                        }
 #pragma unroll
                         for (int s = 0; s < NSLOT; ++s)
-                        {
-                            if (NPTS % 32 != 0 && lane + 32 * s >= NPTS) continue;
-                            double wv = wm[pw0[s]] * wm[pw1[s]];
-                            if (NDIM == 3) wv *= wm[pw2[s]];
-                            acc[base + poff[s]] += wv;
-                        }
+                            if (NPTS % 32 == 0 || lane + 32 * s < NPTS) av[s] = *reinterpret_cast<double*>(accb + ab + poffb[s]);
+#pragma unroll
+                        for (int s = 0; s < NSLOT; ++s)
+                            if (NPTS % 32 == 0 || lane + 32 * s < NPTS) *reinterpret_cast<double*>(accb + ab + poffb[s]) = av[s] + wv[s];
                     }
                     else if (lane == 0 && args.exc_list)
                     {
@@ -518,11 +546,11 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     static const int cap_env = getenv("IBK_SPREAD_CAP") ? atoi(getenv("IBK_SPREAD_CAP")) : 0;
     constexpr int target_ctas = (M <= 2) ? 3 : 2;
     constexpr long long budget = 233472 / target_ctas - 1024 - 2304 - (long long)sizeof(double) * RPTS;
-    constexpr int per_marker = (int)sizeof(double) * NDIM * W + (int)sizeof(int);
+    constexpr int per_marker = (int)sizeof(double) * NDIM * W + 2 * (int)sizeof(int);
     constexpr int cap_fit = (int)(budget / per_marker);
     args.cap = (cap_env >= 8 && cap_env <= 1024) ? cap_env : std::max(32, std::min(256, cap_fit));
     args.cap = std::min(args.cap, SPREAD_TASKS * SPREAD_THREADS / NDIM); // fetch()/evaluate() hold SPREAD_TASKS tasks per thread
-    const size_t smem = sizeof(double) * ((size_t)RPTS + (size_t)args.cap * NDIM * W) + sizeof(int) * (size_t)args.cap;
+    const size_t smem = sizeof(double) * ((size_t)RPTS + (size_t)args.cap * NDIM * W) + 2 * sizeof(int) * (size_t)args.cap;
     // TMA moves the block when it can address the array and the block starts on an even x coordinate
     TmaMapSet maps;
     std::memset(&maps, 0, sizeof(maps));
