@@ -51,7 +51,8 @@ __device__ int g_tl_n;
 #define TL(k)
 #endif
 constexpr int SPREAD_THREADS = 256;
-constexpr int SPREAD_TASKS = 2; // (marker, dimension) stencil evaluations per thread and window
+constexpr int SPREAD_TASKS = 1; // (marker, dimension) stencil evaluations per thread and window (measured: a second one
+                                // serialises two sqrt/div chains before the barrier: 85-marker windows beat 100-marker ones)
 constexpr int SPREAD_WARPS = SPREAD_THREADS / 32;
 
 struct SpreadArgs
