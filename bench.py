@@ -233,25 +233,30 @@ def run_gpu(args):
     rebin_ms = ctx.last_ms(2)
     touched = ib.count_touched_dofs(KERNEL)
 
+    # Multi-rank: the messages of the halo exchange are in flight while the tiles that do not touch the exchanged
+    # regions are processed (ibk_*_part; include/ibk.h).
     def spread_part():
         if hx is None:
             ib.spreadForce(accumulate_halo=True)
         else:
             lib, hnd = ctx.lib, ctx.h
             ctx.check(lib.ibk_spread_begin(hnd))
-            ib.spreadForce(accumulate_halo=False)
-            hx.accumulate_begin()
+            ib.spreadForcePart(2)        # boundary tiles: everything the neighbours need
+            hx.accumulate_post()         # pack + start the messages
+            ib.spreadForcePart(1)        # interior tiles, overlapping the transfers
             ib.halo("f")
-            hx.accumulate_end()
+            hx.accumulate_finish()       # wait (on the stream) + add
             ctx.check(lib.ibk_spread_end(hnd))
 
     def interp_part():
         if hx is None:
             ib.interpolateVelocity(fill_halo=True)
         else:
+            hx.fill_post()
             ib.halo("u")
-            hx.fill()
-            ib.interpolateVelocity(fill_halo=False)
+            ib.interpolateVelocityPart(1)  # interior tiles read no ghost cell
+            hx.fill_finish()
+            ib.interpolateVelocityPart(2)
 
     def step():
         spread_part()

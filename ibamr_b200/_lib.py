@@ -97,6 +97,10 @@ SYMBOLS = {
     "ibk_markers_download": (_i, [_vp, _i, _pd]),
     "ibk_markers_count": (_i, [_vp]),
     "ibk_rebin": (_i, [_vp, _i]),
+    "ibk_halo_pack_many": (_i, [_vp, _i, _i, _pi, _pi, _pi, _pi, C.POINTER(C.c_longlong), _vp]),
+    "ibk_halo_unpack_many": (_i, [_vp, _i, _i, _pi, _pi, _pi, _pi, C.POINTER(C.c_longlong), _vp, _i]),
+    "ibk_spread_force_part": (_i, [_vp, _s, _i]),
+    "ibk_interpolate_velocity_part": (_i, [_vp, _s, _i]),
     "ibk_markers_set_ids": (_i, [_vp, C.POINTER(C.c_uint), C.c_uint]),
     "ibk_markers_get_ids": (_i, [_vp, C.POINTER(C.c_uint)]),
     "ibk_migrate_plan": (_i, [_vp, _i, _pi, _pi, _pi, _i, _i, _pi]),

@@ -550,6 +550,13 @@ class IBMethodB200:
         """U = J[u]: u_data_idx -> the resident u (ghosts filled first when fill_halo)."""
         self.ctx.check(self.ctx.lib.ibk_interpolate_velocity(self.ctx.h, self.interp_kernel_fcn.encode(), int(fill_halo)))
 
+    def spreadForcePart(self, part):
+        """ibk_spread_force_part: 1 = interior tiles, 2 = boundary tiles; no halo handling."""
+        self.ctx.check(self.ctx.lib.ibk_spread_force_part(self.ctx.h, self.spread_kernel_fcn.encode(), int(part)))
+
+    def interpolateVelocityPart(self, part):
+        self.ctx.check(self.ctx.lib.ibk_interpolate_velocity_part(self.ctx.h, self.interp_kernel_fcn.encode(), int(part)))
+
     def halo(self, which):
         self.ctx.check(self.ctx.lib.ibk_halo_local(self.ctx.h, {"u": 0, "f": 1}[which]))
 

@@ -90,6 +90,19 @@ cudaError_t scatter_columns(Launcher& L, const double* d_in, long long in_stride
                             const uint32_t* d_perm, int n, int ncols);
 cudaError_t extract_low32(Launcher& L, const uint64_t* d_keys, uint32_t* d_out, int n, int bits);
 
+// ibk_halo.cu: all regions of one message in one launch
+struct HaloItem
+{
+    double* ptr;       // array of the (patch, axis)
+    long long pitch;
+    int n1;
+    int off[3], ext[3]; // region in array coordinates
+    long long buf_off;  // first element of the region in the message buffer
+    long long count;
+};
+// op 0: buffer <- regions (pack); 1: regions <- buffer (copy); 2: regions += buffer
+cudaError_t launch_halo_items(Launcher& L, const HaloItem* d_items, int n_items, double* buf, int op);
+
 // ibk_force.cu
 // Force elements by Lagrangian index plus, per node, the elements it takes part in (CSR), all on the device.
 struct ForceTables
@@ -148,6 +161,11 @@ struct MarkerView
     long long v_cstride;
     long long v_istride;
     const uint32_t* src;  // optional gather index (sorted position -> value row); nullptr = identity
+    // optional restriction to a subset of the marker tiles (overlap of the inter-rank halo exchange with the
+    // tiles that do not touch it): part 0 = all tiles, 1 = tiles with sel_lo <= index <= sel_hi in every
+    // dimension, 2 = the others
+    int part = 0;
+    int sel_lo[3] = { 0, 0, 0 }, sel_hi[3] = { 0, 0, 0 };
 };
 
 struct TmaMaps; // opaque, ibk_interp.cu

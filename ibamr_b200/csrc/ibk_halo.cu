@@ -138,6 +138,34 @@ cudaError_t launch_unpack(Launcher& L, double* arr, long long pitch, int n1, con
     return cudaGetLastError();
 }
 
+__global__ void halo_items_kernel(const HaloItem* __restrict__ items, double* __restrict__ buf, int op)
+{
+    const HaloItem it = items[blockIdx.y];
+    const long long e0 = it.ext[0], e01 = (long long)it.ext[0] * it.ext[1];
+    double* b = buf + it.buf_off;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < it.count; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int k = (int)(q / e01);
+        const long long r = q - (long long)k * e01;
+        const int j = (int)(r / e0), i = (int)(r - (long long)j * e0);
+        double* a = it.ptr + ((long long)(it.off[2] + k) * it.n1 + (it.off[1] + j)) * it.pitch + (it.off[0] + i);
+        if (op == 0)
+            b[q] = *a;
+        else if (op == 1)
+            *a = b[q];
+        else
+            *a += b[q];
+    }
+}
+
+cudaError_t launch_halo_items(Launcher& L, const HaloItem* d_items, int n_items, double* buf, int op)
+{
+    if (n_items <= 0) return cudaSuccess;
+    halo_items_kernel<<<dim3(48, (unsigned)n_items), 256, 0, L.stream>>>(d_items, buf, op);
+    L.launches++;
+    return cudaGetLastError();
+}
+
 __global__ void fill_kernel(double* __restrict__ p, size_t n, double v)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;

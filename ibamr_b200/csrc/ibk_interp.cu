@@ -37,6 +37,7 @@ struct InterpArgs
     long long v_cstride, v_istride;
     const uint32_t* src;
     unsigned tma_mask; // bit a set: component a is staged by TMA
+    int part, sel_lo[3], sel_hi[3]; // MarkerView's tile selection
 };
 
 constexpr int INTERP_THREADS = 256;
@@ -58,11 +59,6 @@ __global__ void __launch_bounds__(INTERP_THREADS)
     __shared__ uint64_t bar;
 
     const int tile = blockIdx.x;
-    const int b0 = tp.brick_base + tile * BRICKS_PER_TILE;
-    const int s0 = args.brick_start[b0];
-    const int s1 = args.brick_start[b0 + BRICKS_PER_TILE];
-    if (s0 >= s1) return;
-
     int t[3];
     {
         int r = tile;
@@ -71,6 +67,18 @@ __global__ void __launch_bounds__(INTERP_THREADS)
         t[1] = r % tp.nt[1];
         t[2] = r / tp.nt[1];
     }
+    if (args.part)
+    {
+        bool in = true;
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) in = in && t[d] >= args.sel_lo[d] && t[d] <= args.sel_hi[d];
+        if ((args.part == 1) != in) return;
+    }
+    const int b0 = tp.brick_base + tile * BRICKS_PER_TILE;
+    const int s0 = args.brick_start[b0];
+    const int s1 = args.brick_start[b0 + BRICKS_PER_TILE];
+    if (s0 >= s1) return;
+
     // pp coordinate of the first staged point per dimension
     int sp0[3];
 #pragma unroll
@@ -280,6 +288,12 @@ static cudaError_t launch_interp_t(Launcher& L, const TileParams& tp, const Bins
     args.v_istride = mv.v_istride;
     args.src = mv.src;
     args.tma_mask = 0;
+    args.part = mv.part;
+    for (int d = 0; d < 3; ++d)
+    {
+        args.sel_lo[d] = mv.sel_lo[d];
+        args.sel_hi[d] = mv.sel_hi[d];
+    }
     static const bool no_tma = getenv("IBK_NO_TMA") != nullptr;
     static const bool dbg = getenv("IBK_DEBUG") != nullptr;
     for (int a = 0; a < tp.ncomp; ++a)

@@ -297,10 +297,19 @@ struct HaloPlan
     std::vector<double*> d_face_save; // [patch][axis]: 2 boundary layers of f's axis-normal component
     std::vector<void*> allocs;
 };
+// device copy of the item table of one message (ibk_halo_pack_many / _unpack_many), keyed by its content
+struct ItemTable
+{
+    unsigned long long key = 0;
+    HaloItem* d_items = nullptr;
+    int n = 0;
+    bool disjoint = true; // no two regions of the same array overlap: one launch may add them all
+};
 struct LevelExtra
 {
     HaloPlan halo;
     std::vector<TileParams> tp; // per patch: [u params, f params] interleaved: tp[2*p + which]
+    std::vector<ItemTable> item_tables;
 };
 static std::vector<std::pair<ibk_ctx*, LevelExtra*>> g_extra;
 LevelExtra* extra_of(ibk_ctx* ctx, bool create)
@@ -317,6 +326,8 @@ void extra_drop(ibk_ctx* ctx)
         if (g_extra[i].first == ctx)
         {
             for (void* p : g_extra[i].second->halo.allocs) cudaFree(p);
+            for (ItemTable& t : g_extra[i].second->item_tables)
+                if (t.d_items) cudaFree(t.d_items);
             delete g_extra[i].second;
             g_extra.erase(g_extra.begin() + i);
             return;
@@ -1445,7 +1456,122 @@ extern "C" int ibk_halo_unpack(ibk_ctx* ctx, int which, int patch, int axis, con
                      mode));
     return IBK_OK;
 }
+// One call per message: the items of a neighbour's buffer in order (same kernels as ibk_halo_pack / _unpack; the
+// host side of a many-region exchange then costs one library call instead of one per region).
+static int item_table(ibk_ctx* ctx, int which, int n_items, const int* patch, const int* axis, const int* lower, const int* upper,
+                      const long long* buf_offset, const ItemTable** out)
+{
+    LevelExtra* ex = extra_of(ctx, false);
+    if (!ex) return fail(ctx, IBK_ERR_STATE, "level parameters missing");
+    const int ndim = ctx->lv.ndim;
+    unsigned long long key = 1469598103934665603ull; // FNV-1a over everything that defines the table
+    auto mix = [&](long long v) {
+        for (int b = 0; b < 8; ++b)
+        {
+            key ^= (unsigned long long)((v >> (8 * b)) & 0xff);
+            key *= 1099511628211ull;
+        }
+    };
+    mix(which);
+    mix(n_items);
+    for (int k = 0; k < n_items; ++k)
+    {
+        mix(patch[k]);
+        mix(axis[k]);
+        mix(buf_offset[k]);
+        for (int d = 0; d < ndim; ++d)
+        {
+            mix(lower[(size_t)k * ndim + d]);
+            mix(upper[(size_t)k * ndim + d]);
+        }
+    }
+    for (const ItemTable& t : ex->item_tables)
+        if (t.key == key && t.n == n_items)
+        {
+            *out = &t;
+            return IBK_OK;
+        }
+    std::vector<HaloItem> h(n_items);
+    ItemTable t;
+    t.key = key;
+    t.n = n_items;
+    for (int k = 0; k < n_items; ++k)
+    {
+        int off[3], ext[3];
+        if (int rc = region_args(ctx, which, patch[k], axis[k], lower + (size_t)k * ndim, upper + (size_t)k * ndim, off, ext)) return rc;
+        PatchState& ps = ctx->lv.patches[patch[k]];
+        h[k].ptr = which == 0 ? ps.u[axis[k]] : ps.f[axis[k]];
+        h[k].pitch = ps.pitch[axis[k]];
+        h[k].n1 = ps.n[axis[k]][1];
+        h[k].count = 1;
+        for (int d = 0; d < 3; ++d)
+        {
+            h[k].off[d] = off[d];
+            h[k].ext[d] = ext[d];
+            h[k].count *= ext[d];
+        }
+        h[k].buf_off = buf_offset[k];
+        for (int k2 = 0; k2 < k; ++k2) // do two regions of one array overlap?
+        {
+            if (h[k2].ptr != h[k].ptr) continue;
+            bool ov = true;
+            for (int d = 0; d < 3; ++d) ov = ov && h[k].off[d] < h[k2].off[d] + h[k2].ext[d] && h[k2].off[d] < h[k].off[d] + h[k].ext[d];
+            if (ov) t.disjoint = false;
+        }
+    }
+    if (n_items > 0)
+    {
+        CK(cudaMalloc(&t.d_items, sizeof(HaloItem) * (size_t)n_items));
+        CK(cudaMemcpy(t.d_items, h.data(), sizeof(HaloItem) * (size_t)n_items, cudaMemcpyHostToDevice));
+    }
+    ex->item_tables.push_back(t);
+    *out = &ex->item_tables.back();
+    return IBK_OK;
+}
 
+// One call and (when the regions of an array are disjoint) one launch per message: the items of a neighbour's
+// buffer in order.  The item table is kept on the device, keyed by its content.
+extern "C" int ibk_halo_pack_many(ibk_ctx* ctx, int which, int n_items, const int* patch, const int* axis, const int* lower,
+                                  const int* upper, const long long* buf_offset, double* d_buf)
+{
+    NEED_LEVEL();
+    if (n_items < 0 || (n_items > 0 && (!patch || !axis || !lower || !upper || !buf_offset || !d_buf)))
+        return fail(ctx, IBK_ERR_INVALID, "bad item arrays");
+    if (which < 0 || which > 1) return fail(ctx, IBK_ERR_INVALID, "which must be 0 (u) or 1 (f)");
+    if (n_items == 0) return IBK_OK;
+    GRID_DEPS(which);
+    const ItemTable* t = nullptr;
+    if (int rc = item_table(ctx, which, n_items, patch, axis, lower, upper, buf_offset, &t)) return rc;
+    CK(launch_halo_items(ctx->L, t->d_items, n_items, d_buf, 0));
+    return IBK_OK;
+}
+extern "C" int ibk_halo_unpack_many(ibk_ctx* ctx, int which, int n_items, const int* patch, const int* axis, const int* lower,
+                                    const int* upper, const long long* buf_offset, const double* d_buf, int mode)
+{
+    NEED_LEVEL();
+    if (n_items < 0 || (n_items > 0 && (!patch || !axis || !lower || !upper || !buf_offset || !d_buf)))
+        return fail(ctx, IBK_ERR_INVALID, "bad item arrays");
+    if (which < 0 || which > 1 || mode < 0 || mode > 1) return fail(ctx, IBK_ERR_INVALID, "bad which / mode");
+    if (n_items == 0) return IBK_OK;
+    GRID_DEPS(which);
+    const ItemTable* t = nullptr;
+    if (int rc = item_table(ctx, which, n_items, patch, axis, lower, upper, buf_offset, &t)) return rc;
+    if (t->disjoint)
+    {
+        CK(launch_halo_items(ctx->L, t->d_items, n_items, const_cast<double*>(d_buf), mode == 0 ? 1 : 2));
+        return IBK_OK;
+    }
+    const int ndim = ctx->lv.ndim; // overlapping regions: one launch per item, in order (fixed order of the additions)
+    for (int k = 0; k < n_items; ++k)
+    {
+        int off[3], ext[3];
+        if (int rc = region_args(ctx, which, patch[k], axis[k], lower + (size_t)k * ndim, upper + (size_t)k * ndim, off, ext)) return rc;
+        PatchState& ps = ctx->lv.patches[patch[k]];
+        CK(launch_unpack(ctx->L, which == 0 ? ps.u[axis[k]] : ps.f[axis[k]], ps.pitch[axis[k]], ps.n[axis[k]][1], off, ext,
+                         d_buf + buf_offset[k], ndim, mode));
+    }
+    return IBK_OK;
+}
 // ---------------------------------------------------------------------------------------------
 // spreadForce / interpolateVelocity
 // ---------------------------------------------------------------------------------------------
@@ -1490,7 +1616,7 @@ extern "C" int ibk_spread_end(ibk_ctx* ctx)
     return face_layers(ctx, 1);
 }
 
-static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo)
+static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo, int part = 0)
 {
     NEED_LEVEL();
     GRID_DEPS(op == 1 ? 1 : 0);
@@ -1517,8 +1643,30 @@ static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo)
     mv.v_cstride = lv.stride;
     mv.v_istride = 1;
     mv.src = nullptr;
+    if (part < 0 || part > 2) return fail(ctx, IBK_ERR_INVALID, "part must be 0 (all), 1 (interior tiles) or 2 (boundary tiles)");
+    mv.part = part;
     for (size_t p = 0; p < lv.patches.size(); ++p)
     {
+        if (part)
+        {
+            // Interior tiles: neither the block of the spread (tile -+ M points, + the TMA alignment column) nor the
+            // staged box of the interpolation (tile -+ M + 2) reaches a ghost cell or a boundary face of the patch,
+            // i.e. anything the halo exchange reads or writes.  pp = index - lower + G.
+            const PatchState& ps = lv.patches[p];
+            const int reach = (ibk_get_stencil_size(fcn) + 1) / 2 + 2; // kernel reach M + the spare columns of the TMA boxes
+            for (int d = 0; d < 3; ++d)
+            {
+                if (d >= lv.ndim)
+                {
+                    mv.sel_lo[d] = 0;
+                    mv.sel_hi[d] = 0;
+                    continue;
+                }
+                const int n = ps.upper[d] - ps.lower[d] + 1;
+                mv.sel_lo[d] = (lv.G + reach) / 16 + 1;     // 16 t - reach > G: clear of the low ghosts and the boundary face
+                mv.sel_hi[d] = (lv.G + n - 17 - reach) / 16; // 16 t + 16 + reach <= G + n - 1: clear of the high face and ghosts
+            }
+        }
         std::string err;
         cudaError_t e = (op == 0) ? launch_interp(ctx->L, kernel, ex->tp[2 * p + 0], lv.bins, mv, err) :
                                     launch_spread(ctx->L, kernel, ex->tp[2 * p + 1], lv.bins, mv, err);
@@ -1544,6 +1692,15 @@ extern "C" int ibk_spread_force(ibk_ctx* ctx, const char* spread_fcn, int accumu
 extern "C" int ibk_interpolate_velocity(ibk_ctx* ctx, const char* interp_fcn, int fill_halo)
 {
     return level_op(ctx, 0, interp_fcn, fill_halo);
+}
+
+extern "C" int ibk_spread_force_part(ibk_ctx* ctx, const char* spread_fcn, int part)
+{
+    return level_op(ctx, 1, spread_fcn, 0, part);
+}
+extern "C" int ibk_interpolate_velocity_part(ibk_ctx* ctx, const char* interp_fcn, int part)
+{
+    return level_op(ctx, 0, interp_fcn, 0, part);
 }
 
 extern "C" int ibk_count_touched_dofs(ibk_ctx* ctx, const char* kernel_fcn, long long* touched)

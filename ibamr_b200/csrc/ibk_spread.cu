@@ -72,6 +72,7 @@ struct SpreadArgs
     int exc_capacity;
     int cap; // markers whose stencil weights are staged at a time (sizes the dynamic shared memory)
     unsigned tma_mask; // bit a: the block of component a is loaded / stored by TMA (else zero-fill + red write-out)
+    int part, sel_lo[3], sel_hi[3]; // MarkerView's tile selection
 };
 
 // Brick colouring of a tile, worked out at compile time: the bricks of a tile in colour-major order
@@ -155,6 +156,13 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
         r /= args.ntc[0];
         t[1] = 2 * (r % args.ntc[1]) + args.colour[1];
         if (NDIM == 3) t[2] = 2 * (r / args.ntc[1]) + args.colour[2];
+    }
+    if (args.part)
+    {
+        bool in = true;
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) in = in && t[d] >= args.sel_lo[d] && t[d] <= args.sel_hi[d];
+        if ((args.part == 1) != in) return;
     }
     const int a = blockIdx.y;
     const CompGeom& cg = tp.comp[a];
@@ -538,6 +546,12 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     args.exc_count = g_exc_buf;
     args.exc_list = g_exc_buf + 1;
     args.exc_capacity = EXC_CAPACITY;
+    args.part = mv.part;
+    for (int d = 0; d < 3; ++d)
+    {
+        args.sel_lo[d] = mv.sel_lo[d];
+        args.sel_hi[d] = mv.sel_hi[d];
+    }
     // does this patch hold any marker at all?
     bool any = bins.range_base.empty();
     for (size_t p = 0; p < bins.range_base.size(); ++p)

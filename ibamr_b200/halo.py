@@ -161,18 +161,41 @@ class HaloExchange:
                 continue
             off = 0
             buf = self.buf[(name, src, dst)]
+            if hasattr(self.be, "pack_many"):  # one library call per message
+                self.be.pack_many(which, self._batch(name, src, dst, items, True), buf)
+                continue
             for it in items:
                 self.be.pack(which, it.src.local_id, it.axis, it.src_lo, it.src_hi, self.be.view(buf, off, it.count))
                 off += it.count
 
-    def _exchange(self, name, table):
+    def _batch(self, name, src, dst, items, sending):
+        """The item arrays of one message (built once): local patch, axis, boxes, offsets into the buffer."""
+        key = (name, src, dst, sending)
+        cache = self.__dict__.setdefault("_batches", {})
+        if key not in cache:
+            import numpy as np
+            off, offs = 0, []
+            for it in items:
+                offs.append(off)
+                off += it.count
+            side = (lambda it: (it.src.local_id, it.src_lo, it.src_hi)) if sending else (lambda it: (it.dst.local_id, it.dst_lo, it.dst_hi))
+            cache[key] = (np.array([side(it)[0] for it in items], dtype=np.int32), np.array([it.axis for it in items], dtype=np.int32),
+                          np.ascontiguousarray([side(it)[1] for it in items], dtype=np.int32).reshape(-1),
+                          np.ascontiguousarray([side(it)[2] for it in items], dtype=np.int32).reshape(-1),
+                          np.array(offs, dtype=np.int64))
+        return cache[key]
+
+    def _ops(self, name, table):
         ops = []
         for (src, dst) in sorted(table):
             if src == self.plan.rank:
                 ops.append(self.be.isend(self.buf[(name, src, dst)], dst))
             elif dst == self.plan.rank:
                 ops.append(self.be.irecv(self.buf[(name, src, dst)], src))
-        self.be.run(ops)
+        return ops
+
+    def _exchange(self, name, table):
+        self.be.run(self._ops(name, table))
 
     def _unpack(self, name, table, which, mode):
         for (src, dst), items in sorted(table.items()):  # ascending source rank: fixed add order
@@ -180,6 +203,9 @@ class HaloExchange:
                 continue
             off = 0
             buf = self.buf[(name, src, dst)]
+            if hasattr(self.be, "unpack_many"):
+                self.be.unpack_many(which, self._batch(name, src, dst, items, False), buf, mode)
+                continue
             for it in items:
                 self.be.unpack(which, it.dst.local_id, it.axis, it.dst_lo, it.dst_hi, self.be.view(buf, off, it.count), mode)
                 off += it.count
@@ -196,6 +222,24 @@ class HaloExchange:
 
     def accumulate_end(self):
         self._exchange("accum", self.plan.accum)
+        self._unpack("accum", self.plan.accum, 1, 1)
+
+    # The same two operations split so that the messages are in flight while the caller launches the tiles that
+    # do not touch the exchanged regions (ibk_*_part): post = pack + start the messages, finish = wait + unpack.
+    def fill_post(self):
+        self._pack("fill", self.plan.fill, 0)
+        self._pending_fill = self.be.post(self._ops("fill", self.plan.fill))
+
+    def fill_finish(self):
+        self.be.wait(self._pending_fill)
+        self._unpack("fill", self.plan.fill, 0, 0)
+
+    def accumulate_post(self):
+        self._pack("accum", self.plan.accum, 1)
+        self._pending_accum = self.be.post(self._ops("accum", self.plan.accum))
+
+    def accumulate_finish(self):
+        self.be.wait(self._pending_accum)
         self._unpack("accum", self.plan.accum, 1, 1)
 
 
@@ -244,6 +288,24 @@ class IbkBackend:
         self.ib.migrate_unpack(buf.data_ptr(), n_recv, id_bound)
         self.ib.ctx.synchronize()
 
+    def pack_many(self, which, batch, buf):
+        C = self.C
+        patch, axis, lo, hi, offs = batch
+        ctx = self.ib.ctx
+        pi = C.POINTER(C.c_int)
+        ctx.check(ctx.lib.ibk_halo_pack_many(ctx.h, which, len(patch), patch.ctypes.data_as(pi), axis.ctypes.data_as(pi),
+                                             lo.ctypes.data_as(pi), hi.ctypes.data_as(pi),
+                                             offs.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_void_p(buf.data_ptr())))
+
+    def unpack_many(self, which, batch, buf, mode):
+        C = self.C
+        patch, axis, lo, hi, offs = batch
+        ctx = self.ib.ctx
+        pi = C.POINTER(C.c_int)
+        ctx.check(ctx.lib.ibk_halo_unpack_many(ctx.h, which, len(patch), patch.ctypes.data_as(pi), axis.ctypes.data_as(pi),
+                                               lo.ctypes.data_as(pi), hi.ctypes.data_as(pi),
+                                               offs.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_void_p(buf.data_ptr()), mode))
+
     def isend(self, buf, dst):
         return self.dist.P2POp(self.dist.isend, buf, dst)
 
@@ -254,6 +316,14 @@ class IbkBackend:
         if ops:
             for r in self.dist.batch_isend_irecv(ops):
                 r.wait()
+
+    def post(self, ops):
+        """Starts the messages (NCCL: on its own stream, after the work already queued on the current one)."""
+        return self.dist.batch_isend_irecv(ops) if ops else []
+
+    def wait(self, reqs):
+        for r in reqs:
+            r.wait()  # NCCL: the current stream waits, the host does not
 
 
 class MarkerMigration:

@@ -399,6 +399,16 @@ int ibk_spread_end(ibk_ctx* ctx);
  * (IBMethod.cpp:672-694): (fill_halo != 0) ghost fill of u among this process's patches incl.
  * periodic wrap (replaces u_ghost_fill_scheds[ln]->fillData, :744), then U = J[u]. */
 int ibk_interpolate_velocity(ibk_ctx* ctx, const char* interp_fcn, int fill_halo);
+/* The same operations restricted to a part of the marker tiles, without any halo handling: part 1 = the tiles that
+ * touch neither ghost cells nor the layers next to a patch boundary (nothing an exchange reads or writes), part 2 =
+ * the others, part 0 = all.  They let the inter-process exchange overlap the bulk of the work
+ * (ibamr_b200/halo.py::HaloExchange.*_post / *_finish, bench.py):
+ *   spread:  ibk_spread_begin; part 2; ibk_halo_pack ...; post the exchange; part 1; ibk_halo_local(f);
+ *            complete the exchange; ibk_halo_unpack(add) ...; ibk_spread_end
+ *   interp:  ibk_halo_pack ...; post the exchange; ibk_halo_local(u); part 1; complete the exchange;
+ *            ibk_halo_unpack(copy) ...; part 2 */
+int ibk_spread_force_part(ibk_ctx* ctx, const char* spread_fcn, int part);
+int ibk_interpolate_velocity_part(ibk_ctx* ctx, const char* interp_fcn, int part);
 
 /* Halo ops on their own (device pack/unpack around an external exchange; multi-process runs
  * move the packed buffers with NCCL, see ibamr_b200/halo.py).  which: 0 = u (copy), 1 = f (add). */
@@ -408,6 +418,11 @@ int ibk_halo_local(ibk_ctx* ctx, int which);
 int ibk_halo_pack(ibk_ctx* ctx, int which, int patch, int axis, const int* lower, const int* upper, double* d_buf);
 int ibk_halo_unpack(ibk_ctx* ctx, int which, int patch, int axis, const int* lower, const int* upper,
                     const double* d_buf, int mode);
+/* All regions of one neighbour's message in one call (items in buffer order; buf_offset[k] in doubles). */
+int ibk_halo_pack_many(ibk_ctx* ctx, int which, int n_items, const int* patch, const int* axis, const int* lower, const int* upper,
+                       const long long* buf_offset, double* d_buf);
+int ibk_halo_unpack_many(ibk_ctx* ctx, int which, int n_items, const int* patch, const int* axis, const int* lower,
+                         const int* upper, const long long* buf_offset, const double* d_buf, int mode);
 
 /* Device pointers for zero-copy callers (torch tensors, NCCL): SoA marker columns in SORTED
  * order ([ndim][capacity] with the given stride) and pitched grid arrays. */

@@ -37,13 +37,14 @@ def periodic_side_field(pg, axis, ncell, seed):
 
 def main():
     kernel = sys.argv[1] if len(sys.argv) > 1 else "IB_4"
-    migrate = len(sys.argv) > 2 and sys.argv[2] == "migrate"
+    migrate = "migrate" in sys.argv[2:]
+    overlap = "overlap" in sys.argv[2:]
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = api.Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    n = 32
+    n = 64 if overlap else 32  # with 64 cells per rank there are interior tiles
     pgrid = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
     patches = halo.cartesian_patches(3, pgrid, (n, n, n))
     dom = tuple(n * pgrid[d] for d in range(3))
@@ -90,17 +91,32 @@ def main():
         ib.setPositions(X[mine])
         ib.setLData("F", F[mine])
         ib.beginDataRedistribution()
-    # spreadForce with the inter-rank exchange interleaved (see include/ibk.h, ibk_spread_begin)
-    ctx.check(ctx.lib.ibk_spread_begin(ctx.h))
-    ib.spreadForce(accumulate_halo=False)
-    hx.accumulate_begin()
-    ib.halo("f")
-    hx.accumulate_end()
-    ctx.check(ctx.lib.ibk_spread_end(ctx.h))
-    # interpolateVelocity with the inter-rank ghost fill
-    ib.halo("u")
-    hx.fill()
-    ib.interpolateVelocity(fill_halo=False)
+    if overlap:
+        # the exchange in flight while the interior tiles are processed (ibk_*_part, HaloExchange.*_post/_finish)
+        ctx.check(ctx.lib.ibk_spread_begin(ctx.h))
+        ib.spreadForcePart(2)
+        hx.accumulate_post()
+        ib.spreadForcePart(1)
+        ib.halo("f")
+        hx.accumulate_finish()
+        ctx.check(ctx.lib.ibk_spread_end(ctx.h))
+        hx.fill_post()
+        ib.halo("u")
+        ib.interpolateVelocityPart(1)
+        hx.fill_finish()
+        ib.interpolateVelocityPart(2)
+    else:
+        # spreadForce with the inter-rank exchange interleaved (see include/ibk.h, ibk_spread_begin)
+        ctx.check(ctx.lib.ibk_spread_begin(ctx.h))
+        ib.spreadForce(accumulate_halo=False)
+        hx.accumulate_begin()
+        ib.halo("f")
+        hx.accumulate_end()
+        ctx.check(ctx.lib.ibk_spread_end(ctx.h))
+        # interpolateVelocity with the inter-rank ghost fill
+        ib.halo("u")
+        hx.fill()
+        ib.interpolateVelocity(fill_halo=False)
     U = ib.getLData("U")
     f = [ib.grid_download("f", 0, a) for a in range(3)]
 
@@ -119,7 +135,7 @@ def main():
     t = torch.tensor([err_u, err_f], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"MGPU_PARITY kernel={kernel} world={world} migrate={int(migrate)} interp_rel_err={t[0].item():.3e} spread_rel_err={t[1].item():.3e} "
+        print(f"MGPU_PARITY kernel={kernel} world={world} migrate={int(migrate)} overlap={int(overlap)} interp_rel_err={t[0].item():.3e} spread_rel_err={t[1].item():.3e} "
               f"fill_bytes={plan.bytes_per_exchange(plan.fill)} accum_bytes={plan.bytes_per_exchange(plan.accum)}", flush=True)
         assert t[0].item() <= 1e-12 and t[1].item() <= 1e-12
     ib.close()

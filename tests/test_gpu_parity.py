@@ -482,6 +482,56 @@ def test_spread_is_bit_reproducible(api):
         assert np.array_equal(runs[0][a], runs[2][a])
 
 
+@pytest.mark.parametrize("kernel", ["IB_4", "IB_6", "PIECEWISE_LINEAR"])
+def test_interior_plus_boundary_tiles_equal_the_whole(api, kernel):
+    """ibk_spread_force_part / ibk_interpolate_velocity_part: parts 1 and 2 partition the marker tiles (both
+    non-empty here), interior tiles touch neither ghost cells nor boundary faces."""
+    ndim, n = 3, 96
+    level = _level_case(ndim, n, (1, 1, 1), kernel)
+    g = level.gcw[0]
+    N = 120000
+    X = np.stack([_uniform(301 + d, N, 0.0, 1.0) for d in range(3)], axis=1)
+    F = np.stack([_uniform(311 + d, N, -1.0, 1.0) for d in range(3)], axis=1)
+    ib = api.IBMethodB200(3, (0,) * 3, (n - 1,) * 3, (0.0,) * 3, (1.0,) * 3, (1,) * 3, level.boxes, kernel_fcn=kernel)
+    pg = level.patch_geom(0)
+    u = _periodic_side_fields(pg, 700)
+    for a in range(3):
+        ib.grid_upload("u", 0, a, u[a])
+    ib.setPositions(X)
+    ib.setLData("F", F)
+    ib.beginDataRedistribution()
+    # reference: the whole operation without halo handling
+    ib.grid_fill("f", 0.0)
+    ib.spreadForce(accumulate_halo=False)
+    f_all = [ib.grid_download("f", 0, a) for a in range(3)]
+    ib.interpolateVelocity(fill_halo=False)
+    U_all = ib.getLData("U")
+    # interior tiles only: nothing lands in a ghost cell or on a boundary face, and something is spread
+    ib.grid_fill("f", 0.0)
+    ib.spreadForcePart(1)
+    f_int = [ib.grid_download("f", 0, a) for a in range(3)]
+    for a in range(3):
+        inner = tuple(slice(g + 1, s - g - 1) for s in f_int[a].shape)
+        outer = f_int[a].copy()
+        outer[inner] = 0.0
+        assert np.all(outer == 0.0) and np.any(f_int[a] != 0.0)
+    ib.spreadForcePart(2)
+    f_sum = [ib.grid_download("f", 0, a) for a in range(3)]
+    for a in range(3):
+        assert np.any(f_sum[a] != f_int[a])
+        assert np.max(np.abs(f_sum[a] - f_all[a])) <= 1e-13 * np.max(np.abs(f_all[a]))
+    ib.setLData("U", np.full((N, 3), 7.0))
+    ib.interpolateVelocityPart(1)
+    U1 = ib.getLData("U")
+    ib.interpolateVelocityPart(2)
+    U2 = ib.getLData("U")
+    touched1 = np.any(U1 != 7.0, axis=1)
+    assert 0 < touched1.sum() < N
+    assert np.array_equal(U2, U_all)
+    assert np.array_equal(U1[touched1], U_all[touched1])
+    ib.close()
+
+
 def test_marker_migration_between_two_contexts(api):
     """ibk_markers_set_ids / ibk_migrate_plan / _pack / _unpack with two contexts on one device standing for two
     ranks (the all-to-all is a pair of device copies): afterwards each side holds exactly the markers whose cell
@@ -659,3 +709,9 @@ def test_multi_gpu_parity_two_ranks():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MGPU_PARITY" in r.stdout and "migrate=1" in r.stdout
+    # the exchange overlapped with the interior tiles (ibk_*_part)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29519", os.path.join(root, "tests", "mgpu_worker.py"), "IB_4", "overlap"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MGPU_PARITY" in r.stdout and "overlap=1" in r.stdout
