@@ -271,6 +271,40 @@ def run_gpu(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    if os.environ.get("IBK_BENCH_PHASES") and hx is not None:
+        # all ranks run the instrumented step (the exchange is collective); rank 0 prints
+        lib, hnd = ctx.lib, ctx.h
+        seq = [("spread_begin", lambda: ctx.check(lib.ibk_spread_begin(hnd))), ("spread boundary tiles", lambda: ib.spreadForcePart(2)),
+               ("accumulate_post (pack+send)", hx.accumulate_post), ("spread interior tiles", lambda: ib.spreadForcePart(1)),
+               ("halo_local f", lambda: ib.halo("f")), ("accumulate_finish (wait+unpack)", hx.accumulate_finish),
+               ("spread_end", lambda: ctx.check(lib.ibk_spread_end(hnd))), ("fill_post (pack+send)", hx.fill_post),
+               ("halo_local u", lambda: ib.halo("u")), ("interp interior tiles", lambda: ib.interpolateVelocityPart(1)),
+               ("fill_finish (wait+unpack)", hx.fill_finish), ("interp boundary tiles", lambda: ib.interpolateVelocityPart(2))]
+        for rep in range(2):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(seq) + 1)]
+            evs[0].record(stream)
+            for k, (_, fn) in enumerate(seq):
+                fn()
+                evs[k + 1].record(stream)
+            torch.cuda.synchronize()
+            if rank == 0 and rep == 1:
+                for k, (name, _) in enumerate(seq):
+                    print(f"[phases] {name:34s} {evs[k].elapsed_time(evs[k + 1]):7.3f} ms", file=sys.stderr)
+                print(f"[phases] total {evs[0].elapsed_time(evs[-1]):7.3f} ms", file=sys.stderr)
+        # the bare exchanges, nothing overlapped
+        for name, post, fin in (("fill", hx.fill_post, hx.fill_finish), ("accumulate", hx.accumulate_post, hx.accumulate_finish)):
+            for rep in range(3):
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                barrier()
+                e0.record(stream)
+                post()
+                e1.record(stream)
+                fin()
+                e2.record(stream)
+                torch.cuda.synchronize()
+            if rank == 0:
+                print(f"[phases] bare {name}: post {e0.elapsed_time(e1):.3f} ms, finish {e1.elapsed_time(e2):.3f} ms", file=sys.stderr)
+        barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -101,7 +101,7 @@ struct HaloItem
     long long count;
 };
 // op 0: buffer <- regions (pack); 1: regions <- buffer (copy); 2: regions += buffer
-cudaError_t launch_halo_items(Launcher& L, const HaloItem* d_items, int n_items, double* buf, int op);
+cudaError_t launch_halo_items(Launcher& L, const HaloItem* d_items, int n_items, long long max_count, double* buf, int op);
 
 // ibk_force.cu
 // Force elements by Lagrangian index plus, per node, the elements it takes part in (CSR), all on the device.

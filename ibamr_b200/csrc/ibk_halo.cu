@@ -158,10 +158,12 @@ __global__ void halo_items_kernel(const HaloItem* __restrict__ items, double* __
     }
 }
 
-cudaError_t launch_halo_items(Launcher& L, const HaloItem* d_items, int n_items, double* buf, int op)
+cudaError_t launch_halo_items(Launcher& L, const HaloItem* d_items, int n_items, long long max_count, double* buf, int op)
 {
     if (n_items <= 0) return cudaSuccess;
-    halo_items_kernel<<<dim3(48, (unsigned)n_items), 256, 0, L.stream>>>(d_items, buf, op);
+    // grid.x follows the largest region (4 elements per thread); the blocks beyond a small region's end leave at once
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(1024, (max_count + 1023) / 1024));
+    halo_items_kernel<<<dim3(gx, (unsigned)n_items), 256, 0, L.stream>>>(d_items, buf, op);
     L.launches++;
     return cudaGetLastError();
 }

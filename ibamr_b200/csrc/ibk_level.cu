@@ -304,6 +304,7 @@ struct ItemTable
     HaloItem* d_items = nullptr;
     int n = 0;
     bool disjoint = true; // no two regions of the same array overlap: one launch may add them all
+    long long max_count = 0;
 };
 struct LevelExtra
 {
@@ -1511,6 +1512,7 @@ static int item_table(ibk_ctx* ctx, int which, int n_items, const int* patch, co
             h[k].count *= ext[d];
         }
         h[k].buf_off = buf_offset[k];
+        t.max_count = std::max(t.max_count, h[k].count);
         for (int k2 = 0; k2 < k; ++k2) // do two regions of one array overlap?
         {
             if (h[k2].ptr != h[k].ptr) continue;
@@ -1542,7 +1544,7 @@ extern "C" int ibk_halo_pack_many(ibk_ctx* ctx, int which, int n_items, const in
     GRID_DEPS(which);
     const ItemTable* t = nullptr;
     if (int rc = item_table(ctx, which, n_items, patch, axis, lower, upper, buf_offset, &t)) return rc;
-    CK(launch_halo_items(ctx->L, t->d_items, n_items, d_buf, 0));
+    CK(launch_halo_items(ctx->L, t->d_items, n_items, t->max_count, d_buf, 0));
     return IBK_OK;
 }
 extern "C" int ibk_halo_unpack_many(ibk_ctx* ctx, int which, int n_items, const int* patch, const int* axis, const int* lower,
@@ -1558,7 +1560,7 @@ extern "C" int ibk_halo_unpack_many(ibk_ctx* ctx, int which, int n_items, const 
     if (int rc = item_table(ctx, which, n_items, patch, axis, lower, upper, buf_offset, &t)) return rc;
     if (t->disjoint)
     {
-        CK(launch_halo_items(ctx->L, t->d_items, n_items, const_cast<double*>(d_buf), mode == 0 ? 1 : 2));
+        CK(launch_halo_items(ctx->L, t->d_items, n_items, t->max_count, const_cast<double*>(d_buf), mode == 0 ? 1 : 2));
         return IBK_OK;
     }
     const int ndim = ctx->lv.ndim; // overlapping regions: one launch per item, in order (fixed order of the additions)
