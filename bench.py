@@ -160,7 +160,7 @@ def workload_config(n_gpus, args):
     pg = process_grid(n_gpus)
     n = args.cells
     return {"workload": f"C5 shard (weak scaling): per GPU one {n}^3 patch of a periodic staggered grid + 2^{args.log2_markers} "
-                        f"uniform markers, IB_4, fp64; process grid {pg[0]}x{pg[1]}x{pg[2]} "
+                        f"{args.markers} markers, IB_4, fp64; process grid {pg[0]}x{pg[1]}x{pg[2]} "
                         f"(global {n * pg[0]}x{n * pg[1]}x{n * pg[2]}, {n_gpus * (1 << args.log2_markers)} markers)",
             "kernel": KERNEL, "cells_per_gpu": [n, n, n], "markers_per_gpu": 1 << args.log2_markers,
             "step": "spreadForce (ghost zero + spread + halo accumulate) + interpolateVelocity (halo fill + interp), markers pre-binned",
@@ -205,6 +205,15 @@ def run_gpu(args):
     h = 1.0 / n
     idx = np.arange(N, dtype=np.uint64) + np.uint64(rank) * np.uint64(N)
     X = np.stack([(me.lower[d] + n * splitmix_unit(7 + d, idx)) * h for d in range(3)], axis=1)
+    if args.markers == "shell":
+        # diagnostic workload (BASELINE config C2's shape): a Fibonacci-lattice sphere of radius n/4 cells in the
+        # middle of the rank's patch: a dense surface (tens of markers per cell) instead of uniform markers
+        k = np.arange(N, dtype=np.float64) + 0.5
+        phi = np.arccos(1.0 - 2.0 * k / N)
+        th = np.pi * (1.0 + 5.0 ** 0.5) * k
+        c = [(me.lower[d] + 0.5 * n) * h for d in range(3)]
+        R = 0.25 * n * h
+        X = np.stack([c[0] + R * np.cos(th) * np.sin(phi), c[1] + R * np.sin(th) * np.sin(phi), c[2] + R * np.cos(phi)], axis=1)
     F = np.stack([2.0 * splitmix_unit(1 + d, idx) - 1.0 for d in range(3)], axis=1)
     # pinned host buffers for the e2e leg
     hX = torch.from_numpy(X).pin_memory()
@@ -448,6 +457,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=512, help="cells per dimension per GPU")
     ap.add_argument("--log2-markers", type=int, default=23, help="log2 of the markers per GPU")
+    ap.add_argument("--markers", default="uniform", choices=["uniform", "shell"],
+                    help="marker distribution: uniform (the benchmark) or a dense spherical shell (diagnostic)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-breakdown", action="store_true", help="print the e2e phases, each synchronised, to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -144,6 +144,19 @@ __global__ void bin_keys_kernel(BinParams bp,
     if (owner_out) owner_out[i] = owner;
 }
 
+// ids of the bricks with more than `thresh` markers, appended in no particular order
+__global__ void dense_bricks_kernel(const int* __restrict__ brick_start, int total_bricks, int thresh, int* __restrict__ list,
+                                    int capacity, int* __restrict__ count)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total_bricks) return;
+    if (brick_start[b + 1] - brick_start[b] > thresh)
+    {
+        const int pos = atomicAdd(count, 1);
+        if (pos < capacity) list[pos] = b;
+    }
+}
+
 // brick_start[b] = first sorted position whose brick id is >= b; brick_start[total] = n_active.
 __global__ void brick_offsets_kernel(const uint64_t* __restrict__ keys, int n, int shift, int total_bricks,
                                      int* __restrict__ brick_start)
@@ -238,6 +251,8 @@ void bins_free(Bins& b)
     }
     if (b.sort_temp) cudaFree(b.sort_temp);
     if (b.brick_start) cudaFree(b.brick_start);
+    if (b.dense_list) cudaFree(b.dense_list);
+    if (b.dense_count) cudaFree(b.dense_count);
     b = Bins();
 }
 
@@ -276,6 +291,22 @@ cudaError_t bins_build(Bins& b, Launcher& L, const CellGeom& cg, const PatchBin*
                                                                          total_bricks, b.brick_start);
     L.launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // dense bricks: at most n / (thresh + 1) of them
+    {
+        const int cap = n_entries / (DENSE_BRICK_MARKERS + 1) + 1;
+        if (cap > b.dense_capacity)
+        {
+            if (b.dense_list) cudaFree(b.dense_list);
+            if ((e = cudaMalloc(&b.dense_list, sizeof(int) * (size_t)cap)) != cudaSuccess) return e;
+            b.dense_capacity = cap;
+        }
+        if (!b.dense_count && (e = cudaMalloc(&b.dense_count, sizeof(int))) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(b.dense_count, 0, sizeof(int), L.stream)) != cudaSuccess) return e;
+        dense_bricks_kernel<<<(total_bricks + T - 1) / T, T, 0, L.stream>>>(b.brick_start, total_bricks, DENSE_BRICK_MARKERS, b.dense_list,
+                                                                           b.dense_capacity, b.dense_count);
+        L.launches++;
+        if ((e = cudaMemcpyAsync(&b.n_dense, b.dense_count, sizeof(int), cudaMemcpyDeviceToHost, L.stream)) != cudaSuccess) return e;
+    }
     // marker range of every patch (its bricks are one contiguous id range)
     b.range_base.assign(n_patches, 0);
     b.range_first.assign(n_patches, 0);

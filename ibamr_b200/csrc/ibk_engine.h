@@ -61,7 +61,14 @@ struct Bins
     // per patch (keyed by its first brick id): sorted positions [first, last) of its markers, read
     // back once per binning so that launches need no device->host round trip
     std::vector<int> range_base, range_first, range_last;
+    // bricks holding more than DENSE_BRICK_MARKERS markers (structures: tens of markers per cell), in no particular
+    // order; the spread gives them a kernel of their own (ibk_spread.cu, spread_dense_kernel)
+    int* dense_list = nullptr; // [dense_capacity] brick ids
+    int* dense_count = nullptr; // device counter
+    int dense_capacity = 0;
+    int n_dense = 0;
 };
+constexpr int DENSE_BRICK_MARKERS = 48;
 
 struct Launcher
 {

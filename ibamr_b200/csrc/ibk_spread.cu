@@ -73,6 +73,7 @@ struct SpreadArgs
     int cap; // markers whose stencil weights are staged at a time (sizes the dynamic shared memory)
     unsigned tma_mask; // bit a: the block of component a is loaded / stored by TMA (else zero-fill + red write-out)
     int part, sel_lo[3], sel_hi[3]; // MarkerView's tile selection
+    int dense_thresh;               // > 0: bricks with more markers than this are left to spread_dense_kernel
 };
 
 // Brick colouring of a tile, worked out at compile time: the bricks of a tile in colour-major order
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
         const int s = sbs[my_q], e = sbs[my_q + 1];
         bfirst[threadIdx.x] = s;
         my_cnt = e - s;
+        if (args.dense_thresh > 0 && my_cnt > args.dense_thresh) my_cnt = 0; // a dense brick: spread_dense_kernel's
     }
     if (warp < 2)
     {
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     }
     __syncthreads();
     TL(3);
-    const int total = s1 - s0;
+    const int total = bpre[NBRICKS]; // without the dense bricks
 
     // stencil-evaluation tasks of this thread for a window: the global loads are issued by fetch() -- for window
     // w + 1 before the accumulation of window w starts, so their latency hides behind it -- and consumed by
@@ -459,6 +461,154 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dense bricks (3D, kernels with M = 2).  A structure puts tens of markers into a cell, hundreds into a brick; the
+// tile kernel would walk them with ONE warp (a brick is the unit of its colouring).  Here a CTA takes one dense
+// brick and one component: every warp holds the brick's whole footprint ((4 + 2M)^3 = 8^3 points) in registers,
+// 16 points per lane, and adds every 8th batch of the brick's markers into it with zero-padded 1-D weight
+// vectors -- branch-free, no shared-memory read-modify-write, no conflicts.  The eight partial footprints are then
+// summed in a fixed tree and added to f.  Bricks NC apart have disjoint footprints: NC^3 launches (colours).
+// Order of the additions: fixed by (batch order within a warp, tree over the warps, brick colour): reproducible.
+// ---------------------------------------------------------------------------------------------
+constexpr int DENSE_BATCH = 10; // markers per warp and stencil-evaluation round: 3 * 10 lanes busy
+
+template <int K>
+__global__ void __launch_bounds__(256)
+    spread_dense_kernel(const __grid_constant__ TileParams tp, SpreadArgs args, const int* __restrict__ dense_list, int c0, int c1,
+                        int c2)
+{
+    constexpr int W = KTraits<K>::W;
+    constexpr int M = KTraits<K>::M;
+    static_assert(M == 2, "the register footprint is laid out for 8^3 points");
+    constexpr int FP = BRICK + 2 * M; // 8
+    constexpr int NC = (BRICK + 2 * M + BRICK - 1) / BRICK;
+    __shared__ double wpad[8][DENSE_BATCH][3][FP]; // zero-padded 1-D weights over the footprint, per warp
+    __shared__ double red[4][FP * FP * FP];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = __ldg(&dense_list[blockIdx.x]);
+    const int relb = b - tp.brick_base;
+    const int nbricks = tp.nt[0] * tp.nt[1] * tp.nt[2] * 64;
+    if (relb < 0 || relb >= nbricks) return; // another patch's brick
+    int gb[3];
+    {
+        int tile = relb >> 6;
+        const int q = relb & 63;
+        const int t0 = tile % tp.nt[0];
+        tile /= tp.nt[0];
+        gb[0] = 4 * t0 + (q & 3);
+        gb[1] = 4 * (tile % tp.nt[1]) + ((q >> 2) & 3);
+        gb[2] = 4 * (tile / tp.nt[1]) + (q >> 4);
+    }
+    if (gb[0] % NC != c0 || gb[1] % NC != c1 || gb[2] % NC != c2) return; // another colour's brick
+    const int a = blockIdx.y;
+    const CompGeom& cg = tp.comp[a];
+    const int s = __ldg(&args.brick_start[b]), e = __ldg(&args.brick_start[b + 1]);
+    int fo[3]; // pp coordinate of the footprint's first point
+#pragma unroll
+    for (int d = 0; d < 3; ++d) fo[d] = BRICK * gb[d] - M;
+
+    const int x = lane & 7, y0 = lane >> 3, y1 = y0 + 4;
+    double acc0[FP], acc1[FP];
+#pragma unroll
+    for (int z = 0; z < FP; ++z) acc0[z] = acc1[z] = 0.0;
+
+    for (int first = s + warp * DENSE_BATCH; first < e; first += 8 * DENSE_BATCH)
+    {
+        const int nb = min(DENSE_BATCH, e - first);
+        if (lane < nb * 3)
+        {
+            const int m = lane / 3, d = lane - 3 * m;
+            const int i = first + m;
+            const double xs = __ldg(&args.X[d * args.x_stride + i]);
+            const double xr = args.Xraw ? __ldg(&args.Xraw[d * args.x_stride + i]) : xs;
+            double w[W];
+            int l;
+            stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w);
+            const int r0 = l + tp.G - fo[d];
+            const bool fits = r0 >= 0 && r0 + W <= FP;
+            double scale = 1.0;
+            if (d == 2)
+            {
+                const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
+                scale = __ldg(&args.V[cg.vcol * args.v_cstride + row * args.v_istride]) * tp.inv_vol;
+            }
+            double* wp = wpad[warp][m][d];
+#pragma unroll
+            for (int z = 0; z < FP; ++z) wp[z] = 0.0;
+            if (fits)
+            {
+#pragma unroll
+                for (int j = 0; j < W; ++j) wp[r0 + j] = w[j] * scale;
+            }
+            else if (args.exc_list) // the whole (marker, component) goes to the fix-up; a zero factor removes it here
+            {
+                const int slot = atomicAdd(args.exc_count, 1);
+                if (slot < args.exc_capacity) args.exc_list[slot] = i * 8 + a;
+            }
+        }
+        __syncwarp();
+        for (int m = 0; m < nb; ++m)
+        {
+            const double* wp = &wpad[warp][m][0][0];
+            const double wx = wp[x];
+            const double p0 = wx * wp[FP + y0], p1 = wx * wp[FP + y1];
+#pragma unroll
+            for (int z = 0; z < FP; ++z)
+            {
+                const double wz = wp[2 * FP + z];
+                acc0[z] += p0 * wz;
+                acc1[z] += p1 * wz;
+            }
+        }
+        __syncwarp();
+    }
+
+    // fixed reduction tree over the warps: (w, w + 4), (w, w + 2), (0, 1); point (x, y, z) at (z * 8 + y) * 8 + x
+    auto put = [&](double* dst) {
+#pragma unroll
+        for (int z = 0; z < FP; ++z)
+        {
+            dst[(z * FP + y0) * FP + x] = acc0[z];
+            dst[(z * FP + y1) * FP + x] = acc1[z];
+        }
+    };
+    auto take = [&](const double* src) {
+#pragma unroll
+        for (int z = 0; z < FP; ++z)
+        {
+            acc0[z] += src[(z * FP + y0) * FP + x];
+            acc1[z] += src[(z * FP + y1) * FP + x];
+        }
+    };
+    if (warp >= 4) put(red[warp - 4]);
+    __syncthreads();
+    if (warp < 4) take(red[warp]);
+    __syncthreads();
+    if (warp == 2 || warp == 3) put(red[warp - 2]);
+    __syncthreads();
+    if (warp < 2) take(red[warp]);
+    __syncthreads();
+    if (warp == 1) put(red[0]);
+    __syncthreads();
+    if (warp == 0)
+    {
+        take(red[0]);
+        put(red[1]);
+    }
+    __syncthreads();
+    // f += footprint, dropping the points outside the array (same-colour bricks are disjoint: plain read-modify-write)
+    for (int pt = threadIdx.x; pt < FP * FP * FP; pt += 256)
+    {
+        const double v = red[1][pt];
+        if (v == 0.0) continue;
+        const int px = pt & 7, py = (pt >> 3) & 7, pz = pt >> 6;
+        const int gi = fo[0] + px - cg.pp0[0], gj = fo[1] + py - cg.pp0[1], gk = fo[2] + pz - cg.pp0[2];
+        if (gi < 0 || gi >= cg.n[0] || gj < 0 || gj >= cg.n[1] || gk < 0 || gk >= cg.n[2]) continue;
+        cg.ptr[((long long)gk * cg.n[1] + gj) * cg.pitch + gi] += v;
+    }
+}
+
 // Fix-up for the (practically never occurring) (marker, component) pairs whose stencil does not fit the
 // haloed block of their tile: one thread, sorted order, the whole stencil, clipped to the array only.
 template <int NDIM, int K>
@@ -587,6 +737,25 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     {
         err = "cudaFuncSetAttribute(spread) failed";
         return e;
+    }
+    // dense bricks first (their own kernel), then the tiles without them
+    args.dense_thresh = 0;
+    if constexpr (NDIM == 3 && M == 2)
+    {
+        static const bool no_dense = getenv("IBK_NO_DENSE") != nullptr;
+        if (bins.n_dense > 0 && !no_dense && mv.part != 1) // (with a tile selection the dense bricks go with the boundary part)
+        {
+            args.dense_thresh = DENSE_BRICK_MARKERS;
+            constexpr int NCB = (BRICK + 2 * M + BRICK - 1) / BRICK;
+            for (int c = 0; c < NCB * NCB * NCB; ++c)
+            {
+                spread_dense_kernel<K><<<dim3((unsigned)bins.n_dense, (unsigned)tp.ncomp), 256, 0, L.stream>>>(
+                    tp, args, bins.dense_list, c % NCB, (c / NCB) % NCB, c / (NCB * NCB));
+                L.launches++;
+            }
+        }
+        else if (bins.n_dense > 0 && !no_dense)
+            args.dense_thresh = DENSE_BRICK_MARKERS; // part 1: the dense bricks are (were) done with part 2 / 0
     }
     // 2^ndim tile colours, one launch each (same-colour blocks are disjoint)
     const int ncol = (NDIM == 3) ? 8 : 4;
