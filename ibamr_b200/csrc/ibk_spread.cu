@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
 constexpr int DENSE_BATCH = 10; // markers per warp and stencil-evaluation round: 3 * 10 lanes busy
 
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     spread_dense_kernel(const __grid_constant__ TileParams tp, SpreadArgs args, const int* __restrict__ dense_list, int c0, int c1,
                         int c2)
 {
@@ -513,26 +513,38 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int z = 0; z < FP; ++z) acc0[z] = acc1[z] = 0.0;
 
+    // the lane's stencil task (marker m of the batch, dimension d); its loads run one batch ahead
+    const int tm = lane / 3, td = lane - 3 * tm;
+    double nxs = 0.0, nxr = 0.0, nv = 1.0;
+    auto fetch = [&](int first) {
+        const int i = first + tm;
+        if (lane < 3 * DENSE_BATCH && i < e)
+        {
+            nxs = __ldg(&args.X[td * args.x_stride + i]);
+            nxr = args.Xraw ? __ldg(&args.Xraw[td * args.x_stride + i]) : nxs;
+            if (td == 2)
+            {
+                const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
+                nv = __ldg(&args.V[cg.vcol * args.v_cstride + row * args.v_istride]);
+            }
+        }
+    };
+    fetch(s + warp * DENSE_BATCH);
     for (int first = s + warp * DENSE_BATCH; first < e; first += 8 * DENSE_BATCH)
     {
         const int nb = min(DENSE_BATCH, e - first);
+        const double xs = nxs, xr = nxr, fv = nv;
+        fetch(first + 8 * DENSE_BATCH);
         if (lane < nb * 3)
         {
-            const int m = lane / 3, d = lane - 3 * m;
+            const int m = tm, d = td;
             const int i = first + m;
-            const double xs = __ldg(&args.X[d * args.x_stride + i]);
-            const double xr = args.Xraw ? __ldg(&args.Xraw[d * args.x_stride + i]) : xs;
             double w[W];
             int l;
             stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w);
             const int r0 = l + tp.G - fo[d];
             const bool fits = r0 >= 0 && r0 + W <= FP;
-            double scale = 1.0;
-            if (d == 2)
-            {
-                const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
-                scale = __ldg(&args.V[cg.vcol * args.v_cstride + row * args.v_istride]) * tp.inv_vol;
-            }
+            const double scale = (d == 2) ? fv * tp.inv_vol : 1.0;
             double* wp = wpad[warp][m][d];
 #pragma unroll
             for (int z = 0; z < FP; ++z) wp[z] = 0.0;
