@@ -462,10 +462,10 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Dense bricks (3D, kernels with M = 2).  A structure puts tens of markers into a cell, hundreds into a brick; the
+// Dense bricks (3D).  A structure puts tens of markers into a cell, hundreds into a brick; the
 // tile kernel would walk them with ONE warp (a brick is the unit of its colouring).  Here a CTA takes one dense
-// brick and one component: every warp holds the brick's whole footprint ((4 + 2M)^3 = 8^3 points) in registers,
-// 16 points per lane, and adds every 8th batch of the brick's markers into it with zero-padded 1-D weight
+// brick and one component: every warp holds the brick's footprint ((4 + 2M)^3 points; for M = 3 one z half of it) in
+// registers, 12-20 points per lane, and adds every 8th (4th) batch of the brick's markers into it with zero-padded 1-D weight
 // vectors -- branch-free, no shared-memory read-modify-write, no conflicts.  The eight partial footprints are then
 // summed in a fixed tree and added to f.  Bricks NC apart have disjoint footprints: NC^3 launches (colours).
 // Order of the additions: fixed by (batch order within a warp, tree over the warps, brick colour): reproducible.
@@ -473,19 +473,25 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
 constexpr int DENSE_BATCH = 10; // markers per warp and stencil-evaluation round: 3 * 10 lanes busy
 
 template <int K>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, (KTraits<K>::M <= 2) ? 3 : 2)
     spread_dense_kernel(const __grid_constant__ TileParams tp, SpreadArgs args, const int* __restrict__ dense_list, int c0, int c1,
                         int c2)
 {
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
-    static_assert(M == 2, "the register footprint is laid out for 8^3 points");
-    constexpr int FP = BRICK + 2 * M; // 8
+    constexpr int FP = BRICK + 2 * M;       // footprint edge: 6, 8 or 10 points
     constexpr int NC = (BRICK + 2 * M + BRICK - 1) / BRICK;
+    constexpr int NXY = FP * FP;            // (x, y) columns of the footprint
+    constexpr int PPL = (NXY + 31) / 32;    // columns per lane
+    constexpr int ZSPLIT = (FP > 8) ? 2 : 1; // a 10^3 footprint is shared by a pair of warps (lower / upper z half)
+    constexpr int ZN = FP / ZSPLIT;         // z planes per warp
+    constexpr int NG = 8 / ZSPLIT;          // warp groups, each taking every NG-th batch of markers
+    static_assert(FP % ZSPLIT == 0, "z planes split evenly");
     __shared__ double wpad[8][DENSE_BATCH][3][FP]; // zero-padded 1-D weights over the footprint, per warp
-    __shared__ double red[4][FP * FP * FP];
+    __shared__ double red[NG / 2][FP * FP * FP];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = warp % NG, zh = warp / NG;
     const int b = __ldg(&dense_list[blockIdx.x]);
     const int relb = b - tp.brick_base;
     const int nbricks = tp.nt[0] * tp.nt[1] * tp.nt[2] * 64;
@@ -508,10 +514,22 @@ __global__ void __launch_bounds__(256, 3)
 #pragma unroll
     for (int d = 0; d < 3; ++d) fo[d] = BRICK * gb[d] - M;
 
-    const int x = lane & 7, y0 = lane >> 3, y1 = y0 + 4;
-    double acc0[FP], acc1[FP];
+    // this lane's columns (x, y) of the footprint; a column index beyond NXY is parked on column 0 with weight 0
+    int cx[PPL], cy[PPL];
+    bool cok[PPL];
 #pragma unroll
-    for (int z = 0; z < FP; ++z) acc0[z] = acc1[z] = 0.0;
+    for (int k = 0; k < PPL; ++k)
+    {
+        const int c = lane + 32 * k;
+        cok[k] = c < NXY;
+        cx[k] = cok[k] ? c % FP : 0;
+        cy[k] = cok[k] ? c / FP : 0;
+    }
+    double acc[PPL][ZN];
+#pragma unroll
+    for (int k = 0; k < PPL; ++k)
+#pragma unroll
+        for (int z = 0; z < ZN; ++z) acc[k][z] = 0.0;
 
     // the lane's stencil task (marker m of the batch, dimension d); its loads run one batch ahead
     const int tm = lane / 3, td = lane - 3 * tm;
@@ -529,12 +547,12 @@ __global__ void __launch_bounds__(256, 3)
             }
         }
     };
-    fetch(s + warp * DENSE_BATCH);
-    for (int first = s + warp * DENSE_BATCH; first < e; first += 8 * DENSE_BATCH)
+    fetch(s + grp * DENSE_BATCH);
+    for (int first = s + grp * DENSE_BATCH; first < e; first += NG * DENSE_BATCH)
     {
         const int nb = min(DENSE_BATCH, e - first);
         const double xs = nxs, xr = nxr, fv = nv;
-        fetch(first + 8 * DENSE_BATCH);
+        fetch(first + NG * DENSE_BATCH);
         if (lane < nb * 3)
         {
             const int m = tm, d = td;
@@ -553,7 +571,7 @@ __global__ void __launch_bounds__(256, 3)
 #pragma unroll
                 for (int j = 0; j < W; ++j) wp[r0 + j] = w[j] * scale;
             }
-            else if (args.exc_list) // the whole (marker, component) goes to the fix-up; a zero factor removes it here
+            else if (args.exc_list && zh == 0) // the whole (marker, component) goes to the fix-up; a zero factor removes it here
             {
                 const int slot = atomicAdd(args.exc_count, 1);
                 if (slot < args.exc_capacity) args.exc_list[slot] = i * 8 + a;
@@ -563,58 +581,52 @@ __global__ void __launch_bounds__(256, 3)
         for (int m = 0; m < nb; ++m)
         {
             const double* wp = &wpad[warp][m][0][0];
-            const double wx = wp[x];
-            const double p0 = wx * wp[FP + y0], p1 = wx * wp[FP + y1];
+            double pxy[PPL];
 #pragma unroll
-            for (int z = 0; z < FP; ++z)
+            for (int k = 0; k < PPL; ++k) pxy[k] = cok[k] ? wp[cx[k]] * wp[FP + cy[k]] : 0.0;
+#pragma unroll
+            for (int z = 0; z < ZN; ++z)
             {
-                const double wz = wp[2 * FP + z];
-                acc0[z] += p0 * wz;
-                acc1[z] += p1 * wz;
+                const double wz = wp[2 * FP + zh * ZN + z];
+#pragma unroll
+                for (int k = 0; k < PPL; ++k) acc[k][z] += pxy[k] * wz;
             }
         }
         __syncwarp();
     }
 
-    // fixed reduction tree over the warps: (w, w + 4), (w, w + 2), (0, 1); point (x, y, z) at (z * 8 + y) * 8 + x
+    // fixed reduction tree over the warp groups (per z half): (g, g + NG/2), (g, g + NG/4), ...; point (x, y, z) at
+    // (z * FP + y) * FP + x
     auto put = [&](double* dst) {
 #pragma unroll
-        for (int z = 0; z < FP; ++z)
-        {
-            dst[(z * FP + y0) * FP + x] = acc0[z];
-            dst[(z * FP + y1) * FP + x] = acc1[z];
-        }
+        for (int k = 0; k < PPL; ++k)
+            if (cok[k])
+#pragma unroll
+                for (int z = 0; z < ZN; ++z) dst[((zh * ZN + z) * FP + cy[k]) * FP + cx[k]] = acc[k][z];
     };
     auto take = [&](const double* src) {
 #pragma unroll
-        for (int z = 0; z < FP; ++z)
-        {
-            acc0[z] += src[(z * FP + y0) * FP + x];
-            acc1[z] += src[(z * FP + y1) * FP + x];
-        }
+        for (int k = 0; k < PPL; ++k)
+            if (cok[k])
+#pragma unroll
+                for (int z = 0; z < ZN; ++z) acc[k][z] += src[((zh * ZN + z) * FP + cy[k]) * FP + cx[k]];
     };
-    if (warp >= 4) put(red[warp - 4]);
-    __syncthreads();
-    if (warp < 4) take(red[warp]);
-    __syncthreads();
-    if (warp == 2 || warp == 3) put(red[warp - 2]);
-    __syncthreads();
-    if (warp < 2) take(red[warp]);
-    __syncthreads();
-    if (warp == 1) put(red[0]);
-    __syncthreads();
-    if (warp == 0)
+#pragma unroll
+    for (int half = NG / 2; half >= 1; half >>= 1)
     {
-        take(red[0]);
-        put(red[1]);
+        if (grp >= half && grp < 2 * half) put(red[grp - half]);
+        __syncthreads();
+        if (grp < half) take(red[grp]);
+        __syncthreads();
     }
+    if (grp == 0) put(red[0]);
     __syncthreads();
     // f += footprint, dropping the points outside the array (same-colour bricks are disjoint: plain read-modify-write)
     for (int pt = threadIdx.x; pt < FP * FP * FP; pt += 256)
     {
-        const double v = red[1][pt];
+        const double v = red[0][pt];
         if (v == 0.0) continue;
-        const int px = pt & 7, py = (pt >> 3) & 7, pz = pt >> 6;
+        const int px = pt % FP, py = (pt / FP) % FP, pz = pt / (FP * FP);
         const int gi = fo[0] + px - cg.pp0[0], gj = fo[1] + py - cg.pp0[1], gk = fo[2] + pz - cg.pp0[2];
         if (gi < 0 || gi >= cg.n[0] || gj < 0 || gj >= cg.n[1] || gk < 0 || gk >= cg.n[2]) continue;
         cg.ptr[((long long)gk * cg.n[1] + gj) * cg.pitch + gi] += v;
@@ -752,7 +764,7 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     }
     // dense bricks first (their own kernel), then the tiles without them
     args.dense_thresh = 0;
-    if constexpr (NDIM == 3 && M == 2)
+    if constexpr (NDIM == 3)
     {
         static const bool no_dense = getenv("IBK_NO_DENSE") != nullptr;
         if (bins.n_dense > 0 && !no_dense && mv.part != 1) // (with a tile selection the dense bricks go with the boundary part)

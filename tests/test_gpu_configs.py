@@ -173,3 +173,21 @@ def test_nonperiodic_walls(api, kernel):
     F = np.stack([2 * splitmix64_unit(1 + d, np.arange(N)) - 1 for d in range(3)], axis=1)
     eu, ef = _run_level_case(api, level, kernel, X, F)
     assert eu <= TOL and ef <= TOL
+
+
+@pytest.mark.parametrize("kernel", ["IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR"])
+def test_dense_bricks_every_kernel(api, kernel):
+    """A structure-like cloud: 40k markers in a slab a few cells thick that crosses patch boundaries and the periodic
+    boundary, i.e. hundreds of markers per 4^3-cell brick: these bricks take spread_dense_kernel (register
+    footprints of 6^3 / 8^3 / 10^3 points), their sparse neighbours the tile kernel; together they must equal the
+    reference's serial spreading."""
+    n, N = 32, 40000
+    g = orc.min_ghost_width(kernel)
+    i = np.arange(N)
+    X = np.stack([splitmix64_unit(41, i), splitmix64_unit(42, i), 0.97 + 0.08 * splitmix64_unit(43, i)], axis=1)  # z in [0.97, 1.05): wraps
+    X[: N // 4, 0] = 0.48 + 0.05 * splitmix64_unit(44, i[: N // 4])  # and a denser streak across the patch boundary at x = 0.5
+    F = np.stack([2 * splitmix64_unit(51 + d, i) - 1 for d in range(3)], axis=1)
+    boxes = [((0, 0, 0), (15, 31, 31)), ((16, 0, 0), (31, 31, 31))]
+    level = orc.Level(3, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), boxes, (g,) * 3)
+    eu, ef = _run_level_case(api, level, kernel, X, F)
+    assert eu <= TOL and ef <= TOL
