@@ -244,15 +244,26 @@ def run_gpu(args):
 
     # Multi-rank: the messages of the halo exchange are in flight while the tiles that do not touch the exchanged
     # regions are processed (ibk_*_part; include/ibk.h).
+    part_ms = {"spread": 0.0, "interp": 0.0}  # multi-rank: device time of the tile kernels, both parts (last step)
+
+    def timed_part(key, fn, part):
+        if not part_ms.get("on"):
+            return fn(part)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn(part)
+        e1.record(stream)
+        part_ms.setdefault("events", []).append((key, e0, e1))
+
     def spread_part():
         if hx is None:
             ib.spreadForce(accumulate_halo=True)
         else:
             lib, hnd = ctx.lib, ctx.h
             ctx.check(lib.ibk_spread_begin(hnd))
-            ib.spreadForcePart(2)        # boundary tiles: everything the neighbours need
-            hx.accumulate_post()         # pack + start the messages
-            ib.spreadForcePart(1)        # interior tiles, overlapping the transfers
+            timed_part("spread", ib.spreadForcePart, 2)  # boundary tiles: everything the neighbours need
+            hx.accumulate_post()                         # pack + start the messages
+            timed_part("spread", ib.spreadForcePart, 1)  # interior tiles, overlapping the transfers
             ib.halo("f")
             hx.accumulate_finish()       # wait (on the stream) + add
             ctx.check(lib.ibk_spread_end(hnd))
@@ -263,9 +274,9 @@ def run_gpu(args):
         else:
             hx.fill_post()
             ib.halo("u")
-            ib.interpolateVelocityPart(1)  # interior tiles read no ghost cell
+            timed_part("interp", ib.interpolateVelocityPart, 1)  # interior tiles read no ghost cell
             hx.fill_finish()
-            ib.interpolateVelocityPart(2)
+            timed_part("interp", ib.interpolateVelocityPart, 2)
 
     def step():
         spread_part()
@@ -329,10 +340,18 @@ def run_gpu(args):
     # per-kernel-group device times (CUDA events on the ctx stream inside libibk): a few extra steps,
     # read back one by one so the events of each step are still the "last" ones
     for _ in range(min(args.steps, 5)):
+        part_ms["on"] = hx is not None
+        part_ms["events"] = []
         step()
         ctx.synchronize()
-        spread_ms.append(ctx.last_ms(0))
-        interp_ms.append(ctx.last_ms(1))
+        torch.cuda.synchronize()
+        part_ms["on"] = False
+        if hx is None:
+            spread_ms.append(ctx.last_ms(0))
+            interp_ms.append(ctx.last_ms(1))
+        else:  # boundary + interior launches of each operation
+            spread_ms.append(sum(a.elapsed_time(b) for k, a, b in part_ms["events"] if k == "spread"))
+            interp_ms.append(sum(a.elapsed_time(b) for k, a, b in part_ms["events"] if k == "interp"))
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     ms_per_step = total_ms / args.steps
