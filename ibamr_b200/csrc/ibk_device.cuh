@@ -48,6 +48,28 @@ struct KTraits<IBK_BSPLINE_4>
 {
     static constexpr int W = 4, M = 2;
 };
+// N4 kernels.  M counts from the marker's BINNING cell: for the side-shifted dimension the stencil's centre cell can
+// be one above it, hence M = h + 1 for the centred rules (ib_3 h = 1, bspline_5 h = 2).
+template <>
+struct KTraits<IBK_IB_3>
+{
+    static constexpr int W = 3, M = 2;
+};
+template <>
+struct KTraits<IBK_BSPLINE_5>
+{
+    static constexpr int W = 5, M = 3;
+};
+template <>
+struct KTraits<IBK_BSPLINE_6>
+{
+    static constexpr int W = 6, M = 3;
+};
+template <>
+struct KTraits<IBK_PIECEWISE_CUBIC>
+{
+    static constexpr int W = 4, M = 2;
+};
 
 // Fortran NINT (round half away from zero).
 __device__ __forceinline__ int nint_f(double x)
@@ -74,6 +96,46 @@ __device__ __forceinline__ double bspline_4_delta(double x)
     const double r3 = r2 * r;
     if (modx <= 1.0) return (1.0 / 6.0) * (3.0 * r3 - 24.0 * r2 + 60.0 * r - 44.0);
     if (modx <= 2.0) return (1.0 / 6.0) * (-r3 + 12.0 * r2 - 48.0 * r + 64.0);
+    return 0.0;
+}
+
+// lagrangian_delta.f.m4:123-143 (sixth / third are the reference's truncated decimals)
+__device__ __forceinline__ double ib_3_delta(double r)
+{
+    const double sixth = 0.16666666666667, third = 0.333333333333333;
+    r = fabs(r);
+    if (r < 0.5) return third * (1.0 + sqrt(1.0 - 3.0 * r * r));
+    if (r < 1.5) return sixth * (5.0 - 3.0 * r - sqrt(1.0 - 3.0 * (1.0 - r) * (1.0 - r)));
+    return 0.0;
+}
+// lagrangian_delta.f.m4:296-320
+__device__ __forceinline__ double bspline_5_delta(double x)
+{
+    const double modx = fabs(x);
+    const double r = modx + 2.5;
+    const double r2 = r * r, r3 = r2 * r, r4 = r3 * r;
+    if (modx <= 0.5) return (1.0 / 24.0) * (6.0 * r4 - 60.0 * r3 + 210.0 * r2 - 300.0 * r + 155.0);
+    if (modx <= 1.5) return (1.0 / 24.0) * (-4.0 * r4 + 60.0 * r3 - 330.0 * r2 + 780.0 * r - 655.0);
+    if (modx <= 2.5) return (1.0 / 24.0) * (r4 - 20.0 * r3 + 150.0 * r2 - 500.0 * r + 625.0);
+    return 0.0;
+}
+// lagrangian_delta.f.m4:328-352
+__device__ __forceinline__ double bspline_6_delta(double x)
+{
+    const double modx = fabs(x);
+    const double r = modx + 3.0;
+    const double r2 = r * r, r3 = r2 * r, r4 = r3 * r, r5 = r4 * r;
+    if (modx <= 1.0) return (1.0 / 60.0) * (2193.0 - 3465.0 * r + 2130.0 * r2 - 630.0 * r3 + 90.0 * r4 - 5.0 * r5);
+    if (modx <= 2.0) return (1.0 / 120.0) * (-10974.0 + 12270.0 * r - 5340.0 * r2 + 1140.0 * r3 - 120.0 * r4 + 5.0 * r5);
+    if (modx <= 3.0) return (1.0 / 120.0) * (7776.0 - 6480.0 * r + 2160.0 * r2 - 360.0 * r3 + 30.0 * r4 - r5);
+    return 0.0;
+}
+// lagrangian_delta.f.m4:74-93
+__device__ __forceinline__ double piecewise_cubic_delta(double r)
+{
+    r = fabs(r);
+    if (r < 1.0) return 1.0 - 0.5 * r - r * r + 0.5 * r * r * r;
+    if (r < 2.0) return 1.0 - (11.0 / 6.0) * r + r * r - (1.0 / 6.0) * r * r * r;
     return 0.0;
 }
 
@@ -145,6 +207,36 @@ __device__ __forceinline__ void stencil_1d(double Xs, double Xraw, double x_lowe
         {
             const double X_cell = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)(lo + j), 0.5), dx));
             w[j] = bspline_4_delta(__ddiv_rn(__dsub_rn(Xs, X_cell), dx));
+        }
+    }
+    else if constexpr (K == IBK_IB_3 || K == IBK_BSPLINE_5)
+    {
+        // centred rule [c - h, c + h] (3d.f.m4: ib_3 :1038-1066, bspline_5), weight = delta((Xs - X_cell)/dx)
+        constexpr int h = (K == IBK_IB_3) ? 1 : 2;
+        const int c = (int)floor(t);
+        lo = c - h;
+#pragma unroll
+        for (int j = 0; j < 2 * h + 1; ++j)
+        {
+            const double X_cell = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)(lo + j), 0.5), dx));
+            const double r = __ddiv_rn(__dsub_rn(Xs, X_cell), dx);
+            w[j] = (K == IBK_IB_3) ? ib_3_delta(r) : bspline_5_delta(r);
+        }
+    }
+    else if constexpr (K == IBK_BSPLINE_6 || K == IBK_PIECEWISE_CUBIC)
+    {
+        // sided rule (3d.f.m4: bspline_6, piecewise_cubic): the UNSHIFTED X against X_cell(c) picks [c - h, c + h - 1]
+        // or [c - h + 1, c + h]
+        constexpr int h = (K == IBK_BSPLINE_6) ? 3 : 2;
+        const int c = (int)floor(t);
+        const double X_cell_c = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)c, 0.5), dx));
+        lo = (Xraw < X_cell_c) ? c - h : c - h + 1;
+#pragma unroll
+        for (int j = 0; j < 2 * h; ++j)
+        {
+            const double X_cell = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)(lo + j), 0.5), dx));
+            const double r = __ddiv_rn(__dsub_rn(Xs, X_cell), dx);
+            w[j] = (K == IBK_BSPLINE_6) ? bspline_6_delta(r) : piecewise_cubic_delta(r);
         }
     }
     else

@@ -332,6 +332,14 @@ static cudaError_t launch_interp_k(Launcher& L, int kernel, const TileParams& tp
         return launch_interp_t<NDIM, IBK_BSPLINE_3>(L, tp, bins, mv, err);
     case IBK_BSPLINE_4:
         return launch_interp_t<NDIM, IBK_BSPLINE_4>(L, tp, bins, mv, err);
+    case IBK_IB_3:
+        return launch_interp_t<NDIM, IBK_IB_3>(L, tp, bins, mv, err);
+    case IBK_BSPLINE_5:
+        return launch_interp_t<NDIM, IBK_BSPLINE_5>(L, tp, bins, mv, err);
+    case IBK_BSPLINE_6:
+        return launch_interp_t<NDIM, IBK_BSPLINE_6>(L, tp, bins, mv, err);
+    case IBK_PIECEWISE_CUBIC:
+        return launch_interp_t<NDIM, IBK_PIECEWISE_CUBIC>(L, tp, bins, mv, err);
     default:
         err = "unknown kernel";
         return cudaErrorInvalidValue;

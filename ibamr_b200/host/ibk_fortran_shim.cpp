@@ -105,8 +105,16 @@ IBK_SHIM_3D(ib_4, IBK_IB_4)
 IBK_SHIM_3D(ib_6, IBK_IB_6)
 IBK_SHIM_3D(bspline_3, IBK_BSPLINE_3)
 IBK_SHIM_3D(bspline_4, IBK_BSPLINE_4)
+IBK_SHIM_3D(ib_3, IBK_IB_3)
+IBK_SHIM_3D(bspline_5, IBK_BSPLINE_5)
+IBK_SHIM_3D(bspline_6, IBK_BSPLINE_6)
+IBK_SHIM_3D(piecewise_cubic, IBK_PIECEWISE_CUBIC)
 IBK_SHIM_2D(piecewise_linear, IBK_PIECEWISE_LINEAR)
 IBK_SHIM_2D(ib_4, IBK_IB_4)
 IBK_SHIM_2D(ib_6, IBK_IB_6)
 IBK_SHIM_2D(bspline_3, IBK_BSPLINE_3)
 IBK_SHIM_2D(bspline_4, IBK_BSPLINE_4)
+IBK_SHIM_2D(ib_3, IBK_IB_3)
+IBK_SHIM_2D(bspline_5, IBK_BSPLINE_5)
+IBK_SHIM_2D(bspline_6, IBK_BSPLINE_6)
+IBK_SHIM_2D(piecewise_cubic, IBK_PIECEWISE_CUBIC)

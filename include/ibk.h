@@ -49,15 +49,20 @@ typedef enum ibk_status
     IBK_ERR_ESCAPED = -7         /* "IB point has escaped ...", LDataManager.cpp:1410-1416      */
 } ibk_status;
 
-/* The five in-scope delta kernels (names as LEInteractor::string_to_kernel accepts them,
- * LEInteractor.cpp:1923-2016). */
+/* The delta kernels (names as LEInteractor::string_to_kernel accepts them, LEInteractor.cpp:1923-2016): the five
+ * of the hot path's scope and, as a first part of SURVEY.md 8(f) N4, four more of the "delta function per stencil
+ * point" kind (lagrangian_interaction3d.f.m4: ib_3, bspline_5, bspline_6, piecewise_cubic). */
 typedef enum ibk_kernel
 {
     IBK_PIECEWISE_LINEAR = 0,
     IBK_IB_4 = 1,
     IBK_IB_6 = 2,
     IBK_BSPLINE_3 = 3,
-    IBK_BSPLINE_4 = 4
+    IBK_BSPLINE_4 = 4,
+    IBK_IB_3 = 5,
+    IBK_BSPLINE_5 = 6,
+    IBK_BSPLINE_6 = 7,
+    IBK_PIECEWISE_CUBIC = 8
 } ibk_kernel;
 
 /* ---- LEInteractor static queries (ibtk/include/ibtk/LEInteractor.h:99-117) ------------------ */

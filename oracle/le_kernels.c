@@ -48,7 +48,12 @@ enum
     K_IB_4 = 1,
     K_IB_6 = 2,
     K_BSPLINE_3 = 3,
-    K_BSPLINE_4 = 4
+    K_BSPLINE_4 = 4,
+    /* N4: four more of the reference's kernels, all of the "delta function per stencil point" kind */
+    K_IB_3 = 5,
+    K_BSPLINE_5 = 6,
+    K_BSPLINE_6 = 7,
+    K_PIECEWISE_CUBIC = 8
 };
 
 typedef struct
@@ -147,6 +152,86 @@ static void stencil_ib_6(double Xs, double x_lower, double dx, int ilower, int i
     s->hi = ic_lower + istop;
 }
 
+/* lagrangian_delta.f.m4:123-143 (the constants sixth / third are the reference's truncated decimals) */
+static double ib_3_delta(double r)
+{
+    const double sixth = 0.16666666666667, third = 0.333333333333333;
+    if (r < 0.0) r = -r;
+    if (r < 0.5) return third * (1.0 + sqrt(1.0 - 3.0 * r * r));
+    if (r < 1.5) return sixth * (5.0 - 3.0 * r - sqrt(1.0 - 3.0 * (1.0 - r) * (1.0 - r)));
+    return 0.0;
+}
+/* lagrangian_delta.f.m4:296-320 */
+static double bspline_5_delta(double x)
+{
+    const double modx = fabs(x);
+    const double r = modx + 2.5;
+    const double r2 = r * r, r3 = r2 * r, r4 = r3 * r;
+    if (modx <= 0.5) return (1.0 / 24.0) * (6.0 * r4 - 60.0 * r3 + 210.0 * r2 - 300.0 * r + 155.0);
+    if (modx <= 1.5) return (1.0 / 24.0) * (-4.0 * r4 + 60.0 * r3 - 330.0 * r2 + 780.0 * r - 655.0);
+    if (modx <= 2.5) return (1.0 / 24.0) * (r4 - 20.0 * r3 + 150.0 * r2 - 500.0 * r + 625.0);
+    return 0.0;
+}
+/* lagrangian_delta.f.m4:328-352 */
+static double bspline_6_delta(double x)
+{
+    const double modx = fabs(x);
+    const double r = modx + 3.0;
+    const double r2 = r * r, r3 = r2 * r, r4 = r3 * r, r5 = r4 * r;
+    if (modx <= 1.0) return (1.0 / 60.0) * (2193.0 - 3465.0 * r + 2130.0 * r2 - 630.0 * r3 + 90.0 * r4 - 5.0 * r5);
+    if (modx <= 2.0) return (1.0 / 120.0) * (-10974.0 + 12270.0 * r - 5340.0 * r2 + 1140.0 * r3 - 120.0 * r4 + 5.0 * r5);
+    if (modx <= 3.0) return (1.0 / 120.0) * (7776.0 - 6480.0 * r + 2160.0 * r2 - 360.0 * r3 + 30.0 * r4 - r5);
+    return 0.0;
+}
+/* lagrangian_delta.f.m4:74-93 */
+static double piecewise_cubic_delta(double r)
+{
+    if (r < 0.0) r = -r;
+    if (r < 1.0) return 1.0 - 0.5 * r - r * r + 0.5 * r * r * r;
+    if (r < 2.0) return 1.0 - (11.0 / 6.0) * r + r * r - (1.0 / 6.0) * r * r * r;
+    return 0.0;
+}
+
+/* The four N4 kernels share two index rules (lagrangian_interaction3d.f.m4):
+ *   centred, odd width 2h+1 (ib_3 :1038-1066 h = 1, bspline_5 h = 2): [c - h, c + h], c = floor((X+Xshift-x_lower)/dx)
+ *   sided, even width 2h (piecewise_cubic h = 2, bspline_6 h = 3): unshifted X < X_cell(c) ? [c - h, c + h - 1] : [c - h + 1, c + h]
+ * both clamped to the ghost box, weights indexed from the CLAMPED lower bound, weight = delta((X+Xshift-X_cell)/dx). */
+static void stencil_delta(double (*delta)(double), int h, int sided, double Xs, double Xraw, double x_lower, double dx, int ilower,
+                          int iupper, int g, stencil1d* s)
+{
+    const int ic_center = (int)floor((Xs - x_lower) / dx) + ilower;
+    int ic_lower, ic_upper;
+    if (!sided)
+    {
+        ic_lower = ic_center - h;
+        ic_upper = ic_center + h;
+    }
+    else
+    {
+        const double X_cell_c = x_lower + ((double)(ic_center - ilower) + 0.5) * dx;
+        if (Xraw < X_cell_c)
+        {
+            ic_lower = ic_center - h;
+            ic_upper = ic_center + h - 1;
+        }
+        else
+        {
+            ic_lower = ic_center - h + 1;
+            ic_upper = ic_center + h;
+        }
+    }
+    if (ic_lower < ilower - g) ic_lower = ilower - g;
+    if (ic_upper > iupper + g) ic_upper = iupper + g;
+    for (int ic = ic_lower; ic <= ic_upper; ++ic)
+    {
+        const double X_cell = x_lower + ((double)(ic - ilower) + 0.5) * dx;
+        s->w[ic - ic_lower] = delta((Xs - X_cell) / dx);
+    }
+    s->wbase = ic_lower;
+    s->lo = ic_lower;
+    s->hi = ic_upper;
+}
+
 /* 3d.f.m4:2659-2678: weights are indexed from the CLAMPED lower bound. */
 static void stencil_bspline_3(double Xs, double x_lower, double dx, int ilower, int iupper, int g, stencil1d* s)
 {
@@ -242,6 +327,18 @@ static void make_stencil(int kernel,
         break;
     case K_BSPLINE_3:
         stencil_bspline_3(Xs, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_IB_3:
+        stencil_delta(ib_3_delta, 1, 0, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_BSPLINE_5:
+        stencil_delta(bspline_5_delta, 2, 0, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_BSPLINE_6:
+        stencil_delta(bspline_6_delta, 3, 1, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_PIECEWISE_CUBIC:
+        stencil_delta(piecewise_cubic_delta, 2, 1, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
         break;
     default:
         stencil_bspline_4(Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
@@ -505,8 +602,16 @@ DEFINE_3D(ib_4, K_IB_4)
 DEFINE_3D(ib_6, K_IB_6)
 DEFINE_3D(bspline_3, K_BSPLINE_3)
 DEFINE_3D(bspline_4, K_BSPLINE_4)
+DEFINE_3D(ib_3, K_IB_3)
+DEFINE_3D(bspline_5, K_BSPLINE_5)
+DEFINE_3D(bspline_6, K_BSPLINE_6)
+DEFINE_3D(piecewise_cubic, K_PIECEWISE_CUBIC)
 DEFINE_2D(piecewise_linear, K_PIECEWISE_LINEAR)
 DEFINE_2D(ib_4, K_IB_4)
 DEFINE_2D(ib_6, K_IB_6)
 DEFINE_2D(bspline_3, K_BSPLINE_3)
 DEFINE_2D(bspline_4, K_BSPLINE_4)
+DEFINE_2D(ib_3, K_IB_3)
+DEFINE_2D(bspline_5, K_BSPLINE_5)
+DEFINE_2D(bspline_6, K_BSPLINE_6)
+DEFINE_2D(piecewise_cubic, K_PIECEWISE_CUBIC)

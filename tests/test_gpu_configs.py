@@ -175,7 +175,8 @@ def test_nonperiodic_walls(api, kernel):
     assert eu <= TOL and ef <= TOL
 
 
-@pytest.mark.parametrize("kernel", ["IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR"])
+@pytest.mark.parametrize("kernel", ["IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR", "IB_3", "BSPLINE_5", "BSPLINE_6",
+                                    "PIECEWISE_CUBIC"])
 def test_dense_bricks_every_kernel(api, kernel):
     """A structure-like cloud: 40k markers in a slab a few cells thick that crosses patch boundaries and the periodic
     boundary, i.e. hundreds of markers per 4^3-cell brick: these bricks take spread_dense_kernel (register
