@@ -64,6 +64,8 @@ extern "C" int ibk_kernel_from_string(const char* s)
     if (!strcmp(s, "BSPLINE_5")) return IBK_BSPLINE_5;
     if (!strcmp(s, "BSPLINE_6")) return IBK_BSPLINE_6;
     if (!strcmp(s, "PIECEWISE_CUBIC")) return IBK_PIECEWISE_CUBIC;
+    if (!strcmp(s, "IB_5")) return IBK_IB_5;
+    if (!strcmp(s, "PIECEWISE_CONSTANT")) return IBK_PIECEWISE_CONSTANT;
     return IBK_ERR_UNKNOWN_KERNEL;
 }
 extern "C" int ibk_is_known_kernel(const char* s)
@@ -92,6 +94,10 @@ extern "C" int ibk_get_stencil_size(const char* s)
         return 6;
     case IBK_PIECEWISE_CUBIC:
         return 4;
+    case IBK_IB_5:
+        return 6;
+    case IBK_PIECEWISE_CONSTANT:
+        return 1;
     default:
         return IBK_ERR_UNKNOWN_KERNEL;
     }
@@ -316,7 +322,7 @@ static int raw_op(ibk_ctx* ctx, int op, int kernel, const ibk_array_desc* desc, 
                   const int* d_indices, const double* d_Xshift, int nindices, const double* d_X, int n_markers, double* d_V)
 {
     if (!ctx || !desc) return IBK_ERR_INVALID;
-    if (kernel < 0 || kernel > IBK_PIECEWISE_CUBIC) return fail(ctx, IBK_ERR_UNKNOWN_KERNEL, "unknown kernel");
+    if (kernel < 0 || kernel > IBK_PIECEWISE_CONSTANT) return fail(ctx, IBK_ERR_UNKNOWN_KERNEL, "unknown kernel");
     const int ndim = desc->ndim;
     if (ndim != 2 && ndim != 3) return fail(ctx, IBK_ERR_INVALID, "ndim must be 2 or 3");
     if (desc->depth < 1 || desc->depth > IBK_MAX_COMP) return fail(ctx, IBK_ERR_INVALID, "depth out of range");

@@ -70,6 +70,16 @@ struct KTraits<IBK_PIECEWISE_CUBIC>
 {
     static constexpr int W = 4, M = 2;
 };
+template <>
+struct KTraits<IBK_IB_5>
+{
+    static constexpr int W = 5, M = 3;
+};
+template <>
+struct KTraits<IBK_PIECEWISE_CONSTANT>
+{
+    static constexpr int W = 1, M = 1;
+};
 
 // Fortran NINT (round half away from zero).
 __device__ __forceinline__ int nint_f(double x)
@@ -208,6 +218,31 @@ __device__ __forceinline__ void stencil_1d(double Xs, double Xraw, double x_lowe
             const double X_cell = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)(lo + j), 0.5), dx));
             w[j] = bspline_4_delta(__ddiv_rn(__dsub_rn(Xs, X_cell), dx));
         }
+    }
+    else if constexpr (K == IBK_IB_5)
+    {
+        // lagrangian_ib_5_interp3d: centre cell floor(t), points c-2..c+2, r = (Xs - X_cell(c))/dx
+        const double Kc = (38.0 - 8.306623862918075) / 60.0; // (38 - sqrt(69))/60, sqrt(69) correctly rounded
+        const int c = (int)floor(t);
+        lo = c - 2;
+        const double X_cell = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)c, 0.5), dx));
+        const double r = __ddiv_rn(__dsub_rn(Xs, X_cell), dx);
+        const double r2 = r * r, r3 = r2 * r, r4 = r2 * r2, r6 = r4 * r2;
+        const double phi = (136.0 - 40.0 * Kc - 40.0 * r2 +
+                            1.4142135623730951 * sqrt(3123.0 - 6840.0 * Kc + 3600.0 * (Kc * Kc) - 12440.0 * r2 + 25680.0 * Kc * r2 -
+                                                      12600.0 * (Kc * Kc) * r2 + 8080.0 * r4 - 8400.0 * Kc * r4 - 1400.0 * r6)) /
+                           280.0;
+        w[0] = (1.0 / 12.0) * (-2.0 + 2.0 * phi + 2.0 * Kc + r - 3.0 * Kc * r + 2.0 * r2 - r3);
+        w[1] = (1.0 / 6.0) * (4.0 - 4.0 * phi - Kc - 4.0 * r + 3.0 * Kc * r - r2 + r3);
+        w[2] = phi;
+        w[3] = (1.0 / 6.0) * (4.0 - 4.0 * phi - Kc + 4.0 * r - 3.0 * Kc * r - r2 - r3);
+        w[4] = (1.0 / 12.0) * (-2.0 + 2.0 * phi + 2.0 * Kc - r + 3.0 * Kc * r + 2.0 * r2 + r3);
+    }
+    else if constexpr (K == IBK_PIECEWISE_CONSTANT)
+    {
+        // lagrangian_piecewise_constant_interp3d: the cell NINT(t - 0.5), weight 1
+        lo = nint_f(__dsub_rn(t, 0.5));
+        w[0] = 1.0;
     }
     else if constexpr (K == IBK_IB_3 || K == IBK_BSPLINE_5)
     {

@@ -340,6 +340,10 @@ static cudaError_t launch_interp_k(Launcher& L, int kernel, const TileParams& tp
         return launch_interp_t<NDIM, IBK_BSPLINE_6>(L, tp, bins, mv, err);
     case IBK_PIECEWISE_CUBIC:
         return launch_interp_t<NDIM, IBK_PIECEWISE_CUBIC>(L, tp, bins, mv, err);
+    case IBK_IB_5:
+        return launch_interp_t<NDIM, IBK_IB_5>(L, tp, bins, mv, err);
+    case IBK_PIECEWISE_CONSTANT:
+        return launch_interp_t<NDIM, IBK_PIECEWISE_CONSTANT>(L, tp, bins, mv, err);
     default:
         err = "unknown kernel";
         return cudaErrorInvalidValue;

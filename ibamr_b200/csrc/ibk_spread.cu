@@ -848,6 +848,10 @@ static cudaError_t launch_spread_k(Launcher& L, int kernel, const TileParams& tp
         return launch_spread_t<NDIM, IBK_BSPLINE_6>(L, tp, bins, mv, err);
     case IBK_PIECEWISE_CUBIC:
         return launch_spread_t<NDIM, IBK_PIECEWISE_CUBIC>(L, tp, bins, mv, err);
+    case IBK_IB_5:
+        return launch_spread_t<NDIM, IBK_IB_5>(L, tp, bins, mv, err);
+    case IBK_PIECEWISE_CONSTANT:
+        return launch_spread_t<NDIM, IBK_PIECEWISE_CONSTANT>(L, tp, bins, mv, err);
     default:
         err = "unknown kernel";
         return cudaErrorInvalidValue;

@@ -109,6 +109,8 @@ IBK_SHIM_3D(ib_3, IBK_IB_3)
 IBK_SHIM_3D(bspline_5, IBK_BSPLINE_5)
 IBK_SHIM_3D(bspline_6, IBK_BSPLINE_6)
 IBK_SHIM_3D(piecewise_cubic, IBK_PIECEWISE_CUBIC)
+IBK_SHIM_3D(ib_5, IBK_IB_5)
+IBK_SHIM_3D(piecewise_constant, IBK_PIECEWISE_CONSTANT)
 IBK_SHIM_2D(piecewise_linear, IBK_PIECEWISE_LINEAR)
 IBK_SHIM_2D(ib_4, IBK_IB_4)
 IBK_SHIM_2D(ib_6, IBK_IB_6)
@@ -118,3 +120,5 @@ IBK_SHIM_2D(ib_3, IBK_IB_3)
 IBK_SHIM_2D(bspline_5, IBK_BSPLINE_5)
 IBK_SHIM_2D(bspline_6, IBK_BSPLINE_6)
 IBK_SHIM_2D(piecewise_cubic, IBK_PIECEWISE_CUBIC)
+IBK_SHIM_2D(ib_5, IBK_IB_5)
+IBK_SHIM_2D(piecewise_constant, IBK_PIECEWISE_CONSTANT)

@@ -50,8 +50,8 @@ typedef enum ibk_status
 } ibk_status;
 
 /* The delta kernels (names as LEInteractor::string_to_kernel accepts them, LEInteractor.cpp:1923-2016): the five
- * of the hot path's scope and, as a first part of SURVEY.md 8(f) N4, four more of the "delta function per stencil
- * point" kind (lagrangian_interaction3d.f.m4: ib_3, bspline_5, bspline_6, piecewise_cubic). */
+ * of the hot path's scope and, as a first part of SURVEY.md 8(f) N4, six more that do not depend on the component
+ * axis (lagrangian_interaction3d.f.m4: ib_3, bspline_5, bspline_6, piecewise_cubic, ib_5, piecewise_constant). */
 typedef enum ibk_kernel
 {
     IBK_PIECEWISE_LINEAR = 0,
@@ -62,7 +62,9 @@ typedef enum ibk_kernel
     IBK_IB_3 = 5,
     IBK_BSPLINE_5 = 6,
     IBK_BSPLINE_6 = 7,
-    IBK_PIECEWISE_CUBIC = 8
+    IBK_PIECEWISE_CUBIC = 8,
+    IBK_IB_5 = 9,
+    IBK_PIECEWISE_CONSTANT = 10
 } ibk_kernel;
 
 /* ---- LEInteractor static queries (ibtk/include/ibtk/LEInteractor.h:99-117) ------------------ */

@@ -53,7 +53,9 @@ enum
     K_IB_3 = 5,
     K_BSPLINE_5 = 6,
     K_BSPLINE_6 = 7,
-    K_PIECEWISE_CUBIC = 8
+    K_PIECEWISE_CUBIC = 8,
+    K_IB_5 = 9,
+    K_PIECEWISE_CONSTANT = 10
 };
 
 typedef struct
@@ -232,6 +234,46 @@ static void stencil_delta(double (*delta)(double), int h, int sided, double Xs, 
     s->hi = ic_upper;
 }
 
+/* ib_5 (lagrangian_interaction3d.f.m4, lagrangian_ib_5_interp3d): centre cell floor(...), five points c-2..c+2,
+ * closed-form weights from r = (X - X_cell(c))/dx with K = (38 - sqrt(69))/60; loop bounds clipped to the ghost box,
+ * weights indexed from the UNCLIPPED lower bound (istart/istop), products formed as w0*w1*w2*u. */
+static void stencil_ib_5(double Xs, double x_lower, double dx, int ilower, int iupper, int g, stencil1d* s)
+{
+    const double K = (38.0 - sqrt(69.0)) / 60.0;
+    const int ic_center = (int)floor((Xs - x_lower) / dx) + ilower;
+    const int ic_lower = ic_center - 2, ic_upper = ic_center + 2;
+    const double X_cell = x_lower + ((double)(ic_center - ilower) + 0.5) * dx;
+    const double r = (Xs - X_cell) / dx;
+    const double r2 = r * r, r3 = r2 * r, r4 = r2 * r2, r6 = r4 * r2;
+    const double phi = (136.0 - 40.0 * K - 40.0 * r2 +
+                        sqrt(2.0) * sqrt(3123.0 - 6840.0 * K + 3600.0 * (K * K) - 12440.0 * r2 + 25680.0 * K * r2 -
+                                         12600.0 * (K * K) * r2 + 8080.0 * r4 - 8400.0 * K * r4 - 1400.0 * r6)) /
+                       280.0;
+    s->w[0] = (1.0 / 12.0) * (-2.0 + 2.0 * phi + 2.0 * K + r - 3.0 * K * r + 2.0 * r2 - r3);
+    s->w[1] = (1.0 / 6.0) * (4.0 - 4.0 * phi - K - 4.0 * r + 3.0 * K * r - r2 + r3);
+    s->w[2] = phi;
+    s->w[3] = (1.0 / 6.0) * (4.0 - 4.0 * phi - K + 4.0 * r - 3.0 * K * r - r2 - r3);
+    s->w[4] = (1.0 / 12.0) * (-2.0 + 2.0 * phi + 2.0 * K - r + 3.0 * K * r + 2.0 * r2 + r3);
+    const int ig_lower = ilower - g, ig_upper = iupper + g;
+    const int istart = (ig_lower - ic_lower > 0) ? ig_lower - ic_lower : 0;
+    const int istop = 4 - ((ic_upper - ig_upper > 0) ? ic_upper - ig_upper : 0);
+    s->wbase = ic_lower;
+    s->lo = ic_lower + istart;
+    s->hi = ic_lower + istop;
+}
+
+/* piecewise_constant (lagrangian_piecewise_constant_interp3d): the one cell ilower + NINT((X-x_lower)/dx - 0.5), weight 1.
+ * The Fortran does not clip (a point outside the ghost box would index out of the array); here such a point is skipped. */
+static void stencil_piecewise_constant(double Xs, double x_lower, double dx, int ilower, int iupper, int g, stencil1d* s)
+{
+    const int ic = ilower + nint_f((Xs - x_lower) / dx - 0.5);
+    s->w[0] = 1.0;
+    s->wbase = ic;
+    s->lo = (ic >= ilower - g) ? ic : ic + 1; /* lo > hi: nothing */
+    s->hi = (ic <= iupper + g) ? ic : ic - 1;
+    if (ic < ilower - g) s->hi = ic - 1, s->lo = ic;
+}
+
 /* 3d.f.m4:2659-2678: weights are indexed from the CLAMPED lower bound. */
 static void stencil_bspline_3(double Xs, double x_lower, double dx, int ilower, int iupper, int g, stencil1d* s)
 {
@@ -339,6 +381,12 @@ static void make_stencil(int kernel,
         break;
     case K_PIECEWISE_CUBIC:
         stencil_delta(piecewise_cubic_delta, 2, 1, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_IB_5:
+        stencil_ib_5(Xs, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_PIECEWISE_CONSTANT:
+        stencil_piecewise_constant(Xs, x_lower, dx, ilower, iupper, g, s);
         break;
     default:
         stencil_bspline_4(Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
@@ -606,6 +654,8 @@ DEFINE_3D(ib_3, K_IB_3)
 DEFINE_3D(bspline_5, K_BSPLINE_5)
 DEFINE_3D(bspline_6, K_BSPLINE_6)
 DEFINE_3D(piecewise_cubic, K_PIECEWISE_CUBIC)
+DEFINE_3D(ib_5, K_IB_5)
+DEFINE_3D(piecewise_constant, K_PIECEWISE_CONSTANT)
 DEFINE_2D(piecewise_linear, K_PIECEWISE_LINEAR)
 DEFINE_2D(ib_4, K_IB_4)
 DEFINE_2D(ib_6, K_IB_6)
@@ -615,3 +665,5 @@ DEFINE_2D(ib_3, K_IB_3)
 DEFINE_2D(bspline_5, K_BSPLINE_5)
 DEFINE_2D(bspline_6, K_BSPLINE_6)
 DEFINE_2D(piecewise_cubic, K_PIECEWISE_CUBIC)
+DEFINE_2D(ib_5, K_IB_5)
+DEFINE_2D(piecewise_constant, K_PIECEWISE_CONSTANT)

@@ -32,10 +32,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 KERNELS = {"PIECEWISE_LINEAR": 0, "IB_4": 1, "IB_6": 2, "BSPLINE_3": 3, "BSPLINE_4": 4, "IB_3": 5, "BSPLINE_5": 6, "BSPLINE_6": 7,
-           "PIECEWISE_CUBIC": 8}
+           "PIECEWISE_CUBIC": 8, "IB_5": 9, "PIECEWISE_CONSTANT": 10}
 # LEInteractor::getStencilSize (LEInteractor.cpp:2052-2108) and getMinimumGhostWidth (:2110-2114)
 STENCIL_SIZE = {"PIECEWISE_LINEAR": 2, "IB_4": 4, "IB_6": 6, "BSPLINE_3": 4, "BSPLINE_4": 4, "IB_3": 4, "BSPLINE_5": 6, "BSPLINE_6": 6,
-                "PIECEWISE_CUBIC": 4}  # LEInteractor::getStencilSize (LEInteractor.cpp:2052-2103)
+                "PIECEWISE_CUBIC": 4, "IB_5": 6, "PIECEWISE_CONSTANT": 1}  # LEInteractor::getStencilSize (LEInteractor.cpp:2052-2103)
 
 
 def min_ghost_width(kernel: str) -> int:

@@ -5,7 +5,7 @@
 set -e
 REF=${1:-/root/reference}
 HERE=$(dirname "$0")
-for k in ib_4 ib_6 bspline_3 bspline_4 piecewise_linear ib_3 bspline_5 bspline_6 piecewise_cubic; do
+for k in ib_4 ib_6 bspline_3 bspline_4 piecewise_linear ib_3 bspline_5 bspline_6 piecewise_cubic ib_5 piecewise_constant; do
   for d in 2d 3d; do
     cp "$REF/tests/interpolate/interpolate_01_$d.$k.output" "$HERE/"
   done

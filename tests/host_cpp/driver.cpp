@@ -25,7 +25,7 @@ using IBTK_B200::LEInteractor;
 
 static int run_static()
 {
-    const char* names[] = { "IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR", "IB_3", "BSPLINE_5", "BSPLINE_6", "PIECEWISE_CUBIC" };
+    const char* names[] = { "IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR", "IB_3", "BSPLINE_5", "BSPLINE_6", "PIECEWISE_CUBIC", "IB_5", "PIECEWISE_CONSTANT" };
     for (const char* n : names)
         std::printf("%s known=%d stencil=%d ghosts=%d\n", n, (int)LEInteractor::isKnownKernel(n), LEInteractor::getStencilSize(n),
                     LEInteractor::getMinimumGhostWidth(n));

@@ -12,7 +12,8 @@ from tests.util import (read_ghost_accumulation_golden, read_interpolate_golden,
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = ["IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR", "IB_3", "BSPLINE_5", "BSPLINE_6", "PIECEWISE_CUBIC"]
+KERNELS = ["IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR", "IB_3", "BSPLINE_5", "BSPLINE_6", "PIECEWISE_CUBIC", "IB_5",
+           "PIECEWISE_CONSTANT"]
 TOL = 1e-12
 
 
@@ -131,7 +132,7 @@ def test_golden_interpolate_01_2d(api, kernel, golden_dir):
     Q = np.full((100, 2), np.finfo(np.float64).max)
     api.LEInteractor.interpolate(Q, 2, X, 2, q, patch, box, kernel)
     reach = {"IB_4": 2, "IB_6": 3, "BSPLINE_3": 2, "BSPLINE_4": 2, "PIECEWISE_LINEAR": 1, "IB_3": 2, "BSPLINE_5": 3, "BSPLINE_6": 3,
-             "PIECEWISE_CUBIC": 2}[kernel]
+             "PIECEWISE_CUBIC": 2, "IB_5": 3, "PIECEWISE_CONSTANT": 1}[kernel]
     cell = np.floor((X - 0.25) / patch.dx[0]).astype(int)
     inside = np.all((cell - reach >= 0) & (cell + reach <= N - 1), axis=1)
     np.testing.assert_allclose(Q[inside], gold[inside][:, 3:5], rtol=0, atol={"BSPLINE_6": 2e-12, "BSPLINE_5": 2e-13}.get(kernel, 5e-14))
@@ -311,7 +312,7 @@ def test_error_behaviour(api):
         api.LEInteractor.interpolate(np.zeros((4, 1)), 1, X, 2, api.SideData(box, 1, 3), patch, box, "IB_4")
     assert e.value.code == api.IBK_ERR_DEPTH
     with pytest.raises(api.IBKError) as e:
-        api.LEInteractor.interpolate(Q, 2, X, 2, api.SideData(box, 1, 3), patch, box, "IB_5")
+        api.LEInteractor.interpolate(Q, 2, X, 2, api.SideData(box, 1, 3), patch, box, "IB_4_W8")  # not built (N4)
     assert e.value.code == api.IBK_ERR_UNKNOWN_KERNEL
     # spread with too few ghosts is only an error at a physical boundary (:5250-5266)
     api.LEInteractor.spread(api.SideData(box, 1, 1), Q, 2, X, 2, patch, box, "PIECEWISE_LINEAR")

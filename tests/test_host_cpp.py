@@ -47,7 +47,7 @@ def test_cpp_static_queries_and_refusal(driver):
 
 def test_fortran_shim_exports_all_symbols(driver):
     out = subprocess.run(["nm", os.path.join(BUILD, "shim.o")], capture_output=True, text=True, check=True).stdout
-    for k in ("piecewise_linear", "ib_4", "ib_6", "bspline_3", "bspline_4", "ib_3", "bspline_5", "bspline_6", "piecewise_cubic"):
+    for k in ("piecewise_linear", "ib_4", "ib_6", "bspline_3", "bspline_4", "ib_3", "bspline_5", "bspline_6", "piecewise_cubic", "ib_5", "piecewise_constant"):
         for op in ("interp", "spread"):
             for d in ("2d", "3d"):
                 assert f" T lagrangian_{k}_{op}{d}_" in out

@@ -12,7 +12,7 @@ from oracle import oracle as orc
 from tests.util import (read_ghost_accumulation_golden, read_index_utilities_golden, read_interpolate_golden,
                         std_uniform_stream)
 
-KERNELS = ["IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR", "IB_3", "BSPLINE_5", "BSPLINE_6", "PIECEWISE_CUBIC"]
+KERNELS = ["IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR", "IB_3", "BSPLINE_5", "BSPLINE_6", "PIECEWISE_CUBIC", "IB_5", "PIECEWISE_CONSTANT"]
 
 
 def _interp_patch(ndim, N):
@@ -65,7 +65,7 @@ def test_interpolate_01_2d(kernel, golden_dir):
     np.testing.assert_allclose(X, gold[:, :2], rtol=1e-15, atol=0)
     Q = orc.cell_interp_positions(kernel, pg, u, 2, X)
     reach = {'IB_4': 2, 'IB_6': 3, 'BSPLINE_3': 2, 'BSPLINE_4': 2, 'PIECEWISE_LINEAR': 1, 'IB_3': 2, 'BSPLINE_5': 3, 'BSPLINE_6': 3,
-             'PIECEWISE_CUBIC': 2}[kernel]
+             'PIECEWISE_CUBIC': 2, 'IB_5': 3, 'PIECEWISE_CONSTANT': 1}[kernel]
     cell = np.floor((X - 0.25) / dx[0]).astype(int)  # 0..15 within the patch
     inside = np.all((cell - reach >= 0) & (cell + reach <= N - 1), axis=1)
     assert inside.sum() >= 30, inside.sum()
