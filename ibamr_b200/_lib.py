@@ -82,6 +82,10 @@ SYMBOLS = {
     "ibk_side_spread_host": (_i, [_vp, _s, C.POINTER(PatchDesc), _ppd, _i, _pi, _pi, _pd, _i, _i, _pd, _i, _i]),
     "ibk_cell_interpolate_host": (_i, [_vp, _s, C.POINTER(PatchDesc), _pd, _i, _pi, _pi, _pd, _i, _i, _pd, _i, _i]),
     "ibk_cell_spread_host": (_i, [_vp, _s, C.POINTER(PatchDesc), _pd, _i, _pi, _pi, _pd, _i, _i, _pd, _i, _i]),
+    "ibk_node_interpolate_host": (_i, [_vp, _s, C.POINTER(PatchDesc), _pd, _i, _pi, _pi, _pd, _i, _i, _pd, _i, _i]),
+    "ibk_node_spread_host": (_i, [_vp, _s, C.POINTER(PatchDesc), _pd, _i, _pi, _pi, _pd, _i, _i, _pd, _i, _i]),
+    "ibk_edge_interpolate_host": (_i, [_vp, _s, C.POINTER(PatchDesc), _ppd, _i, _pi, _pi, _pd, _i, _i, _pd, _i, _i]),
+    "ibk_edge_spread_host": (_i, [_vp, _s, C.POINTER(PatchDesc), _ppd, _i, _pi, _pi, _pd, _i, _i, _pd, _i, _i]),
     "ibk_side_interpolate_indexed_host": (_i, [_vp, _s, C.POINTER(PatchDesc), _ppd, _pi, _pd, _i, _pd, _i, _pd]),
     "ibk_side_spread_indexed_host": (_i, [_vp, _s, C.POINTER(PatchDesc), _ppd, _pi, _pd, _i, _pd, _i, _pd]),
     "ibk_level_create": (_i, [_vp, C.POINTER(LevelDesc)]),

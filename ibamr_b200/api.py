@@ -193,6 +193,54 @@ class CellData:
         self.array[...] = v
 
 
+class NodeData:
+    """pdat::NodeData<NDIM,double>: array of shape (depth, [n2+1,] n1+1, n0+1) over toNodeBox(box) grown by gcw."""
+
+    def __init__(self, box: Box, depth: int, gcw, array=None):
+        self.box, self.depth = box, depth
+        ndim = len(box.lower)
+        self.gcw = tuple(gcw) if np.ndim(gcw) else (int(gcw),) * ndim
+        n = [box.upper[d] - box.lower[d] + 2 + 2 * self.gcw[d] for d in range(ndim)]
+        shape = (depth,) + tuple(reversed(n))
+        self.array = np.zeros(shape) if array is None else np.ascontiguousarray(array, dtype=np.float64).reshape(shape)
+
+    def getDepth(self):
+        return self.depth
+
+    def getGhostCellWidth(self):
+        return self.gcw
+
+    def getPointer(self):
+        return self.array
+
+
+class EdgeData:
+    """pdat::EdgeData<NDIM,double>: one array per axis over toEdgeBox(box, axis) (one more point in every dimension but
+    the axis) grown by gcw."""
+
+    def __init__(self, box: Box, depth: int, gcw, arrays=None):
+        self.box, self.depth = box, depth
+        ndim = len(box.lower)
+        self.gcw = tuple(gcw) if np.ndim(gcw) else (int(gcw),) * ndim
+        if arrays is None:
+            arrays = [np.zeros(self.shape(axis)) for axis in range(ndim)]
+        self.arrays = [np.ascontiguousarray(a, dtype=np.float64) for a in arrays]
+
+    def shape(self, axis):
+        ndim = len(self.box.lower)
+        n = [self.box.upper[d] - self.box.lower[d] + 1 + (0 if d == axis else 1) + 2 * self.gcw[d] for d in range(ndim)]
+        return tuple(reversed(n))
+
+    def getDepth(self):
+        return self.depth
+
+    def getGhostCellWidth(self):
+        return self.gcw
+
+    def getPointer(self, axis):
+        return self.arrays[axis]
+
+
 def _patch_desc(patch: Patch, gcw) -> PatchDesc:
     pd = PatchDesc()
     ndim = patch.ndim
@@ -244,10 +292,15 @@ class LEInteractor:
         Q = Q_data.reshape(-1)
         pd = _patch_desc(patch, q_data.getGhostCellWidth())
         lo, hi = _i32(interp_box.lower), _i32(interp_box.upper)
-        if isinstance(q_data, SideData):
+        if isinstance(q_data, (SideData, EdgeData)):
             P = (C.POINTER(C.c_double) * patch.ndim)(*[_dp(a) for a in q_data.arrays])
-            rc = ctx.lib.ibk_side_interpolate_host(ctx.h, interp_fcn.encode(), C.byref(pd), P, q_data.getDepth(), _ip(lo),
-                                                   _ip(hi), _dp(X), X.size, X_depth, _dp(Q), Q.size, Q_depth)
+            fn = ctx.lib.ibk_side_interpolate_host if isinstance(q_data, SideData) else ctx.lib.ibk_edge_interpolate_host
+            rc = fn(ctx.h, interp_fcn.encode(), C.byref(pd), P, q_data.getDepth(), _ip(lo), _ip(hi), _dp(X), X.size, X_depth,
+                    _dp(Q), Q.size, Q_depth)
+        elif isinstance(q_data, NodeData):
+            rc = ctx.lib.ibk_node_interpolate_host(ctx.h, interp_fcn.encode(), C.byref(pd), _dp(q_data.array),
+                                                   q_data.getDepth(), _ip(lo), _ip(hi), _dp(X), X.size, X_depth, _dp(Q),
+                                                   Q.size, Q_depth)
         else:
             rc = ctx.lib.ibk_cell_interpolate_host(ctx.h, interp_fcn.encode(), C.byref(pd), _dp(q_data.array),
                                                    q_data.getDepth(), _ip(lo), _ip(hi), _dp(X), X.size, X_depth, _dp(Q),
@@ -262,10 +315,14 @@ class LEInteractor:
         Q = _f64(Q_data).reshape(-1)
         pd = _patch_desc(patch, q_data.getGhostCellWidth())
         lo, hi = _i32(spread_box.lower), _i32(spread_box.upper)
-        if isinstance(q_data, SideData):
+        if isinstance(q_data, (SideData, EdgeData)):
             P = (C.POINTER(C.c_double) * patch.ndim)(*[_dp(a) for a in q_data.arrays])
-            rc = ctx.lib.ibk_side_spread_host(ctx.h, spread_fcn.encode(), C.byref(pd), P, q_data.getDepth(), _ip(lo), _ip(hi),
-                                              _dp(X), X.size, X_depth, _dp(Q), Q.size, Q_depth)
+            fn = ctx.lib.ibk_side_spread_host if isinstance(q_data, SideData) else ctx.lib.ibk_edge_spread_host
+            rc = fn(ctx.h, spread_fcn.encode(), C.byref(pd), P, q_data.getDepth(), _ip(lo), _ip(hi), _dp(X), X.size, X_depth,
+                    _dp(Q), Q.size, Q_depth)
+        elif isinstance(q_data, NodeData):
+            rc = ctx.lib.ibk_node_spread_host(ctx.h, spread_fcn.encode(), C.byref(pd), _dp(q_data.array), q_data.getDepth(),
+                                              _ip(lo), _ip(hi), _dp(X), X.size, X_depth, _dp(Q), Q.size, Q_depth)
         else:
             rc = ctx.lib.ibk_cell_spread_host(ctx.h, spread_fcn.encode(), C.byref(pd), _dp(q_data.array), q_data.getDepth(),
                                               _ip(lo), _ip(hi), _dp(X), X.size, X_depth, _dp(Q), Q.size, Q_depth)

@@ -276,7 +276,7 @@ void make_tile_params(TileParams& tp, int ndim, const double* dx, const double x
 // and Xr (raw) of stride `stride`; values are addressed through d_indices (nullable).
 int run_entries_op(ibk_ctx* ctx, int op, int kernel, TileParams& tp, const CellGeom& cg, PatchBin& pb, const double* d_Xe,
                    const double* d_Xr, long long stride, int n_entries, const int* d_indices, double* d_V, long long v_cstride,
-                   long long v_istride)
+                   long long v_istride, bool zero_unreached = true)
 {
     if (n_entries <= 0) return IBK_OK;
     const int ndim = tp.ndim;
@@ -305,7 +305,10 @@ int run_entries_op(ibk_ctx* ctx, int op, int kernel, TileParams& tp, const CellG
     mv.v_istride = v_istride;
     mv.src = ctx->b_src.as<uint32_t>();
     std::string err;
-    if (op == 0)
+    // Index-list forms: a listed marker whose stencil finds no array point interpolates to 0 (the Fortran sets V = 0 and
+    // adds nothing).  Position-only forms: the markers outside the box are simply not listed, their entries stay as
+    // the caller left them (LEInteractor.cpp:6088-6126).
+    if (op == 0 && zero_unreached)
         CK(zero_discarded(ctx->L, ctx->sbins.brick_start, ctx->sbins.total_bricks, n_entries, mv.src, d_V, v_cstride, v_istride,
                           tp.ncomp));
     cudaError_t e = (op == 0) ? launch_interp(ctx->L, kernel, tp, ctx->sbins, mv, err) :
@@ -465,7 +468,9 @@ extern "C" int ibk_raw_spread_host(ibk_ctx* ctx, int kernel, const ibk_array_des
 // ---------------------------------------------------------------------------------------------
 // seam B3: patch-level LEInteractor calls on host data
 // ---------------------------------------------------------------------------------------------
-// centering: 0 = side (ndim arrays, one per axis), 1 = cell (one array with q_depth slices)
+// centering: 0 = side (ndim arrays, one per axis, shifted along the axis), 1 = cell (one array with q_depth slices),
+//            2 = node (one array with q_depth slices, shifted in every dimension; LEInteractor.cpp:2983-3043),
+//            3 = edge (ndim arrays, array `axis` shifted in every dimension but `axis`; LEInteractor.cpp:3260-3340)
 static int patch_host_op(ibk_ctx* ctx, int op, const char* fcn, const ibk_patch_desc* patch, int centering,
                          double* const* h_q, int q_depth, const int* box_lower, const int* box_upper,
                          const int* h_indices, const double* h_shifts, int n_indices, const double* h_X, int n_markers,
@@ -476,10 +481,14 @@ static int patch_host_op(ibk_ctx* ctx, int op, const char* fcn, const ibk_patch_
     if (kernel < 0) return fail(ctx, IBK_ERR_UNKNOWN_KERNEL, std::string("unknown kernel function ") + (fcn ? fcn : "(null)"));
     const int ndim = patch->ndim;
     if (ndim != 2 && ndim != 3) return fail(ctx, IBK_ERR_INVALID, "ndim must be 2 or 3");
-    if (centering == 0 && (Q_depth != ndim || q_depth != 1))
-        return fail(ctx, IBK_ERR_DEPTH, "side-centered interpolation/spreading requires vector-valued data");
-    if (centering == 1 && (Q_depth != q_depth || q_depth < 1 || q_depth > IBK_MAX_COMP))
-        return fail(ctx, IBK_ERR_DEPTH, "Q_depth must equal the CellData depth");
+    const bool per_axis = centering == 0 || centering == 3; // one array per axis, vector-valued Lagrangian data
+    if (per_axis && (Q_depth != ndim || q_depth != 1))
+        return fail(ctx, IBK_ERR_DEPTH, centering == 0 ? "side-centered interpolation/spreading requires vector-valued data" :
+                                                         "edge-centered interpolation/spreading requires vector-valued data");
+    if (!per_axis && (Q_depth != q_depth || q_depth < 1 || q_depth > IBK_MAX_COMP))
+        return fail(ctx, IBK_ERR_DEPTH, "Q_depth must equal the data depth");
+    // is dimension d of array a shifted by half a cell (index i at x_lower + i dx instead of x_lower + (i + 1/2) dx)?
+    auto shifted = [&](int a, int d) { return centering == 0 ? d == a : centering == 2 ? true : centering == 3 ? d != a : false; };
     // ghost-width validation: LEInteractor.cpp:4488-4498 (interp: always), :5250-5266 (spread: only
     // when the patch touches a physical boundary)
     const int min_ghosts = ibk_get_minimum_ghost_width(fcn);
@@ -502,7 +511,7 @@ static int patch_host_op(ibk_ctx* ctx, int op, const char* fcn, const ibk_patch_
     cudaStream_t st = ctx->L.stream;
 
     // ---- geometry
-    const int ncomp = centering == 0 ? ndim : q_depth;
+    const int ncomp = per_axis ? ndim : q_depth;
     ArrayComp comps[IBK_MAX_COMP];
     size_t off[IBK_MAX_COMP + 1];
     off[0] = 0;
@@ -510,9 +519,10 @@ static int patch_host_op(ibk_ctx* ctx, int op, const char* fcn, const ibk_patch_
     {
         for (int d = 0; d < 3; ++d)
         {
-            comps[a].n[d] = d < ndim ? patch->upper[d] - patch->lower[d] + 1 + 2 * patch->gcw[d] + ((centering == 0 && d == a) ? 1 : 0) : 1;
+            const int sh = (d < ndim && shifted(a, d)) ? 1 : 0;
+            comps[a].n[d] = d < ndim ? patch->upper[d] - patch->lower[d] + 1 + 2 * patch->gcw[d] + sh : 1;
             comps[a].nugc[d] = d < ndim ? patch->gcw[d] : 0;
-            comps[a].var[d] = (centering == 0 && d == a) ? 1 : 0;
+            comps[a].var[d] = sh;
         }
         comps[a].pitch = round_pitch(comps[a].n[0]);
         comps[a].vcol = a;
@@ -522,7 +532,7 @@ static int patch_host_op(ibk_ctx* ctx, int op, const char* fcn, const ibk_patch_
     for (int a = 0; a < ncomp; ++a)
     {
         comps[a].ptr = ctx->b_io[0].as<double>() + off[a];
-        const double* src = centering == 0 ? h_q[a] : h_q[0] + (size_t)a * comps[a].n[0] * comps[a].n[1] * comps[a].n[2];
+        const double* src = per_axis ? h_q[a] : h_q[0] + (size_t)a * comps[a].n[0] * comps[a].n[1] * comps[a].n[2];
         CK(copy_dense_to_pitched(ctx->L, src, comps[a].ptr, comps[a].pitch, comps[a].n, ndim, cudaMemcpyHostToDevice));
     }
     const int G = gmax + 4;
@@ -554,7 +564,7 @@ static int patch_host_op(ibk_ctx* ctx, int op, const char* fcn, const ibk_patch_
         cg.iupper[d] = patch->upper[d];
         xl[d][0] = patch->x_lower[d];
         xl[d][1] = patch->x_lower[d] - 0.5 * patch->dx[d]; // x_lower_axis[axis] -= 0.5 * dx[axis], LEInteractor.cpp:2464
-        nvar[d] = centering == 0 ? 2 : 1;
+        nvar[d] = centering == 1 ? 1 : 2;
     }
     TileParams tp;
     make_tile_params(tp, ndim, patch->dx, xl, nvar, pb, ncomp, comps);
@@ -583,7 +593,7 @@ static int patch_host_op(ibk_ctx* ctx, int op, const char* fcn, const ibk_patch_
     CK(build_entries(ctx->L, ctx->b_io[3].as<double>(), d_idx, d_shift, n_entries, ndim, ctx->b_Xe.as<double>(),
                      ctx->b_Xr.as<double>(), n_entries));
     int rc = run_entries_op(ctx, op, kernel, tp, cg, pb, ctx->b_Xe.as<double>(), d_shift ? ctx->b_Xr.as<double>() : nullptr,
-                            n_entries, n_entries, d_idx, ctx->b_io[4].as<double>(), 1, Q_depth);
+                            n_entries, n_entries, d_idx, ctx->b_io[4].as<double>(), 1, Q_depth, /*zero_unreached*/ indexed);
     if (rc != IBK_OK) return rc;
     if (op == 0)
     {
@@ -593,7 +603,7 @@ static int patch_host_op(ibk_ctx* ctx, int op, const char* fcn, const ibk_patch_
     {
         for (int a = 0; a < ncomp; ++a)
         {
-            double* dst = centering == 0 ? h_q[a] : h_q[0] + (size_t)a * comps[a].n[0] * comps[a].n[1] * comps[a].n[2];
+            double* dst = per_axis ? h_q[a] : h_q[0] + (size_t)a * comps[a].n[0] * comps[a].n[1] * comps[a].n[2];
             CK(copy_pitched_to_dense(ctx->L, comps[a].ptr, comps[a].pitch, dst, comps[a].n, ndim, cudaMemcpyDeviceToHost));
         }
     }
@@ -640,6 +650,48 @@ extern "C" int ibk_cell_spread_host(ibk_ctx* ctx, const char* fcn, const ibk_pat
     if (X_depth != patch->ndim) return fail(ctx, IBK_ERR_INVALID, "X_depth must be NDIM");
     (void)Q_size;
     return patch_host_op(ctx, 1, fcn, patch, 1, &h_q, q_depth, box_lower, box_upper, nullptr, nullptr, 0, h_X, X_size / X_depth,
+                         const_cast<double*>(h_Q), Q_depth);
+}
+// NodeData (one array, any depth) and EdgeData (one array per axis, vector-valued), position-only overloads
+extern "C" int ibk_node_interpolate_host(ibk_ctx* ctx, const char* fcn, const ibk_patch_desc* patch, const double* h_q,
+                                         int q_depth, const int* box_lower, const int* box_upper, const double* h_X, int X_size,
+                                         int X_depth, double* h_Q, int Q_size, int Q_depth)
+{
+    if (!patch) return IBK_ERR_INVALID;
+    if (X_depth != patch->ndim) return fail(ctx, IBK_ERR_INVALID, "X_depth must be NDIM");
+    (void)Q_size;
+    double* q = const_cast<double*>(h_q);
+    return patch_host_op(ctx, 0, fcn, patch, 2, &q, q_depth, box_lower, box_upper, nullptr, nullptr, 0, h_X, X_size / X_depth,
+                         h_Q, Q_depth);
+}
+extern "C" int ibk_node_spread_host(ibk_ctx* ctx, const char* fcn, const ibk_patch_desc* patch, double* h_q, int q_depth,
+                                    const int* box_lower, const int* box_upper, const double* h_X, int X_size, int X_depth,
+                                    const double* h_Q, int Q_size, int Q_depth)
+{
+    if (!patch) return IBK_ERR_INVALID;
+    if (X_depth != patch->ndim) return fail(ctx, IBK_ERR_INVALID, "X_depth must be NDIM");
+    (void)Q_size;
+    return patch_host_op(ctx, 1, fcn, patch, 2, &h_q, q_depth, box_lower, box_upper, nullptr, nullptr, 0, h_X, X_size / X_depth,
+                         const_cast<double*>(h_Q), Q_depth);
+}
+extern "C" int ibk_edge_interpolate_host(ibk_ctx* ctx, const char* fcn, const ibk_patch_desc* patch, const double* const* h_q,
+                                         int q_depth, const int* box_lower, const int* box_upper, const double* h_X, int X_size,
+                                         int X_depth, double* h_Q, int Q_size, int Q_depth)
+{
+    if (!patch) return IBK_ERR_INVALID;
+    if (X_depth != patch->ndim) return fail(ctx, IBK_ERR_INVALID, "X_depth must be NDIM");
+    (void)Q_size;
+    return patch_host_op(ctx, 0, fcn, patch, 3, const_cast<double* const*>(h_q), q_depth, box_lower, box_upper, nullptr,
+                         nullptr, 0, h_X, X_size / X_depth, h_Q, Q_depth);
+}
+extern "C" int ibk_edge_spread_host(ibk_ctx* ctx, const char* fcn, const ibk_patch_desc* patch, double* const* h_q, int q_depth,
+                                    const int* box_lower, const int* box_upper, const double* h_X, int X_size, int X_depth,
+                                    const double* h_Q, int Q_size, int Q_depth)
+{
+    if (!patch) return IBK_ERR_INVALID;
+    if (X_depth != patch->ndim) return fail(ctx, IBK_ERR_INVALID, "X_depth must be NDIM");
+    (void)Q_size;
+    return patch_host_op(ctx, 1, fcn, patch, 3, h_q, q_depth, box_lower, box_upper, nullptr, nullptr, 0, h_X, X_size / X_depth,
                          const_cast<double*>(h_Q), Q_depth);
 }
 extern "C" int ibk_side_interpolate_indexed_host(ibk_ctx* ctx, const char* fcn, const ibk_patch_desc* patch,

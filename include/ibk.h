@@ -226,6 +226,21 @@ int ibk_cell_spread_host(ibk_ctx* ctx,
                          const double* h_Q,
                          int Q_size,
                          int Q_depth);
+/* NodeData (one array over toNodeBox(box), any depth, index i at x_lower + i dx in every dimension; LEInteractor.cpp:2983-3043,
+ * 4122-4186) and EdgeData (one array per axis over toEdgeBox(box, axis), shifted in every dimension but the axis, vector-valued
+ * Lagrangian data; LEInteractor.cpp:3260-3340, 4386-4466), position-only forms.  N4 of SURVEY.md 8(f). */
+int ibk_node_interpolate_host(ibk_ctx* ctx, const char* interp_fcn, const ibk_patch_desc* patch, const double* h_q, int q_depth,
+                              const int* box_lower, const int* box_upper, const double* h_X, int X_size, int X_depth, double* h_Q,
+                              int Q_size, int Q_depth);
+int ibk_node_spread_host(ibk_ctx* ctx, const char* spread_fcn, const ibk_patch_desc* patch, double* h_q, int q_depth,
+                         const int* box_lower, const int* box_upper, const double* h_X, int X_size, int X_depth, const double* h_Q,
+                         int Q_size, int Q_depth);
+int ibk_edge_interpolate_host(ibk_ctx* ctx, const char* interp_fcn, const ibk_patch_desc* patch, const double* const* h_q,
+                              int q_depth, const int* box_lower, const int* box_upper, const double* h_X, int X_size, int X_depth,
+                              double* h_Q, int Q_size, int Q_depth);
+int ibk_edge_spread_host(ibk_ctx* ctx, const char* spread_fcn, const ibk_patch_desc* patch, double* const* h_q, int q_depth,
+                         const int* box_lower, const int* box_upper, const double* h_X, int X_size, int X_depth, const double* h_Q,
+                         int Q_size, int Q_depth);
 /* Index-set SideData forms (LEInteractor.h:184-192, 704-712; .cpp:2402-2489, 3627-3714): the
  * caller passes the flat lists LIndexSetData caches (local PETSc indices + periodic shifts). */
 int ibk_side_interpolate_indexed_host(ibk_ctx* ctx,

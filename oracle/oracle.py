@@ -248,6 +248,58 @@ def cell_spread_positions(kernel, pg, u_cell, depth, X, Q, box_lower=None, box_u
                       pg.gcw, u_cell)
 
 
+def _shifted_geom(pg, shifted):
+    """Array geometry the private funnel receives for a centering (LEInteractor.cpp:3021-3026 node, :3313-3323 edge):
+    x_lower - dx/2 and one more index in every shifted dimension."""
+    xl = [pg.x_lower[d] - (0.5 * pg.dx[d] if shifted[d] else 0.0) for d in range(pg.ndim)]
+    up = [pg.upper[d] + (1 if shifted[d] else 0) for d in range(pg.ndim)]
+    return xl, up
+
+
+def node_interp_positions(kernel, pg, u_node, depth, X):
+    """Position-only NodeData interpolate (LEInteractor.cpp:2983-3043); u_node shape (depth, [n2+1,] n1+1, n0+1)."""
+    idx = indices_in_box(X, pg, pg.lower, pg.upper)
+    ndim = pg.ndim
+    xl, up = _shifted_geom(pg, [True] * ndim)
+    V = np.full((np.asarray(X).size // ndim, depth), np.finfo(np.float64).max)
+    return interp_raw(kernel, ndim, pg.dx, xl, depth, pg.lower, up, pg.gcw, u_node, idx, np.zeros(idx.size * ndim), X, V)
+
+
+def node_spread_positions(kernel, pg, u_node, depth, X, Q):
+    """Position-only NodeData spread (LEInteractor.cpp:4122-4186)."""
+    idx = indices_in_box(X, pg, pg.lower, pg.upper)
+    ndim = pg.ndim
+    xl, up = _shifted_geom(pg, [True] * ndim)
+    return spread_raw(kernel, ndim, pg.dx, xl, depth, idx, np.zeros(idx.size * ndim), X, Q, pg.lower, up, pg.gcw, u_node)
+
+
+def edge_interp_positions(kernel, pg, u_edges, X):
+    """Position-only EdgeData interpolate (LEInteractor.cpp:3260-3340): per axis a scalar interpolation on the array
+    shifted in every dimension but the axis; listed markers get component `axis` of Q."""
+    idx = indices_in_box(X, pg, pg.lower, pg.upper)
+    ndim = pg.ndim
+    n = np.asarray(X).size // ndim
+    Q = np.full((n, ndim), np.finfo(np.float64).max)
+    for axis in range(ndim):
+        xl, up = _shifted_geom(pg, [d != axis for d in range(ndim)])
+        V = np.full((n, 1), np.finfo(np.float64).max)
+        interp_raw(kernel, ndim, pg.dx, xl, 1, pg.lower, up, pg.gcw, u_edges[axis], idx, np.zeros(idx.size * ndim), X, V)
+        Q[:, axis] = V[:, 0]
+    return Q
+
+
+def edge_spread_positions(kernel, pg, u_edges, X, Q):
+    """Position-only EdgeData spread (LEInteractor.cpp:4386-4466)."""
+    idx = indices_in_box(X, pg, pg.lower, pg.upper)
+    ndim = pg.ndim
+    Q = _f64(Q).reshape(-1, ndim)
+    for axis in range(ndim):
+        xl, up = _shifted_geom(pg, [d != axis for d in range(ndim)])
+        spread_raw(kernel, ndim, pg.dx, xl, 1, idx, np.zeros(idx.size * ndim), X, np.ascontiguousarray(Q[:, axis:axis + 1]), pg.lower,
+                   up, pg.gcw, u_edges[axis])
+    return u_edges
+
+
 # ----------------------------------------------------------------------------------------------
 # level = set of patches on one refinement level of a Cartesian domain
 # ----------------------------------------------------------------------------------------------

@@ -234,6 +234,59 @@ def _side_fields(pg, seed):
 
 
 @pytest.mark.parametrize("ndim", [2, 3])
+@pytest.mark.parametrize("kernel", ["IB_4", "IB_6", "BSPLINE_3", "PIECEWISE_LINEAR", "BSPLINE_5"])
+def test_node_and_edge_centerings_vs_oracle(api, kernel, ndim):
+    """NodeData (depth 2, shifted in every dimension) and EdgeData (per axis, shifted in every dimension but the axis)
+    position-only interpolate / spread (LEInteractor.cpp:2983-3043, 3260-3340, 4122-4186, 4386-4466) against the oracle
+    driven with the same shifted array geometry; markers also outside the patch (not listed: untouched)."""
+    g = orc.min_ghost_width(kernel)
+    n = 20
+    lo, hi = (4,) * ndim, (4 + n - 1,) * ndim
+    dx = (1.0 / 32,) * ndim
+    xl = tuple(dx[d] * lo[d] for d in range(ndim))
+    xu = tuple(dx[d] * (hi[d] + 1) for d in range(ndim))
+    pg = orc.PatchGeom(lo, hi, xl, xu, dx, (g,) * ndim)
+    box = api.Box(lo, hi)
+    patch = api.Patch(box, xl, xu, dx)
+    N = 4000
+    X = np.stack([_uniform(53 + d, N, xl[d] - 2 * dx[d], xu[d] + 2 * dx[d]) for d in range(ndim)], axis=1)
+    sentinel = 123.25
+    # ---- node
+    depth = 2
+    qn = api.NodeData(box, depth, g)
+    qn.array[...] = _uniform(61, qn.array.size, -1.0, 1.0).reshape(qn.array.shape)
+    Qo = orc.node_interp_positions(kernel, pg, qn.array, depth, X)
+    Q = np.full((N, depth), np.finfo(np.float64).max)
+    api.LEInteractor.interpolate(Q, depth, X, ndim, qn, patch, box, kernel)
+    assert relerr(Q, Qo) <= TOL
+    F = np.stack([_uniform(70 + d, N, -1.0, 1.0) for d in range(depth)], axis=1)
+    fo = np.zeros_like(qn.array)
+    orc.node_spread_positions(kernel, pg, fo, depth, X, F)
+    qs = api.NodeData(box, depth, g)
+    api.LEInteractor.spread(qs, F, depth, X, ndim, patch, box, kernel)
+    assert relerr(qs.array, fo) <= TOL and np.any(fo != 0.0)
+    # ---- edge
+    qe = api.EdgeData(box, 1, g)
+    for a in range(ndim):
+        qe.arrays[a][...] = _uniform(80 + a, qe.arrays[a].size, -1.0, 1.0).reshape(qe.arrays[a].shape)
+    Qo = orc.edge_interp_positions(kernel, pg, qe.arrays, X)
+    Q = np.full((N, ndim), np.finfo(np.float64).max)
+    api.LEInteractor.interpolate(Q, ndim, X, ndim, qe, patch, box, kernel)
+    assert relerr(Q, Qo) <= TOL
+    Fe = np.stack([_uniform(90 + d, N, -1.0, 1.0) for d in range(ndim)], axis=1)
+    eo = [np.zeros_like(a) for a in qe.arrays]
+    orc.edge_spread_positions(kernel, pg, eo, X, Fe)
+    qs = api.EdgeData(box, 1, g)
+    api.LEInteractor.spread(qs, Fe, ndim, X, ndim, patch, box, kernel)
+    for a in range(ndim):
+        assert relerr(qs.arrays[a], eo[a]) <= TOL and np.any(eo[a] != 0.0)
+    # edge data is vector-valued: a scalar Q is refused like the reference does
+    with pytest.raises(api.IBKError) as e:
+        api.LEInteractor.interpolate(np.zeros((N, 1)), 1, X, ndim, qe, patch, box, kernel)
+    assert e.value.code == api.IBK_ERR_DEPTH
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_side_positions_vs_oracle(api, kernel, ndim):
     g = orc.min_ghost_width(kernel)
