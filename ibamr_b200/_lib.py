@@ -112,6 +112,7 @@ SYMBOLS = {
     "ibk_migrate_unpack": (_i, [_vp, _vp, _i, C.c_uint]),
     "ibk_markers_lincomb": (_i, [_vp, _i, _d, _i, _d, _i]),
     "ibk_markers_zero_rows": (_i, [_vp, _i, _pi, _i]),
+    "ibk_markers_scale_rows": (_i, [_vp, _i, _i, _pd]),
     "ibk_force_set_springs": (_i, [_vp, _i, _pi, _pi, _pd, _pd]),
     "ibk_force_set_beams": (_i, [_vp, _i, _pi, _pi, _pi, _pd, _pd]),
     "ibk_force_set_target_points": (_i, [_vp, _i, _pi, _pd, _pd, _pd]),

@@ -540,6 +540,12 @@ class IBMethodB200:
         """IBMethod::computeLagrangianForce (IBMethod.cpp:834-858): F = springs + beams + target points."""
         self.ctx.check(self.ctx.lib.ibk_compute_lagrangian_force(self.ctx.h, COLUMNS[x], COLUMNS[u], COLUMNS[f]))
 
+    def scaleRows(self, dst, src, ds):
+        """dst = src * ds row by row: the F * ds product of LDataManager::spread (LDataManager.cpp:416-447)."""
+        w = _f64(ds).reshape(-1)
+        assert w.size == self.n_markers
+        self.ctx.check(self.ctx.lib.ibk_markers_scale_rows(self.ctx.h, COLUMNS[dst], COLUMNS[src], _dp(w)))
+
     def resetAnchorPointValues(self, name, anchor_idx):
         """IBMethod::resetAnchorPointValues (IBMethod.cpp:1915-1943): zero the rows of the anchored nodes."""
         a = _i32(anchor_idx)

@@ -142,6 +142,8 @@ cudaError_t launch_lagrangian_force(Launcher& L, int ndim, const ForceTables& t,
 cudaError_t launch_pos_of_id(Launcher& L, const uint32_t* id_of_pos, int n, int* pos_of_id, int id_bound);
 cudaError_t launch_lincomb(Launcher& L, double* dst, double alpha, const double* a, double beta, const double* b, long long stride,
                            int n, int ndim);
+cudaError_t launch_scale_rows(Launcher& L, double* dst, const double* src, long long stride, int n, int ndim, const double* d_ds,
+                              const uint32_t* row_of_pos);
 cudaError_t launch_zero_rows(Launcher& L, double* col, long long stride, int ndim, const int* d_ids, int n_ids, const int* pos_of_id,
                              int id_bound);
 

@@ -155,6 +155,29 @@ cudaError_t launch_lincomb(Launcher& L, double* dst, double alpha, const double*
     return cudaGetLastError();
 }
 
+// dst[d][i] = src[d][i] * ds[row(i)]: the F * ds product of LDataManager::spread (LDataManager.cpp:416-447); ds is given
+// per host row (Lagrangian order), row_of_pos maps the storage position to it
+__global__ void scale_rows_kernel(double* __restrict__ dst, const double* __restrict__ src, long long stride, int n, int ndim,
+                                  const double* __restrict__ ds, const uint32_t* __restrict__ row_of_pos)
+{
+    const long long total = (long long)n * ndim;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int d = (int)(q / n), i = (int)(q - (long long)d * n);
+        dst[d * stride + i] = __dmul_rn(src[d * stride + i], ds[row_of_pos[i]]);
+    }
+}
+cudaError_t launch_scale_rows(Launcher& L, double* dst, const double* src, long long stride, int n, int ndim, const double* d_ds,
+                              const uint32_t* row_of_pos)
+{
+    if (n <= 0) return cudaSuccess;
+    const long long total = (long long)n * ndim;
+    scale_rows_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, L.stream>>>(dst, src, stride, n, ndim, d_ds,
+                                                                                                       row_of_pos);
+    L.launches++;
+    return cudaGetLastError();
+}
+
 __global__ void zero_rows_kernel(double* __restrict__ col, long long stride, int ndim, const int* __restrict__ ids, int n_ids,
                                  const int* __restrict__ pos_of_id, int id_bound)
 {

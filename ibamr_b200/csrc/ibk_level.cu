@@ -1351,6 +1351,22 @@ extern "C" int ibk_markers_lincomb(ibk_ctx* ctx, int dst, double alpha, int a, d
     return IBK_OK;
 }
 
+extern "C" int ibk_markers_scale_rows(ibk_ctx* ctx, int dst, int src, const double* h_ds)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    for (int c : { dst, src })
+        if (int rc = ensure_column(ctx, c)) return rc;
+    if (!h_ds && lv.n > 0) return fail(ctx, IBK_ERR_INVALID, "null weight array");
+    if (lv.n == 0) return IBK_OK;
+    CK(ctx->b_io[7].reserve(sizeof(double) * (size_t)lv.n));
+    CK(cudaMemcpyAsync(ctx->b_io[7].p, h_ds, sizeof(double) * (size_t)lv.n, cudaMemcpyHostToDevice, ctx->L.stream));
+    CK(launch_scale_rows(ctx->L, column_of(lv, dst), column_of(lv, src), lv.stride, lv.n, lv.ndim, ctx->b_io[7].as<double>(), lv.lag));
+    CK(cudaStreamSynchronize(ctx->L.stream)); // h_ds is the caller's (pageable) memory
+    if (dst == 0) lv.binned = false;
+    return IBK_OK;
+}
+
 extern "C" int ibk_markers_zero_rows(ibk_ctx* ctx, int which, const int* lag_idx, int n)
 {
     NEED_LEVEL();

@@ -371,6 +371,9 @@ enum
 };
 int ibk_markers_lincomb(ibk_ctx* ctx, int dst, double alpha, int a, double beta, int b);
 int ibk_markers_zero_rows(ibk_ctx* ctx, int which, const int* lag_idx, int n);
+/* dst = src * ds row by row (h_ds[n], host-row order): the F * ds product LDataManager::spread forms when it is given a
+ * node-weight LData (LDataManager.cpp:416-447). */
+int ibk_markers_scale_rows(ibk_ctx* ctx, int dst, int src, const double* h_ds);
 int ibk_force_set_springs(ibk_ctx* ctx, int n, const int* master, const int* slave, const double* kappa, const double* rest_length);
 int ibk_force_set_beams(ibk_ctx* ctx, int n, const int* curr, const int* next, const int* prev, const double* rigidity,
                         const double* curvature);

@@ -8,7 +8,8 @@
 // out.bin : double Q[N][3] (LEInteractor::interpolate), per-axis f arrays (LEInteractor::spread into zero),
 //           double U[N][3] (IBMethodB200::interpolateVelocity), per-axis f arrays (IBMethodB200::spreadForce),
 //           double Fl[N][3] (computeLagrangianForce for a closed ring of springs i -> i+1, kappa 1.5, rest 0.01, and
-//           target points on every 7th marker), double Xnew[N][3] (forwardEulerStep with dt = 0.01)
+//           target points on every 7th marker), double Xnew[N][3] (forwardEulerStep with dt = 0.01), double ok (1.0 if the
+//           LDataB200 host mirror of the F column behaved: read, modify + restore, refetch after a kernel)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,6 +19,7 @@
 #define NDIM 3
 #include "../../ibamr_b200/host/IBMethodB200.h"
 #include "../../ibamr_b200/host/IBStandardInitializerB200.h"
+#include "../../ibamr_b200/host/LDataB200.h"
 #include "../../ibamr_b200/host/LEInteractorB200.h"
 
 using namespace SAMRAI_standin;
@@ -156,6 +158,34 @@ int main(int argc, char** argv)
         ib.forwardEulerStep(0.0, 0.01);
         ib.getColumn(IBK_COL_X_NEW, Xnew);
         std::fwrite(Xnew.data(), 8, Xnew.size(), fo);
+        // seam B2: LData-shaped lazy host mirror of the F column: read, modify on the host, restore, recompute
+        IBTK_B200::LDataB200 Fdata("F", ib.ctx(), IBK_COL_F, 3);
+        const IBTK_B200::LDataB200& Fconst = Fdata;
+        const double* f_ro = Fconst.getLocalFormVecArray();
+        int ok = 1;
+        for (size_t k = 0; k < Fl.size(); ++k) ok &= (f_ro[k] == Fl[k]);
+        ok &= Fdata.hostCopyIsCurrent() ? 1 : 0;
+        double* f_rw = Fdata.getLocalFormVecArray();
+        for (size_t k = 0; k < Fl.size(); ++k) f_rw[k] = 2.0 * f_rw[k];
+        Fdata.restoreArrays();
+        std::vector<double> F2;
+        ib.getColumn(IBK_COL_F, F2);
+        for (size_t k = 0; k < Fl.size(); ++k) ok &= (F2[k] == 2.0 * Fl[k]);
+        ib.computeLagrangianForce(); // a kernel rewrites the column: the mirror must refetch
+        Fdata.markDeviceModified();
+        ok &= Fdata.hostCopyIsCurrent() ? 0 : 1;
+        const double* f_again = Fconst.getLocalFormVecArray();
+        std::vector<double> F3; // X is the midpoint position by now, so this is a new force, not Fl
+        ib.getColumn(IBK_COL_F, F3);
+        int changed = 0;
+        for (size_t k = 0; k < Fl.size(); ++k)
+        {
+            ok &= (f_again[k] == F3[k]);
+            changed |= (F3[k] != F2[k]);
+        }
+        ok &= changed;
+        const double okd = (double)ok;
+        std::fwrite(&okd, 8, 1, fo);
     }
     catch (const std::exception& e)
     {

@@ -100,6 +100,9 @@ def test_column_algebra_and_anchor_rows(api):
     U2 = U.copy()
     U2[anchors] = 0.0
     assert np.array_equal(ib.getLData("U"), U2)
+    ds = _u(420, N, 0.5, 2.0)
+    ib.scaleRows("aux", "U", ds)  # F * ds of LDataManager::spread, here on U
+    assert np.array_equal(ib.getLData("aux"), U2 * ds[:, None])
     ib.postprocessIntegrateData()
     assert np.array_equal(ib.getLData("X"), Xn)
     with pytest.raises(api.IBKError):

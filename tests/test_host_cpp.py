@@ -114,6 +114,8 @@ def test_cpp_host_mirror_vs_oracle(driver, kernel, tmp_path):
     # N1 through the C++ mirror: computeLagrangianForce (ring of springs + target points) and forwardEulerStep
     Fl = raw[off:off + 3 * N].reshape(N, 3); off += 3 * N
     Xnew = raw[off:off + 3 * N].reshape(N, 3); off += 3 * N
+    assert raw[off] == 1.0, "LDataB200: lazy host mirror (read, modify + restore, refetch after a kernel)"
+    off += 1
     assert off == raw.size
     Xw, _ = orc.wrap_positions(X, level.x_lower, level.x_upper, level.periodic)
     Xw = Xw.reshape(N, 3)
