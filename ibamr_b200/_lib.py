@@ -24,6 +24,7 @@ class ArrayDesc(C.Structure):
         ("ilower", C.c_int * 3),
         ("iupper", C.c_int * 3),
         ("nugc", C.c_int * 3),
+        ("axis", C.c_int),
     ]
 
 

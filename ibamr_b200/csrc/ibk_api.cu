@@ -66,6 +66,16 @@ extern "C" int ibk_kernel_from_string(const char* s)
     if (!strcmp(s, "PIECEWISE_CUBIC")) return IBK_PIECEWISE_CUBIC;
     if (!strcmp(s, "IB_5")) return IBK_IB_5;
     if (!strcmp(s, "PIECEWISE_CONSTANT")) return IBK_PIECEWISE_CONSTANT;
+    if (!strcmp(s, "COMPOSITE_BSPLINE_32")) return IBK_COMPOSITE_BSPLINE_32;
+    if (!strcmp(s, "COMPOSITE_BSPLINE_23")) return IBK_COMPOSITE_BSPLINE_23;
+    if (!strcmp(s, "COMPOSITE_BSPLINE_43")) return IBK_COMPOSITE_BSPLINE_43;
+    if (!strcmp(s, "COMPOSITE_BSPLINE_34")) return IBK_COMPOSITE_BSPLINE_34;
+    if (!strcmp(s, "COMPOSITE_BSPLINE_54")) return IBK_COMPOSITE_BSPLINE_54;
+    if (!strcmp(s, "COMPOSITE_BSPLINE_45")) return IBK_COMPOSITE_BSPLINE_45;
+    if (!strcmp(s, "COMPOSITE_BSPLINE_65")) return IBK_COMPOSITE_BSPLINE_65;
+    if (!strcmp(s, "COMPOSITE_BSPLINE_56")) return IBK_COMPOSITE_BSPLINE_56;
+    if (!strcmp(s, "DISCONTINUOUS_LINEAR")) return IBK_DISCONTINUOUS_LINEAR;
+    if (!strcmp(s, "IB_4_W8")) return IBK_IB_4_W8;
     return IBK_ERR_UNKNOWN_KERNEL;
 }
 extern "C" int ibk_is_known_kernel(const char* s)
@@ -98,6 +108,21 @@ extern "C" int ibk_get_stencil_size(const char* s)
         return 6;
     case IBK_PIECEWISE_CONSTANT:
         return 1;
+    case IBK_COMPOSITE_BSPLINE_32:
+    case IBK_COMPOSITE_BSPLINE_23:
+    case IBK_COMPOSITE_BSPLINE_43:
+    case IBK_COMPOSITE_BSPLINE_34:
+        return 4;
+    case IBK_COMPOSITE_BSPLINE_54:
+    case IBK_COMPOSITE_BSPLINE_45:
+        return 5;
+    case IBK_COMPOSITE_BSPLINE_65:
+    case IBK_COMPOSITE_BSPLINE_56:
+        return 6;
+    case IBK_DISCONTINUOUS_LINEAR:
+        return 2;
+    case IBK_IB_4_W8:
+        return 8;
     default:
         return IBK_ERR_UNKNOWN_KERNEL;
     }
@@ -232,6 +257,7 @@ struct ArrayComp
     int nugc[3];
     int var[3];
     int vcol;
+    int axis;
 };
 
 void make_tile_params(TileParams& tp, int ndim, const double* dx, const double xl[3][2], const int* nvar, const PatchBin& pb,
@@ -263,6 +289,7 @@ void make_tile_params(TileParams& tp, int ndim, const double* dx, const double x
         c.ptr = comps[a].ptr;
         c.pitch = comps[a].pitch;
         c.vcol = comps[a].vcol;
+        c.axis = comps[a].axis;
         for (int d = 0; d < 3; ++d)
         {
             c.n[d] = d < ndim ? comps[a].n[d] : 1;
@@ -325,7 +352,7 @@ static int raw_op(ibk_ctx* ctx, int op, int kernel, const ibk_array_desc* desc, 
                   const int* d_indices, const double* d_Xshift, int nindices, const double* d_X, int n_markers, double* d_V)
 {
     if (!ctx || !desc) return IBK_ERR_INVALID;
-    if (kernel < 0 || kernel > IBK_PIECEWISE_CONSTANT) return fail(ctx, IBK_ERR_UNKNOWN_KERNEL, "unknown kernel");
+    if (kernel < 0 || kernel > IBK_KERNEL_LAST) return fail(ctx, IBK_ERR_UNKNOWN_KERNEL, "unknown kernel");
     const int ndim = desc->ndim;
     if (ndim != 2 && ndim != 3) return fail(ctx, IBK_ERR_INVALID, "ndim must be 2 or 3");
     if (desc->depth < 1 || desc->depth > IBK_MAX_COMP) return fail(ctx, IBK_ERR_INVALID, "depth out of range");
@@ -346,6 +373,7 @@ static int raw_op(ibk_ctx* ctx, int op, int kernel, const ibk_array_desc* desc, 
         comps[c].ptr = d_u + (size_t)c * plane;
         comps[c].pitch = pitch;
         comps[c].vcol = c;
+        comps[c].axis = desc->axis;
         for (int d = 0; d < 3; ++d)
         {
             comps[c].n[d] = n[d];
@@ -526,6 +554,7 @@ static int patch_host_op(ibk_ctx* ctx, int op, const char* fcn, const ibk_patch_
         }
         comps[a].pitch = round_pitch(comps[a].n[0]);
         comps[a].vcol = a;
+        comps[a].axis = per_axis ? a : 0; // LEInteractor passes the SideData / EdgeData axis, 0 for Cell / Node data
         off[a + 1] = off[a] + (size_t)comps[a].pitch * comps[a].n[1] * comps[a].n[2];
     }
     CK(ctx->b_io[0].reserve(sizeof(double) * off[ncomp]));

@@ -80,6 +80,58 @@ struct KTraits<IBK_PIECEWISE_CONSTANT>
 {
     static constexpr int W = 1, M = 1;
 };
+// N4, second part: kernels whose 1-D function depends on whether the dimension is the component's axis
+// (3d.f.m4:237-490, 3510-5460) and the 8-point ib_4.  Index rules are those of the wider member of the pair.
+template <>
+struct KTraits<IBK_COMPOSITE_BSPLINE_32>
+{
+    static constexpr int W = 3, M = 2;
+};
+template <>
+struct KTraits<IBK_COMPOSITE_BSPLINE_23>
+{
+    static constexpr int W = 3, M = 2;
+};
+template <>
+struct KTraits<IBK_COMPOSITE_BSPLINE_43>
+{
+    static constexpr int W = 4, M = 2;
+};
+template <>
+struct KTraits<IBK_COMPOSITE_BSPLINE_34>
+{
+    static constexpr int W = 4, M = 2;
+};
+template <>
+struct KTraits<IBK_COMPOSITE_BSPLINE_54>
+{
+    static constexpr int W = 5, M = 3;
+};
+template <>
+struct KTraits<IBK_COMPOSITE_BSPLINE_45>
+{
+    static constexpr int W = 5, M = 3;
+};
+template <>
+struct KTraits<IBK_COMPOSITE_BSPLINE_65>
+{
+    static constexpr int W = 6, M = 3;
+};
+template <>
+struct KTraits<IBK_COMPOSITE_BSPLINE_56>
+{
+    static constexpr int W = 6, M = 3;
+};
+template <>
+struct KTraits<IBK_DISCONTINUOUS_LINEAR>
+{
+    static constexpr int W = 2, M = 1; // off the axis: the centre cell with weight 1 and a second point with weight 0
+};
+template <>
+struct KTraits<IBK_IB_4_W8>
+{
+    static constexpr int W = 8, M = 4;
+};
 
 // Fortran NINT (round half away from zero).
 __device__ __forceinline__ int nint_f(double x)
@@ -149,14 +201,55 @@ __device__ __forceinline__ double piecewise_cubic_delta(double r)
     return 0.0;
 }
 
+// lagrangian_delta.f.m4:29-45
+__device__ __forceinline__ double piecewise_linear_delta(double r)
+{
+    r = fabs(r);
+    return (r < 1.0) ? 1.0 - r : 0.0;
+}
+// the B-spline of order `order` (2 = piecewise linear)
+template <int order>
+__device__ __forceinline__ double bspline_delta(double r)
+{
+    if constexpr (order == 2) return piecewise_linear_delta(r);
+    if constexpr (order == 3) return bspline_3_delta(r);
+    if constexpr (order == 4) return bspline_4_delta(r);
+    if constexpr (order == 5) return bspline_5_delta(r);
+    return bspline_6_delta(r);
+}
+// COMPOSITE_BSPLINE_<A><B>: order A along the component's axis, order B in the other dimensions
+template <int K>
+struct CompositeOrders
+{
+    static constexpr bool is = false;
+    static constexpr int A = 0, B = 0;
+};
+#define IBK_COMPOSITE(AA, BB)                            \
+    template <>                                          \
+    struct CompositeOrders<IBK_COMPOSITE_BSPLINE_##AA##BB> \
+    {                                                    \
+        static constexpr bool is = true;                 \
+        static constexpr int A = AA, B = BB;             \
+    };
+IBK_COMPOSITE(3, 2)
+IBK_COMPOSITE(2, 3)
+IBK_COMPOSITE(4, 3)
+IBK_COMPOSITE(3, 4)
+IBK_COMPOSITE(5, 4)
+IBK_COMPOSITE(4, 5)
+IBK_COMPOSITE(6, 5)
+IBK_COMPOSITE(5, 6)
+#undef IBK_COMPOSITE
+
 // One dimension of a stencil.  Inputs: Xs = X + Xshift, Xraw = X (BSPLINE_4 quirk), x_lower and
 // dx of the array, all exactly as the Fortran receives them.  Output: `lo` = first stencil index
 // RELATIVE to the array's ilower (ic_lower - ilower) and W weights; weight j belongs to index
 // lo + j.  Clipping to the ghost box is the caller's job: every in-scope kernel's weights depend
 // only on the point's own index, so "clamp the bounds, then weigh" (3d.f.m4:2666-2678) equals
 // "weigh, then skip the clipped points".
+// on_axis: the dimension is the `axis` argument of the axis-dependent Fortran routines (ignored by the others).
 template <int K>
-__device__ __forceinline__ void stencil_1d(double Xs, double Xraw, double x_lower, double dx, int& lo, double* w)
+__device__ __forceinline__ void stencil_1d(double Xs, double Xraw, double x_lower, double dx, int& lo, double* w, bool on_axis = false)
 {
     // (X + Xshift - x_lower)/dx, 3d.f.m4:1265 / :2660 / :565
     const double t = __ddiv_rn(__dsub_rn(Xs, x_lower), dx);
@@ -274,10 +367,57 @@ __device__ __forceinline__ void stencil_1d(double Xs, double Xraw, double x_lowe
             w[j] = (K == IBK_BSPLINE_6) ? bspline_6_delta(r) : piecewise_cubic_delta(r);
         }
     }
+    else if constexpr (CompositeOrders<K>::is)
+    {
+        // composite B-splines (3d.f.m4:3510-5460): centred rule [c - h, c + h] for the odd widths, sided rule (the
+        // UNSHIFTED X against X_cell(c)) for the even ones; weight = delta_A on the axis, delta_B off it
+        constexpr int W = KTraits<K>::W;
+        constexpr int h = W / 2;
+        const int c = (int)floor(t);
+        if constexpr (W % 2 == 1)
+            lo = c - h;
+        else
+        {
+            const double X_cell_c = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)c, 0.5), dx));
+            lo = (Xraw < X_cell_c) ? c - h : c - h + 1;
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+        {
+            const double X_cell = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)(lo + j), 0.5), dx));
+            const double r = __ddiv_rn(__dsub_rn(Xs, X_cell), dx);
+            w[j] = on_axis ? bspline_delta<CompositeOrders<K>::A>(r) : bspline_delta<CompositeOrders<K>::B>(r);
+        }
+    }
+    else if constexpr (K == IBK_IB_4_W8)
+    {
+        // 3d.f.m4:1545-1560: first point NINT(t) - 4; odd points from r = (t - (lo + 3 + 1/2))/2, even ones from r + 1/2
+        lo = nint_f(t) - 4;
+        double r = 0.5 * __dsub_rn(t, __dadd_rn((double)(lo + 3), 0.5));
+        double q = sqrt(1.0 + 4.0 * r * (1.0 - r));
+        w[1] = 0.0625 * (3.0 - 2.0 * r - q);
+        w[3] = 0.0625 * (3.0 - 2.0 * r + q);
+        w[5] = 0.0625 * (1.0 + 2.0 * r + q);
+        w[7] = 0.0625 * (1.0 + 2.0 * r - q);
+        r = r + 0.5;
+        q = sqrt(1.0 + 4.0 * r * (1.0 - r));
+        w[0] = 0.0625 * (3.0 - 2.0 * r - q);
+        w[2] = 0.0625 * (3.0 - 2.0 * r + q);
+        w[4] = 0.0625 * (1.0 + 2.0 * r + q);
+        w[6] = 0.0625 * (1.0 + 2.0 * r - q);
+    }
     else
     {
-        // PIECEWISE_LINEAR, 3d.f.m4:563-579
+        // PIECEWISE_LINEAR, 3d.f.m4:563-579; DISCONTINUOUS_LINEAR (3d.f.m4:296-321) is the same along the axis and the
+        // centre cell alone (weight 1; the second point carries weight 0) in the other dimensions
         const int c = nint_f(__dsub_rn(t, 0.5));
+        if (K == IBK_DISCONTINUOUS_LINEAR && !on_axis)
+        {
+            lo = c;
+            w[0] = 1.0;
+            w[1] = 0.0;
+            return;
+        }
         const double X_cell = __dadd_rn(x_lower, __dmul_rn(__dadd_rn((double)c, 0.5), dx));
         if (Xs < X_cell)
         {
@@ -315,6 +455,7 @@ struct CompGeom
     int pp0[3];            // pp coordinate of element 0  (= G - nugc)
     int var[3];            // which x_lower variant each dimension uses (see TileParams::xl)
     int vcol;              // which marker value column this component reads / writes
+    int axis;              // the `axis` argument of the axis-dependent kernels (SideData / EdgeData: the component)
 };
 
 struct TileParams

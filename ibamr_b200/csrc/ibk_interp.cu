@@ -41,9 +41,13 @@ struct InterpArgs
 };
 
 constexpr int INTERP_THREADS = 256;
+// A tile of the uniform benchmark holds 256 +- 16 markers: with 256 threads every second tile pays a second, almost empty
+// pass over the stencil gather.  Kernels whose register need allows three 320-thread CTAs per SM take 320 threads.
+constexpr int INTERP_THREADS_WIDE = 320;
+constexpr bool INTERP_WIDE_DEFAULT = false; // until measured on the GPU (IBK_INTERP_WIDE=1 selects it)
 
-template <int NDIM, int K>
-__global__ void __launch_bounds__(INTERP_THREADS)
+template <int NDIM, int K, int NT>
+__global__ void __launch_bounds__(NT, (NT > 256) ? 3 : 1)
     interp_tile_kernel(const __grid_constant__ TileParams tp, const __grid_constant__ TmaMapSet maps, InterpArgs args)
 {
     constexpr int W = KTraits<K>::W;
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(INTERP_THREADS)
         else
         {
             constexpr int NPTS = (NDIM == 3) ? SX * S * S : SX * S;
-            for (int q = threadIdx.x; q < NPTS; q += INTERP_THREADS)
+            for (int q = threadIdx.x; q < NPTS; q += NT)
             {
                 const int i = q % SX;
                 const int j = (q / SX) % S;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(INTERP_THREADS)
             __syncthreads();
         }
 
-        for (int i = s0 + threadIdx.x; i < s1; i += INTERP_THREADS)
+        for (int i = s0 + threadIdx.x; i < s1; i += NT)
         {
             double w[NDIM][W];
             int lo[NDIM]; // stencil origin in pp coordinates
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(INTERP_THREADS)
                 const double xs = (i == i_first) ? xs0[d] : args.X[d * args.x_stride + i];
                 const double xr = (i == i_first) ? xr0[d] : (args.Xraw ? args.Xraw[d * args.x_stride + i] : xs);
                 int l;
-                stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w[d]);
+                stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w[d], d == cg.axis);
                 lo[d] = l + tp.G;
                 staged = staged && (lo[d] >= sp0[d]) && (lo[d] + W <= sp0[d] + S);
             }
@@ -255,7 +259,7 @@ static PFN_encodeTiled get_encode_fn()
     return fn;
 }
 
-bool make_tensor_map(CUtensorMap* m, const CompGeom& cg, int ndim, unsigned bx, unsigned by, unsigned bz)
+bool make_tensor_map(CUtensorMap* m, const CompGeom& cg, int ndim, unsigned bx, unsigned by, unsigned bz, int promo)
 {
     if (((uintptr_t)cg.ptr % 16 != 0) || ((cg.pitch * 8) % 16 != 0)) return false;
     PFN_encodeTiled enc = get_encode_fn();
@@ -265,7 +269,9 @@ bool make_tensor_map(CUtensorMap* m, const CompGeom& cg, int ndim, unsigned bx, 
     cuuint32_t box[3] = { (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz };
     cuuint32_t estr[3] = { 1, 1, 1 };
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)ndim, (void*)cg.ptr, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
+                     promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -296,24 +302,33 @@ static cudaError_t launch_interp_t(Launcher& L, const TileParams& tp, const Bins
     }
     static const bool no_tma = getenv("IBK_NO_TMA") != nullptr;
     static const bool dbg = getenv("IBK_DEBUG") != nullptr;
+    static const int promo = getenv("IBK_TMA_PROMO_INTERP") ? atoi(getenv("IBK_TMA_PROMO_INTERP")) : 2;
     for (int a = 0; a < tp.ncomp; ++a)
-        if (!no_tma && make_tensor_map(&maps.m[a], tp.comp[a], NDIM, S + 2, S, S)) args.tma_mask |= (1u << a);
+        if (!no_tma && make_tensor_map(&maps.m[a], tp.comp[a], NDIM, S + 2, S, S, promo)) args.tma_mask |= (1u << a);
     if (dbg)
         fprintf(stderr, "[ibk] interp<%d,%d> ncomp=%d tma_mask=%x ntiles=%d n=(%d,%d,%d) pitch=%lld ptr=%p sizeof(tp)=%zu\n", NDIM, K,
                 tp.ncomp, args.tma_mask, tp.nt[0] * tp.nt[1] * tp.nt[2], tp.comp[0].n[0], tp.comp[0].n[1], tp.comp[0].n[2],
                 tp.comp[0].pitch, (void*)tp.comp[0].ptr, sizeof(TileParams));
-    auto kfn = interp_tile_kernel<NDIM, K>;
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess)
-    {
-        err = "cudaFuncSetAttribute(interp) failed";
-        return e;
-    }
     const int ntiles = tp.nt[0] * tp.nt[1] * tp.nt[2];
     if (ntiles <= 0) return cudaSuccess;
-    kfn<<<ntiles, INTERP_THREADS, smem, L.stream>>>(tp, maps, args);
-    L.launches++;
-    return cudaGetLastError();
+    auto go = [&](auto kfn, int nt) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+        {
+            err = "cudaFuncSetAttribute(interp) failed";
+            return e;
+        }
+        kfn<<<ntiles, nt, smem, L.stream>>>(tp, maps, args);
+        L.launches++;
+        return cudaGetLastError();
+    };
+    if constexpr (NDIM == 3 && M <= 2 && KTraits<K>::W <= 4)
+    {
+        static const char* env = getenv("IBK_INTERP_WIDE"); // 0 / 1 overrides the default
+        static const bool wide = env ? atoi(env) != 0 : INTERP_WIDE_DEFAULT;
+        if (wide) return go(interp_tile_kernel<NDIM, K, INTERP_THREADS_WIDE>, INTERP_THREADS_WIDE);
+    }
+    return go(interp_tile_kernel<NDIM, K, INTERP_THREADS>, INTERP_THREADS);
 }
 
 template <int NDIM>
@@ -344,6 +359,26 @@ static cudaError_t launch_interp_k(Launcher& L, int kernel, const TileParams& tp
         return launch_interp_t<NDIM, IBK_IB_5>(L, tp, bins, mv, err);
     case IBK_PIECEWISE_CONSTANT:
         return launch_interp_t<NDIM, IBK_PIECEWISE_CONSTANT>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_32:
+        return launch_interp_t<NDIM, IBK_COMPOSITE_BSPLINE_32>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_23:
+        return launch_interp_t<NDIM, IBK_COMPOSITE_BSPLINE_23>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_43:
+        return launch_interp_t<NDIM, IBK_COMPOSITE_BSPLINE_43>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_34:
+        return launch_interp_t<NDIM, IBK_COMPOSITE_BSPLINE_34>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_54:
+        return launch_interp_t<NDIM, IBK_COMPOSITE_BSPLINE_54>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_45:
+        return launch_interp_t<NDIM, IBK_COMPOSITE_BSPLINE_45>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_65:
+        return launch_interp_t<NDIM, IBK_COMPOSITE_BSPLINE_65>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_56:
+        return launch_interp_t<NDIM, IBK_COMPOSITE_BSPLINE_56>(L, tp, bins, mv, err);
+    case IBK_DISCONTINUOUS_LINEAR:
+        return launch_interp_t<NDIM, IBK_DISCONTINUOUS_LINEAR>(L, tp, bins, mv, err);
+    case IBK_IB_4_W8:
+        return launch_interp_t<NDIM, IBK_IB_4_W8>(L, tp, bins, mv, err);
     default:
         err = "unknown kernel";
         return cudaErrorInvalidValue;

@@ -28,6 +28,7 @@ struct ArrayComp
     int nugc[3];
     int var[3];
     int vcol;
+    int axis;
 };
 void make_tile_params(TileParams& tp, int ndim, const double* dx, const double xl[3][2], const int* nvar, const PatchBin& pb,
                       int ncomp, const ArrayComp* comps);
@@ -619,6 +620,7 @@ extern "C" int ibk_level_create(ibk_ctx* ctx, const ibk_level_desc* desc)
                 comps[a].ptr = which == 0 ? ps.u[a] : ps.f[a];
                 comps[a].pitch = ps.pitch[a];
                 comps[a].vcol = a;
+                comps[a].axis = a;
                 for (int d = 0; d < 3; ++d)
                 {
                     comps[a].n[d] = ps.n[a][d];

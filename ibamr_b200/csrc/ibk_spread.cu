@@ -51,6 +51,15 @@ __device__ int g_tl_n;
 #define TL(k)
 #endif
 constexpr int SPREAD_THREADS = 256;
+// PLANE OWNERS (3D, 4-point kernels): the accumulation of a window is not organised by bricks and colours but by planes
+// of the block: warp `id` owns the two z planes 2 id, 2 id + 1 and walks ALL markers of the window whose stencil meets
+// them (2 or 3 warps per marker), lanes = 4 x 4 (x, y) points x 2 planes.  No two warps share a word, so the only CTA
+// barriers left are the two around the stencil evaluation of a window; the order of the additions at a grid point is
+// the window's marker order, the same as with the brick colours (results are bit-identical to that path).
+constexpr bool SPREAD_PLANES_DEFAULT = false; // until measured on the GPU (IBK_SPREAD_PLANES=1 selects it)
+constexpr int SPREAD_THREADS_PLANES = 320; // 10 warps = the 10 plane pairs of a 20-plane block
+template <int NDIM, int K>
+constexpr bool spread_planes_ok = (NDIM == 3 && KTraits<K>::W == 4 && KTraits<K>::M == 2);
 constexpr int SPREAD_TASKS = 1; // (marker, dimension) stencil evaluations per thread and window (measured: a second one
                                 // serialises two sqrt/div chains before the barrier: 85-marker windows beat 100-marker ones)
 constexpr int SPREAD_WARPS = SPREAD_THREADS / 32;
@@ -113,13 +122,16 @@ __constant__ BrickColouring<NDIM, NC> c_colouring = BrickColouring<NDIM, NC>(); 
 template <int NDIM, int NC>
 __device__ const BrickColouring<NDIM, NC> d_colouring = BrickColouring<NDIM, NC>(); // per-lane reads (order[])
 
-template <int NDIM, int K>
-__global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
+template <int NDIM, int K, bool PL>
+__global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     spread_tile_kernel(const __grid_constant__ TileParams tp, const __grid_constant__ TmaMapSet maps, SpreadArgs args)
 {
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
     constexpr int R = TILE + 2 * M; // haloed block edge
+    constexpr int NT = PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS;
+    constexpr int NWARPS = NT / 32;
+    static_assert(!PL || spread_planes_ok<NDIM, K>, "plane owners: 3D, W = 4, M = 2");
     // TMA boxes of 8-byte elements must start on an even x coordinate and have an even x extent (16 bytes):
     // the block gets XO spare columns on the left and is RX wide in x.
     constexpr int XO = M & 1;
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     int my_q = 0;
     if (threadIdx.x <= NBRICKS) sbs[threadIdx.x] = __ldg(&args.brick_start[b0 + threadIdx.x]);
     if (threadIdx.x < NBRICKS) my_q = __ldg(&d_colouring<NDIM, NC>.order[threadIdx.x]);
-    for (int q = threadIdx.x; q < args.cap; q += SPREAD_THREADS) relb[q] = 0;
+    for (int q = threadIdx.x; q < args.cap; q += NT) relb[q] = 0;
 #ifdef IBK_TIMELINE
     long long tl[16];
     for (int k = 0; k < 16; ++k) tl[k] = 0;
@@ -222,7 +234,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
         if (lane == 31) wsum[warp] = my_incl;
     }
     if (!use_tma)
-        for (int q = threadIdx.x; q < RPTS; q += SPREAD_THREADS) acc[q] = 0.0;
+        for (int q = threadIdx.x; q < RPTS; q += NT) acc[q] = 0.0;
     __syncthreads();
     TL(2);
     if (use_tma && threadIdx.x == 0)
@@ -277,7 +289,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
 #pragma unroll
         for (int k = 0; k < SPREAD_TASKS; ++k)
         {
-            const int tix = threadIdx.x + k * SPREAD_THREADS;
+            const int tix = threadIdx.x + k * NT;
             t_i[k] = -1;
             if (tix >= cnt * NDIM) continue;
             const int m = tix / NDIM, d = tix - m * NDIM;
@@ -306,21 +318,34 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
         for (int k = 0; k < SPREAD_TASKS; ++k)
         {
             if (t_i[k] < 0) continue;
-            const int tix = threadIdx.x + k * SPREAD_THREADS;
+            const int tix = threadIdx.x + k * NT;
             const int m = tix / NDIM, d = tix - m * NDIM;
             const double xl_s = tp.xl[d][cg.var[d]];
             const double dx_s = tp.dx[d];
             const int blo_s = (d == 0) ? blo[0] : (d == 1) ? blo[1] : blo[2];
             double w[W];
             int l;
-            stencil_1d<K>(t_xs[k], Xr ? t_xr[k] : t_xs[k], xl_s, dx_s, l, w);
+            stencil_1d<K>(t_xs[k], Xr ? t_xr[k] : t_xs[k], xl_s, dx_s, l, w, d == cg.axis);
             const int r0 = l + G - blo_s; // first stencil point relative to the block
             const bool fits = r0 >= 0 && r0 + W <= R;
             const double scale = (d == LD) ? t_v[k] * inv_vol : 1.0;
 #pragma unroll
             for (int j = 0; j < W; ++j) wgt[(m * NDIM + d) * W + j] = w[j] * scale;
-            const int stride_b = (d == 0) ? 8 : (d == 1) ? 8 * RX : 8 * RX * R; // bytes per point along d in the block
-            atomicAdd(&relb[par * cap + m], fits ? r0 * stride_b : -(1 << 29));
+            if constexpr (PL)
+            {
+                // (x, y) byte offset in the low 20 bits, first z plane above them
+                atomicAdd(&relb[par * cap + m], !fits ? -(1 << 29) : (d == 0) ? r0 * 8 : (d == 1) ? r0 * 8 * RX : (r0 << 20));
+                if (!fits && args.exc_list) // left to the fix-up (which removes duplicates)
+                {
+                    const int slot = atomicAdd(args.exc_count, 1);
+                    if (slot < args.exc_capacity) args.exc_list[slot] = t_i[k] * 8 + a;
+                }
+            }
+            else
+            {
+                const int stride_b = (d == 0) ? 8 : (d == 1) ? 8 * RX : 8 * RX * R; // bytes per point along d in the block
+                atomicAdd(&relb[par * cap + m], fits ? r0 * stride_b : -(1 << 29));
+            }
         }
     };
 
@@ -337,11 +362,50 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
         if (off == 0) TL(5);
         const int col_lo = wcol[par][0], col_hi = wcol[par][1];
         if (off + cap < total) fetch(off + cap, par ^ 1);
+        if constexpr (PL)
+        {
+            // ---- phase B, plane owners: no barrier until the window is done
+            static_assert(8 * RX * R < (1 << 20), "(x, y) byte offset fits 20 bits");
+            constexpr int PLANE_B = 8 * RX * R;
+            constexpr int NW = NDIM * W;
+            const int* rp = relb + par * cap;
+            const int ix = lane & 3, iy = (lane >> 2) & 3, iz = lane >> 4;
+            const double* wl = wgt + ix; // this lane's x weight of marker 0; y weight at + W + (iy - ix)
+            for (int id = warp; id < R / 2; id += NWARPS)
+            {
+                const int plane = 2 * id + iz;
+                char* const accp = reinterpret_cast<char*>(acc) + plane * PLANE_B + 8 * (iy * RX + ix + XO);
+                for (int c0 = 0; c0 < cnt; c0 += 32)
+                {
+                    const int mm = c0 + lane;
+                    const int ab = (mm < cnt) ? rp[mm] : -1;
+                    const int r0l = ab >> 20;
+                    unsigned hits = __ballot_sync(0xffffffffu, ab >= 0 && r0l <= 2 * id + 1 && r0l + 3 >= 2 * id);
+                    while (hits)
+                    {
+                        const int b = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const int abm = __shfl_sync(0xffffffffu, ab, b);
+                        const int kz = plane - (abm >> 20);
+                        const double* wp = wl + (c0 + b) * NW;
+                        if ((unsigned)kz < (unsigned)W)
+                        {
+                            const double wv = (wp[0] * wp[W + iy - ix]) * wp[2 * W + kz - ix];
+                            double* pt = reinterpret_cast<double*>(accp + (abm & 0xFFFFF));
+                            *pt = *pt + wv;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        else
         // ---- phase B, colour by colour (only the colours this window holds)
         for (int col = col_lo; col <= col_hi; ++col)
         {
             const int cend = bc.start[col + 1];
-            for (int p = bc.start[col] + warp; p < cend; p += SPREAD_WARPS)
+            for (int p = bc.start[col] + warp; p < cend; p += NWARPS)
             {
                 const int p0 = bpre[p], p1 = bpre[p + 1];
                 const int m0 = max(p0, off) - off, m1 = min(p1, off + cnt) - off;
@@ -429,7 +493,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     // the stream, so the order of the additions is fixed and the result bit-reproducible.
     {
         constexpr int ROWS = (NDIM == 3) ? R * R : R;
-        constexpr int RSTEP = SPREAD_THREADS / 8; // rows per sweep: a group of 8 lanes takes one row at a time,
+        constexpr int RSTEP = NT / 8; // rows per sweep: a group of 8 lanes takes one row at a time,
         const int g8 = threadIdx.x >> 3, l8 = threadIdx.x & 7; // 8 lanes x 3 points cover R <= 24 points
         const int gx0 = blo[0] - cg.pp0[0] + l8;
         bool okx[3];
@@ -559,7 +623,7 @@ __global__ void __launch_bounds__(256, (KTraits<K>::M <= 2) ? 3 : 2)
             const int i = first + m;
             double w[W];
             int l;
-            stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w);
+            stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w, d == cg.axis);
             const int r0 = l + tp.G - fo[d];
             const bool fits = r0 >= 0 && r0 + W <= FP;
             const double scale = (d == 2) ? fv * tp.inv_vol : 1.0;
@@ -668,7 +732,7 @@ __global__ void spread_fixup_kernel(const __grid_constant__ TileParams tp, Sprea
             const double xs = args.X[d * args.x_stride + i];
             const double xr = args.Xraw ? args.Xraw[d * args.x_stride + i] : xs;
             int l;
-            stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w[d]);
+            stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w[d], d == cg.axis);
             lo[d] = l + tp.G;
         }
         const double f = args.V[cg.vcol * args.v_cstride + row * args.v_istride] * tp.inv_vol;
@@ -693,9 +757,26 @@ __global__ void spread_fixup_kernel(const __grid_constant__ TileParams tp, Sprea
 static int* g_exc_buf = nullptr; // [1 + capacity] per process (device); tiny
 constexpr int EXC_CAPACITY = 4096;
 
+template <int NDIM, int K, bool PL>
+static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err);
+
 template <int NDIM, int K>
 static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err)
 {
+    if constexpr (spread_planes_ok<NDIM, K>)
+    {
+        // IBK_SPREAD_PLANES=0 / 1 overrides the default
+        static const char* env = getenv("IBK_SPREAD_PLANES");
+        static const bool planes = env ? atoi(env) != 0 : SPREAD_PLANES_DEFAULT;
+        if (planes) return launch_spread_pl<NDIM, K, true>(L, tp, bins, mv, err);
+    }
+    return launch_spread_pl<NDIM, K, false>(L, tp, bins, mv, err);
+}
+
+template <int NDIM, int K, bool PL>
+static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err)
+{
+    constexpr int NT = PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS;
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
     constexpr int R = TILE + 2 * M;
@@ -738,15 +819,16 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     constexpr int per_marker = (int)sizeof(double) * NDIM * W + 2 * (int)sizeof(int);
     constexpr int cap_fit = (int)(budget / per_marker);
     args.cap = (cap_env >= 8 && cap_env <= 1024) ? cap_env : std::max(32, std::min(256, cap_fit));
-    args.cap = std::min(args.cap, SPREAD_TASKS * SPREAD_THREADS / NDIM); // fetch()/evaluate() hold SPREAD_TASKS tasks per thread
+    args.cap = std::min(args.cap, SPREAD_TASKS * NT / NDIM); // fetch()/evaluate() hold SPREAD_TASKS tasks per thread
     const size_t smem = sizeof(double) * ((size_t)RPTS + (size_t)args.cap * NDIM * W) + 2 * sizeof(int) * (size_t)args.cap;
     // TMA moves the block when it can address the array and the block starts on an even x coordinate
     TmaMapSet maps;
     std::memset(&maps, 0, sizeof(maps));
     args.tma_mask = 0;
     static const bool no_tma = getenv("IBK_NO_TMA") != nullptr;
+    static const int promo = getenv("IBK_TMA_PROMO_SPREAD") ? atoi(getenv("IBK_TMA_PROMO_SPREAD")) : 2;
     for (int a = 0; a < tp.ncomp; ++a)
-        if (!no_tma && ((tp.comp[a].pp0[0] + M + XO) % 2 == 0) && make_tensor_map(&maps.m[a], tp.comp[a], NDIM, RX, R, R))
+        if (!no_tma && ((tp.comp[a].pp0[0] + M + XO) % 2 == 0) && make_tensor_map(&maps.m[a], tp.comp[a], NDIM, RX, R, R, promo))
             args.tma_mask |= (1u << a);
     static const bool dbg = getenv("IBK_DEBUG") != nullptr;
     if (dbg)
@@ -754,7 +836,7 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
             fprintf(stderr, "[ibk] spread<%d,%d> comp %d tma=%u n=(%d,%d,%d) pitch=%lld pp0=(%d,%d,%d) ptr=%p nt=(%d,%d,%d) box=(%d,%d)\n", NDIM,
                     K, a, (args.tma_mask >> a) & 1u, tp.comp[a].n[0], tp.comp[a].n[1], tp.comp[a].n[2], tp.comp[a].pitch,
                     tp.comp[a].pp0[0], tp.comp[a].pp0[1], tp.comp[a].pp0[2], (void*)tp.comp[a].ptr, tp.nt[0], tp.nt[1], tp.nt[2], RX, R);
-    auto kfn = spread_tile_kernel<NDIM, K>;
+    auto kfn = spread_tile_kernel<NDIM, K, PL>;
     auto ffn = spread_fixup_kernel<NDIM, K>;
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
@@ -764,7 +846,7 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
     }
     // dense bricks first (their own kernel), then the tiles without them
     args.dense_thresh = 0;
-    if constexpr (NDIM == 3)
+    if constexpr (NDIM == 3 && KTraits<K>::M <= 3) // (a 12^3 footprint does not fit the dense kernel's static shared memory)
     {
         static const bool no_dense = getenv("IBK_NO_DENSE") != nullptr;
         if (bins.n_dense > 0 && !no_dense && mv.part != 1) // (with a tile selection the dense bricks go with the boundary part)
@@ -794,7 +876,7 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
         }
         if (ntiles <= 0) continue;
         dim3 grid((unsigned)ntiles, (unsigned)tp.ncomp);
-        kfn<<<grid, SPREAD_THREADS, smem, L.stream>>>(tp, maps, args);
+        kfn<<<grid, NT, smem, L.stream>>>(tp, maps, args);
         L.launches++;
     }
     ffn<<<1, 32, 0, L.stream>>>(tp, args);
@@ -852,6 +934,26 @@ static cudaError_t launch_spread_k(Launcher& L, int kernel, const TileParams& tp
         return launch_spread_t<NDIM, IBK_IB_5>(L, tp, bins, mv, err);
     case IBK_PIECEWISE_CONSTANT:
         return launch_spread_t<NDIM, IBK_PIECEWISE_CONSTANT>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_32:
+        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_32>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_23:
+        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_23>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_43:
+        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_43>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_34:
+        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_34>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_54:
+        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_54>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_45:
+        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_45>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_65:
+        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_65>(L, tp, bins, mv, err);
+    case IBK_COMPOSITE_BSPLINE_56:
+        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_56>(L, tp, bins, mv, err);
+    case IBK_DISCONTINUOUS_LINEAR:
+        return launch_spread_t<NDIM, IBK_DISCONTINUOUS_LINEAR>(L, tp, bins, mv, err);
+    case IBK_IB_4_W8:
+        return launch_spread_t<NDIM, IBK_IB_4_W8>(L, tp, bins, mv, err);
     default:
         err = "unknown kernel";
         return cudaErrorInvalidValue;

@@ -64,7 +64,20 @@ typedef enum ibk_kernel
     IBK_BSPLINE_6 = 7,
     IBK_PIECEWISE_CUBIC = 8,
     IBK_IB_5 = 9,
-    IBK_PIECEWISE_CONSTANT = 10
+    IBK_PIECEWISE_CONSTANT = 10,
+    /* axis-dependent kernels (the Fortran routines take an `axis` argument, lagrangian_interaction3d.f.m4:237-243,
+     * 3510-3516): COMPOSITE_BSPLINE_<A><B> = B-spline of order A along the component's axis, order B elsewhere */
+    IBK_COMPOSITE_BSPLINE_32 = 11,
+    IBK_COMPOSITE_BSPLINE_23 = 12,
+    IBK_COMPOSITE_BSPLINE_43 = 13,
+    IBK_COMPOSITE_BSPLINE_34 = 14,
+    IBK_COMPOSITE_BSPLINE_54 = 15,
+    IBK_COMPOSITE_BSPLINE_45 = 16,
+    IBK_COMPOSITE_BSPLINE_65 = 17,
+    IBK_COMPOSITE_BSPLINE_56 = 18,
+    IBK_DISCONTINUOUS_LINEAR = 19,
+    IBK_IB_4_W8 = 20, /* lagrangian_ib_4_w8_*: the 4-point function broadened to 8 meshwidths */
+    IBK_KERNEL_LAST = IBK_IB_4_W8
 } ibk_kernel;
 
 /* ---- LEInteractor static queries (ibtk/include/ibtk/LEInteractor.h:99-117) ------------------ */
@@ -106,6 +119,8 @@ typedef struct ibk_array_desc
     int ilower[IBK_MAX_DIM];       /* data box (toSideBox'ed for SideData)                       */
     int iupper[IBK_MAX_DIM];
     int nugc[IBK_MAX_DIM];         /* ghost width of the array                                   */
+    int axis;                      /* `axis` of the axis-dependent routines (LEInteractor passes the SideData /
+                                      EdgeData component, 0 otherwise: LEInteractor.h:1341); ignored by the others */
 } ibk_array_desc;
 
 /* V(d, indices[l]) = sum_stencil w * u(..., d); markers not listed are left untouched. */

@@ -184,7 +184,7 @@ void le_oracle_side_interp(int kernel,
         for (int d = 0; d < ndim; ++d) x_lower_axis[d] = x_lower[d];
         x_lower_axis[axis] -= 0.5 * dx[axis]; /* LEInteractor.cpp:2464 */
         side_box(ndim, axis, patch_lower, patch_upper, slo, shi);
-        le_oracle_interp(kernel, ndim, dx, x_lower_axis, 1, slo, shi, gcw, u[axis], indices, shifts, nindices, X, Q_axis);
+        le_oracle_interp(kernel | (axis << 8), ndim, dx, x_lower_axis, 1, slo, shi, gcw, u[axis], indices, shifts, nindices, X, Q_axis);
         for (int l = 0; l < nindices; ++l) Q[(size_t)ndim * indices[l] + axis] = Q_axis[indices[l]];
     }
     free(Q_axis);
@@ -218,7 +218,7 @@ void le_oracle_side_spread(int kernel,
         x_lower_axis[axis] -= 0.5 * dx[axis]; /* LEInteractor.cpp:3689 */
         side_box(ndim, axis, patch_lower, patch_upper, slo, shi);
         for (int l = 0; l < nindices; ++l) Q_axis[indices[l]] = Q[(size_t)ndim * indices[l] + axis];
-        le_oracle_spread(kernel, ndim, dx, x_lower_axis, 1, indices, shifts, nindices, X, Q_axis, slo, shi, gcw, u[axis]);
+        le_oracle_spread(kernel | (axis << 8), ndim, dx, x_lower_axis, 1, indices, shifts, nindices, X, Q_axis, slo, shi, gcw, u[axis]);
     }
     free(Q_axis);
 }

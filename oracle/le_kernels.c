@@ -40,7 +40,7 @@
 #include <math.h>
 #include <stddef.h>
 
-#define MAXW 6
+#define MAXW 8
 
 enum
 {
@@ -55,7 +55,20 @@ enum
     K_BSPLINE_6 = 7,
     K_PIECEWISE_CUBIC = 8,
     K_IB_5 = 9,
-    K_PIECEWISE_CONSTANT = 10
+    K_PIECEWISE_CONSTANT = 10,
+    /* N4, second part: the kernels whose 1-D function depends on whether the dimension is the component's `axis`
+     * (the Fortran routines take an extra `axis` argument, 3d.f.m4:237, 3510-5460), and the broadened ib_4.
+     * The axis travels in bits 8.. of the `kernel` argument of le_oracle_interp / le_oracle_spread. */
+    K_COMPOSITE_BSPLINE_32 = 11,
+    K_COMPOSITE_BSPLINE_23 = 12,
+    K_COMPOSITE_BSPLINE_43 = 13,
+    K_COMPOSITE_BSPLINE_34 = 14,
+    K_COMPOSITE_BSPLINE_54 = 15,
+    K_COMPOSITE_BSPLINE_45 = 16,
+    K_COMPOSITE_BSPLINE_65 = 17,
+    K_COMPOSITE_BSPLINE_56 = 18,
+    K_DISCONTINUOUS_LINEAR = 19,
+    K_IB_4_W8 = 20
 };
 
 typedef struct
@@ -346,7 +359,57 @@ static void stencil_piecewise_linear(double Xs, double x_lower, double dx, int i
     s->hi = (ic_upper < iupper + g) ? ic_upper : iupper + g;
 }
 
+/* lagrangian_delta.f.m4:29-45 */
+static double piecewise_linear_delta(double r)
+{
+    if (r < 0.0) r = -r;
+    return (r < 1.0) ? 1.0 - r : 0.0;
+}
+
+/* discontinuous_linear (3d.f.m4:296-336): centre cell NINT(t - 1/2); along `axis` the two-point hat of piecewise_linear,
+ * in the other dimensions the centre cell alone with weight 1; trimmed bounds, weights indexed from the untrimmed lower
+ * bound, products formed inline as w0*w1*w2*u. */
+static void stencil_discontinuous_linear(int on_axis, double Xs, double x_lower, double dx, int ilower, int iupper, int g, stencil1d* s)
+{
+    if (on_axis)
+    {
+        stencil_piecewise_linear(Xs, x_lower, dx, ilower, iupper, g, s);
+        return;
+    }
+    const int ic_center = ilower + nint_f((Xs - x_lower) / dx - 0.5);
+    s->w[0] = 1.0;
+    s->wbase = ic_center;
+    s->lo = (ic_center > ilower - g) ? ic_center : ilower - g;
+    s->hi = (ic_center < iupper + g) ? ic_center : iupper + g;
+}
+
+/* ib_4_w8 (3d.f.m4:1545-1560): the 4-point function broadened to 8 meshwidths: first point NINT(t) - 4, the odd points
+ * from r = (t - (lo + 3 + 1/2))/2, the even ones from r + 1/2, each scaled by 1/16; loop bounds clipped, weights indexed
+ * from the unclipped first point, products w0*(w1*w2) (tensor style). */
+static void stencil_ib_4_w8(double Xs, double x_lower, double dx, int ilower, int iupper, int g, stencil1d* s)
+{
+    const double X_o_dx = (Xs - x_lower) / dx;
+    const int ic_lower = nint_f(X_o_dx) + ilower - 4;
+    const int ic_upper = ic_lower + 7;
+    double r = 0.5 * (X_o_dx - ((double)(ic_lower + 3 - ilower) + 0.5));
+    double q = sqrt(1.0 + 4.0 * r * (1.0 - r));
+    s->w[1] = 0.0625 * (3.0 - 2.0 * r - q);
+    s->w[3] = 0.0625 * (3.0 - 2.0 * r + q);
+    s->w[5] = 0.0625 * (1.0 + 2.0 * r + q);
+    s->w[7] = 0.0625 * (1.0 + 2.0 * r - q);
+    r = r + 0.5;
+    q = sqrt(1.0 + 4.0 * r * (1.0 - r));
+    s->w[0] = 0.0625 * (3.0 - 2.0 * r - q);
+    s->w[2] = 0.0625 * (3.0 - 2.0 * r + q);
+    s->w[4] = 0.0625 * (1.0 + 2.0 * r + q);
+    s->w[6] = 0.0625 * (1.0 + 2.0 * r - q);
+    s->wbase = ic_lower;
+    s->lo = (ic_lower > ilower - g) ? ic_lower : ilower - g;
+    s->hi = (ic_upper < iupper + g) ? ic_upper : iupper + g;
+}
+
 static void make_stencil(int kernel,
+                         int on_axis,
                          double Xs,
                          double Xraw,
                          double x_lower,
@@ -388,6 +451,38 @@ static void make_stencil(int kernel,
     case K_PIECEWISE_CONSTANT:
         stencil_piecewise_constant(Xs, x_lower, dx, ilower, iupper, g, s);
         break;
+    /* composite B-splines (3d.f.m4:3510-5460): the index rule of the wider of the two (centred 3 / 5 points, sided 4 / 6
+     * points); the first digit names the function along `axis`, the second the function of the other dimensions */
+    case K_COMPOSITE_BSPLINE_32:
+        stencil_delta(on_axis ? bspline_3_delta : piecewise_linear_delta, 1, 0, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_COMPOSITE_BSPLINE_23:
+        stencil_delta(on_axis ? piecewise_linear_delta : bspline_3_delta, 1, 0, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_COMPOSITE_BSPLINE_43:
+        stencil_delta(on_axis ? bspline_4_delta : bspline_3_delta, 2, 1, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_COMPOSITE_BSPLINE_34:
+        stencil_delta(on_axis ? bspline_3_delta : bspline_4_delta, 2, 1, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_COMPOSITE_BSPLINE_54:
+        stencil_delta(on_axis ? bspline_5_delta : bspline_4_delta, 2, 0, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_COMPOSITE_BSPLINE_45:
+        stencil_delta(on_axis ? bspline_4_delta : bspline_5_delta, 2, 0, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_COMPOSITE_BSPLINE_65:
+        stencil_delta(on_axis ? bspline_6_delta : bspline_5_delta, 3, 1, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_COMPOSITE_BSPLINE_56:
+        stencil_delta(on_axis ? bspline_5_delta : bspline_6_delta, 3, 1, Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_DISCONTINUOUS_LINEAR:
+        stencil_discontinuous_linear(on_axis, Xs, x_lower, dx, ilower, iupper, g, s);
+        break;
+    case K_IB_4_W8:
+        stencil_ib_4_w8(Xs, x_lower, dx, ilower, iupper, g, s);
+        break;
     default:
         stencil_bspline_4(Xs, Xraw, x_lower, dx, ilower, iupper, g, s);
         break;
@@ -396,7 +491,7 @@ static void make_stencil(int kernel,
 
 static inline int is_tensor_style(int kernel)
 {
-    return kernel == K_IB_4 || kernel == K_IB_6;
+    return kernel == K_IB_4 || kernel == K_IB_6 || kernel == K_IB_4_W8;
 }
 
 /*
@@ -426,6 +521,8 @@ void le_oracle_interp(int kernel,
         iglo[d] = ilower[d] - nugc[d];
     }
     const ptrdiff_t comp_stride = n[0] * n[1] * n[2];
+    const int axis = kernel >> 8; /* the Fortran routines' `axis` argument (0 unless the caller set it) */
+    kernel &= 0xff;
     const int tensor = is_tensor_style(kernel);
     for (int l = 0; l < nindices; ++l)
     {
@@ -437,7 +534,7 @@ void le_oracle_interp(int kernel,
         {
             const double Xraw = X[(ptrdiff_t)ndim * s + d];
             const double Xs = Xraw + Xshift[(ptrdiff_t)ndim * l + d];
-            make_stencil(kernel, Xs, Xraw, x_lower[d], dx[d], ilower[d], iupper[d], nugc[d], &st[d]);
+            make_stencil(kernel, d == axis, Xs, Xraw, x_lower[d], dx[d], ilower[d], iupper[d], nugc[d], &st[d]);
         }
         for (int d = 0; d < depth; ++d)
         {
@@ -496,6 +593,8 @@ void le_oracle_spread(int kernel,
         iglo[d] = ilower[d] - nugc[d];
     }
     const ptrdiff_t comp_stride = n[0] * n[1] * n[2];
+    const int axis = kernel >> 8;
+    kernel &= 0xff;
     const int tensor = is_tensor_style(kernel);
     const double dxprod = (ndim == 3) ? dx[0] * dx[1] * dx[2] : dx[0] * dx[1];
     for (int l = 0; l < nindices; ++l)
@@ -508,7 +607,7 @@ void le_oracle_spread(int kernel,
         {
             const double Xraw = X[(ptrdiff_t)ndim * s + d];
             const double Xs = Xraw + Xshift[(ptrdiff_t)ndim * l + d];
-            make_stencil(kernel, Xs, Xraw, x_lower[d], dx[d], ilower[d], iupper[d], nugc[d], &st[d]);
+            make_stencil(kernel, d == axis, Xs, Xraw, x_lower[d], dx[d], ilower[d], iupper[d], nugc[d], &st[d]);
         }
         for (int d = 0; d < depth; ++d)
         {
@@ -667,3 +766,63 @@ DEFINE_2D(bspline_6, K_BSPLINE_6)
 DEFINE_2D(piecewise_cubic, K_PIECEWISE_CUBIC)
 DEFINE_2D(ib_5, K_IB_5)
 DEFINE_2D(piecewise_constant, K_PIECEWISE_CONSTANT)
+
+/* The axis-dependent routines take `axis` right after `depth` (3d.f.m4:237-243, 3510-3516; 2d twins). */
+#define DEFINE_AXIS_3D(NAME, KERNEL)                                                                                   \
+    void lagrangian_##NAME##_interp3d_(const double* dx, const double* x_lower, const double* x_upper, const int* depth, \
+                                       const int* axis, const int* ilower0, const int* iupper0, const int* ilower1,    \
+                                       const int* iupper1, const int* ilower2, const int* iupper2, const int* nugc0,   \
+                                       const int* nugc1, const int* nugc2, const double* u, const int* indices,        \
+                                       const double* Xshift, const int* nindices, const double* X, double* V)          \
+    {                                                                                                                  \
+        (void)x_upper;                                                                                                 \
+        const int il[3] = { *ilower0, *ilower1, *ilower2 }, iu[3] = { *iupper0, *iupper1, *iupper2 };                  \
+        const int ng[3] = { *nugc0, *nugc1, *nugc2 };                                                                  \
+        le_oracle_interp(KERNEL | (*axis << 8), 3, dx, x_lower, *depth, il, iu, ng, u, indices, Xshift, *nindices, X, V); \
+    }                                                                                                                  \
+    void lagrangian_##NAME##_spread3d_(const double* dx, const double* x_lower, const double* x_upper, const int* depth, \
+                                       const int* axis, const int* indices, const double* Xshift, const int* nindices, \
+                                       const double* X, const double* V, const int* ilower0, const int* iupper0,       \
+                                       const int* ilower1, const int* iupper1, const int* ilower2, const int* iupper2, \
+                                       const int* nugc0, const int* nugc1, const int* nugc2, double* u)                \
+    {                                                                                                                  \
+        (void)x_upper;                                                                                                 \
+        const int il[3] = { *ilower0, *ilower1, *ilower2 }, iu[3] = { *iupper0, *iupper1, *iupper2 };                  \
+        const int ng[3] = { *nugc0, *nugc1, *nugc2 };                                                                  \
+        le_oracle_spread(KERNEL | (*axis << 8), 3, dx, x_lower, *depth, indices, Xshift, *nindices, X, V, il, iu, ng, u); \
+    }
+#define DEFINE_AXIS_2D(NAME, KERNEL)                                                                                   \
+    void lagrangian_##NAME##_interp2d_(const double* dx, const double* x_lower, const double* x_upper, const int* depth, \
+                                       const int* axis, const int* ilower0, const int* iupper0, const int* ilower1,    \
+                                       const int* iupper1, const int* nugc0, const int* nugc1, const double* u,        \
+                                       const int* indices, const double* Xshift, const int* nindices, const double* X, \
+                                       double* V)                                                                      \
+    {                                                                                                                  \
+        (void)x_upper;                                                                                                 \
+        const int il[2] = { *ilower0, *ilower1 }, iu[2] = { *iupper0, *iupper1 };                                      \
+        const int ng[2] = { *nugc0, *nugc1 };                                                                          \
+        le_oracle_interp(KERNEL | (*axis << 8), 2, dx, x_lower, *depth, il, iu, ng, u, indices, Xshift, *nindices, X, V); \
+    }                                                                                                                  \
+    void lagrangian_##NAME##_spread2d_(const double* dx, const double* x_lower, const double* x_upper, const int* depth, \
+                                       const int* axis, const int* indices, const double* Xshift, const int* nindices, \
+                                       const double* X, const double* V, const int* ilower0, const int* iupper0,       \
+                                       const int* ilower1, const int* iupper1, const int* nugc0, const int* nugc1,     \
+                                       double* u)                                                                      \
+    {                                                                                                                  \
+        (void)x_upper;                                                                                                 \
+        const int il[2] = { *ilower0, *ilower1 }, iu[2] = { *iupper0, *iupper1 };                                      \
+        const int ng[2] = { *nugc0, *nugc1 };                                                                          \
+        le_oracle_spread(KERNEL | (*axis << 8), 2, dx, x_lower, *depth, indices, Xshift, *nindices, X, V, il, iu, ng, u); \
+    }
+DEFINE_3D(ib_4_w8, K_IB_4_W8)
+DEFINE_2D(ib_4_w8, K_IB_4_W8)
+#define DEFINE_AXIS(NAME, KERNEL) DEFINE_AXIS_3D(NAME, KERNEL) DEFINE_AXIS_2D(NAME, KERNEL)
+DEFINE_AXIS(composite_bspline_32, K_COMPOSITE_BSPLINE_32)
+DEFINE_AXIS(composite_bspline_23, K_COMPOSITE_BSPLINE_23)
+DEFINE_AXIS(composite_bspline_43, K_COMPOSITE_BSPLINE_43)
+DEFINE_AXIS(composite_bspline_34, K_COMPOSITE_BSPLINE_34)
+DEFINE_AXIS(composite_bspline_54, K_COMPOSITE_BSPLINE_54)
+DEFINE_AXIS(composite_bspline_45, K_COMPOSITE_BSPLINE_45)
+DEFINE_AXIS(composite_bspline_65, K_COMPOSITE_BSPLINE_65)
+DEFINE_AXIS(composite_bspline_56, K_COMPOSITE_BSPLINE_56)
+DEFINE_AXIS(discontinuous_linear, K_DISCONTINUOUS_LINEAR)

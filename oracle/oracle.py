@@ -32,10 +32,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 KERNELS = {"PIECEWISE_LINEAR": 0, "IB_4": 1, "IB_6": 2, "BSPLINE_3": 3, "BSPLINE_4": 4, "IB_3": 5, "BSPLINE_5": 6, "BSPLINE_6": 7,
-           "PIECEWISE_CUBIC": 8, "IB_5": 9, "PIECEWISE_CONSTANT": 10}
+           "PIECEWISE_CUBIC": 8, "IB_5": 9, "PIECEWISE_CONSTANT": 10,
+           "COMPOSITE_BSPLINE_32": 11, "COMPOSITE_BSPLINE_23": 12, "COMPOSITE_BSPLINE_43": 13, "COMPOSITE_BSPLINE_34": 14,
+           "COMPOSITE_BSPLINE_54": 15, "COMPOSITE_BSPLINE_45": 16, "COMPOSITE_BSPLINE_65": 17, "COMPOSITE_BSPLINE_56": 18,
+           "DISCONTINUOUS_LINEAR": 19, "IB_4_W8": 20}
 # LEInteractor::getStencilSize (LEInteractor.cpp:2052-2108) and getMinimumGhostWidth (:2110-2114)
 STENCIL_SIZE = {"PIECEWISE_LINEAR": 2, "IB_4": 4, "IB_6": 6, "BSPLINE_3": 4, "BSPLINE_4": 4, "IB_3": 4, "BSPLINE_5": 6, "BSPLINE_6": 6,
-                "PIECEWISE_CUBIC": 4, "IB_5": 6, "PIECEWISE_CONSTANT": 1}  # LEInteractor::getStencilSize (LEInteractor.cpp:2052-2103)
+                "PIECEWISE_CUBIC": 4, "IB_5": 6, "PIECEWISE_CONSTANT": 1,
+                "COMPOSITE_BSPLINE_32": 4, "COMPOSITE_BSPLINE_23": 4, "COMPOSITE_BSPLINE_43": 4, "COMPOSITE_BSPLINE_34": 4,
+                "COMPOSITE_BSPLINE_54": 5, "COMPOSITE_BSPLINE_45": 5, "COMPOSITE_BSPLINE_65": 6, "COMPOSITE_BSPLINE_56": 6,
+                "DISCONTINUOUS_LINEAR": 2, "IB_4_W8": 8}  # LEInteractor::getStencilSize (LEInteractor.cpp:2052-2103)
 
 
 def min_ghost_width(kernel: str) -> int:
@@ -83,7 +89,8 @@ def _i32(a):
 # ----------------------------------------------------------------------------------------------
 # raw funnel (seam B4): same argument meaning as the Fortran routines
 # ----------------------------------------------------------------------------------------------
-def interp_raw(kernel, ndim, dx, x_lower, depth, ilower, iupper, nugc, u, indices, Xshift, X, V=None):
+def interp_raw(kernel, ndim, dx, x_lower, depth, ilower, iupper, nugc, u, indices, Xshift, X, V=None, axis=0):
+    """`axis`: the extra argument of the axis-dependent Fortran routines (composite B-splines, discontinuous linear)."""
     X = _f64(X)
     indices = _i32(indices)
     Xshift = _f64(Xshift)
@@ -91,19 +98,19 @@ def interp_raw(kernel, ndim, dx, x_lower, depth, ilower, iupper, nugc, u, indice
     if V is None:
         V = np.zeros((X.size // ndim, depth))
     lib().le_oracle_interp(
-        KERNELS[kernel], ndim, _dp(_f64(dx)), _dp(_f64(x_lower)), depth, _ip(_i32(ilower)), _ip(_i32(iupper)),
+        KERNELS[kernel] | (axis << 8), ndim, _dp(_f64(dx)), _dp(_f64(x_lower)), depth, _ip(_i32(ilower)), _ip(_i32(iupper)),
         _ip(_i32(nugc)), _dp(u), _ip(indices), _dp(Xshift), int(indices.size), _dp(X), _dp(V))
     return V
 
 
-def spread_raw(kernel, ndim, dx, x_lower, depth, indices, Xshift, X, V, ilower, iupper, nugc, u):
+def spread_raw(kernel, ndim, dx, x_lower, depth, indices, Xshift, X, V, ilower, iupper, nugc, u, axis=0):
     assert u.dtype == np.float64 and u.flags.c_contiguous
     X = _f64(X)
     V = _f64(V)
     indices = _i32(indices)
     Xshift = _f64(Xshift)
     lib().le_oracle_spread(
-        KERNELS[kernel], ndim, _dp(_f64(dx)), _dp(_f64(x_lower)), depth, _ip(indices), _dp(Xshift),
+        KERNELS[kernel] | (axis << 8), ndim, _dp(_f64(dx)), _dp(_f64(x_lower)), depth, _ip(indices), _dp(Xshift),
         int(indices.size), _dp(X), _dp(V), _ip(_i32(ilower)), _ip(_i32(iupper)), _ip(_i32(nugc)), _dp(u))
     return u
 
@@ -283,7 +290,7 @@ def edge_interp_positions(kernel, pg, u_edges, X):
     for axis in range(ndim):
         xl, up = _shifted_geom(pg, [d != axis for d in range(ndim)])
         V = np.full((n, 1), np.finfo(np.float64).max)
-        interp_raw(kernel, ndim, pg.dx, xl, 1, pg.lower, up, pg.gcw, u_edges[axis], idx, np.zeros(idx.size * ndim), X, V)
+        interp_raw(kernel, ndim, pg.dx, xl, 1, pg.lower, up, pg.gcw, u_edges[axis], idx, np.zeros(idx.size * ndim), X, V, axis=axis)
         Q[:, axis] = V[:, 0]
     return Q
 
@@ -296,7 +303,7 @@ def edge_spread_positions(kernel, pg, u_edges, X, Q):
     for axis in range(ndim):
         xl, up = _shifted_geom(pg, [d != axis for d in range(ndim)])
         spread_raw(kernel, ndim, pg.dx, xl, 1, idx, np.zeros(idx.size * ndim), X, np.ascontiguousarray(Q[:, axis:axis + 1]), pg.lower,
-                   up, pg.gcw, u_edges[axis])
+                   up, pg.gcw, u_edges[axis], axis=axis)
     return u_edges
 
 

@@ -5,7 +5,9 @@
 set -e
 REF=${1:-/root/reference}
 HERE=$(dirname "$0")
-for k in ib_4 ib_6 bspline_3 bspline_4 piecewise_linear ib_3 bspline_5 bspline_6 piecewise_cubic ib_5 piecewise_constant; do
+for k in ib_4 ib_6 bspline_3 bspline_4 piecewise_linear ib_3 bspline_5 bspline_6 piecewise_cubic ib_5 piecewise_constant \
+         composite_bspline_32 composite_bspline_23 composite_bspline_43 composite_bspline_34 composite_bspline_54 \
+         composite_bspline_45 composite_bspline_65 composite_bspline_56 discontinuous_linear ib_4_w8; do
   for d in 2d 3d; do
     cp "$REF/tests/interpolate/interpolate_01_$d.$k.output" "$HERE/"
   done

@@ -27,7 +27,8 @@ using IBTK_B200::LEInteractor;
 
 static int run_static()
 {
-    const char* names[] = { "IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR", "IB_3", "BSPLINE_5", "BSPLINE_6", "PIECEWISE_CUBIC", "IB_5", "PIECEWISE_CONSTANT" };
+    const char* names[] = { "IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR", "IB_3", "BSPLINE_5", "BSPLINE_6", "PIECEWISE_CUBIC", "IB_5", "PIECEWISE_CONSTANT",
+                            "COMPOSITE_BSPLINE_32", "DISCONTINUOUS_LINEAR", "IB_4_W8" };
     for (const char* n : names)
         std::printf("%s known=%d stencil=%d ghosts=%d\n", n, (int)LEInteractor::isKnownKernel(n), LEInteractor::getStencilSize(n),
                     LEInteractor::getMinimumGhostWidth(n));

@@ -39,7 +39,10 @@ def test_header_symbols_are_exported(lib):
 def test_kernel_queries_match_leinteractor(lib):
     # LEInteractor::getStencilSize / getMinimumGhostWidth (LEInteractor.cpp:2052-2114)
     expect = {"IB_4": (4, 3), "IB_6": (6, 4), "BSPLINE_3": (4, 3), "BSPLINE_4": (4, 3), "PIECEWISE_LINEAR": (2, 2), "IB_3": (4, 3),
-              "BSPLINE_5": (6, 4), "BSPLINE_6": (6, 4), "PIECEWISE_CUBIC": (4, 3), "IB_5": (6, 4), "PIECEWISE_CONSTANT": (1, 1)}
+              "BSPLINE_5": (6, 4), "BSPLINE_6": (6, 4), "PIECEWISE_CUBIC": (4, 3), "IB_5": (6, 4), "PIECEWISE_CONSTANT": (1, 1),
+              "COMPOSITE_BSPLINE_32": (4, 3), "COMPOSITE_BSPLINE_23": (4, 3), "COMPOSITE_BSPLINE_43": (4, 3), "COMPOSITE_BSPLINE_34": (4, 3),
+              "COMPOSITE_BSPLINE_54": (5, 3), "COMPOSITE_BSPLINE_45": (5, 3), "COMPOSITE_BSPLINE_65": (6, 4), "COMPOSITE_BSPLINE_56": (6, 4),
+              "DISCONTINUOUS_LINEAR": (2, 2), "IB_4_W8": (8, 5)}
     for name, (sz, g) in expect.items():
         assert lib.ibk_is_known_kernel(name.encode()) == 1
         assert lib.ibk_get_stencil_size(name.encode()) == sz

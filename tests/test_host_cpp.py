@@ -26,7 +26,7 @@ def driver():
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
         subprocess.run([CXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-o", exe, src, "-L" + libdir, "-libk",
                         "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
-        # the Fortran-symbol shim must compile and define all 20 in-scope entry points
+        # the Fortran-symbol shim must compile and define every entry point (21 kernels x interp/spread x 2d/3d)
         obj = os.path.join(BUILD, "shim.o")
         subprocess.run([CXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-c", "-o", obj,
                         os.path.join(libdir, "host", "ibk_fortran_shim.cpp")], check=True, capture_output=True, text=True)
@@ -47,7 +47,9 @@ def test_cpp_static_queries_and_refusal(driver):
 
 def test_fortran_shim_exports_all_symbols(driver):
     out = subprocess.run(["nm", os.path.join(BUILD, "shim.o")], capture_output=True, text=True, check=True).stdout
-    for k in ("piecewise_linear", "ib_4", "ib_6", "bspline_3", "bspline_4", "ib_3", "bspline_5", "bspline_6", "piecewise_cubic", "ib_5", "piecewise_constant"):
+    for k in ("piecewise_linear", "ib_4", "ib_6", "bspline_3", "bspline_4", "ib_3", "bspline_5", "bspline_6", "piecewise_cubic", "ib_5", "piecewise_constant",
+              "composite_bspline_32", "composite_bspline_23", "composite_bspline_43", "composite_bspline_34", "composite_bspline_54",
+              "composite_bspline_45", "composite_bspline_65", "composite_bspline_56", "discontinuous_linear", "ib_4_w8"):
         for op in ("interp", "spread"):
             for d in ("2d", "3d"):
                 assert f" T lagrangian_{k}_{op}{d}_" in out
