@@ -44,6 +44,7 @@ constexpr int INTERP_THREADS = 256;
 // A tile of the uniform benchmark holds 256 +- 16 markers: with 256 threads every second tile pays a second, almost empty
 // pass over the stencil gather.  Kernels whose register need allows three 320-thread CTAs per SM take 320 threads.
 constexpr int INTERP_THREADS_WIDE = 320;
+constexpr bool INTERP_ROT_DEFAULT = false;  // until measured on the GPU (IBK_INTERP_ROT=1 selects interp_rot_kernel)
 constexpr bool INTERP_WIDE_DEFAULT = false; // until measured on the GPU (IBK_INTERP_WIDE=1 selects it)
 
 template <int NDIM, int K, int NT>
@@ -238,6 +239,236 @@ __global__ void __launch_bounds__(NT, (NT > 256) ? 3 : 1)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bank-conflict-free gather (3D, 4-point kernels with M = 2: staged box 22 x 20 x 20).
+// A thread gathers the 64 stencil values of one marker with the same 64 offsets as every other lane, so the bank
+// pattern of all 64 loads is decided by the lanes' box origins: random origins cost 2.9 wavefronts per half-warp load
+// (ncu: 300 M shared wavefronts against 104 M ideal).  Two facts remove them:
+//  * rows (j, k) of the box add 6 j + 8 k (mod 16) to the 8-byte bank: row q = 4 k + j adds 6 q.  A lane that visits
+//    its 16 rows in the ROTATED order q + r therefore shifts all its loads by 6 r, i.e. to any bank of the same parity
+//    (6 r runs over the even residues for r = 0..7), and keeps that shift for all 64 loads.
+//  * the parity of a lane's bank is the parity of its x origin.  The markers of a chunk are split into an even and an
+//    odd list (deterministic ballot scan) and a half-warp takes 8 of each: lane l aims at bank 2 (l & 7) + (l >> 3),
+//    so the 16 lanes of a half-warp always hit 16 different banks: one wavefront per half-warp load.
+// The rotation only reorders the 16 row sums of a marker; which rotation a marker gets depends on its rank in its
+// parity list, i.e. on the tile's markers alone: results are reproducible run to run.
+// ---------------------------------------------------------------------------------------------
+template <int K, int NT>
+__global__ void __launch_bounds__(NT, 3)
+    interp_rot_kernel(const __grid_constant__ TileParams tp, const __grid_constant__ TmaMapSet maps, InterpArgs args)
+{
+    constexpr int NDIM = 3;
+    constexpr int W = KTraits<K>::W;
+    constexpr int M = KTraits<K>::M;
+    constexpr int S = TILE + 2 * M;
+    constexpr int SX = S + 2;
+    static_assert(W == 4 && (SX % 16) == 6 && ((S * SX) % 16) == 8, "row q = 4 k + j shifts the bank by 6 q");
+    constexpr int NWARP = NT / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* su = reinterpret_cast<double*>(smem_raw);
+    __shared__ uint64_t bar;
+    __shared__ unsigned short plist[2][NT]; // chunk-local marker numbers with an even / odd x origin
+    __shared__ int wcnt[2][NWARP];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x;
+    int t[3];
+    {
+        int r = tile;
+        t[0] = r % tp.nt[0];
+        r /= tp.nt[0];
+        t[1] = r % tp.nt[1];
+        t[2] = r / tp.nt[1];
+    }
+    if (args.part)
+    {
+        bool in = true;
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) in = in && t[d] >= args.sel_lo[d] && t[d] <= args.sel_hi[d];
+        if ((args.part == 1) != in) return;
+    }
+    const int b0 = tp.brick_base + tile * 64;
+    const int s0 = args.brick_start[b0];
+    const int s1 = args.brick_start[b0 + 64];
+    if (s0 >= s1) return;
+    int sp0[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) sp0[d] = TILE * t[d] - M;
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    if (threadIdx.x == 0)
+    {
+        for (int a = 1; a < tp.ncomp; ++a)
+        {
+            const CompGeom& cg = tp.comp[a];
+            int c0 = sp0[0] - cg.pp0[0];
+            c0 -= (c0 & 1);
+            const int c1 = sp0[1] - cg.pp0[1], c2 = sp0[2] - cg.pp0[2];
+            asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&maps.m[a]), "r"(c0), "r"(c1), "r"(c2) : "memory");
+        }
+    }
+    for (int a = 0; a < tp.ncomp; ++a)
+    {
+        const CompGeom& cg = tp.comp[a];
+        int e0[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) e0[d] = sp0[d] - cg.pp0[d];
+        const int xodd = e0[0] & 1;
+        e0[0] -= xodd;
+        const int sx0 = sp0[0] - xodd; // pp coordinate of the first staged column
+        if (threadIdx.x == 0)
+        {
+            constexpr uint32_t bytes = SX * S * S * sizeof(double);
+            fence_proxy_async_smem();
+            mbar_expect_tx(&bar, bytes);
+            tma_load_3d(su, &maps.m[a], &bar, e0[0], e0[1], e0[2]);
+        }
+        bool waited = false;
+        for (int chunk = s0; chunk < s1; chunk += NT)
+        {
+            // ---- the chunk's markers by the parity of their x origin, in storage order (ballot scan: deterministic)
+            const int i1 = chunk + threadIdx.x;
+            const bool valid = i1 < s1;
+            int par = 0;
+            if (valid)
+            {
+                const double xs = args.X[i1];
+                const double xr = args.Xraw ? args.Xraw[i1] : xs;
+                double wtmp[W];
+                int l;
+                stencil_1d<K>(xs, xr, tp.xl[0][cg.var[0]], tp.dx[0], l, wtmp, 0 == cg.axis);
+                par = (l + tp.G - sx0) & 1;
+            }
+            const unsigned mE = __ballot_sync(0xffffffffu, valid && par == 0), mO = __ballot_sync(0xffffffffu, valid && par == 1);
+            if (lane == 0)
+            {
+                wcnt[0][warp] = __popc(mE);
+                wcnt[1][warp] = __popc(mO);
+            }
+            __syncthreads();
+            int nE = 0, nO = 0, bE = 0, bO = 0;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w)
+            {
+                if (w == warp)
+                {
+                    bE = nE;
+                    bO = nO;
+                }
+                nE += wcnt[0][w];
+                nO += wcnt[1][w];
+            }
+            if (valid)
+            {
+                const unsigned lt = (1u << lane) - 1u;
+                if (par == 0)
+                    plist[0][bE + __popc(mE & lt)] = (unsigned short)threadIdx.x;
+                else
+                    plist[1][bO + __popc(mO & lt)] = (unsigned short)threadIdx.x;
+            }
+            __syncthreads();
+            if (!waited)
+            {
+                mbar_wait(&bar, phase);
+                phase ^= 1;
+                waited = true;
+            }
+            // ---- gather: a half-warp takes 8 even and 8 odd markers
+            const int hl = threadIdx.x & 15, grp = hl >> 3;
+            const int ngrp = grp ? nO : nE;
+            const int nmax = max(nE, nO);
+            for (int slot = threadIdx.x >> 4; slot * 8 < nmax; slot += NT / 16)
+            {
+                const int idx = slot * 8 + (hl & 7);
+                if (idx >= ngrp) continue;
+                const int i = chunk + plist[grp][idx];
+                double w[NDIM][W];
+                int lo[NDIM];
+                bool staged = true;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d)
+                {
+                    const double xs = args.X[d * args.x_stride + i];
+                    const double xr = args.Xraw ? args.Xraw[d * args.x_stride + i] : xs;
+                    int l;
+                    stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w[d], d == cg.axis);
+                    lo[d] = l + tp.G;
+                    staged = staged && (lo[d] >= sp0[d]) && (lo[d] + W <= sp0[d] + S);
+                }
+                double acc = 0.0;
+                if (staged)
+                {
+                    const int b = ((lo[2] - sp0[2]) * S + (lo[1] - sp0[1])) * SX + (lo[0] - sx0);
+                    const int tgt = 2 * (hl & 7) + grp; // this lane's bank; b has the parity of grp
+                    const int r = (3 * (((tgt - b) & 15) >> 1)) & 7;
+                    const int rj = r & 3, rk = r >> 2;
+                    auto sel4 = [](const double* v, int q) { return q == 0 ? v[0] : q == 1 ? v[1] : q == 2 ? v[2] : v[3]; };
+                    double w1r[W], w2r[W];
+                    int jo[W], ko[W];
+                    bool cy[W];
+#pragma unroll
+                    for (int j = 0; j < W; ++j)
+                    {
+                        const int jj = (j + rj) & 3, kk = (j + rk) & 3;
+                        w1r[j] = sel4(w[1], jj);
+                        jo[j] = jj * SX;
+                        cy[j] = (j + rj) >= 4;
+                        w2r[j] = sel4(w[2], kk);
+                        ko[j] = kk * (S * SX);
+                    }
+                    const double* bp = su + b;
+#pragma unroll
+                    for (int k = 0; k < W; ++k)
+#pragma unroll
+                        for (int j = 0; j < W; ++j)
+                        {
+                            // static step 4 k + j visits row 4 k + j + r: (j + rj) & 3 in plane (k + rk + carry) & 3
+                            const double w2s = cy[j] ? w2r[(k + 1) & 3] : w2r[k];
+                            const int kos = cy[j] ? ko[(k + 1) & 3] : ko[k];
+                            const double wyz = w1r[j] * w2s;
+                            const double* row = bp + jo[j] + kos;
+#pragma unroll
+                            for (int ii = 0; ii < W; ++ii) acc += (w[0][ii] * wyz) * row[ii];
+                        }
+                }
+                else
+                {
+                    // clipped global path (3d.f.m4:1309-1327)
+#pragma unroll
+                    for (int k = 0; k < W; ++k)
+                    {
+                        const int gk = lo[2] + k - cg.pp0[2];
+                        if (gk < 0 || gk >= cg.n[2]) continue;
+#pragma unroll
+                        for (int j = 0; j < W; ++j)
+                        {
+                            const int gj = lo[1] + j - cg.pp0[1];
+                            if (gj < 0 || gj >= cg.n[1]) continue;
+                            const double wyz = w[1][j] * w[2][k];
+#pragma unroll
+                            for (int ii = 0; ii < W; ++ii)
+                            {
+                                const int gi = lo[0] + ii - cg.pp0[0];
+                                if (gi < 0 || gi >= cg.n[0]) continue;
+                                acc += (w[0][ii] * wyz) * cg.ptr[((long long)gk * cg.n[1] + gj) * cg.pitch + gi];
+                            }
+                        }
+                    }
+                }
+                const long long row = args.src ? (long long)args.src[i] : (long long)i;
+                args.V[cg.vcol * args.v_cstride + row * args.v_istride] = acc;
+            }
+            __syncthreads(); // the lists and (after the last chunk) su are free again
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -322,6 +553,13 @@ static cudaError_t launch_interp_t(Launcher& L, const TileParams& tp, const Bins
         L.launches++;
         return cudaGetLastError();
     };
+    if constexpr (NDIM == 3 && M == 2 && KTraits<K>::W == 4)
+    {
+        // the conflict-free gather needs every component staged by TMA
+        static const char* env = getenv("IBK_INTERP_ROT"); // 0 / 1 overrides the default
+        static const bool rot = env ? atoi(env) != 0 : INTERP_ROT_DEFAULT;
+        if (rot && args.tma_mask == (1u << tp.ncomp) - 1u) return go(interp_rot_kernel<K, INTERP_THREADS_WIDE>, INTERP_THREADS_WIDE);
+    }
     if constexpr (NDIM == 3 && M <= 2 && KTraits<K>::W <= 4)
     {
         static const char* env = getenv("IBK_INTERP_WIDE"); // 0 / 1 overrides the default

@@ -37,6 +37,7 @@ void make_tile_params(TileParams& tp, int ndim, const double* dx, const double x
 // halo kernels
 // ---------------------------------------------------------------------------------------------
 constexpr int HALO_MAXSRC = 64;
+constexpr int HALO_FILTER_DEFAULT = 0; // until measured on the GPU (IBK_HALO_FILTER=1 selects it)
 struct HaloSrc
 {
     const double* ptr;
@@ -55,6 +56,7 @@ struct HaloArgs
     int ilo[3], ihi[3]; // interior (side) box of the destination
     int rim;            // ghost width (thickness of the interior rim that ghosts of others can reach)
     int nsrc;
+    int filter; // 1: the kernels first narrow the sources down to those that can reach their slab
     HaloSrc src[HALO_MAXSRC];
 };
 
@@ -101,6 +103,65 @@ __device__ __forceinline__ bool slab_box(int ndim, int slab, const int* olo, con
     return true;
 }
 
+
+// The sources of a halo operation that can reach a slab at all, in canonical order (one warp tests them; a periodic
+// single patch has 26 images of itself, a z slab meets 9 of them, an x slab one).
+template <bool INTERIOR>
+__device__ __forceinline__ int slab_sources(const HaloArgs& A, const int* lo, const int* hi, unsigned char* list)
+{
+    __shared__ int n_out;
+    if (!A.filter)
+    {
+        if (threadIdx.x < A.nsrc) list[threadIdx.x] = (unsigned char)threadIdx.x;
+        __syncthreads();
+        return A.nsrc;
+    }
+    if (threadIdx.x < 32)
+    {
+        const int lane = threadIdx.x;
+        int n = 0;
+        for (int base = 0; base < A.nsrc; base += 32)
+        {
+            const int s = base + lane;
+            bool hit = false;
+            if (s < A.nsrc)
+            {
+                const HaloSrc& S = A.src[s];
+                hit = true;
+                for (int d = 0; d < 3; ++d)
+                {
+                    const int slo = INTERIOR ? S.ilo[d] : S.alo[d], shi = INTERIOR ? S.ihi[d] : S.ahi[d];
+                    hit = hit && max(lo[d], slo) <= min(hi[d], shi);
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) list[n + __popc(m & ((1u << lane) - 1u))] = (unsigned char)s;
+            n += __popc(m);
+        }
+        if (lane == 0) n_out = n;
+    }
+    __syncthreads();
+    return n_out;
+}
+// element q of a slab of extents (e0, e1, .): 32-bit arithmetic whenever the slab allows it
+__device__ __forceinline__ void slab_coords(long long q, bool small, int e0, int e1, int& i0, int& i1, int& i2)
+{
+    if (small)
+    {
+        const unsigned qq = (unsigned)q, t = qq / (unsigned)e0;
+        i0 = (int)(qq - t * (unsigned)e0);
+        i2 = (int)(t / (unsigned)e1);
+        i1 = (int)(t - (unsigned)i2 * (unsigned)e1);
+    }
+    else
+    {
+        i0 = (int)(q % e0);
+        const long long t = q / e0;
+        i1 = (int)(t % e1);
+        i2 = (int)(t / e1);
+    }
+}
+
 // u ghost fill: every ghost element of dst takes the value of the first source whose INTERIOR holds it.
 __global__ void halo_fill_kernel(const HaloArgs* __restrict__ argp)
 {
@@ -109,14 +170,19 @@ __global__ void halo_fill_kernel(const HaloArgs* __restrict__ argp)
     if (!slab_box(A.ndim, blockIdx.y, A.alo, A.ahi, A.ilo, A.ihi, lo, hi)) return;
     const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
     const long long total = (long long)e0 * e1 * e2;
+    __shared__ unsigned char cand[HALO_MAXSRC];
+    const int ncand = slab_sources<true>(A, lo, hi, cand);
+    const bool small = total < (1ll << 31);
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
     {
-        const int I0 = lo[0] + (int)(q % e0);
-        const long long t = q / e0;
-        const int I1 = lo[1] + (int)(t % e1), I2 = lo[2] + (int)(t / e1);
-        for (int s = 0; s < A.nsrc; ++s)
+        int I0, I1, I2;
+        slab_coords(q, small, e0, e1, I0, I1, I2);
+        I0 += lo[0];
+        I1 += lo[1];
+        I2 += lo[2];
+        for (int c = 0; c < ncand; ++c)
         {
-            const HaloSrc& S = A.src[s];
+            const HaloSrc& S = A.src[cand[c]];
             if (I0 >= S.ilo[0] && I0 <= S.ihi[0] && I1 >= S.ilo[1] && I1 <= S.ihi[1] && I2 >= S.ilo[2] && I2 <= S.ihi[2])
             {
                 const double v = S.ptr[((long long)(I2 - S.alo[2]) * S.n1 + (I1 - S.alo[1])) * S.pitch + (I0 - S.alo[0])];
@@ -148,17 +214,23 @@ __global__ void halo_accum_kernel(const HaloArgs* __restrict__ argp)
     if (!slab_box(A.ndim, blockIdx.y, A.ilo, A.ihi, inlo, inhi, lo, hi)) return;
     const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
     const long long total = (long long)e0 * e1 * e2;
+    __shared__ unsigned char cand[HALO_MAXSRC];
+    const int ncand = slab_sources<false>(A, lo, hi, cand);
+    if (ncand == 0) return;
+    const bool small = total < (1ll << 31);
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
     {
-        const int I0 = lo[0] + (int)(q % e0);
-        const long long t = q / e0;
-        const int I1 = lo[1] + (int)(t % e1), I2 = lo[2] + (int)(t / e1);
+        int I0, I1, I2;
+        slab_coords(q, small, e0, e1, I0, I1, I2);
+        I0 += lo[0];
+        I1 += lo[1];
+        I2 += lo[2];
         double* p = A.dst + ((long long)(I2 - A.alo[2]) * A.n1 + (I1 - A.alo[1])) * A.pitch + (I0 - A.alo[0]);
         double acc = *p;
         bool any = false;
-        for (int s = 0; s < A.nsrc; ++s)
+        for (int c = 0; c < ncand; ++c)
         {
-            const HaloSrc& S = A.src[s];
+            const HaloSrc& S = A.src[cand[c]];
             const bool in_arr = I0 >= S.alo[0] && I0 <= S.ahi[0] && I1 >= S.alo[1] && I1 <= S.ahi[1] && I2 >= S.alo[2] && I2 <= S.ahi[2];
             if (!in_arr) continue;
             const bool in_int = I0 >= S.ilo[0] && I0 <= S.ihi[0] && I1 >= S.ilo[1] && I1 <= S.ihi[1] && I2 >= S.ilo[2] && I2 <= S.ihi[2];
@@ -179,11 +251,14 @@ __global__ void halo_zero_ghost_kernel(const HaloArgs* __restrict__ argp)
     if (!slab_box(A.ndim, blockIdx.y, A.alo, A.ahi, A.ilo, A.ihi, lo, hi)) return;
     const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
     const long long total = (long long)e0 * e1 * e2;
+    const bool small = total < (1ll << 31);
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
     {
-        const int I0 = lo[0] + (int)(q % e0);
-        const long long t = q / e0;
-        const int I1 = lo[1] + (int)(t % e1), I2 = lo[2] + (int)(t / e1);
+        int I0, I1, I2;
+        slab_coords(q, small, e0, e1, I0, I1, I2);
+        I0 += lo[0];
+        I1 += lo[1];
+        I2 += lo[2];
         A.dst[((long long)(I2 - A.alo[2]) * A.n1 + (I1 - A.alo[1])) * A.pitch + (I0 - A.alo[0])] = 0.0;
     }
 }
@@ -384,6 +459,10 @@ static int build_halo_plan(ibk_ctx* ctx)
                 A.n1 = ps.n[axis][1];
                 A.ndim = ndim;
                 A.rim = 0;
+                {
+                    static const char* env = getenv("IBK_HALO_FILTER"); // 0 / 1 overrides the default
+                    A.filter = env ? (atoi(env) != 0) : HALO_FILTER_DEFAULT;
+                }
                 for (int d = 0; d < 3; ++d)
                 {
                     A.alo[d] = alo[d];
