@@ -41,14 +41,14 @@ struct InterpArgs
 };
 
 constexpr int INTERP_THREADS = 256;
-// A tile of the uniform benchmark holds 256 +- 16 markers: with 256 threads every second tile pays a second, almost empty
-// pass over the stencil gather.  Kernels whose register need allows three 320-thread CTAs per SM take 320 threads.
+// A tile of the uniform benchmark holds 256 +- 16 markers: interp_rot_kernel takes 320 threads (20 half-warps x 8 markers
+// per parity list) so that one pass covers a tile.  (Measured: 320 threads alone do nothing for the plain tile kernel, 1.56 ms.)
 constexpr int INTERP_THREADS_WIDE = 320;
-constexpr bool INTERP_ROT_DEFAULT = false;  // until measured on the GPU (IBK_INTERP_ROT=1 selects interp_rot_kernel)
-constexpr bool INTERP_WIDE_DEFAULT = false; // until measured on the GPU (IBK_INTERP_WIDE=1 selects it)
+constexpr bool INTERP_ROT_DEFAULT = true; // measured: 1.35 ms against 1.54 ms on the C5 shard (IBK_INTERP_ROT=0: the plain tile kernel)
 
+// (min CTAs per SM = what the staged box allows: without it ptxas takes 110 registers and only two CTAs fit)
 template <int NDIM, int K, int NT>
-__global__ void __launch_bounds__(NT, (NT > 256) ? 3 : 1)
+__global__ void __launch_bounds__(NT, (KTraits<K>::M <= 2) ? 3 : (KTraits<K>::M == 3) ? 2 : 1)
     interp_tile_kernel(const __grid_constant__ TileParams tp, const __grid_constant__ TmaMapSet maps, InterpArgs args)
 {
     constexpr int W = KTraits<K>::W;
@@ -559,12 +559,6 @@ static cudaError_t launch_interp_t(Launcher& L, const TileParams& tp, const Bins
         static const char* env = getenv("IBK_INTERP_ROT"); // 0 / 1 overrides the default
         static const bool rot = env ? atoi(env) != 0 : INTERP_ROT_DEFAULT;
         if (rot && args.tma_mask == (1u << tp.ncomp) - 1u) return go(interp_rot_kernel<K, INTERP_THREADS_WIDE>, INTERP_THREADS_WIDE);
-    }
-    if constexpr (NDIM == 3 && M <= 2 && KTraits<K>::W <= 4)
-    {
-        static const char* env = getenv("IBK_INTERP_WIDE"); // 0 / 1 overrides the default
-        static const bool wide = env ? atoi(env) != 0 : INTERP_WIDE_DEFAULT;
-        if (wide) return go(interp_tile_kernel<NDIM, K, INTERP_THREADS_WIDE>, INTERP_THREADS_WIDE);
     }
     return go(interp_tile_kernel<NDIM, K, INTERP_THREADS>, INTERP_THREADS);
 }

@@ -56,7 +56,8 @@ constexpr int SPREAD_THREADS = 256;
 // them (2 or 3 warps per marker), lanes = 4 x 4 (x, y) points x 2 planes.  No two warps share a word, so the only CTA
 // barriers left are the two around the stencil evaluation of a window; the order of the additions at a grid point is
 // the window's marker order, the same as with the brick colours (results are bit-identical to that path).
-constexpr bool SPREAD_PLANES_DEFAULT = false; // until measured on the GPU (IBK_SPREAD_PLANES=1 selects it)
+constexpr bool SPREAD_PLANES_DEFAULT = false; // measured SLOWER than the brick colours (5.83 ms against 4.41 ms on the C5 shard:
+                                              // 2.5 dependent visits per marker instead of one); kept for reference, IBK_SPREAD_PLANES=1
 constexpr int SPREAD_THREADS_PLANES = 320; // 10 warps = the 10 plane pairs of a 20-plane block
 template <int NDIM, int K>
 constexpr bool spread_planes_ok = (NDIM == 3 && KTraits<K>::W == 4 && KTraits<K>::M == 2);
@@ -826,7 +827,8 @@ static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bin
     std::memset(&maps, 0, sizeof(maps));
     args.tma_mask = 0;
     static const bool no_tma = getenv("IBK_NO_TMA") != nullptr;
-    static const int promo = getenv("IBK_TMA_PROMO_SPREAD") ? atoi(getenv("IBK_TMA_PROMO_SPREAD")) : 2;
+    // L2 promotion of the block loads: 64 B measured best (4.28 ms; 128 B and none 4.41 ms on the C5 shard)
+    static const int promo = getenv("IBK_TMA_PROMO_SPREAD") ? atoi(getenv("IBK_TMA_PROMO_SPREAD")) : 1;
     for (int a = 0; a < tp.ncomp; ++a)
         if (!no_tma && ((tp.comp[a].pp0[0] + M + XO) % 2 == 0) && make_tensor_map(&maps.m[a], tp.comp[a], NDIM, RX, R, R, promo))
             args.tma_mask |= (1u << a);

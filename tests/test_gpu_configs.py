@@ -176,7 +176,8 @@ def test_nonperiodic_walls(api, kernel):
 
 
 @pytest.mark.parametrize("kernel", ["IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR", "IB_3", "BSPLINE_5", "BSPLINE_6",
-                                    "PIECEWISE_CUBIC", "IB_5", "PIECEWISE_CONSTANT"])
+                                    "PIECEWISE_CUBIC", "IB_5", "PIECEWISE_CONSTANT", "COMPOSITE_BSPLINE_32", "COMPOSITE_BSPLINE_43",
+                                    "COMPOSITE_BSPLINE_45", "COMPOSITE_BSPLINE_56", "DISCONTINUOUS_LINEAR", "IB_4_W8"])
 def test_dense_bricks_every_kernel(api, kernel):
     """A structure-like cloud: 40k markers in a slab a few cells thick that crosses patch boundaries and the periodic
     boundary, i.e. hundreds of markers per 4^3-cell brick: these bricks take spread_dense_kernel (register
