@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(NT, 3)
     __shared__ uint64_t bar;
     __shared__ unsigned short plist[2][NT]; // chunk-local marker numbers with an even / odd x origin
     __shared__ int wcnt[2][NWARP];
+    __shared__ int ntot[2];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = blockIdx.x;
@@ -330,49 +331,67 @@ __global__ void __launch_bounds__(NT, 3)
             tma_load_3d(su, &maps.m[a], &bar, e0[0], e0[1], e0[2]);
         }
         bool waited = false;
+        // components with the same x geometry (all but the x-normal one) have the same parity lists
+        const bool same_lists = a > 0 && s1 - s0 <= NT && cg.var[0] == tp.comp[a - 1].var[0] && cg.pp0[0] == tp.comp[a - 1].pp0[0] &&
+                                (0 == cg.axis) == (0 == tp.comp[a - 1].axis);
         for (int chunk = s0; chunk < s1; chunk += NT)
         {
             // ---- the chunk's markers by the parity of their x origin, in storage order (ballot scan: deterministic)
             const int i1 = chunk + threadIdx.x;
             const bool valid = i1 < s1;
             int par = 0;
-            if (valid)
+            if (!same_lists)
             {
-                const double xs = args.X[i1];
-                const double xr = args.Xraw ? args.Xraw[i1] : xs;
-                double wtmp[W];
-                int l;
-                stencil_1d<K>(xs, xr, tp.xl[0][cg.var[0]], tp.dx[0], l, wtmp, 0 == cg.axis);
-                par = (l + tp.G - sx0) & 1;
-            }
-            const unsigned mE = __ballot_sync(0xffffffffu, valid && par == 0), mO = __ballot_sync(0xffffffffu, valid && par == 1);
-            if (lane == 0)
-            {
-                wcnt[0][warp] = __popc(mE);
-                wcnt[1][warp] = __popc(mO);
-            }
-            __syncthreads();
-            int nE = 0, nO = 0, bE = 0, bO = 0;
-#pragma unroll
-            for (int w = 0; w < NWARP; ++w)
-            {
-                if (w == warp)
+                if (valid)
                 {
-                    bE = nE;
-                    bO = nO;
+                    if (a == 0) // the gather reads y and z through the lists (uncoalesced): have them in L1 by then
+                    {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(args.X + args.x_stride + i1));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(args.X + 2 * args.x_stride + i1));
+                    }
+                    const double xs = args.X[i1];
+                    const double xr = args.Xraw ? args.Xraw[i1] : xs;
+                    double wtmp[W];
+                    int l;
+                    stencil_1d<K>(xs, xr, tp.xl[0][cg.var[0]], tp.dx[0], l, wtmp, 0 == cg.axis);
+                    par = (l + tp.G - sx0) & 1;
                 }
-                nE += wcnt[0][w];
-                nO += wcnt[1][w];
+                const unsigned mE = __ballot_sync(0xffffffffu, valid && par == 0), mO = __ballot_sync(0xffffffffu, valid && par == 1);
+                if (lane == 0)
+                {
+                    wcnt[0][warp] = __popc(mE);
+                    wcnt[1][warp] = __popc(mO);
+                }
+                __syncthreads();
+                int nE = 0, nO = 0, bE = 0, bO = 0;
+    #pragma unroll
+                for (int w = 0; w < NWARP; ++w)
+                {
+                    if (w == warp)
+                    {
+                        bE = nE;
+                        bO = nO;
+                    }
+                    nE += wcnt[0][w];
+                    nO += wcnt[1][w];
+                }
+                // (these totals go to ntot[] below; the gather reads them from there)
+                if (valid)
+                {
+                    const unsigned lt = (1u << lane) - 1u;
+                    if (par == 0)
+                        plist[0][bE + __popc(mE & lt)] = (unsigned short)threadIdx.x;
+                    else
+                        plist[1][bO + __popc(mO & lt)] = (unsigned short)threadIdx.x;
+                }
+                if (threadIdx.x == 0)
+                {
+                    ntot[0] = nE;
+                    ntot[1] = nO;
+                }
+                __syncthreads();
             }
-            if (valid)
-            {
-                const unsigned lt = (1u << lane) - 1u;
-                if (par == 0)
-                    plist[0][bE + __popc(mE & lt)] = (unsigned short)threadIdx.x;
-                else
-                    plist[1][bO + __popc(mO & lt)] = (unsigned short)threadIdx.x;
-            }
-            __syncthreads();
+            const int nE = ntot[0], nO = ntot[1];
             if (!waited)
             {
                 mbar_wait(&bar, phase);
@@ -423,6 +442,7 @@ __global__ void __launch_bounds__(NT, 3)
                         ko[j] = kk * (S * SX);
                     }
                     const double* bp = su + b;
+                    double pacc[W] = { 0.0, 0.0, 0.0, 0.0 };
 #pragma unroll
                     for (int k = 0; k < W; ++k)
 #pragma unroll
@@ -434,8 +454,9 @@ __global__ void __launch_bounds__(NT, 3)
                             const double wyz = w1r[j] * w2s;
                             const double* row = bp + jo[j] + kos;
 #pragma unroll
-                            for (int ii = 0; ii < W; ++ii) acc += (w[0][ii] * wyz) * row[ii];
+                            for (int ii = 0; ii < W; ++ii) pacc[j] += (w[0][ii] * wyz) * row[ii];
                         }
+                    acc = (pacc[0] + pacc[1]) + (pacc[2] + pacc[3]); // four chains of 16 instead of one of 64
                 }
                 else
                 {
