@@ -42,9 +42,10 @@ struct InterpArgs
 
 constexpr int INTERP_THREADS = 256;
 // A tile of the uniform benchmark holds 256 +- 16 markers: interp_rot_kernel takes 320 threads (20 half-warps x 8 markers
-// per parity list) so that one pass covers a tile.  (Measured: 320 threads alone do nothing for the plain tile kernel, 1.56 ms.)
+// per parity list) so that one pass covers a tile.  (Measured: 320 threads alone do nothing for the plain tile kernel, 1.56 ms;
+// 288 threads for this one: 1.31 ms against 1.26 ms; one CTA per (tile, component): 1.38 ms.)
 constexpr int INTERP_THREADS_WIDE = 320;
-constexpr bool INTERP_ROT_DEFAULT = true; // measured: 1.35 ms against 1.54 ms on the C5 shard (IBK_INTERP_ROT=0: the plain tile kernel)
+constexpr bool INTERP_ROT_DEFAULT = true; // measured: 1.26 ms against 1.54 ms on the C5 shard (IBK_INTERP_ROT=0: the plain tile kernel)
 
 // (min CTAs per SM = what the staged box allows: without it ptxas takes 110 registers and only two CTAs fit)
 template <int NDIM, int K, int NT>
@@ -193,9 +194,13 @@ __global__ void __launch_bounds__(NT, (KTraits<K>::M <= 2) ? 3 : (KTraits<K>::M 
 #pragma unroll
                         for (int j = 0; j < W; ++j)
                         {
+                            // the row's x sum first, then its (y, z) weight (the terms of w0 (w1 w2) u, associated
+                            // differently: W + 1 instead of 2 W + 1 fp64 instructions per row)
                             const double wyz = w[1][j] * w[2][k];
+                            double rs = w[0][0] * base[(k * S + j) * SX];
 #pragma unroll
-                            for (int ii = 0; ii < W; ++ii) acc += (w[0][ii] * wyz) * base[(k * S + j) * SX + ii];
+                            for (int ii = 1; ii < W; ++ii) rs += w[0][ii] * base[(k * S + j) * SX + ii];
+                            acc += wyz * rs;
                         }
                 }
                 else
@@ -453,8 +458,12 @@ __global__ void __launch_bounds__(NT, 3)
                             const int kos = cy[j] ? ko[(k + 1) & 3] : ko[k];
                             const double wyz = w1r[j] * w2s;
                             const double* row = bp + jo[j] + kos;
+                            // the row's x sum first, then its (y, z) weight: 5 instead of 9 fp64 instructions per row
+                            // (same terms as w0 (w1 w2) u, associated differently: rounding-level difference only)
+                            double rs = w[0][0] * row[0];
 #pragma unroll
-                            for (int ii = 0; ii < W; ++ii) pacc[j] += (w[0][ii] * wyz) * row[ii];
+                            for (int ii = 1; ii < W; ++ii) rs += w[0][ii] * row[ii];
+                            pacc[j] += wyz * rs;
                         }
                     acc = (pacc[0] + pacc[1]) + (pacc[2] + pacc[3]); // four chains of 16 instead of one of 64
                 }
