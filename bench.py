@@ -450,7 +450,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "kernel": "spread_tile_kernel<3,IB_4> (+ fix-up)", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes": spread_bytes, "launch_ms": sp_ms,
-                         "interp": {"kernel": "interp_tile_kernel<3,IB_4>", "achieved": interp_bytes / (in_ms * 1e-3) / 1e9,
+                         "interp": {"kernel": "interp_rot_kernel<IB_4,320>", "achieved": interp_bytes / (in_ms * 1e-3) / 1e9,
                                     "frac": interp_bytes / (in_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": interp_bytes,
                                     "traffic": traffic_interp,
                                     "launch_ms": in_ms},

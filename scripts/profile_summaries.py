@@ -1,5 +1,5 @@
 """Turns the ncu outputs of a round into the committed summaries under profiles/.
-usage: profile_summaries.py <launch_list.csv> <spread.ncu-rep> <round>"""
+usage: profile_summaries.py <launch_list.csv> <spread.ncu-rep> <round> [<interp.ncu-rep>]"""
 import csv, json, shutil, subprocess, sys, io
 lst, rep, rnd = sys.argv[1], sys.argv[2], int(sys.argv[3])
 root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
@@ -79,6 +79,28 @@ for k, vv in prof.items():
         new["(older) " + k.replace("(current", "(earlier")] = vv
     else:
         new[k] = vv
+if len(sys.argv) > 4:  # the interpolation kernel's full-set capture
+    out = subprocess.run(["ncu", "-i", sys.argv[4], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(io.StringIO(out)))
+    hh, u, v = r[0], r[1], r[2]
+    isum = {}
+    for k in want + ["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "memory_l1_wavefronts_shared_ideal"]:
+        for i, x in enumerate(hh):
+            if x == k:
+                isum[k] = {"value": v[i], "unit": u[i]}
+    st = {}
+    for i, x in enumerate(hh):
+        if x.startswith("smsp__pcsamp_warps_issue_stalled_") and not x.endswith("_not_issued"):
+            try:
+                st[x.replace("smsp__pcsamp_warps_issue_stalled_", "")] = float(v[i].replace(",", ""))
+            except ValueError:
+                pass
+    t = sum(st.values())
+    isum["stall_share_of_pc_samples"] = {k: round(x / t, 4) for k, x in sorted(st.items(), key=lambda kv: -kv[1]) if x / t > 0.01}
+    ikey = ("interp_rot_kernel<IB_4,320> (current); ncu --set full --clock-control none --import-source on -k regex:interp_rot -s 3 -c 1 "
+            "python bench.py --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1")
+    new = {k: vv for k, vv in new.items() if not k.startswith("interp_rot_kernel")}
+    new = {ikey: isum, **new}
 json.dump(new, open(path, "w"), indent=1)
 print(json.dumps(summ["stall_share_of_pc_samples"]))
 print({k: summ[k]["value"] for k in ("gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum")})
