@@ -26,6 +26,7 @@
 // A marker whose stencil does not fit the haloed block (possible only if its binning cell and its stencil
 // origin disagree by a rounding) is skipped here and spread by spread_fixup_kernel, one thread, in sorted
 // order, after the last colour.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -56,6 +57,8 @@ constexpr int SPREAD_THREADS = 256;
 // them (2 or 3 warps per marker), lanes = 4 x 4 (x, y) points x 2 planes.  No two warps share a word, so the only CTA
 // barriers left are the two around the stencil evaluation of a window; the order of the additions at a grid point is
 // the window's marker order, the same as with the brick colours (results are bit-identical to that path).
+constexpr bool SPREAD_CLUSTER_DEFAULT = false; // correct (all parity tests pass) but 13.6 ms: the read-modify-write of the share by
+                                               // the threads is far too slow; next: dense repack + TMA reducing store (IBK_SPREAD_CLUSTER=1)
 constexpr bool SPREAD_PLANES_DEFAULT = false; // measured SLOWER than the brick colours (5.83 ms against 4.41 ms on the C5 shard:
                                               // 2.5 dependent visits per marker instead of one); kept for reference, IBK_SPREAD_PLANES=1
 constexpr int SPREAD_THREADS_PLANES = 320; // 10 warps = the 10 plane pairs of a 20-plane block
@@ -83,6 +86,7 @@ struct SpreadArgs
     int cap; // markers whose stencil weights are staged at a time (sizes the dynamic shared memory)
     unsigned tma_mask; // bit a: the block of component a is loaded / stored by TMA (else zero-fill + red write-out)
     int part, sel_lo[3], sel_hi[3]; // MarkerView's tile selection
+    int tma_reduce;                 // 1 (3D): the block starts from zero and is ADDED to f by TMA's reducing store
     int dense_thresh;               // > 0: bricks with more markers than this are left to spread_dense_kernel
 };
 
@@ -123,7 +127,13 @@ __constant__ BrickColouring<NDIM, NC> c_colouring = BrickColouring<NDIM, NC>(); 
 template <int NDIM, int NC>
 __device__ const BrickColouring<NDIM, NC> d_colouring = BrickColouring<NDIM, NC>(); // per-lane reads (order[])
 
-template <int NDIM, int K, bool PL>
+// CL (3D): a thread-block CLUSTER of 2 x 2 x 2 CTAs acts as one 32^3 tile.  Each CTA accumulates the markers of its own
+// 16^3 tile into its own block starting from zero; after a cluster barrier it sums, in rank order, its own block and the
+// parts of its siblings' blocks (read through distributed shared memory) that cover its share of the cluster's
+// (32 + 2M)^3 points -- its tile plus the halo on the cluster's outer sides -- and adds that share to f once.  Only the
+// cluster's outer shell is shared with other launches (the colours are those of the cluster tiles), so f moves
+// ((32 + 2M) / 32)^3 times instead of ((16 + 2M) / 16)^3, and points nothing was spread to are neither read nor written.
+template <int NDIM, int K, bool PL, bool CL = false>
 __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     spread_tile_kernel(const __grid_constant__ TileParams tp, const __grid_constant__ TmaMapSet maps, SpreadArgs args)
 {
@@ -133,6 +143,7 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
     constexpr int NT = PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS;
     constexpr int NWARPS = NT / 32;
     static_assert(!PL || spread_planes_ok<NDIM, K>, "plane owners: 3D, W = 4, M = 2");
+    static_assert(!CL || (NDIM == 3 && !PL), "clusters: 3D, brick-colour accumulation");
     // TMA boxes of 8-byte elements must start on an even x coordinate and have an even x extent (16 bytes):
     // the block gets XO spare columns on the left and is RX wide in x.
     constexpr int XO = M & 1;
@@ -164,19 +175,36 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
 
     // which marker tile (of this launch's colour) and which component
     int t[3] = { 0, 0, 0 };
+    bool has_tile = true; // CL: the cluster tile may stick out of the tile grid
+    bool active = true;   // this CTA has markers to spread
+    const int crank = CL ? (int)(blockIdx.x & 7u) : 0; // rank in the cluster: bit d = upper half along d
     {
-        int r = blockIdx.x;
+        int r = CL ? (int)(blockIdx.x >> 3) : (int)blockIdx.x;
         t[0] = 2 * (r % args.ntc[0]) + args.colour[0];
         r /= args.ntc[0];
         t[1] = 2 * (r % args.ntc[1]) + args.colour[1];
         if (NDIM == 3) t[2] = 2 * (r / args.ntc[1]) + args.colour[2];
+        if constexpr (CL)
+        {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+                t[d] = 2 * t[d] + ((crank >> d) & 1); // (t[] held the cluster tile)
+                has_tile = has_tile && t[d] < tp.nt[d];
+            }
+            active = has_tile;
+        }
     }
     if (args.part)
     {
         bool in = true;
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) in = in && t[d] >= args.sel_lo[d] && t[d] <= args.sel_hi[d];
-        if ((args.part == 1) != in) return;
+        if ((args.part == 1) != in)
+        {
+            if constexpr (!CL) return;
+            active = false; // the other part's tile: nothing to spread, but the share still collects the siblings' halos
+        }
     }
     const int a = blockIdx.y;
     const CompGeom& cg = tp.comp[a];
@@ -184,7 +212,7 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
     const int b0 = tp.brick_base + tile * NBRICKS;
     // one coalesced read of the tile's NBRICKS + 1 segment offsets, and (independent of it) the colour order
     int my_q = 0;
-    if (threadIdx.x <= NBRICKS) sbs[threadIdx.x] = __ldg(&args.brick_start[b0 + threadIdx.x]);
+    if (threadIdx.x <= NBRICKS) sbs[threadIdx.x] = active ? __ldg(&args.brick_start[b0 + threadIdx.x]) : 0;
     if (threadIdx.x < NBRICKS) my_q = __ldg(&d_colouring<NDIM, NC>.order[threadIdx.x]);
     for (int q = threadIdx.x; q < args.cap; q += NT) relb[q] = 0;
 #ifdef IBK_TIMELINE
@@ -195,7 +223,11 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
 #endif
     __syncthreads();
     const int s0 = sbs[0], s1 = sbs[NBRICKS];
-    if (s0 >= s1) return;
+    if (s0 >= s1)
+    {
+        if constexpr (!CL) return;
+        active = false;
+    }
     TL(1);
 
     int blo[3]; // pp coordinate of the block's first point
@@ -206,9 +238,12 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
     // (Measured on B200: a TMA tensor STORE with a negative start coordinate traps, loads do not; the blocks of the
     // first tile per dimension therefore take the fallback.  The store also writes whole 16-byte units, i.e. one
     // element of the row padding when n[0] is odd: harmless, nothing reads the padding.)
-    const bool use_tma = ((args.tma_mask >> a) & 1u) && (blo[0] - XO - cg.pp0[0] >= 0) && (blo[1] - cg.pp0[1] >= 0) &&
+    const bool use_tma = !CL && ((args.tma_mask >> a) & 1u) && (blo[0] - XO - cg.pp0[0] >= 0) && (blo[1] - cg.pp0[1] >= 0) &&
                          (NDIM == 2 || blo[2] - cg.pp0[2] >= 0);
-    if (use_tma && threadIdx.x == 0)
+    // TMA's reducing store (cp.reduce.async.bulk.tensor .add; measured to work on fp64 tensors, scripts/tma_reduce_probe.cu):
+    // the block starts from zero and is added to f in L2, no load.  One CTA per grid point and launch: the order is fixed.
+    const bool use_red = NDIM == 3 && use_tma && args.tma_reduce;
+    if (use_tma && !use_red && threadIdx.x == 0)
     {
         mbar_init(&tma_bar, 1);
         mbar_fence_init();
@@ -216,7 +251,7 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
 
     // marker ranges of the bricks in colour-major order, and their running count (two-warp scan)
     int my_cnt = 0, my_incl = 0;
-    if (threadIdx.x < NBRICKS)
+    if (threadIdx.x < NBRICKS) // (an inactive CTA of a cluster has sbs[] = 0: no markers)
     {
         const int s = sbs[my_q], e = sbs[my_q + 1];
         bfirst[threadIdx.x] = s;
@@ -234,11 +269,11 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
         }
         if (lane == 31) wsum[warp] = my_incl;
     }
-    if (!use_tma)
+    if (!use_tma || use_red)
         for (int q = threadIdx.x; q < RPTS; q += NT) acc[q] = 0.0;
     __syncthreads();
     TL(2);
-    if (use_tma && threadIdx.x == 0)
+    if (use_tma && !use_red && threadIdx.x == 0)
     {
         mbar_expect_tx(&tma_bar, (uint32_t)(RPTS * sizeof(double)));
         if (NDIM == 3)
@@ -359,7 +394,7 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
         evaluate(par);
         __syncthreads();
         if (off == 0) TL(4);
-        if (use_tma && off == 0) mbar_wait(&tma_bar, 0); // the block holds f now
+        if (use_tma && !use_red && off == 0) mbar_wait(&tma_bar, 0); // the block holds f now
         if (off == 0) TL(5);
         const int col_lo = wcol[par][0], col_hi = wcol[par][1];
         if (off + cap < total) fetch(off + cap, par ^ 1);
@@ -465,6 +500,84 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
     }
     TL(8);
 
+    if constexpr (CL)
+    {
+        // ---- cluster write-out: this CTA's share of the cluster's points = own block + the siblings' halos, in rank order
+        namespace cgx = cooperative_groups;
+        cgx::cluster_group cluster = cgx::this_cluster();
+        cluster.sync(); // every block of the cluster is complete
+        if (has_tile)
+        {
+            constexpr int SH = TILE + M; // share edge: the tile and the halo on the cluster's outer side
+            constexpr int UNR = 8;       // points per thread and round: their loads are in flight together
+            unsigned sok = 0; // siblings that exist (their tile is inside the tile grid)
+#pragma unroll
+            for (int sr = 0; sr < 8; ++sr)
+            {
+                bool ok = true;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) ok = ok && (t[d] - ((crank >> d) & 1) + ((sr >> d) & 1)) < tp.nt[d];
+                if (ok) sok |= 1u << sr;
+            }
+            const int o0 = (crank & 1) ? M : 0, o1 = (crank & 2) ? M : 0, o2 = (crank & 4) ? M : 0;
+            // the element of f behind share point q (nullptr: outside the array)
+            auto gaddr = [&](int q) -> double* {
+                const int gi = blo[0] + q % SH + o0 - cg.pp0[0], gj = blo[1] + (q / SH) % SH + o1 - cg.pp0[1],
+                          gk = blo[2] + q / (SH * SH) + o2 - cg.pp0[2];
+                if (gi < 0 || gi >= cg.n[0] || gj < 0 || gj >= cg.n[1] || gk < 0 || gk >= cg.n[2]) return nullptr;
+                return cg.ptr + ((long long)(gk * cg.n[1] + gj) * cg.pitch + gi);
+            };
+            for (int q0 = threadIdx.x; q0 < SH * SH * SH; q0 += NT * UNR)
+            {
+                double v[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u)
+                {
+                    const int q = q0 + u * NT;
+                    v[u] = 0.0;
+                    if (q >= SH * SH * SH) continue;
+                    const int lx = q % SH + o0, ly = (q / SH) % SH + o1, lz = q / (SH * SH) + o2; // in this CTA's block
+                    // along d the other sibling's block holds the point too iff it lies in the 2M-wide overlap
+                    const unsigned both = ((crank & 1) ? (lx < 2 * M) : (lx >= TILE)) | (((crank & 2) ? (ly < 2 * M) : (ly >= TILE)) << 1) |
+                                          (((crank & 4) ? (lz < 2 * M) : (lz >= TILE)) << 2);
+                    if (both == 0)
+                        v[u] = acc[(lz * R + ly) * RX + lx + XO];
+                    else
+                    {
+#pragma unroll
+                        for (int sr = 0; sr < 8; ++sr)
+                        {
+                            const unsigned diff = (unsigned)sr ^ (unsigned)crank;
+                            if ((diff & ~both) != 0 || !((sok >> sr) & 1u)) continue;
+                            // the sibling's block starts 16 points later (earlier) along the dimensions where it is the upper (lower) one
+                            const int cx = lx + ((diff & 1) ? ((crank & 1) ? TILE : -TILE) : 0);
+                            const int cy = ly + ((diff & 2) ? ((crank & 2) ? TILE : -TILE) : 0);
+                            const int cz = lz + ((diff & 4) ? ((crank & 4) ? TILE : -TILE) : 0);
+                            v[u] += cluster.map_shared_rank(acc, sr)[(cz * R + cy) * RX + cx + XO];
+                        }
+                    }
+                }
+                // f += share: inside a launch a grid point belongs to exactly one CTA (plain read-modify-write, fixed order);
+                // points nothing was spread to are neither read nor written
+                unsigned wr = 0;
+#pragma unroll
+                for (int u = 0; u < UNR; ++u)
+                {
+                    if (v[u] == 0.0) continue;
+                    const double* g = gaddr(q0 + u * NT);
+                    if (!g) continue;
+                    v[u] = *g + v[u];
+                    wr |= 1u << u;
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u)
+                    if ((wr >> u) & 1u) *gaddr(q0 + u * NT) = v[u];
+            }
+        }
+        cluster.sync(); // nobody reads this CTA's block any more
+        return;
+    }
+
     // ---- write-out.  TMA: the block (= old f + the spread values) is stored back, clipped to the array.
     if (use_tma)
     {
@@ -472,7 +585,11 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
         __syncthreads();
         if (threadIdx.x == 0)
         {
-            if (NDIM == 3)
+            if (use_red)
+                asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&maps.m[a]),
+                             "r"(smem_u32(acc)), "r"(blo[0] - XO - cg.pp0[0]), "r"(blo[1] - cg.pp0[1]), "r"(blo[2] - cg.pp0[2])
+                             : "memory");
+            else if (NDIM == 3)
                 tma_store_3d(&maps.m[a], acc, blo[0] - XO - cg.pp0[0], blo[1] - cg.pp0[1], blo[2] - cg.pp0[2]);
             else
                 tma_store_2d(&maps.m[a], acc, blo[0] - XO - cg.pp0[0], blo[1] - cg.pp0[1]);
@@ -803,6 +920,11 @@ static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bin
     args.exc_list = g_exc_buf + 1;
     args.exc_capacity = EXC_CAPACITY;
     args.part = mv.part;
+    {
+        // measured 4.08 ms against 4.28 ms; tests/test_gpu_configs.py passes with it, the full parity suite has not been run yet
+        static const bool red = getenv("IBK_SPREAD_REDUCE") ? atoi(getenv("IBK_SPREAD_REDUCE")) != 0 : false;
+        args.tma_reduce = red ? 1 : 0;
+    }
     for (int d = 0; d < 3; ++d)
     {
         args.sel_lo[d] = mv.sel_lo[d];
@@ -864,6 +986,56 @@ static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bin
         }
         else if (bins.n_dense > 0 && !no_dense)
             args.dense_thresh = DENSE_BRICK_MARKERS; // part 1: the dense bricks are (were) done with part 2 / 0
+    }
+    if constexpr (NDIM == 3 && !PL)
+    {
+        static const char* env = getenv("IBK_SPREAD_CLUSTER"); // 0 / 1 overrides the default
+        static const bool use_cluster = env ? atoi(env) != 0 : SPREAD_CLUSTER_DEFAULT;
+        if (use_cluster)
+        {
+            // clusters of 2 x 2 x 2 CTAs = 32^3 cluster tiles; 8 colours of cluster tiles, one launch each
+            auto cfn = spread_tile_kernel<NDIM, K, false, true>;
+            e = cudaFuncSetAttribute(cfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess)
+            {
+                err = "cudaFuncSetAttribute(spread, cluster) failed";
+                return e;
+            }
+            for (int c = 0; c < 8; ++c)
+            {
+                int nclusters = 1;
+                for (int d = 0; d < 3; ++d)
+                {
+                    const int nct = (tp.nt[d] + 1) / 2; // cluster tiles along d
+                    args.colour[d] = (c >> d) & 1;
+                    args.ntc[d] = (nct - args.colour[d] + 1) / 2;
+                    nclusters *= args.ntc[d];
+                }
+                if (nclusters <= 0) continue;
+                cudaLaunchConfig_t cfg;
+                std::memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3(8u * (unsigned)nclusters, (unsigned)tp.ncomp);
+                cfg.blockDim = dim3(NT);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = L.stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = 8;
+                at[0].val.clusterDim.y = 1;
+                at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                if ((e = cudaLaunchKernelEx(&cfg, cfn, tp, maps, args)) != cudaSuccess)
+                {
+                    err = "cudaLaunchKernelEx(spread, cluster) failed";
+                    return e;
+                }
+                L.launches++;
+            }
+            ffn<<<1, 32, 0, L.stream>>>(tp, args);
+            L.launches++;
+            return cudaGetLastError();
+        }
     }
     // 2^ndim tile colours, one launch each (same-colour blocks are disjoint)
     const int ncol = (NDIM == 3) ? 8 : 4;
