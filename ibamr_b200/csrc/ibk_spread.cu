@@ -505,12 +505,29 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
         // ---- cluster write-out: this CTA's share of the cluster's points = own block + the siblings' halos, in rank order
         namespace cgx = cooperative_groups;
         cgx::cluster_group cluster = cgx::this_cluster();
+        __shared__ int cl_any; // this CTA spread something (the siblings read it)
+        if (threadIdx.x == 0) cl_any = total > 0 ? 1 : 0;
         cluster.sync(); // every block of the cluster is complete
+        {
+            int any = 0;
+#pragma unroll
+            for (int sr = 0; sr < 8; ++sr) any |= *cluster.map_shared_rank(&cl_any, sr);
+            if (!any) // nothing was spread into this cluster tile: nothing to add (the same decision in all eight CTAs)
+            {
+                cluster.sync();
+                return;
+            }
+        }
+        constexpr int SH = TILE + M; // share edge: the tile and the halo on the cluster's outer side
+        const int o0 = (crank & 1) ? M : 0, o1 = (crank & 2) ? M : 0, o2 = (crank & 4) ? M : 0;
+        // Write-out by ONE reducing TMA store of the densely repacked share (the share maps have an SH^3 box) when the
+        // share starts inside the array on an even x coordinate; else by the threads.
+        const int c0 = blo[0] + o0 - cg.pp0[0], c1 = blo[1] + o1 - cg.pp0[1], c2 = blo[2] + o2 - cg.pp0[2];
+        const bool by_tma = has_tile && XO == 0 && args.tma_reduce && ((args.tma_mask >> a) & 1u) && c0 >= 0 && (c0 & 1) == 0 && c1 >= 0 && c2 >= 0;
         if (has_tile)
         {
-            constexpr int SH = TILE + M; // share edge: the tile and the halo on the cluster's outer side
-            constexpr int UNR = 8;       // points per thread and round: their loads are in flight together
-            unsigned sok = 0; // siblings that exist (their tile is inside the tile grid)
+            constexpr int UNR = 8; // points per thread and round: their loads are in flight together
+            unsigned sok = 0;      // siblings that exist (their tile is inside the tile grid)
 #pragma unroll
             for (int sr = 0; sr < 8; ++sr)
             {
@@ -519,62 +536,100 @@ __global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (
                 for (int d = 0; d < 3; ++d) ok = ok && (t[d] - ((crank >> d) & 1) + ((sr >> d) & 1)) < tp.nt[d];
                 if (ok) sok |= 1u << sr;
             }
-            const int o0 = (crank & 1) ? M : 0, o1 = (crank & 2) ? M : 0, o2 = (crank & 4) ? M : 0;
-            // the element of f behind share point q (nullptr: outside the array)
-            auto gaddr = [&](int q) -> double* {
-                const int gi = blo[0] + q % SH + o0 - cg.pp0[0], gj = blo[1] + (q / SH) % SH + o1 - cg.pp0[1],
-                          gk = blo[2] + q / (SH * SH) + o2 - cg.pp0[2];
-                if (gi < 0 || gi >= cg.n[0] || gj < 0 || gj >= cg.n[1] || gk < 0 || gk >= cg.n[2]) return nullptr;
-                return cg.ptr + ((long long)(gk * cg.n[1] + gj) * cg.pitch + gi);
+            // the total at share point (lx, ly, lz) of this CTA's block; `both`: the dimensions along which the other
+            // sibling's block holds the point too (it lies in the 2M-wide overlap)
+            auto overlap = [&](int lx, int ly, int lz) -> unsigned {
+                return ((crank & 1) ? (lx < 2 * M) : (lx >= TILE)) | (((crank & 2) ? (ly < 2 * M) : (ly >= TILE)) << 1) |
+                       (((crank & 4) ? (lz < 2 * M) : (lz >= TILE)) << 2);
             };
-            for (int q0 = threadIdx.x; q0 < SH * SH * SH; q0 += NT * UNR)
+            auto total_at = [&](int lx, int ly, int lz, unsigned both) -> double {
+                double v = 0.0;
+#pragma unroll
+                for (int sr = 0; sr < 8; ++sr)
+                {
+                    const unsigned diff = (unsigned)sr ^ (unsigned)crank;
+                    if ((diff & ~both) != 0 || !((sok >> sr) & 1u)) continue;
+                    // the sibling's block starts 16 points later (earlier) along the dimensions where it is the upper (lower) one
+                    const int cx = lx + ((diff & 1) ? ((crank & 1) ? TILE : -TILE) : 0);
+                    const int cy = ly + ((diff & 2) ? ((crank & 2) ? TILE : -TILE) : 0);
+                    const int cz = lz + ((diff & 4) ? ((crank & 4) ? TILE : -TILE) : 0);
+                    v += cluster.map_shared_rank(acc, sr)[(cz * R + cy) * RX + cx + XO];
+                }
+                return v;
+            };
+            if (by_tma)
             {
-                double v[UNR];
-#pragma unroll
-                for (int u = 0; u < UNR; ++u)
+                // totals IN PLACE: a CTA's share and the strips its siblings read from its block are disjoint, and the
+                // share points outside the overlaps already hold their total
+                for (int q = threadIdx.x; q < SH * SH * SH; q += NT)
                 {
-                    const int q = q0 + u * NT;
-                    v[u] = 0.0;
-                    if (q >= SH * SH * SH) continue;
-                    const int lx = q % SH + o0, ly = (q / SH) % SH + o1, lz = q / (SH * SH) + o2; // in this CTA's block
-                    // along d the other sibling's block holds the point too iff it lies in the 2M-wide overlap
-                    const unsigned both = ((crank & 1) ? (lx < 2 * M) : (lx >= TILE)) | (((crank & 2) ? (ly < 2 * M) : (ly >= TILE)) << 1) |
-                                          (((crank & 4) ? (lz < 2 * M) : (lz >= TILE)) << 2);
-                    if (both == 0)
-                        v[u] = acc[(lz * R + ly) * RX + lx + XO];
-                    else
+                    const int lx = q % SH + o0, ly = (q / SH) % SH + o1, lz = q / (SH * SH) + o2;
+                    const unsigned both = overlap(lx, ly, lz);
+                    if (both) acc[(lz * R + ly) * RX + lx + XO] = total_at(lx, ly, lz, both);
+                }
+            }
+            else
+            {
+                // the element of f behind share point q (nullptr: outside the array)
+                auto gaddr = [&](int q) -> double* {
+                    const int gi = c0 + q % SH, gj = c1 + (q / SH) % SH, gk = c2 + q / (SH * SH);
+                    if (gi < 0 || gi >= cg.n[0] || gj < 0 || gj >= cg.n[1] || gk < 0 || gk >= cg.n[2]) return nullptr;
+                    return cg.ptr + ((long long)(gk * cg.n[1] + gj) * cg.pitch + gi);
+                };
+                for (int q0 = threadIdx.x; q0 < SH * SH * SH; q0 += NT * UNR)
+                {
+                    double v[UNR];
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u)
                     {
-#pragma unroll
-                        for (int sr = 0; sr < 8; ++sr)
-                        {
-                            const unsigned diff = (unsigned)sr ^ (unsigned)crank;
-                            if ((diff & ~both) != 0 || !((sok >> sr) & 1u)) continue;
-                            // the sibling's block starts 16 points later (earlier) along the dimensions where it is the upper (lower) one
-                            const int cx = lx + ((diff & 1) ? ((crank & 1) ? TILE : -TILE) : 0);
-                            const int cy = ly + ((diff & 2) ? ((crank & 2) ? TILE : -TILE) : 0);
-                            const int cz = lz + ((diff & 4) ? ((crank & 4) ? TILE : -TILE) : 0);
-                            v[u] += cluster.map_shared_rank(acc, sr)[(cz * R + cy) * RX + cx + XO];
-                        }
+                        const int q = q0 + u * NT;
+                        v[u] = 0.0;
+                        if (q >= SH * SH * SH) continue;
+                        const int lx = q % SH + o0, ly = (q / SH) % SH + o1, lz = q / (SH * SH) + o2; // in this CTA's block
+                        const unsigned both = overlap(lx, ly, lz);
+                        v[u] = both ? total_at(lx, ly, lz, both) : acc[(lz * R + ly) * RX + lx + XO];
                     }
-                }
-                // f += share: inside a launch a grid point belongs to exactly one CTA (plain read-modify-write, fixed order);
-                // points nothing was spread to are neither read nor written
-                unsigned wr = 0;
+                    // f += share: inside a launch a grid point belongs to exactly one CTA (plain read-modify-write, fixed
+                    // order); points nothing was spread to are neither read nor written
+                    unsigned wr = 0;
 #pragma unroll
-                for (int u = 0; u < UNR; ++u)
-                {
-                    if (v[u] == 0.0) continue;
-                    const double* g = gaddr(q0 + u * NT);
-                    if (!g) continue;
-                    v[u] = *g + v[u];
-                    wr |= 1u << u;
-                }
+                    for (int u = 0; u < UNR; ++u)
+                    {
+                        if (v[u] == 0.0) continue;
+                        const double* g = gaddr(q0 + u * NT);
+                        if (!g) continue;
+                        v[u] = *g + v[u];
+                        wr |= 1u << u;
+                    }
 #pragma unroll
-                for (int u = 0; u < UNR; ++u)
-                    if ((wr >> u) & 1u) *gaddr(q0 + u * NT) = v[u];
+                    for (int u = 0; u < UNR; ++u)
+                        if ((wr >> u) & 1u) *gaddr(q0 + u * NT) = v[u];
+                }
             }
         }
         cluster.sync(); // nobody reads this CTA's block any more
+        if (by_tma)
+        {
+            // dense repack of the share to the start of the block: destination q never lies behind its source, so chunks of
+            // NT points in ascending order only need their reads separated from their writes
+            for (int q0 = 0; q0 < SH * SH * SH; q0 += NT)
+            {
+                const int q = q0 + threadIdx.x;
+                double val = 0.0;
+                if (q < SH * SH * SH) val = acc[((q / (SH * SH) + o2) * R + (q / SH) % SH + o1) * RX + q % SH + o0];
+                __syncthreads();
+                if (q < SH * SH * SH) acc[q] = val;
+            }
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&maps.m[a]),
+                             "r"(smem_u32(acc)), "r"(c0), "r"(c1), "r"(c2)
+                             : "memory");
+                tma_store_commit_and_wait_read();
+            }
+        }
         return;
     }
 
@@ -995,6 +1050,17 @@ static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bin
         {
             // clusters of 2 x 2 x 2 CTAs = 32^3 cluster tiles; 8 colours of cluster tiles, one launch each
             auto cfn = spread_tile_kernel<NDIM, K, false, true>;
+            // IBK_SPREAD_CLUSTER=2: the shares are added by TMA's reducing store (maps with a (16 + M)^3 box; even M only)
+            static const bool share_tma = env && atoi(env) == 2;
+            args.tma_reduce = 0;
+            args.tma_mask = 0;
+            if (share_tma && M % 2 == 0)
+            {
+                args.tma_reduce = 1;
+                for (int a = 0; a < tp.ncomp; ++a)
+                    if (!no_tma && ((tp.comp[a].pp0[0] + M) % 2 == 0) && make_tensor_map(&maps.m[a], tp.comp[a], NDIM, TILE + M, TILE + M, TILE + M, promo))
+                        args.tma_mask |= (1u << a);
+            }
             e = cudaFuncSetAttribute(cfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess)
             {
