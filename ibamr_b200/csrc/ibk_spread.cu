@@ -133,14 +133,15 @@ __device__ const BrickColouring<NDIM, NC> d_colouring = BrickColouring<NDIM, NC>
 // (32 + 2M)^3 points -- its tile plus the halo on the cluster's outer sides -- and adds that share to f once.  Only the
 // cluster's outer shell is shared with other launches (the colours are those of the cluster tiles), so f moves
 // ((32 + 2M) / 32)^3 times instead of ((16 + 2M) / 16)^3, and points nothing was spread to are neither read nor written.
-template <int NDIM, int K, bool PL, bool CL = false>
-__global__ void __launch_bounds__(PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
+// WIDE: 320 instead of 256 threads with the brick colours: the window grows from 85 to 100 markers (one stencil task per thread).
+template <int NDIM, int K, bool PL, bool CL = false, bool WIDE = false>
+__global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
     spread_tile_kernel(const __grid_constant__ TileParams tp, const __grid_constant__ TmaMapSet maps, SpreadArgs args)
 {
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
     constexpr int R = TILE + 2 * M; // haloed block edge
-    constexpr int NT = PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS;
+    constexpr int NT = (PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_THREADS;
     constexpr int NWARPS = NT / 32;
     static_assert(!PL || spread_planes_ok<NDIM, K>, "plane owners: 3D, W = 4, M = 2");
     static_assert(!CL || (NDIM == 3 && !PL), "clusters: 3D, brick-colour accumulation");
@@ -930,7 +931,7 @@ __global__ void spread_fixup_kernel(const __grid_constant__ TileParams tp, Sprea
 static int* g_exc_buf = nullptr; // [1 + capacity] per process (device); tiny
 constexpr int EXC_CAPACITY = 4096;
 
-template <int NDIM, int K, bool PL>
+template <int NDIM, int K, bool PL, bool WIDE = false>
 static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err);
 
 template <int NDIM, int K>
@@ -942,14 +943,16 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
         static const char* env = getenv("IBK_SPREAD_PLANES");
         static const bool planes = env ? atoi(env) != 0 : SPREAD_PLANES_DEFAULT;
         if (planes) return launch_spread_pl<NDIM, K, true>(L, tp, bins, mv, err);
+        static const bool wide = getenv("IBK_SPREAD_WIDE") ? atoi(getenv("IBK_SPREAD_WIDE")) != 0 : false; // not measured yet
+        if (wide) return launch_spread_pl<NDIM, K, false, true>(L, tp, bins, mv, err);
     }
     return launch_spread_pl<NDIM, K, false>(L, tp, bins, mv, err);
 }
 
-template <int NDIM, int K, bool PL>
+template <int NDIM, int K, bool PL, bool WIDE>
 static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err)
 {
-    constexpr int NT = PL ? SPREAD_THREADS_PLANES : SPREAD_THREADS;
+    constexpr int NT = (PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_THREADS;
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
     constexpr int R = TILE + 2 * M;
@@ -1015,7 +1018,7 @@ static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bin
             fprintf(stderr, "[ibk] spread<%d,%d> comp %d tma=%u n=(%d,%d,%d) pitch=%lld pp0=(%d,%d,%d) ptr=%p nt=(%d,%d,%d) box=(%d,%d)\n", NDIM,
                     K, a, (args.tma_mask >> a) & 1u, tp.comp[a].n[0], tp.comp[a].n[1], tp.comp[a].n[2], tp.comp[a].pitch,
                     tp.comp[a].pp0[0], tp.comp[a].pp0[1], tp.comp[a].pp0[2], (void*)tp.comp[a].ptr, tp.nt[0], tp.nt[1], tp.nt[2], RX, R);
-    auto kfn = spread_tile_kernel<NDIM, K, PL>;
+    auto kfn = spread_tile_kernel<NDIM, K, PL, false, WIDE>;
     auto ffn = spread_fixup_kernel<NDIM, K>;
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
@@ -1042,7 +1045,7 @@ static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bin
         else if (bins.n_dense > 0 && !no_dense)
             args.dense_thresh = DENSE_BRICK_MARKERS; // part 1: the dense bricks are (were) done with part 2 / 0
     }
-    if constexpr (NDIM == 3 && !PL)
+    if constexpr (NDIM == 3 && !PL && !WIDE)
     {
         static const char* env = getenv("IBK_SPREAD_CLUSTER"); // 0 / 1 overrides the default
         static const bool use_cluster = env ? atoi(env) != 0 : SPREAD_CLUSTER_DEFAULT;
