@@ -456,7 +456,8 @@ def run_gpu(args):
                                     "launch_ms": in_ms},
                          "touched_side_dofs": touched},
             "clocks": sampler.result(),
-            "phases_ms": {"spread_kernels": sp_ms, "interp_kernels": in_ms, "step": ms_per_step, "rebin": rebin_ms},
+            "phases_ms": {"spread_kernels": sp_ms, "interp_kernels": in_ms, "halo_and_gaps": ms_per_step - sp_ms - in_ms, "step": ms_per_step,
+                          "rebin": rebin_ms},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline()
