@@ -229,6 +229,15 @@ cudaError_t bins_reserve(Bins& b, int n_entries, int total_bricks)
         if (b.sort_temp) cudaFree(b.sort_temp);
         b.sort_temp_bytes = radix_sort_temp_bytes(cap);
         if ((e = cudaMalloc(&b.sort_temp, b.sort_temp_bytes)) != cudaSuccess) return e;
+        if (b.exc_flags) cudaFree(b.exc_flags);
+        const size_t words = (size_t)cap / 4 + 1;
+        if ((e = cudaMalloc(&b.exc_flags, sizeof(unsigned) * words)) != cudaSuccess) return e;
+        if ((e = cudaMemset(b.exc_flags, 0, sizeof(unsigned) * words)) != cudaSuccess) return e;
+        if (!b.exc_count)
+        {
+            if ((e = cudaMalloc(&b.exc_count, sizeof(int))) != cudaSuccess) return e;
+            if ((e = cudaMemset(b.exc_count, 0, sizeof(int))) != cudaSuccess) return e;
+        }
         b.capacity = cap;
     }
     if (total_bricks + 1 > b.brick_capacity)
@@ -253,6 +262,8 @@ void bins_free(Bins& b)
     if (b.brick_start) cudaFree(b.brick_start);
     if (b.dense_list) cudaFree(b.dense_list);
     if (b.dense_count) cudaFree(b.dense_count);
+    if (b.exc_flags) cudaFree(b.exc_flags);
+    if (b.exc_count) cudaFree(b.exc_count);
     b = Bins();
 }
 

@@ -67,6 +67,11 @@ struct Bins
     int* dense_count = nullptr; // device counter
     int dense_capacity = 0;
     int n_dense = 0;
+    // spread exceptions: (entry, component) pairs whose stencil does not fit the accumulator of their tile are flagged here by
+    // the tile kernels and spread by spread_fixup_kernel.  One byte per sorted position (bit a = component a), held as 32-bit
+    // words: the list cannot overflow.  All zero between spreads (the fix-up clears what it consumes).
+    unsigned* exc_flags = nullptr; // [capacity / 4 + 1]
+    int* exc_count = nullptr;      // number of flagged pairs (an upper bound: a pair may be flagged twice)
 };
 constexpr int DENSE_BRICK_MARKERS = 48;
 
@@ -175,6 +180,10 @@ struct MarkerView
     // dimension, 2 = the others
     int part = 0;
     int sel_lo[3] = { 0, 0, 0 }, sel_hi[3] = { 0, 0, 0 };
+    // true: every entry was binned into the interior of a patch whose ghost width covers the kernel, so no stencil reaches
+    // outside the arrays (the resident level).  The spread may then start its first accumulator block per dimension at the
+    // array's first element instead of M points before the first tile.
+    bool clip_free = false;
 };
 
 struct TmaMaps; // opaque, ibk_interp.cu

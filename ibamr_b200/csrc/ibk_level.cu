@@ -1742,6 +1742,7 @@ static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo, int part = 
     mv.v_cstride = lv.stride;
     mv.v_istride = 1;
     mv.src = nullptr;
+    mv.clip_free = true; // owners only, ghost width checked above: no stencil leaves the arrays
     if (part < 0 || part > 2) return fail(ctx, IBK_ERR_INVALID, "part must be 0 (all), 1 (interior tiles) or 2 (boundary tiles)");
     mv.part = part;
     for (size_t p = 0; p < lv.patches.size(); ++p)

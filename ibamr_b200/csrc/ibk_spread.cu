@@ -4,29 +4,27 @@
 // lagrangian_interaction3d.f.m4:1344-1475 ib_4, :2384-2582 ib_6, :2703-2805 bspline_3,
 // :2933-3041 bspline_4, :617-730 piecewise_linear; 2D twins in lagrangian_interaction2d.f.m4) and
 // the per-axis loop of LEInteractor (LEInteractor.cpp:3676-3711).  The reference is serial over
-// markers, so it has no write conflicts; here the work is organised so that none can occur:
+// markers, so it has no write conflicts; here the work is organised so that none can occur and the
+// order of the additions at every grid point is fixed (bit-reproducible, no float atomics):
 //
-//  * MARKER TILES WITH A HALOED ACCUMULATOR.  One CTA takes one marker tile (16^ndim cells = 4^ndim
-//    bricks, one contiguous run of the sorted markers) and ONE component, and accumulates the full
-//    stencils of its markers into a shared-memory block of (16 + 2M)^ndim points (M = kernel reach), so
-//    every marker is visited exactly once per component and no stencil is ever clipped.
-//  * TILE COLOURING.  The blocks of two tiles whose indices differ by 2 in some dimension are disjoint
-//    (32 >= 16 + 2M), so the tiles are processed in 2^ndim launches (colours); inside a launch every
-//    grid point is touched by at most one CTA, which finishes with one `f += block` pass over its
-//    haloed block (the contract of LDataManager::spread, LDataManager.cpp:662-663).
-//  * BRICK COLOURING inside the CTA.  One warp takes one brick (4^ndim cells) at a time and walks its
-//    markers in storage order with the 32 lanes spread over the stencil points.  Bricks NC apart have
-//    disjoint footprints; the bricks are visited colour by colour with a CTA barrier between colours, so no
-//    two warps ever touch the same accumulator word at the same time.
-//  * 1-D weights are evaluated one thread per (marker, dimension) for a window of markers and parked in
-//    shared memory; the scaled force is folded into the last dimension's weights.
-//  The summation order at every grid point is fixed by (tile colour, brick colour, sorted marker order):
-//  results are bit-reproducible run to run.
+//  3D, kernels with a reach of at most 3 cells (all but IB_4_W8): spread_march_kernel.  One CTA owns a COLUMN
+//    of 32 x 32 cells and a chunk of marker tiles in z, and marches through it one brick layer (4 cells in z) at
+//    a time.  The accumulator is a RING of z planes of (32 + 2M)^2 points in shared memory; when a layer is done
+//    its four lowest planes are final and are ADDED to f by TMA's reducing store (cp.reduce.async.bulk.tensor
+//    .add: no load of f, the addition happens in L2) while the next layer is accumulated, then zeroed and reused.
+//    The CTA is warp-specialised: producer warps evaluate the 1-D stencils of layer s + 1 (one thread per marker,
+//    three independent div/sqrt chains), consumer warps accumulate layer s, one warp flushes the planes of
+//    layer s - 1.  A consumer warp takes one ROW of eight bricks along x and walks the bricks NC apart
+//    (disjoint footprints) as independent chains side by side; rows NC apart are disjoint, so a layer takes NC
+//    consumer-only barriers.  March tiles 2 apart are disjoint: 8 launches (colours).  f moves
+//    (36/32 in y) x (40/32 in x, 32-byte sectors) x (68/64 in z) = 1.5 times instead of 2.3 times with 16^3 tiles.
+//  2D and IB_4_W8: spread_tile_kernel.  One CTA per (marker tile of 16^ndim cells, component) with a haloed
+//    block in shared memory loaded from / stored to f by TMA, brick colours inside, 2^ndim tile colours.
+//  Dense bricks (3D, > 48 markers): spread_dense_kernel, register footprints.
 //
-// A marker whose stencil does not fit the haloed block (possible only if its binning cell and its stencil
-// origin disagree by a rounding) is skipped here and spread by spread_fixup_kernel, one thread, in sorted
-// order, after the last colour.
-#include <cooperative_groups.h>
+// An (entry, component) pair whose stencil does not fit the accumulator of its tile (its binning cell and its
+// stencil origin disagree: positions moved since the binning, or a rounding) is flagged in Bins::exc_flags and
+// spread by spread_fixup_kernel in sorted order after the last colour: exact, never dropped, slow.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -39,33 +37,7 @@
 
 namespace ibk
 {
-// -DIBK_TIMELINE: thread 0 of a few CTAs records clock64() at the phase boundaries (printed by the launcher)
-#ifdef IBK_TIMELINE
-__device__ long long g_tl[64][16];
-__device__ int g_tl_n;
-#define TL(k)                                             \
-    do                                                    \
-    {                                                     \
-        if (threadIdx.x == 0 && tl_on) tl[k] = clock64(); \
-    } while (0)
-#else
-#define TL(k)
-#endif
 constexpr int SPREAD_THREADS = 256;
-// PLANE OWNERS (3D, 4-point kernels): the accumulation of a window is not organised by bricks and colours but by planes
-// of the block: warp `id` owns the two z planes 2 id, 2 id + 1 and walks ALL markers of the window whose stencil meets
-// them (2 or 3 warps per marker), lanes = 4 x 4 (x, y) points x 2 planes.  No two warps share a word, so the only CTA
-// barriers left are the two around the stencil evaluation of a window; the order of the additions at a grid point is
-// the window's marker order, the same as with the brick colours (results are bit-identical to that path).
-constexpr bool SPREAD_CLUSTER_DEFAULT = false; // correct (all parity tests pass) but 13.6 ms: the read-modify-write of the share by
-                                               // the threads is far too slow; next: dense repack + TMA reducing store (IBK_SPREAD_CLUSTER=1)
-constexpr bool SPREAD_PLANES_DEFAULT = false; // measured SLOWER than the brick colours (5.83 ms against 4.41 ms on the C5 shard:
-                                              // 2.5 dependent visits per marker instead of one); kept for reference, IBK_SPREAD_PLANES=1
-constexpr int SPREAD_THREADS_PLANES = 320; // 10 warps = the 10 plane pairs of a 20-plane block
-template <int NDIM, int K>
-constexpr bool spread_planes_ok = (NDIM == 3 && KTraits<K>::W == 4 && KTraits<K>::M == 2);
-constexpr int SPREAD_TASKS = 1; // (marker, dimension) stencil evaluations per thread and window (measured: a second one
-                                // serialises two sqrt/div chains before the barrier: 85-marker windows beat 100-marker ones)
 constexpr int SPREAD_WARPS = SPREAD_THREADS / 32;
 
 struct SpreadArgs
@@ -79,17 +51,532 @@ struct SpreadArgs
     const uint32_t* src;
     int colour[3]; // tile colour (parity per dimension) handled by this launch
     int ntc[3];    // number of tiles of that colour per dimension
-    // exceptions (stencil outside the haloed block): (sorted position * 8 + component), see spread_fixup_kernel
     int* exc_count;
-    int* exc_list;
-    int exc_capacity;
+    unsigned* exc_flags;
+    int n_entries;
     int cap; // markers whose stencil weights are staged at a time (sizes the dynamic shared memory)
-    unsigned tma_mask; // bit a: the block of component a is loaded / stored by TMA (else zero-fill + red write-out)
+    unsigned tma_mask; // bit a: the block of component a is moved by TMA
     int part, sel_lo[3], sel_hi[3]; // MarkerView's tile selection
-    int tma_reduce;                 // 1 (3D): the block starts from zero and is ADDED to f by TMA's reducing store
+    int clip_free;                  // MarkerView::clip_free
     int dense_thresh;               // > 0: bricks with more markers than this are left to spread_dense_kernel
+    int chunk_tiles;                // march kernel: marker tiles per chunk in z
 };
 
+__device__ __forceinline__ void flag_exception(const SpreadArgs& args, int i, int a)
+{
+    atomicOr(&args.exc_flags[i >> 2], 1u << (8 * (i & 3) + a));
+    atomicAdd(args.exc_count, 1);
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2)
+{
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// shared-memory accesses by 32-bit shared-space address (no generic-address arithmetic in the inner loop)
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(uint32_t a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int2 lds_v2s32(uint32_t a)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// =============================================================================================
+// 3D march kernel
+// =============================================================================================
+constexpr int MARCH_CELLS = 2 * TILE;          // column edge: 2 x 2 marker tiles
+constexpr int MARCH_BR = MARCH_CELLS / BRICK;  // 8 bricks per row / rows per layer
+constexpr int MARCH_WARPS = 16;                 // 4 per SM sub-partition: 128 registers per thread
+constexpr int MARCH_MAX_LAYERS = 32;
+
+template <int K>
+struct MarchCfg
+{
+    static constexpr int W = KTraits<K>::W;
+    static constexpr int M = KTraits<K>::M;
+    static constexpr int R = MARCH_CELLS + 2 * M; // haloed plane edge (y, and x before alignment)
+    static constexpr int XO = M & 1;              // TMA boxes of 8-byte elements start on an even x coordinate
+    static constexpr int RX = (R + XO + 1) & ~1;
+    static constexpr int PLANE = (R * RX + 15) & ~15; // points per plane slot (a TMA source must start on a 128-byte boundary)
+    static constexpr int FZ = BRICK + 2 * M;      // planes a brick layer reaches
+    static constexpr int NRING = FZ + BRICK;      // + the four planes being flushed
+    static constexpr int NC = (BRICK + 2 * M + BRICK - 1) / BRICK; // brick colours per dimension
+    static constexpr int NCW = (MARCH_BR + NC - 1) / NC;           // consumer warps = rows per row colour = chains per warp
+    static constexpr int NPW = MARCH_WARPS - NCW - 1;                // producer warps
+    static constexpr int NT = 32 * MARCH_WARPS;
+    static constexpr int NPTS = W * W * W;
+    static constexpr int NSLOT = (NPTS + 31) / 32;
+    // per-marker record: W byte offsets (one per z plane of the stencil; negative: skip), then 3 x W weights
+    static constexpr int ZO_BYTES = ((W * 4 + 15) / 16) * 16;
+    static constexpr int REC = ((ZO_BYTES + 3 * W * 8 + 15) / 16) * 16;
+    static constexpr bool FAST4 = (W == 4); // 64 points = 2 slots of 32 lanes with the same (x, y) per lane
+    static constexpr int SINK_B = ((8 * (3 * RX + 4) + 127) / 128) * 128; // where the lanes of a dummy record add their zeros
+};
+
+template <int K>
+__global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
+    spread_march_kernel(const __grid_constant__ TileParams tp, const __grid_constant__ TmaMapSet maps, const SpreadArgs args)
+{
+    using C = MarchCfg<K>;
+    constexpr int W = C::W, M = C::M, R = C::R, XO = C::XO, RX = C::RX, PLANE = C::PLANE, FZ = C::FZ, NRING = C::NRING;
+    constexpr int NC = C::NC, NCW = C::NCW, REC = C::REC, ZO_BYTES = C::ZO_BYTES;
+    constexpr int NPROD = 32 * C::NPW;
+    constexpr int PLANE_B = PLANE * 8;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* const ringb = smem_raw;                                  // [NRING][R][RX] doubles
+    // FAST4: a record that must not be spread here (a chain that has run out, a stencil left to the fix-up) points at a
+    // SINK behind the ring instead of being branched around; record `cap` of each buffer is such a dummy
+    constexpr int SINK_OFF = NRING * PLANE_B; // (relative to the ring)
+    constexpr int SINK_B = C::SINK_B;
+    unsigned char* const recb = smem_raw + (size_t)NRING * PLANE_B + SINK_B; // [2][cap + 1][REC]
+    const int cap1 = args.cap + 1;
+    __shared__ int s_pre[2][MARCH_BR * MARCH_BR + 1]; // markers before brick p of the layer (row-major: p = row * 8 + brick in row)
+    __shared__ int s_first[2][MARCH_BR * MARCH_BR];   // sorted position of the brick's first marker
+    __shared__ int s_desc[2][8];                      // step: layer, window offset, markers in the window, pre/first buffer, first window?, end?
+    __shared__ int s_tot[MARCH_MAX_LAYERS + 1];       // markers per layer (decides which planes are flushed)
+    __shared__ int s_any;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int role = warp < NCW ? 0 : (warp == NCW ? 1 : 2); // consumer / flusher / producer
+    const int ptid = tid - 32 * (NCW + 1);                   // producer thread index
+
+    // ---- which column, chunk and component
+    int col[3];
+    {
+        int r = (int)blockIdx.x;
+        col[0] = 2 * (r % args.ntc[0]) + args.colour[0];
+        r /= args.ntc[0];
+        col[1] = 2 * (r % args.ntc[1]) + args.colour[1];
+        col[2] = 2 * (r / args.ntc[1]) + args.colour[2];
+    }
+    const int a = blockIdx.y;
+    const CompGeom& cg = tp.comp[a];
+    const int tz0 = col[2] * args.chunk_tiles;
+    const int ntz = min(args.chunk_tiles, tp.nt[2] - tz0);
+    const int NL = ntz * TILE_BRICKS; // brick layers of this chunk
+
+    // tile selection (halo overlap): is tile (txi, tyi, tz) of this column part of this launch?
+    auto tile_on = [&](int txi, int tyi, int tz) -> bool {
+        const int tx = 2 * col[0] + txi, ty = 2 * col[1] + tyi;
+        if (tx >= tp.nt[0] || ty >= tp.nt[1]) return false;
+        if (!args.part) return true;
+        const bool in = tx >= args.sel_lo[0] && tx <= args.sel_hi[0] && ty >= args.sel_lo[1] && ty <= args.sel_hi[1] &&
+                        tz >= args.sel_lo[2] && tz <= args.sel_hi[2];
+        return (args.part == 1) == in;
+    };
+    auto tile_b0 = [&](int txi, int tyi, int tz) -> int {
+        const int tx = 2 * col[0] + txi, ty = 2 * col[1] + tyi;
+        return tp.brick_base + ((tz * tp.nt[1] + ty) * tp.nt[0] + tx) * 64;
+    };
+    // anything to spread in this chunk?
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    if (tid < 4 * ntz)
+    {
+        const int tz = tz0 + tid / 4, txi = tid & 1, tyi = (tid >> 1) & 1;
+        if (tile_on(txi, tyi, tz))
+        {
+            const int b0 = tile_b0(txi, tyi, tz);
+            if (__ldg(&args.brick_start[b0 + 64]) > __ldg(&args.brick_start[b0])) s_any = 1;
+        }
+    }
+    __syncthreads();
+    if (!s_any) return;
+
+    // ---- geometry of the accumulator: smem column 0 / row 0 / plane 0 in pp coordinates
+    int bx0 = MARCH_CELLS * col[0] - M - XO, by0 = MARCH_CELLS * col[1] - M;
+    const int zq0 = TILE * tz0 - M;
+    bool use_tma = (args.tma_mask >> a) & 1u;
+    if (bx0 < cg.pp0[0])
+    {
+        if (args.clip_free) bx0 = cg.pp0[0]; // nothing reaches the points before the array: start the block at its first element
+        else use_tma = false;                // a TMA store with a negative start coordinate traps (measured)
+    }
+    if (by0 < cg.pp0[1])
+    {
+        if (args.clip_free) by0 = cg.pp0[1];
+        else use_tma = false;
+    }
+
+    // ---- zero the ring
+    {
+        double2* r2 = reinterpret_cast<double2*>(ringb);
+        for (int q = tid; q < (NRING * PLANE_B + SINK_B) / 16; q += C::NT) r2[q] = make_double2(0.0, 0.0);
+        if (tid < 2 * (REC / 4)) // the dummy records: offsets = the sink, weights = 0
+        {
+            int* dr = reinterpret_cast<int*>(recb + ((size_t)(tid / (REC / 4)) * cap1 + args.cap) * REC);
+            const int wd = tid % (REC / 4);
+            dr[wd] = (wd < W) ? SINK_OFF : 0;
+        }
+        fence_proxy_async_smem();
+    }
+
+    // =========================================================================================
+    // producer: counts of a layer, then one thread per marker
+    // =========================================================================================
+    int p_layer = -1, p_off = 0, p_total = 0, p_lb = 1; // (uniform over the producer threads)
+    int n_s = 0, n_m = 0, n_e = 0;                      // prefetched segment offsets of the lane's two bricks (next layer)
+    bool n_ok = false;
+    // lane l of producer warp 0 holds bricks p = 2 l, 2 l + 1 (same row, same tile, consecutive ids)
+    auto counts_fetch = [&](int layer) {
+        n_ok = false;
+        if (ptid < 32 && layer < NL)
+        {
+            const int row = ptid >> 2, i = (2 * ptid) & 7;
+            const int tz = tz0 + layer / TILE_BRICKS, lz = layer % TILE_BRICKS;
+            const int txi = i >> 2, tyi = row >> 2;
+            if (tile_on(txi, tyi, tz))
+            {
+                const int b = tile_b0(txi, tyi, tz) + 16 * lz + 4 * (row & 3) + (i & 3);
+                n_s = __ldg(&args.brick_start[b]);
+                n_m = __ldg(&args.brick_start[b + 1]);
+                n_e = __ldg(&args.brick_start[b + 2]);
+                n_ok = true;
+            }
+        }
+    };
+    auto counts_publish = [&](int lb) -> void {
+        // (producer warp 0) exclusive scan of the 64 counts, two per lane
+        if (ptid < 32)
+        {
+            int c0 = n_ok ? n_m - n_s : 0, c1 = n_ok ? n_e - n_m : 0;
+            if (args.dense_thresh > 0)
+            {
+                if (c0 > args.dense_thresh) c0 = 0; // a dense brick: spread_dense_kernel's
+                if (c1 > args.dense_thresh) c1 = 0;
+            }
+            int incl = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int excl = incl - c0 - c1;
+            s_pre[lb][2 * ptid + 1] = excl + c0;
+            s_pre[lb][2 * ptid + 2] = incl;
+            if (ptid == 0) s_pre[lb][0] = 0;
+            s_first[lb][2 * ptid] = n_s;
+            s_first[lb][2 * ptid + 1] = n_m;
+        }
+    };
+    // prepares step t + 1 into buffers (nb = step parity): descriptor, (new layer: counts), records
+    auto produce = [&](int nb) {
+        int first_win = 0;
+        if (p_layer >= 0 && p_off + args.cap < p_total)
+            p_off += args.cap;
+        else
+        {
+            ++p_layer;
+            p_off = 0;
+            p_lb ^= 1;
+            first_win = 1;
+            if (p_layer < NL)
+            {
+                counts_publish(p_lb);
+                counts_fetch(p_layer + 1);
+                named_bar_sync(2, NPROD);
+                p_total = s_pre[p_lb][MARCH_BR * MARCH_BR];
+            }
+            else
+                p_total = 0;
+        }
+        const int cnt = min(args.cap, p_total - p_off);
+        if (ptid == 0)
+        {
+            s_desc[nb][0] = p_layer;
+            s_desc[nb][1] = p_off;
+            s_desc[nb][2] = cnt;
+            s_desc[nb][3] = p_lb;
+            s_desc[nb][4] = first_win;
+            s_desc[nb][5] = p_layer >= NL ? 1 : 0;
+            if (first_win && p_layer <= MARCH_MAX_LAYERS) s_tot[p_layer] = p_total;
+        }
+        if (p_layer >= NL) return;
+        unsigned char* const rb = recb + (size_t)nb * cap1 * REC;
+        const int* pre = s_pre[p_lb];
+        const int zlo = BRICK * p_layer; // the layer's first plane (relative to plane 0 of the chunk)
+        for (int slot = ptid; slot < cnt; slot += NPROD)
+        {
+            const int m = p_off + slot;
+            int p = 0; // last p with pre[p] <= m
+#pragma unroll
+            for (int step = 32; step >= 1; step >>= 1)
+                if (pre[p + step] <= m) p += step;
+            const int i = s_first[p_lb][p] + (m - pre[p]);
+            double xs[3], xr[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+                xs[d] = __ldg(&args.X[d * args.x_stride + i]);
+                xr[d] = args.Xraw ? __ldg(&args.Xraw[d * args.x_stride + i]) : xs[d];
+            }
+            const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
+            const double fv = __ldg(&args.V[cg.vcol * args.v_cstride + row * args.v_istride]) * tp.inv_vol;
+            unsigned char* const r = rb + (size_t)slot * REC;
+            double* const wr = reinterpret_cast<double*>(r + ZO_BYTES);
+            int r0[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+                double w[W];
+                int l;
+                stencil_1d<K>(xs[d], xr[d], tp.xl[d][cg.var[d]], tp.dx[d], l, w, d == cg.axis);
+                r0[d] = l + tp.G - (d == 0 ? bx0 : d == 1 ? by0 : zq0);
+                if (d == 2)
+                {
+#pragma unroll
+                    for (int j = 0; j < W; ++j)
+                    {
+                        // FAST4: the z weights in the order (0, 2, 1, 3): lane group g reads the pair (g, g + 2) at once
+                        const int jj = C::FAST4 ? ((j & 1) * 2 + (j >> 1)) : j;
+                        wr[2 * W + jj] = w[j] * fv;
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) wr[d * W + j] = w[j];
+                }
+            }
+            // the stencil must stay inside the footprint of the marker's BRICK (what the chains and row colours rely on) and
+            // inside the block
+            const int fx = MARCH_CELLS * col[0] + BRICK * (p & 7) - M - bx0, fy = MARCH_CELLS * col[1] + BRICK * (p >> 3) - M - by0;
+            const bool fits = r0[0] >= max(fx, 0) && r0[0] + W <= min(fx + FZ, RX) && r0[1] >= max(fy, 0) && r0[1] + W <= min(fy + FZ, R) &&
+                              r0[2] >= zlo && r0[2] + W <= zlo + FZ;
+            int* const zo = reinterpret_cast<int*>(r);
+            const int xy = 8 * (r0[1] * RX + r0[0]);
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+            {
+                const int jj = C::FAST4 ? ((j & 1) * 2 + (j >> 1)) : j;
+                zo[jj] = fits ? ((r0[2] + j) % NRING) * PLANE_B + xy : (C::FAST4 ? SINK_OFF : -1);
+            }
+            if (!fits) flag_exception(args, i, a);
+        }
+    };
+
+    // =========================================================================================
+    // consumer: rows of bricks, NC colours of rows, chains of bricks NC apart inside a row
+    // =========================================================================================
+    auto consume = [&](int b, int lb, int off, int cnt) {
+        const unsigned char* const rb = recb + (size_t)b * cap1 * REC;
+        const int* pre = s_pre[lb];
+        // this lane's stencil point(s)
+        int lxy[C::NSLOT], lz4[C::NSLOT], lwx[C::NSLOT], lwy[C::NSLOT], lwz[C::NSLOT];
+#pragma unroll
+        for (int s = 0; s < C::NSLOT; ++s)
+        {
+            const int q = min(lane + 32 * s, C::NPTS - 1);
+            const int ix = q % W, iy = (q / W) % W, iz = q / (W * W);
+            lxy[s] = 8 * (iy * RX + ix);
+            lz4[s] = 4 * iz;
+            lwx[s] = ZO_BYTES + 8 * ix;
+            lwy[s] = ZO_BYTES + 8 * (W + iy);
+            lwz[s] = ZO_BYTES + 8 * (2 * W + iz);
+        }
+        const int g4 = lane >> 4; // FAST4: z pair (g4, g4 + 2)
+        const uint32_t rec_s = smem_u32(rb), rec_dummy = rec_s + (uint32_t)args.cap * REC;
+        const uint32_t ring_lane = smem_u32(ringb) + (uint32_t)lxy[0];
+        for (int ph = 0; ph < NC; ++ph)
+        {
+            const int row = ph + NC * warp;
+            if (row < MARCH_BR)
+            {
+#pragma unroll 1
+                for (int sp = 0; sp < NC; ++sp)
+                {
+                    int cur[NCW], end[NCW];
+                    int longest = 0;
+#pragma unroll
+                    for (int c = 0; c < NCW; ++c)
+                    {
+                        const int i = sp + NC * c;
+                        cur[c] = end[c] = 0;
+                        if (i < MARCH_BR)
+                        {
+                            const int p = row * MARCH_BR + i;
+                            cur[c] = max(pre[p], off) - off;
+                            end[c] = min(pre[p + 1], off + cnt) - off;
+                            longest = max(longest, end[c] - cur[c]);
+                        }
+                    }
+                    for (int k = 0; k < longest; ++k)
+                    {
+                        if constexpr (C::FAST4)
+                        {
+                            // branch-free: a chain that has run out reads the dummy record and adds zeros to the sink
+                            int2 zo[NCW];
+                            double wx[NCW], wy[NCW];
+                            double2 wz[NCW];
+                            double a0[NCW], a1[NCW];
+#pragma unroll
+                            for (int c = 0; c < NCW; ++c)
+                            {
+                                const uint32_t r = (cur[c] + k < end[c]) ? rec_s + (uint32_t)(cur[c] + k) * REC : rec_dummy;
+                                zo[c] = lds_v2s32(r + 8 * g4);
+                                wx[c] = lds_f64(r + lwx[0]);
+                                wy[c] = lds_f64(r + lwy[0]);
+                                wz[c] = lds_v2f64(r + ZO_BYTES + 8 * 2 * W + 16 * g4);
+                            }
+#pragma unroll
+                            for (int c = 0; c < NCW; ++c)
+                            {
+                                a0[c] = lds_f64(ring_lane + zo[c].x);
+                                a1[c] = lds_f64(ring_lane + zo[c].y);
+                            }
+#pragma unroll
+                            for (int c = 0; c < NCW; ++c)
+                            {
+                                const double wxy = wx[c] * wy[c];
+                                sts_f64(ring_lane + zo[c].x, fma(wxy, wz[c].x, a0[c]));
+                                sts_f64(ring_lane + zo[c].y, fma(wxy, wz[c].y, a1[c]));
+                            }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int c = 0; c < NCW; ++c)
+                            {
+                                if (cur[c] + k >= end[c]) continue;
+                                const unsigned char* r = rb + (size_t)(cur[c] + k) * REC;
+                                if (*reinterpret_cast<const int*>(r) < 0) continue; // does not fit: the fix-up's
+                                double wv[C::NSLOT], av[C::NSLOT];
+                                int ad[C::NSLOT];
+#pragma unroll
+                                for (int s = 0; s < C::NSLOT; ++s)
+                                {
+                                    ad[s] = *reinterpret_cast<const int*>(r + lz4[s]) + lxy[s];
+                                    wv[s] = (*reinterpret_cast<const double*>(r + lwx[s]) * *reinterpret_cast<const double*>(r + lwy[s])) *
+                                            *reinterpret_cast<const double*>(r + lwz[s]);
+                                }
+#pragma unroll
+                                for (int s = 0; s < C::NSLOT; ++s)
+                                    if (C::NPTS % 32 == 0 || lane + 32 * s < C::NPTS) av[s] = *reinterpret_cast<const double*>(ringb + ad[s]);
+#pragma unroll
+                                for (int s = 0; s < C::NSLOT; ++s)
+                                    if (C::NPTS % 32 == 0 || lane + 32 * s < C::NPTS) *reinterpret_cast<double*>(ringb + ad[s]) = av[s] + wv[s];
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            if (ph + 1 < NC) named_bar_sync(1, 32 * NCW);
+        }
+        fence_proxy_async_smem(); // this thread's writes to the ring -> visible to the TMA stores of the flusher
+    };
+
+    // =========================================================================================
+    // flusher: planes [qlo, qhi) are final: f += plane (TMA reducing store), then zero them for reuse
+    // =========================================================================================
+    auto plane_dirty = [&](int q) -> bool {
+        // touched by the layers s with 4 s <= q < 4 s + FZ
+        bool dirty = false;
+        for (int s = max(0, (q - FZ + BRICK) / BRICK); s <= min(q / BRICK, NL - 1); ++s)
+            if (BRICK * s <= q && q < BRICK * s + FZ && s_tot[s] > 0) dirty = true;
+        return dirty;
+    };
+    auto flush = [&](int qlo, int qhi) {
+        const int x0 = bx0 - cg.pp0[0], y0 = by0 - cg.pp0[1];
+        bool any = false;
+        for (int q = qlo; q < qhi; ++q)
+        {
+            if (!plane_dirty(q)) continue;
+            any = true;
+            const int gz = zq0 + q - cg.pp0[2];
+            if (gz < 0 || gz >= cg.n[2]) continue;
+            const double* pl = reinterpret_cast<const double*>(ringb + (size_t)(q % NRING) * PLANE_B);
+            if (use_tma)
+            {
+                if (lane == 0) tma_reduce_add_3d(&maps.m[a], pl, x0, y0, gz);
+            }
+            else
+            {
+                // the array is not addressable by TMA here (alignment, or the block starts before the array): plain
+                // read-modify-write by the lanes, clipped to the array.  One CTA per grid point and launch: fixed order.
+                for (int y = 0; y < R; ++y)
+                {
+                    const int gy = y0 + y;
+                    if (gy < 0 || gy >= cg.n[1]) continue;
+                    double* grow = cg.ptr + ((long long)gz * cg.n[1] + gy) * cg.pitch;
+                    for (int x = lane; x < RX; x += 32)
+                    {
+                        const int gx = x0 + x;
+                        const double v = pl[y * RX + x];
+                        if (gx >= 0 && gx < cg.n[0] && v != 0.0) grow[gx] += v;
+                    }
+                }
+            }
+        }
+        if (!any) return;
+        if (use_tma && lane == 0) tma_store_commit_and_wait_read(); // the planes have been read
+        __syncwarp();
+        for (int q = qlo; q < qhi; ++q)
+        {
+            if (!plane_dirty(q)) continue;
+            double2* pl = reinterpret_cast<double2*>(ringb + (size_t)(q % NRING) * PLANE_B);
+            for (int e = lane; e < PLANE / 2; e += 32) pl[e] = make_double2(0.0, 0.0);
+        }
+        fence_proxy_async_smem();
+    };
+
+    // ---- the march
+    if (role == 2)
+    {
+        counts_fetch(0);
+        produce(0);
+    }
+    __syncthreads();
+    for (int t = 0;; ++t)
+    {
+        const int b = t & 1;
+        const int layer = s_desc[b][0], off = s_desc[b][1], cnt = s_desc[b][2], lb = s_desc[b][3], first_win = s_desc[b][4],
+                  is_end = s_desc[b][5];
+        if (role == 2)
+        {
+            if (!is_end) produce(b ^ 1);
+        }
+        else if (role == 0)
+        {
+            if (!is_end && cnt > 0) consume(b, lb, off, cnt);
+        }
+        else
+        {
+            if (is_end)
+                flush(BRICK * (NL - 1), BRICK * NL + 2 * M);
+            else if (first_win && layer > 0)
+                flush(BRICK * (layer - 1), BRICK * layer);
+        }
+        if (is_end) break;
+        __syncthreads();
+    }
+}
+
+// =============================================================================================
+// tile kernel (2D, and the 8-point kernel in 3D)
+// =============================================================================================
 // Brick colouring of a tile, worked out at compile time: the bricks of a tile in colour-major order
 // (colour = brick index mod NC per dimension; NC bricks apart, two footprints of BRICK + 2M cells are disjoint).
 template <int NDIM, int NC>
@@ -127,24 +614,21 @@ __constant__ BrickColouring<NDIM, NC> c_colouring = BrickColouring<NDIM, NC>(); 
 template <int NDIM, int NC>
 __device__ const BrickColouring<NDIM, NC> d_colouring = BrickColouring<NDIM, NC>(); // per-lane reads (order[])
 
-// CL (3D): a thread-block CLUSTER of 2 x 2 x 2 CTAs acts as one 32^3 tile.  Each CTA accumulates the markers of its own
-// 16^3 tile into its own block starting from zero; after a cluster barrier it sums, in rank order, its own block and the
-// parts of its siblings' blocks (read through distributed shared memory) that cover its share of the cluster's
-// (32 + 2M)^3 points -- its tile plus the halo on the cluster's outer sides -- and adds that share to f once.  Only the
-// cluster's outer shell is shared with other launches (the colours are those of the cluster tiles), so f moves
-// ((32 + 2M) / 32)^3 times instead of ((16 + 2M) / 16)^3, and points nothing was spread to are neither read nor written.
-// WIDE: 320 instead of 256 threads with the brick colours: the window grows from 85 to 100 markers (one stencil task per thread).
-template <int NDIM, int K, bool PL, bool CL = false, bool WIDE = false>
-__global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : 2)
+//  * One CTA takes one marker tile (16^ndim cells = 4^ndim bricks, one contiguous run of the sorted markers) and ONE
+//    component, and accumulates the full stencils of its markers into a shared-memory block of (16 + 2M)^ndim points.
+//  * The blocks of two tiles whose indices differ by 2 in some dimension are disjoint: 2^ndim launches (colours).
+//  * Inside the CTA one warp takes one brick at a time and walks its markers in storage order with the 32 lanes spread
+//    over the stencil points; the bricks are visited colour by colour with a CTA barrier between colours.
+//  * 1-D weights are evaluated one thread per (marker, dimension) for a window of markers and parked in shared memory.
+template <int NDIM, int K>
+__global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : (KTraits<K>::M <= 3 ? 2 : 1))
     spread_tile_kernel(const __grid_constant__ TileParams tp, const __grid_constant__ TmaMapSet maps, SpreadArgs args)
 {
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
     constexpr int R = TILE + 2 * M; // haloed block edge
-    constexpr int NT = (PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_THREADS;
+    constexpr int NT = SPREAD_THREADS;
     constexpr int NWARPS = NT / 32;
-    static_assert(!PL || spread_planes_ok<NDIM, K>, "plane owners: 3D, W = 4, M = 2");
-    static_assert(!CL || (NDIM == 3 && !PL), "clusters: 3D, brick-colour accumulation");
     // TMA boxes of 8-byte elements must start on an even x coordinate and have an even x extent (16 bytes):
     // the block gets XO spare columns on the left and is RX wide in x.
     constexpr int XO = M & 1;
@@ -156,7 +640,7 @@ __global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_
     constexpr int NPTS = (NDIM == 3) ? W * W * W : W * W;
     constexpr int NSLOT = (NPTS + 31) / 32;
     constexpr int LD = NDIM - 1;
-    static_assert(R <= 24 && R < 128, "write-out covers a row with 8 lanes x 3 points; origins are kept in bytes");
+    static_assert(R <= 24 && R < 128, "origins are kept in bytes");
     const Colouring& bc = c_colouring<NDIM, NC>;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -176,36 +660,19 @@ __global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_
 
     // which marker tile (of this launch's colour) and which component
     int t[3] = { 0, 0, 0 };
-    bool has_tile = true; // CL: the cluster tile may stick out of the tile grid
-    bool active = true;   // this CTA has markers to spread
-    const int crank = CL ? (int)(blockIdx.x & 7u) : 0; // rank in the cluster: bit d = upper half along d
     {
-        int r = CL ? (int)(blockIdx.x >> 3) : (int)blockIdx.x;
+        int r = (int)blockIdx.x;
         t[0] = 2 * (r % args.ntc[0]) + args.colour[0];
         r /= args.ntc[0];
         t[1] = 2 * (r % args.ntc[1]) + args.colour[1];
         if (NDIM == 3) t[2] = 2 * (r / args.ntc[1]) + args.colour[2];
-        if constexpr (CL)
-        {
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-            {
-                t[d] = 2 * t[d] + ((crank >> d) & 1); // (t[] held the cluster tile)
-                has_tile = has_tile && t[d] < tp.nt[d];
-            }
-            active = has_tile;
-        }
     }
     if (args.part)
     {
         bool in = true;
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) in = in && t[d] >= args.sel_lo[d] && t[d] <= args.sel_hi[d];
-        if ((args.part == 1) != in)
-        {
-            if constexpr (!CL) return;
-            active = false; // the other part's tile: nothing to spread, but the share still collects the siblings' halos
-        }
+        if ((args.part == 1) != in) return;
     }
     const int a = blockIdx.y;
     const CompGeom& cg = tp.comp[a];
@@ -213,38 +680,31 @@ __global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_
     const int b0 = tp.brick_base + tile * NBRICKS;
     // one coalesced read of the tile's NBRICKS + 1 segment offsets, and (independent of it) the colour order
     int my_q = 0;
-    if (threadIdx.x <= NBRICKS) sbs[threadIdx.x] = active ? __ldg(&args.brick_start[b0 + threadIdx.x]) : 0;
+    if (threadIdx.x <= NBRICKS) sbs[threadIdx.x] = __ldg(&args.brick_start[b0 + threadIdx.x]);
     if (threadIdx.x < NBRICKS) my_q = __ldg(&d_colouring<NDIM, NC>.order[threadIdx.x]);
     for (int q = threadIdx.x; q < args.cap; q += NT) relb[q] = 0;
-#ifdef IBK_TIMELINE
-    long long tl[16];
-    for (int k = 0; k < 16; ++k) tl[k] = 0;
-    const bool tl_on = threadIdx.x == 0 && blockIdx.y == 0 && (blockIdx.x % 97) == 5;
-    TL(0);
-#endif
     __syncthreads();
     const int s0 = sbs[0], s1 = sbs[NBRICKS];
-    if (s0 >= s1)
-    {
-        if constexpr (!CL) return;
-        active = false;
-    }
-    TL(1);
+    if (s0 >= s1) return;
 
-    int blo[3]; // pp coordinate of the block's first point
+    int blo[3]; // pp coordinate of the block's first point (x: of the first of the XO spare columns)
+    bool inside = true; // the block does not start before the array
 #pragma unroll
-    for (int d = 0; d < 3; ++d) blo[d] = TILE * t[d] - M;
+    for (int d = 0; d < 3; ++d)
+    {
+        blo[d] = TILE * t[d] - M - (d == 0 ? XO : 0);
+        if (d < NDIM && blo[d] < cg.pp0[d])
+        {
+            if (args.clip_free) blo[d] = cg.pp0[d]; // nothing reaches the points before the array
+            else inside = false;
+        }
+    }
     // With TMA the block starts as a copy of f (out-of-array points read as zero) and is stored back at the end
     // (out-of-array points dropped): `f += S[F]` without a separate zero / add pass and without atomics.
-    // (Measured on B200: a TMA tensor STORE with a negative start coordinate traps, loads do not; the blocks of the
-    // first tile per dimension therefore take the fallback.  The store also writes whole 16-byte units, i.e. one
-    // element of the row padding when n[0] is odd: harmless, nothing reads the padding.)
-    const bool use_tma = !CL && ((args.tma_mask >> a) & 1u) && (blo[0] - XO - cg.pp0[0] >= 0) && (blo[1] - cg.pp0[1] >= 0) &&
-                         (NDIM == 2 || blo[2] - cg.pp0[2] >= 0);
-    // TMA's reducing store (cp.reduce.async.bulk.tensor .add; measured to work on fp64 tensors, scripts/tma_reduce_probe.cu):
-    // the block starts from zero and is added to f in L2, no load.  One CTA per grid point and launch: the order is fixed.
-    const bool use_red = NDIM == 3 && use_tma && args.tma_reduce;
-    if (use_tma && !use_red && threadIdx.x == 0)
+    // (Measured on B200: a TMA tensor STORE with a negative start coordinate traps, loads do not.  The store also writes
+    // whole 16-byte units, i.e. one element of the row padding when n[0] is odd: harmless, nothing reads the padding.)
+    const bool use_tma = ((args.tma_mask >> a) & 1u) && inside;
+    if (use_tma && threadIdx.x == 0)
     {
         mbar_init(&tma_bar, 1);
         mbar_fence_init();
@@ -252,7 +712,7 @@ __global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_
 
     // marker ranges of the bricks in colour-major order, and their running count (two-warp scan)
     int my_cnt = 0, my_incl = 0;
-    if (threadIdx.x < NBRICKS) // (an inactive CTA of a cluster has sbs[] = 0: no markers)
+    if (threadIdx.x < NBRICKS)
     {
         const int s = sbs[my_q], e = sbs[my_q + 1];
         bfirst[threadIdx.x] = s;
@@ -270,17 +730,16 @@ __global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_
         }
         if (lane == 31) wsum[warp] = my_incl;
     }
-    if (!use_tma || use_red)
+    if (!use_tma)
         for (int q = threadIdx.x; q < RPTS; q += NT) acc[q] = 0.0;
     __syncthreads();
-    TL(2);
-    if (use_tma && !use_red && threadIdx.x == 0)
+    if (use_tma && threadIdx.x == 0)
     {
         mbar_expect_tx(&tma_bar, (uint32_t)(RPTS * sizeof(double)));
         if (NDIM == 3)
-            tma_load_3d(acc, &maps.m[a], &tma_bar, blo[0] - XO - cg.pp0[0], blo[1] - cg.pp0[1], blo[2] - cg.pp0[2]);
+            tma_load_3d(acc, &maps.m[a], &tma_bar, blo[0] - cg.pp0[0], blo[1] - cg.pp0[1], blo[2] - cg.pp0[2]);
         else
-            tma_load_2d(acc, &maps.m[a], &tma_bar, blo[0] - XO - cg.pp0[0], blo[1] - cg.pp0[1]);
+            tma_load_2d(acc, &maps.m[a], &tma_bar, blo[0] - cg.pp0[0], blo[1] - cg.pp0[1]);
     }
     if (threadIdx.x < NBRICKS)
     {
@@ -292,8 +751,6 @@ __global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_
     // ---- The tile's markers are taken in windows of `cap` markers in COLOUR-MAJOR brick order.  Per window:
     // (A) all threads evaluate the 1-D stencils, one thread per (marker, dimension); (B) brick colour by brick
     // colour, each warp walks the markers of one brick with the 32 lanes spread over the stencil points.
-    // Same-colour bricks have disjoint footprints and a barrier separates the colours, so no two warps ever
-    // touch the same accumulator word at the same time.
     const double* Xp = args.X;
     const double* Xr = args.Xraw;
     const int G = tp.G;
@@ -307,83 +764,61 @@ __global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_
     {
         const int q = lane + 32 * s;
         const int ix = q % W, iy = (q / W) % W, iz = (NDIM == 3) ? q / (W * W) : 0;
-        poffb[s] = 8 * ((iz * R + iy) * RX + ix + XO);
+        poffb[s] = 8 * ((iz * R + iy) * RX + ix);
         pw0[s] = ix;
         pw1[s] = W + iy;
         pw2[s] = 2 * W + iz;
     }
     __syncthreads();
-    TL(3);
     const int total = bpre[NBRICKS]; // without the dense bricks
 
-    // stencil-evaluation tasks of this thread for a window: the global loads are issued by fetch() -- for window
+    // stencil-evaluation task of this thread for a window: the global loads are issued by fetch() -- for window
     // w + 1 before the accumulation of window w starts, so their latency hides behind it -- and consumed by
     // evaluate() at the top of the window.
-    int t_i[SPREAD_TASKS];
-    double t_xs[SPREAD_TASKS], t_xr[SPREAD_TASKS], t_v[SPREAD_TASKS];
+    int t_i;
+    double t_xs, t_xr, t_v;
     auto fetch = [&](int off, int par) {
         const int cnt = min(cap, total - off);
+        const int tix = threadIdx.x;
+        t_i = -1;
+        if (tix >= cnt * NDIM) return;
+        const int m = tix / NDIM, d = tix - m * NDIM;
+        const int lp = off + m; // position in the tile's colour-major marker list
+        int p = 0;              // its brick (colour-order position): last p with bpre[p] <= lp
 #pragma unroll
-        for (int k = 0; k < SPREAD_TASKS; ++k)
+        for (int step = NBRICKS / 2; step >= 1; step >>= 1)
+            if (bpre[p + step] <= lp) p += step;
+        if (d == 0 && m == 0) wcol[par][0] = bc.colour[p];
+        if (d == 0 && m == cnt - 1) wcol[par][1] = bc.colour[p];
+        const int i = bfirst[p] + (lp - bpre[p]);
+        if (d == 0 && off > 0) relb[par * cap + m] = 0;
+        t_i = i;
+        t_xs = __ldg(&Xp[d * args.x_stride + i]);
+        t_xr = Xr ? __ldg(&Xr[d * args.x_stride + i]) : 0.0;
+        t_v = 1.0;
+        if (d == LD)
         {
-            const int tix = threadIdx.x + k * NT;
-            t_i[k] = -1;
-            if (tix >= cnt * NDIM) continue;
-            const int m = tix / NDIM, d = tix - m * NDIM;
-            const int lp = off + m; // position in the tile's colour-major marker list
-            int p = 0;              // its brick (colour-order position): last p with bpre[p] <= lp
-#pragma unroll
-            for (int step = NBRICKS / 2; step >= 1; step >>= 1)
-                if (bpre[p + step] <= lp) p += step;
-            if (d == 0 && m == 0) wcol[par][0] = bc.colour[p];
-            if (d == 0 && m == cnt - 1) wcol[par][1] = bc.colour[p];
-            const int i = bfirst[p] + (lp - bpre[p]);
-            if (d == 0 && off > 0) relb[par * cap + m] = 0;
-            t_i[k] = i;
-            t_xs[k] = __ldg(&Xp[d * args.x_stride + i]);
-            t_xr[k] = Xr ? __ldg(&Xr[d * args.x_stride + i]) : 0.0;
-            t_v[k] = 1.0;
-            if (d == LD)
-            {
-                const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
-                t_v[k] = __ldg(&args.V[vcol * args.v_cstride + row * args.v_istride]);
-            }
+            const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
+            t_v = __ldg(&args.V[vcol * args.v_cstride + row * args.v_istride]);
         }
     };
     auto evaluate = [&](int par) {
+        if (t_i < 0) return;
+        const int tix = threadIdx.x;
+        const int m = tix / NDIM, d = tix - m * NDIM;
+        const double xl_s = tp.xl[d][cg.var[d]];
+        const double dx_s = tp.dx[d];
+        const int blo_s = (d == 0) ? blo[0] : (d == 1) ? blo[1] : blo[2];
+        double w[W];
+        int l;
+        stencil_1d<K>(t_xs, Xr ? t_xr : t_xs, xl_s, dx_s, l, w, d == cg.axis);
+        const int r0 = l + G - blo_s; // first stencil point relative to the block
+        const bool fits = r0 >= 0 && r0 + W <= ((d == 0) ? RX : R);
+        const double scale = (d == LD) ? t_v * inv_vol : 1.0;
 #pragma unroll
-        for (int k = 0; k < SPREAD_TASKS; ++k)
-        {
-            if (t_i[k] < 0) continue;
-            const int tix = threadIdx.x + k * NT;
-            const int m = tix / NDIM, d = tix - m * NDIM;
-            const double xl_s = tp.xl[d][cg.var[d]];
-            const double dx_s = tp.dx[d];
-            const int blo_s = (d == 0) ? blo[0] : (d == 1) ? blo[1] : blo[2];
-            double w[W];
-            int l;
-            stencil_1d<K>(t_xs[k], Xr ? t_xr[k] : t_xs[k], xl_s, dx_s, l, w, d == cg.axis);
-            const int r0 = l + G - blo_s; // first stencil point relative to the block
-            const bool fits = r0 >= 0 && r0 + W <= R;
-            const double scale = (d == LD) ? t_v[k] * inv_vol : 1.0;
-#pragma unroll
-            for (int j = 0; j < W; ++j) wgt[(m * NDIM + d) * W + j] = w[j] * scale;
-            if constexpr (PL)
-            {
-                // (x, y) byte offset in the low 20 bits, first z plane above them
-                atomicAdd(&relb[par * cap + m], !fits ? -(1 << 29) : (d == 0) ? r0 * 8 : (d == 1) ? r0 * 8 * RX : (r0 << 20));
-                if (!fits && args.exc_list) // left to the fix-up (which removes duplicates)
-                {
-                    const int slot = atomicAdd(args.exc_count, 1);
-                    if (slot < args.exc_capacity) args.exc_list[slot] = t_i[k] * 8 + a;
-                }
-            }
-            else
-            {
-                const int stride_b = (d == 0) ? 8 : (d == 1) ? 8 * RX : 8 * RX * R; // bytes per point along d in the block
-                atomicAdd(&relb[par * cap + m], fits ? r0 * stride_b : -(1 << 29));
-            }
-        }
+        for (int j = 0; j < W; ++j) wgt[(m * NDIM + d) * W + j] = w[j] * scale;
+        const int stride_b = (d == 0) ? 8 : (d == 1) ? 8 * RX : 8 * RX * R; // bytes per point along d in the block
+        atomicAdd(&relb[par * cap + m], fits ? r0 * stride_b : -(1 << 29));
     };
 
     fetch(0, 0);
@@ -394,50 +829,9 @@ __global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_
         // ---- phase A
         evaluate(par);
         __syncthreads();
-        if (off == 0) TL(4);
-        if (use_tma && !use_red && off == 0) mbar_wait(&tma_bar, 0); // the block holds f now
-        if (off == 0) TL(5);
+        if (use_tma && off == 0) mbar_wait(&tma_bar, 0); // the block holds f now
         const int col_lo = wcol[par][0], col_hi = wcol[par][1];
         if (off + cap < total) fetch(off + cap, par ^ 1);
-        if constexpr (PL)
-        {
-            // ---- phase B, plane owners: no barrier until the window is done
-            static_assert(8 * RX * R < (1 << 20), "(x, y) byte offset fits 20 bits");
-            constexpr int PLANE_B = 8 * RX * R;
-            constexpr int NW = NDIM * W;
-            const int* rp = relb + par * cap;
-            const int ix = lane & 3, iy = (lane >> 2) & 3, iz = lane >> 4;
-            const double* wl = wgt + ix; // this lane's x weight of marker 0; y weight at + W + (iy - ix)
-            for (int id = warp; id < R / 2; id += NWARPS)
-            {
-                const int plane = 2 * id + iz;
-                char* const accp = reinterpret_cast<char*>(acc) + plane * PLANE_B + 8 * (iy * RX + ix + XO);
-                for (int c0 = 0; c0 < cnt; c0 += 32)
-                {
-                    const int mm = c0 + lane;
-                    const int ab = (mm < cnt) ? rp[mm] : -1;
-                    const int r0l = ab >> 20;
-                    unsigned hits = __ballot_sync(0xffffffffu, ab >= 0 && r0l <= 2 * id + 1 && r0l + 3 >= 2 * id);
-                    while (hits)
-                    {
-                        const int b = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        const int abm = __shfl_sync(0xffffffffu, ab, b);
-                        const int kz = plane - (abm >> 20);
-                        const double* wp = wl + (c0 + b) * NW;
-                        if ((unsigned)kz < (unsigned)W)
-                        {
-                            const double wv = (wp[0] * wp[W + iy - ix]) * wp[2 * W + kz - ix];
-                            double* pt = reinterpret_cast<double*>(accp + (abm & 0xFFFFF));
-                            *pt = *pt + wv;
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        else
         // ---- phase B, colour by colour (only the colours this window holds)
         for (int col = col_lo; col <= col_hi; ++col)
         {
@@ -486,152 +880,13 @@ __global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_
                         for (int s = 0; s < NSLOT; ++s)
                             if (NPTS % 32 == 0 || lane + 32 * s < NPTS) *reinterpret_cast<double*>(accb + ab + poffb[s]) = av[s] + wv[s];
                     }
-                    else if (lane == 0 && args.exc_list)
-                    {
-                        const int slot = atomicAdd(args.exc_count, 1);
-                        if (slot < args.exc_capacity) args.exc_list[slot] = (bfirst[p] + (off + m - p0)) * 8 + a;
-                    }
+                    else if (lane == 0)
+                        flag_exception(args, bfirst[p] + (off + m - p0), a);
                     __syncwarp();
                 }
             }
             __syncthreads();
         }
-        if (off == 0) TL(6);
-        if (off == cap) TL(7);
-    }
-    TL(8);
-
-    if constexpr (CL)
-    {
-        // ---- cluster write-out: this CTA's share of the cluster's points = own block + the siblings' halos, in rank order
-        namespace cgx = cooperative_groups;
-        cgx::cluster_group cluster = cgx::this_cluster();
-        __shared__ int cl_any; // this CTA spread something (the siblings read it)
-        if (threadIdx.x == 0) cl_any = total > 0 ? 1 : 0;
-        cluster.sync(); // every block of the cluster is complete
-        {
-            int any = 0;
-#pragma unroll
-            for (int sr = 0; sr < 8; ++sr) any |= *cluster.map_shared_rank(&cl_any, sr);
-            if (!any) // nothing was spread into this cluster tile: nothing to add (the same decision in all eight CTAs)
-            {
-                cluster.sync();
-                return;
-            }
-        }
-        constexpr int SH = TILE + M; // share edge: the tile and the halo on the cluster's outer side
-        const int o0 = (crank & 1) ? M : 0, o1 = (crank & 2) ? M : 0, o2 = (crank & 4) ? M : 0;
-        // Write-out by ONE reducing TMA store of the densely repacked share (the share maps have an SH^3 box) when the
-        // share starts inside the array on an even x coordinate; else by the threads.
-        const int c0 = blo[0] + o0 - cg.pp0[0], c1 = blo[1] + o1 - cg.pp0[1], c2 = blo[2] + o2 - cg.pp0[2];
-        const bool by_tma = has_tile && XO == 0 && args.tma_reduce && ((args.tma_mask >> a) & 1u) && c0 >= 0 && (c0 & 1) == 0 && c1 >= 0 && c2 >= 0;
-        if (has_tile)
-        {
-            constexpr int UNR = 8; // points per thread and round: their loads are in flight together
-            unsigned sok = 0;      // siblings that exist (their tile is inside the tile grid)
-#pragma unroll
-            for (int sr = 0; sr < 8; ++sr)
-            {
-                bool ok = true;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) ok = ok && (t[d] - ((crank >> d) & 1) + ((sr >> d) & 1)) < tp.nt[d];
-                if (ok) sok |= 1u << sr;
-            }
-            // the total at share point (lx, ly, lz) of this CTA's block; `both`: the dimensions along which the other
-            // sibling's block holds the point too (it lies in the 2M-wide overlap)
-            auto overlap = [&](int lx, int ly, int lz) -> unsigned {
-                return ((crank & 1) ? (lx < 2 * M) : (lx >= TILE)) | (((crank & 2) ? (ly < 2 * M) : (ly >= TILE)) << 1) |
-                       (((crank & 4) ? (lz < 2 * M) : (lz >= TILE)) << 2);
-            };
-            auto total_at = [&](int lx, int ly, int lz, unsigned both) -> double {
-                double v = 0.0;
-#pragma unroll
-                for (int sr = 0; sr < 8; ++sr)
-                {
-                    const unsigned diff = (unsigned)sr ^ (unsigned)crank;
-                    if ((diff & ~both) != 0 || !((sok >> sr) & 1u)) continue;
-                    // the sibling's block starts 16 points later (earlier) along the dimensions where it is the upper (lower) one
-                    const int cx = lx + ((diff & 1) ? ((crank & 1) ? TILE : -TILE) : 0);
-                    const int cy = ly + ((diff & 2) ? ((crank & 2) ? TILE : -TILE) : 0);
-                    const int cz = lz + ((diff & 4) ? ((crank & 4) ? TILE : -TILE) : 0);
-                    v += cluster.map_shared_rank(acc, sr)[(cz * R + cy) * RX + cx + XO];
-                }
-                return v;
-            };
-            if (by_tma)
-            {
-                // totals IN PLACE: a CTA's share and the strips its siblings read from its block are disjoint, and the
-                // share points outside the overlaps already hold their total
-                for (int q = threadIdx.x; q < SH * SH * SH; q += NT)
-                {
-                    const int lx = q % SH + o0, ly = (q / SH) % SH + o1, lz = q / (SH * SH) + o2;
-                    const unsigned both = overlap(lx, ly, lz);
-                    if (both) acc[(lz * R + ly) * RX + lx + XO] = total_at(lx, ly, lz, both);
-                }
-            }
-            else
-            {
-                // the element of f behind share point q (nullptr: outside the array)
-                auto gaddr = [&](int q) -> double* {
-                    const int gi = c0 + q % SH, gj = c1 + (q / SH) % SH, gk = c2 + q / (SH * SH);
-                    if (gi < 0 || gi >= cg.n[0] || gj < 0 || gj >= cg.n[1] || gk < 0 || gk >= cg.n[2]) return nullptr;
-                    return cg.ptr + ((long long)(gk * cg.n[1] + gj) * cg.pitch + gi);
-                };
-                for (int q0 = threadIdx.x; q0 < SH * SH * SH; q0 += NT * UNR)
-                {
-                    double v[UNR];
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u)
-                    {
-                        const int q = q0 + u * NT;
-                        v[u] = 0.0;
-                        if (q >= SH * SH * SH) continue;
-                        const int lx = q % SH + o0, ly = (q / SH) % SH + o1, lz = q / (SH * SH) + o2; // in this CTA's block
-                        const unsigned both = overlap(lx, ly, lz);
-                        v[u] = both ? total_at(lx, ly, lz, both) : acc[(lz * R + ly) * RX + lx + XO];
-                    }
-                    // f += share: inside a launch a grid point belongs to exactly one CTA (plain read-modify-write, fixed
-                    // order); points nothing was spread to are neither read nor written
-                    unsigned wr = 0;
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u)
-                    {
-                        if (v[u] == 0.0) continue;
-                        const double* g = gaddr(q0 + u * NT);
-                        if (!g) continue;
-                        v[u] = *g + v[u];
-                        wr |= 1u << u;
-                    }
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u)
-                        if ((wr >> u) & 1u) *gaddr(q0 + u * NT) = v[u];
-                }
-            }
-        }
-        cluster.sync(); // nobody reads this CTA's block any more
-        if (by_tma)
-        {
-            // dense repack of the share to the start of the block: destination q never lies behind its source, so chunks of
-            // NT points in ascending order only need their reads separated from their writes
-            for (int q0 = 0; q0 < SH * SH * SH; q0 += NT)
-            {
-                const int q = q0 + threadIdx.x;
-                double val = 0.0;
-                if (q < SH * SH * SH) val = acc[((q / (SH * SH) + o2) * R + (q / SH) % SH + o1) * RX + q % SH + o0];
-                __syncthreads();
-                if (q < SH * SH * SH) acc[q] = val;
-            }
-            fence_proxy_async_smem();
-            __syncthreads();
-            if (threadIdx.x == 0)
-            {
-                asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&maps.m[a]),
-                             "r"(smem_u32(acc)), "r"(c0), "r"(c1), "r"(c2)
-                             : "memory");
-                tma_store_commit_and_wait_read();
-            }
-        }
-        return;
     }
 
     // ---- write-out.  TMA: the block (= old f + the spread values) is stored back, clipped to the array.
@@ -641,59 +896,30 @@ __global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_
         __syncthreads();
         if (threadIdx.x == 0)
         {
-            if (use_red)
-                asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&maps.m[a]),
-                             "r"(smem_u32(acc)), "r"(blo[0] - XO - cg.pp0[0]), "r"(blo[1] - cg.pp0[1]), "r"(blo[2] - cg.pp0[2])
-                             : "memory");
-            else if (NDIM == 3)
-                tma_store_3d(&maps.m[a], acc, blo[0] - XO - cg.pp0[0], blo[1] - cg.pp0[1], blo[2] - cg.pp0[2]);
+            if (NDIM == 3)
+                tma_store_3d(&maps.m[a], acc, blo[0] - cg.pp0[0], blo[1] - cg.pp0[1], blo[2] - cg.pp0[2]);
             else
-                tma_store_2d(&maps.m[a], acc, blo[0] - XO - cg.pp0[0], blo[1] - cg.pp0[1]);
+                tma_store_2d(&maps.m[a], acc, blo[0] - cg.pp0[0], blo[1] - cg.pp0[1]);
             tma_store_commit_and_wait_read(); // shared memory must stay alive until it has been read
-#ifdef IBK_TIMELINE
-            TL(9);
-            if (tl_on)
-            {
-                const int slot = atomicAdd(&g_tl_n, 1);
-                if (slot < 64)
-                    for (int k = 0; k < 16; ++k) g_tl[slot][k] = tl[k];
-            }
-#endif
         }
         return;
     }
-    // Fallback (array not addressable by TMA): f += block with `red.global.add.f64`, rows along x, dropping points
-    // outside the array.  Inside one launch a grid point belongs to at most one CTA and the launches are ordered by
-    // the stream, so the order of the additions is fixed and the result bit-reproducible.
+    // Fallback (array not addressable by TMA, or the block starts before the array): f += block by plain loads and
+    // stores, rows along x, dropping points outside the array.  Inside one launch a grid point belongs to at most one CTA
+    // and the launches are ordered by the stream, so the order of the additions is fixed.
     {
         constexpr int ROWS = (NDIM == 3) ? R * R : R;
-        constexpr int RSTEP = NT / 8; // rows per sweep: a group of 8 lanes takes one row at a time,
-        const int g8 = threadIdx.x >> 3, l8 = threadIdx.x & 7; // 8 lanes x 3 points cover R <= 24 points
-        const int gx0 = blo[0] - cg.pp0[0] + l8;
-        bool okx[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) okx[k] = (l8 + 8 * k < R) && (gx0 + 8 * k >= 0) && (gx0 + 8 * k < cg.n[0]);
-        int y = g8 % R, z = g8 / R;
-        const int gy0 = blo[1] - cg.pp0[1], gz0 = (NDIM == 3) ? blo[2] - cg.pp0[2] : 0;
-        const double* arow = acc + g8 * RX + XO + l8;
-        for (int row = g8; row < ROWS; row += RSTEP, arow += RSTEP * RX)
+        const int gx0 = blo[0] - cg.pp0[0], gy0 = blo[1] - cg.pp0[1], gz0 = (NDIM == 3) ? blo[2] - cg.pp0[2] : 0;
+        for (int row = warp; row < ROWS; row += NWARPS)
         {
-            const int gj = gy0 + y, gk = gz0 + z;
-            y += RSTEP % R;
-            z += RSTEP / R;
-            if (y >= R)
-            {
-                y -= R;
-                ++z;
-            }
+            const int gj = gy0 + row % R, gk = gz0 + row / R;
             if (gj < 0 || gj >= cg.n[1] || gk < 0 || gk >= cg.n[2]) continue;
-            double* prow = cg.ptr + ((long long)(gk * cg.n[1] + gj) * cg.pitch + gx0);
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
+            double* prow = cg.ptr + ((long long)gk * cg.n[1] + gj) * cg.pitch;
+            if (lane < RX)
             {
-                if (!okx[k]) continue;
-                const double v = arow[8 * k];
-                if (v != 0.0) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(prow + 8 * k), "d"(v) : "memory");
+                const int gi = gx0 + lane;
+                const double v = acc[row * RX + lane];
+                if (gi >= 0 && gi < cg.n[0] && v != 0.0) prow[gi] += v;
             }
         }
     }
@@ -701,7 +927,7 @@ __global__ void __launch_bounds__((PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_
 
 // ---------------------------------------------------------------------------------------------
 // Dense bricks (3D).  A structure puts tens of markers into a cell, hundreds into a brick; the
-// tile kernel would walk them with ONE warp (a brick is the unit of its colouring).  Here a CTA takes one dense
+// tile kernels would walk them with ONE warp (a brick is the unit of their colouring).  Here a CTA takes one dense
 // brick and one component: every warp holds the brick's footprint ((4 + 2M)^3 points; for M = 3 one z half of it) in
 // registers, 12-20 points per lane, and adds every 8th (4th) batch of the brick's markers into it with zero-padded 1-D weight
 // vectors -- branch-free, no shared-memory read-modify-write, no conflicts.  The eight partial footprints are then
@@ -809,11 +1035,8 @@ __global__ void __launch_bounds__(256, (KTraits<K>::M <= 2) ? 3 : 2)
 #pragma unroll
                 for (int j = 0; j < W; ++j) wp[r0 + j] = w[j] * scale;
             }
-            else if (args.exc_list && zh == 0) // the whole (marker, component) goes to the fix-up; a zero factor removes it here
-            {
-                const int slot = atomicAdd(args.exc_count, 1);
-                if (slot < args.exc_capacity) args.exc_list[slot] = i * 8 + a;
-            }
+            else if (zh == 0) // the whole (marker, component) goes to the fix-up; a zero factor removes it here
+                flag_exception(args, i, a);
         }
         __syncwarp();
         for (int m = 0; m < nb; ++m)
@@ -871,101 +1094,102 @@ __global__ void __launch_bounds__(256, (KTraits<K>::M <= 2) ? 3 : 2)
     }
 }
 
-// Fix-up for the (practically never occurring) (marker, component) pairs whose stencil does not fit the
-// haloed block of their tile: one thread, sorted order, the whole stencil, clipped to the array only.
+// ---------------------------------------------------------------------------------------------
+// Fix-up for the flagged (entry, component) pairs: ONE CTA walks the flag words in order; each flagged pair is spread by
+// warp 0 with its whole stencil, clipped to the array only, lanes over the stencil points.  Order: sorted position, then
+// component.  The words are cleared on the way, so the flags are all zero again afterwards.
+// ---------------------------------------------------------------------------------------------
+constexpr int FIXUP_THREADS = 256;
 template <int NDIM, int K>
-__global__ void spread_fixup_kernel(const __grid_constant__ TileParams tp, SpreadArgs args)
+__global__ void __launch_bounds__(FIXUP_THREADS) spread_fixup_kernel(const __grid_constant__ TileParams tp, SpreadArgs args)
 {
     constexpr int W = KTraits<K>::W;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int n = *args.exc_count;
-    if (n <= 0) return;
-    if (n > args.exc_capacity) n = args.exc_capacity;
-    for (int a = 1; a < n; ++a) // insertion sort (tiny list)
+    constexpr int NPTS = (NDIM == 3) ? W * W * W : W * W;
+    __shared__ int s_list[FIXUP_THREADS];
+    __shared__ unsigned s_word[FIXUP_THREADS];
+    __shared__ int s_wcnt[FIXUP_THREADS / 32 + 1];
+    if (*args.exc_count <= 0) return; // (uniform)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwords = (args.n_entries + 3) / 4;
+    for (int base = 0; base < nwords; base += FIXUP_THREADS)
     {
-        const int v = args.exc_list[a];
-        int b = a - 1;
-        while (b >= 0 && args.exc_list[b] > v)
+        const int wi = base + threadIdx.x;
+        const unsigned w = wi < nwords ? args.exc_flags[wi] : 0u;
+        // ordered compaction of the nonzero words of this chunk
+        const unsigned bal = __ballot_sync(0xffffffffu, w != 0u);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int k = 0; k < FIXUP_THREADS / 32; ++k)
         {
-            args.exc_list[b + 1] = args.exc_list[b];
-            --b;
+            if (k < warp) before += s_wcnt[k];
+            total += s_wcnt[k];
         }
-        args.exc_list[b + 1] = v;
-    }
-    for (int e = 0; e < n; ++e)
-    {
-        const int code = args.exc_list[e];
-        if (e > 0 && args.exc_list[e - 1] == code) continue;
-        const int i = code >> 3, a = code & 7;
-        const CompGeom& cg = tp.comp[a];
-        const long long row = args.src ? (long long)args.src[i] : (long long)i;
-        double w[3][W];
-        int lo[3] = { 0, 0, 0 };
-        for (int d = 0; d < NDIM; ++d)
+        if (w != 0u)
         {
-            const double xs = args.X[d * args.x_stride + i];
-            const double xr = args.Xraw ? args.Xraw[d * args.x_stride + i] : xs;
-            int l;
-            stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w[d], d == cg.axis);
-            lo[d] = l + tp.G;
+            const int pos = before + __popc(bal & ((1u << lane) - 1u));
+            s_list[pos] = wi;
+            s_word[pos] = w;
+            args.exc_flags[wi] = 0u;
         }
-        const double f = args.V[cg.vcol * args.v_cstride + row * args.v_istride] * tp.inv_vol;
-        const int KW = (NDIM == 3) ? W : 1;
-        for (int k = 0; k < KW; ++k)
-            for (int j = 0; j < W; ++j)
-                for (int ii = 0; ii < W; ++ii)
+        __syncthreads();
+        if (warp == 0)
+        {
+            for (int e = 0; e < total; ++e)
+            {
+                const unsigned word = s_word[e];
+                for (int bit = 0; bit < 32; ++bit)
                 {
-                    const int gi = lo[0] + ii - cg.pp0[0], gj = lo[1] + j - cg.pp0[1],
-                              gk = (NDIM == 3) ? lo[2] + k - cg.pp0[2] : 0;
-                    if (gi < 0 || gi >= cg.n[0] || gj < 0 || gj >= cg.n[1] || gk < 0 || gk >= cg.n[2]) continue;
-                    double wv = w[0][ii] * w[1][j];
-                    if (NDIM == 3) wv *= w[2][k];
-                    cg.ptr[((long long)gk * cg.n[1] + gj) * cg.pitch + gi] += wv * f;
+                    if (!((word >> bit) & 1u)) continue;
+                    const int i = s_list[e] * 4 + (bit >> 3), a = bit & 7;
+                    if (i >= args.n_entries || a >= tp.ncomp) continue;
+                    const CompGeom& cg = tp.comp[a];
+                    const long long row = args.src ? (long long)args.src[i] : (long long)i;
+                    double w1[3][W];
+                    int lo[3] = { 0, 0, 0 };
+                    for (int d = 0; d < NDIM; ++d)
+                    {
+                        const double xs = args.X[d * args.x_stride + i];
+                        const double xr = args.Xraw ? args.Xraw[d * args.x_stride + i] : xs;
+                        int l;
+                        stencil_1d<K>(xs, xr, tp.xl[d][cg.var[d]], tp.dx[d], l, w1[d], d == cg.axis);
+                        lo[d] = l + tp.G;
+                    }
+                    const double f = args.V[cg.vcol * args.v_cstride + row * args.v_istride] * tp.inv_vol;
+                    for (int q = lane; q < NPTS; q += 32)
+                    {
+                        const int ii = q % W, j = (q / W) % W, k = (NDIM == 3) ? q / (W * W) : 0;
+                        const int gi = lo[0] + ii - cg.pp0[0], gj = lo[1] + j - cg.pp0[1], gk = (NDIM == 3) ? lo[2] + k - cg.pp0[2] : 0;
+                        if (gi < 0 || gi >= cg.n[0] || gj < 0 || gj >= cg.n[1] || gk < 0 || gk >= cg.n[2]) continue;
+                        double wv = w1[0][ii] * w1[1][j];
+                        if (NDIM == 3) wv *= w1[2][k];
+                        cg.ptr[((long long)gk * cg.n[1] + gj) * cg.pitch + gi] += wv * f;
+                    }
+                    __syncwarp();
                 }
+            }
+        }
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *args.exc_count = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int* g_exc_buf = nullptr; // [1 + capacity] per process (device); tiny
-constexpr int EXC_CAPACITY = 4096;
-
-template <int NDIM, int K, bool PL, bool WIDE = false>
-static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err);
-
 template <int NDIM, int K>
 static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err)
 {
-    if constexpr (spread_planes_ok<NDIM, K>)
-    {
-        // IBK_SPREAD_PLANES=0 / 1 overrides the default
-        static const char* env = getenv("IBK_SPREAD_PLANES");
-        static const bool planes = env ? atoi(env) != 0 : SPREAD_PLANES_DEFAULT;
-        if (planes) return launch_spread_pl<NDIM, K, true>(L, tp, bins, mv, err);
-        static const bool wide = getenv("IBK_SPREAD_WIDE") ? atoi(getenv("IBK_SPREAD_WIDE")) != 0 : false; // not measured yet
-        if (wide) return launch_spread_pl<NDIM, K, false, true>(L, tp, bins, mv, err);
-    }
-    return launch_spread_pl<NDIM, K, false>(L, tp, bins, mv, err);
-}
-
-template <int NDIM, int K, bool PL, bool WIDE>
-static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bins& bins, const MarkerView& mv, std::string& err)
-{
-    constexpr int NT = (PL || WIDE) ? SPREAD_THREADS_PLANES : SPREAD_THREADS;
     constexpr int W = KTraits<K>::W;
     constexpr int M = KTraits<K>::M;
-    constexpr int R = TILE + 2 * M;
-    constexpr int XO = M & 1;
-    constexpr int RX = (R + XO + 1) & ~1;
-    constexpr int RPTS = (NDIM == 3) ? R * R * RX : R * RX;
     cudaError_t e;
-    if (!g_exc_buf)
+    if (!bins.exc_flags || !bins.exc_count)
     {
-        if ((e = cudaMalloc(&g_exc_buf, sizeof(int) * (1 + EXC_CAPACITY))) != cudaSuccess) return e;
+        err = "spread: the bins carry no exception flags";
+        return cudaErrorInvalidValue;
     }
-    if ((e = cudaMemsetAsync(g_exc_buf, 0, sizeof(int), L.stream)) != cudaSuccess) return e;
     SpreadArgs args;
+    std::memset(&args, 0, sizeof(args));
     args.brick_start = bins.brick_start;
     args.X = mv.X;
     args.Xraw = mv.Xraw;
@@ -974,15 +1198,10 @@ static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bin
     args.v_cstride = mv.v_cstride;
     args.v_istride = mv.v_istride;
     args.src = mv.src;
-    args.exc_count = g_exc_buf;
-    args.exc_list = g_exc_buf + 1;
-    args.exc_capacity = EXC_CAPACITY;
+    args.exc_count = bins.exc_count;
+    args.exc_flags = bins.exc_flags;
+    args.n_entries = bins.n_entries;
     args.part = mv.part;
-    {
-        // measured 4.08 ms against 4.28 ms; tests/test_gpu_configs.py passes with it, the full parity suite has not been run yet
-        static const bool red = getenv("IBK_SPREAD_REDUCE") ? atoi(getenv("IBK_SPREAD_REDUCE")) != 0 : false;
-        args.tma_reduce = red ? 1 : 0;
-    }
     for (int d = 0; d < 3; ++d)
     {
         args.sel_lo[d] = mv.sel_lo[d];
@@ -993,42 +1212,22 @@ static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bin
     for (size_t p = 0; p < bins.range_base.size(); ++p)
         if (bins.range_base[p] == tp.brick_base && bins.range_last[p] > bins.range_first[p]) any = true;
     if (!any) return cudaSuccess;
-    // window size: as many markers as the shared memory left by the block allows at the target residency
-    static const int cap_env = getenv("IBK_SPREAD_CAP") ? atoi(getenv("IBK_SPREAD_CAP")) : 0;
-    constexpr int target_ctas = (M <= 2) ? 3 : 2;
-    constexpr long long budget = 233472 / target_ctas - 1024 - 2304 - (long long)sizeof(double) * RPTS;
-    constexpr int per_marker = (int)sizeof(double) * NDIM * W + 2 * (int)sizeof(int);
-    constexpr int cap_fit = (int)(budget / per_marker);
-    args.cap = (cap_env >= 8 && cap_env <= 1024) ? cap_env : std::max(32, std::min(256, cap_fit));
-    args.cap = std::min(args.cap, SPREAD_TASKS * NT / NDIM); // fetch()/evaluate() hold SPREAD_TASKS tasks per thread
-    const size_t smem = sizeof(double) * ((size_t)RPTS + (size_t)args.cap * NDIM * W) + 2 * sizeof(int) * (size_t)args.cap;
-    // TMA moves the block when it can address the array and the block starts on an even x coordinate
+    static const bool no_tma = getenv("IBK_NO_TMA") != nullptr; // (debugging: every block takes the plain write-out)
+    constexpr bool MARCH = (NDIM == 3 && M <= 3);
+    // the first block per dimension may start at the array's first element when no stencil reaches outside the arrays and
+    // the shifted block stays clear of the next block of the same colour
+    args.clip_free = mv.clip_free ? 1 : 0;
+    for (int a = 0; a < tp.ncomp; ++a)
+        for (int d = 0; d < NDIM; ++d)
+            if (tp.comp[a].pp0[d] > (MARCH ? 2 * TILE : TILE) - 1 - 3 * M) args.clip_free = 0;
     TmaMapSet maps;
     std::memset(&maps, 0, sizeof(maps));
     args.tma_mask = 0;
-    static const bool no_tma = getenv("IBK_NO_TMA") != nullptr;
-    // L2 promotion of the block loads: 64 B measured best (4.28 ms; 128 B and none 4.41 ms on the C5 shard)
-    static const int promo = getenv("IBK_TMA_PROMO_SPREAD") ? atoi(getenv("IBK_TMA_PROMO_SPREAD")) : 1;
-    for (int a = 0; a < tp.ncomp; ++a)
-        if (!no_tma && ((tp.comp[a].pp0[0] + M + XO) % 2 == 0) && make_tensor_map(&maps.m[a], tp.comp[a], NDIM, RX, R, R, promo))
-            args.tma_mask |= (1u << a);
-    static const bool dbg = getenv("IBK_DEBUG") != nullptr;
-    if (dbg)
-        for (int a = 0; a < tp.ncomp; ++a)
-            fprintf(stderr, "[ibk] spread<%d,%d> comp %d tma=%u n=(%d,%d,%d) pitch=%lld pp0=(%d,%d,%d) ptr=%p nt=(%d,%d,%d) box=(%d,%d)\n", NDIM,
-                    K, a, (args.tma_mask >> a) & 1u, tp.comp[a].n[0], tp.comp[a].n[1], tp.comp[a].n[2], tp.comp[a].pitch,
-                    tp.comp[a].pp0[0], tp.comp[a].pp0[1], tp.comp[a].pp0[2], (void*)tp.comp[a].ptr, tp.nt[0], tp.nt[1], tp.nt[2], RX, R);
-    auto kfn = spread_tile_kernel<NDIM, K, PL, false, WIDE>;
     auto ffn = spread_fixup_kernel<NDIM, K>;
-    e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess)
-    {
-        err = "cudaFuncSetAttribute(spread) failed";
-        return e;
-    }
+
     // dense bricks first (their own kernel), then the tiles without them
     args.dense_thresh = 0;
-    if constexpr (NDIM == 3 && KTraits<K>::M <= 3) // (a 12^3 footprint does not fit the dense kernel's static shared memory)
+    if constexpr (NDIM == 3 && M <= 3) // (a 12^3 footprint does not fit the dense kernel's static shared memory)
     {
         static const bool no_dense = getenv("IBK_NO_DENSE") != nullptr;
         if (bins.n_dense > 0 && !no_dense && mv.part != 1) // (with a tile selection the dense bricks go with the boundary part)
@@ -1045,107 +1244,98 @@ static cudaError_t launch_spread_pl(Launcher& L, const TileParams& tp, const Bin
         else if (bins.n_dense > 0 && !no_dense)
             args.dense_thresh = DENSE_BRICK_MARKERS; // part 1: the dense bricks are (were) done with part 2 / 0
     }
-    if constexpr (NDIM == 3 && !PL && !WIDE)
+
+    if constexpr (MARCH)
     {
-        static const char* env = getenv("IBK_SPREAD_CLUSTER"); // 0 / 1 overrides the default
-        static const bool use_cluster = env ? atoi(env) != 0 : SPREAD_CLUSTER_DEFAULT;
-        if (use_cluster)
+        using C = MarchCfg<K>;
+        // planes are added to f by TMA when it can address the array and the block starts on an even x coordinate
+        for (int a = 0; a < tp.ncomp; ++a)
+            if (!no_tma && ((tp.comp[a].pp0[0] + M + C::XO) % 2 == 0) && make_tensor_map(&maps.m[a], tp.comp[a], 3, C::RX, C::R, 1, 0))
+                args.tma_mask |= (1u << a);
+        constexpr size_t ring_bytes = (size_t)C::NRING * C::PLANE * sizeof(double);
+        constexpr size_t budget = 232448 - 3072 - ring_bytes - C::SINK_B - 2 * C::REC; // (static shared memory: the per-layer tables)
+        static const int cap_env = getenv("IBK_SPREAD_CAP") ? atoi(getenv("IBK_SPREAD_CAP")) : 0;
+        args.cap = (int)std::min<size_t>(384, budget / (2 * C::REC));
+        if (cap_env >= 32 && cap_env < args.cap) args.cap = cap_env;
+        const size_t smem = ring_bytes + C::SINK_B + 2 * (size_t)(args.cap + 1) * C::REC;
+        static const int chunk_env = getenv("IBK_SPREAD_CHUNK") ? atoi(getenv("IBK_SPREAD_CHUNK")) : 0;
+        args.chunk_tiles = (chunk_env >= 1 && chunk_env <= MARCH_MAX_LAYERS / TILE_BRICKS) ? chunk_env : 4;
+        auto kfn = spread_march_kernel<K>;
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
         {
-            // clusters of 2 x 2 x 2 CTAs = 32^3 cluster tiles; 8 colours of cluster tiles, one launch each
-            auto cfn = spread_tile_kernel<NDIM, K, false, true>;
-            // IBK_SPREAD_CLUSTER=2: the shares are added by TMA's reducing store (maps with a (16 + M)^3 box; even M only)
-            static const bool share_tma = env && atoi(env) == 2;
-            args.tma_reduce = 0;
-            args.tma_mask = 0;
-            if (share_tma && M % 2 == 0)
+            err = "cudaFuncSetAttribute(spread march) failed";
+            return e;
+        }
+        int nm[3]; // march tiles per dimension
+        nm[0] = (tp.nt[0] + 1) / 2;
+        nm[1] = (tp.nt[1] + 1) / 2;
+        nm[2] = (tp.nt[2] + args.chunk_tiles - 1) / args.chunk_tiles;
+        for (int c = 0; c < 8; ++c)
+        {
+            int ntiles = 1;
+            for (int d = 0; d < 3; ++d)
             {
-                args.tma_reduce = 1;
-                for (int a = 0; a < tp.ncomp; ++a)
-                    if (!no_tma && ((tp.comp[a].pp0[0] + M) % 2 == 0) && make_tensor_map(&maps.m[a], tp.comp[a], NDIM, TILE + M, TILE + M, TILE + M, promo))
-                        args.tma_mask |= (1u << a);
+                args.colour[d] = (c >> d) & 1;
+                args.ntc[d] = (nm[d] - args.colour[d] + 1) / 2;
+                ntiles *= args.ntc[d];
             }
-            e = cudaFuncSetAttribute(cfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess)
-            {
-                err = "cudaFuncSetAttribute(spread, cluster) failed";
-                return e;
-            }
-            for (int c = 0; c < 8; ++c)
-            {
-                int nclusters = 1;
-                for (int d = 0; d < 3; ++d)
-                {
-                    const int nct = (tp.nt[d] + 1) / 2; // cluster tiles along d
-                    args.colour[d] = (c >> d) & 1;
-                    args.ntc[d] = (nct - args.colour[d] + 1) / 2;
-                    nclusters *= args.ntc[d];
-                }
-                if (nclusters <= 0) continue;
-                cudaLaunchConfig_t cfg;
-                std::memset(&cfg, 0, sizeof(cfg));
-                cfg.gridDim = dim3(8u * (unsigned)nclusters, (unsigned)tp.ncomp);
-                cfg.blockDim = dim3(NT);
-                cfg.dynamicSmemBytes = smem;
-                cfg.stream = L.stream;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = 8;
-                at[0].val.clusterDim.y = 1;
-                at[0].val.clusterDim.z = 1;
-                cfg.attrs = at;
-                cfg.numAttrs = 1;
-                if ((e = cudaLaunchKernelEx(&cfg, cfn, tp, maps, args)) != cudaSuccess)
-                {
-                    err = "cudaLaunchKernelEx(spread, cluster) failed";
-                    return e;
-                }
-                L.launches++;
-            }
-            ffn<<<1, 32, 0, L.stream>>>(tp, args);
+            if (ntiles <= 0) continue;
+            kfn<<<dim3((unsigned)ntiles, (unsigned)tp.ncomp), C::NT, smem, L.stream>>>(tp, maps, args);
             L.launches++;
-            return cudaGetLastError();
         }
     }
-    // 2^ndim tile colours, one launch each (same-colour blocks are disjoint)
-    const int ncol = (NDIM == 3) ? 8 : 4;
-    for (int c = 0; c < ncol; ++c)
+    else
     {
-        int ntiles = 1;
-        for (int d = 0; d < 3; ++d)
+        constexpr int R = TILE + 2 * M;
+        constexpr int XO = M & 1;
+        constexpr int RX = (R + XO + 1) & ~1;
+        constexpr int RPTS = (NDIM == 3) ? R * R * RX : R * RX;
+        // window size: as many markers as the shared memory left by the block allows at the target residency
+        constexpr int target_ctas = (M <= 2) ? 3 : (M <= 3 ? 2 : 1);
+        constexpr long long budget = 233472 / target_ctas - 1024 - 2304 - (long long)sizeof(double) * RPTS;
+        constexpr int per_marker = (int)sizeof(double) * NDIM * W + 2 * (int)sizeof(int);
+        constexpr int cap_fit = (int)(budget / per_marker);
+        args.cap = std::max(32, std::min(256, cap_fit));
+        args.cap = std::min(args.cap, SPREAD_THREADS / NDIM); // one stencil task per thread and window
+        const size_t smem = sizeof(double) * ((size_t)RPTS + (size_t)args.cap * NDIM * W) + 2 * sizeof(int) * (size_t)args.cap;
+        // L2 promotion of the block loads: 64 B measured best
+        for (int a = 0; a < tp.ncomp; ++a)
+            if (!no_tma && ((tp.comp[a].pp0[0] + M + XO) % 2 == 0) && make_tensor_map(&maps.m[a], tp.comp[a], NDIM, RX, R, R, 1))
+                args.tma_mask |= (1u << a);
+        auto kfn = spread_tile_kernel<NDIM, K>;
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
         {
-            args.colour[d] = (d < NDIM) ? (c >> d) & 1 : 0;
-            args.ntc[d] = (d < NDIM) ? (tp.nt[d] - args.colour[d] + 1) / 2 : 1;
-            ntiles *= args.ntc[d];
+            err = "cudaFuncSetAttribute(spread) failed";
+            return e;
         }
-        if (ntiles <= 0) continue;
-        dim3 grid((unsigned)ntiles, (unsigned)tp.ncomp);
-        kfn<<<grid, NT, smem, L.stream>>>(tp, maps, args);
-        L.launches++;
+        // 2^ndim tile colours, one launch each (same-colour blocks are disjoint)
+        const int ncol = (NDIM == 3) ? 8 : 4;
+        for (int c = 0; c < ncol; ++c)
+        {
+            int ntiles = 1;
+            for (int d = 0; d < 3; ++d)
+            {
+                args.colour[d] = (d < NDIM) ? (c >> d) & 1 : 0;
+                args.ntc[d] = (d < NDIM) ? (tp.nt[d] - args.colour[d] + 1) / 2 : 1;
+                ntiles *= args.ntc[d];
+            }
+            if (ntiles <= 0) continue;
+            kfn<<<dim3((unsigned)ntiles, (unsigned)tp.ncomp), SPREAD_THREADS, smem, L.stream>>>(tp, maps, args);
+            L.launches++;
+        }
     }
-    ffn<<<1, 32, 0, L.stream>>>(tp, args);
+    static const bool dbg_exc = getenv("IBK_DEBUG_EXC") != nullptr;
+    if (dbg_exc)
+    {
+        int h = 0;
+        cudaMemcpyAsync(&h, args.exc_count, sizeof(int), cudaMemcpyDeviceToHost, L.stream);
+        cudaStreamSynchronize(L.stream);
+        fprintf(stderr, "[ibk] spread<%d,%d>: %d flagged (entry, component) pairs of %d entries\n", NDIM, K, h, args.n_entries);
+    }
+    ffn<<<1, FIXUP_THREADS, 0, L.stream>>>(tp, args);
     L.launches++;
-#ifdef IBK_TIMELINE
-    {
-        static int calls = 0;
-        if (++calls == 6)
-        {
-            cudaStreamSynchronize(L.stream);
-            static long long h[64][16];
-            int n = 0;
-            cudaMemcpyFromSymbol(&n, g_tl_n, sizeof(int));
-            cudaMemcpyFromSymbol(h, g_tl, sizeof(h));
-            n = std::min(n, 64);
-            double avg[16] = { 0 };
-            int used = 0;
-            for (int i = n / 2; i < n; ++i, ++used)
-                for (int k = 1; k < 10; ++k) avg[k] += (double)(h[i][k] - h[i][0]);
-            fprintf(stderr, "[timeline] %d samples; cycles since CTA start:", used);
-            const char* nm[10] = { "start", "offsets", "bricks", "scan", "phaseA0", "tma_wait", "phaseB0", "window1", "allB", "stored" };
-            for (int k = 1; k < 10; ++k) fprintf(stderr, " %s=%.0f", nm[k], avg[k] / std::max(used, 1));
-            fprintf(stderr, "\n");
-        }
-    }
-#endif
     return cudaGetLastError();
 }
 
@@ -1155,48 +1345,31 @@ static cudaError_t launch_spread_k(Launcher& L, int kernel, const TileParams& tp
 {
     switch (kernel)
     {
-    case IBK_PIECEWISE_LINEAR:
-        return launch_spread_t<NDIM, IBK_PIECEWISE_LINEAR>(L, tp, bins, mv, err);
-    case IBK_IB_4:
-        return launch_spread_t<NDIM, IBK_IB_4>(L, tp, bins, mv, err);
-    case IBK_IB_6:
-        return launch_spread_t<NDIM, IBK_IB_6>(L, tp, bins, mv, err);
-    case IBK_BSPLINE_3:
-        return launch_spread_t<NDIM, IBK_BSPLINE_3>(L, tp, bins, mv, err);
-    case IBK_BSPLINE_4:
-        return launch_spread_t<NDIM, IBK_BSPLINE_4>(L, tp, bins, mv, err);
-    case IBK_IB_3:
-        return launch_spread_t<NDIM, IBK_IB_3>(L, tp, bins, mv, err);
-    case IBK_BSPLINE_5:
-        return launch_spread_t<NDIM, IBK_BSPLINE_5>(L, tp, bins, mv, err);
-    case IBK_BSPLINE_6:
-        return launch_spread_t<NDIM, IBK_BSPLINE_6>(L, tp, bins, mv, err);
-    case IBK_PIECEWISE_CUBIC:
-        return launch_spread_t<NDIM, IBK_PIECEWISE_CUBIC>(L, tp, bins, mv, err);
-    case IBK_IB_5:
-        return launch_spread_t<NDIM, IBK_IB_5>(L, tp, bins, mv, err);
-    case IBK_PIECEWISE_CONSTANT:
-        return launch_spread_t<NDIM, IBK_PIECEWISE_CONSTANT>(L, tp, bins, mv, err);
-    case IBK_COMPOSITE_BSPLINE_32:
-        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_32>(L, tp, bins, mv, err);
-    case IBK_COMPOSITE_BSPLINE_23:
-        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_23>(L, tp, bins, mv, err);
-    case IBK_COMPOSITE_BSPLINE_43:
-        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_43>(L, tp, bins, mv, err);
-    case IBK_COMPOSITE_BSPLINE_34:
-        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_34>(L, tp, bins, mv, err);
-    case IBK_COMPOSITE_BSPLINE_54:
-        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_54>(L, tp, bins, mv, err);
-    case IBK_COMPOSITE_BSPLINE_45:
-        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_45>(L, tp, bins, mv, err);
-    case IBK_COMPOSITE_BSPLINE_65:
-        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_65>(L, tp, bins, mv, err);
-    case IBK_COMPOSITE_BSPLINE_56:
-        return launch_spread_t<NDIM, IBK_COMPOSITE_BSPLINE_56>(L, tp, bins, mv, err);
-    case IBK_DISCONTINUOUS_LINEAR:
-        return launch_spread_t<NDIM, IBK_DISCONTINUOUS_LINEAR>(L, tp, bins, mv, err);
-    case IBK_IB_4_W8:
-        return launch_spread_t<NDIM, IBK_IB_4_W8>(L, tp, bins, mv, err);
+#define IBK_CASE(KK) \
+    case KK:         \
+        return launch_spread_t<NDIM, KK>(L, tp, bins, mv, err);
+        IBK_CASE(IBK_PIECEWISE_LINEAR)
+        IBK_CASE(IBK_IB_4)
+        IBK_CASE(IBK_IB_6)
+        IBK_CASE(IBK_BSPLINE_3)
+        IBK_CASE(IBK_BSPLINE_4)
+        IBK_CASE(IBK_IB_3)
+        IBK_CASE(IBK_BSPLINE_5)
+        IBK_CASE(IBK_BSPLINE_6)
+        IBK_CASE(IBK_PIECEWISE_CUBIC)
+        IBK_CASE(IBK_IB_5)
+        IBK_CASE(IBK_PIECEWISE_CONSTANT)
+        IBK_CASE(IBK_COMPOSITE_BSPLINE_32)
+        IBK_CASE(IBK_COMPOSITE_BSPLINE_23)
+        IBK_CASE(IBK_COMPOSITE_BSPLINE_43)
+        IBK_CASE(IBK_COMPOSITE_BSPLINE_34)
+        IBK_CASE(IBK_COMPOSITE_BSPLINE_54)
+        IBK_CASE(IBK_COMPOSITE_BSPLINE_45)
+        IBK_CASE(IBK_COMPOSITE_BSPLINE_65)
+        IBK_CASE(IBK_COMPOSITE_BSPLINE_56)
+        IBK_CASE(IBK_DISCONTINUOUS_LINEAR)
+        IBK_CASE(IBK_IB_4_W8)
+#undef IBK_CASE
     default:
         err = "unknown kernel";
         return cudaErrorInvalidValue;

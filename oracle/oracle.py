@@ -447,6 +447,15 @@ class Baseline:
     def zero_f(self):
         lib().le_oracle_baseline_zero_f(self._h)
 
+    def npatch(self):
+        return int(lib().le_oracle_baseline_npatch(self._h))
+
+    def patch_array(self, which, q, axis):
+        """A copy of worker q's private array (`which` = "u" or "f", component `axis`), flat, x fastest, ghosts included."""
+        fn = lib().le_oracle_baseline_f if which == "f" else lib().le_oracle_baseline_u
+        n = int(lib().le_oracle_baseline_array_size(self._h, int(q), int(axis)))
+        return np.ctypeslib.as_array(fn(self._h, int(q), int(axis)), shape=(n,)).copy()
+
     @staticmethod
     def threads():
         """All cores this process may run on (torchrun's OMP_NUM_THREADS=1 default is overridden)."""
