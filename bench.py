@@ -17,8 +17,9 @@ the fluid solver stays on the CPU.  Inputs (2 x 3.3 GB of grid data per GPU) are
 
 --impl reference times the reference's own CPU path: the oracle's restatement of the Fortran kernels
 driven the way the reference parallelises (one worker per patch with private arrays, redundant
-ghost-region spreading), on all host cores (OpenMP threads; MPI is not in this image), on a bounded
-density-preserving sample (256^3 cells, 2^20 markers per step).
+ghost-region spreading), on all host cores (OpenMP threads; MPI is not in this image), on the GPU arm's N = 1
+workload (512^3 cells, 2^23 markers).  The `cpu_baseline` object of the GPU arm's own line is a bounded
+density-preserving sample of it (256^3 cells, 2^20 markers).
 """
 from __future__ import annotations
 
@@ -144,12 +145,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(steps=max(args.steps, 1), warmup=max(min(args.warmup, 2), 1))
+    # the configuration the GPU arm runs at N = 1 (one 512^3 patch group, 2^23 markers), on all host cores
+    cb = cpu_baseline(steps=max(args.steps, 1), warmup=max(min(args.warmup, 2), 1), n=args.cells, log2_markers=args.log2_markers)
+    cfg = workload_config(1, args)
+    cfg["workload"] = (f"C5 shard on the host: one {args.cells}^3 periodic staggered grid + 2^{args.log2_markers} uniform markers, "
+                       f"IB_4, fp64 -- the N = 1 workload of the GPU arm (the CPU arm does not scale with --gpus)")
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, args),
+        "config": cfg,
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -165,6 +170,102 @@ def workload_config(n_gpus, args):
             "kernel": KERNEL, "cells_per_gpu": [n, n, n], "markers_per_gpu": 1 << args.log2_markers,
             "step": "spreadForce (ghost zero + spread + halo accumulate) + interpolateVelocity (halo fill + interp), markers pre-binned",
             "l2": "inputs larger than L2 (2 x 3.3 GB grid data per GPU vs 126 MB)"}
+
+
+# --------------------------------------------------------------------------------------------------
+# result checks (outside every timed region)
+# --------------------------------------------------------------------------------------------------
+def owned(arr, a, g, n):
+    """The DOFs of component `a` this rank owns: interior cells, and along the axis the faces 0..n-1 (the upper face is the
+    neighbour's / the periodic image of face 0).  arr is [z][y][x] with g ghost layers."""
+    return arr[g:g + n, g:g + n, g:g + n]
+
+
+def invariant_check(hf, hu, hF, hU, g, n, h, world, dist, torch):
+    """Size-independent properties of the benchmark's own result: the spread conserves the total force,
+    sum_owned f_a h^3 = sum_i F_ia, and spread and interpolation are discretely adjoint, <S F, u> h^3 = <F, J u>.
+    hf = S[F] (f was zero), hU = J[u]: the host arrays the e2e step left behind.  Sums are all-reduced over the ranks."""
+    vol = h ** 3
+    parts = []
+    for a in range(3):
+        fa = owned(hf[a].numpy(), a, g, n)
+        parts += [float(fa.sum(dtype=np.float64)) * vol, float(hF.numpy()[:, a].sum(dtype=np.float64)),
+                  float(np.abs(hF.numpy()[:, a]).sum(dtype=np.float64))]
+    sfu = sum(float(np.vdot(owned(hf[a].numpy(), a, g, n), owned(hu[a].numpy(), a, g, n))) for a in range(3)) * vol
+    fju = float(np.vdot(hF.numpy(), hU.numpy()))
+    scale = float(np.abs(hF.numpy() * hU.numpy()).sum(dtype=np.float64))
+    v = np.array(parts + [sfu, fju, scale], dtype=np.float64)
+    if world > 1:
+        t = torch.from_numpy(v).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        v = t.cpu().numpy()
+    force = [abs(v[3 * a] - v[3 * a + 1]) / v[3 * a + 2] for a in range(3)]
+    adj = abs(v[9] - v[10]) / v[11]
+    ok = bool(max(force) <= 1e-10 and adj <= 1e-10)
+    return {"total_force_rel_err": [float(x) for x in force], "adjointness_rel_err": float(adj), "tolerance": 1e-10, "ok": ok,
+            "what": "on the benchmark workload itself, all ranks: sum_owned f_a h^3 vs sum_i F_ia (relative to sum |F_ia|), "
+                    "<S F, u> h^3 vs <F, J u> (relative to sum |F.U|)"}
+
+
+def sample_parity(ctx_device, n=256, log2_markers=20):
+    """The CPU arm's sample (n^3 periodic grid, 2^log2_markers uniform markers, IB_4) through the GPU path, compared value by
+    value with the oracle's model of the reference (its patch-private arrays, redundant ghost-region spreading)."""
+    from ibamr_b200 import api
+    from oracle import oracle as orc
+    threads = orc.Baseline.threads()
+    t = 1
+    while t * 2 <= min(threads, 8):
+        t *= 2
+    npatch = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[t]
+    N = 1 << log2_markers
+    X = np.stack([splitmix_unit(7 + d, np.arange(N)) for d in range(3)], axis=1).copy()
+    F = np.stack([2.0 * splitmix_unit(1 + d, np.arange(N)) - 1.0 for d in range(3)], axis=1).copy()
+    U_ref = np.zeros((N, 3))
+    g = 3
+    b = orc.Baseline(3, (n, n, n), npatch, g, (0.0,) * 3, (1.0,) * 3, X, field_seed=0)
+    b.zero_f()
+    b.step(KERNEL, F, U_ref)
+    # global interior arrays from the workers' patches
+    w = [n // npatch[d] for d in range(3)]
+    u_glob = [np.zeros(tuple(n + (1 if (2 - k) == a else 0) for k in range(3))) for a in range(3)]  # [z][y][x]
+    f_glob = [np.zeros_like(u_glob[a]) for a in range(3)]
+    q = 0
+    for pz in range(npatch[2]):
+        for py in range(npatch[1]):
+            for px in range(npatch[0]):
+                lo = (px * w[0], py * w[1], pz * w[2])
+                for a in range(3):
+                    shp = tuple(w[2 - k] + 2 * g + (1 if (2 - k) == a else 0) for k in range(3))
+                    sl = tuple(slice(g, shp[k] - g) for k in range(3))
+                    dst = tuple(slice(lo[2 - k], lo[2 - k] + w[2 - k] + (1 if (2 - k) == a else 0)) for k in range(3))
+                    u_glob[a][dst] = b.patch_array("u", q, a).reshape(shp)[sl]
+                    f_glob[a][dst] = b.patch_array("f", q, a).reshape(shp)[sl]
+                q += 1
+    b.close()
+    ib = api.IBMethodB200(3, (0, 0, 0), (n - 1,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), [((0, 0, 0), (n - 1,) * 3)],
+                          kernel_fcn=KERNEL, ctx=api.Context(ctx_device))
+    gg = ib.gcw[0]
+    for a in range(3):
+        arr = np.zeros(ib.side_shape(0, a))
+        arr[tuple(slice(gg, s - gg) for s in arr.shape)] = u_glob[a]
+        ib.grid_upload("u", 0, a, arr)
+    ib.setPositions(X)
+    ib.setLData("F", F)
+    ib.beginDataRedistribution()
+    ib.grid_fill("f", 0.0)
+    ib.spreadForce(accumulate_halo=True)
+    ib.interpolateVelocity(fill_halo=True)
+    U = ib.getLData("U")
+    err_f = 0.0
+    for a in range(3):
+        fa = ib.grid_download("f", 0, a)
+        fa = fa[tuple(slice(gg, s - gg) for s in fa.shape)]
+        err_f = max(err_f, float(np.max(np.abs(fa - f_glob[a])) / np.max(np.abs(f_glob[a]))))
+    err_u = float(np.max(np.abs(U - U_ref)) / np.max(np.abs(U_ref)))
+    ib.close()
+    return {"max_rel_err_U": err_u, "max_rel_err_f": err_f, "tolerance": 1e-12, "ok": bool(err_u <= 1e-12 and err_f <= 1e-12),
+            "what": f"{n}^3 periodic grid, 2^{log2_markers} uniform markers, IB_4: GPU path (one resident patch, halo fill / "
+                    f"accumulate) vs the oracle's reference model ({npatch[0]}x{npatch[1]}x{npatch[2]} patches), max-norm relative"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -408,6 +509,8 @@ def run_gpu(args):
     grid_bytes = sum(int(np.prod(ib.side_shape(0, a))) for a in range(3)) * 8
     h2d = 2 * N * 3 * 8 + grid_bytes
     d2h = N * 3 * 8 + grid_bytes
+    # ---- checks on the result of the last e2e step (hf = S[F] into a zeroed f, hU = J[u]); every rank takes part
+    check = invariant_check(hf, hu, hF, hU, g, n, h, world, dist, torch)
 
     # ---- reduce over ranks (max time)
     if world > 1:
@@ -459,10 +562,16 @@ def run_gpu(args):
             "phases_ms": {"spread_kernels": sp_ms, "interp_kernels": in_ms, "halo_and_gaps": ms_per_step - sp_ms - in_ms, "step": ms_per_step,
                           "rebin": rebin_ms},
         }
+        line["check"] = check
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline()
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if world == 1 and not args.no_sample_parity:
+            line["check"]["sample_vs_oracle"] = sample_parity(local_rank)
+            line["check"]["ok"] = bool(line["check"]["ok"] and line["check"]["sample_vs_oracle"]["ok"])
         print(json.dumps(line), flush=True)
+        if not line["check"]["ok"]:
+            raise SystemExit("bench.py: result check FAILED: " + json.dumps(line["check"]))
     ib.close()
     if world > 1:
         dist.barrier()
@@ -482,6 +591,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-breakdown", action="store_true", help="print the e2e phases, each synchronised, to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sample-parity", action="store_true", help="skip the 256^3 value-by-value comparison with the oracle (N = 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

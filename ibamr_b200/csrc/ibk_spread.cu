@@ -104,9 +104,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 // =============================================================================================
 // 3D march kernel
 // =============================================================================================
+// a plane of zeros: the flusher refills flushed planes from it by bulk copies instead of storing zeros itself
+__device__ __align__(128) double g_march_zeros[2048];
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 constexpr int MARCH_CELLS = 2 * TILE;          // column edge: 2 x 2 marker tiles
 constexpr int MARCH_BR = MARCH_CELLS / BRICK;  // 8 bricks per row / rows per layer
-constexpr int MARCH_WARPS = 16;                 // 4 per SM sub-partition: 128 registers per thread
 constexpr int MARCH_MAX_LAYERS = 32;
 
 template <int K>
@@ -121,17 +128,64 @@ struct MarchCfg
     static constexpr int FZ = BRICK + 2 * M;      // planes a brick layer reaches
     static constexpr int NRING = FZ + BRICK;      // + the four planes being flushed
     static constexpr int NC = (BRICK + 2 * M + BRICK - 1) / BRICK; // brick colours per dimension
-    static constexpr int NCW = (MARCH_BR + NC - 1) / NC;           // consumer warps = rows per row colour = chains per warp
-    static constexpr int NPW = MARCH_WARPS - NCW - 1;                // producer warps
-    static constexpr int NT = 32 * MARCH_WARPS;
+    static constexpr int NCW = (MARCH_BR + NC - 1) / NC;           // rows per row colour = chains per row and sub-phase
+    static constexpr bool FAST4 = (W == 4); // 64 points = 2 slots of 32 lanes with the same (x, y) per lane
+    // FAST4: a row is shared by a PAIR of consumer warps (two of the four chains each): 8 consumer warps, two per SM
+    // sub-partition, so one warp's shared-memory latency is covered by the other's issue slots
+    static constexpr int WPR = FAST4 ? 2 : 1;                      // consumer warps per row
+    static constexpr int NCONS = NCW * WPR;                        // consumer warps
+    static constexpr int CPW = NCW / WPR;                          // chains per consumer warp
+    static constexpr int WARPS = FAST4 ? 20 : 16;                  // 5 / 4 warps per SM sub-partition: 96 / 128 registers
+    static constexpr int NPW = WARPS - NCONS - 1;                  // producer warps
+    static constexpr int NT = 32 * WARPS;
     static constexpr int NPTS = W * W * W;
     static constexpr int NSLOT = (NPTS + 31) / 32;
     // per-marker record: W byte offsets (one per z plane of the stencil; negative: skip), then 3 x W weights
     static constexpr int ZO_BYTES = ((W * 4 + 15) / 16) * 16;
-    static constexpr int REC = ((ZO_BYTES + 3 * W * 8 + 15) / 16) * 16;
-    static constexpr bool FAST4 = (W == 4); // 64 points = 2 slots of 32 lanes with the same (x, y) per lane
+    // FAST4 (W = 4): 128 bytes.  Lane group g (= lane / 16, stencil planes g and g + 2) reads one 32-byte block at 32 g:
+    // {int offset(g), int offset(g + 2), 8 spare bytes, double wz(g), double wz(g + 2)}; wx[4] at 64, wy[4] at 96.
+    // (+ 16 spare bytes: with a stride of 128 the producers' stores of 32 records would all hit the same banks)
+    static constexpr int REC = (W == 4) ? 144 : ((ZO_BYTES + 3 * W * 8 + 15) / 16) * 16;
     static constexpr int SINK_B = ((8 * (3 * RX + 4) + 127) / 128) * 128; // where the lanes of a dummy record add their zeros
 };
+
+// FAST4 consumer body: iterations [k, kend) of N chains side by side.  adr[c]: this lane's 32-byte block of chain c's
+// current record; ring_lane: the ring plus the lane's (x, y) offset.  All record loads, then all ring loads, then all
+// ring stores: the N read-modify-writes are independent (bricks NC apart) and overlap.
+template <int N, int REC>
+__device__ __forceinline__ void march_chains(uint32_t (&adr)[2], int& k, int kend, uint32_t ring_lane, int lane_wx, int lane_wy)
+{
+    for (; k < kend; ++k)
+    {
+        int2 zo[N];
+        double wx[N], wy[N];
+        double2 wz[N];
+        double a0[N], a1[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c)
+        {
+            zo[c] = lds_v2s32(adr[c]);
+            wz[c] = lds_v2f64(adr[c] + 16);
+            wx[c] = lds_f64(adr[c] + lane_wx);
+            wy[c] = lds_f64(adr[c] + lane_wy);
+            adr[c] += REC;
+        }
+#pragma unroll
+        for (int c = 0; c < N; ++c)
+        {
+            a0[c] = lds_f64(ring_lane + zo[c].x);
+            a1[c] = lds_f64(ring_lane + zo[c].y);
+        }
+#pragma unroll
+        for (int c = 0; c < N; ++c)
+        {
+            const double wxy = wx[c] * wy[c];
+            sts_f64(ring_lane + zo[c].x, fma(wxy, wz[c].x, a0[c]));
+            sts_f64(ring_lane + zo[c].y, fma(wxy, wz[c].y, a1[c]));
+        }
+        __syncwarp();
+    }
+}
 
 template <int K>
 __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
@@ -142,6 +196,7 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
     constexpr int NC = C::NC, NCW = C::NCW, REC = C::REC, ZO_BYTES = C::ZO_BYTES;
     constexpr int NPROD = 32 * C::NPW;
     constexpr int PLANE_B = PLANE * 8;
+    static_assert(PLANE <= 2048, "g_march_zeros holds one plane");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* const ringb = smem_raw;                                  // [NRING][R][RX] doubles
@@ -156,10 +211,12 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
     __shared__ int s_desc[2][8];                      // step: layer, window offset, markers in the window, pre/first buffer, first window?, end?
     __shared__ int s_tot[MARCH_MAX_LAYERS + 1];       // markers per layer (decides which planes are flushed)
     __shared__ int s_any;
+    __shared__ __align__(8) uint64_t s_zbar; // completion of the zero refills of the flusher
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int role = warp < NCW ? 0 : (warp == NCW ? 1 : 2); // consumer / flusher / producer
-    const int ptid = tid - 32 * (NCW + 1);                   // producer thread index
+    constexpr int NCONS = C::NCONS, CPW = C::CPW;
+    const int role = warp < NCONS ? 0 : (warp == NCONS ? 1 : 2); // consumer / flusher / producer
+    const int ptid = tid - 32 * (NCONS + 1);                     // producer thread index
 
     // ---- which column, chunk and component
     int col[3];
@@ -190,7 +247,12 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
         return tp.brick_base + ((tz * tp.nt[1] + ty) * tp.nt[0] + tx) * 64;
     };
     // anything to spread in this chunk?
-    if (tid == 0) s_any = 0;
+    if (tid == 0)
+    {
+        s_any = 0;
+        mbar_init(&s_zbar, 1);
+        mbar_fence_init();
+    }
     __syncthreads();
     if (tid < 4 * ntz)
     {
@@ -223,11 +285,11 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
     {
         double2* r2 = reinterpret_cast<double2*>(ringb);
         for (int q = tid; q < (NRING * PLANE_B + SINK_B) / 16; q += C::NT) r2[q] = make_double2(0.0, 0.0);
-        if (tid < 2 * (REC / 4)) // the dummy records: offsets = the sink, weights = 0
+        if (C::FAST4 && tid < 2 * (REC / 4)) // the dummy records: offsets = the sink, weights = 0
         {
             int* dr = reinterpret_cast<int*>(recb + ((size_t)(tid / (REC / 4)) * cap1 + args.cap) * REC);
             const int wd = tid % (REC / 4);
-            dr[wd] = (wd < W) ? SINK_OFF : 0;
+            dr[wd] = (wd == 0 || wd == 1 || wd == 8 || wd == 9) ? SINK_OFF : 0;
         }
         fence_proxy_async_smem();
     }
@@ -237,7 +299,7 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
     // =========================================================================================
     int p_layer = -1, p_off = 0, p_total = 0, p_lb = 1; // (uniform over the producer threads)
     int n_s = 0, n_m = 0, n_e = 0;                      // prefetched segment offsets of the lane's two bricks (next layer)
-    bool n_ok = false;
+    bool n_ok = false, prefetch_pending = false;
     // lane l of producer warp 0 holds bricks p = 2 l, 2 l + 1 (same row, same tile, consecutive ids)
     auto counts_fetch = [&](int layer) {
         n_ok = false;
@@ -296,6 +358,7 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
             {
                 counts_publish(p_lb);
                 counts_fetch(p_layer + 1);
+                prefetch_pending = true;
                 named_bar_sync(2, NPROD);
                 p_total = s_pre[p_lb][MARCH_BR * MARCH_BR];
             }
@@ -335,7 +398,7 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
             const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
             const double fv = __ldg(&args.V[cg.vcol * args.v_cstride + row * args.v_istride]) * tp.inv_vol;
             unsigned char* const r = rb + (size_t)slot * REC;
-            double* const wr = reinterpret_cast<double*>(r + ZO_BYTES);
+            double* const wr = reinterpret_cast<double*>(r + (C::FAST4 ? 64 : ZO_BYTES));
             int r0[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d)
@@ -344,20 +407,15 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
                 int l;
                 stencil_1d<K>(xs[d], xr[d], tp.xl[d][cg.var[d]], tp.dx[d], l, w, d == cg.axis);
                 r0[d] = l + tp.G - (d == 0 ? bx0 : d == 1 ? by0 : zq0);
-                if (d == 2)
-                {
 #pragma unroll
-                    for (int j = 0; j < W; ++j)
-                    {
-                        // FAST4: the z weights in the order (0, 2, 1, 3): lane group g reads the pair (g, g + 2) at once
-                        const int jj = C::FAST4 ? ((j & 1) * 2 + (j >> 1)) : j;
-                        wr[2 * W + jj] = w[j] * fv;
-                    }
-                }
-                else
+                for (int j = 0; j < W; ++j)
                 {
-#pragma unroll
-                    for (int j = 0; j < W; ++j) wr[d * W + j] = w[j];
+                    if (d < 2)
+                        wr[d * W + j] = w[j];
+                    else if (C::FAST4)
+                        *reinterpret_cast<double*>(r + 32 * (j & 1) + 16 + 8 * (j >> 1)) = w[j] * fv;
+                    else
+                        wr[2 * W + j] = w[j] * fv;
                 }
             }
             // the stencil must stay inside the footprint of the marker's BRICK (what the chains and row colours rely on) and
@@ -365,16 +423,31 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
             const int fx = MARCH_CELLS * col[0] + BRICK * (p & 7) - M - bx0, fy = MARCH_CELLS * col[1] + BRICK * (p >> 3) - M - by0;
             const bool fits = r0[0] >= max(fx, 0) && r0[0] + W <= min(fx + FZ, RX) && r0[1] >= max(fy, 0) && r0[1] + W <= min(fy + FZ, R) &&
                               r0[2] >= zlo && r0[2] + W <= zlo + FZ;
-            int* const zo = reinterpret_cast<int*>(r);
             const int xy = 8 * (r0[1] * RX + r0[0]);
 #pragma unroll
             for (int j = 0; j < W; ++j)
             {
-                const int jj = C::FAST4 ? ((j & 1) * 2 + (j >> 1)) : j;
-                zo[jj] = fits ? ((r0[2] + j) % NRING) * PLANE_B + xy : (C::FAST4 ? SINK_OFF : -1);
+                // a stencil that does not fit: FAST4 adds it to the sink (branch-free consumer), else it is skipped
+                const int o = fits ? ((r0[2] + j) % NRING) * PLANE_B + xy : (C::FAST4 ? SINK_OFF : -1);
+                if (C::FAST4)
+                    *reinterpret_cast<int*>(r + 32 * (j & 1) + 4 * (j >> 1)) = o;
+                else
+                    reinterpret_cast<int*>(r)[j] = o;
             }
             if (!fits) flag_exception(args, i, a);
         }
+        // the marker data of the NEXT layer (its segment offsets have arrived by now) on its way into L2
+        if (prefetch_pending && ptid < 32 && n_ok && n_e > n_s)
+        {
+            const long long vrow = cg.vcol * args.v_cstride;
+            for (int i = n_s & ~15; i < n_e; i += 16) // 128-byte lines
+            {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(&args.X[d * args.x_stride + i]));
+                if (!args.src) asm volatile("prefetch.global.L2 [%0];" ::"l"(&args.V[vrow + (long long)i * args.v_istride]));
+            }
+        }
+        prefetch_pending = false;
     };
 
     // =========================================================================================
@@ -397,22 +470,25 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
             lwz[s] = ZO_BYTES + 8 * (2 * W + iz);
         }
         const int g4 = lane >> 4; // FAST4: z pair (g4, g4 + 2)
-        const uint32_t rec_s = smem_u32(rb), rec_dummy = rec_s + (uint32_t)args.cap * REC;
+        const uint32_t rec_s = smem_u32(rb);
         const uint32_t ring_lane = smem_u32(ringb) + (uint32_t)lxy[0];
+        // FAST4: this lane's wx / wy relative to its 32-byte block of the record
+        const int lane_wx = 64 + 8 * (lane & 3) - 32 * g4, lane_wy = 96 + 8 * ((lane >> 2) & 3) - 32 * g4;
+        const int rslot = warp / C::WPR, half = warp % C::WPR; // which row of the colour, which half of its chains
         for (int ph = 0; ph < NC; ++ph)
         {
-            const int row = ph + NC * warp;
+            const int row = ph + NC * rslot;
             if (row < MARCH_BR)
             {
 #pragma unroll 1
                 for (int sp = 0; sp < NC; ++sp)
                 {
-                    int cur[NCW], end[NCW];
+                    int cur[CPW], end[CPW];
                     int longest = 0;
 #pragma unroll
-                    for (int c = 0; c < NCW; ++c)
+                    for (int c = 0; c < CPW; ++c)
                     {
-                        const int i = sp + NC * c;
+                        const int i = sp + NC * (CPW * half + c);
                         cur[c] = end[c] = 0;
                         if (i < MARCH_BR)
                         {
@@ -422,42 +498,41 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
                             longest = max(longest, end[c] - cur[c]);
                         }
                     }
-                    for (int k = 0; k < longest; ++k)
+                    if constexpr (C::FAST4)
                     {
-                        if constexpr (C::FAST4)
+                        // two chains side by side while both last, then the longer one alone: nothing idles and nothing
+                        // branches inside a body.  (The order of the additions at a grid point is the order inside its
+                        // brick's chain: same-sub-phase bricks are disjoint.)
+                        static_assert(CPW == 2, "two chains per consumer warp");
+                        uint32_t adr[2];
+                        int len[2];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
                         {
-                            // branch-free: a chain that has run out reads the dummy record and adds zeros to the sink
-                            int2 zo[NCW];
-                            double wx[NCW], wy[NCW];
-                            double2 wz[NCW];
-                            double a0[NCW], a1[NCW];
-#pragma unroll
-                            for (int c = 0; c < NCW; ++c)
-                            {
-                                const uint32_t r = (cur[c] + k < end[c]) ? rec_s + (uint32_t)(cur[c] + k) * REC : rec_dummy;
-                                zo[c] = lds_v2s32(r + 8 * g4);
-                                wx[c] = lds_f64(r + lwx[0]);
-                                wy[c] = lds_f64(r + lwy[0]);
-                                wz[c] = lds_v2f64(r + ZO_BYTES + 8 * 2 * W + 16 * g4);
-                            }
-#pragma unroll
-                            for (int c = 0; c < NCW; ++c)
-                            {
-                                a0[c] = lds_f64(ring_lane + zo[c].x);
-                                a1[c] = lds_f64(ring_lane + zo[c].y);
-                            }
-#pragma unroll
-                            for (int c = 0; c < NCW; ++c)
-                            {
-                                const double wxy = wx[c] * wy[c];
-                                sts_f64(ring_lane + zo[c].x, fma(wxy, wz[c].x, a0[c]));
-                                sts_f64(ring_lane + zo[c].y, fma(wxy, wz[c].y, a1[c]));
-                            }
+                            adr[c] = rec_s + (uint32_t)cur[c] * REC + 32 * g4;
+                            len[c] = max(end[c] - cur[c], 0);
                         }
-                        else
+                        if (len[0] < len[1])
+                        {
+                            const int tl = len[0];
+                            len[0] = len[1];
+                            len[1] = tl;
+                            const uint32_t ta = adr[0];
+                            adr[0] = adr[1];
+                            adr[1] = ta;
+                        }
+                        int k = 0;
+                        march_chains<2, C::REC>(adr, k, len[1], ring_lane, lane_wx, lane_wy);
+                        march_chains<1, C::REC>(adr, k, len[0], ring_lane, lane_wx, lane_wy);
+                        // the next sub-phase of this row touches the neighbouring bricks: wait for the other half of the row
+                        if (sp + 1 < NC) named_bar_sync(4 + rslot, 32 * C::WPR);
+                    }
+                    if constexpr (!C::FAST4)
+                    {
+                        for (int k = 0; k < longest; ++k)
                         {
 #pragma unroll
-                            for (int c = 0; c < NCW; ++c)
+                            for (int c = 0; c < CPW; ++c)
                             {
                                 if (cur[c] + k >= end[c]) continue;
                                 const unsigned char* r = rb + (size_t)(cur[c] + k) * REC;
@@ -478,12 +553,16 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
                                 for (int s = 0; s < C::NSLOT; ++s)
                                     if (C::NPTS % 32 == 0 || lane + 32 * s < C::NPTS) *reinterpret_cast<double*>(ringb + ad[s]) = av[s] + wv[s];
                             }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
                 }
             }
-            if (ph + 1 < NC) named_bar_sync(1, 32 * NCW);
+            else if constexpr (C::FAST4)
+            {
+                // (a row slot without a row in this colour: FAST4 has 8 rows in 2 colours of 4, so this does not happen)
+            }
+            if (ph + 1 < NC) named_bar_sync(1, 32 * NCONS);
         }
         fence_proxy_async_smem(); // this thread's writes to the ring -> visible to the TMA stores of the flusher
     };
@@ -491,20 +570,18 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
     // =========================================================================================
     // flusher: planes [qlo, qhi) are final: f += plane (TMA reducing store), then zero them for reuse
     // =========================================================================================
-    auto plane_dirty = [&](int q) -> bool {
-        // touched by the layers s with 4 s <= q < 4 s + FZ
-        bool dirty = false;
-        for (int s = max(0, (q - FZ + BRICK) / BRICK); s <= min(q / BRICK, NL - 1); ++s)
-            if (BRICK * s <= q && q < BRICK * s + FZ && s_tot[s] > 0) dirty = true;
-        return dirty;
-    };
+    uint32_t zphase = 0;
     auto flush = [&](int qlo, int qhi) {
         const int x0 = bx0 - cg.pp0[0], y0 = by0 - cg.pp0[1];
-        bool any = false;
+        // which of the planes were touched: plane q by the layers s with 4 s <= q < 4 s + FZ that held markers
+        unsigned dirty = 0;
+        for (int s = max(0, (qlo - FZ + BRICK) / BRICK); s <= min((qhi - 1) / BRICK, NL - 1); ++s)
+            if (s_tot[s] > 0)
+                for (int q = max(qlo, BRICK * s); q < min(qhi, BRICK * s + FZ); ++q) dirty |= 1u << (q - qlo);
+        if (!dirty) return;
         for (int q = qlo; q < qhi; ++q)
         {
-            if (!plane_dirty(q)) continue;
-            any = true;
+            if (!((dirty >> (q - qlo)) & 1u)) continue;
             const int gz = zq0 + q - cg.pp0[2];
             if (gz < 0 || gz >= cg.n[2]) continue;
             const double* pl = reinterpret_cast<const double*>(ringb + (size_t)(q % NRING) * PLANE_B);
@@ -530,12 +607,25 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
                 }
             }
         }
-        if (!any) return;
-        if (use_tma && lane == 0) tma_store_commit_and_wait_read(); // the planes have been read
+        if (use_tma)
+        {
+            // zeros for the next use of the slots, by bulk copies from a plane of zeros (L2-resident) once the stores have
+            // read the planes; the TMA unit does the work, this warp only waits
+            if (lane == 0)
+            {
+                tma_store_commit_and_wait_read();
+                mbar_expect_tx(&s_zbar, (uint32_t)(__popc(dirty) * PLANE_B));
+                for (int q = qlo; q < qhi; ++q)
+                    if ((dirty >> (q - qlo)) & 1u) bulk_copy_g2s(ringb + (size_t)(q % NRING) * PLANE_B, g_march_zeros, PLANE_B, &s_zbar);
+            }
+            mbar_wait(&s_zbar, zphase);
+            zphase ^= 1u;
+            return;
+        }
         __syncwarp();
         for (int q = qlo; q < qhi; ++q)
         {
-            if (!plane_dirty(q)) continue;
+            if (!((dirty >> (q - qlo)) & 1u)) continue;
             double2* pl = reinterpret_cast<double2*>(ringb + (size_t)(q % NRING) * PLANE_B);
             for (int e = lane; e < PLANE / 2; e += 32) pl[e] = make_double2(0.0, 0.0);
         }
