@@ -245,6 +245,10 @@ cudaError_t bins_reserve(Bins& b, int n_entries, int total_bricks)
         if (b.brick_start) cudaFree(b.brick_start);
         if ((e = cudaMalloc(&b.brick_start, sizeof(int) * (size_t)(total_bricks + 1))) != cudaSuccess) return e;
         b.brick_capacity = total_bricks + 1;
+        // a march tile holds at least one marker tile (16 bricks in 2D, 64 in 3D)
+        if (b.march_sync) cudaFree(b.march_sync);
+        b.march_sync_capacity = ((size_t)total_bricks / 16 + 8) * IBK_MAX_COMP + 1;
+        if ((e = cudaMalloc(&b.march_sync, sizeof(int) * b.march_sync_capacity)) != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
@@ -262,6 +266,7 @@ void bins_free(Bins& b)
     if (b.brick_start) cudaFree(b.brick_start);
     if (b.dense_list) cudaFree(b.dense_list);
     if (b.dense_count) cudaFree(b.dense_count);
+    if (b.march_sync) cudaFree(b.march_sync);
     if (b.exc_flags) cudaFree(b.exc_flags);
     if (b.exc_count) cudaFree(b.exc_count);
     b = Bins();

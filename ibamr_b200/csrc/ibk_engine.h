@@ -70,6 +70,9 @@ struct Bins
     // spread exceptions: (entry, component) pairs whose stencil does not fit the accumulator of their tile are flagged here by
     // the tile kernels and spread by spread_fixup_kernel.  One byte per sorted position (bit a = component a), held as 32-bit
     // words: the list cannot overflow.  All zero between spreads (the fix-up clears what it consumes).
+    // 3D march spread: [0] the ticket counter of its persistent CTAs, [1 ...] one done flag per (march tile, component)
+    int* march_sync = nullptr;
+    size_t march_sync_capacity = 0;
     unsigned* exc_flags = nullptr; // [capacity / 4 + 1]
     int* exc_count = nullptr;      // number of flagged pairs (an upper bound: a pair may be flagged twice)
 };

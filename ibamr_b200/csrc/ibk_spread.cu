@@ -60,6 +60,12 @@ struct SpreadArgs
     int clip_free;                  // MarkerView::clip_free
     int dense_thresh;               // > 0: bricks with more markers than this are left to spread_dense_kernel
     int chunk_tiles;                // march kernel: marker tiles per chunk in z
+    int debug_skip;                 // (IBK_MARCH_SKIP, timing experiments only: wrong results) 1 flusher, 2 consumers, 4 producers' records
+    // march kernel, persistent CTAs: work items = (march tile, component) in colour-major order, taken by ticket
+    int nm[3];          // march tiles per dimension
+    int item_base[9];   // first item of each tile colour (colour = x parity + 2 y parity + 4 z parity)
+    int* work_counter;  // next ticket
+    int* done_flags;    // [march tile][component]: the item has been added to f completely
 };
 
 __device__ __forceinline__ void flag_exception(const SpreadArgs& args, int i, int a)
@@ -155,12 +161,38 @@ struct MarchCfg
 template <int N, int REC>
 __device__ __forceinline__ void march_chains(uint32_t (&adr)[2], int& k, int kend, uint32_t ring_lane, int lane_wx, int lane_wy)
 {
+    if (k >= kend) return;
+    // software pipeline: the record of iteration k + 1 is loaded while the ring words of iteration k are read, updated
+    // and written, so only the ring's load -> fma -> store chain separates two markers of a brick.  (The load after the
+    // last record of a chain reads the next record or the dummy behind the buffer: unused.)
+    int2 zo[N];
+    double wx[N], wy[N];
+    double2 wz[N];
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+    {
+        zo[c] = lds_v2s32(adr[c]);
+        wz[c] = lds_v2f64(adr[c] + 16);
+        wx[c] = lds_f64(adr[c] + lane_wx);
+        wy[c] = lds_f64(adr[c] + lane_wy);
+        adr[c] += REC;
+    }
     for (; k < kend; ++k)
     {
-        int2 zo[N];
-        double wx[N], wy[N];
-        double2 wz[N];
         double a0[N], a1[N];
+        uint32_t p0[N], p1[N];
+        double wa[N], wb[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c)
+        {
+            p0[c] = ring_lane + zo[c].x;
+            p1[c] = ring_lane + zo[c].y;
+            a0[c] = lds_f64(p0[c]);
+            a1[c] = lds_f64(p1[c]);
+            const double wxy = wx[c] * wy[c];
+            wa[c] = wxy * wz[c].x;
+            wb[c] = wxy * wz[c].y;
+        }
 #pragma unroll
         for (int c = 0; c < N; ++c)
         {
@@ -173,18 +205,13 @@ __device__ __forceinline__ void march_chains(uint32_t (&adr)[2], int& k, int ken
 #pragma unroll
         for (int c = 0; c < N; ++c)
         {
-            a0[c] = lds_f64(ring_lane + zo[c].x);
-            a1[c] = lds_f64(ring_lane + zo[c].y);
-        }
-#pragma unroll
-        for (int c = 0; c < N; ++c)
-        {
-            const double wxy = wx[c] * wy[c];
-            sts_f64(ring_lane + zo[c].x, fma(wxy, wz[c].x, a0[c]));
-            sts_f64(ring_lane + zo[c].y, fma(wxy, wz[c].y, a1[c]));
+            sts_f64(p0[c], a0[c] + wa[c]);
+            sts_f64(p1[c], a1[c] + wb[c]);
         }
         __syncwarp();
     }
+#pragma unroll
+    for (int c = 0; c < N; ++c) adr[c] -= REC; // the record loaded ahead was not consumed
 }
 
 template <int K>
@@ -218,20 +245,13 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
     const int role = warp < NCONS ? 0 : (warp == NCONS ? 1 : 2); // consumer / flusher / producer
     const int ptid = tid - 32 * (NCONS + 1);                     // producer thread index
 
-    // ---- which column, chunk and component
-    int col[3];
-    {
-        int r = (int)blockIdx.x;
-        col[0] = 2 * (r % args.ntc[0]) + args.colour[0];
-        r /= args.ntc[0];
-        col[1] = 2 * (r % args.ntc[1]) + args.colour[1];
-        col[2] = 2 * (r / args.ntc[1]) + args.colour[2];
-    }
-    const int a = blockIdx.y;
-    const CompGeom& cg = tp.comp[a];
-    const int tz0 = col[2] * args.chunk_tiles;
-    const int ntz = min(args.chunk_tiles, tp.nt[2] - tz0);
-    const int NL = ntz * TILE_BRICKS; // brick layers of this chunk
+    // ---- the work item in hand (set by the item loop below; the lambdas read it)
+    int col[3] = { 0, 0, 0 }; // march tile
+    int a = 0;                // component
+    int tz0 = 0, NL = 0;      // first marker tile in z, brick layers of the chunk
+    int bx0 = 0, by0 = 0, zq0 = 0; // smem column 0 / row 0 / plane 0 of the accumulator in pp coordinates
+    bool use_tma = false;
+    __shared__ int s_item;
 
     // tile selection (halo overlap): is tile (txi, tyi, tz) of this column part of this launch?
     auto tile_on = [&](int txi, int tyi, int tz) -> bool {
@@ -246,41 +266,11 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
         const int tx = 2 * col[0] + txi, ty = 2 * col[1] + tyi;
         return tp.brick_base + ((tz * tp.nt[1] + ty) * tp.nt[0] + tx) * 64;
     };
-    // anything to spread in this chunk?
     if (tid == 0)
     {
-        s_any = 0;
         mbar_init(&s_zbar, 1);
         mbar_fence_init();
     }
-    __syncthreads();
-    if (tid < 4 * ntz)
-    {
-        const int tz = tz0 + tid / 4, txi = tid & 1, tyi = (tid >> 1) & 1;
-        if (tile_on(txi, tyi, tz))
-        {
-            const int b0 = tile_b0(txi, tyi, tz);
-            if (__ldg(&args.brick_start[b0 + 64]) > __ldg(&args.brick_start[b0])) s_any = 1;
-        }
-    }
-    __syncthreads();
-    if (!s_any) return;
-
-    // ---- geometry of the accumulator: smem column 0 / row 0 / plane 0 in pp coordinates
-    int bx0 = MARCH_CELLS * col[0] - M - XO, by0 = MARCH_CELLS * col[1] - M;
-    const int zq0 = TILE * tz0 - M;
-    bool use_tma = (args.tma_mask >> a) & 1u;
-    if (bx0 < cg.pp0[0])
-    {
-        if (args.clip_free) bx0 = cg.pp0[0]; // nothing reaches the points before the array: start the block at its first element
-        else use_tma = false;                // a TMA store with a negative start coordinate traps (measured)
-    }
-    if (by0 < cg.pp0[1])
-    {
-        if (args.clip_free) by0 = cg.pp0[1];
-        else use_tma = false;
-    }
-
     // ---- zero the ring
     {
         double2* r2 = reinterpret_cast<double2*>(ringb);
@@ -376,7 +366,7 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
             s_desc[nb][5] = p_layer >= NL ? 1 : 0;
             if (first_win && p_layer <= MARCH_MAX_LAYERS) s_tot[p_layer] = p_total;
         }
-        if (p_layer >= NL) return;
+        if (p_layer >= NL || (args.debug_skip & 4)) return;
         unsigned char* const rb = recb + (size_t)nb * cap1 * REC;
         const int* pre = s_pre[p_lb];
         const int zlo = BRICK * p_layer; // the layer's first plane (relative to plane 0 of the chunk)
@@ -396,7 +386,7 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
                 xr[d] = args.Xraw ? __ldg(&args.Xraw[d * args.x_stride + i]) : xs[d];
             }
             const long long row = args.src ? (long long)__ldg(&args.src[i]) : (long long)i;
-            const double fv = __ldg(&args.V[cg.vcol * args.v_cstride + row * args.v_istride]) * tp.inv_vol;
+            const double fv = __ldg(&args.V[tp.comp[a].vcol * args.v_cstride + row * args.v_istride]) * tp.inv_vol;
             unsigned char* const r = rb + (size_t)slot * REC;
             double* const wr = reinterpret_cast<double*>(r + (C::FAST4 ? 64 : ZO_BYTES));
             int r0[3];
@@ -405,7 +395,7 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
             {
                 double w[W];
                 int l;
-                stencil_1d<K>(xs[d], xr[d], tp.xl[d][cg.var[d]], tp.dx[d], l, w, d == cg.axis);
+                stencil_1d<K>(xs[d], xr[d], tp.xl[d][tp.comp[a].var[d]], tp.dx[d], l, w, d == tp.comp[a].axis);
                 r0[d] = l + tp.G - (d == 0 ? bx0 : d == 1 ? by0 : zq0);
 #pragma unroll
                 for (int j = 0; j < W; ++j)
@@ -439,7 +429,7 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
         // the marker data of the NEXT layer (its segment offsets have arrived by now) on its way into L2
         if (prefetch_pending && ptid < 32 && n_ok && n_e > n_s)
         {
-            const long long vrow = cg.vcol * args.v_cstride;
+            const long long vrow = tp.comp[a].vcol * args.v_cstride;
             for (int i = n_s & ~15; i < n_e; i += 16) // 128-byte lines
             {
 #pragma unroll
@@ -572,7 +562,7 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
     // =========================================================================================
     uint32_t zphase = 0;
     auto flush = [&](int qlo, int qhi) {
-        const int x0 = bx0 - cg.pp0[0], y0 = by0 - cg.pp0[1];
+        const int x0 = bx0 - tp.comp[a].pp0[0], y0 = by0 - tp.comp[a].pp0[1];
         // which of the planes were touched: plane q by the layers s with 4 s <= q < 4 s + FZ that held markers
         unsigned dirty = 0;
         for (int s = max(0, (qlo - FZ + BRICK) / BRICK); s <= min((qhi - 1) / BRICK, NL - 1); ++s)
@@ -582,8 +572,8 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
         for (int q = qlo; q < qhi; ++q)
         {
             if (!((dirty >> (q - qlo)) & 1u)) continue;
-            const int gz = zq0 + q - cg.pp0[2];
-            if (gz < 0 || gz >= cg.n[2]) continue;
+            const int gz = zq0 + q - tp.comp[a].pp0[2];
+            if (gz < 0 || gz >= tp.comp[a].n[2]) continue;
             const double* pl = reinterpret_cast<const double*>(ringb + (size_t)(q % NRING) * PLANE_B);
             if (use_tma)
             {
@@ -596,13 +586,13 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
                 for (int y = 0; y < R; ++y)
                 {
                     const int gy = y0 + y;
-                    if (gy < 0 || gy >= cg.n[1]) continue;
-                    double* grow = cg.ptr + ((long long)gz * cg.n[1] + gy) * cg.pitch;
+                    if (gy < 0 || gy >= tp.comp[a].n[1]) continue;
+                    double* grow = tp.comp[a].ptr + ((long long)gz * tp.comp[a].n[1] + gy) * tp.comp[a].pitch;
                     for (int x = lane; x < RX; x += 32)
                     {
                         const int gx = x0 + x;
                         const double v = pl[y * RX + x];
-                        if (gx >= 0 && gx < cg.n[0] && v != 0.0) grow[gx] += v;
+                        if (gx >= 0 && gx < tp.comp[a].n[0] && v != 0.0) grow[gx] += v;
                     }
                 }
             }
@@ -632,35 +622,133 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
         fence_proxy_async_smem();
     };
 
-    // ---- the march
-    if (role == 2)
-    {
-        counts_fetch(0);
-        produce(0);
-    }
+    // ---- one-time set-up is done; the item loop
     __syncthreads();
-    for (int t = 0;; ++t)
+    const int ncomp = tp.ncomp;
+    for (;;)
     {
-        const int b = t & 1;
-        const int layer = s_desc[b][0], off = s_desc[b][1], cnt = s_desc[b][2], lb = s_desc[b][3], first_win = s_desc[b][4],
-                  is_end = s_desc[b][5];
+        if (tid == 0) s_item = atomicAdd(args.work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= args.item_base[8]) break;
+        // decode: colour, then (position, component) with the component fastest (the three components of a tile run side by side
+        // on three SMs and share the marker data in L2)
+        int c = 0;
+        while (item >= args.item_base[c + 1]) ++c;
+        int ntc[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ntc[d] = (args.nm[d] - ((c >> d) & 1) + 1) / 2;
+        {
+            int r = item - args.item_base[c];
+            a = r % ncomp;
+            r /= ncomp;
+            col[0] = 2 * (r % ntc[0]) + (c & 1);
+            r /= ntc[0];
+            col[1] = 2 * (r % ntc[1]) + ((c >> 1) & 1);
+            col[2] = 2 * (r / ntc[1]) + ((c >> 2) & 1);
+        }
+        tz0 = col[2] * args.chunk_tiles;
+        const int ntz = min(args.chunk_tiles, tp.nt[2] - tz0);
+        NL = ntz * TILE_BRICKS;
+        int* const my_flag = args.done_flags + (((long long)col[2] * args.nm[1] + col[1]) * args.nm[0] + col[0]) * ncomp + a;
+        // anything to spread in this chunk?
+        if (tid == 0) s_any = 0;
+        __syncthreads();
+        if (tid < 4 * ntz)
+        {
+            const int tz = tz0 + tid / 4, txi = tid & 1, tyi = (tid >> 1) & 1;
+            if (tile_on(txi, tyi, tz))
+            {
+                const int b0 = tile_b0(txi, tyi, tz);
+                if (__ldg(&args.brick_start[b0 + 64]) > __ldg(&args.brick_start[b0])) s_any = 1;
+            }
+        }
+        __syncthreads();
+        if (!s_any)
+        {
+            if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], 1;" ::"l"(my_flag) : "memory");
+            continue;
+        }
+        // geometry of the accumulator
+        bx0 = MARCH_CELLS * col[0] - M - XO;
+        by0 = MARCH_CELLS * col[1] - M;
+        zq0 = TILE * tz0 - M;
+        use_tma = (args.tma_mask >> a) & 1u;
+        if (bx0 < tp.comp[a].pp0[0])
+        {
+            if (args.clip_free) bx0 = tp.comp[a].pp0[0]; // nothing reaches the points before the array: start the block at its first element
+            else use_tma = false;                        // a TMA store with a negative start coordinate traps (measured)
+        }
+        if (by0 < tp.comp[a].pp0[1])
+        {
+            if (args.clip_free) by0 = tp.comp[a].pp0[1];
+            else use_tma = false;
+        }
+        // The neighbouring march tiles of a LOWER colour overlap this one's halo and must have been added to f completely
+        // before this item adds anything (fixed order of the additions at every grid point).  They hold smaller tickets, so
+        // they are running or done: no deadlock.
+        if (tid < 27 && tid != 13)
+        {
+            const int n0 = col[0] + tid % 3 - 1, n1 = col[1] + (tid / 3) % 3 - 1, n2 = col[2] + tid / 9 - 1;
+            if (n0 >= 0 && n0 < args.nm[0] && n1 >= 0 && n1 < args.nm[1] && n2 >= 0 && n2 < args.nm[2] &&
+                (n0 & 1) + 2 * (n1 & 1) + 4 * (n2 & 1) < c)
+            {
+                const int* fl = args.done_flags + (((long long)n2 * args.nm[1] + n1) * args.nm[0] + n0) * ncomp + a;
+                int v;
+                do
+                {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+                    if (!v) __nanosleep(200);
+                } while (!v);
+            }
+        }
+        // ---- the march
+        p_layer = -1;
+        p_off = 0;
+        p_total = 0;
+        p_lb = 1;
+        prefetch_pending = false;
         if (role == 2)
         {
-            if (!is_end) produce(b ^ 1);
+            counts_fetch(0);
+            produce(0);
         }
-        else if (role == 0)
-        {
-            if (!is_end && cnt > 0) consume(b, lb, off, cnt);
-        }
-        else
-        {
-            if (is_end)
-                flush(BRICK * (NL - 1), BRICK * NL + 2 * M);
-            else if (first_win && layer > 0)
-                flush(BRICK * (layer - 1), BRICK * layer);
-        }
-        if (is_end) break;
         __syncthreads();
+        for (int t = 0;; ++t)
+        {
+            const int b = t & 1;
+            const int layer = s_desc[b][0], off = s_desc[b][1], cnt = s_desc[b][2], lb = s_desc[b][3], first_win = s_desc[b][4],
+                      is_end = s_desc[b][5];
+            if (role == 2)
+            {
+                if (!is_end) produce(b ^ 1);
+            }
+            else if (role == 0)
+            {
+                if (!is_end && cnt > 0 && !(args.debug_skip & 2)) consume(b, lb, off, cnt);
+            }
+            else if (!(args.debug_skip & 1))
+            {
+                if (is_end)
+                    flush(BRICK * (NL - 1), BRICK * NL + 2 * M);
+                else if (first_win && layer > 0)
+                    flush(BRICK * (layer - 1), BRICK * layer);
+            }
+            if (is_end) break;
+            __syncthreads();
+        }
+        // the item is complete when its reducing stores are: then the flag (release) lets the neighbours of higher colours go
+        if (role == 1)
+        {
+            __threadfence(); // (the plain write-out of a block TMA cannot address)
+            __syncwarp();
+            if (lane == 0)
+            {
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                __threadfence();
+                asm volatile("st.release.gpu.global.s32 [%0], 1;" ::"l"(my_flag) : "memory");
+            }
+        }
     }
 }
 
@@ -1350,6 +1438,8 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
         const size_t smem = ring_bytes + C::SINK_B + 2 * (size_t)(args.cap + 1) * C::REC;
         static const int chunk_env = getenv("IBK_SPREAD_CHUNK") ? atoi(getenv("IBK_SPREAD_CHUNK")) : 0;
         args.chunk_tiles = (chunk_env >= 1 && chunk_env <= MARCH_MAX_LAYERS / TILE_BRICKS) ? chunk_env : 4;
+        static const int skip_env = getenv("IBK_MARCH_SKIP") ? atoi(getenv("IBK_MARCH_SKIP")) : 0;
+        args.debug_skip = skip_env;
         auto kfn = spread_march_kernel<K>;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
@@ -1357,21 +1447,34 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
             err = "cudaFuncSetAttribute(spread march) failed";
             return e;
         }
-        int nm[3]; // march tiles per dimension
-        nm[0] = (tp.nt[0] + 1) / 2;
-        nm[1] = (tp.nt[1] + 1) / 2;
-        nm[2] = (tp.nt[2] + args.chunk_tiles - 1) / args.chunk_tiles;
+        // persistent CTAs, one per SM (the ring fills the shared memory), taking (march tile, component) items by ticket in
+        // colour-major order; an item waits for its neighbours of lower colours (done flags), so ONE launch does what took
+        // one launch per colour, without their eight tails
+        for (int d = 0; d < 3; ++d) args.nm[d] = d < 2 ? (tp.nt[d] + 1) / 2 : (tp.nt[2] + args.chunk_tiles - 1) / args.chunk_tiles;
+        args.item_base[0] = 0;
         for (int c = 0; c < 8; ++c)
         {
             int ntiles = 1;
-            for (int d = 0; d < 3; ++d)
+            for (int d = 0; d < 3; ++d) ntiles *= (args.nm[d] - ((c >> d) & 1) + 1) / 2;
+            args.item_base[c + 1] = args.item_base[c] + ntiles * tp.ncomp;
+        }
+        const int n_items = args.item_base[8];
+        const size_t n_flags = (size_t)args.nm[0] * args.nm[1] * args.nm[2] * tp.ncomp;
+        if (n_items > 0)
+        {
+            if (!bins.march_sync || n_flags + 1 > bins.march_sync_capacity)
             {
-                args.colour[d] = (c >> d) & 1;
-                args.ntc[d] = (nm[d] - args.colour[d] + 1) / 2;
-                ntiles *= args.ntc[d];
+                err = "spread march: the bins carry no work counter / done flags of that size";
+                return cudaErrorInvalidValue;
             }
-            if (ntiles <= 0) continue;
-            kfn<<<dim3((unsigned)ntiles, (unsigned)tp.ncomp), C::NT, smem, L.stream>>>(tp, maps, args);
+            args.work_counter = bins.march_sync;
+            args.done_flags = bins.march_sync + 1;
+            if ((e = cudaMemsetAsync(bins.march_sync, 0, sizeof(int) * (n_flags + 1), L.stream)) != cudaSuccess) return e;
+            int dev = 0, sms = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int grid = std::max(1, std::min(n_items, sms > 0 ? sms : 148));
+            kfn<<<grid, C::NT, smem, L.stream>>>(tp, maps, args);
             L.launches++;
         }
     }
