@@ -60,7 +60,6 @@ struct SpreadArgs
     int clip_free;                  // MarkerView::clip_free
     int dense_thresh;               // > 0: bricks with more markers than this are left to spread_dense_kernel
     int chunk_tiles;                // march kernel: marker tiles per chunk in z
-    int debug_skip;                 // (IBK_MARCH_SKIP, timing experiments only: wrong results) 1 flusher, 2 consumers, 4 producers' records
     // march kernel, persistent CTAs: work items = (march tile, component) in colour-major order, taken by ticket
     int nm[3];          // march tiles per dimension
     int item_base[9];   // first item of each tile colour (colour = x parity + 2 y parity + 4 z parity)
@@ -366,7 +365,7 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
             s_desc[nb][5] = p_layer >= NL ? 1 : 0;
             if (first_win && p_layer <= MARCH_MAX_LAYERS) s_tot[p_layer] = p_total;
         }
-        if (p_layer >= NL || (args.debug_skip & 4)) return;
+        if (p_layer >= NL) return;
         unsigned char* const rb = recb + (size_t)nb * cap1 * REC;
         const int* pre = s_pre[p_lb];
         const int zlo = BRICK * p_layer; // the layer's first plane (relative to plane 0 of the chunk)
@@ -725,9 +724,9 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
             }
             else if (role == 0)
             {
-                if (!is_end && cnt > 0 && !(args.debug_skip & 2)) consume(b, lb, off, cnt);
+                if (!is_end && cnt > 0) consume(b, lb, off, cnt);
             }
-            else if (!(args.debug_skip & 1))
+            else
             {
                 if (is_end)
                     flush(BRICK * (NL - 1), BRICK * NL + 2 * M);
@@ -1432,14 +1431,10 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
                 args.tma_mask |= (1u << a);
         constexpr size_t ring_bytes = (size_t)C::NRING * C::PLANE * sizeof(double);
         constexpr size_t budget = 232448 - 3072 - ring_bytes - C::SINK_B - 2 * C::REC; // (static shared memory: the per-layer tables)
-        static const int cap_env = getenv("IBK_SPREAD_CAP") ? atoi(getenv("IBK_SPREAD_CAP")) : 0;
         args.cap = (int)std::min<size_t>(384, budget / (2 * C::REC));
-        if (cap_env >= 32 && cap_env < args.cap) args.cap = cap_env;
         const size_t smem = ring_bytes + C::SINK_B + 2 * (size_t)(args.cap + 1) * C::REC;
-        static const int chunk_env = getenv("IBK_SPREAD_CHUNK") ? atoi(getenv("IBK_SPREAD_CHUNK")) : 0;
-        args.chunk_tiles = (chunk_env >= 1 && chunk_env <= MARCH_MAX_LAYERS / TILE_BRICKS) ? chunk_env : 4;
-        static const int skip_env = getenv("IBK_MARCH_SKIP") ? atoi(getenv("IBK_MARCH_SKIP")) : 0;
-        args.debug_skip = skip_env;
+        // 8 marker tiles (128 cells, 32 brick layers) per chunk in z: measured best (4: 3.06 ms, 8: 2.89 ms on the C5 shard)
+        args.chunk_tiles = MARCH_MAX_LAYERS / TILE_BRICKS;
         auto kfn = spread_march_kernel<K>;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
@@ -1518,14 +1513,6 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
             kfn<<<dim3((unsigned)ntiles, (unsigned)tp.ncomp), SPREAD_THREADS, smem, L.stream>>>(tp, maps, args);
             L.launches++;
         }
-    }
-    static const bool dbg_exc = getenv("IBK_DEBUG_EXC") != nullptr;
-    if (dbg_exc)
-    {
-        int h = 0;
-        cudaMemcpyAsync(&h, args.exc_count, sizeof(int), cudaMemcpyDeviceToHost, L.stream);
-        cudaStreamSynchronize(L.stream);
-        fprintf(stderr, "[ibk] spread<%d,%d>: %d flagged (entry, component) pairs of %d entries\n", NDIM, K, h, args.n_entries);
     }
     ffn<<<1, FIXUP_THREADS, 0, L.stream>>>(tp, args);
     L.launches++;

@@ -14,6 +14,10 @@ import pytest
 from oracle import oracle as orc
 from tests.util import splitmix64_unit
 
+
+def _uniform(seed, n, lo, hi):
+    return lo + (hi - lo) * splitmix64_unit(seed, np.arange(n))
+
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
@@ -118,6 +122,20 @@ def test_c2_spherical_shell_dense(api):
     assert eu <= TOL and ef <= TOL
 
 
+def test_c2_spherical_shell_full_size(api):
+    """C2 at BASELINE.json's stated size: 2^20 markers on a shell of radius 0.25 on the 256^3 periodic unit cube (IB_4), value by
+    value against the oracle (the configs were only checked at reduced size)."""
+    N, n = 1 << 20, 256
+    k = np.arange(N) + 0.5
+    phi = np.arccos(1 - 2 * k / N)
+    th = np.pi * (1 + 5 ** 0.5) * k
+    X = 0.5 + 0.25 * np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1)
+    F = np.stack([2 * splitmix64_unit(1 + d, np.arange(N)) - 1 for d in range(3)], axis=1)
+    level = orc.Level(3, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), [((0,) * 3, (n - 1,) * 3)], (3,) * 3)
+    eu, ef = _run_level_case(api, level, "IB_4", X, F)
+    assert eu <= TOL and ef <= TOL
+
+
 def test_c3_ib6_uniform_plus_jittered_shell(api):
     """C3 (reduced): IB_6, uniform markers + shell R = 0.3 with radial jitter N(0, h), 2x2x1 patches of a 48^3 grid."""
     n, N = 48, 30000
@@ -193,3 +211,52 @@ def test_dense_bricks_every_kernel(api, kernel):
     level = orc.Level(3, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), boxes, (g,) * 3)
     eu, ef = _run_level_case(api, level, kernel, X, F)
     assert eu <= TOL and ef <= TOL
+
+
+@pytest.mark.parametrize("kernel", ["IB_4", "IB_6"])
+def test_many_stencils_outside_their_tile_are_still_spread_exactly(api, kernel):
+    """ADVICE r1 (silent overflow of the 4096-entry exception list): positions that moved since the binning put thousands of
+    stencils outside the accumulator of their tile.  They must all be spread (by the fix-up, in sorted order), none dropped.
+    The positions are changed behind the library's back through the device pointer of the X column (ibk_markers_upload would
+    demand a re-bin), 20000 markers by 3 cells each: every one of them misses its brick's footprint."""
+    import torch
+
+    ndim, n, N = 3, 64, 30000
+    g = orc.min_ghost_width(kernel)
+    level = orc.Level(ndim, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), [((0,) * 3, (n - 1,) * 3)], (g,) * 3)
+    h = 1.0 / n
+    X = np.stack([_uniform(901 + d, N, 8 * h, 1.0 - 8 * h) for d in range(3)], axis=1)
+    F = np.stack([_uniform(911 + d, N, -1.0, 1.0) for d in range(3)], axis=1)
+    ib = api.IBMethodB200(3, (0,) * 3, (n - 1,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), level.boxes, kernel_fcn=kernel)
+    ib.setPositions(X)
+    ib.setLData("F", F)
+    ib.beginDataRedistribution()
+    order = ib.getSortedLagrangianIndices()          # storage position -> Lagrangian index
+    moved = np.zeros(N, dtype=bool)
+    moved[:20000] = True
+    Xn = X.copy()
+    Xn[moved] += np.array([3 * h, -3 * h, 3 * h])
+    ptr, stride = ib.marker_device_ptr("X")
+    Xs = np.ascontiguousarray(Xn[order].T)           # SoA in storage order
+    # (raw copy into the library's column: wrap it as a torch tensor through the CUDA array interface)
+    class _Dev:
+        def __init__(self, p, count):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (p, False), "version": 2}
+    ib.ctx.synchronize()
+    for d in range(3):
+        torch.as_tensor(_Dev(ptr + 8 * stride * d, N), device="cuda").copy_(torch.from_numpy(Xs[d]))
+    torch.cuda.synchronize()
+    ib.grid_fill("f", 0.0)
+    ib.spreadForce(accumulate_halo=False)
+    pg = level.patch_geom(0)
+    f_ref = [np.zeros(pg.side_shape(a)) for a in range(3)]
+    orc.side_spread(kernel, pg, f_ref, Xn, F, np.arange(N, dtype=np.int32), np.zeros(3 * N))
+    for a in range(3):
+        f = ib.grid_download("f", 0, a)
+        assert np.max(np.abs(f - f_ref[a])) <= 1e-12 * np.max(np.abs(f_ref[a]))
+    # and the flags are clean again: a second spread adds exactly the same once more
+    ib.spreadForce(accumulate_halo=False)
+    for a in range(3):
+        f = ib.grid_download("f", 0, a)
+        assert np.max(np.abs(f - 2.0 * f_ref[a])) <= 1e-12 * np.max(np.abs(f_ref[a])) * 2
+    ib.close()
