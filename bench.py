@@ -299,8 +299,10 @@ def run_gpu(args):
     g = ib.gcw[0]
     hx = None
     if world > 1:
-        plan = halo.HaloPlan(patches, dom, (1, 1, 1), ib.gcw, rank)
-        hx = halo.HaloExchange(plan, halo.IbkBackend(ib, dist, torch))
+        # the multi-rank layer of libibk.so: its own NCCL communicator (id handed round by torch.distributed), plan, pack,
+        # messages on the context's communication stream, unpack
+        halo.CommExchange.init_nccl(ctx, dist, torch, rank, world)
+        hx = halo.CommExchange(ib, patches)
 
     # ---- synthetic inputs: uniform markers in the rank's patch, smooth + noisy velocity
     h = 1.0 / n

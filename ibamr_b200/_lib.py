@@ -137,6 +137,23 @@ SYMBOLS = {
     "ibk_markers_device_ptr": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_ll)]),
     "ibk_grid_device_ptr": (_i, [_vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_ll), _pi]),
     "ibk_count_touched_dofs": (_i, [_vp, _s, C.POINTER(_ll)]),
+    "ibk_halo_plan_create": (_i, [_i, _i, _pi, _pi, _pi, _pi, _pi, _pi, _i, C.POINTER(_vp)]),
+    "ibk_halo_plan_destroy": (None, [_vp]),
+    "ibk_halo_plan_messages": (_i, [_vp, _i]),
+    "ibk_halo_plan_message": (_i, [_vp, _i, _i, _pi, _pi, _pi, C.POINTER(_ll)]),
+    "ibk_halo_plan_items": (_i, [_vp, _i, _i, _pi, _pi, _pi, _pi, _pi, _pi, _pi]),
+    "ibk_comm_unique_id": (_i, [_vp]),
+    "ibk_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "ibk_comm_init_loopback": (_i, [C.POINTER(_vp), _i]),
+    "ibk_comm_set_patches": (_i, [_vp, _i, _pi, _pi, _pi]),
+    "ibk_comm_destroy": (_i, [_vp]),
+    "ibk_halo_fill_post": (_i, [_vp]),
+    "ibk_halo_fill_finish": (_i, [_vp]),
+    "ibk_halo_accumulate_post": (_i, [_vp]),
+    "ibk_halo_accumulate_finish": (_i, [_vp]),
+    "ibk_halo_bytes": (_ll, [_vp, _i]),
+    "ibk_migrate": (_i, [_vp, C.c_uint, _pi, _pi]),
+    "ibk_migrate_loopback": (_i, [C.POINTER(_vp), _i, C.c_uint, _pi]),
 }
 
 _LIB = None

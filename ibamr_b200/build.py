@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["ibk_api.cu", "ibk_level.cu", "ibk_bin.cu", "ibk_sort.cu", "ibk_interp.cu", "ibk_spread.cu", "ibk_halo.cu", "ibk_migrate.cu", "ibk_force.cu", "ibk_io.cu"]
+SOURCES = ["ibk_api.cu", "ibk_level.cu", "ibk_bin.cu", "ibk_sort.cu", "ibk_interp.cu", "ibk_spread.cu", "ibk_halo.cu", "ibk_migrate.cu", "ibk_force.cu", "ibk_io.cu", "ibk_comm.cu"]
 HEADERS = ["ibk_device.cuh", "ibk_engine.h", "ibk_ctx.h", "ibk_tma.h", os.path.join("..", "..", "include", "ibk.h")]
 LIB = os.path.join(HERE, "libibk.so")
 OBJDIR = os.path.join(HERE, "_obj")
@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()):
     if failed:
         raise RuntimeError("libibk.so: compilation failed")
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + (["-ccbin", host_cc] if host_cc else []) + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + (["-ccbin", host_cc] if host_cc else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("libibk.so: link failed\n" + r.stdout + r.stderr)

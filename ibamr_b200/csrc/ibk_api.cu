@@ -155,12 +155,14 @@ extern "C" int ibk_ctx_create(int device, ibk_ctx** out)
 }
 
 extern "C" int ibk_level_destroy(ibk_ctx* ctx);
+extern "C" int ibk_comm_destroy(ibk_ctx* ctx);
 
 extern "C" int ibk_ctx_destroy(ibk_ctx* ctx)
 {
     if (!ctx) return IBK_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->L.stream);
+    ibk_comm_destroy(ctx);
     ibk_level_destroy(ctx);
     bins_free(ctx->sbins);
     ctx->b_Xe.release();

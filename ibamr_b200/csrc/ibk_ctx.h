@@ -112,6 +112,6 @@ struct ibk_ctx
     cudaEvent_t ev_in[2], ev_out[2], ev_order;
     bool xfer_created = false;
     bool pend_in[2] = { false, false }, pend_out[2] = { false, false };
-    ibk::DevBuf b_mig[8];   // marker migration scratch (keys/vals ping-pong, sort temp, box list, offsets)
+    ibk::DevBuf b_mig[10];  // marker migration scratch (keys/vals ping-pong, sort temp, box list, offsets; [8], [9]: send / receive rows of ibk_migrate)
     ibk::DevBuf b_stage[3]; // staging blocks of the grid transfers: compute stream, copy-in stream, copy-out stream
 };

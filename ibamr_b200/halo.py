@@ -8,15 +8,17 @@ Replaces, across processes, the SAMRAI schedules the reference runs around the h
               face shared by two patches), SAMRAIGhostDataAccumulator::accumulateGhostData reverse
               scatter, ibtk/src/math/SAMRAIGhostDataAccumulator.cpp:327-334
 
-Copies between patches of the SAME process are done by ibk_halo_local inside libibk.so; this module
-only plans and moves what crosses a process boundary: device pack kernel -> one message per
-neighbour rank (torch.distributed batch_isend_irecv: NCCL over NVLink on the GPU box, gloo in the CPU
-tests) -> device unpack(-add) kernel.  The plan is static (boxes do not change between regrids) and
-is derived identically on both ends from the global box list, so no metadata is exchanged.
-Unpack-adds run in a fixed order (source rank, then item order), so sums are reproducible.
+Copies between patches of the SAME process are done by ibk_halo_local inside libibk.so.  What crosses a process
+boundary is planned, packed, sent and unpacked inside libibk.so as well (csrc/ibk_comm.cu: ibk_halo_plan_*,
+ibk_comm_*, ibk_halo_*_post / *_finish, ibk_migrate; NCCL over NVLink): CommExchange below only forwards the calls,
+the way a C++ IBAMR rank would make them.  The plan is static (boxes do not change between regrids) and is derived
+identically on both ends from the global box list, so no metadata is exchanged.  Unpack-adds run in a fixed order
+(source rank, then item order), so sums are reproducible.
 
-The pack/unpack backend is injected: IbkBackend drives libibk.so on device buffers; the CPU tests
-inject a numpy stand-in to exercise exactly this planning/messaging logic without a GPU.
+HaloPlan / HaloExchange expose the same C++ plan to the CPU tests: they run it over torch.distributed (gloo) with a
+numpy stand-in for the pack / unpack kernels, so the planning and the message order are exercised without a GPU.
+IbkBackend (device pack / unpack + torch.distributed messages) is the round-1 path, kept as a cross-check of the
+library's own transport.
 """
 from __future__ import annotations
 
@@ -32,44 +34,6 @@ class GlobalPatch:
     upper: tuple
     rank: int
     local_id: int  # index among the patches of `rank`
-
-
-def _side_boxes(gp: GlobalPatch, axis, gcw):
-    ndim = len(gp.lower)
-    ilo = tuple(gp.lower)
-    ihi = tuple(gp.upper[d] + (1 if d == axis else 0) for d in range(ndim))
-    alo = tuple(ilo[d] - gcw[d] for d in range(ndim))
-    ahi = tuple(ihi[d] + gcw[d] for d in range(ndim))
-    return ilo, ihi, alo, ahi
-
-
-def _intersect(lo1, hi1, lo2, hi2):
-    lo = tuple(max(a, b) for a, b in zip(lo1, lo2))
-    hi = tuple(min(a, b) for a, b in zip(hi1, hi2))
-    if any(h < l for l, h in zip(lo, hi)):
-        return None
-    return lo, hi
-
-
-def _box_minus(lo, hi, ilo, ihi):
-    """Box difference [lo,hi] \\ [ilo,ihi] as disjoint boxes (highest dimension first)."""
-    out = []
-    ndim = len(lo)
-    cur_lo, cur_hi = list(lo), list(hi)
-    inter = _intersect(lo, hi, ilo, ihi)
-    if inter is None:
-        return [(tuple(lo), tuple(hi))]
-    for d in reversed(range(ndim)):
-        if cur_lo[d] < inter[0][d]:
-            l, h = list(cur_lo), list(cur_hi)
-            h[d] = inter[0][d] - 1
-            out.append((tuple(l), tuple(h)))
-        if cur_hi[d] > inter[1][d]:
-            l, h = list(cur_lo), list(cur_hi)
-            l[d] = inter[1][d] + 1
-            out.append((tuple(l), tuple(h)))
-        cur_lo[d], cur_hi[d] = inter[0][d], inter[1][d]
-    return out
 
 
 @dataclass
@@ -89,46 +53,48 @@ class Item:
 
 
 class HaloPlan:
-    """All inter-rank items of one level, for `fill` (u) and `accumulate` (f)."""
+    """All inter-rank items of one level, for `fill` (u) and `accumulate` (f): a view of the C++ plan
+    (ibk_halo_plan_create in libibk.so, host code: works without a GPU)."""
 
     def __init__(self, patches: list, domain_ncells, periodic, gcw, rank: int):
+        import ctypes as C
+
+        from . import _lib
+        lib = _lib.load()
         self.patches, self.rank = patches, rank
         ndim = len(domain_ncells)
         self.ndim = ndim
-        offs = [(-1, 0, 1) if periodic[d] else (0,) for d in range(ndim)]
-        self.fill: dict = {}  # (src_rank, dst_rank) -> [Item]
-        self.accum: dict = {}
-        for axis in range(ndim):
-            for dst in patches:
-                d_ilo, d_ihi, d_alo, d_ahi = _side_boxes(dst, axis, gcw)
-                for src in patches:
-                    if src.rank == dst.rank:
-                        continue  # same process: ibk_halo_local
-                    if src.rank != rank and dst.rank != rank:
-                        continue
-                    s_ilo, s_ihi, s_alo, s_ahi = _side_boxes(src, axis, gcw)
-                    for o in itertools.product(*offs):
-                        sh = tuple(o[d] * domain_ncells[d] for d in range(ndim))
-                        # ---- fill: ghost region of dst  <-  interior of src (shifted by sh)
-                        si = (tuple(s_ilo[d] + sh[d] for d in range(ndim)), tuple(s_ihi[d] + sh[d] for d in range(ndim)))
-                        for glo, ghi in _box_minus(d_alo, d_ahi, d_ilo, d_ihi):
-                            r = _intersect(glo, ghi, *si)
-                            if r:
-                                self.fill.setdefault((src.rank, dst.rank), []).append(
-                                    Item(axis, src, dst, tuple(r[0][d] - sh[d] for d in range(ndim)),
-                                         tuple(r[1][d] - sh[d] for d in range(ndim)), r[0], r[1]))
-                        # ---- accumulate: interior of dst  +=  every copy src holds of it (ghosts, shared face)
-                        sa = (tuple(s_alo[d] + sh[d] for d in range(ndim)), tuple(s_ahi[d] + sh[d] for d in range(ndim)))
-                        r = _intersect(d_ilo, d_ihi, *sa)
-                        if r:
-                            self.accum.setdefault((src.rank, dst.rank), []).append(
-                                Item(axis, src, dst, tuple(r[0][d] - sh[d] for d in range(ndim)),
-                                     tuple(r[1][d] - sh[d] for d in range(ndim)), r[0], r[1]))
-        # first-match semantics of the fill (a ghost cell covered by two source interiors, i.e. a shared
-        # face, carries the same value in both) and a canonical order everywhere
-        for table in (self.fill, self.accum):
-            for key in table:
-                table[key].sort(key=lambda it: (it.axis, it.dst.local_id, it.src.rank, it.src.local_id, it.dst_lo, it.dst_hi))
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        pi = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        lo, hi = i32([p.lower for p in patches]).reshape(-1), i32([p.upper for p in patches]).reshape(-1)
+        rk = i32([p.rank for p in patches])
+        h = C.c_void_p()
+        rc = lib.ibk_halo_plan_create(ndim, len(patches), pi(lo), pi(hi), pi(rk), pi(i32(domain_ncells)), pi(i32([1 if x else 0 for x in periodic])),
+                                      pi(i32(gcw)), int(rank), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"ibk_halo_plan_create failed ({rc})")
+        # local ids as the library numbers them: position among the patches of the same rank, in list order
+        seen, by_local = {}, {}
+        for p in patches:
+            k = seen.get(p.rank, 0)
+            seen[p.rank] = k + 1
+            by_local[(p.rank, k)] = p
+        self.fill, self.accum = {}, {}  # (src_rank, dst_rank) -> [Item]
+        for t, table in ((0, self.fill), (1, self.accum)):
+            for k in range(lib.ibk_halo_plan_messages(h, t)):
+                src, dst, n, cnt = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+                lib.ibk_halo_plan_message(h, t, k, C.byref(src), C.byref(dst), C.byref(n), C.byref(cnt))
+                n = n.value
+                ax, sl, dl = (np.zeros(n, dtype=np.int32) for _ in range(3))
+                slo, shi, dlo, dhi = (np.zeros(n * ndim, dtype=np.int32) for _ in range(4))
+                lib.ibk_halo_plan_items(h, t, k, pi(ax), pi(sl), pi(dl), pi(slo), pi(shi), pi(dlo), pi(dhi))
+                table[(src.value, dst.value)] = [
+                    Item(int(ax[i]), by_local[(src.value, int(sl[i]))], by_local[(dst.value, int(dl[i]))],
+                         tuple(int(v) for v in slo[i * ndim:(i + 1) * ndim]), tuple(int(v) for v in shi[i * ndim:(i + 1) * ndim]),
+                         tuple(int(v) for v in dlo[i * ndim:(i + 1) * ndim]), tuple(int(v) for v in dhi[i * ndim:(i + 1) * ndim]))
+                    for i in range(n)]
+                assert sum(it.count for it in table[(src.value, dst.value)]) == cnt.value
+        lib.ibk_halo_plan_destroy(h)
 
     def neighbours(self, table):
         send = sorted({dst for (src, dst) in table if src == self.rank})
@@ -137,6 +103,75 @@ class HaloPlan:
 
     def bytes_per_exchange(self, table):
         return 8 * sum(it.count for (src, dst), items in table.items() if src == self.rank for it in items)
+
+
+class CommExchange:
+    """The device path: the communicator of the context inside libibk.so (ibk_comm_*; NCCL, or loopback between contexts of
+    one process) does the planning, packing, messaging and unpacking; this class only forwards the calls."""
+
+    def __init__(self, ib, patches):
+        import ctypes as C
+        self.ib, self.C = ib, C
+        ctx = ib.ctx
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        pi = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        lo, hi = i32([p.lower for p in patches]).reshape(-1), i32([p.upper for p in patches]).reshape(-1)
+        rk = i32([p.rank for p in patches])
+        ctx.check(ctx.lib.ibk_comm_set_patches(ctx.h, len(patches), pi(lo), pi(hi), pi(rk)))
+
+    @staticmethod
+    def init_nccl(ctx, dist, torch, rank, world):
+        """Rank 0 creates the NCCL id, torch.distributed (the host program's own messaging) hands it round."""
+        import ctypes as C
+        idbuf = (C.c_char * 128)()
+        if rank == 0:
+            ctx.check(ctx.lib.ibk_comm_unique_id(idbuf))
+        t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
+        ctx.check(ctx.lib.ibk_comm_init(ctx.h, C.c_char_p(raw), rank, world))
+
+    @staticmethod
+    def init_loopback(contexts):
+        import ctypes as C
+        arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+        contexts[0].check(contexts[0].lib.ibk_comm_init_loopback(arr, len(contexts)))
+
+    def _call(self, name):
+        ctx = self.ib.ctx
+        ctx.check(getattr(ctx.lib, name)(ctx.h))
+
+    def fill_post(self):
+        self._call("ibk_halo_fill_post")
+
+    def fill_finish(self):
+        self._call("ibk_halo_fill_finish")
+
+    def accumulate_post(self):
+        self._call("ibk_halo_accumulate_post")
+
+    def accumulate_finish(self):
+        self._call("ibk_halo_accumulate_finish")
+
+    def bytes(self, which):
+        return int(self.ib.ctx.lib.ibk_halo_bytes(self.ib.ctx.h, which))
+
+    # the unsplit forms
+    def fill(self):
+        self.fill_post()
+        self.fill_finish()
+
+    accumulate_begin = accumulate_post  # pack BEFORE any local accumulation touches the values ...
+    accumulate_end = accumulate_finish  # ... add AFTER it
+
+    def migrate(self, id_bound):
+        C = self.C
+        ns, nr = C.c_int(), C.c_int()
+        ctx = self.ib.ctx
+        ctx.check(ctx.lib.ibk_migrate(ctx.h, C.c_uint(int(id_bound)), C.byref(ns), C.byref(nr)))
+        return ns.value, nr.value
 
 
 class HaloExchange:

@@ -464,6 +464,54 @@ int ibk_halo_pack_many(ibk_ctx* ctx, int which, int n_items, const int* patch, c
 int ibk_halo_unpack_many(ibk_ctx* ctx, int which, int n_items, const int* patch, const int* axis, const int* lower,
                          const int* upper, const long long* buf_offset, const double* d_buf, int mode);
 
+/* ---- the multi-rank layer (one process per GPU; seam B1 across processes) -------------------------------------
+ * What the reference reaches from C++ around the hot path when the level is spread over MPI ranks:
+ *   fill        ghost cells of u <- owner interiors, periodic wrap included
+ *               (u_ghost_fill_scheds[ln]->fillData, ibtk/src/lagrangian/LDataManager.cpp:744);
+ *   accumulate  owner interiors of f += every other copy of the DOF, ghost copies and the interior copy of a face shared
+ *               by two patches (SAMRAIGhostDataAccumulator::accumulateGhostData,
+ *               ibtk/src/math/SAMRAIGhostDataAccumulator.cpp:327-344, called LDataManager.cpp:597-620);
+ *   migrate     the scatter of the marker rows to their new owners (LDataManager.cpp:1824-1837).
+ *
+ * PLAN (host code, no context, no GPU): every rank derives the same plan from the global patch list, so no metadata is
+ * exchanged.  table 0 = fill, 1 = accumulate.  A message is everything one rank sends another in one exchange; its items
+ * are regions in a canonical order ((axis, destination patch, source rank, source patch, region)), unpack-adds run in
+ * ascending source rank, then item order: sums are reproducible.  Boxes are [n][ndim] cell boxes, inclusive;
+ * src_local / dst_local number a patch among the patches of its own rank, in list order. */
+typedef struct ibk_halo_plan ibk_halo_plan;
+int ibk_halo_plan_create(int ndim, int n_patches, const int* lower, const int* upper, const int* rank, const int* domain_ncells,
+                         const int* periodic, const int* gcw, int my_rank, ibk_halo_plan** out);
+void ibk_halo_plan_destroy(ibk_halo_plan* plan);
+int ibk_halo_plan_messages(const ibk_halo_plan* plan, int table); /* number of messages that involve my_rank (< 0: error) */
+int ibk_halo_plan_message(const ibk_halo_plan* plan, int table, int k, int* src_rank, int* dst_rank, int* n_items, long long* count);
+int ibk_halo_plan_items(const ibk_halo_plan* plan, int table, int k, int* axis, int* src_local, int* dst_local, int* src_lo, int* src_hi,
+                        int* dst_lo, int* dst_hi);
+/* COMMUNICATOR of a context.  NCCL (resolved with dlopen at the first call: libibk.so itself does not link it): rank 0 obtains
+ * a 128-byte id with ibk_comm_unique_id and hands it to the other ranks by whatever the host program has (MPI_Bcast in
+ * IBAMR), every rank calls ibk_comm_init.  ibk_comm_init_loopback makes several contexts of ONE process the ranks
+ * 0..nranks-1 of a communicator that moves messages by device copies (tests on one GPU; one process driving several GPUs).
+ * ibk_comm_set_patches (after ibk_level_create; the same list on every rank, the k-th patch of a rank in the list being
+ * the k-th patch of its level) builds the plan and allocates the message buffers. */
+int ibk_comm_unique_id(void* id128);
+int ibk_comm_init(ibk_ctx* ctx, const void* id128, int rank, int nranks);
+int ibk_comm_init_loopback(ibk_ctx** ctxs, int nranks);
+int ibk_comm_set_patches(ibk_ctx* ctx, int n_patches, const int* lower, const int* upper, const int* rank);
+int ibk_comm_destroy(ibk_ctx* ctx);
+/* The exchanges, split so that the messages are in flight while the tiles that do not touch the exchanged regions are
+ * processed (ibk_*_part): post = pack on the context's stream + start the messages on its communication stream,
+ * finish = the context's stream waits for them + unpack (fill: copy, accumulate: add).  Sequences as listed at
+ * ibk_spread_force_part.  Every rank posts before any rank can finish (collective, like the schedules they replace). */
+int ibk_halo_fill_post(ibk_ctx* ctx);
+int ibk_halo_fill_finish(ibk_ctx* ctx);
+int ibk_halo_accumulate_post(ibk_ctx* ctx);
+int ibk_halo_accumulate_finish(ibk_ctx* ctx);
+long long ibk_halo_bytes(ibk_ctx* ctx, int which); /* bytes this rank sends per fill (0) / accumulate (1) */
+/* Marker migration over the communicator: ibk_migrate_plan, counts all-gathered, rows sent and received in one group,
+ * ibk_migrate_unpack.  ibk_rebin precedes and follows.  ibk_migrate_loopback does it for all ranks of a loopback
+ * communicator in one call. */
+int ibk_migrate(ibk_ctx* ctx, unsigned id_bound, int* n_sent, int* n_received);
+int ibk_migrate_loopback(ibk_ctx** ctxs, int nranks, unsigned id_bound, int* n_moved);
+
 /* Device pointers for zero-copy callers (torch tensors, NCCL): SoA marker columns in SORTED
  * order ([ndim][capacity] with the given stride) and pitched grid arrays. */
 int ibk_markers_device_ptr(ibk_ctx* ctx, int which, double** d_ptr, long long* stride);

@@ -1,12 +1,12 @@
 """Multi-GPU parity worker (run under torchrun, one rank per GPU): patch-partitioned periodic level,
 markers owned by the rank whose patch holds their cell, spreadForce / interpolateVelocity with the
-NCCL halo exchange, gathered and compared on rank 0 with the oracle's model of the reference path
+NCCL halo exchange of libibk.so (ibk_comm_*), gathered and compared on rank 0 with the oracle's model of the reference path
 (redundant ghost-region spreading, interiors kept; interpolation after a ghost fill).
 
     torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_worker.py IB_4 [migrate]
 
 With `migrate` the markers start on arbitrary ranks and are moved to their owners first
-(halo.MarkerMigration over ibk_migrate_*; LDataManager.cpp:1824-1837).
+(ibk_migrate over the NCCL communicator of libibk.so; LDataManager.cpp:1824-1837).
 """
 import os
 import sys
@@ -60,8 +60,9 @@ def main():
 
     ib = api.IBMethodB200(3, (0,) * 3, tuple(d - 1 for d in dom), (0.0,) * 3, xup, (1, 1, 1), [(me.lower, me.upper)], gcw=g,
                           kernel_fcn=kernel, ctx=ctx)
-    plan = halo.HaloPlan(patches, dom, (1, 1, 1), ib.gcw, rank)
-    hx = halo.HaloExchange(plan, halo.IbkBackend(ib, dist, torch))
+    # the library's own multi-rank layer (csrc/ibk_comm.cu): NCCL communicator of the context, plan, pack, messages, unpack
+    halo.CommExchange.init_nccl(ctx, dist, torch, rank, world)
+    hx = halo.CommExchange(ib, patches)
     pg = level.patch_geom(rank)
     u = [periodic_side_field(pg, a, dom, 300) for a in range(3)]
     for a in range(3):
@@ -79,13 +80,13 @@ def main():
         ib.setLData("F", F[start])
         ib.setIds(start, N)
         ib.beginDataRedistribution()
-        mig = halo.MarkerMigration(patches, rank, world, halo.IbkBackend(ib, dist, torch), N)
-        n_sent, n_recv = mig.migrate()
+        n_sent, n_recv = hx.migrate(N)
+        ib.n_markers = int(ctx.lib.ibk_markers_count(ctx.h))
         ib.beginDataRedistribution()
         assert n_sent > 0 and n_recv > 0
         assert np.array_equal(ib.getIds(), mine), "after the migration a rank holds exactly the markers of its patch"
         assert np.array_equal(ib.getLData("X"), X[mine]) and np.array_equal(ib.getLData("F"), F[mine])
-        assert mig.migrate() == (0, 0)
+        assert hx.migrate(N) == (0, 0)
         ib.beginDataRedistribution()
     else:
         ib.setPositions(X[mine])
@@ -136,7 +137,7 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(f"MGPU_PARITY kernel={kernel} world={world} migrate={int(migrate)} overlap={int(overlap)} interp_rel_err={t[0].item():.3e} spread_rel_err={t[1].item():.3e} "
-              f"fill_bytes={plan.bytes_per_exchange(plan.fill)} accum_bytes={plan.bytes_per_exchange(plan.accum)}", flush=True)
+              f"fill_bytes={hx.bytes(0)} accum_bytes={hx.bytes(1)}", flush=True)
         assert t[0].item() <= 1e-12 and t[1].item() <= 1e-12
     ib.close()
     dist.barrier()

@@ -749,6 +749,136 @@ def test_adjointness_and_moments_large(api, kernel):
     ib.close()
 
 
+@pytest.mark.parametrize("world,kernel,mode", [(2, "IB_4", "plain"), (2, "IB_4", "overlap"), (2, "IB_6", "overlap"), (4, "IB_4", "overlap"),
+                                               (2, "IB_4", "migrate")])
+def test_ranks_as_contexts_of_one_process(api, world, kernel, mode):
+    """The multi-rank path on ONE GPU (N > 1 had no driver-side parity evidence): `world` contexts of this
+    process are the ranks of a loopback communicator of libibk.so (ibk_comm_init_loopback); each owns one patch of a
+    2 x 1 x 1 / 2 x 2 x 1 decomposition of a periodic level and the markers in it.  The C-ABI plan, pack, message,
+    unpack(-add) and migration code is the code the NCCL transport runs; the overlapped sequence is the one bench.py times
+    at N > 1.  Compared per rank with the oracle's model of the reference (redundant ghost-region spreading)."""
+    from ibamr_b200 import halo
+    n = 64 if mode == "overlap" else 32  # with 64 cells per rank there are interior tiles
+    pgrid = {2: (2, 1, 1), 4: (2, 2, 1)}[world]
+    patches = halo.cartesian_patches(3, pgrid, (n, n, n))
+    dom = tuple(n * pgrid[d] for d in range(3))
+    g = orc.min_ghost_width(kernel)
+    xup = tuple(float(p) for p in pgrid)
+    level = orc.Level(3, (0,) * 3, dom, (0.0,) * 3, xup, (1, 1, 1), [(p.lower, p.upper) for p in patches], (g,) * 3)
+    N = 40000
+    X = np.stack([xup[d] * _uniform(61 + d, N, 0.0, 1.0) for d in range(3)], axis=1)
+    F = np.stack([_uniform(71 + d, N, -1.0, 1.0) for d in range(3)], axis=1)
+    ref = orc.bin_level(level, X)
+    ctxs = [api.Context(0) for _ in range(world)]
+    halo.CommExchange.init_loopback(ctxs)
+    ibs, hxs, us = [], [], []
+    for r in range(world):
+        me = patches[r]
+        ib = api.IBMethodB200(3, (0,) * 3, tuple(d - 1 for d in dom), (0.0,) * 3, xup, (1, 1, 1), [(me.lower, me.upper)], gcw=g,
+                              kernel_fcn=kernel, ctx=ctxs[r])
+        pg = level.patch_geom(r)
+        u = _periodic_side_fields_global(pg, dom, 300)
+        for a in range(3):
+            garbage = u[a].copy()
+            mask = np.ones(garbage.shape, bool)
+            mask[tuple(slice(g, s - g) for s in garbage.shape)] = False
+            garbage[mask] = 1e30  # the ghost values must come from the exchange
+            ib.grid_upload("u", 0, a, garbage)
+            ib.grid_upload("f", 0, a, np.full(pg.side_shape(a), 0.25))
+        ibs.append(ib)
+        us.append(u)
+        hxs.append(halo.CommExchange(ib, patches))
+    mine = [np.nonzero(ref["owner"] == r)[0] for r in range(world)]
+    if mode == "migrate":
+        import ctypes as C
+        for r in range(world):  # start from an arbitrary distribution (index mod world) and let the markers find their owners
+            start = np.arange(r, N, world)
+            ibs[r].setPositions(X[start])
+            ibs[r].setLData("F", F[start])
+            ibs[r].setIds(start, N)
+            ibs[r].beginDataRedistribution()
+        arr = (C.c_void_p * world)(*[c.h for c in ctxs])
+        moved = C.c_int()
+        ctxs[0].check(ctxs[0].lib.ibk_migrate_loopback(arr, world, C.c_uint(N), C.byref(moved)))
+        assert moved.value > 0
+        for r in range(world):
+            ibs[r].n_markers = int(ctxs[r].lib.ibk_markers_count(ctxs[r].h))
+            ibs[r].beginDataRedistribution()
+            assert np.array_equal(ibs[r].getIds(), mine[r]), "after the migration a rank holds exactly the markers of its patch"
+            assert np.array_equal(ibs[r].getLData("X"), X[mine[r]]) and np.array_equal(ibs[r].getLData("F"), F[mine[r]])
+    else:
+        for r in range(world):
+            ibs[r].setPositions(X[mine[r]])
+            ibs[r].setLData("F", F[mine[r]])
+            ibs[r].beginDataRedistribution()
+    chk = lambda r, rc: ctxs[r].check(rc)
+    if mode == "overlap":
+        for r in range(world):
+            chk(r, ctxs[r].lib.ibk_spread_begin(ctxs[r].h))
+            ibs[r].spreadForcePart(2)
+            hxs[r].accumulate_post()
+            ibs[r].spreadForcePart(1)
+            ibs[r].halo("f")
+        for r in range(world):
+            hxs[r].accumulate_finish()
+            chk(r, ctxs[r].lib.ibk_spread_end(ctxs[r].h))
+        for r in range(world):
+            hxs[r].fill_post()
+            ibs[r].halo("u")
+            ibs[r].interpolateVelocityPart(1)
+        for r in range(world):
+            hxs[r].fill_finish()
+            ibs[r].interpolateVelocityPart(2)
+    else:
+        for r in range(world):
+            chk(r, ctxs[r].lib.ibk_spread_begin(ctxs[r].h))
+            ibs[r].spreadForce(accumulate_halo=False)
+            hxs[r].accumulate_post()
+            ibs[r].halo("f")
+        for r in range(world):
+            hxs[r].accumulate_finish()
+            chk(r, ctxs[r].lib.ibk_spread_end(ctxs[r].h))
+        for r in range(world):
+            ibs[r].halo("u")
+            hxs[r].fill_post()
+        for r in range(world):
+            hxs[r].fill_finish()
+            ibs[r].interpolateVelocity(fill_halo=False)
+    for r in range(world):
+        pg = level.patch_geom(r)
+        U = ibs[r].getLData("U")
+        lst = ref["patches"][r]
+        ii = lst["all_idx"][lst["interior_mask"]]
+        sh = lst["all_shift"].reshape(-1, 3)[lst["interior_mask"]]
+        U_ref = orc.side_interp(kernel, pg, us[r], X, ii, sh.reshape(-1))
+        f_ref = [np.zeros(pg.side_shape(a)) for a in range(3)]
+        orc.side_spread(kernel, pg, f_ref, X, F, lst["all_idx"], lst["all_shift"])
+        assert relerr(U, U_ref[mine[r]]) <= TOL
+        for a in range(3):
+            f = ibs[r].grid_download("f", 0, a)
+            sl = tuple(slice(g, s - g) for s in f.shape)
+            assert np.max(np.abs(f[sl] - 0.25 - f_ref[a][sl])) <= TOL * np.max(np.abs(f_ref[a][sl]))
+        assert hxs[r].bytes(0) > 0 and hxs[r].bytes(1) > 0
+    for ib in ibs:
+        ib.close()
+
+
+def _periodic_side_fields_global(pg, ncell, seed):
+    """Smooth + noisy side-centred fields that are periodic over the GLOBAL domain (the same value at periodic images)."""
+    out = []
+    for axis in range(3):
+        c = pg.side_coords(axis)
+        f = np.sin(2 * np.pi * c[axis] / (ncell[axis] * pg.dx[axis])) * np.cos(2 * np.pi * c[(axis + 1) % 3] / (ncell[(axis + 1) % 3] * pg.dx[0]))
+        gi = []
+        for d in range(3):
+            cnt = pg.upper[d] - pg.lower[d] + 1 + (1 if d == axis else 0) + 2 * pg.gcw[d]
+            gi.append(np.mod(np.arange(cnt) + pg.lower[d] - pg.gcw[d], ncell[d]))
+        mesh = np.meshgrid(*reversed(gi), indexing="ij")[::-1]
+        lin = mesh[0] + ncell[0] * (mesh[1] + ncell[1] * mesh[2])
+        out.append(np.ascontiguousarray(f + 1e-3 * splitmix64_unit(seed + axis, lin.reshape(-1)).reshape(f.shape)))
+    return out
+
+
 def test_multi_gpu_parity_two_ranks():
     """Patch-partitioned level on 2 GPUs with the NCCL halo exchange (tests/mgpu_worker.py) against the
     oracle; needs >= 2 visible GPUs (the driver's single-GPU tier skips it)."""
