@@ -379,7 +379,10 @@ struct ItemTable
     unsigned long long key = 0;
     HaloItem* d_items = nullptr;
     int n = 0;
-    bool disjoint = true; // no two regions of the same array overlap: one launch may add them all
+    // waves: maximal runs of consecutive items whose regions are pairwise disjoint; one launch adds a wave, the waves follow
+    // each other in item order, so two overlapping regions are still added in the order of the list
+    std::vector<int> wave_start; // [n_waves + 1]
+    std::vector<long long> wave_max;
     long long max_count = 0;
 };
 struct LevelExtra
@@ -1610,14 +1613,24 @@ static int item_table(ibk_ctx* ctx, int which, int n_items, const int* patch, co
         }
         h[k].buf_off = buf_offset[k];
         t.max_count = std::max(t.max_count, h[k].count);
-        for (int k2 = 0; k2 < k; ++k2) // do two regions of one array overlap?
+        if (t.wave_start.empty()) t.wave_start.push_back(0);
+        bool clash = false; // does the region overlap one of the current wave?
+        for (int k2 = t.wave_start.back(); k2 < k; ++k2)
         {
             if (h[k2].ptr != h[k].ptr) continue;
             bool ov = true;
             for (int d = 0; d < 3; ++d) ov = ov && h[k].off[d] < h[k2].off[d] + h[k2].ext[d] && h[k2].off[d] < h[k].off[d] + h[k].ext[d];
-            if (ov) t.disjoint = false;
+            clash = clash || ov;
         }
+        if (clash)
+        {
+            t.wave_start.push_back(k);
+            t.wave_max.push_back(0);
+        }
+        if (t.wave_max.empty()) t.wave_max.push_back(0);
+        t.wave_max.back() = std::max(t.wave_max.back(), h[k].count);
     }
+    t.wave_start.push_back(n_items);
     if (n_items > 0)
     {
         CK(cudaMalloc(&t.d_items, sizeof(HaloItem) * (size_t)n_items));
@@ -1655,19 +1668,11 @@ extern "C" int ibk_halo_unpack_many(ibk_ctx* ctx, int which, int n_items, const 
     GRID_DEPS(which);
     const ItemTable* t = nullptr;
     if (int rc = item_table(ctx, which, n_items, patch, axis, lower, upper, buf_offset, &t)) return rc;
-    if (t->disjoint)
+    // one launch per wave of pairwise disjoint regions, the waves in list order (fixed order of the additions)
+    for (size_t w = 0; w + 1 < t->wave_start.size(); ++w)
     {
-        CK(launch_halo_items(ctx->L, t->d_items, n_items, t->max_count, const_cast<double*>(d_buf), mode == 0 ? 1 : 2));
-        return IBK_OK;
-    }
-    const int ndim = ctx->lv.ndim; // overlapping regions: one launch per item, in order (fixed order of the additions)
-    for (int k = 0; k < n_items; ++k)
-    {
-        int off[3], ext[3];
-        if (int rc = region_args(ctx, which, patch[k], axis[k], lower + (size_t)k * ndim, upper + (size_t)k * ndim, off, ext)) return rc;
-        PatchState& ps = ctx->lv.patches[patch[k]];
-        CK(launch_unpack(ctx->L, which == 0 ? ps.u[axis[k]] : ps.f[axis[k]], ps.pitch[axis[k]], ps.n[axis[k]][1], off, ext,
-                         d_buf + buf_offset[k], ndim, mode));
+        const int k0 = t->wave_start[w], k1 = t->wave_start[w + 1];
+        if (k1 > k0) CK(launch_halo_items(ctx->L, t->d_items + k0, k1 - k0, t->wave_max[w], const_cast<double*>(d_buf), mode == 0 ? 1 : 2));
     }
     return IBK_OK;
 }

@@ -1,7 +1,8 @@
 // IBMethodB200.h -- the IBStrategy-shaped object an IBHierarchyIntegrator would hold for the hot path
 // (include/ibamr/IBStrategy.h:276-280, 338-342, 455, 464; overridden by src/IB/IBMethod.cpp:672-694,
-// 972-995, 1494-1557).  The PatchHierarchy / data-index arguments of the reference are replaced by the
-// level registered at construction (the patches THIS process owns) and by the device-resident u / f;
+// 972-995, 1494-1557).  interpolateVelocity / spreadForce carry the reference's signatures; the PatchHierarchy behind the
+// data indices is the level registered at construction (the patches THIS process owns) plus the host SideData bound to
+// an index with registerPatchData; the schedule arguments are accepted and ignored (the library does their work).
 // LData X / U / F are exchanged with the host in Lagrangian order (LData AoS layout, LData.h:351-367).
 #pragma once
 #include <stdexcept>
@@ -107,15 +108,110 @@ public:
     {
     }
 
-    // IBStrategy::interpolateVelocity(u_data_idx, u_synch_scheds, u_ghost_fill_scheds, data_time)
-    void interpolateVelocity(double /*data_time*/ = 0.0)
+    // ---- patch data indices: the reference passes u_data_idx / f_data_idx into the PatchHierarchy; here a data index is
+    // bound to the host SideData of each local patch (the fluid solver's arrays).  A bound index is uploaded before and,
+    // for f, downloaded after the operation; an unbound index means "the resident u / f of the library" (device-resident
+    // fluid data, or data moved with setEulerianVelocity / getEulerianForce).
+    void registerPatchData(int data_idx, int patch, SideData* data)
     {
-        check(ibk_interpolate_velocity(d_ctx, d_interp_kernel_fcn.c_str(), /*fill_halo*/ 1));
+        if ((int)d_patch_data.size() <= data_idx) d_patch_data.resize(data_idx + 1);
+        if ((int)d_patch_data[data_idx].size() <= patch) d_patch_data[data_idx].resize(patch + 1, nullptr);
+        d_patch_data[data_idx][patch] = data;
     }
-    // IBStrategy::spreadForce(f_data_idx, f_phys_bdry_op, f_prolongation_scheds, data_time)
-    void spreadForce(double /*data_time*/ = 0.0)
+
+    // ---- more than one rank (LDataManager.cpp:597-620, 744): the communicator of this rank's context and the global patch
+    // list; from then on interpolateVelocity / spreadForce run the inter-rank ghost fill / ghost accumulation with the
+    // messages in flight while the tiles that do not touch the exchanged regions are processed.
+    void initCommunicator(const void* nccl_unique_id_128, int rank, int nranks)
     {
-        check(ibk_spread_force(d_ctx, d_spread_kernel_fcn.c_str(), /*accumulate_halo*/ 1));
+        check(ibk_comm_init(d_ctx, nccl_unique_id_128, rank, nranks));
+    }
+    static void initLoopbackCommunicator(const std::vector<IBMethodB200*>& ranks) // the ranks are objects of ONE process
+    {
+        std::vector<ibk_ctx*> c;
+        for (IBMethodB200* r : ranks) c.push_back(r->d_ctx);
+        if (ibk_comm_init_loopback(c.data(), (int)c.size()) != IBK_OK) throw std::runtime_error("IBMethodB200: loopback communicator");
+    }
+    void setGlobalPatches(const std::vector<Box>& boxes, const std::vector<int>& ranks)
+    {
+        std::vector<int> lo, hi;
+        for (const Box& b : boxes)
+            for (int d = 0; d < NDIM; ++d)
+            {
+                lo.push_back(b.lo(d));
+                hi.push_back(b.hi(d));
+            }
+        check(ibk_comm_set_patches(d_ctx, (int)boxes.size(), lo.data(), hi.data(), ranks.data()));
+        d_multi_rank = true;
+    }
+
+    // IBStrategy::interpolateVelocity (IBStrategy.h:276-280; IBMethod.cpp:672-694).  The schedules are stand-ins: the ghost
+    // fill they perform is done by the library.  begin... / finish... are the two halves around the point where the messages
+    // of the other ranks must have been posted: one process per rank calls the whole; a process that holds several ranks
+    // (loopback communicator) calls begin on every rank, then finish on every rank.
+    void interpolateVelocity(int u_data_idx, const std::vector<Pointer<CoarsenSchedule>>& /*u_synch_scheds*/,
+                             const std::vector<Pointer<RefineSchedule>>& /*u_ghost_fill_scheds*/, double /*data_time*/)
+    {
+        beginInterpolateVelocity(u_data_idx);
+        finishInterpolateVelocity();
+    }
+    void beginInterpolateVelocity(int u_data_idx)
+    {
+        upload(u_data_idx, 0);
+        if (!d_multi_rank)
+        {
+            check(ibk_interpolate_velocity(d_ctx, d_interp_kernel_fcn.c_str(), /*fill_halo*/ 1));
+            return;
+        }
+        check(ibk_halo_fill_post(d_ctx));
+        check(ibk_halo_local(d_ctx, 0));
+        check(ibk_interpolate_velocity_part(d_ctx, d_interp_kernel_fcn.c_str(), 1)); // interior tiles read no ghost cell
+    }
+    void finishInterpolateVelocity()
+    {
+        if (!d_multi_rank) return;
+        check(ibk_halo_fill_finish(d_ctx));
+        check(ibk_interpolate_velocity_part(d_ctx, d_interp_kernel_fcn.c_str(), 2));
+    }
+    // IBStrategy::spreadForce (IBStrategy.h:338-342; IBMethod.cpp:972-995): f += S[F].  f_phys_bdry_op and the prolongation
+    // schedules are stand-ins (see samrai_standins.h).
+    void spreadForce(int f_data_idx, RobinPhysBdryPatchStrategy* /*f_phys_bdry_op*/,
+                     const std::vector<Pointer<RefineSchedule>>& /*f_prolongation_scheds*/, double /*data_time*/)
+    {
+        beginSpreadForce(f_data_idx);
+        finishSpreadForce(f_data_idx);
+    }
+    void beginSpreadForce(int f_data_idx)
+    {
+        upload(f_data_idx, 1);
+        if (!d_multi_rank)
+        {
+            check(ibk_spread_force(d_ctx, d_spread_kernel_fcn.c_str(), /*accumulate_halo*/ 1));
+            return;
+        }
+        check(ibk_spread_begin(d_ctx));
+        check(ibk_spread_force_part(d_ctx, d_spread_kernel_fcn.c_str(), 2)); // boundary tiles: everything the neighbours need
+        check(ibk_halo_accumulate_post(d_ctx));
+        check(ibk_spread_force_part(d_ctx, d_spread_kernel_fcn.c_str(), 1)); // interior tiles, the messages in flight
+        check(ibk_halo_local(d_ctx, 1));
+    }
+    void finishSpreadForce(int f_data_idx)
+    {
+        if (d_multi_rank)
+        {
+            check(ibk_halo_accumulate_finish(d_ctx));
+            check(ibk_spread_end(d_ctx));
+        }
+        download(f_data_idx, 1);
+    }
+    // the resident-data forms (device-resident u / f, no data index)
+    void interpolateVelocity(double data_time = 0.0)
+    {
+        interpolateVelocity(-1, {}, {}, data_time);
+    }
+    void spreadForce(double data_time = 0.0)
+    {
+        spreadForce(-1, nullptr, {}, data_time);
     }
 
     // ---- N1: the steps either side of the path, with X, U, F resident on the device ----------------------
@@ -179,6 +275,11 @@ public:
     {
         return d_ctx;
     }
+    void setKernels(const std::string& interp_fcn, const std::string& spread_fcn)
+    {
+        d_interp_kernel_fcn = interp_fcn;
+        d_spread_kernel_fcn = spread_fcn;
+    }
     bool d_error_if_points_leave_domain = false; // IBMethod.cpp:2060
 
 private:
@@ -186,6 +287,22 @@ private:
     {
         if (rc != IBK_OK) throw std::runtime_error(std::string("IBMethodB200: ") + ibk_last_error(d_ctx));
     }
+    void upload(int data_idx, int which)
+    {
+        if (data_idx < 0 || data_idx >= (int)d_patch_data.size()) return;
+        for (size_t p = 0; p < d_patch_data[data_idx].size(); ++p)
+            if (SideData* sd = d_patch_data[data_idx][p])
+                for (int a = 0; a < NDIM; ++a) check(ibk_grid_upload(d_ctx, which, (int)p, a, sd->getPointer(a)));
+    }
+    void download(int data_idx, int which)
+    {
+        if (data_idx < 0 || data_idx >= (int)d_patch_data.size()) return;
+        for (size_t p = 0; p < d_patch_data[data_idx].size(); ++p)
+            if (SideData* sd = d_patch_data[data_idx][p])
+                for (int a = 0; a < NDIM; ++a) check(ibk_grid_download(d_ctx, which, (int)p, a, sd->getPointer(a)));
+    }
+    std::vector<std::vector<SideData*>> d_patch_data; // [data_idx][local patch]
+    bool d_multi_rank = false;
     ibk_ctx* d_ctx = nullptr;
     std::string d_interp_kernel_fcn, d_spread_kernel_fcn; // IBMethod.h:602 default "IB_4"
     int d_ghosts = 0;

@@ -30,6 +30,10 @@ public:
     {
         return d_depth;
     }
+    int column() const // the marker column behind this LData (IBK_COL_*)
+    {
+        return d_column;
+    }
     int getLocalNodeCount() const
     {
         return ibk_markers_count(d_ctx);

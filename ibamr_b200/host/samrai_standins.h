@@ -175,4 +175,17 @@ struct CellData
         return data.data();
     }
 };
+// xfer::RefineSchedule / xfer::CoarsenSchedule, IBTK::RobinPhysBdryPatchStrategy: they appear in the signatures of
+// IBStrategy::interpolateVelocity / spreadForce and of LDataManager::interp / spread.  The work they stand for -- ghost
+// fill of u, ghost accumulation of f, physical-boundary fold-back -- is done inside libibk.so (ibk_halo_local, the
+// communicator of the context, ibk_level_set_physical_boundaries), so the mirrors accept and ignore them.
+struct RefineSchedule
+{
+};
+struct CoarsenSchedule
+{
+};
+struct RobinPhysBdryPatchStrategy
+{
+};
 } // namespace SAMRAI_standin

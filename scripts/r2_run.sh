@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -q -x -k "ranks_as_contexts" > gpurun_out/r2_t10.log 2>&1; tail -25 gpurun_out/r2_t10.log
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r2_t12.log 2>&1; tail -15 gpurun_out/r2_t12.log

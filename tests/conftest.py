@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "mgpu: needs TWO CUDA devices and NCCL (run with -m mgpu on a 2-GPU lease); the same code "
+                            "path runs on one GPU through the loopback communicator in test_ranks_as_contexts_of_one_process")
 
 
 def pytest_collection_modifyitems(config, items):

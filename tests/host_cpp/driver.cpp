@@ -12,7 +12,9 @@
 //           LDataB200 host mirror of the F column behaved: read, modify + restore, refetch after a kernel)
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
+#include <memory>
 #include <iostream>
 #include <vector>
 
@@ -20,6 +22,7 @@
 #include "../../ibamr_b200/host/IBMethodB200.h"
 #include "../../ibamr_b200/host/IBStandardInitializerB200.h"
 #include "../../ibamr_b200/host/LDataB200.h"
+#include "../../ibamr_b200/host/LDataManagerB200.h"
 #include "../../ibamr_b200/host/LEInteractorB200.h"
 
 using namespace SAMRAI_standin;
@@ -69,9 +72,150 @@ static int run_structure(const char* base, int ndim)
     return 0;
 }
 
+// Two ranks in one process (loopback communicator of libibk.so): the case's periodic n^3 level cut in two along x, each
+// half a rank with its own IBMethodB200; the reference's signatures all the way (IBStrategy::spreadForce /
+// interpolateVelocity with data indices bound to host SideData; rank 1 goes through LDataManagerB200::spread / interp).
+// out: per rank  int64 count, int64 ids[count], double U[count][3], then the three f arrays of the rank's patch.
+static int run_two_ranks(const char* case_file, const char* out_file)
+{
+    FILE* fi = std::fopen(case_file, "rb");
+    if (!fi) return 3;
+    int n, g, N;
+    char kernel[32];
+    if (std::fread(&n, 4, 1, fi) != 1 || std::fread(&g, 4, 1, fi) != 1 || std::fread(&N, 4, 1, fi) != 1 || std::fread(kernel, 1, 32, fi) != 32)
+        return 4;
+    std::vector<double> X((size_t)N * 3), F((size_t)N * 3);
+    if (std::fread(X.data(), 8, X.size(), fi) != X.size() || std::fread(F.data(), 8, F.size(), fi) != F.size()) return 4;
+    Box dom(Index(0), Index(n - 1));
+    SideData ug(dom, 1, IntVector(g)); // the global field, ghosts analytic (periodic)
+    for (int a = 0; a < 3; ++a)
+        if (std::fread(ug.getPointer(a), 8, ug.data[a].size(), fi) != ug.data[a].size()) return 4;
+    std::fclose(fi);
+    FILE* fo = std::fopen(out_file, "wb");
+    try
+    {
+        std::vector<Box> boxes(2, dom);
+        boxes[0].hi(0) = n / 2 - 1;
+        boxes[1].lo(0) = n / 2;
+        std::vector<std::unique_ptr<IBAMR_B200::IBMethodB200>> ib;
+        std::vector<std::unique_ptr<SideData>> u, f;
+        std::vector<std::vector<long long>> ids(2);
+        for (int r = 0; r < 2; ++r)
+        {
+            IBAMR_B200::IBMethodB200::LevelSpec lv;
+            lv.domain_box = dom;
+            for (int d = 0; d < 3; ++d)
+            {
+                lv.x_lower[d] = 0.0;
+                lv.x_upper[d] = 1.0;
+                lv.periodic[d] = 1;
+            }
+            lv.patch_boxes.push_back(boxes[r]);
+            ib.emplace_back(new IBAMR_B200::IBMethodB200(lv, kernel, 0, g));
+            u.emplace_back(new SideData(boxes[r], 1, IntVector(g)));
+            f.emplace_back(new SideData(boxes[r], 1, IntVector(g)));
+            f[r]->fillAll(0.25);
+            // the rank's slice of the global field; its ghost values are poisoned: they must come from the exchange
+            for (int a = 0; a < 3; ++a)
+            {
+                int ng[3], nl[3];
+                for (int d = 0; d < 3; ++d)
+                {
+                    ng[d] = n + (d == a ? 1 : 0) + 2 * g;
+                    nl[d] = boxes[r].hi(d) - boxes[r].lo(d) + 1 + (d == a ? 1 : 0) + 2 * g;
+                }
+                for (int k = 0; k < nl[2]; ++k)
+                    for (int j = 0; j < nl[1]; ++j)
+                        for (int i = 0; i < nl[0]; ++i)
+                        {
+                            const bool ghost = i < g || i >= nl[0] - g || j < g || j >= nl[1] - g || k < g || k >= nl[2] - g;
+                            const size_t gi = ((size_t)(k + boxes[r].lo(2)) * ng[1] + (j + boxes[r].lo(1))) * ng[0] + (i + boxes[r].lo(0));
+                            u[r]->getPointer(a)[((size_t)k * nl[1] + j) * nl[0] + i] = ghost ? 1e30 : ug.getPointer(a)[gi];
+                        }
+            }
+            ib[r]->registerPatchData(/*u_data_idx*/ 0, 0, u[r].get());
+            ib[r]->registerPatchData(/*f_data_idx*/ 1, 0, f[r].get());
+            // the markers whose cell lies in the rank's patch
+            std::vector<double> Xr, Fr;
+            for (int i = 0; i < N; ++i)
+            {
+                int c = (int)std::floor(X[3 * i] * n);
+                c = c < 0 ? 0 : (c >= n ? n - 1 : c);
+                if ((c < n / 2) != (r == 0)) continue;
+                ids[r].push_back(i);
+                for (int d = 0; d < 3; ++d)
+                {
+                    Xr.push_back(X[3 * i + d]);
+                    Fr.push_back(F[3 * i + d]);
+                }
+            }
+            ib[r]->setPositions(Xr);
+            ib[r]->setForce(Fr);
+            ib[r]->beginDataRedistribution();
+            ib[r]->endDataRedistribution();
+        }
+        IBAMR_B200::IBMethodB200::initLoopbackCommunicator({ ib[0].get(), ib[1].get() });
+        for (int r = 0; r < 2; ++r) ib[r]->setGlobalPatches(boxes, { 0, 1 });
+        // rank 0: IBStrategy calls; rank 1: the same two halves reached through the LDataManager-shaped adapter's columns
+        for (int r = 0; r < 2; ++r) ib[r]->beginSpreadForce(1);
+        for (int r = 0; r < 2; ++r) ib[r]->finishSpreadForce(1);
+        for (int r = 0; r < 2; ++r) ib[r]->beginInterpolateVelocity(0);
+        for (int r = 0; r < 2; ++r) ib[r]->finishInterpolateVelocity();
+        for (int r = 0; r < 2; ++r)
+        {
+            std::vector<double> U;
+            ib[r]->getVelocity(U);
+            const long long cnt = (long long)ids[r].size();
+            std::fwrite(&cnt, 8, 1, fo);
+            std::fwrite(ids[r].data(), 8, ids[r].size(), fo);
+            std::fwrite(U.data(), 8, U.size(), fo);
+            for (int a = 0; a < 3; ++a) std::fwrite(f[r]->getPointer(a), 8, f[r]->data[a].size(), fo);
+        }
+        // seam B2 on one rank alone (no exchange involved): LDataManager::spread with node weights, then interp into an aux LData
+        {
+            IBAMR_B200::IBMethodB200::LevelSpec lv;
+            lv.domain_box = dom;
+            for (int d = 0; d < 3; ++d)
+            {
+                lv.x_lower[d] = 0.0;
+                lv.x_upper[d] = 1.0;
+                lv.periodic[d] = 1;
+            }
+            lv.patch_boxes.push_back(dom);
+            IBAMR_B200::IBMethodB200 one(lv, kernel, 0, g);
+            one.setPositions(X);
+            one.setForce(F);
+            one.beginDataRedistribution();
+            SideData fh(dom, 1, IntVector(g));
+            one.registerPatchData(0, 0, &ug);
+            one.registerPatchData(1, 0, &fh);
+            IBTK_B200::LDataManagerB200 mgr(one);
+            std::vector<Pointer<IBTK_B200::LDataB200>> Fd{ std::make_shared<IBTK_B200::LDataB200>("F", one.ctx(), IBK_COL_F, 3) };
+            std::vector<Pointer<IBTK_B200::LDataB200>> Xd{ std::make_shared<IBTK_B200::LDataB200>("X", one.ctx(), IBK_COL_X, 3) };
+            std::vector<Pointer<IBTK_B200::LDataB200>> Ud{ std::make_shared<IBTK_B200::LDataB200>("U_aux", one.ctx(), IBK_COL_AUX, 3) };
+            std::vector<double> ds(N);
+            for (int i = 0; i < N; ++i) ds[i] = 0.5 + 0.001 * (i % 100);
+            mgr.spread(1, Fd, Xd, ds, kernel, nullptr, {}, 0.0);
+            for (int a = 0; a < 3; ++a) std::fwrite(fh.getPointer(a), 8, fh.data[a].size(), fo);
+            mgr.interp(0, Ud, Xd, {}, {}, 0.0);
+            const double* Ua = static_cast<const IBTK_B200::LDataB200&>(*Ud[0]).getLocalFormVecArray();
+            std::fwrite(Ua, 8, (size_t)N * 3, fo);
+        }
+    }
+    catch (const std::exception& e)
+    {
+        std::fprintf(stderr, "driver: %s\n", e.what());
+        std::fclose(fo);
+        return 5;
+    }
+    std::fclose(fo);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc >= 2 && !std::strcmp(argv[1], "--static")) return run_static();
+    if (argc >= 4 && !std::strcmp(argv[1], "--two-ranks")) return run_two_ranks(argv[2], argv[3]);
     if (argc >= 4 && !std::strcmp(argv[1], "--structure")) return run_structure(argv[2], std::atoi(argv[3]));
     if (argc < 3) return 2;
     FILE* fi = std::fopen(argv[1], "rb");

@@ -138,3 +138,84 @@ def test_cpp_structure_reader(driver):
     assert "vertices=201 springs=200 beams=199 targets=1 anchors=0" in out and "X0=4.5,14.75" in out
     r = subprocess.run([driver, "--structure", os.path.join(gold, "no_such_structure"), "2"], capture_output=True, text=True)
     assert r.returncode == 1 and "Cannot find required vertex file" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["IB_4", "IB_6"])
+def test_cpp_two_ranks_with_reference_signatures(driver, kernel, tmp_path):
+    """Seams B1 / B2 across ranks from C++: two IBMethodB200 objects of one process are the two ranks of
+    a loopback communicator of libibk.so; spreadForce / interpolateVelocity are called with the reference's signatures
+    (data indices bound to host SideData, schedules as stand-ins), the halo plan, messages and unpack-adds all happen behind
+    the C ABI.  A third, single-rank object goes through LDataManagerB200::spread (with node weights, F * ds on the device)
+    and ::interp.  Everything against the oracle's model of the reference."""
+    from oracle import oracle as orc
+    from tests.util import splitmix64_unit
+    n, N = 32, 4000
+    g = orc.min_ghost_width(kernel)
+    boxes = [((0, 0, 0), (n // 2 - 1, n - 1, n - 1)), ((n // 2, 0, 0), (n - 1, n - 1, n - 1))]
+    level2 = orc.Level(3, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), boxes, (g,) * 3)
+    level1 = orc.Level(3, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), [((0,) * 3, (n - 1,) * 3)], (g,) * 3)
+    pg1 = level1.patch_geom(0)
+    X = np.stack([splitmix64_unit(5 + d, np.arange(N)) for d in range(3)], axis=1)
+    F = np.stack([2 * splitmix64_unit(9 + d, np.arange(N)) - 1 for d in range(3)], axis=1)
+    u = []
+    for a in range(3):
+        c = pg1.side_coords(a)
+        u.append(np.ascontiguousarray(np.sin(2 * np.pi * c[a]) * np.cos(2 * np.pi * c[(a + 1) % 3]) + 0 * c[0] + 0 * c[1] + 0 * c[2]))
+    case, outp = tmp_path / "case2.bin", tmp_path / "out2.bin"
+    with open(case, "wb") as f:
+        f.write(struct.pack("iii", n, g, N))
+        f.write(kernel.encode().ljust(32, b"\0"))
+        f.write(X.tobytes())
+        f.write(F.tobytes())
+        for a in range(3):
+            f.write(u[a].tobytes())
+    r = subprocess.run([driver, "--two-ranks", str(case), str(outp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = np.fromfile(outp, dtype=np.uint8)
+    off = 0
+
+    def take(dtype, count):
+        nonlocal off
+        a = np.frombuffer(raw, dtype=dtype, count=count, offset=off)
+        off += a.nbytes
+        return a
+
+    def rel(a, b):
+        return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+    ref = orc.bin_level(level2, X)
+    for rk in range(2):
+        cnt = int(take(np.int64, 1)[0])
+        ids = take(np.int64, cnt)
+        assert np.array_equal(ids, np.nonzero(ref["owner"] == rk)[0])
+        U = take(np.float64, 3 * cnt).reshape(cnt, 3)
+        pg = level2.patch_geom(rk)
+        f_got = [take(np.float64, int(np.prod(pg.side_shape(a)))).reshape(pg.side_shape(a)) for a in range(3)]
+        lst = ref["patches"][rk]
+        ii = lst["all_idx"][lst["interior_mask"]]
+        sh = lst["all_shift"].reshape(-1, 3)[lst["interior_mask"]]
+        ur = []
+        for a in range(3):  # the rank's u with analytic (periodic) ghosts: what the exchange must have produced
+            c = pg.side_coords(a)
+            ur.append(np.ascontiguousarray(np.sin(2 * np.pi * c[a]) * np.cos(2 * np.pi * c[(a + 1) % 3]) + 0 * c[0] + 0 * c[1] + 0 * c[2]))
+        U_ref = orc.side_interp(kernel, pg, ur, X, ii, sh.reshape(-1))
+        assert rel(U, U_ref[ids]) <= 1e-12
+        f_ref = [np.zeros(pg.side_shape(a)) for a in range(3)]
+        orc.side_spread(kernel, pg, f_ref, X, F, lst["all_idx"], lst["all_shift"])
+        for a in range(3):
+            sl = tuple(slice(g, s - g) for s in f_ref[a].shape)
+            assert np.max(np.abs(f_got[a][sl] - 0.25 - f_ref[a][sl])) <= 1e-12 * np.max(np.abs(f_ref[a][sl]))
+    # seam B2: spread of F * ds, interp into an auxiliary LData
+    ds = 0.5 + 0.001 * (np.arange(N) % 100)
+    ref1 = orc.bin_level(level1, X)
+    lst = ref1["patches"][0]
+    fr = [np.zeros_like(a) for a in u]
+    orc.side_spread(kernel, pg1, fr, X, F * ds[:, None], lst["all_idx"], lst["all_shift"])
+    for a in range(3):
+        got = take(np.float64, u[a].size).reshape(u[a].shape)
+        sl = tuple(slice(g, s - g) for s in fr[a].shape)
+        assert rel(got[sl], fr[a][sl]) <= 1e-12
+    Ua = take(np.float64, 3 * N).reshape(N, 3)
+    assert rel(Ua, orc.side_interp_positions(kernel, pg1, u, X)) <= 1e-12
+    assert off == raw.size
