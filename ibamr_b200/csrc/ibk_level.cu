@@ -37,7 +37,6 @@ void make_tile_params(TileParams& tp, int ndim, const double* dx, const double x
 // halo kernels
 // ---------------------------------------------------------------------------------------------
 constexpr int HALO_MAXSRC = 64;
-constexpr int HALO_FILTER_DEFAULT = 1; // measured: 0.19 ms less per step on the C5 shard (IBK_HALO_FILTER=0: every source tested per element)
 struct HaloSrc
 {
     const double* ptr;
@@ -56,211 +55,101 @@ struct HaloArgs
     int ilo[3], ihi[3]; // interior (side) box of the destination
     int rim;            // ghost width (thickness of the interior rim that ghosts of others can reach)
     int nsrc;
-    int filter; // 1: the kernels first narrow the sources down to those that can reach their slab
     HaloSrc src[HALO_MAXSRC];
 };
 
-// Enumerates `outer \ inner` as up to 6 slabs (blockIdx.y selects the slab).
-__device__ __forceinline__ bool slab_box(int ndim, int slab, const int* olo, const int* ohi, const int* ilo, const int* ihi,
-                                         int* lo, int* hi)
+// Walks a slab row by row: a warp takes one row (contiguous in x) and calls f(I1, I2, x_first, x_last) with x advancing by
+// the lane stride 32 (coalesced 256-byte accesses, the row's index arithmetic done once per row); thin slabs (the x ghost
+// layers, a few elements per row) are walked with 32 / e0 rows per warp, one element per lane.
+template <class F>
+__device__ __forceinline__ void slab_rows(const int* lo, const int* hi, unsigned bx, unsigned nbx, F f)
 {
-    // slab order: (dim ndim-1 low, high), ..., (dim 0 low, high); dims above the slab's dim are
-    // restricted to the inner range so the slabs are disjoint
-    const int d = ndim - 1 - slab / 2;
-    const int side = slab & 1;
-    if (d < 0) return false;
-    for (int e = 0; e < 3; ++e)
+    const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    const long long nrows = (long long)e1 * e2;
+    if (e0 >= 16)
     {
-        if (e >= ndim)
+        // work item = (row, chunk of 128 elements): a slab of a few long rows (the z ghost layers: 3 x 518 rows of 519) still
+        // spreads over thousands of warps, each with four independent elements per lane in flight
+        constexpr int CHUNK = 128;
+        const int nch = (e0 + CHUNK - 1) / CHUNK;
+        const long long nitems = nrows * nch;
+        for (long long it = (long long)bx * wpb + warp; it < nitems; it += (long long)nbx * wpb)
         {
-            lo[e] = hi[e] = 0;
+            const long long row = it / nch;
+            const int ch = (int)(it - row * nch);
+            const int k = (int)(row / e1);
+            const int xs = lo[0] + ch * CHUNK;
+            f(lo[1] + (int)(row - (long long)k * e1), lo[2] + k, xs + lane, min(hi[0], xs + CHUNK - 1));
         }
-        else if (e > d)
-        {
-            lo[e] = max(olo[e], ilo[e]);
-            hi[e] = min(ohi[e], ihi[e]);
-        }
-        else if (e == d)
-        {
-            if (side == 0)
-            {
-                lo[e] = olo[e];
-                hi[e] = min(ohi[e], ilo[e] - 1);
-            }
-            else
-            {
-                lo[e] = max(olo[e], ihi[e] + 1);
-                hi[e] = ohi[e];
-            }
-        }
-        else
-        {
-            lo[e] = olo[e];
-            hi[e] = ohi[e];
-        }
-        if (hi[e] < lo[e]) return false;
-    }
-    return true;
-}
-
-
-// The sources of a halo operation that can reach a slab at all, in canonical order (one warp tests them; a periodic
-// single patch has 26 images of itself, a z slab meets 9 of them, an x slab one).
-template <bool INTERIOR>
-__device__ __forceinline__ int slab_sources(const HaloArgs& A, const int* lo, const int* hi, unsigned char* list)
-{
-    __shared__ int n_out;
-    if (!A.filter)
-    {
-        if (threadIdx.x < A.nsrc) list[threadIdx.x] = (unsigned char)threadIdx.x;
-        __syncthreads();
-        return A.nsrc;
-    }
-    if (threadIdx.x < 32)
-    {
-        const int lane = threadIdx.x;
-        int n = 0;
-        for (int base = 0; base < A.nsrc; base += 32)
-        {
-            const int s = base + lane;
-            bool hit = false;
-            if (s < A.nsrc)
-            {
-                const HaloSrc& S = A.src[s];
-                hit = true;
-                for (int d = 0; d < 3; ++d)
-                {
-                    const int slo = INTERIOR ? S.ilo[d] : S.alo[d], shi = INTERIOR ? S.ihi[d] : S.ahi[d];
-                    hit = hit && max(lo[d], slo) <= min(hi[d], shi);
-                }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (hit) list[n + __popc(m & ((1u << lane) - 1u))] = (unsigned char)s;
-            n += __popc(m);
-        }
-        if (lane == 0) n_out = n;
-    }
-    __syncthreads();
-    return n_out;
-}
-// element q of a slab of extents (e0, e1, .): 32-bit arithmetic whenever the slab allows it
-__device__ __forceinline__ void slab_coords(long long q, bool small, int e0, int e1, int& i0, int& i1, int& i2)
-{
-    if (small)
-    {
-        const unsigned qq = (unsigned)q, t = qq / (unsigned)e0;
-        i0 = (int)(qq - t * (unsigned)e0);
-        i2 = (int)(t / (unsigned)e1);
-        i1 = (int)(t - (unsigned)i2 * (unsigned)e1);
     }
     else
     {
-        i0 = (int)(q % e0);
-        const long long t = q / e0;
-        i1 = (int)(t % e1);
-        i2 = (int)(t / e1);
+        const int rpw = 32 / e0, r = lane / e0, x = lo[0] + lane - r * e0;
+        for (long long g = (long long)bx * wpb + warp; g * rpw < nrows; g += (long long)nbx * wpb)
+        {
+            const long long row = g * rpw + r;
+            if (r >= rpw || row >= nrows) continue;
+            const int k = (int)(row / e1);
+            f(lo[1] + (int)(row - (long long)k * e1), lo[2] + k, x, x);
+        }
     }
 }
 
-// u ghost fill: every ghost element of dst takes the value of the first source whose INTERIOR holds it.
-__global__ void halo_fill_kernel(const HaloArgs* __restrict__ argp)
+// The local halo operations as lists of box operations worked out once per level (build_halo_plan):
+//   MODE 0  dst box <- src box                      ghost fill of u
+//   MODE 1  dst box += src_0 box + src_1 box + ...   ghost accumulation of f: the sources of a box in canonical order
+//   MODE 2  dst box = 0                              ghost regions of f before a spread
+// No per-element tests.  The CTAs of a launch are dealt out to the items in proportion to their size (block0 / nblocks),
+// a warp walks a row (or a few short rows) of its item.
+constexpr int REGION_MAXSRC = 8;
+struct RegionMulti
 {
-    const HaloArgs& A = *argp;
-    int lo[3], hi[3];
-    if (!slab_box(A.ndim, blockIdx.y, A.alo, A.ahi, A.ilo, A.ihi, lo, hi)) return;
-    const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
-    const long long total = (long long)e0 * e1 * e2;
-    __shared__ unsigned char cand[HALO_MAXSRC];
-    const int ncand = slab_sources<true>(A, lo, hi, cand);
-    const bool small = total < (1ll << 31);
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    double* dst;
+    long long dst_pitch;
+    int dst_n1;
+    int dst_off[3], ext[3];
+    int nsrc;
+    unsigned block0, nblocks;
+    const double* src[REGION_MAXSRC];
+    long long src_pitch[REGION_MAXSRC];
+    int src_n1[REGION_MAXSRC];
+    int src_off[REGION_MAXSRC][3];
+};
+template <int MODE>
+__global__ void region_items_kernel(const RegionMulti* __restrict__ items, int n_items)
+{
+    int lo_i = 0, hi_i = n_items - 1; // the item this CTA belongs to: the last one with block0 <= blockIdx.x
+    while (lo_i < hi_i)
     {
-        int I0, I1, I2;
-        slab_coords(q, small, e0, e1, I0, I1, I2);
-        I0 += lo[0];
-        I1 += lo[1];
-        I2 += lo[2];
-        for (int c = 0; c < ncand; ++c)
+        const int mid = (lo_i + hi_i + 1) >> 1;
+        if (items[mid].block0 <= blockIdx.x) lo_i = mid;
+        else hi_i = mid - 1;
+    }
+    const RegionMulti& r = items[lo_i];
+    const int lo[3] = { 0, 0, 0 }, hi[3] = { r.ext[0] - 1, r.ext[1] - 1, r.ext[2] - 1 };
+    slab_rows(lo, hi, blockIdx.x - r.block0, r.nblocks, [&](int j, int k, int x0, int x1) {
+        double* drow = r.dst + ((long long)(r.dst_off[2] + k) * r.dst_n1 + (r.dst_off[1] + j)) * r.dst_pitch + r.dst_off[0];
+        if (MODE == 2)
         {
-            const HaloSrc& S = A.src[cand[c]];
-            if (I0 >= S.ilo[0] && I0 <= S.ihi[0] && I1 >= S.ilo[1] && I1 <= S.ihi[1] && I2 >= S.ilo[2] && I2 <= S.ihi[2])
+            for (int x = x0; x <= x1; x += 32) drow[x] = 0.0;
+            return;
+        }
+        const double* srow[REGION_MAXSRC];
+        for (int c = 0; c < r.nsrc; ++c)
+            srow[c] = r.src[c] + ((long long)(r.src_off[c][2] + k) * r.src_n1[c] + (r.src_off[c][1] + j)) * r.src_pitch[c] + r.src_off[c][0];
+        for (int x = x0; x <= x1; x += 32)
+        {
+            if (MODE == 0)
+                drow[x] = srow[0][x];
+            else
             {
-                const double v = S.ptr[((long long)(I2 - S.alo[2]) * S.n1 + (I1 - S.alo[1])) * S.pitch + (I0 - S.alo[0])];
-                A.dst[((long long)(I2 - A.alo[2]) * A.n1 + (I1 - A.alo[1])) * A.pitch + (I0 - A.alo[0])] = v;
-                break;
+                double acc = drow[x];
+                for (int c = 0; c < r.nsrc; ++c) acc += srow[c][x];
+                drow[x] = acc;
             }
         }
-    }
-}
-
-// f ghost accumulation: every interior element of dst within `rim` of the interior boundary adds the
-// GHOST copies other arrays (or periodic images of itself) hold of it, sources in canonical order.
-__global__ void halo_accum_kernel(const HaloArgs* __restrict__ argp)
-{
-    const HaloArgs& A = *argp;
-    int inlo[3], inhi[3], lo[3], hi[3];
-    for (int d = 0; d < 3; ++d)
-    {
-        inlo[d] = A.ilo[d] + (d < A.ndim ? A.rim : 0);
-        inhi[d] = A.ihi[d] - (d < A.ndim ? A.rim : 0);
-        if (d < A.ndim && inhi[d] < inlo[d])
-        {
-            // interior thinner than two rims: the whole interior is rim; make the inner box empty
-            inlo[d] = A.ihi[d] + 1;
-            inhi[d] = A.ihi[d];
-        }
-    }
-    // when the inner box is empty along some dim, slab "low" of that dim covers everything
-    if (!slab_box(A.ndim, blockIdx.y, A.ilo, A.ihi, inlo, inhi, lo, hi)) return;
-    const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
-    const long long total = (long long)e0 * e1 * e2;
-    __shared__ unsigned char cand[HALO_MAXSRC];
-    const int ncand = slab_sources<false>(A, lo, hi, cand);
-    if (ncand == 0) return;
-    const bool small = total < (1ll << 31);
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
-    {
-        int I0, I1, I2;
-        slab_coords(q, small, e0, e1, I0, I1, I2);
-        I0 += lo[0];
-        I1 += lo[1];
-        I2 += lo[2];
-        double* p = A.dst + ((long long)(I2 - A.alo[2]) * A.n1 + (I1 - A.alo[1])) * A.pitch + (I0 - A.alo[0]);
-        double acc = *p;
-        bool any = false;
-        for (int c = 0; c < ncand; ++c)
-        {
-            const HaloSrc& S = A.src[cand[c]];
-            const bool in_arr = I0 >= S.alo[0] && I0 <= S.ahi[0] && I1 >= S.alo[1] && I1 <= S.ahi[1] && I2 >= S.alo[2] && I2 <= S.ahi[2];
-            if (!in_arr) continue;
-            const bool in_int = I0 >= S.ilo[0] && I0 <= S.ihi[0] && I1 >= S.ilo[1] && I1 <= S.ihi[1] && I2 >= S.ilo[2] && I2 <= S.ihi[2];
-            if (in_int) continue; // interior copies of shared faces are summed by face_sync_kernel
-            acc += S.ptr[((long long)(I2 - S.alo[2]) * S.n1 + (I1 - S.alo[1])) * S.pitch + (I0 - S.alo[0])];
-            any = true;
-        }
-        if (any) *p = acc;
-    }
-}
-
-// f ghosts are scratch for the spread: LDataManager::spread zeroes them (setToScalar(f, 0,
-// interior_only = false), LDataManager.cpp:594) before anything is spread into them.
-__global__ void halo_zero_ghost_kernel(const HaloArgs* __restrict__ argp)
-{
-    const HaloArgs& A = *argp;
-    int lo[3], hi[3];
-    if (!slab_box(A.ndim, blockIdx.y, A.alo, A.ahi, A.ilo, A.ihi, lo, hi)) return;
-    const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
-    const long long total = (long long)e0 * e1 * e2;
-    const bool small = total < (1ll << 31);
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
-    {
-        int I0, I1, I2;
-        slab_coords(q, small, e0, e1, I0, I1, I2);
-        I0 += lo[0];
-        I1 += lo[1];
-        I2 += lo[2];
-        A.dst[((long long)(I2 - A.alo[2]) * A.n1 + (I1 - A.alo[1])) * A.pitch + (I0 - A.alo[0])] = 0.0;
-    }
+    });
 }
 
 struct FacePair
@@ -295,9 +184,17 @@ __global__ void face_sync_kernel(const FacePair* __restrict__ pairs)
 // take part in the face/ghost sums (the reference spreads into a zeroed f and adds the old f to the
 // interiors afterwards, LDataManager.cpp:589-594, 662-663): park it, zero the layers, restore-add later.
 // mode 0: save + zero, mode 1: layer += saved.
-__global__ void face_layers_kernel(const HaloArgs* __restrict__ argp, int axis, double* __restrict__ save, int mode)
+struct FaceLayerJob
 {
-    const HaloArgs& A = *argp;
+    const HaloArgs* args;
+    int axis;
+    double* save;
+};
+__global__ void face_layers_kernel(const FaceLayerJob* __restrict__ jobs, int mode)
+{
+    const HaloArgs& A = *jobs[blockIdx.y].args;
+    const int axis = jobs[blockIdx.y].axis;
+    double* __restrict__ save = jobs[blockIdx.y].save;
     int ext[3];
     for (int d = 0; d < 3; ++d) ext[d] = (d == axis) ? 1 : (A.ihi[d] - A.ilo[d] + 1);
     const long long per = (long long)ext[0] * ext[1] * ext[2];
@@ -372,6 +269,16 @@ struct HaloPlan
     std::vector<int> n_pairs;
     std::vector<double*> d_face_save; // [patch][axis]: 2 boundary layers of f's axis-normal component
     std::vector<void*> allocs;
+    // box operations of the whole level: [0] ghost fill of u, [1] ghost accumulation of f (in waves: the items of a wave
+    // write disjoint elements, the waves follow the canonical source order), [2] zero of the ghost regions of f
+    RegionMulti* d_ops[3] = { nullptr, nullptr, nullptr };
+    int n_ops[3] = { 0, 0, 0 };
+    unsigned n_blocks[3] = { 0, 0, 0 };
+    FacePair* d_all_pairs = nullptr; // the face pairs of all axes (one launch)
+    int n_all_pairs = 0;
+    FaceLayerJob* d_face_jobs = nullptr; // [patch][axis]
+    int n_face_jobs = 0;
+    unsigned face_job_blocks = 1;
 };
 // device copy of the item table of one message (ibk_halo_pack_many / _unpack_many), keyed by its content
 struct ItemTable
@@ -433,6 +340,61 @@ static void side_geom(const LevelState& lv, const PatchState& ps, int axis, int*
     }
 }
 
+namespace
+{
+struct HBox
+{
+    int lo[3], hi[3];
+};
+bool hbox_intersect(const HBox& a, const HBox& b, HBox& r)
+{
+    for (int d = 0; d < 3; ++d)
+    {
+        r.lo[d] = std::max(a.lo[d], b.lo[d]);
+        r.hi[d] = std::min(a.hi[d], b.hi[d]);
+        if (r.hi[d] < r.lo[d]) return false;
+    }
+    return true;
+}
+// a \ b as disjoint boxes (highest dimension first)
+void hbox_minus(const HBox& a, const HBox& b, std::vector<HBox>& out)
+{
+    HBox in;
+    if (!hbox_intersect(a, b, in))
+    {
+        out.push_back(a);
+        return;
+    }
+    HBox cur = a;
+    for (int d = 2; d >= 0; --d)
+    {
+        if (cur.lo[d] < in.lo[d])
+        {
+            HBox p = cur;
+            p.hi[d] = in.lo[d] - 1;
+            out.push_back(p);
+        }
+        if (cur.hi[d] > in.hi[d])
+        {
+            HBox p = cur;
+            p.lo[d] = in.hi[d] + 1;
+            out.push_back(p);
+        }
+        cur.lo[d] = in.lo[d];
+        cur.hi[d] = in.hi[d];
+    }
+}
+// warp work items of a region (as slab_rows cuts it)
+long long region_work(const int* ext)
+{
+    const long long rows = (long long)ext[1] * ext[2];
+    if (ext[0] >= 16) return rows * ((ext[0] + 127) / 128);
+    const int rpw = 32 / std::max(ext[0], 1);
+    return (rows + rpw - 1) / rpw;
+}
+} // namespace
+
+static unsigned halo_blocks(const LevelState& lv, const PatchState& ps, int axis);
 static int build_halo_plan(ibk_ctx* ctx)
 {
     LevelState& lv = ctx->lv;
@@ -442,6 +404,9 @@ static int build_halo_plan(ibk_ctx* ctx)
     int N[3] = { 1, 1, 1 };
     for (int d = 0; d < ndim; ++d) N[d] = lv.domain_upper[d] - lv.domain_lower[d] + 1;
     for (int which = 0; which < 2; ++which) hp.d_args[which].assign((size_t)P * ndim, nullptr);
+    std::vector<RegionMulti> ops[3]; // fill, accumulate, zero (all patches and axes)
+    std::vector<FacePair> all_pairs;
+    std::vector<FaceLayerJob> face_jobs;
     hp.d_face_save.assign((size_t)P * ndim, nullptr);
     hp.d_pairs.assign(ndim, nullptr);
     hp.n_pairs.assign(ndim, 0);
@@ -462,10 +427,6 @@ static int build_halo_plan(ibk_ctx* ctx)
                 A.n1 = ps.n[axis][1];
                 A.ndim = ndim;
                 A.rim = 0;
-                {
-                    static const char* env = getenv("IBK_HALO_FILTER"); // 0 / 1 overrides the default
-                    A.filter = env ? (atoi(env) != 0) : HALO_FILTER_DEFAULT;
-                }
                 for (int d = 0; d < 3; ++d)
                 {
                     A.alo[d] = alo[d];
@@ -554,6 +515,126 @@ static int build_halo_plan(ibk_ctx* ctx)
                                 }
                             }
                 }
+                // ---- the same operations as box lists (region_items_kernel)
+                {
+                    HBox arr, inter;
+                    for (int d = 0; d < 3; ++d)
+                    {
+                        arr.lo[d] = alo[d];
+                        arr.hi[d] = ahi[d];
+                        inter.lo[d] = ilo[d];
+                        inter.hi[d] = ihi[d];
+                    }
+                    auto make_op = [&](const HBox& r) {
+                        RegionMulti op;
+                        std::memset(&op, 0, sizeof(op));
+                        op.dst = A.dst;
+                        op.dst_pitch = A.pitch;
+                        op.dst_n1 = A.n1;
+                        for (int d = 0; d < 3; ++d)
+                        {
+                            op.dst_off[d] = r.lo[d] - alo[d];
+                            op.ext[d] = r.hi[d] - r.lo[d] + 1;
+                        }
+                        return op;
+                    };
+                    auto add_src = [&](RegionMulti& op, const HBox& r, const HaloSrc& S) {
+                        const int c = op.nsrc++;
+                        op.src[c] = S.ptr;
+                        op.src_pitch[c] = S.pitch;
+                        op.src_n1[c] = S.n1;
+                        for (int d = 0; d < 3; ++d) op.src_off[c][d] = r.lo[d] - S.alo[d];
+                    };
+                    std::vector<HBox> ghost;
+                    hbox_minus(arr, inter, ghost);
+                    if (which == 0)
+                    {
+                        // fill: every ghost element from the FIRST source whose interior holds it: what a source covers is taken
+                        // out of the remaining region
+                        std::vector<HBox> remaining = ghost;
+                        for (int sidx = 0; sidx < A.nsrc && !remaining.empty(); ++sidx)
+                        {
+                            const HaloSrc& S = A.src[sidx];
+                            HBox sint;
+                            for (int d = 0; d < 3; ++d)
+                            {
+                                sint.lo[d] = S.ilo[d];
+                                sint.hi[d] = S.ihi[d];
+                            }
+                            std::vector<HBox> next;
+                            for (const HBox& R : remaining)
+                            {
+                                HBox I;
+                                if (!hbox_intersect(R, sint, I))
+                                {
+                                    next.push_back(R);
+                                    continue;
+                                }
+                                RegionMulti op = make_op(I);
+                                add_src(op, I, S);
+                                ops[0].push_back(op);
+                                hbox_minus(R, I, next);
+                            }
+                            remaining.swap(next);
+                        }
+                    }
+                    else
+                    {
+                        // zero of the ghost regions
+                        for (const HBox& R : ghost) ops[2].push_back(make_op(R));
+                        // accumulation: the interior adds the GHOST copies every source holds of it (interior copies of shared faces
+                        // are face_sync_kernel's).  The rim of the interior is cut into boxes that each have ONE ordered list of
+                        // sources (canonical order), so that an element's additions happen in one thread, in that order.
+                        std::vector<std::pair<HBox, std::vector<int>>> cells;
+                        for (int sidx = 0; sidx < A.nsrc; ++sidx)
+                        {
+                            const HaloSrc& S = A.src[sidx];
+                            HBox sarr, sint, I;
+                            for (int d = 0; d < 3; ++d)
+                            {
+                                sarr.lo[d] = S.alo[d];
+                                sarr.hi[d] = S.ahi[d];
+                                sint.lo[d] = S.ilo[d];
+                                sint.hi[d] = S.ihi[d];
+                            }
+                            if (!hbox_intersect(inter, sarr, I)) continue;
+                            std::vector<HBox> parts;
+                            hbox_minus(I, sint, parts);
+                            for (const HBox& B : parts)
+                            {
+                                std::vector<std::pair<HBox, std::vector<int>>> next;
+                                std::vector<HBox> uncovered{ B };
+                                for (auto& cell : cells)
+                                {
+                                    HBox J;
+                                    if (!hbox_intersect(cell.first, B, J))
+                                    {
+                                        next.push_back(cell);
+                                        continue;
+                                    }
+                                    std::vector<int> lst = cell.second;
+                                    lst.push_back(sidx);
+                                    next.push_back({ J, lst });
+                                    std::vector<HBox> rest;
+                                    hbox_minus(cell.first, J, rest);
+                                    for (const HBox& R : rest) next.push_back({ R, cell.second });
+                                    std::vector<HBox> unc2;
+                                    for (const HBox& U : uncovered) hbox_minus(U, J, unc2);
+                                    uncovered.swap(unc2);
+                                }
+                                for (const HBox& U : uncovered) next.push_back({ U, std::vector<int>{ sidx } });
+                                cells.swap(next);
+                            }
+                        }
+                        for (auto& cell : cells)
+                        {
+                            if ((int)cell.second.size() > REGION_MAXSRC) return fail(ctx, IBK_ERR_INVALID, "too many ghost copies of one region");
+                            RegionMulti op = make_op(cell.first);
+                            for (int sidx : cell.second) add_src(op, cell.first, A.src[sidx]);
+                            ops[1].push_back(op);
+                        }
+                    }
+                }
                 HaloArgs* d_A = nullptr;
                 CK(cudaMalloc(&d_A, sizeof(HaloArgs)));
                 hp.allocs.push_back(d_A);
@@ -568,8 +649,18 @@ static int build_halo_plan(ibk_ctx* ctx)
                 }
                 CK(cudaMemcpy(d_A, &A, sizeof(HaloArgs), cudaMemcpyHostToDevice));
                 hp.d_args[which][(size_t)p * ndim + axis] = d_A;
+                if (which == 1)
+                {
+                    FaceLayerJob job;
+                    job.args = d_A;
+                    job.axis = axis;
+                    job.save = hp.d_face_save[(size_t)p * ndim + axis];
+                    face_jobs.push_back(job);
+                    hp.face_job_blocks = std::max(hp.face_job_blocks, halo_blocks(lv, ps, axis));
+                }
             }
         }
+        all_pairs.insert(all_pairs.end(), pairs.begin(), pairs.end());
         hp.n_pairs[axis] = (int)pairs.size();
         if (!pairs.empty())
         {
@@ -580,7 +671,51 @@ static int build_halo_plan(ibk_ctx* ctx)
             hp.d_pairs[axis] = d_p;
         }
     }
+    // CTAs in proportion to the size of the items: 16 warp work items (one row chunk each) per CTA
+    for (int t = 0; t < 3; ++t)
+    {
+        std::vector<RegionMulti>& v = ops[t];
+        unsigned nb = 0;
+        for (RegionMulti& op : v)
+        {
+            op.block0 = nb;
+            op.nblocks = (unsigned)std::max<long long>(1, (region_work(op.ext) + 15) / 16);
+            nb += op.nblocks;
+        }
+        hp.n_ops[t] = (int)v.size();
+        hp.n_blocks[t] = nb;
+        if (!v.empty())
+        {
+            CK(cudaMalloc(&hp.d_ops[t], sizeof(RegionMulti) * v.size()));
+            hp.allocs.push_back(hp.d_ops[t]);
+            CK(cudaMemcpy(hp.d_ops[t], v.data(), sizeof(RegionMulti) * v.size(), cudaMemcpyHostToDevice));
+        }
+    }
+    hp.n_all_pairs = (int)all_pairs.size();
+    if (!all_pairs.empty())
+    {
+        CK(cudaMalloc(&hp.d_all_pairs, sizeof(FacePair) * all_pairs.size()));
+        hp.allocs.push_back(hp.d_all_pairs);
+        CK(cudaMemcpy(hp.d_all_pairs, all_pairs.data(), sizeof(FacePair) * all_pairs.size(), cudaMemcpyHostToDevice));
+    }
+    hp.n_face_jobs = (int)face_jobs.size();
+    if (!face_jobs.empty())
+    {
+        CK(cudaMalloc(&hp.d_face_jobs, sizeof(FaceLayerJob) * face_jobs.size()));
+        hp.allocs.push_back(hp.d_face_jobs);
+        CK(cudaMemcpy(hp.d_face_jobs, face_jobs.data(), sizeof(FaceLayerJob) * face_jobs.size(), cudaMemcpyHostToDevice));
+    }
     return IBK_OK;
+}
+
+// all box operations of one kind in one launch
+template <int MODE>
+static cudaError_t launch_region_items(ibk_ctx* ctx, const HaloPlan& hp, int t)
+{
+    if (hp.n_ops[t] <= 0) return cudaSuccess;
+    region_items_kernel<MODE><<<hp.n_blocks[t], 256, 0, ctx->L.stream>>>(hp.d_ops[t], hp.n_ops[t]);
+    ctx->L.launches++;
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1487,30 +1622,15 @@ extern "C" int ibk_halo_local(ibk_ctx* ctx, int which)
     if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
     if (which < 0 || which > 1) return fail(ctx, IBK_ERR_INVALID, "which must be 0 (u: fill) or 1 (f: accumulate)");
     GRID_DEPS(which);
-    const int ndim = lv.ndim, P = (int)lv.patches.size();
-    const unsigned nslab = 2 * ndim;
-    if (which == 1)
+    if (which == 1 && ex->halo.n_all_pairs > 0)
     {
-        for (int axis = 0; axis < ndim; ++axis)
-            if (ex->halo.n_pairs[axis] > 0)
-            {
-                dim3 grid(64, ex->halo.n_pairs[axis]);
-                face_sync_kernel<<<grid, 256, 0, ctx->L.stream>>>(ex->halo.d_pairs[axis]);
-                ctx->L.launches++;
-            }
+        face_sync_kernel<<<dim3(64, ex->halo.n_all_pairs), 256, 0, ctx->L.stream>>>(ex->halo.d_all_pairs);
+        ctx->L.launches++;
     }
-    for (int p = 0; p < P; ++p)
-        for (int axis = 0; axis < ndim; ++axis)
-        {
-            dim3 grid(halo_blocks(lv, lv.patches[p], axis), nslab);
-            const HaloArgs* A = ex->halo.d_args[which][(size_t)p * ndim + axis];
-            if (which == 0)
-                halo_fill_kernel<<<grid, 256, 0, ctx->L.stream>>>(A);
-            else
-                halo_accum_kernel<<<grid, 256, 0, ctx->L.stream>>>(A);
-            ctx->L.launches++;
-        }
-    CK(cudaGetLastError());
+    if (which == 0)
+        CK(launch_region_items<0>(ctx, ex->halo, 0));
+    else
+        CK(launch_region_items<1>(ctx, ex->halo, 1));
     return IBK_OK;
 }
 
@@ -1684,13 +1804,12 @@ static int face_layers(ibk_ctx* ctx, int mode)
     LevelState& lv = ctx->lv;
     LevelExtra* ex = extra_of(ctx, false);
     if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
-    for (size_t p = 0; p < lv.patches.size(); ++p)
-        for (int axis = 0; axis < lv.ndim; ++axis)
-        {
-            face_layers_kernel<<<halo_blocks(lv, lv.patches[p], axis), 256, 0, ctx->L.stream>>>(
-                ex->halo.d_args[1][p * lv.ndim + axis], axis, ex->halo.d_face_save[p * lv.ndim + axis], mode);
-            ctx->L.launches++;
-        }
+    (void)lv;
+    if (ex->halo.n_face_jobs > 0)
+    {
+        face_layers_kernel<<<dim3(std::min(ex->halo.face_job_blocks, 256u), ex->halo.n_face_jobs), 256, 0, ctx->L.stream>>>(ex->halo.d_face_jobs, mode);
+        ctx->L.launches++;
+    }
     CK(cudaGetLastError());
     return IBK_OK;
 }
@@ -1703,14 +1822,7 @@ extern "C" int ibk_spread_begin(ibk_ctx* ctx)
     LevelExtra* ex = extra_of(ctx, false);
     if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
     // the ghost regions of f receive fresh spread values only (LDataManager.cpp:594)
-    const unsigned nslab = 2 * lv.ndim;
-    for (size_t p = 0; p < lv.patches.size(); ++p)
-        for (int axis = 0; axis < lv.ndim; ++axis)
-        {
-            dim3 grid(halo_blocks(lv, lv.patches[p], axis), nslab);
-            halo_zero_ghost_kernel<<<grid, 256, 0, ctx->L.stream>>>(ex->halo.d_args[1][p * lv.ndim + axis]);
-            ctx->L.launches++;
-        }
+    CK(launch_region_items<2>(ctx, ex->halo, 2));
     return face_layers(ctx, 0);
 }
 extern "C" int ibk_spread_end(ibk_ctx* ctx)
