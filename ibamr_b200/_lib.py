@@ -127,6 +127,7 @@ SYMBOLS = {
     "ibk_io_read_anchor_file": (_i, [_s, _i, _i, _pi, _i, _pi]),
     "ibk_bin_get_cells": (_i, [_vp, _pi, _pi]),
     "ibk_bin_get_order": (_i, [_vp, _pi]),
+    "ibk_bin_get_patch_lists": (_i, [_vp, _i, _pi, _pi, _pd, _pi]),
     "ibk_spread_force": (_i, [_vp, _s, _i]),
     "ibk_spread_begin": (_i, [_vp]),
     "ibk_spread_end": (_i, [_vp]),

@@ -511,6 +511,18 @@ class IBMethodB200:
         return cells, owner
 
     # -- N1: Lagrangian force + position updates on the device (IBStandardForceGen, IBMethod steps) ----
+    def getPatchLists(self, patch):
+        """LIndexSetData::cacheLocalIndices for one patch: (lag_idx[n], periodic_shifts[n][ndim], interior[n] as bool)."""
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.lib.ibk_bin_get_patch_lists(self.ctx.h, patch, C.byref(n), None, None, None))
+        cnt = n.value
+        idx = np.zeros(max(cnt, 1), dtype=np.int32)
+        sh = np.zeros((max(cnt, 1), self.ndim))
+        interior = np.zeros(max(cnt, 1), dtype=np.int32)
+        n = C.c_int(cnt)
+        self.ctx.check(self.ctx.lib.ibk_bin_get_patch_lists(self.ctx.h, patch, C.byref(n), _ip(idx), _dp(sh), _ip(interior)))
+        return idx[:cnt], sh[:cnt], interior[:cnt].astype(bool)
+
     def lincomb(self, dst, alpha, a, beta, b):
         """dst = alpha * a + beta * b on marker columns (VecWAXPY / VecAXPBYPCZ of IBMethod.cpp:714-826)."""
         self.ctx.check(self.ctx.lib.ibk_markers_lincomb(self.ctx.h, COLUMNS[dst], float(alpha), COLUMNS[a], float(beta), COLUMNS[b]))

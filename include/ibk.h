@@ -420,6 +420,13 @@ int ibk_bin_get_cells(ibk_ctx* ctx, int* h_cells, int* h_owner);
 /* Sorted order: h_lag_idx[i] = Lagrangian index of the marker stored at sorted position i
  * (the "local PETSc index -> Lagrangian index" map, LDataManager.cpp:2897-2911). */
 int ibk_bin_get_order(ibk_ctx* ctx, int* h_lag_idx);
+/* The index sets of LIndexSetData::cacheLocalIndices for one patch (ibtk/src/lagrangian/LIndexSetData.cpp:53-141): every
+ * marker whose cell, or a periodic image of it, lies in the patch's ghost box, in the reference's order (cell k-j-i inside the
+ * ghost box, then Lagrangian index), with the periodic shift of the image (:89-101, [n][ndim]) and interior (1) / ghost (0)
+ * (:104).  The interior / ghost lists of the reference are the sublists by that flag.  *n_entries: in = capacity of the
+ * arrays, out = length of the list; null arrays or too small a capacity: the count only.  The device holds the markers this
+ * process owns: the lists are complete when all patches of the level are local. */
+int ibk_bin_get_patch_lists(ibk_ctx* ctx, int patch, int* n_entries, int* h_lag_idx, double* h_shift, int* h_interior);
 
 /* LDataManager::spread core (LDataManager.cpp:551-667) as IBMethod::spreadForce calls it
  * (src/IB/IBMethod.cpp:972-995): f += S[F] from the markers each patch OWNS into interior and

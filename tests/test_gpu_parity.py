@@ -435,6 +435,14 @@ def test_binning_bit_exact(api):
         lst = ref["patches"][p]
         theirs = np.sort(lst["all_idx"][lst["interior_mask"]])
         assert np.array_equal(mine, theirs)
+    # the index sets themselves, bit for bit (LIndexSetData::cacheLocalIndices, a11): every entry of the patch's ghost box
+    # in the reference's order, periodic shifts, interior / ghost
+    for p in range(len(level.boxes)):
+        idx, sh, interior = ib.getPatchLists(p)
+        lst = ref["patches"][p]
+        assert np.array_equal(idx, lst["all_idx"])
+        assert np.array_equal(sh.reshape(-1), lst["all_shift"])
+        assert np.array_equal(interior, lst["interior_mask"])
     # same cell => ascending Lagrangian index (LDataManager.cpp:1505)
     key = [tuple(c) for c in cells[lag]]
     for i in range(1, N):
