@@ -131,6 +131,8 @@ SYMBOLS = {
     "ibk_spread_force": (_i, [_vp, _s, _i]),
     "ibk_spread_begin": (_i, [_vp]),
     "ibk_spread_end": (_i, [_vp]),
+    "ibk_level_set_wall_bc": (_i, [_vp, _pd, _pd]),
+    "ibk_spread_fold_walls": (_i, [_vp]),
     "ibk_interpolate_velocity": (_i, [_vp, _s, _i]),
     "ibk_halo_local": (_i, [_vp, _i]),
     "ibk_halo_pack": (_i, [_vp, _i, _i, _i, _pi, _pi, _vp]),

@@ -511,6 +511,13 @@ class IBMethodB200:
         return cells, owner
 
     # -- N1: Lagrangian force + position updates on the device (IBStandardForceGen, IBMethod steps) ----
+    def setWallBc(self, acoef, bcoef):
+        """Robin coefficients [ndim][2][ndim] of the physical boundaries: switches the fold-back of the spread force on
+        (f_phys_bdry_op of IBStrategy::spreadForce; CartSideRobinPhysBdryOp::accumulateFromPhysicalBoundaryData)."""
+        a, b = _f64(acoef).reshape(-1), _f64(bcoef).reshape(-1)
+        assert a.size == b.size == self.ndim * 2 * self.ndim
+        self.ctx.check(self.ctx.lib.ibk_level_set_wall_bc(self.ctx.h, _dp(a), _dp(b)))
+
     def getPatchLists(self, patch):
         """LIndexSetData::cacheLocalIndices for one patch: (lag_idx[n], periodic_shifts[n][ndim], interior[n] as bool)."""
         n = C.c_int(0)

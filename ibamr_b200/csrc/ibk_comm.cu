@@ -541,6 +541,8 @@ int halo_post(ibk_ctx* ctx, int t)
     if (!c || !c->plan) return cfail(ctx, IBK_ERR_STATE, "no halo plan: call ibk_comm_init and ibk_comm_set_patches first");
     if (c->posted[t]) return cfail(ctx, IBK_ERR_STATE, "the previous exchange of this kind was posted but not finished");
     CCK(cudaSetDevice(ctx->device));
+    if (t == 1) // what lies beyond a physical boundary is folded back before any ghost value leaves
+        if (int rc = ibk_spread_fold_walls(ctx)) return rc;
     for (Message& m : c->send[t])
     {
         if (c->transport == 2 && m.consumed_pending) // the peer must have copied the previous content

@@ -221,6 +221,64 @@ __global__ void face_layers_kernel(const FaceLayerJob* __restrict__ jobs, int mo
     }
 }
 
+// Physical-boundary fold-back of the spread force: the adjoint of the linear ghost-cell extrapolation of a Robin boundary
+// condition a u + b du/dn = g, CartSideRobinPhysBdryOp::accumulateFromPhysicalBoundaryData
+// (ibtk/src/boundary/physical_boundary/CartSideRobinPhysBdryOp.cpp:552-617) with the co-dimension-one Fortran kernels in
+// adjoint mode (fortran/cartphysbdryop3d.f.m4: scrobinphysbdryop1x3d :787-905 for the component normal to the wall,
+// ccrobinphysbdryop1x3d :78-168 for the transverse ones; homogeneous form: g = 0).  One thread per column along the wall
+// normal, over the WHOLE transverse extent of the array (ghost columns included: what a neighbouring patch's fold-back would
+// have put into its own interior reaches it afterwards through the ghost accumulation).
+struct WallJob
+{
+    double* ptr;
+    long long stride[3]; // element strides of the array
+    int n[3];            // extents incl. ghosts
+    int dim, side;       // wall normal, 0 lower / 1 upper
+    int normal;          // the component is the one normal to the wall
+    int ib;              // normal: array index of the boundary face; transverse: of the first interior cell next to the wall
+    int gcw;
+    double a, b, h;
+};
+__global__ void wall_fold_kernel(const WallJob* __restrict__ jobs)
+{
+    const WallJob& J = jobs[blockIdx.y];
+    const int d = J.dim, e1 = (d + 1) % 3, e2 = (d + 2) % 3;
+    const long long total = (long long)J.n[e1] * J.n[e2];
+    const int sgn = J.side ? +1 : -1;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x)
+    {
+        const int j1 = (int)(q % J.n[e1]), j2 = (int)(q / J.n[e1]);
+        double* col = J.ptr + j1 * J.stride[e1] + j2 * J.stride[e2];
+        if (J.normal)
+        {
+            const bool dirichlet = fabs(J.b) < 1.0e-12;
+            double ub = dirichlet ? 0.0 : col[J.ib * J.stride[d]]; // (Dirichlet: u_b = g / a = 0 is written first, f.m4:864-865)
+            for (int i = 1; i <= J.gcw; ++i)
+            {
+                const int ig = J.ib + sgn * i, ii = J.ib - sgn * i;
+                if (ig < 0 || ig >= J.n[d] || ii < 0 || ii >= J.n[d]) continue;
+                const double ug = col[ig * J.stride[d]];
+                const double fi = dirichlet ? -1.0 : 1.0;
+                const double fb = dirichlet ? 2.0 : -J.a * (2.0 * i) * J.h / J.b;
+                col[ii * J.stride[d]] += fi * ug;
+                ub += fb * ug;
+            }
+            col[J.ib * J.stride[d]] = ub;
+        }
+        else
+        {
+            for (int i = 0; i < J.gcw; ++i)
+            {
+                const int ig = J.ib + sgn * (1 + i), ii = J.ib - sgn * i;
+                if (ig < 0 || ig >= J.n[d] || ii < 0 || ii >= J.n[d]) continue;
+                const double nn = 1.0 + 2.0 * i;
+                const double fi = -(J.a * nn * J.h - 2.0 * J.b) / (J.a * nn * J.h + 2.0 * J.b);
+                col[ii * J.stride[d]] += fi * col[ig * J.stride[d]];
+            }
+        }
+    }
+}
+
 __global__ void count_nonzero_kernel(const double* __restrict__ p, long long pitch, int n0, long long rows,
                                      unsigned long long* __restrict__ out)
 {
@@ -276,6 +334,10 @@ struct HaloPlan
     unsigned n_blocks[3] = { 0, 0, 0 };
     FacePair* d_all_pairs = nullptr; // the face pairs of all axes (one launch)
     int n_all_pairs = 0;
+    WallJob* d_wall_jobs = nullptr; // physical-boundary fold-back (ibk_level_set_wall_bc)
+    int n_wall_jobs = 0;
+    unsigned wall_blocks = 1;
+    bool walls_folded = false; // since the last ibk_spread_begin
     FaceLayerJob* d_face_jobs = nullptr; // [patch][axis]
     int n_face_jobs = 0;
     unsigned face_job_blocks = 1;
@@ -313,6 +375,7 @@ void extra_drop(ibk_ctx* ctx)
         if (g_extra[i].first == ctx)
         {
             for (void* p : g_extra[i].second->halo.allocs) cudaFree(p);
+            if (g_extra[i].second->halo.d_wall_jobs) cudaFree(g_extra[i].second->halo.d_wall_jobs);
             for (ItemTable& t : g_extra[i].second->item_tables)
                 if (t.d_items) cudaFree(t.d_items);
             delete g_extra[i].second;
@@ -1614,6 +1677,7 @@ static unsigned halo_blocks(const LevelState& lv, const PatchState& ps, int axis
     return (unsigned)std::min<long long>(std::max<long long>(nb, 1), 148 * 8);
 }
 
+extern "C" int ibk_spread_fold_walls(ibk_ctx* ctx);
 extern "C" int ibk_halo_local(ibk_ctx* ctx, int which)
 {
     NEED_LEVEL();
@@ -1622,6 +1686,8 @@ extern "C" int ibk_halo_local(ibk_ctx* ctx, int which)
     if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
     if (which < 0 || which > 1) return fail(ctx, IBK_ERR_INVALID, "which must be 0 (u: fill) or 1 (f: accumulate)");
     GRID_DEPS(which);
+    if (which == 1)
+        if (int rc = ibk_spread_fold_walls(ctx)) return rc;
     if (which == 1 && ex->halo.n_all_pairs > 0)
     {
         face_sync_kernel<<<dim3(64, ex->halo.n_all_pairs), 256, 0, ctx->L.stream>>>(ex->halo.d_all_pairs);
@@ -1823,6 +1889,7 @@ extern "C" int ibk_spread_begin(ibk_ctx* ctx)
     if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
     // the ghost regions of f receive fresh spread values only (LDataManager.cpp:594)
     CK(launch_region_items<2>(ctx, ex->halo, 2));
+    ex->halo.walls_folded = false;
     return face_layers(ctx, 0);
 }
 extern "C" int ibk_spread_end(ibk_ctx* ctx)
@@ -1830,6 +1897,87 @@ extern "C" int ibk_spread_end(ibk_ctx* ctx)
     NEED_LEVEL();
     GRID_DEPS(1);
     return face_layers(ctx, 1);
+}
+
+// Robin coefficients of the physical boundaries, [ndim][2 sides][ndim components] each (a u + b du/dn = g; the fold-back
+// is the homogeneous adjoint and does not use g).  From then on every spread with halo handling folds what it put into
+// the ghost cells outside the domain back into the interior before the ghost accumulation.  Null pointers switch it off.
+extern "C" int ibk_level_set_wall_bc(ibk_ctx* ctx, const double* acoef, const double* bcoef)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    LevelExtra* ex = extra_of(ctx, false);
+    if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
+    HaloPlan& hp = ex->halo;
+    cudaStreamSynchronize(ctx->L.stream);
+    if (hp.d_wall_jobs) cudaFree(hp.d_wall_jobs);
+    hp.d_wall_jobs = nullptr;
+    hp.n_wall_jobs = 0;
+    if (!acoef || !bcoef) return IBK_OK;
+    const int ndim = lv.ndim;
+    int nwall = 0;
+    for (int d = 0; d < ndim; ++d) nwall += lv.periodic[d] ? 0 : 1;
+    if (nwall > 1)
+        return fail(ctx, IBK_ERR_INVALID,
+                    "physical boundaries in more than one dimension: the co-dimension two / three extrapolations "
+                    "(CartSideRobinPhysBdryOp.cpp:586-598) are not built");
+    std::vector<WallJob> jobs;
+    for (const PatchState& ps : lv.patches)
+        for (int d = 0; d < ndim; ++d)
+        {
+            if (lv.periodic[d]) continue;
+            for (int side = 0; side < 2; ++side)
+            {
+                const bool touches = side == 0 ? ps.lower[d] == lv.domain_lower[d] : ps.upper[d] == lv.domain_upper[d];
+                if (!touches) continue;
+                for (int comp = 0; comp < ndim; ++comp)
+                {
+                    WallJob J;
+                    std::memset(&J, 0, sizeof(J));
+                    J.ptr = ps.f[comp];
+                    J.stride[0] = 1;
+                    J.stride[1] = ps.pitch[comp];
+                    J.stride[2] = ps.pitch[comp] * ps.n[comp][1];
+                    for (int e = 0; e < 3; ++e) J.n[e] = ps.n[comp][e];
+                    J.dim = d;
+                    J.side = side;
+                    J.normal = comp == d ? 1 : 0;
+                    J.gcw = lv.gcw[d];
+                    const int ncell = ps.upper[d] - ps.lower[d] + 1;
+                    // array index = index - (lower - gcw): boundary face (normal) = lower / upper + 1, first interior cell
+                    // (transverse) = lower / upper
+                    if (J.normal) J.ib = side == 0 ? lv.gcw[d] : lv.gcw[d] + ncell;
+                    else J.ib = side == 0 ? lv.gcw[d] : lv.gcw[d] + ncell - 1;
+                    J.a = acoef[(d * 2 + side) * ndim + comp];
+                    J.b = bcoef[(d * 2 + side) * ndim + comp];
+                    J.h = lv.dx[d];
+                    jobs.push_back(J);
+                    const long long cols = (long long)J.n[(d + 1) % 3] * J.n[(d + 2) % 3];
+                    hp.wall_blocks = std::max<unsigned>(hp.wall_blocks, (unsigned)std::min<long long>(148 * 8, (cols + 255) / 256));
+                }
+            }
+        }
+    if (jobs.empty()) return IBK_OK;
+    CK(cudaMalloc(&hp.d_wall_jobs, sizeof(WallJob) * jobs.size()));
+    CK(cudaMemcpy(hp.d_wall_jobs, jobs.data(), sizeof(WallJob) * jobs.size(), cudaMemcpyHostToDevice));
+    hp.n_wall_jobs = (int)jobs.size();
+    return IBK_OK;
+}
+// The fold-back itself: once per spread (after the tiles that can reach a ghost cell, before any ghost value is packed or
+// accumulated).  ibk_spread_force and ibk_halo_local(f) / ibk_halo_accumulate_post call it themselves.
+extern "C" int ibk_spread_fold_walls(ibk_ctx* ctx)
+{
+    NEED_LEVEL();
+    LevelExtra* ex = extra_of(ctx, false);
+    if (!ex) return fail(ctx, IBK_ERR_STATE, "halo plan missing");
+    HaloPlan& hp = ex->halo;
+    if (hp.n_wall_jobs <= 0 || hp.walls_folded) return IBK_OK;
+    GRID_DEPS(1);
+    wall_fold_kernel<<<dim3(hp.wall_blocks, hp.n_wall_jobs), 256, 0, ctx->L.stream>>>(hp.d_wall_jobs);
+    ctx->L.launches++;
+    hp.walls_folded = true;
+    CK(cudaGetLastError());
+    return IBK_OK;
 }
 
 static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo, int part = 0)

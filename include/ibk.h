@@ -442,6 +442,17 @@ int ibk_spread_force(ibk_ctx* ctx, const char* spread_fcn, int accumulate_halo);
  * parked face content. */
 int ibk_spread_begin(ibk_ctx* ctx);
 int ibk_spread_end(ibk_ctx* ctx);
+/* Physical boundaries (N3 of SURVEY.md 8(f), the f_phys_bdry_op argument of IBStrategy::spreadForce): what the spread puts
+ * into ghost cells OUTSIDE a non-periodic domain is folded back into the interior by the adjoint of the linear ghost-cell
+ * extrapolation of the Robin condition a u + b du/dn = g, CartSideRobinPhysBdryOp::accumulateFromPhysicalBoundaryData
+ * (ibtk/src/boundary/physical_boundary/CartSideRobinPhysBdryOp.cpp:552-617, called LDataManager.cpp:653-657; kernels
+ * fortran/cartphysbdryop3d.f.m4:78-168 transverse components, :787-905 normal component, adjoint_op = 1, homogeneous).
+ * acoef / bcoef: [ndim][2 sides][ndim components].  Built for walls in ONE dimension (the others periodic): with walls in
+ * two or three dimensions the co-dimension two / three extrapolations would be needed and the call is refused.
+ * Null pointers switch the fold-back off (the ghost values outside the domain are then dropped).
+ * ibk_spread_fold_walls runs it (once per spread; ibk_spread_force, ibk_halo_local(f) and ibk_halo_accumulate_post call it). */
+int ibk_level_set_wall_bc(ibk_ctx* ctx, const double* acoef, const double* bcoef);
+int ibk_spread_fold_walls(ibk_ctx* ctx);
 /* LDataManager::interp core (LDataManager.cpp:698-813) as IBMethod::interpolateVelocity calls it
  * (IBMethod.cpp:672-694): (fill_halo != 0) ghost fill of u among this process's patches incl.
  * periodic wrap (replaces u_ghost_fill_scheds[ln]->fillData, :744), then U = J[u]. */

@@ -368,6 +368,64 @@ def bin_level(level: Level, X):
     return dict(cells=cells, owner=owner, patches=patches)
 
 
+def fold_walls(level: Level, p, arrays, acoef, bcoef):
+    """CartSideRobinPhysBdryOp::accumulateFromPhysicalBoundaryData for patch p, co-dimension one, LINEAR, homogeneous
+    (ibtk/src/boundary/physical_boundary/CartSideRobinPhysBdryOp.cpp:552-617): the adjoint of the ghost-cell extrapolation,
+    restated from fortran/cartphysbdryop3d.f.m4 (scrobinphysbdryop1x3d :787-905 for the component normal to the wall,
+    ccrobinphysbdryop1x3d :78-168 for the transverse ones; adjoint_op = 1).  arrays[axis]: the patch's side arrays with
+    ghosts, modified in place over the patch's own (side-box) extent in the transverse directions.
+    acoef / bcoef [ndim][2][ndim components]."""
+    ndim = level.ndim
+    lo, hi = level.boxes[p]
+    g = level.gcw
+    acoef = np.asarray(acoef, dtype=np.float64).reshape(ndim, 2, ndim)
+    bcoef = np.asarray(bcoef, dtype=np.float64).reshape(ndim, 2, ndim)
+    for d in range(ndim):
+        if level.periodic[d]:
+            continue
+        for side in (0, 1):
+            touches = lo[d] == level.domain_lower[d] if side == 0 else hi[d] == level.domain_upper()[d]
+            if not touches:
+                continue
+            ncell = hi[d] - lo[d] + 1
+            h = level.dx[d]
+            sgn = -1 if side == 0 else 1
+            for comp in range(ndim):
+                u = arrays[comp]
+                a, b = acoef[d, side, comp], bcoef[d, side, comp]
+                # view with the wall normal as the LAST python axis removed: index helper along array axis (ndim - 1 - d)
+                ax = ndim - 1 - d
+                sl = [slice(None)] * ndim
+                for e in range(ndim):  # transverse extent: the component's side box (interior)
+                    if e == d:
+                        continue
+                    n_int = hi[e] - lo[e] + 1 + (1 if e == comp else 0)
+                    sl[ndim - 1 - e] = slice(g[e], g[e] + n_int)
+
+                def at(i):
+                    t = list(sl)
+                    t[ax] = i
+                    return tuple(t)
+                if comp == d:
+                    ib = g[d] if side == 0 else g[d] + ncell
+                    dirichlet = abs(b) < 1e-12
+                    if dirichlet:
+                        u[at(ib)] = 0.0  # u_b = g / a with g = 0 (f.m4:864-865)
+                    for i in range(1, g[d] + 1):
+                        ug = u[at(ib + sgn * i)].copy()
+                        fi = -1.0 if dirichlet else 1.0
+                        fb = 2.0 if dirichlet else -a * (2.0 * i) * h / b
+                        u[at(ib - sgn * i)] += fi * ug
+                        u[at(ib)] += fb * ug
+                else:
+                    ii = g[d] if side == 0 else g[d] + ncell - 1
+                    for i in range(g[d]):
+                        nn = 1.0 + 2.0 * i
+                        fi = -(a * nn * h - 2.0 * b) / (a * nn * h + 2.0 * b)
+                        u[at(ii - sgn * i)] += fi * u[at(ii + sgn * (1 + i))]
+    return arrays
+
+
 def ghost_accumulate(level: Level, arrays, centering="side"):
     """SAMRAIGhostDataAccumulator::accumulateGhostData on one level.
 

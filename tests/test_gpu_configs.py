@@ -181,8 +181,8 @@ def test_c4_two_level_amr_fine_patches(api):
 @pytest.mark.parametrize("kernel", ["BSPLINE_4", "PIECEWISE_LINEAR"])
 def test_nonperiodic_walls(api, kernel):
     """Wall-bounded domain: markers close to the walls spread into ghost cells outside the domain, which have no
-    owner and are dropped (the physical-boundary fold-back, CartSideRobinPhysBdryOp.cpp:552-617, is out of scope);
-    interiors must still equal the reference's."""
+    owner and, with no boundary conditions registered (ibk_level_set_wall_bc), are dropped; interiors must still equal the
+    reference's plain spread.  (The fold-back itself: test_walls_fold_back_the_spread_force.)"""
     n, N = 24, 8000
     g = orc.min_ghost_width(kernel)
     boxes = [((0, 0, 0), (11, 23, 23)), ((12, 0, 0), (23, 23, 23))]
@@ -191,6 +191,59 @@ def test_nonperiodic_walls(api, kernel):
     F = np.stack([2 * splitmix64_unit(1 + d, np.arange(N)) - 1 for d in range(3)], axis=1)
     eu, ef = _run_level_case(api, level, kernel, X, F)
     assert eu <= TOL and ef <= TOL
+
+
+@pytest.mark.parametrize("kernel,bc", [("IB_4", "dirichlet"), ("IB_4", "robin"), ("BSPLINE_3", "dirichlet"), ("IB_6", "mixed")])
+def test_walls_fold_back_the_spread_force(api, kernel, bc):
+    """N3, wall part: a channel (periodic in x and y, walls in z) cut into two patches.  With boundary conditions registered
+    the force spread into the ghost cells outside the domain is folded back by the adjoint of the Robin extrapolation
+    (CartSideRobinPhysBdryOp::accumulateFromPhysicalBoundaryData) instead of being dropped.  Reference model: every patch
+    spreads all markers of its ghost box (periodic images included) into a zeroed array, then folds its own walls
+    (LDataManager.cpp:623-657); interiors are compared."""
+    n, N = 32, 12000
+    g = orc.min_ghost_width(kernel)
+    boxes = [((0, 0, 0), (15, 31, 31)), ((16, 0, 0), (31, 31, 31))]
+    level = orc.Level(3, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 0), boxes, (g,) * 3)
+    i = np.arange(N)
+    X = np.stack([splitmix64_unit(20, i), splitmix64_unit(21, i), 0.005 + 0.99 * splitmix64_unit(22, i)], axis=1)
+    X[: N // 2, 2] = np.where(splitmix64_unit(23, i[: N // 2]) < 0.5, 0.002 + 0.08 * splitmix64_unit(24, i[: N // 2]),
+                              0.998 - 0.08 * splitmix64_unit(25, i[: N // 2]))  # half of them within a few cells of a wall
+    F = np.stack([2 * splitmix64_unit(1 + d, i) - 1 for d in range(3)], axis=1)
+    a = np.ones((3, 2, 3))
+    b = np.zeros((3, 2, 3))
+    if bc == "robin":
+        b[:] = 0.5
+    elif bc == "mixed":
+        b[2, 0, :] = 0.25          # lower wall Robin, upper wall Dirichlet
+        a[2, 0, :] = 2.0
+    ib = api.IBMethodB200(3, (0,) * 3, (n - 1,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 0), level.boxes, gcw=g, kernel_fcn=kernel)
+    ib.setWallBc(a, b)
+    ib.setPositions(X)
+    ib.setLData("F", F)
+    ib.beginDataRedistribution()
+    ib.grid_fill("f", 0.0)
+    ib.spreadForce(accumulate_halo=True)
+    ref = orc.bin_level(level, X)
+    worst = 0.0
+    for p in range(2):
+        pg = level.patch_geom(p)
+        lst = ref["patches"][p]
+        fr = [np.zeros(pg.side_shape(c)) for c in range(3)]
+        orc.side_spread(kernel, pg, fr, X, F, lst["all_idx"], lst["all_shift"])
+        before = [x.copy() for x in fr]
+        orc.fold_walls(level, p, fr, a, b)
+        assert any(np.max(np.abs(fr[c] - before[c])) > 1e-6 for c in range(3)), "the case must exercise the fold-back"
+        for c in range(3):
+            got = ib.grid_download("f", p, c)
+            sl = tuple(slice(g, s - g) for s in got.shape)
+            worst = max(worst, np.max(np.abs(got[sl] - fr[c][sl])) / np.max(np.abs(fr[c][sl])))
+    ib.close()
+    assert worst <= TOL
+    # walls in two dimensions need the co-dimension two extrapolation: refused, not silently wrong
+    ib = api.IBMethodB200(3, (0,) * 3, (n - 1,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 0, 0), level.boxes, gcw=g, kernel_fcn=kernel)
+    with pytest.raises(api.IBKError):
+        ib.setWallBc(a, b)
+    ib.close()
 
 
 @pytest.mark.parametrize("kernel", ["IB_4", "IB_6", "BSPLINE_3", "BSPLINE_4", "PIECEWISE_LINEAR", "IB_3", "BSPLINE_5", "BSPLINE_6",

@@ -81,3 +81,60 @@ def test_interpolation_reproduces_constants_and_linear_fields(kernel, ndim):
         U = orc.side_interp_positions(kernel, pg, lin, X)
         exact = 1.5 + X @ np.asarray(coef)
         assert np.max(np.abs(U - exact[:, None])) <= 1e-11
+
+
+def test_wall_fold_back_is_the_adjoint_of_the_robin_extrapolation():
+    """oracle.fold_walls (the adjoint_op = 1 branch of fortran/cartphysbdryop3d.f.m4:78-168, 787-905) against the forward
+    branch of the same routines restated here: <v, E u> over the ghosted array = <E^T v, u> over the interior."""
+    n, g = 8, 3
+    level = orc.Level(3, (0,) * 3, (n,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 0), [((0,) * 3, (n - 1,) * 3)], (g,) * 3)
+    pg = level.patch_geom(0)
+    rng = np.random.default_rng(0)
+    for bval in (0.0, 0.3):
+        a, b = np.ones((3, 2, 3)), np.full((3, 2, 3), bval)
+        h = level.dx[2]
+
+        def extrap(u):  # homogeneous ghost-cell extrapolation, adjoint_op = 0
+            u = [x.copy() for x in u]
+            for side in (0, 1):
+                sgn = -1 if side == 0 else 1
+                for comp in range(3):
+                    A = u[comp]
+                    if comp == 2:
+                        ib = g if side == 0 else g + n
+                        if bval == 0.0:
+                            A[ib] = 0.0
+                        for i in range(1, g + 1):
+                            if bval == 0.0:
+                                A[ib + sgn * i] = -A[ib - sgn * i] + 2.0 * A[ib]
+                            else:
+                                A[ib + sgn * i] = A[ib - sgn * i] + (-a[2, side, comp] * (2.0 * i) * h / bval) * A[ib]
+                    else:
+                        ii = g if side == 0 else g + n - 1
+                        for i in range(g):
+                            nn = 1 + 2 * i
+                            fi = -(a[2, side, comp] * nn * h - 2 * bval) / (a[2, side, comp] * nn * h + 2 * bval)
+                            A[ii + sgn * (1 + i)] = fi * A[ii - sgn * i]
+            return u
+
+        def transverse_interior(c):
+            m = np.zeros(pg.side_shape(c), bool)
+            sl = [slice(None)] * 3
+            for e in (0, 1):
+                sl[2 - e] = slice(g, g + n + (1 if e == c else 0))
+            m[tuple(sl)] = True
+            return m
+
+        u = [rng.standard_normal(pg.side_shape(c)) * transverse_interior(c) for c in range(3)]
+        v = [rng.standard_normal(pg.side_shape(c)) * transverse_interior(c) for c in range(3)]
+        if bval == 0.0:  # Dirichlet pins the boundary face: it is not a degree of freedom of u
+            for side_idx in (g, g + n):
+                u[2][side_idx] = 0.0
+        Eu = extrap(u)
+        Fv = orc.fold_walls(level, 0, [x.copy() for x in v], a, b)
+
+        def zin(c, arr):
+            return arr[g:g + n + (1 if c == 2 else 0)]
+        lhs = sum(np.vdot(v[c], Eu[c]) for c in range(3))
+        rhs = sum(np.vdot(zin(c, Fv[c]), zin(c, u[c])) for c in range(3))
+        assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), 1.0)
