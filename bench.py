@@ -36,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-KERNEL = "IB_4"
+KERNEL = "IB_4"  # (--config C3 switches to IB_6: set in main())
 METRIC = "IB_4 spread+interp markers/sec"
 UNIT = "markers/s"
 
@@ -126,7 +126,7 @@ def cpu_baseline(steps=2, warmup=1, n=256, log2_markers=20):
     X = np.stack([splitmix_unit(7 + d, np.arange(N)) for d in range(3)], axis=1).copy()
     F = np.stack([2.0 * splitmix_unit(1 + d, np.arange(N)) - 1.0 for d in range(3)], axis=1).copy()
     U = np.zeros((N, 3))
-    b = orc.Baseline(3, (n, n, n), npatch, 3, (0.0,) * 3, (1.0,) * 3, X, field_seed=0)
+    b = orc.Baseline(3, (n, n, n), npatch, orc.min_ghost_width(KERNEL), (0.0,) * 3, (1.0,) * 3, X, field_seed=0)
     for _ in range(warmup):
         b.step(KERNEL, F, U)
     t0 = time.perf_counter()
@@ -136,7 +136,7 @@ def cpu_baseline(steps=2, warmup=1, n=256, log2_markers=20):
     b.close()
     return {"value": N / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n}^3 periodic staggered grid cut into {npatch[0]}x{npatch[1]}x{npatch[2]} patches (one worker each, "
-                      f"gcw 3, redundant ghost-region spreading), 2^{log2_markers} uniform markers, IB_4 spread+interp, "
+                      f"gcw {orc.min_ghost_width(KERNEL)}, redundant ghost-region spreading), 2^{log2_markers} uniform markers, {KERNEL} spread+interp, "
                       f"{steps} timed passes; oracle/_ref unbuildable here (needs m4+gfortran+SAMRAI+PETSc+MPI)",
             "ms_per_step": dt * 1e3}
 
@@ -164,8 +164,10 @@ def run_reference(args):
 def workload_config(n_gpus, args):
     pg = process_grid(n_gpus)
     n = args.cells
-    return {"workload": f"C5 shard (weak scaling): per GPU one {n}^3 patch of a periodic staggered grid + 2^{args.log2_markers} "
-                        f"{args.markers} markers, IB_4, fp64; process grid {pg[0]}x{pg[1]}x{pg[2]} "
+    name = {"C5": "C5 shard (weak scaling)", "C3": "C3 (IB_6, uniform + clustered shell; per-GPU shard at N > 1)",
+            "C2": "C2 (spherical shell)"}[args.config]
+    return {"workload": f"{name}: per GPU one {n}^3 patch of a periodic staggered grid + 2^{args.log2_markers} "
+                        f"{args.markers} markers, {KERNEL}, fp64; process grid {pg[0]}x{pg[1]}x{pg[2]} "
                         f"(global {n * pg[0]}x{n * pg[1]}x{n * pg[2]}, {n_gpus * (1 << args.log2_markers)} markers)",
             "kernel": KERNEL, "cells_per_gpu": [n, n, n], "markers_per_gpu": 1 << args.log2_markers,
             "step": "spreadForce (ghost zero + spread + halo accumulate) + interpolateVelocity (halo fill + interp), markers pre-binned",
@@ -221,7 +223,7 @@ def sample_parity(ctx_device, n=256, log2_markers=20):
     X = np.stack([splitmix_unit(7 + d, np.arange(N)) for d in range(3)], axis=1).copy()
     F = np.stack([2.0 * splitmix_unit(1 + d, np.arange(N)) - 1.0 for d in range(3)], axis=1).copy()
     U_ref = np.zeros((N, 3))
-    g = 3
+    g = orc.min_ghost_width(KERNEL)
     b = orc.Baseline(3, (n, n, n), npatch, g, (0.0,) * 3, (1.0,) * 3, X, field_seed=0)
     b.zero_f()
     b.step(KERNEL, F, U_ref)
@@ -264,7 +266,7 @@ def sample_parity(ctx_device, n=256, log2_markers=20):
     err_u = float(np.max(np.abs(U - U_ref)) / np.max(np.abs(U_ref)))
     ib.close()
     return {"max_rel_err_U": err_u, "max_rel_err_f": err_f, "tolerance": 1e-12, "ok": bool(err_u <= 1e-12 and err_f <= 1e-12),
-            "what": f"{n}^3 periodic grid, 2^{log2_markers} uniform markers, IB_4: GPU path (one resident patch, halo fill / "
+            "what": f"{n}^3 periodic grid, 2^{log2_markers} uniform markers, {KERNEL}: GPU path (one resident patch, halo fill / "
                     f"accumulate) vs the oracle's reference model ({npatch[0]}x{npatch[1]}x{npatch[2]} patches), max-norm relative"}
 
 
@@ -317,6 +319,16 @@ def run_gpu(args):
         c = [(me.lower[d] + 0.5 * n) * h for d in range(3)]
         R = 0.25 * n * h
         X = np.stack([c[0] + R * np.cos(th) * np.sin(phi), c[1] + R * np.sin(th) * np.sin(phi), c[2] + R * np.cos(phi)], axis=1)
+    if args.markers == "mixed":
+        # BASELINE config C3: half of the markers uniform, half on a jittered spherical shell (radius n/4 cells, a few cells
+        # thick) in the middle of the rank's patch
+        half = N // 2
+        k = np.arange(half, dtype=np.float64) + 0.5
+        phi = np.arccos(1.0 - 2.0 * k / half)
+        th = np.pi * (1.0 + 5.0 ** 0.5) * k
+        c = [(me.lower[d] + 0.5 * n) * h for d in range(3)]
+        R = (0.25 * n + 3.0 * (splitmix_unit(91, idx[:half]) - 0.5)) * h
+        X[:half] = np.stack([c[0] + R * np.cos(th) * np.sin(phi), c[1] + R * np.sin(th) * np.sin(phi), c[2] + R * np.cos(phi)], axis=1)
     F = np.stack([2.0 * splitmix_unit(1 + d, idx) - 1.0 for d in range(3)], axis=1)
     # pinned host buffers for the e2e leg
     hX = torch.from_numpy(X).pin_memory()
@@ -552,10 +564,10 @@ def run_gpu(args):
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                     "what": "host X, F, u (pinned) -> device, re-bin, step, U and f -> host; all copies inside the timed region, u upload / f download on copy streams overlapping the kernels"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "spread_tile_kernel<3,IB_4> (+ fix-up)", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": f"spread_march_kernel<{KERNEL}> (+ dense bricks, fix-up)", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": traffic if args.config == "C5" else None, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes": spread_bytes, "launch_ms": sp_ms,
-                         "interp": {"kernel": "interp_rot_kernel<IB_4,320>", "achieved": interp_bytes / (in_ms * 1e-3) / 1e9,
+                         "interp": {"kernel": "interp_rot_kernel<IB_4,320>" if KERNEL == "IB_4" else f"interp_tile_kernel<3,{KERNEL}>", "achieved": interp_bytes / (in_ms * 1e-3) / 1e9,
                                     "frac": interp_bytes / (in_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": interp_bytes,
                                     "traffic": traffic_interp,
                                     "launch_ms": in_ms},
@@ -588,13 +600,25 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=512, help="cells per dimension per GPU")
     ap.add_argument("--log2-markers", type=int, default=23, help="log2 of the markers per GPU")
-    ap.add_argument("--markers", default="uniform", choices=["uniform", "shell"],
-                    help="marker distribution: uniform (the benchmark) or a dense spherical shell (diagnostic)")
+    ap.add_argument("--markers", default=None, choices=["uniform", "shell", "mixed"],
+                    help="marker distribution: uniform (C5), a dense spherical shell (C2), half uniform + half jittered shell (C3)")
+    ap.add_argument("--config", default="C5", choices=["C5", "C3", "C2"],
+                    help="BASELINE.json configuration: C5 (default, the headline: IB_4, 512^3 + 2^23 uniform markers per GPU), "
+                         "C3 (IB_6, 512^3, 2^23 markers uniform + clustered shell), C2 (IB_4, 256^3, 2^20 markers on a shell)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-breakdown", action="store_true", help="print the e2e phases, each synchronised, to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sample-parity", action="store_true", help="skip the 256^3 value-by-value comparison with the oracle (N = 1)")
     args = ap.parse_args()
+    global KERNEL, METRIC
+    if args.config == "C3":
+        KERNEL, METRIC = "IB_6", "IB_6 spread+interp markers/sec"
+        args.markers = args.markers or "mixed"
+    elif args.config == "C2":
+        args.markers = args.markers or "shell"
+        if args.cells == 512 and args.log2_markers == 23:
+            args.cells, args.log2_markers = 256, 20
+    args.markers = args.markers or "uniform"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

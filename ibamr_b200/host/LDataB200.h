@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/ibk.h"
+#include "samrai_standins.h"
 
 namespace IBTK_B200
 {
@@ -21,6 +22,34 @@ public:
     // column: IBK_COL_X ... IBK_COL_AUX; depth is the level's NDIM
     LDataB200(std::string name, ibk_ctx* ctx, int column, int depth) : d_name(std::move(name)), d_ctx(ctx), d_column(column), d_depth(depth)
     {
+    }
+    // Restart (ibtk/src/lagrangian/LData.cpp:99-130): the column is filled from the database's "vals".  The level of `ctx`
+    // must hold num_local_nodes markers already (positions are restored first: an LData("X") record through
+    // IBMethodB200::setPositions, then ibk_rebin).  Rows are host rows (Lagrangian order): the reference writes the PETSc
+    // local order, which is a product of LDataManager's own restart data, not of LData.
+    LDataB200(const std::shared_ptr<SAMRAI_standin::Database>& db, ibk_ctx* ctx, int column)
+        : d_name(db->getString("d_name")), d_ctx(ctx), d_column(column), d_depth(db->getInteger("d_depth"))
+    {
+        const int num_local_nodes = db->getInteger("num_local_nodes"), num_ghost_nodes = db->getInteger("num_ghost_nodes");
+        if (num_ghost_nodes != 0) throw std::runtime_error("LDataB200 " + d_name + ": ghost nodes in the restart record (owner-only design)");
+        if (num_local_nodes != ibk_markers_count(ctx)) throw std::runtime_error("LDataB200 " + d_name + ": node count differs from the level's");
+        d_host.assign((size_t)num_local_nodes * d_depth, 0.0);
+        if (num_local_nodes > 0) db->getDoubleArray("vals", d_host.data(), d_depth * num_local_nodes);
+        d_host_newer = true;
+        d_device_newer = false;
+        restoreArrays();
+    }
+    // LData::putToDatabase (LData.cpp:186-209): same keys; no ghost nodes here
+    void putToDatabase(const std::shared_ptr<SAMRAI_standin::Database>& db)
+    {
+        const int num_local_nodes = getLocalNodeCount();
+        db->putString("d_name", d_name);
+        db->putInteger("d_depth", d_depth);
+        db->putInteger("num_local_nodes", num_local_nodes);
+        db->putInteger("num_ghost_nodes", 0);
+        const double* vals = static_cast<const LDataB200*>(this)->getLocalFormVecArray();
+        if (num_local_nodes > 0) db->putDoubleArray("vals", vals, d_depth * num_local_nodes);
+        restoreArrays();
     }
     const std::string& getName() const
     {

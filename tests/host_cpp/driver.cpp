@@ -212,8 +212,100 @@ static int run_two_ranks(const char* case_file, const char* out_file)
     return 0;
 }
 
+// LData restart round trip (LData.cpp:99-130, 186-209): a level with X, U, F on the device is written to a database file,
+// a SECOND level is rebuilt from the file alone; the columns must come back bit for bit and the next spread must produce
+// the very same f (the spread is deterministic).  Prints "restart ok" on success.
+static int run_restart(const char* tmp_path)
+{
+    try
+    {
+        const int n = 32, N = 5000, g = 3;
+        Box dom(Index(0), Index(n - 1));
+        IBAMR_B200::IBMethodB200::LevelSpec lv;
+        lv.domain_box = dom;
+        for (int d = 0; d < 3; ++d)
+        {
+            lv.x_lower[d] = 0.0;
+            lv.x_upper[d] = 1.0;
+            lv.periodic[d] = 1;
+        }
+        lv.patch_boxes.push_back(dom);
+        std::vector<double> X((size_t)N * 3), F((size_t)N * 3);
+        unsigned long long sd = 12345;
+        auto rnd = [&]() {
+            sd = sd * 6364136223846793005ull + 1442695040888963407ull;
+            return (double)(sd >> 11) * (1.0 / 9007199254740992.0);
+        };
+        for (auto& v : X) v = rnd();
+        for (auto& v : F) v = 2.0 * rnd() - 1.0;
+        std::vector<double> f_first[3], Xa, Ua, Fa;
+        {
+            IBAMR_B200::IBMethodB200 ib(lv, "IB_4", 0, g);
+            ib.setPositions(X);
+            ib.setForce(F);
+            ib.beginDataRedistribution();
+            SideData u(dom, 1, IntVector(g)), f(dom, 1, IntVector(g));
+            for (int a = 0; a < 3; ++a)
+                for (size_t k = 0; k < u.data[a].size(); ++k) u.data[a][k] = std::sin(0.001 * (double)k);
+            ib.registerPatchData(0, 0, &u);
+            ib.registerPatchData(1, 0, &f);
+            ib.interpolateVelocity(0, {}, {}, 0.0);
+            ib.spreadForce(1, nullptr, {}, 0.0);
+            for (int a = 0; a < 3; ++a) f_first[a] = f.data[a];
+            ib.getColumn(IBK_COL_X, Xa);
+            ib.getColumn(IBK_COL_U, Ua);
+            ib.getColumn(IBK_COL_F, Fa);
+            const char* names[3] = { "X", "U", "F" };
+            const int cols[3] = { IBK_COL_X, IBK_COL_U, IBK_COL_F };
+            for (int c = 0; c < 3; ++c)
+            {
+                auto db = std::make_shared<Database>();
+                IBTK_B200::LDataB200 data(names[c], ib.ctx(), cols[c], 3);
+                data.putToDatabase(db);
+                db->writeToFile(std::string(tmp_path) + "." + names[c]);
+            }
+        }
+        {
+            IBAMR_B200::IBMethodB200 ib(lv, "IB_4", 0, g);
+            auto dbX = Database::readFromFile(std::string(tmp_path) + ".X");
+            std::vector<double> Xr((size_t)dbX->getInteger("num_local_nodes") * 3);
+            dbX->getDoubleArray("vals", Xr.data(), (int)Xr.size());
+            ib.setPositions(Xr);
+            IBTK_B200::LDataB200 Ud(Database::readFromFile(std::string(tmp_path) + ".U"), ib.ctx(), IBK_COL_U);
+            IBTK_B200::LDataB200 Fd(Database::readFromFile(std::string(tmp_path) + ".F"), ib.ctx(), IBK_COL_F);
+            ib.beginDataRedistribution();
+            std::vector<double> Xb, Ub, Fb;
+            ib.getColumn(IBK_COL_X, Xb);
+            ib.getColumn(IBK_COL_U, Ub);
+            ib.getColumn(IBK_COL_F, Fb);
+            if (Xb != Xa || Ub != Ua || Fb != Fa || Ud.getName() != "U" || Fd.getDepth() != 3)
+            {
+                std::printf("restart: columns differ\n");
+                return 1;
+            }
+            SideData f(dom, 1, IntVector(g));
+            ib.registerPatchData(1, 0, &f);
+            ib.spreadForce(1, nullptr, {}, 0.0);
+            for (int a = 0; a < 3; ++a)
+                if (f.data[a] != f_first[a])
+                {
+                    std::printf("restart: the spread after the restart differs\n");
+                    return 1;
+                }
+        }
+        std::printf("restart ok\n");
+    }
+    catch (const std::exception& e)
+    {
+        std::printf("restart error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc >= 3 && !std::strcmp(argv[1], "--restart")) return run_restart(argv[2]);
     if (argc >= 2 && !std::strcmp(argv[1], "--static")) return run_static();
     if (argc >= 4 && !std::strcmp(argv[1], "--two-ranks")) return run_two_ranks(argv[2], argv[3]);
     if (argc >= 4 && !std::strcmp(argv[1], "--structure")) return run_structure(argv[2], std::atoi(argv[3]));
