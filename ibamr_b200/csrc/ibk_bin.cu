@@ -187,6 +187,52 @@ __global__ void gather_columns_kernel(const double* __restrict__ in, long long i
     for (int c = 0; c < ncols; ++c) out[c * out_stride + i] = in[c * in_stride + s];
 }
 
+__global__ void gather_column_sets_kernel(GatherSets sets, long long stride, const uint32_t* __restrict__ perm, int n, int ncols)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = perm[i];
+    double v[6][3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        if (k < sets.nsets)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (c < ncols) v[k][c] = sets.in[k][c * stride + s];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        if (k < sets.nsets)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (c < ncols) sets.out[k][c * stride + i] = v[k][c];
+}
+
+// The radix sort orders by (brick, cell) only; the markers of one cell are then put into ascending tie (Lagrangian index)
+// order here (LDataManager.cpp:1505): the thread of a run's first element sorts the run by insertion.
+__global__ void sort_ties_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int n, int tie_bits)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t hi = keys[i] >> tie_bits;
+    if (i > 0 && (keys[i - 1] >> tie_bits) == hi) return; // not the first of its run
+    int e = i + 1;
+    while (e < n && (keys[e] >> tie_bits) == hi) ++e;
+    for (int a = i + 1; a < e; ++a)
+    {
+        const uint64_t k = keys[a];
+        const uint32_t v = vals[a];
+        int b = a - 1;
+        while (b >= i && keys[b] > k)
+        {
+            keys[b + 1] = keys[b];
+            vals[b + 1] = vals[b];
+            --b;
+        }
+        keys[b + 1] = k;
+        vals[b + 1] = v;
+    }
+}
+
 __global__ void scatter_columns_kernel(const double* __restrict__ in, long long in_stride, double* __restrict__ out,
                                        long long out_stride, const uint32_t* __restrict__ perm, int n, int ncols)
 {
@@ -299,10 +345,12 @@ cudaError_t bins_build(Bins& b, Launcher& L, const CellGeom& cg, const PatchBin*
                                                                     b.keys[0], b.vals[0], d_cells_out, d_owner_out);
         L.launches++;
     }
-    // sort: tie bits first (skipped on the device when constant), then the brick/cell bits
-    const int end_bit = ((tie_bits + bkey_bits + 7) / 8) * 8;
-    b.sorted_in = radix_sort_pairs(b.keys[0], b.vals[0], b.keys[1], b.vals[1], n_entries, 0, end_bit, b.sort_temp,
+    // sort by the brick / cell bits only (4 passes instead of 7 for 2^23 markers in 2.3 M bricks); the few markers that share
+    // a cell are ordered by their tie bits afterwards
+    const int end_bit = tie_bits + ((bkey_bits + 7) / 8) * 8;
+    b.sorted_in = radix_sort_pairs(b.keys[0], b.vals[0], b.keys[1], b.vals[1], n_entries, tie_bits, end_bit, b.sort_temp,
                                    L.stream, &L.launches);
+    if ((e = sort_ties(L, b.keys[b.sorted_in], b.vals[b.sorted_in], n_entries, tie_bits)) != cudaSuccess) return e;
     brick_offsets_kernel<<<(n_entries + 1 + T - 1) / T, T, 0, L.stream>>>(b.keys[b.sorted_in], n_entries, tie_bits + cshift,
                                                                          total_bricks, b.brick_start);
     L.launches++;
@@ -355,6 +403,23 @@ cudaError_t gather_columns(Launcher& L, const double* d_in, long long in_stride,
     if (n <= 0) return cudaSuccess;
     const int T = 256;
     gather_columns_kernel<<<(n + T - 1) / T, T, 0, L.stream>>>(d_in, in_stride, d_out, out_stride, d_perm, n, ncols);
+    L.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t gather_column_sets(Launcher& L, const GatherSets& sets, long long stride, const uint32_t* d_perm, int n, int ncols)
+{
+    if (n <= 0 || sets.nsets <= 0) return cudaSuccess;
+    const int T = 256;
+    gather_column_sets_kernel<<<(n + T - 1) / T, T, 0, L.stream>>>(sets, stride, d_perm, n, ncols);
+    L.launches++;
+    return cudaGetLastError();
+}
+cudaError_t sort_ties(Launcher& L, uint64_t* keys, uint32_t* vals, int n, int tie_bits)
+{
+    if (n <= 1) return cudaSuccess;
+    const int T = 256;
+    sort_ties_kernel<<<(n + T - 1) / T, T, 0, L.stream>>>(keys, vals, n, tie_bits);
     L.launches++;
     return cudaGetLastError();
 }

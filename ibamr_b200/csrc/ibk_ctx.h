@@ -68,6 +68,10 @@ struct LevelState
     double* F = nullptr;
     double* tmp = nullptr;    // [ndim][stride] permutation scratch
     double* extra[3] = { nullptr, nullptr, nullptr }; // optional columns 3..5 (X_current, X_new, auxiliary), lazily allocated
+    // second copy of every column in use: the re-bin permutes all columns in ONE kernel from the column into its shadow and
+    // swaps the two (allocated at the first re-bin, dropped when the capacity changes)
+    double* shadow[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    long long shadow_stride = 0;
     // Lagrangian force elements (ibk_force_set_*), device tables + the inverse of the storage order
     ForceTables force;
     std::vector<void*> force_allocs; // every device array behind `force`

@@ -101,6 +101,18 @@ cudaError_t wrap_positions(Launcher& L, const DomainGeom& dg, double* d_X, long 
 // out[c][i] = in[c][perm[i]] for c < ncols (SoA gather through the sort permutation)
 cudaError_t gather_columns(Launcher& L, const double* d_in, long long in_stride, double* d_out, long long out_stride,
                            const uint32_t* d_perm, int n, int ncols);
+// out[k][c][i] = in[k][c][perm[i]] for up to 6 column sets of ncols columns in one launch (one read of perm, all gathers of a
+// marker in flight together)
+struct GatherSets
+{
+    const double* in[6];
+    double* out[6];
+    int nsets;
+};
+cudaError_t gather_column_sets(Launcher& L, const GatherSets& sets, long long stride, const uint32_t* d_perm, int n, int ncols);
+// within every run of keys that agree above `tie_bits`, orders the (key, value) pairs by the full key (insertion sort by the
+// thread of the run's first element; runs are cells: a handful of markers)
+cudaError_t sort_ties(Launcher& L, uint64_t* keys, uint32_t* vals, int n, int tie_bits);
 cudaError_t scatter_columns(Launcher& L, const double* d_in, long long in_stride, double* d_out, long long out_stride,
                             const uint32_t* d_perm, int n, int ncols);
 cudaError_t extract_low32(Launcher& L, const uint64_t* d_keys, uint32_t* d_out, int n, int bits);

@@ -808,6 +808,8 @@ extern "C" int ibk_level_destroy(ibk_ctx* ctx)
         if (p) cudaFree(p);
     for (double* p : lv.extra)
         if (p) cudaFree(p);
+    for (double* p : lv.shadow)
+        if (p) cudaFree(p);
     for (void* p : lv.force_allocs) cudaFree(p);
     if (lv.pos_of_id) cudaFree(lv.pos_of_id);
     if (lv.d_missing) cudaFree(lv.d_missing);
@@ -1223,13 +1225,30 @@ extern "C" int ibk_rebin(ibk_ctx* ctx, int error_if_points_leave_domain)
     if (n > 0)
     {
         const uint32_t* perm = lv.bins.vals[lv.bins.sorted_in];
-        for (double** col : { &lv.X, &lv.U, &lv.F, &lv.extra[0], &lv.extra[1], &lv.extra[2] })
+        // all columns in one launch, each into its shadow; then column and shadow swap roles (no copy back)
+        if (lv.shadow_stride != lv.stride)
         {
-            if (!*col) continue;
-            // permute into the scratch column, then swap roles (no copy back)
-            CK(gather_columns(ctx->L, *col, lv.stride, lv.tmp, lv.stride, perm, n, ndim));
-            std::swap(*col, lv.tmp);
+            for (double*& sh : lv.shadow)
+            {
+                if (sh) cudaFree(sh);
+                sh = nullptr;
+            }
+            lv.shadow_stride = lv.stride;
         }
+        GatherSets gs;
+        std::memset(&gs, 0, sizeof(gs));
+        double** cols[6] = { &lv.X, &lv.U, &lv.F, &lv.extra[0], &lv.extra[1], &lv.extra[2] };
+        int which_col[6];
+        for (int k = 0; k < 6; ++k)
+        {
+            if (!*cols[k]) continue;
+            if (!lv.shadow[k]) CK(cudaMalloc(&lv.shadow[k], sizeof(double) * (size_t)lv.stride * ndim));
+            gs.in[gs.nsets] = *cols[k];
+            gs.out[gs.nsets] = lv.shadow[k];
+            which_col[gs.nsets++] = k;
+        }
+        CK(gather_column_sets(ctx->L, gs, lv.stride, perm, n, ndim));
+        for (int q = 0; q < gs.nsets; ++q) std::swap(*cols[which_col[q]], lv.shadow[which_col[q]]);
         if (lv.gid)
         {
             CK(extract_low32(ctx->L, lv.bins.keys[lv.bins.sorted_in], lv.gid, n, lv.bins.tie_bits));
