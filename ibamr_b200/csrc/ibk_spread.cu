@@ -1390,7 +1390,11 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
         if (bins.range_base[p] == tp.brick_base && bins.range_last[p] > bins.range_first[p]) any = true;
     if (!any) return cudaSuccess;
     static const bool no_tma = getenv("IBK_NO_TMA") != nullptr; // (debugging: every block takes the plain write-out)
-    constexpr bool MARCH = (NDIM == 3 && M <= 3);
+    // 3D, reach of at most 2 cells: the march kernel.  Reach 3 (IB_6, IB_5, BSPLINE_5 / 6, ...): the march kernel works (the
+    // whole parity suite passes with it) but its generic 6 x 6 x 6 consumer path is slower than the tile kernel
+    // (measured, 2^23 uniform markers on 512^3, IB_6: march 27.3 ms, tile 14.3 ms), so those take the tile kernel, like the
+    // 8-point kernel and 2D.
+    constexpr bool MARCH = (NDIM == 3 && M <= 2);
     // the first block per dimension may start at the array's first element when no stencil reaches outside the arrays and
     // the shifted block stays clear of the next block of the same colour
     args.clip_free = mv.clip_free ? 1 : 0;
@@ -1422,8 +1426,10 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
             args.dense_thresh = DENSE_BRICK_MARKERS; // part 1: the dense bricks are (were) done with part 2 / 0
     }
 
+    bool done = false;
     if constexpr (MARCH)
     {
+        done = true;
         using C = MarchCfg<K>;
         // planes are added to f by TMA when it can address the array and the block starts on an even x coordinate
         for (int a = 0; a < tp.ncomp; ++a)
@@ -1473,7 +1479,7 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
             L.launches++;
         }
     }
-    else
+    if (!done)
     {
         constexpr int R = TILE + 2 * M;
         constexpr int XO = M & 1;
