@@ -566,4 +566,43 @@ __device__ __forceinline__ void tma_store_commit_and_wait_read()
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+
+// Walks a slab row by row: a warp takes one row (contiguous in x) and calls f(I1, I2, x_first, x_last) with x advancing by
+// the lane stride 32 (coalesced 256-byte accesses, the row's index arithmetic done once per row); thin slabs (the x ghost
+// layers, a few elements per row) are walked with 32 / e0 rows per warp, one element per lane.
+template <class F>
+__device__ __forceinline__ void slab_rows(const int* lo, const int* hi, unsigned bx, unsigned nbx, F f)
+{
+    const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    const long long nrows = (long long)e1 * e2;
+    if (e0 >= 16)
+    {
+        // work item = (row, chunk of 128 elements): a slab of a few long rows (the z ghost layers: 3 x 518 rows of 519) still
+        // spreads over thousands of warps, each with four independent elements per lane in flight
+        constexpr int CHUNK = 128;
+        const int nch = (e0 + CHUNK - 1) / CHUNK;
+        const long long nitems = nrows * nch;
+        for (long long it = (long long)bx * wpb + warp; it < nitems; it += (long long)nbx * wpb)
+        {
+            const long long row = it / nch;
+            const int ch = (int)(it - row * nch);
+            const int k = (int)(row / e1);
+            const int xs = lo[0] + ch * CHUNK;
+            f(lo[1] + (int)(row - (long long)k * e1), lo[2] + k, xs + lane, min(hi[0], xs + CHUNK - 1));
+        }
+    }
+    else
+    {
+        const int rpw = 32 / e0, r = lane / e0, x = lo[0] + lane - r * e0;
+        for (long long g = (long long)bx * wpb + warp; g * rpw < nrows; g += (long long)nbx * wpb)
+        {
+            const long long row = g * rpw + r;
+            if (r >= rpw || row >= nrows) continue;
+            const int k = (int)(row / e1);
+            f(lo[1] + (int)(row - (long long)k * e1), lo[2] + k, x, x);
+        }
+    }
+}
+
 } // namespace ibk

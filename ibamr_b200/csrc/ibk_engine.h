@@ -126,9 +126,13 @@ struct HaloItem
     int off[3], ext[3]; // region in array coordinates
     long long buf_off;  // first element of the region in the message buffer
     long long count;
+    unsigned block0, nblocks; // the CTAs of the launch that work on this item (in proportion to its size)
 };
-// op 0: buffer <- regions (pack); 1: regions <- buffer (copy); 2: regions += buffer
-cudaError_t launch_halo_items(Launcher& L, const HaloItem* d_items, int n_items, long long max_count, double* buf, int op);
+// work (in warp work items of the row walker, ibk_device.cuh::slab_rows) and CTAs of a region
+long long region_work(const int* ext);
+unsigned region_blocks(const int* ext);
+// op 0: buffer <- regions (pack); 1: regions <- buffer (copy); 2: regions += buffer.  total_blocks = sum of nblocks.
+cudaError_t launch_halo_items(Launcher& L, const HaloItem* d_items, int n_items, unsigned total_blocks, double* buf, int op);
 
 // ibk_force.cu
 // Force elements by Lagrangian index plus, per node, the elements it takes part in (CSR), all on the device.

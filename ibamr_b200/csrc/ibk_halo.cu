@@ -138,32 +138,48 @@ cudaError_t launch_unpack(Launcher& L, double* arr, long long pitch, int n1, con
     return cudaGetLastError();
 }
 
-__global__ void halo_items_kernel(const HaloItem* __restrict__ items, double* __restrict__ buf, int op)
+long long region_work(const int* ext)
 {
-    const HaloItem it = items[blockIdx.y];
-    const long long e0 = it.ext[0], e01 = (long long)it.ext[0] * it.ext[1];
-    double* b = buf + it.buf_off;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < it.count; q += (long long)gridDim.x * blockDim.x)
-    {
-        const int k = (int)(q / e01);
-        const long long r = q - (long long)k * e01;
-        const int j = (int)(r / e0), i = (int)(r - (long long)j * e0);
-        double* a = it.ptr + ((long long)(it.off[2] + k) * it.n1 + (it.off[1] + j)) * it.pitch + (it.off[0] + i);
-        if (op == 0)
-            b[q] = *a;
-        else if (op == 1)
-            *a = b[q];
-        else
-            *a += b[q];
-    }
+    const long long rows = (long long)ext[1] * ext[2];
+    if (ext[0] >= 16) return rows * ((ext[0] + 127) / 128);
+    const int rpw = 32 / std::max(ext[0], 1);
+    return (rows + rpw - 1) / rpw;
+}
+unsigned region_blocks(const int* ext)
+{
+    return (unsigned)std::max<long long>(1, (region_work(ext) + 15) / 16); // 16 warp work items per CTA of 8 warps
 }
 
-cudaError_t launch_halo_items(Launcher& L, const HaloItem* d_items, int n_items, long long max_count, double* buf, int op)
+// All regions of a message (or of one wave of it) in one launch: the CTAs are dealt out to the items in proportion to
+// their size, a warp walks a row of its region (contiguous in the array and in the buffer) or a few short rows.
+__global__ void halo_items_kernel(const HaloItem* __restrict__ items, int n_items, double* __restrict__ buf, int op)
 {
-    if (n_items <= 0) return cudaSuccess;
-    // grid.x follows the largest region (4 elements per thread); the blocks beyond a small region's end leave at once
-    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(1024, (max_count + 1023) / 1024));
-    halo_items_kernel<<<dim3(gx, (unsigned)n_items), 256, 0, L.stream>>>(d_items, buf, op);
+    int lo_i = 0, hi_i = n_items - 1; // the last item with block0 <= blockIdx.x
+    while (lo_i < hi_i)
+    {
+        const int mid = (lo_i + hi_i + 1) >> 1;
+        if (items[mid].block0 <= blockIdx.x) lo_i = mid;
+        else hi_i = mid - 1;
+    }
+    const HaloItem& it = items[lo_i];
+    const int lo[3] = { 0, 0, 0 }, hi[3] = { it.ext[0] - 1, it.ext[1] - 1, it.ext[2] - 1 };
+    double* b = buf + it.buf_off;
+    slab_rows(lo, hi, blockIdx.x - it.block0, it.nblocks, [&](int j, int k, int x0, int x1) {
+        double* arow = it.ptr + ((long long)(it.off[2] + k) * it.n1 + (it.off[1] + j)) * it.pitch + it.off[0];
+        double* brow = b + ((long long)k * it.ext[1] + j) * it.ext[0];
+        for (int x = x0; x <= x1; x += 32)
+        {
+            if (op == 0) brow[x] = arow[x];
+            else if (op == 1) arow[x] = brow[x];
+            else arow[x] += brow[x];
+        }
+    });
+}
+
+cudaError_t launch_halo_items(Launcher& L, const HaloItem* d_items, int n_items, unsigned total_blocks, double* buf, int op)
+{
+    if (n_items <= 0 || total_blocks == 0) return cudaSuccess;
+    halo_items_kernel<<<total_blocks, 256, 0, L.stream>>>(d_items, n_items, buf, op);
     L.launches++;
     return cudaGetLastError();
 }

@@ -58,44 +58,6 @@ struct HaloArgs
     HaloSrc src[HALO_MAXSRC];
 };
 
-// Walks a slab row by row: a warp takes one row (contiguous in x) and calls f(I1, I2, x_first, x_last) with x advancing by
-// the lane stride 32 (coalesced 256-byte accesses, the row's index arithmetic done once per row); thin slabs (the x ghost
-// layers, a few elements per row) are walked with 32 / e0 rows per warp, one element per lane.
-template <class F>
-__device__ __forceinline__ void slab_rows(const int* lo, const int* hi, unsigned bx, unsigned nbx, F f)
-{
-    const int e0 = hi[0] - lo[0] + 1, e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1;
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
-    const long long nrows = (long long)e1 * e2;
-    if (e0 >= 16)
-    {
-        // work item = (row, chunk of 128 elements): a slab of a few long rows (the z ghost layers: 3 x 518 rows of 519) still
-        // spreads over thousands of warps, each with four independent elements per lane in flight
-        constexpr int CHUNK = 128;
-        const int nch = (e0 + CHUNK - 1) / CHUNK;
-        const long long nitems = nrows * nch;
-        for (long long it = (long long)bx * wpb + warp; it < nitems; it += (long long)nbx * wpb)
-        {
-            const long long row = it / nch;
-            const int ch = (int)(it - row * nch);
-            const int k = (int)(row / e1);
-            const int xs = lo[0] + ch * CHUNK;
-            f(lo[1] + (int)(row - (long long)k * e1), lo[2] + k, xs + lane, min(hi[0], xs + CHUNK - 1));
-        }
-    }
-    else
-    {
-        const int rpw = 32 / e0, r = lane / e0, x = lo[0] + lane - r * e0;
-        for (long long g = (long long)bx * wpb + warp; g * rpw < nrows; g += (long long)nbx * wpb)
-        {
-            const long long row = g * rpw + r;
-            if (r >= rpw || row >= nrows) continue;
-            const int k = (int)(row / e1);
-            f(lo[1] + (int)(row - (long long)k * e1), lo[2] + k, x, x);
-        }
-    }
-}
-
 // The local halo operations as lists of box operations worked out once per level (build_halo_plan):
 //   MODE 0  dst box <- src box                      ghost fill of u
 //   MODE 1  dst box += src_0 box + src_1 box + ...   ghost accumulation of f: the sources of a box in canonical order
@@ -350,8 +312,9 @@ struct ItemTable
     int n = 0;
     // waves: maximal runs of consecutive items whose regions are pairwise disjoint; one launch adds a wave, the waves follow
     // each other in item order, so two overlapping regions are still added in the order of the list
-    std::vector<int> wave_start; // [n_waves + 1]
-    std::vector<long long> wave_max;
+    std::vector<int> wave_start;      // [n_waves + 1]
+    std::vector<unsigned> wave_blocks; // CTAs per wave
+    unsigned all_blocks = 0;           // CTAs when all items go in one launch (pack)
     long long max_count = 0;
 };
 struct LevelExtra
@@ -446,14 +409,6 @@ void hbox_minus(const HBox& a, const HBox& b, std::vector<HBox>& out)
         cur.lo[d] = in.lo[d];
         cur.hi[d] = in.hi[d];
     }
-}
-// warp work items of a region (as slab_rows cuts it)
-long long region_work(const int* ext)
-{
-    const long long rows = (long long)ext[1] * ext[2];
-    if (ext[0] >= 16) return rows * ((ext[0] + 127) / 128);
-    const int rpw = 32 / std::max(ext[0], 1);
-    return (rows + rpw - 1) / rpw;
 }
 } // namespace
 
@@ -742,7 +697,7 @@ static int build_halo_plan(ibk_ctx* ctx)
         for (RegionMulti& op : v)
         {
             op.block0 = nb;
-            op.nblocks = (unsigned)std::max<long long>(1, (region_work(op.ext) + 15) / 16);
+            op.nblocks = region_blocks(op.ext);
             nb += op.nblocks;
         }
         hp.n_ops[t] = (int)v.size();
@@ -1827,19 +1782,33 @@ static int item_table(ibk_ctx* ctx, int which, int n_items, const int* patch, co
             for (int d = 0; d < 3; ++d) ov = ov && h[k].off[d] < h[k2].off[d] + h[k2].ext[d] && h[k2].off[d] < h[k].off[d] + h[k].ext[d];
             clash = clash || ov;
         }
-        if (clash)
-        {
-            t.wave_start.push_back(k);
-            t.wave_max.push_back(0);
-        }
-        if (t.wave_max.empty()) t.wave_max.push_back(0);
-        t.wave_max.back() = std::max(t.wave_max.back(), h[k].count);
+        if (clash) t.wave_start.push_back(k);
     }
     t.wave_start.push_back(n_items);
+    // CTAs: one numbering for the single-launch pack (block0 over all items) is not compatible with per-wave launches, so
+    // the table is kept twice: [0, n) numbered over all items, [n, 2n) numbered per wave
+    h.resize(2 * (size_t)n_items);
+    for (int k = 0; k < n_items; ++k)
+    {
+        h[k].nblocks = region_blocks(h[k].ext);
+        h[k].block0 = t.all_blocks;
+        t.all_blocks += h[k].nblocks;
+        h[n_items + k] = h[k];
+    }
+    for (size_t w = 0; w + 1 < t.wave_start.size(); ++w)
+    {
+        unsigned nb = 0;
+        for (int k = t.wave_start[w]; k < t.wave_start[w + 1]; ++k)
+        {
+            h[n_items + k].block0 = nb;
+            nb += h[n_items + k].nblocks;
+        }
+        t.wave_blocks.push_back(nb);
+    }
     if (n_items > 0)
     {
-        CK(cudaMalloc(&t.d_items, sizeof(HaloItem) * (size_t)n_items));
-        CK(cudaMemcpy(t.d_items, h.data(), sizeof(HaloItem) * (size_t)n_items, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&t.d_items, sizeof(HaloItem) * 2 * (size_t)n_items));
+        CK(cudaMemcpy(t.d_items, h.data(), sizeof(HaloItem) * 2 * (size_t)n_items, cudaMemcpyHostToDevice));
     }
     ex->item_tables.push_back(t);
     *out = &ex->item_tables.back();
@@ -1859,7 +1828,7 @@ extern "C" int ibk_halo_pack_many(ibk_ctx* ctx, int which, int n_items, const in
     GRID_DEPS(which);
     const ItemTable* t = nullptr;
     if (int rc = item_table(ctx, which, n_items, patch, axis, lower, upper, buf_offset, &t)) return rc;
-    CK(launch_halo_items(ctx->L, t->d_items, n_items, t->max_count, d_buf, 0));
+    CK(launch_halo_items(ctx->L, t->d_items, n_items, t->all_blocks, d_buf, 0));
     return IBK_OK;
 }
 extern "C" int ibk_halo_unpack_many(ibk_ctx* ctx, int which, int n_items, const int* patch, const int* axis, const int* lower,
@@ -1877,7 +1846,7 @@ extern "C" int ibk_halo_unpack_many(ibk_ctx* ctx, int which, int n_items, const 
     for (size_t w = 0; w + 1 < t->wave_start.size(); ++w)
     {
         const int k0 = t->wave_start[w], k1 = t->wave_start[w + 1];
-        if (k1 > k0) CK(launch_halo_items(ctx->L, t->d_items + k0, k1 - k0, t->wave_max[w], const_cast<double*>(d_buf), mode == 0 ? 1 : 2));
+        if (k1 > k0) CK(launch_halo_items(ctx->L, t->d_items + n_items + k0, k1 - k0, t->wave_blocks[w], const_cast<double*>(d_buf), mode == 0 ? 1 : 2));
     }
     return IBK_OK;
 }

@@ -952,7 +952,7 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : (KT
     // stencil-evaluation task of this thread for a window: the global loads are issued by fetch() -- for window
     // w + 1 before the accumulation of window w starts, so their latency hides behind it -- and consumed by
     // evaluate() at the top of the window.
-    int t_i;
+    int t_i, t_fp = 0; // (t_fp: first block coordinate of the marker's BRICK footprint along the task's dimension)
     double t_xs, t_xr, t_v;
     auto fetch = [&](int off, int par) {
         const int cnt = min(cap, total - off);
@@ -970,6 +970,12 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : (KT
         const int i = bfirst[p] + (lp - bpre[p]);
         if (d == 0 && off > 0) relb[par * cap + m] = 0;
         t_i = i;
+        {
+            const int q = d_colouring<NDIM, NC>.order[p]; // brick in the tile, x fastest
+            const int ld = (q >> (2 * d)) & 3;
+            const int blo_d = (d == 0) ? blo[0] : (d == 1) ? blo[1] : blo[2];
+            t_fp = TILE * t[d] + BRICK * ld - M - blo_d;
+        }
         t_xs = __ldg(&Xp[d * args.x_stride + i]);
         t_xr = Xr ? __ldg(&Xr[d * args.x_stride + i]) : 0.0;
         t_v = 1.0;
@@ -990,7 +996,9 @@ __global__ void __launch_bounds__(SPREAD_THREADS, (KTraits<K>::M <= 2) ? 3 : (KT
         int l;
         stencil_1d<K>(t_xs, Xr ? t_xr : t_xs, xl_s, dx_s, l, w, d == cg.axis);
         const int r0 = l + G - blo_s; // first stencil point relative to the block
-        const bool fits = r0 >= 0 && r0 + W <= ((d == 0) ? RX : R);
+        // inside the block AND inside the footprint of the marker's brick (what the brick colours rely on: a stencil that
+        // left its brick's footprint -- positions moved since the binning -- goes to the fix-up instead of racing)
+        const bool fits = r0 >= max(t_fp, 0) && r0 + W <= min(t_fp + BRICK + 2 * M, (d == 0) ? RX : R);
         const double scale = (d == LD) ? t_v * inv_vol : 1.0;
 #pragma unroll
         for (int j = 0; j < W; ++j) wgt[(m * NDIM + d) * W + j] = w[j] * scale;
