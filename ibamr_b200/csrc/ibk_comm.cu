@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -420,6 +421,12 @@ extern "C" int ibk_comm_init(ibk_ctx* ctx, const void* id128, int rank, int nran
     NcclApi::Uid id;
     std::memcpy(id.internal, id128, 128);
     NCK(n.CommInitRank(&c->nccl_comm, nranks, id, rank));
+    {
+        // the NCCL kernels of an exchange need somewhere to run while the spread's persistent CTAs occupy the SMs
+        // (IBK_COMM_RESERVE_SMS overrides; measured on 2 GPUs: see DESIGN.md)
+        const char* env = getenv("IBK_COMM_RESERVE_SMS");
+        ctx->L.reserve_sms = env ? atoi(env) : 8;
+    }
     CCK(cudaMalloc(&c->d_counts, sizeof(double) * (size_t)nranks * nranks));
     return IBK_OK;
 }

@@ -82,6 +82,9 @@ struct Launcher
 {
     cudaStream_t stream = 0;
     long long launches = 0;
+    // SMs the persistent kernels leave free: with a communicator the messages of the halo exchange (NCCL kernels on the
+    // communication stream) must be able to start while the spread's persistent CTAs hold their SMs for milliseconds
+    int reserve_sms = 0;
 };
 
 // ibk_sort.cu

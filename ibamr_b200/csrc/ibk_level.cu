@@ -312,10 +312,17 @@ struct ItemTable
     int n = 0;
     // waves: maximal runs of consecutive items whose regions are pairwise disjoint; one launch adds a wave, the waves follow
     // each other in item order, so two overlapping regions are still added in the order of the list
+    std::vector<HaloItem> h_items;    // host copy (for building the add table)
     std::vector<int> wave_start;      // [n_waves + 1]
     std::vector<unsigned> wave_blocks; // CTAs per wave
     unsigned all_blocks = 0;           // CTAs when all items go in one launch (pack)
     long long max_count = 0;
+    // unpack-ADD in one launch: the destination regions cut into boxes that each have ONE ordered list of buffer sources
+    // (built for the buffer address add_buf at the first unpack-add; region_items_kernel<1>)
+    RegionMulti* d_add_ops = nullptr;
+    int n_add_ops = 0;
+    unsigned add_blocks = 0;
+    const double* add_buf = nullptr;
 };
 struct LevelExtra
 {
@@ -340,7 +347,10 @@ void extra_drop(ibk_ctx* ctx)
             for (void* p : g_extra[i].second->halo.allocs) cudaFree(p);
             if (g_extra[i].second->halo.d_wall_jobs) cudaFree(g_extra[i].second->halo.d_wall_jobs);
             for (ItemTable& t : g_extra[i].second->item_tables)
+            {
                 if (t.d_items) cudaFree(t.d_items);
+                if (t.d_add_ops) cudaFree(t.d_add_ops);
+            }
             delete g_extra[i].second;
             g_extra.erase(g_extra.begin() + i);
             return;
@@ -1807,6 +1817,7 @@ static int item_table(ibk_ctx* ctx, int which, int n_items, const int* patch, co
     }
     if (n_items > 0)
     {
+        t.h_items.assign(h.begin(), h.begin() + n_items);
         CK(cudaMalloc(&t.d_items, sizeof(HaloItem) * 2 * (size_t)n_items));
         CK(cudaMemcpy(t.d_items, h.data(), sizeof(HaloItem) * 2 * (size_t)n_items, cudaMemcpyHostToDevice));
     }
@@ -1842,6 +1853,108 @@ extern "C" int ibk_halo_unpack_many(ibk_ctx* ctx, int which, int n_items, const 
     GRID_DEPS(which);
     const ItemTable* t = nullptr;
     if (int rc = item_table(ctx, which, n_items, patch, axis, lower, upper, buf_offset, &t)) return rc;
+    if (mode == 1 && t->wave_start.size() > 2)
+    {
+        // overlapping regions: ONE launch over boxes that each add their buffer sources in list order
+        ItemTable* tt = const_cast<ItemTable*>(t);
+        if (!tt->d_add_ops || tt->add_buf != d_buf)
+        {
+            if (tt->d_add_ops) cudaFree(tt->d_add_ops);
+            tt->d_add_ops = nullptr;
+            struct Cell
+            {
+                double* dst;
+                HBox box; // in the array coordinates of dst
+                std::vector<int> src;
+            };
+            std::vector<Cell> cells;
+            const std::vector<HaloItem>& H = tt->h_items;
+            for (int k = 0; k < n_items; ++k)
+            {
+                HBox B;
+                for (int d = 0; d < 3; ++d)
+                {
+                    B.lo[d] = H[k].off[d];
+                    B.hi[d] = H[k].off[d] + H[k].ext[d] - 1;
+                }
+                std::vector<Cell> next;
+                std::vector<HBox> uncovered{ B };
+                for (Cell& c : cells)
+                {
+                    HBox J;
+                    if (c.dst != H[k].ptr || !hbox_intersect(c.box, B, J))
+                    {
+                        next.push_back(c);
+                        continue;
+                    }
+                    Cell both{ c.dst, J, c.src };
+                    both.src.push_back(k);
+                    next.push_back(both);
+                    std::vector<HBox> rest;
+                    hbox_minus(c.box, J, rest);
+                    for (const HBox& R : rest) next.push_back(Cell{ c.dst, R, c.src });
+                    std::vector<HBox> unc2;
+                    for (const HBox& U : uncovered) hbox_minus(U, J, unc2);
+                    uncovered.swap(unc2);
+                }
+                for (const HBox& U : uncovered) next.push_back(Cell{ H[k].ptr, U, std::vector<int>{ k } });
+                cells.swap(next);
+            }
+            std::vector<RegionMulti> ops;
+            unsigned nb = 0;
+            for (const Cell& c : cells)
+            {
+                // (more sources than a RegionMulti holds: a second box over the same elements, later in the list)
+                for (size_t s0 = 0; s0 < c.src.size(); s0 += REGION_MAXSRC)
+                {
+                    RegionMulti op;
+                    std::memset(&op, 0, sizeof(op));
+                    const HaloItem& first = H[c.src[0]];
+                    op.dst = c.dst;
+                    op.dst_pitch = first.pitch;
+                    op.dst_n1 = first.n1;
+                    for (int d = 0; d < 3; ++d)
+                    {
+                        op.dst_off[d] = c.box.lo[d];
+                        op.ext[d] = c.box.hi[d] - c.box.lo[d] + 1;
+                    }
+                    for (size_t q = s0; q < std::min(c.src.size(), s0 + REGION_MAXSRC); ++q)
+                    {
+                        const HaloItem& it = H[c.src[q]];
+                        const int cc = op.nsrc++;
+                        op.src[cc] = d_buf + it.buf_off; // the item's region, dense in the buffer
+                        op.src_pitch[cc] = it.ext[0];
+                        op.src_n1[cc] = it.ext[1];
+                        for (int d = 0; d < 3; ++d) op.src_off[cc][d] = c.box.lo[d] - it.off[d];
+                    }
+                    op.block0 = nb;
+                    op.nblocks = region_blocks(op.ext);
+                    nb += op.nblocks;
+                    ops.push_back(op);
+                }
+            }
+            // boxes over the same elements (a cell split for its many sources) must not run in one launch: rare enough to
+            // fall back to the waves
+            bool split = false;
+            for (const Cell& c : cells) split = split || c.src.size() > (size_t)REGION_MAXSRC;
+            if (!split && !ops.empty())
+            {
+                CK(cudaMalloc(&tt->d_add_ops, sizeof(RegionMulti) * ops.size()));
+                CK(cudaMemcpyAsync(tt->d_add_ops, ops.data(), sizeof(RegionMulti) * ops.size(), cudaMemcpyHostToDevice, ctx->L.stream));
+                CK(cudaStreamSynchronize(ctx->L.stream));
+                tt->n_add_ops = (int)ops.size();
+                tt->add_blocks = nb;
+                tt->add_buf = d_buf;
+            }
+        }
+        if (tt->d_add_ops)
+        {
+            region_items_kernel<1><<<tt->add_blocks, 256, 0, ctx->L.stream>>>(tt->d_add_ops, tt->n_add_ops);
+            ctx->L.launches++;
+            CK(cudaGetLastError());
+            return IBK_OK;
+        }
+    }
     // one launch per wave of pairwise disjoint regions, the waves in list order (fixed order of the additions)
     for (size_t w = 0; w + 1 < t->wave_start.size(); ++w)
     {

@@ -1482,7 +1482,7 @@ static cudaError_t launch_spread_t(Launcher& L, const TileParams& tp, const Bins
             int dev = 0, sms = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            const int grid = std::max(1, std::min(n_items, sms > 0 ? sms : 148));
+            const int grid = std::max(1, std::min(n_items, (sms > 0 ? sms : 148) - L.reserve_sms));
             kfn<<<grid, C::NT, smem, L.stream>>>(tp, maps, args);
             L.launches++;
         }

@@ -1,1 +1,2 @@
-timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r2_t23.log 2>&1; tail -4 gpurun_out/r2_t23.log
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r2_t25.log 2>&1; tail -4 gpurun_out/r2_t25.log
+timeout 300 python scripts/loopback_step.py 512 23 3 2>&1 | tail -1
