@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libibk.so")
+LIB_PATH = os.environ.get("IBK_LIB") or os.path.join(HERE, "libibk.so")  # IBK_LIB: an experiment build (scripts/build_variant.sh)
 
 IBK_MAX_DIM = 3
 

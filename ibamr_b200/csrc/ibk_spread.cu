@@ -105,6 +105,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // =============================================================================================
 // 3D march kernel
@@ -117,6 +121,12 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+#ifndef IBK_MARCH_NBAR
+#define IBK_MARCH_NBAR 1
+#endif
+#ifndef IBK_MARCH_SUBARRIVE
+#define IBK_MARCH_SUBARRIVE 1
+#endif
 constexpr int MARCH_CELLS = 2 * TILE;          // column edge: 2 x 2 marker tiles
 constexpr int MARCH_BR = MARCH_CELLS / BRICK;  // 8 bricks per row / rows per layer
 constexpr int MARCH_MAX_LAYERS = 32;
@@ -162,8 +172,8 @@ __device__ __forceinline__ void march_chains(uint32_t (&adr)[2], int& k, int ken
 {
     if (k >= kend) return;
     // software pipeline: the record of iteration k + 1 is loaded while the ring words of iteration k are read, updated
-    // and written, so only the ring's load -> fma -> store chain separates two markers of a brick.  (The load after the
-    // last record of a chain reads the next record or the dummy behind the buffer: unused.)
+    // and written, so only the ring's load -> fma -> store chain separates two markers of a brick.  On return adr[] points at
+    // the first record that was not consumed.
     int2 zo[N];
     double wx[N], wy[N];
     double2 wz[N];
@@ -192,6 +202,8 @@ __device__ __forceinline__ void march_chains(uint32_t (&adr)[2], int& k, int ken
             wa[c] = wxy * wz[c].x;
             wb[c] = wxy * wz[c].y;
         }
+        // (the loads after a chain's last record are wasted wavefronts, yet guarding them -- by a branch or by predicated
+        // loads -- measured 6 % slower)
 #pragma unroll
         for (int c = 0; c < N; ++c)
         {
@@ -210,7 +222,7 @@ __device__ __forceinline__ void march_chains(uint32_t (&adr)[2], int& k, int ken
         __syncwarp();
     }
 #pragma unroll
-    for (int c = 0; c < N; ++c) adr[c] -= REC; // the record loaded ahead was not consumed
+    for (int c = 0; c < N; ++c) adr[c] -= REC; // the record after the last one was not consumed
 }
 
 template <int K>
@@ -413,15 +425,21 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
             const bool fits = r0[0] >= max(fx, 0) && r0[0] + W <= min(fx + FZ, RX) && r0[1] >= max(fy, 0) && r0[1] + W <= min(fy + FZ, R) &&
                               r0[2] >= zlo && r0[2] + W <= zlo + FZ;
             const int xy = 8 * (r0[1] * RX + r0[0]);
+            int zoff[W];
 #pragma unroll
             for (int j = 0; j < W; ++j)
             {
                 // a stencil that does not fit: FAST4 adds it to the sink (branch-free consumer), else it is skipped
                 const int o = fits ? ((r0[2] + j) % NRING) * PLANE_B + xy : (C::FAST4 ? SINK_OFF : -1);
                 if (C::FAST4)
-                    *reinterpret_cast<int*>(r + 32 * (j & 1) + 4 * (j >> 1)) = o;
+                    zoff[j] = o;
                 else
                     reinterpret_cast<int*>(r)[j] = o;
+            }
+            if (C::FAST4) // planes (g, g + 2) of a lane group sit side by side: one 8-byte store each (4-byte stores of 32 records
+            {             // 144 bytes apart hit 8 banks four times over)
+                *reinterpret_cast<int2*>(r) = make_int2(zoff[0], zoff[2]);
+                *reinterpret_cast<int2*>(r + 32) = make_int2(zoff[1], zoff[3]);
             }
             if (!fits) flag_exception(args, i, a);
         }
@@ -514,7 +532,15 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
                         march_chains<2, C::REC>(adr, k, len[1], ring_lane, lane_wx, lane_wy);
                         march_chains<1, C::REC>(adr, k, len[0], ring_lane, lane_wx, lane_wy);
                         // the next sub-phase of this row touches the neighbouring bricks: wait for the other half of the row
-                        if (sp + 1 < NC) named_bar_sync(4 + rslot, 32 * C::WPR);
+                        // (of the other half's bricks only brick 4, the upper half's first, is a neighbour of a brick of the next
+                        // sub-phase, and that is the lower half's brick 3: the upper half announces, the lower half waits)
+                        if (sp + 1 < NC)
+                        {
+                            if (IBK_MARCH_SUBARRIVE && half == 1)
+                                named_bar_arrive(4 + rslot, 32 * C::WPR);
+                            else
+                                named_bar_sync(4 + rslot, 32 * C::WPR);
+                        }
                     }
                     if constexpr (!C::FAST4)
                     {
@@ -551,7 +577,21 @@ __global__ void __launch_bounds__(MarchCfg<K>::NT, 1)
             {
                 // (a row slot without a row in this colour: FAST4 has 8 rows in 2 colours of 4, so this does not happen)
             }
-            if (ph + 1 < NC) named_bar_sync(1, 32 * NCONS);
+            if (ph + 1 < NC)
+            {
+                if constexpr (C::FAST4 && IBK_MARCH_NBAR)
+                {
+                    // row 2 s + 1 overlaps rows 2 s (this pair's own) and 2 s + 2 (the next pair's) only: the pair tells the pair
+                    // before it that its even row is done and waits for the pair after it, not for all four rows
+                    if (rslot > 0) named_bar_arrive(8 + rslot, 64 * C::WPR);
+                    if (rslot + 1 < NCW)
+                        named_bar_sync(8 + rslot + 1, 64 * C::WPR);
+                    else
+                        named_bar_sync(8, 32 * C::WPR); // (the last pair: its own two warps)
+                }
+                else
+                    named_bar_sync(1, 32 * NCONS);
+            }
         }
         fence_proxy_async_smem(); // this thread's writes to the ring -> visible to the TMA stores of the flusher
     };

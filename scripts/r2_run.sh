@@ -1,2 +1,2 @@
-timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r2_t25.log 2>&1; tail -4 gpurun_out/r2_t25.log
-timeout 300 python scripts/loopback_step.py 512 23 3 2>&1 | tail -1
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r2_t26.log 2>&1; tail -3 gpurun_out/r2_t26.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_b26.json 2> gpurun_out/r2_b26.err; python scripts/bench_brief.py < gpurun_out/r2_b26.json
