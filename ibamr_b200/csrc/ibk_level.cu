@@ -2131,6 +2131,13 @@ static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo, int part = 
                 const int n = ps.upper[d] - ps.lower[d] + 1;
                 mv.sel_lo[d] = (lv.G + reach) / 16 + 1;     // 16 t - reach > G: clear of the low ghosts and the boundary face
                 mv.sel_hi[d] = (lv.G + n - 17 - reach) / 16; // 16 t + 16 + reach <= G + n - 1: clear of the high face and ghosts
+                if (op == 1 && lv.ndim == 3 && d < 2)
+                {
+                    // the march kernel works on columns of 2 x 2 tiles: a column cut by the selection would be marched
+                    // twice, half empty each time (measured: + 0.4 ms on the C5 shard).  Whole columns go to one part.
+                    mv.sel_lo[d] += mv.sel_lo[d] & 1;
+                    mv.sel_hi[d] -= !(mv.sel_hi[d] & 1);
+                }
             }
         }
         std::string err;
