@@ -518,6 +518,23 @@ class IBMethodB200:
         assert a.size == b.size == self.ndim * 2 * self.ndim
         self.ctx.check(self.ctx.lib.ibk_level_set_wall_bc(self.ctx.h, _dp(a), _dp(b)))
 
+    # -- N3: AMR transfer operators between two levels on one device (one IBMethodB200 / context per level) ----
+    def prolongFrom(self, coarse, ratio, which="f"):
+        """this (finer) level's `which` := CONSERVATIVE_LINEAR_REFINE of the coarser level's: f_prolongation_scheds[ln]->fillData
+        before the spread on this level (LDataManager.cpp:611-614).  Returns the number of fine points written."""
+        r = np.ascontiguousarray(ratio, dtype=np.int32)
+        n = C.c_longlong(0)
+        self.ctx.check(self.ctx.lib.ibk_amr_refine_side(self.ctx.h, coarse.ctx.h, 0 if which == "u" else 1, _ip(r), C.byref(n)))
+        return n.value
+
+    def coarsenFrom(self, fine, ratio, which="u"):
+        """this (coarser) level's `which` := CONSERVATIVE_COARSEN of the finer level's: f_synch_scheds[ln]->coarsenData before
+        the interpolation (LDataManager.cpp:728-734).  Returns the number of coarse points written."""
+        r = np.ascontiguousarray(ratio, dtype=np.int32)
+        n = C.c_longlong(0)
+        self.ctx.check(self.ctx.lib.ibk_amr_coarsen_side(self.ctx.h, fine.ctx.h, 0 if which == "u" else 1, _ip(r), C.byref(n)))
+        return n.value
+
     def getPatchLists(self, patch):
         """LIndexSetData::cacheLocalIndices for one patch: (lag_idx[n], periodic_shifts[n][ndim], interior[n] as bool)."""
         n = C.c_int(0)

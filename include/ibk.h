@@ -453,6 +453,20 @@ int ibk_spread_end(ibk_ctx* ctx);
  * ibk_spread_fold_walls runs it (once per spread; ibk_spread_force, ibk_halo_local(f) and ibk_halo_accumulate_post call it). */
 int ibk_level_set_wall_bc(ibk_ctx* ctx, const double* acoef, const double* bcoef);
 int ibk_spread_fold_walls(ibk_ctx* ctx);
+/* AMR transfer operators either side of the path (N3 of SURVEY.md 8(f)), side-centred data, between two levels registered
+ * on the SAME device (one context per level; `fine`'s index space is `coarse`'s refined by ratio[ndim]).
+ *   ibk_amr_refine_side(fine, coarse, 1, ratio):  f_prolongation_scheds[ln]->fillData before the spread on level ln
+ *     (LDataManager.cpp:611-614; "CONSERVATIVE_LINEAR_REFINE", src/IB/IBHierarchyIntegrator.cpp:374-377): every point of the
+ *     fine arrays, ghosts included, whose coarse stencil lies inside a coarse patch's array (fill the coarse ghosts first);
+ *   ibk_amr_coarsen_side(coarse, fine, 0, ratio): f_synch_scheds[ln]->coarsenData before the interpolation, finest level
+ *     first (LDataManager.cpp:728-734; "CONSERVATIVE_COARSEN", IBHierarchyIntegrator.cpp:369-372): the coarse patches' own
+ *     sides that the own sides of a fine patch tile.
+ * The operators are SAMRAI's CartesianSideDoubleConservativeLinearRefine / CartesianSideDoubleWeightedAverage (third party,
+ * not in the reference tree): restated from their published algorithm, see csrc/ibk_amr.cu.  which: 0 = u, 1 = f.
+ * n_points (may be null): points written.  The work runs on the destination context's stream, ordered after everything
+ * queued on the source context's stream. */
+int ibk_amr_refine_side(ibk_ctx* fine, ibk_ctx* coarse, int which, const int* ratio, long long* n_points);
+int ibk_amr_coarsen_side(ibk_ctx* coarse, ibk_ctx* fine, int which, const int* ratio, long long* n_points);
 /* LDataManager::interp core (LDataManager.cpp:698-813) as IBMethod::interpolateVelocity calls it
  * (IBMethod.cpp:672-694): (fill_halo != 0) ghost fill of u among this process's patches incl.
  * periodic wrap (replaces u_ghost_fill_scheds[ln]->fillData, :744), then U = J[u]. */

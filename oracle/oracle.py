@@ -426,6 +426,115 @@ def fold_walls(level: Level, p, arrays, acoef, bcoef):
     return arrays
 
 
+def _amr_index(level: Level, p, axis, d):
+    """index of element 0 of patch p's side array (component axis) along dimension d"""
+    return level.boxes[p][0][d] - level.gcw[d]
+
+
+def amr_refine_side(coarse: Level, fine: Level, ratio, c_arrays, f_arrays):
+    """f_arrays[pf][axis] := CONSERVATIVE_LINEAR_REFINE(c_arrays[pc][axis]) (f_prolongation_scheds[ln]->fillData,
+    LDataManager.cpp:611-614; registered src/IB/IBHierarchyIntegrator.cpp:374-377).  The operator is SAMRAI's
+    CartesianSideDoubleConservativeLinearRefine (third party, IBSAMRAI2, not under /root/reference): restated from its
+    published algorithm (Fortran cartclinrefsidedoub{2,3}d{0,1,2}) -- PARITY UNPINNED, no reference fixture holds its output.
+    Every fine point (ghosts included) whose coarse stencil lies inside a coarse patch's array is written; coarse patches
+    in list order.  Arrays are [z][y][x] with ghosts.  Returns the number of points written."""
+    ndim = fine.ndim
+    written = 0
+    for pf in range(len(fine.boxes)):
+        for pc in range(len(coarse.boxes)):
+            for a in range(ndim):
+                C_, F_ = c_arrays[pc][a], f_arrays[pf][a]
+                idx_f, idx_c, ir = [], [], []
+                empty = False
+                for d in range(ndim):
+                    side = 1 if d == a else 0
+                    r = ratio[d]
+                    cu_lo = coarse.boxes[pc][0][d] - coarse.gcw[d] + 1
+                    cu_hi = coarse.boxes[pc][1][d] + coarse.gcw[d] + side - 1
+                    flo = max(fine.boxes[pf][0][d] - fine.gcw[d], cu_lo * r)
+                    fhi = min(fine.boxes[pf][1][d] + fine.gcw[d] + side, cu_hi * r + r - 1)
+                    if fhi < flo:
+                        empty = True
+                        break
+                    i = np.arange(flo, fhi + 1)
+                    ic = np.floor_divide(i, r)
+                    idx_f.append(i - _amr_index(fine, pf, a, d))
+                    idx_c.append(ic - _amr_index(coarse, pc, a, d))
+                    ir.append((i - ic * r).astype(np.float64))
+                if empty:
+                    continue
+
+                def take(shift_d=None, s=0):
+                    ix = [idx_c[d] + (s if d == shift_d else 0) for d in range(ndim)]
+                    return C_[np.ix_(*ix[::-1])]
+                c = take()
+                v = c.copy()
+                for d in range(ndim):
+                    dm = c - take(d, -1)
+                    dp = take(d, +1) - c
+                    coef2 = 0.5 * (dm + dp)
+                    bound = 2.0 * np.minimum(np.abs(dm), np.abs(dp))
+                    slope = np.where(dm * dp > 0.0, np.copysign(np.minimum(np.abs(coef2), bound), coef2) / coarse.dx[d], 0.0)
+                    if d == a:
+                        delta = ir[d] * fine.dx[d]
+                    else:
+                        delta = (ir[d] + 0.5) * fine.dx[d] - coarse.dx[d] * 0.5
+                    shp = [1] * ndim
+                    shp[ndim - 1 - d] = -1
+                    v = v + slope * delta.reshape(shp)
+                F_[np.ix_(*idx_f[::-1])] = v
+                written += v.size
+    return written
+
+
+def amr_coarsen_side(coarse: Level, fine: Level, ratio, c_arrays, f_arrays):
+    """c_arrays[pc][axis] := CONSERVATIVE_COARSEN(f_arrays[pf][axis]) on the coarse patches' own sides tiled by a fine patch's own
+    sides (f_synch_scheds[ln]->coarsenData, LDataManager.cpp:728-734; registered IBHierarchyIntegrator.cpp:369-372).  SAMRAI's
+    CartesianSideDoubleWeightedAverage (third party; Fortran cartwgtavgsidedoub{2,3}d{0,1,2}), restated from its published
+    algorithm: sum of fine * dAf over the fine sides of the coarse side (highest dimension outermost), divided by dAc --
+    PARITY UNPINNED.  Returns the number of points written."""
+    ndim = fine.ndim
+    written = 0
+    for pc in range(len(coarse.boxes)):
+        for pf in range(len(fine.boxes)):
+            for a in range(ndim):
+                C_, F_ = c_arrays[pc][a], f_arrays[pf][a]
+                ics, empty = [], False
+                for d in range(ndim):
+                    r = ratio[d]
+                    flo, fhi = fine.boxes[pf][0][d], fine.boxes[pf][1][d]
+                    lo = -((-flo) // r)
+                    if d == a:
+                        hi = (fhi + 1) // r
+                        lo, hi = max(lo, coarse.boxes[pc][0][d]), min(hi, coarse.boxes[pc][1][d] + 1)
+                    else:
+                        hi = (fhi + 1) // r - 1
+                        lo, hi = max(lo, coarse.boxes[pc][0][d]), min(hi, coarse.boxes[pc][1][d])
+                    if hi < lo:
+                        empty = True
+                        break
+                    ics.append(np.arange(lo, hi + 1))
+                if empty:
+                    continue
+                dAf = dAc = 1.0
+                for d in range(ndim):
+                    if d != a:
+                        dAf *= fine.dx[d]
+                        dAc *= coarse.dx[d]
+                rr = [1 if d == a else ratio[d] for d in range(ndim)] + [1] * (3 - ndim)
+                s = np.zeros(tuple(len(ics[d]) for d in range(ndim))[::-1])
+                for k2 in range(rr[2]):
+                    for k1 in range(rr[1]):
+                        for k0 in range(rr[0]):
+                            k = (k0, k1, k2)
+                            ix = [ics[d] * ratio[d] + (0 if d == a else k[d]) - _amr_index(fine, pf, a, d) for d in range(ndim)]
+                            s = s + F_[np.ix_(*ix[::-1])] * dAf
+                ixc = [ics[d] - _amr_index(coarse, pc, a, d) for d in range(ndim)]
+                C_[np.ix_(*ixc[::-1])] = s / dAc
+                written += s.size
+    return written
+
+
 def ghost_accumulate(level: Level, arrays, centering="side"):
     """SAMRAIGhostDataAccumulator::accumulateGhostData on one level.
 
