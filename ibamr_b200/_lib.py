@@ -152,6 +152,7 @@ SYMBOLS = {
     "ibk_comm_init_loopback": (_i, [C.POINTER(_vp), _i]),
     "ibk_comm_set_patches": (_i, [_vp, _i, _pi, _pi, _pi]),
     "ibk_comm_destroy": (_i, [_vp]),
+    "ibk_comm_set_reserved_sms": (_i, [_vp, _i]),
     "ibk_halo_fill_post": (_i, [_vp]),
     "ibk_halo_fill_finish": (_i, [_vp]),
     "ibk_halo_accumulate_post": (_i, [_vp]),

@@ -627,6 +627,16 @@ extern "C" int ibk_halo_accumulate_finish(ibk_ctx* ctx)
 {
     return ctx ? halo_finish(ctx, 1) : IBK_ERR_INVALID;
 }
+// SMs the persistent spread kernel leaves free for the message kernels (default with the NCCL transport: 8, for the
+// sequence in which the accumulate messages travel WHILE the interior tiles are spread; a sequence that does not overlap
+// messages with the spread, e.g. bench.py's, sets 0)
+extern "C" int ibk_comm_set_reserved_sms(ibk_ctx* ctx, int n_sms)
+{
+    if (!ctx) return IBK_ERR_INVALID;
+    if (n_sms < 0 || n_sms > 64) return cfail(ctx, IBK_ERR_INVALID, "reserved SMs must be in 0..64");
+    ctx->L.reserve_sms = n_sms;
+    return IBK_OK;
+}
 extern "C" long long ibk_halo_bytes(ibk_ctx* ctx, int which)
 {
     Comm* c = comm_of(ctx);

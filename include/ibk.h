@@ -529,6 +529,9 @@ int ibk_comm_init(ibk_ctx* ctx, const void* id128, int rank, int nranks);
 int ibk_comm_init_loopback(ibk_ctx** ctxs, int nranks);
 int ibk_comm_set_patches(ibk_ctx* ctx, int n_patches, const int* lower, const int* upper, const int* rank);
 int ibk_comm_destroy(ibk_ctx* ctx);
+/* SMs the persistent spread kernel leaves free so that message kernels can start while it runs (ibk_comm_init sets 8 for the
+ * NCCL transport, IBK_COMM_RESERVE_SMS overrides; 0 when no message has to start during a spread). */
+int ibk_comm_set_reserved_sms(ibk_ctx* ctx, int n_sms);
 /* The exchanges, split so that the messages are in flight while the tiles that do not touch the exchanged regions are
  * processed (ibk_*_part): post = pack on the context's stream + start the messages on its communication stream,
  * finish = the context's stream waits for them + unpack (fill: copy, accumulate: add).  Sequences as listed at

@@ -36,7 +36,25 @@ for r in range(world):
     hxs.append(halo.CommExchange(ib, patches))
 
 
-def step():
+def step_pipelined():
+    for r in range(world):
+        hxs[r].fill_post()
+    for r in range(world):
+        c = ctxs[r]
+        c.check(c.lib.ibk_spread_begin(c.h))
+        ibs[r].spreadForcePart(0)
+        hxs[r].accumulate_post()
+        ibs[r].halo("f")
+    for r in range(world):
+        ibs[r].halo("u")
+        hxs[r].fill_finish()
+        ibs[r].interpolateVelocityPart(0)
+    for r in range(world):
+        hxs[r].accumulate_finish()
+        ctxs[r].check(ctxs[r].lib.ibk_spread_end(ctxs[r].h))
+
+
+def step_split():
     for r in range(world):
         c = ctxs[r]
         c.check(c.lib.ibk_spread_begin(c.h))
@@ -56,6 +74,7 @@ def step():
         ibs[r].interpolateVelocityPart(2)
 
 
+step = step_split if os.environ.get("IBK_BENCH_SEQUENCE") == "split" else step_pipelined
 for _ in range(2):
     step()
 for c in ctxs:

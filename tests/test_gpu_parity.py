@@ -758,7 +758,7 @@ def test_adjointness_and_moments_large(api, kernel):
 
 
 @pytest.mark.parametrize("world,kernel,mode", [(2, "IB_4", "plain"), (2, "IB_4", "overlap"), (2, "IB_6", "overlap"), (4, "IB_4", "overlap"),
-                                               (2, "IB_4", "migrate")])
+                                               (2, "IB_4", "migrate"), (2, "IB_4", "pipelined"), (4, "IB_6", "pipelined")])
 def test_ranks_as_contexts_of_one_process(api, world, kernel, mode):
     """The multi-rank path on ONE GPU (N > 1 had no driver-side parity evidence): `world` contexts of this
     process are the ranks of a loopback communicator of libibk.so (ibk_comm_init_loopback); each owns one patch of a
@@ -837,6 +837,23 @@ def test_ranks_as_contexts_of_one_process(api, world, kernel, mode):
         for r in range(world):
             hxs[r].fill_finish()
             ibs[r].interpolateVelocityPart(2)
+    elif mode == "pipelined":
+        # the sequence bench.py times at N > 1: the u ghosts travel during the spread, the f ghost contributions during the
+        # interpolation; neither kernel is split
+        for r in range(world):
+            hxs[r].fill_post()
+        for r in range(world):
+            chk(r, ctxs[r].lib.ibk_spread_begin(ctxs[r].h))
+            ibs[r].spreadForce(accumulate_halo=False)
+            hxs[r].accumulate_post()
+            ibs[r].halo("f")
+        for r in range(world):
+            ibs[r].halo("u")
+            hxs[r].fill_finish()
+            ibs[r].interpolateVelocity(fill_halo=False)
+        for r in range(world):
+            hxs[r].accumulate_finish()
+            chk(r, ctxs[r].lib.ibk_spread_end(ctxs[r].h))
     else:
         for r in range(world):
             chk(r, ctxs[r].lib.ibk_spread_begin(ctxs[r].h))
