@@ -587,11 +587,13 @@ def run_gpu(args):
         # DRAM traffic of the same kernels from the committed ncu pass (profiles/, not measured in this run)
         traffic, traffic_interp, traffic_src = None, None, None
         try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_step_kernels_dram.json")) as f:
+            import glob
+            newest = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_step_kernels_dram.json")))[-1]
+            with open(newest) as f:
                 prof = json.load(f)["per_kernel"]
             traffic = sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in prof.items() if k.startswith("spread_"))
             traffic_interp = sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in prof.items() if k.startswith("interp_"))
-            traffic_src = "profiles/r01_step_kernels_dram.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, same workload, 1 GPU)"
+            traffic_src = f"profiles/{os.path.basename(newest)} (ncu dram__bytes_read.sum + dram__bytes_write.sum, same workload, 1 GPU)"
         except Exception:
             pass
         line = {

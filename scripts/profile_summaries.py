@@ -1,9 +1,15 @@
-"""Turns the ncu outputs of a round into the committed summaries under profiles/.
-usage: profile_summaries.py <launch_list.csv> <spread.ncu-rep> <round> [<interp.ncu-rep>]"""
-import csv, json, shutil, subprocess, sys, io
-lst, rep, rnd = sys.argv[1], sys.argv[2], int(sys.argv[3])
-root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
-shutil.copy(lst, f"{root}/profiles/r{rnd:02d}_launch_list_bench_steps2.csv")
+"""Turns the ncu outputs of a round (scripts/r2_profile.sh) into the committed summaries under profiles/.
+usage: profile_summaries.py <round> <launch_list.csv> <spread.ncu-rep> <interp.ncu-rep> [libibk.so]"""
+import collections, csv, io, json, os, re, shutil, subprocess, sys
+
+rnd, lst, rep_s, rep_i = int(sys.argv[1]), sys.argv[2], sys.argv[3], sys.argv[4]
+lib = sys.argv[5] if len(sys.argv) > 5 else None
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = f"r{rnd:02d}"
+out = lambda name: os.path.join(root, "profiles", f"{tag}_{name}")
+shutil.copy(lst, out("launch_list_bench_steps2.csv"))
+
+# ---- the launches of ONE timed step, aggregated per kernel
 rows = list(csv.reader(open(lst)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 h = rows[hi]
@@ -19,9 +25,12 @@ for r in rows[hi + 1:]:
         order.append(k)
     per[k][r[idx["Metric Name"]]] = float(r[idx["Metric Value"]].replace(",", "")) * scale.get(r[idx["Metric Unit"]], 1.0)
 names = [per[k]["name"].split("(")[0].replace("void ", "") for k in order]
-starts = [i for i, n in enumerate(names) if n.startswith("halo_zero_ghost") and (i == 0 or not names[i - 1].startswith("halo_zero_ghost"))]
-s0, s1 = starts[-3], starts[-2]  # one timed step (the last segment holds the e2e step's uploads and re-bin as well)
-agg = {}
+# a step starts with the ghost zero of ibk_spread_begin (region_items_kernel<2>) and ends after the interpolation kernel
+starts = [i for i, n in enumerate(names) if n.startswith("region_items_kernel<2>")]
+ends = [i for i, n in enumerate(names) if n.startswith("interp_")]
+s0 = starts[-3]
+s1 = next(e for e in ends if e > s0) + 1
+agg = collections.OrderedDict()
 for i in range(s0, s1):
     p, n = per[order[i]], names[i]
     a = agg.setdefault(n, {"launches": 0, "time_us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
@@ -37,57 +46,29 @@ for n, a in agg.items():
 json.dump({"round": rnd,
            "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 (cold-cache, serialised "
                      "launches; shares are comparable, absolute times are not bench values) of: python bench.py --steps 2 --warmup 1 --no-cpu-baseline "
-                     f"--e2e-steps 1 (raw list: r{rnd:02d}_launch_list_bench_steps2.csv)",
-           "what": "one timed step = spreadForce (ghost zero, face park, 8 tile-colour launches, fix-up, halo accumulate, face sync/restore) + "
-                   "interpolateVelocity (halo fill, interp)",
-           "per_kernel": agg, "step_total_us": round(tot, 1)}, open(f"{root}/profiles/r{rnd:02d}_step_kernels_dram.json", "w"), indent=1)
-# full-set summary of the spread kernel
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-r = list(csv.reader(io.StringIO(out)))
-hh, u, v = r[0], r[1], r[2]
+                     f"--no-sample-parity --e2e-steps 1 (raw list: {tag}_launch_list_bench_steps2.csv)",
+           "what": "one timed step at N = 1 = spreadForce (ghost zero, face park, ONE persistent march launch, fix-up, face sync, halo accumulate, face "
+                   "restore) + interpolateVelocity (halo fill, interp)",
+           "per_kernel": agg, "step_total_us": round(tot, 1)}, open(out("step_kernels_dram.json"), "w"), indent=1)
+
+# ---- selected counters and stall shares of the two full-set captures
 want = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
-        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
-        "lts__t_sector_hit_rate.pct", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
-summ = {}
-for k in want:
-    for i, x in enumerate(hh):
-        if x == k:
-            summ[k] = {"value": v[i], "unit": u[i]}
-st = {}
-for i, x in enumerate(hh):
-    if x.startswith("smsp__pcsamp_warps_issue_stalled_") and not x.endswith("_not_issued"):
-        try:
-            st[x.replace("smsp__pcsamp_warps_issue_stalled_", "")] = float(v[i].replace(",", ""))
-        except ValueError:
-            pass
-t = sum(st.values())
-summ["stall_share_of_pc_samples"] = {k: round(x / t, 4) for k, x in sorted(st.items(), key=lambda kv: -kv[1]) if x / t > 0.01}
-path = f"{root}/profiles/r{rnd:02d}_ncu_full_summary.json"
-try:
-    prof = json.load(open(path))
-except Exception:
-    prof = {}
-key = ("spread_tile_kernel<3,IB_4> (current), ONE of the 8 tile-colour launches of a spread; ncu --set full --clock-control none --import-source on "
-       "-k regex:spread_tile -s 10 -c 1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1")
-new = {key: summ}
-for k, vv in prof.items():
-    if k.startswith("spread_tile_kernel<3,IB_4> (current"):
-        new["(older) " + k.replace("(current", "(earlier")] = vv
-    else:
-        new[k] = vv
-if len(sys.argv) > 4:  # the interpolation kernel's full-set capture
-    out = subprocess.run(["ncu", "-i", sys.argv[4], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    r = list(csv.reader(io.StringIO(out)))
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "memory_l1_wavefronts_shared_ideal", "launch__grid_size", "launch__block_size",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "lts__t_sector_hit_rate.pct",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
+
+
+def summary(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(io.StringIO(raw)))
     hh, u, v = r[0], r[1], r[2]
-    isum = {}
-    for k in want + ["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "memory_l1_wavefronts_shared_ideal"]:
-        for i, x in enumerate(hh):
-            if x == k:
-                isum[k] = {"value": v[i], "unit": u[i]}
+    d = {"kernel": v[hh.index("Kernel Name")]}
+    for k in want:
+        if k in hh:
+            d[k] = {"value": v[hh.index(k)], "unit": u[hh.index(k)]}
     st = {}
     for i, x in enumerate(hh):
         if x.startswith("smsp__pcsamp_warps_issue_stalled_") and not x.endswith("_not_issued"):
@@ -96,11 +77,38 @@ if len(sys.argv) > 4:  # the interpolation kernel's full-set capture
             except ValueError:
                 pass
     t = sum(st.values())
-    isum["stall_share_of_pc_samples"] = {k: round(x / t, 4) for k, x in sorted(st.items(), key=lambda kv: -kv[1]) if x / t > 0.01}
-    ikey = ("interp_rot_kernel<IB_4,320> (current); ncu --set full --clock-control none --import-source on -k regex:interp_rot -s 3 -c 1 "
-            "python bench.py --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1")
-    new = {k: vv for k, vv in new.items() if not k.startswith("interp_rot_kernel")}
-    new = {ikey: isum, **new}
-json.dump(new, open(path, "w"), indent=1)
-print(json.dumps(summ["stall_share_of_pc_samples"]))
-print({k: summ[k]["value"] for k in ("gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum")})
+    d["stall_share_of_pc_samples"] = {k: round(x / t, 4) for k, x in sorted(st.items(), key=lambda kv: -kv[1]) if x / t > 0.01}
+    return d
+
+
+full = {"how": "ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 1 -c 1 python bench.py --steps 1 --warmup 1 "
+               "--no-cpu-baseline --no-sample-parity --e2e-steps 0 (C5 shard, one B200)"}
+for key, rep, nm in (("spread", rep_s, "spread_march_kernel"), ("interp", rep_i, "interp_rot_kernel")):
+    full[key] = summary(rep)
+    det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout.split("\n")
+    open(out(f"{nm}_details.txt"), "w").write("\n".join(det[:230]) + "\n")
+json.dump(full, open(out("ncu_full_summary.json"), "w"), indent=1)
+for key in ("spread", "interp"):
+    d = full[key]
+    print(key, d["kernel"][:60], {k: d[k]["value"] for k in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                                                              "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed")})
+    print("   stalls", d["stall_share_of_pc_samples"])
+
+# ---- SASS evidence of TMA in the shipped binary: UTMA* mnemonics per kernel
+if lib:
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    counts, cur = collections.OrderedDict(), None
+    for line in sass.split("\n"):
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
+            continue
+        m = re.search(r"\b(UTMALDG|UTMASTG|UTMAREDG|UTMAPF|UBLKCP|UBLKRED|SYNCS|REDG\.E\.ADD\.F64|RED\.E\.ADD\.F64|ATOMG\S*F64)\S*", line)
+        if m and cur:
+            counts.setdefault(cur, collections.Counter())[m.group(1)] += 1
+    with open(out("sass_tma_counts.txt"), "w") as f:
+        f.write(f"cuobjdump -sass {os.path.basename(lib)} | mnemonic counts per kernel (TMA tensor loads / stores / reducing stores, bulk copies,\n"
+                "mbarrier SYNCS; a line with REDG/RED/ATOMG ...F64 would be a global floating-point atomic: there is none)\n")
+        for k, c in counts.items():
+            f.write(f"{k:70s} " + "  ".join(f"{m}={n}" for m, n in sorted(c.items())) + "\n")
+    print(open(out("sass_tma_counts.txt")).read())
