@@ -535,6 +535,23 @@ class IBMethodB200:
         self.ctx.check(self.ctx.lib.ibk_amr_coarsen_side(self.ctx.h, fine.ctx.h, 0 if which == "u" else 1, _ip(r), C.byref(n)))
         return n.value
 
+    # -- N4: matrix form of the interpolation (PETScMatUtilities::constructPatchLevelSCInterpOp) ----
+    def constructInterpOp(self, dof_index, interp_fcn="IB_4"):
+        """Rows of the interpolation operator for the resident markers: (cols, vals), each [ndim * n_markers, stencil^ndim],
+        row ndim * k + axis.  dof_index[patch][axis]: int32 arrays of side_shape(patch, axis) (SideData<int> with ghosts).
+        interp_fcn: "IB_4" / "PIECEWISE_LINEAR" = PETScMatUtilities::ib_4_interp_fcn / pwl_interp_fcn."""
+        fcn, S = {"IB_4": (0, 4), "PIECEWISE_LINEAR": (1, 2)}[interp_fcn]
+        arrs = [np.ascontiguousarray(dof_index[p][a], dtype=np.int32) for p in range(len(self.boxes)) for a in range(self.ndim)]
+        ptrs = (C.POINTER(C.c_int) * len(arrs))(*[_ip(a) for a in arrs])
+        rows = self.ndim * self.n_markers
+        cols = np.zeros((max(rows, 1), S ** self.ndim), dtype=np.int32)
+        vals = np.zeros((max(rows, 1), S ** self.ndim))
+        bad = C.c_int(0)
+        self.ctx.check(self.ctx.lib.ibk_construct_sc_interp_op(self.ctx.h, fcn, ptrs, _ip(cols), _dp(vals), C.byref(bad)))
+        if bad.value:
+            raise IBKError(-1, f"constructInterpOp: {bad.value} rows have no local patch that holds their stencil")
+        return cols[:rows], vals[:rows]
+
     def getPatchLists(self, patch):
         """LIndexSetData::cacheLocalIndices for one patch: (lag_idx[n], periodic_shifts[n][ndim], interior[n] as bool)."""
         n = C.c_int(0)

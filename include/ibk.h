@@ -465,6 +465,23 @@ int ibk_spread_fold_walls(ibk_ctx* ctx);
  * not in the reference tree): restated from their published algorithm, see csrc/ibk_amr.cu.  which: 0 = u, 1 = f.
  * n_points (may be null): points written.  The work runs on the destination context's stream, ordered after everything
  * queued on the source context's stream. */
+/* Matrix form of the interpolation (N4 of SURVEY.md 8(f)): PETScMatUtilities::constructPatchLevelSCInterpOp
+ * (ibtk/src/math/PETScMatUtilities.cpp:783-1020), the operator IBMethod::constructInterpOp gives the implicit solver
+ * (src/IB/IBMethod.cpp:1030-1050).  The reference fills a PETSc AIJ matrix (third party) by one MatSetValues call per row;
+ * here the rows of the resident markers are computed on the device and returned as arrays with a fixed row length
+ * stencil^ndim (CSR with row_ptr[r] = r * stencil^ndim): h_cols / h_vals [ndim * n_markers][stencil^ndim], row ndim * k + axis
+ * for the marker of host row k, entries in the reference's box-iterator order (x fastest).
+ * interp_fcn: PETScMatUtilities::ib_4_interp_fcn (stencil 4) or pwl_interp_fcn (stencil 2) (PETScMatUtilities.h:156-176).
+ * h_dof_index[patch * ndim + axis]: the SideData<int> DOF numbers of (patch, axis), dense, x fastest, ghost width = the level's.
+ * *n_unplaced (may be null): rows whose marker lies in no local patch or whose stencil leaves its ghost box (the reference
+ * asserts there are none); their columns are -1. */
+enum
+{
+    IBK_INTERP_FCN_IB_4 = 0,
+    IBK_INTERP_FCN_PWL = 1
+};
+int ibk_construct_sc_interp_op(ibk_ctx* ctx, int interp_fcn, const int* const* h_dof_index, int* h_cols, double* h_vals,
+                               int* n_unplaced);
 int ibk_amr_refine_side(ibk_ctx* fine, ibk_ctx* coarse, int which, const int* ratio, long long* n_points);
 int ibk_amr_coarsen_side(ibk_ctx* coarse, ibk_ctx* fine, int which, const int* ratio, long long* n_points);
 /* LDataManager::interp core (LDataManager.cpp:698-813) as IBMethod::interpolateVelocity calls it

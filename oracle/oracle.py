@@ -535,6 +535,62 @@ def amr_coarsen_side(coarse: Level, fine: Level, ratio, c_arrays, f_arrays):
     return written
 
 
+def sc_interp_op(level: Level, X, dof_index, interp_fcn="IB_4"):
+    """PETScMatUtilities::constructPatchLevelSCInterpOp (ibtk/src/math/PETScMatUtilities.cpp:783-1020) as (cols, vals), each
+    [ndim * n, stencil^ndim], row ndim * k + axis, entries in box-iterator order (x fastest).  interp_fcn: ib_4_interp_fcn /
+    pwl_interp_fcn of PETScMatUtilities.h:156-176.  dof_index[p][axis]: int arrays [z][y][x] with the level's ghost width."""
+    ndim = level.ndim
+    X = np.asarray(X, dtype=np.float64).reshape(-1, ndim)
+    n = X.shape[0]
+    S = 4 if interp_fcn == "IB_4" else 2
+    dom_lo, dom_hi = level.domain_lower, level.domain_upper()
+    cells = get_cell_index(X, level.x_lower, level.x_upper, level.dx, dom_lo, dom_hi).reshape(-1, ndim)
+    cols = np.full((ndim * n, S ** ndim), -1, dtype=np.int32)
+    vals = np.zeros((ndim * n, S ** ndim))
+
+    def weights(r):
+        if S == 4:
+            q = np.sqrt(-7.0 + 12.0 * r - 4.0 * r * r)
+            return np.stack([0.125 * (5.0 - 2.0 * r - q), 0.125 * (5.0 - 2.0 * r + q), 0.125 * (-1.0 + 2.0 * r + q),
+                             0.125 * (-1.0 + 2.0 * r - q)], axis=1)
+        return np.stack([1.0 - r, r], axis=1)
+    # the patch of every marker: interior first, then the first ghost layer (:861-877), patches in list order
+    pnum = np.full(n, -1)
+    for growth in (0, 1):
+        for p, (lo, hi) in enumerate(level.boxes):
+            inside = np.all((cells >= np.array(lo) - growth) & (cells <= np.array(hi) + growth), axis=1)
+            pnum[(pnum < 0) & inside] = p
+    x_cell = np.stack([(cells[:, d] - dom_lo[d] + 0.5) * level.dx[d] + level.x_lower[d] for d in range(ndim)], axis=1)
+    for axis in range(ndim):
+        lower = np.zeros((n, ndim), dtype=np.int64)
+        w = []
+        for d in range(ndim):
+            if d == axis:
+                lower[:, d] = cells[:, d] - S // 2 + 1
+            else:
+                lower[:, d] = np.where(X[:, d] <= x_cell[:, d], cells[:, d] - S // 2, cells[:, d] - S // 2 + 1)
+            x_sl = ((lower[:, d] - dom_lo[d]).astype(np.float64) + (0.0 if d == axis else 0.5)) * level.dx[d] + level.x_lower[d]
+            w.append(weights((X[:, d] - x_sl) / level.dx[d]))
+        for p, (lo, hi) in enumerate(level.boxes):
+            m = np.nonzero(pnum == p)[0]
+            if m.size == 0:
+                continue
+            dof = np.asarray(dof_index[p][axis])
+            e = 0
+            for kz in range(S if ndim == 3 else 1):
+                for ky in range(S):
+                    for kx in range(S):
+                        k = (kx, ky, kz)
+                        v = w[0][m, kx] * w[1][m, ky]
+                        if ndim == 3:
+                            v = v * w[2][m, kz]
+                        j = [lower[m, d] + k[d] - (lo[d] - level.gcw[d]) for d in range(ndim)]
+                        cols[ndim * m + axis, e] = dof[tuple(j[::-1])]
+                        vals[ndim * m + axis, e] = v
+                        e += 1
+    return cols, vals
+
+
 def ghost_accumulate(level: Level, arrays, centering="side"):
     """SAMRAIGhostDataAccumulator::accumulateGhostData on one level.
 

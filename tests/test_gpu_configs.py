@@ -178,6 +178,26 @@ def test_c4_two_level_amr_fine_patches(api):
     assert eu <= TOL and ef <= TOL
 
 
+def test_c4_two_level_amr_full_size(api):
+    """C4 at BASELINE.json's stated size: coarse 128^3, ratio 4 (512^3 effective), the fine level = 8 patches of 128^3 over
+    the central 256^3 fine cells, 2^20 markers on a sphere inside it; value by value against the oracle."""
+    nfine, N, w = 512, 1 << 20, 128
+    boxes = []
+    for kz in range(2):
+        for ky in range(2):
+            for kx in range(2):
+                lo = (128 + w * kx, 128 + w * ky, 128 + w * kz)
+                boxes.append((lo, tuple(l + w - 1 for l in lo)))
+    level = orc.Level(3, (0,) * 3, (nfine,) * 3, (0.0,) * 3, (1.0,) * 3, (1, 1, 1), boxes, (3,) * 3)
+    k = np.arange(N) + 0.5
+    phi = np.arccos(1 - 2 * k / N)
+    th = np.pi * (1 + 5 ** 0.5) * k
+    X = 0.5 + 0.2 * np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1)
+    F = np.stack([2 * splitmix64_unit(1 + d, np.arange(N)) - 1 for d in range(3)], axis=1)
+    eu, ef = _run_level_case(api, level, "IB_4", X, F)
+    assert eu <= TOL and ef <= TOL
+
+
 @pytest.mark.parametrize("kernel", ["BSPLINE_4", "PIECEWISE_LINEAR"])
 def test_nonperiodic_walls(api, kernel):
     """Wall-bounded domain: markers close to the walls spread into ghost cells outside the domain, which have no

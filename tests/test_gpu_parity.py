@@ -758,7 +758,8 @@ def test_adjointness_and_moments_large(api, kernel):
 
 
 @pytest.mark.parametrize("world,kernel,mode", [(2, "IB_4", "plain"), (2, "IB_4", "overlap"), (2, "IB_6", "overlap"), (4, "IB_4", "overlap"),
-                                               (2, "IB_4", "migrate"), (2, "IB_4", "pipelined"), (4, "IB_6", "pipelined")])
+                                               (2, "IB_4", "migrate"), (2, "IB_4", "pipelined"), (4, "IB_6", "pipelined"), (8, "IB_4", "pipelined"),
+                                               (8, "IB_4", "overlap")])
 def test_ranks_as_contexts_of_one_process(api, world, kernel, mode):
     """The multi-rank path on ONE GPU (N > 1 had no driver-side parity evidence): `world` contexts of this
     process are the ranks of a loopback communicator of libibk.so (ibk_comm_init_loopback); each owns one patch of a
@@ -767,7 +768,7 @@ def test_ranks_as_contexts_of_one_process(api, world, kernel, mode):
     at N > 1.  Compared per rank with the oracle's model of the reference (redundant ghost-region spreading)."""
     from ibamr_b200 import halo
     n = 64 if mode == "overlap" else 32  # with 64 cells per rank there are interior tiles
-    pgrid = {2: (2, 1, 1), 4: (2, 2, 1)}[world]
+    pgrid = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]  # 8: the process grid of the 8-GPU benchmark (every face remote)
     patches = halo.cartesian_patches(3, pgrid, (n, n, n))
     dom = tuple(n * pgrid[d] for d in range(3))
     g = orc.min_ghost_width(kernel)
