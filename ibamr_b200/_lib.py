@@ -133,6 +133,7 @@ SYMBOLS = {
     "ibk_spread_end": (_i, [_vp]),
     "ibk_level_set_wall_bc": (_i, [_vp, _pd, _pd]),
     "ibk_spread_fold_walls": (_i, [_vp]),
+    "ibk_set_user_kernel": (_i, [C.CFUNCTYPE(C.c_double, C.c_double), _i]),
     "ibk_construct_sc_interp_op": (_i, [_vp, _i, C.POINTER(C.POINTER(C.c_int)), _pi, _pd, _pi]),
     "ibk_amr_refine_side": (_i, [_vp, _vp, _i, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "ibk_amr_coarsen_side": (_i, [_vp, _vp, _i, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),

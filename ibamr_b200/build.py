@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["ibk_api.cu", "ibk_level.cu", "ibk_bin.cu", "ibk_sort.cu", "ibk_interp.cu", "ibk_spread.cu", "ibk_halo.cu", "ibk_migrate.cu", "ibk_force.cu", "ibk_io.cu", "ibk_comm.cu", "ibk_lists.cu", "ibk_amr.cu", "ibk_matop.cu"]
+SOURCES = ["ibk_api.cu", "ibk_level.cu", "ibk_bin.cu", "ibk_sort.cu", "ibk_interp.cu", "ibk_spread.cu", "ibk_halo.cu", "ibk_migrate.cu", "ibk_force.cu", "ibk_io.cu", "ibk_comm.cu", "ibk_lists.cu", "ibk_amr.cu", "ibk_matop.cu", "ibk_user.cu"]
 HEADERS = ["ibk_device.cuh", "ibk_engine.h", "ibk_ctx.h", "ibk_tma.h", os.path.join("..", "..", "include", "ibk.h")]
 LIB = os.path.join(HERE, "libibk.so")
 OBJDIR = os.path.join(HERE, "_obj")

@@ -52,6 +52,10 @@ long long round_pitch(int n0)
 // ---------------------------------------------------------------------------------------------
 // LEInteractor statics
 // ---------------------------------------------------------------------------------------------
+namespace ibk
+{
+int user_kernel_stencil_size(); // ibk_user.cu
+}
 extern "C" int ibk_kernel_from_string(const char* s)
 {
     if (!s) return IBK_ERR_UNKNOWN_KERNEL;
@@ -76,6 +80,7 @@ extern "C" int ibk_kernel_from_string(const char* s)
     if (!strcmp(s, "COMPOSITE_BSPLINE_56")) return IBK_COMPOSITE_BSPLINE_56;
     if (!strcmp(s, "DISCONTINUOUS_LINEAR")) return IBK_DISCONTINUOUS_LINEAR;
     if (!strcmp(s, "IB_4_W8")) return IBK_IB_4_W8;
+    if (!strcmp(s, "USER_DEFINED")) return IBK_USER_DEFINED;
     return IBK_ERR_UNKNOWN_KERNEL;
 }
 extern "C" int ibk_is_known_kernel(const char* s)
@@ -123,6 +128,8 @@ extern "C" int ibk_get_stencil_size(const char* s)
         return 2;
     case IBK_IB_4_W8:
         return 8;
+    case IBK_USER_DEFINED:
+        return ibk::user_kernel_stencil_size(); // s_kernel_fcn_stencil_size, LEInteractor.cpp:2099-2100
     default:
         return IBK_ERR_UNKNOWN_KERNEL;
     }
@@ -301,6 +308,10 @@ void make_tile_params(TileParams& tp, int ndim, const double* dx, const double x
     }
 }
 
+int user_kernel_stencil_size();
+int user_entries_op(ibk_ctx* ctx, int op, const TileParams& tp, const CellGeom& cg, const PatchBin& pb, const double* d_Xe,
+                    const double* d_Xr, long long stride, int n_entries, const int* d_indices, double* d_V, long long v_cstride,
+                    long long v_istride, bool filter_box);
 // Runs interp (op 0) or spread (op 1) for `n_entries` entries given as SoA positions Xe (shifted)
 // and Xr (raw) of stride `stride`; values are addressed through d_indices (nullable).
 int run_entries_op(ibk_ctx* ctx, int op, int kernel, TileParams& tp, const CellGeom& cg, PatchBin& pb, const double* d_Xe,
@@ -308,6 +319,8 @@ int run_entries_op(ibk_ctx* ctx, int op, int kernel, TileParams& tp, const CellG
                    long long v_istride, bool zero_unreached = true)
 {
     if (n_entries <= 0) return IBK_OK;
+    if (kernel == IBK_USER_DEFINED) // host callback: its own path (ibk_user.cu); position-only forms list by the box
+        return user_entries_op(ctx, op, tp, cg, pb, d_Xe, d_Xr, stride, n_entries, d_indices, d_V, v_cstride, v_istride, !zero_unreached);
     const int ndim = tp.ndim;
     CK(ctx->b_patchbin.reserve(sizeof(PatchBin)));
     CK(cudaMemcpyAsync(ctx->b_patchbin.p, &pb, sizeof(PatchBin), cudaMemcpyHostToDevice, ctx->L.stream));
@@ -354,7 +367,7 @@ static int raw_op(ibk_ctx* ctx, int op, int kernel, const ibk_array_desc* desc, 
                   const int* d_indices, const double* d_Xshift, int nindices, const double* d_X, int n_markers, double* d_V)
 {
     if (!ctx || !desc) return IBK_ERR_INVALID;
-    if (kernel < 0 || kernel > IBK_KERNEL_LAST) return fail(ctx, IBK_ERR_UNKNOWN_KERNEL, "unknown kernel");
+    if (kernel < 0 || (kernel > IBK_KERNEL_LAST && kernel != IBK_USER_DEFINED)) return fail(ctx, IBK_ERR_UNKNOWN_KERNEL, "unknown kernel");
     const int ndim = desc->ndim;
     if (ndim != 2 && ndim != 3) return fail(ctx, IBK_ERR_INVALID, "ndim must be 2 or 3");
     if (desc->depth < 1 || desc->depth > IBK_MAX_COMP) return fail(ctx, IBK_ERR_INVALID, "depth out of range");

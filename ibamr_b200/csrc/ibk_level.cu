@@ -2089,6 +2089,8 @@ static int level_op(ibk_ctx* ctx, int op, const char* fcn, int halo, int part = 
     if (!lv.binned) return fail(ctx, IBK_ERR_STATE, "markers are not binned: call ibk_rebin first");
     const int kernel = ibk_kernel_from_string(fcn);
     if (kernel < 0) return fail(ctx, IBK_ERR_UNKNOWN_KERNEL, std::string("unknown kernel function ") + (fcn ? fcn : "(null)"));
+    if (kernel == IBK_USER_DEFINED)
+        return fail(ctx, IBK_ERR_UNKNOWN_KERNEL, "USER_DEFINED is a host callback: it is served at the patch seams (ibk_side_*_host ...), not on the resident level");
     const int min_ghosts = ibk_get_minimum_ghost_width(fcn);
     for (int d = 0; d < lv.ndim; ++d)
         if (lv.gcw[d] < min_ghosts) return fail(ctx, IBK_ERR_GHOST_WIDTH, "insufficient ghost cells for the kernel function");

@@ -77,7 +77,8 @@ typedef enum ibk_kernel
     IBK_COMPOSITE_BSPLINE_56 = 18,
     IBK_DISCONTINUOUS_LINEAR = 19,
     IBK_IB_4_W8 = 20, /* lagrangian_ib_4_w8_*: the 4-point function broadened to 8 meshwidths */
-    IBK_KERNEL_LAST = IBK_IB_4_W8
+    IBK_KERNEL_LAST = IBK_IB_4_W8,
+    IBK_USER_DEFINED = 21 /* "USER_DEFINED": LEInteractor::s_kernel_fcn, see ibk_set_user_kernel */
 } ibk_kernel;
 
 /* ---- LEInteractor static queries (ibtk/include/ibtk/LEInteractor.h:99-117) ------------------ */
@@ -89,6 +90,14 @@ int ibk_is_known_kernel(const char* kernel_fcn);
 int ibk_get_stencil_size(const char* kernel_fcn);
 /* LEInteractor::getMinimumGhostWidth (LEInteractor.cpp:2110-2114). */
 int ibk_get_minimum_ghost_width(const char* kernel_fcn);
+/* "USER_DEFINED" (LEInteractor.h:82-83: static double (*s_kernel_fcn)(double r), static int s_kernel_fcn_stencil_size; defaults
+ * LEInteractor.cpp:2019-2020 = the 4-point function, stencil 4).  Process-wide like the reference's statics; a null function
+ * restores the default.  The function is a HOST callback: its values are produced on the host, entry by entry, the way
+ * userDefinedInterpolate / userDefinedSpread do (LEInteractor.cpp:6128-6382); the sums over grid data run on the device, the
+ * spread in the reference's serial order of additions (no atomics).  Served at the funnel seam (ibk_raw_*) and the patch
+ * seams (ibk_{side,cell,node,edge}_*_host); the resident level (ibk_spread_force / ibk_interpolate_velocity) refuses it. */
+typedef double (*ibk_kernel_fcn)(double r);
+int ibk_set_user_kernel(ibk_kernel_fcn fcn, int stencil_size);
 
 /* ---- context ---------------------------------------------------------------------------------- */
 int ibk_ctx_create(int device, ibk_ctx** ctx);

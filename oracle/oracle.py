@@ -115,6 +115,87 @@ def spread_raw(kernel, ndim, dx, x_lower, depth, indices, Xshift, X, V, ilower, 
     return u
 
 
+def ib4_kernel_fcn(r):
+    """LEInteractor.cpp:1526-1546, the default of LEInteractor::s_kernel_fcn (scalar)"""
+    r = abs(r)
+    if r < 1.0:
+        t2 = r * r
+        t6 = np.sqrt(-0.4e1 * t2 + 0.4e1 * r + 0.1e1)
+        return -r / 0.4e1 + 0.3e1 / 0.8e1 + t6 / 0.8e1
+    if r < 2.0:
+        t2 = r * r
+        t6 = np.sqrt(0.12e2 * r - 0.7e1 - 0.4e1 * t2)
+        return -r / 0.4e1 + 0.5e1 / 0.8e1 - t6 / 0.8e1
+    return 0.0
+
+
+def _user_stencils(kernel_fcn, stencil, ndim, dx, x_lower, ilower, iupper, nugc, X, Xshift, l, s):
+    """stencil range and weights of list entry l (marker s), LEInteractor.cpp:6158-6226 / 6286-6354"""
+    lo, hi, w = [], [], []
+    for d in range(ndim):
+        xs = X[s * ndim + d] + (Xshift[l * ndim + d] if Xshift is not None else 0.0)
+        center = int(np.floor((xs - x_lower[d]) / dx[d])) + ilower[d]
+        x_cell = x_lower[d] + (float(center - ilower[d]) + 0.5) * dx[d]
+        if stencil % 2 == 0:
+            if X[s * ndim + d] < x_cell:  # (sic: the unshifted position)
+                a, b = center - stencil // 2, center + stencil // 2 - 1
+            else:
+                a, b = center - stencil // 2 + 1, center + stencil // 2
+        else:
+            a, b = center - stencil // 2, center + stencil // 2
+        a = min(max(a, ilower[d] - nugc[d]), iupper[d] + nugc[d])
+        b = min(max(b, ilower[d] - nugc[d]), iupper[d] + nugc[d])
+        lo.append(a)
+        hi.append(b)
+        w.append([kernel_fcn((xs - (x_cell + float(ic - center) * dx[d])) / dx[d]) for ic in range(a, b + 1)])
+    return lo, hi, w
+
+
+def user_interp_raw(kernel_fcn, stencil, ndim, dx, x_lower, depth, ilower, iupper, nugc, u, indices, Xshift, X, V):
+    """LEInteractor::userDefinedInterpolate (LEInteractor.cpp:6128-6257).  u: [depth][z][y][x] with ghosts, V: [n][depth]."""
+    X, V = np.asarray(X, dtype=np.float64).reshape(-1), V.reshape(-1, depth)
+    sh = None if Xshift is None else np.asarray(Xshift, dtype=np.float64).reshape(-1)
+    shape = tuple(iupper[d] - ilower[d] + 1 + 2 * nugc[d] for d in range(ndim))[::-1]
+    q = np.asarray(u, dtype=np.float64).reshape((depth,) + shape)
+    for l, s in enumerate(np.asarray(indices).reshape(-1)):
+        lo, hi, w = _user_stencils(kernel_fcn, stencil, ndim, dx, x_lower, ilower, iupper, nugc, X, sh, l, int(s))
+        for d in range(depth):
+            acc = 0.0
+            for i2 in range(lo[2], hi[2] + 1) if ndim == 3 else [0]:
+                for i1 in range(lo[1], hi[1] + 1):
+                    for i0 in range(lo[0], hi[0] + 1):
+                        j = (i0 - ilower[0] + nugc[0], i1 - ilower[1] + nugc[1]) + ((i2 - ilower[2] + nugc[2],) if ndim == 3 else ())
+                        ww = w[0][i0 - lo[0]] * w[1][i1 - lo[1]]
+                        if ndim == 3:
+                            ww = ww * w[2][i2 - lo[2]]
+                        acc += ww * q[(d,) + j[::-1]]
+            V[int(s), d] = acc
+    return V
+
+
+def user_spread_raw(kernel_fcn, stencil, ndim, dx, x_lower, depth, indices, Xshift, X, V, ilower, iupper, nugc, u):
+    """LEInteractor::userDefinedSpread (LEInteractor.cpp:6259-6382): serial over the list, q += w0 w1 w2 Q / (dx0 dx1 dx2)."""
+    X, V = np.asarray(X, dtype=np.float64).reshape(-1), np.asarray(V, dtype=np.float64).reshape(-1, depth)
+    sh = None if Xshift is None else np.asarray(Xshift, dtype=np.float64).reshape(-1)
+    shape = tuple(iupper[d] - ilower[d] + 1 + 2 * nugc[d] for d in range(ndim))[::-1]
+    q = u.reshape((depth,) + shape)
+    vol = dx[0] * dx[1]
+    if ndim == 3:
+        vol = vol * dx[2]
+    for l, s in enumerate(np.asarray(indices).reshape(-1)):
+        lo, hi, w = _user_stencils(kernel_fcn, stencil, ndim, dx, x_lower, ilower, iupper, nugc, X, sh, l, int(s))
+        for d in range(depth):
+            for i2 in range(lo[2], hi[2] + 1) if ndim == 3 else [0]:
+                for i1 in range(lo[1], hi[1] + 1):
+                    for i0 in range(lo[0], hi[0] + 1):
+                        j = (i0 - ilower[0] + nugc[0], i1 - ilower[1] + nugc[1]) + ((i2 - ilower[2] + nugc[2],) if ndim == 3 else ())
+                        ww = w[0][i0 - lo[0]] * w[1][i1 - lo[1]]
+                        if ndim == 3:
+                            ww = ww * w[2][i2 - lo[2]]
+                        q[(d,) + j[::-1]] += ww * V[int(s), d] / vol
+    return u
+
+
 def get_cell_index(X, x_lower, x_upper, dx, ilower, iupper):
     X = _f64(X)
     ndim = len(dx)
