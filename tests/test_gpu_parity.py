@@ -372,8 +372,9 @@ def test_error_behaviour(api):
         api.LEInteractor.interpolate(np.zeros((4, 1)), 1, X, 2, api.SideData(box, 1, 3), patch, box, "IB_4")
     assert e.value.code == api.IBK_ERR_DEPTH
     with pytest.raises(api.IBKError) as e:
-        api.LEInteractor.interpolate(Q, 2, X, 2, api.SideData(box, 1, 3), patch, box, "USER_DEFINED")  # a host callback in the reference: not built
+        api.LEInteractor.interpolate(Q, 2, X, 2, api.SideData(box, 1, 3), patch, box, "IB_7")  # no such kernel (LEInteractor.cpp:2038-2050)
     assert e.value.code == api.IBK_ERR_UNKNOWN_KERNEL
+    api.LEInteractor.interpolate(Q, 2, X, 2, api.SideData(box, 1, 3), patch, box, "USER_DEFINED")  # the default callback: the 4-point function
     # spread with too few ghosts is only an error at a physical boundary (:5250-5266)
     api.LEInteractor.spread(api.SideData(box, 1, 1), Q, 2, X, 2, patch, box, "PIECEWISE_LINEAR")
     bpatch = api.Patch(box, (0.0, 0.0), (1.0, 1.0), (0.125, 0.125), touches_regular_bdry=True)
