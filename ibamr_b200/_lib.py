@@ -102,6 +102,7 @@ SYMBOLS = {
     "ibk_markers_download": (_i, [_vp, _i, _pd]),
     "ibk_markers_count": (_i, [_vp]),
     "ibk_rebin": (_i, [_vp, _i]),
+    "ibk_markers_owned_count": (_i, [_vp, _pi]),
     "ibk_halo_pack_many": (_i, [_vp, _i, _i, _pi, _pi, _pi, _pi, C.POINTER(C.c_longlong), _vp]),
     "ibk_halo_unpack_many": (_i, [_vp, _i, _i, _pi, _pi, _pi, _pi, C.POINTER(C.c_longlong), _vp, _i]),
     "ibk_spread_force_part": (_i, [_vp, _s, _i]),

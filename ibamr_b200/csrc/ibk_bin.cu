@@ -57,7 +57,8 @@ void fill_patch_bin(PatchBin& pb, int ndim, const int* lower, const int* upper, 
     pb.nbricks = ntiles * (ndim == 3 ? 64 : 16);
 }
 
-__global__ void wrap_positions_kernel(DomainGeom dg, double* __restrict__ X, long long stride, int n, int* __restrict__ escaped)
+__global__ void wrap_positions_kernel(DomainGeom dg, double* __restrict__ X, long long stride, int n, int* __restrict__ escaped,
+                                      int check_only)
 {
     const double TOL = 1.4901161193847656e-08; // sqrt(DBL_EPSILON), LDataManager.cpp:150
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,7 +80,7 @@ __global__ void wrap_positions_kernel(DomainGeom dg, double* __restrict__ X, lon
             x = fmax(x, lo);
             x = fmin(x, __dsub_rn(hi, __dmul_rn(__dsub_rn(hi, lo), TOL)));
         }
-        X[d * stride + i] = x;
+        if (!check_only) X[d * stride + i] = x;
     }
 }
 
@@ -388,11 +389,11 @@ cudaError_t bins_build(Bins& b, Launcher& L, const CellGeom& cg, const PatchBin*
     return cudaStreamSynchronize(L.stream);
 }
 
-cudaError_t wrap_positions(Launcher& L, const DomainGeom& dg, double* d_X, long long x_stride, int n, int* d_escaped)
+cudaError_t wrap_positions(Launcher& L, const DomainGeom& dg, double* d_X, long long x_stride, int n, int* d_escaped, bool check_only)
 {
     if (n <= 0) return cudaSuccess;
     const int T = 256;
-    wrap_positions_kernel<<<(n + T - 1) / T, T, 0, L.stream>>>(dg, d_X, x_stride, n, d_escaped);
+    wrap_positions_kernel<<<(n + T - 1) / T, T, 0, L.stream>>>(dg, d_X, x_stride, n, d_escaped, check_only ? 1 : 0);
     L.launches++;
     return cudaGetLastError();
 }

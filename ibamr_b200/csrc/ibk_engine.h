@@ -100,7 +100,9 @@ void bins_free(Bins& b);
 cudaError_t bins_build(Bins& b, Launcher& L, const CellGeom& cg, const PatchBin* d_patches, int n_patches,
                        const PatchBin* h_patches, const double* d_X, long long x_stride, const uint32_t* d_tie,
                        uint32_t tie_bound, int n_entries, int* d_cells_out, int* d_owner_out);
-cudaError_t wrap_positions(Launcher& L, const DomainGeom& dg, double* d_X, long long x_stride, int n, int* d_escaped);
+// check_only: count the points outside a non-periodic domain without touching X
+cudaError_t wrap_positions(Launcher& L, const DomainGeom& dg, double* d_X, long long x_stride, int n, int* d_escaped,
+                           bool check_only = false);
 // out[c][i] = in[c][perm[i]] for c < ncols (SoA gather through the sort permutation)
 cudaError_t gather_columns(Launcher& L, const double* d_in, long long in_stride, double* d_out, long long out_stride,
                            const uint32_t* d_perm, int n, int ncols);

@@ -1173,14 +1173,16 @@ extern "C" int ibk_rebin(ibk_ctx* ctx, int error_if_points_leave_domain)
         cg.iupper[d] = lv.domain_upper[d];
     }
     CK(cudaMemsetAsync(lv.escaped, 0, sizeof(int), ctx->L.stream));
-    CK(wrap_positions(ctx->L, dg, lv.X, lv.stride, n, lv.escaped));
     if (error_if_points_leave_domain)
     {
+        // the reference aborts before it moves anything (LDataManager.cpp:1410-1416): check first, X untouched on failure
         int esc = 0;
+        CK(wrap_positions(ctx->L, dg, lv.X, lv.stride, n, lv.escaped, /*check_only*/ true));
         CK(cudaMemcpyAsync(&esc, lv.escaped, sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
         CK(cudaStreamSynchronize(ctx->L.stream));
         if (esc > 0) return fail(ctx, IBK_ERR_ESCAPED, "IB point has escaped from the computational domain!");
     }
+    CK(wrap_positions(ctx->L, dg, lv.X, lv.stride, n, lv.escaped));
     if (n > 0) CK(cudaMemcpyAsync(lv.lag_prev, lv.lag, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->L.stream));
     // in-cell order = ascending Lagrangian index (LDataManager.cpp:1505): the global one when it is known
     CK(bins_build(lv.bins, ctx->L, cg, lv.d_bins, (int)lv.h_bins.size(), lv.h_bins.data(), lv.X, lv.stride,
@@ -1229,6 +1231,22 @@ extern "C" int ibk_rebin(ibk_ctx* ctx, int error_if_points_leave_domain)
         CK(cudaEventRecord(ctx->ev[2][1], ctx->L.stream));
         ctx->ev_valid[2] = true;
     }
+    return IBK_OK;
+}
+
+// Markers of the context that a local patch accepted at the last ibk_rebin.  The others (their cell lies in no local
+// patch: they belong to another rank, or the patches do not cover them) sit behind the binned ones and are skipped by
+// spread, interpolation and the force kernels until ibk_migrate hands them over.
+extern "C" int ibk_markers_owned_count(ibk_ctx* ctx, int* n_owned)
+{
+    NEED_LEVEL();
+    LevelState& lv = ctx->lv;
+    if (!n_owned) return fail(ctx, IBK_ERR_INVALID, "null pointer");
+    if (!lv.binned) return fail(ctx, IBK_ERR_STATE, "ibk_rebin has not run");
+    *n_owned = 0;
+    if (lv.n == 0 || !lv.bins.brick_start) return IBK_OK;
+    CK(cudaMemcpyAsync(n_owned, lv.bins.brick_start + lv.bins.total_bricks, sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
     return IBK_OK;
 }
 

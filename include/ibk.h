@@ -341,6 +341,10 @@ int ibk_markers_count(const ibk_ctx* ctx);
  * device radix sort by (patch, brick, cell) with the Lagrangian index as tie-break, permute all
  * marker columns.  error_if_points_leave_domain follows IBMethod's flag (IBMethod.cpp:2060). */
 int ibk_rebin(ibk_ctx* ctx, int error_if_points_leave_domain);
+/* How many markers a local patch accepted at the last ibk_rebin.  The rest (ibk_markers_count - n_owned: their cell lies in no
+ * local patch) are kept behind the binned ones and skipped by every operation until ibk_migrate sends them to their owners;
+ * with one process a non-zero rest means the patches do not cover the structure. */
+int ibk_markers_owned_count(ibk_ctx* ctx, int* n_owned);
 
 /* ---- more than one process: global Lagrangian indices and marker migration ------------------------------
  * With one process the host rows of ibk_markers_upload/download ARE the Lagrangian indices 0..n-1.  With

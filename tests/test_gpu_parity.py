@@ -904,3 +904,29 @@ def _periodic_side_fields_global(pg, ncell, seed):
         lin = mesh[0] + ncell[0] * (mesh[1] + ncell[1] * mesh[2])
         out.append(np.ascontiguousarray(f + 1e-3 * splitmix64_unit(seed + axis, lin.reshape(-1)).reshape(f.shape)))
     return out
+
+
+def test_rebin_escape_check_leaves_positions_untouched_and_owned_count(api):
+    """IBMethod's error_if_points_leave_domain (IBMethod.cpp:2060 -> LDataManager.cpp:1410-1416): the reference aborts BEFORE it
+    moves anything, so a refused re-bin leaves X as it was; without the flag the points are clamped.  ibk_markers_owned_count
+    tells how many markers a local patch accepted (here one patch covers the lower half of the domain only)."""
+    import ctypes as C
+    n = 16
+    ib = api.IBMethodB200(3, (0,) * 3, (n - 1,) * 3, (0.0,) * 3, (1.0,) * 3, (0, 0, 0), [((0, 0, 0), (n // 2 - 1, n - 1, n - 1))],
+                          kernel_fcn="IB_4", ctx=api.Context(0), error_if_points_leave_domain=True)
+    N = 1000
+    X = np.stack([_uniform(171 + d, N, 0.01, 0.99) for d in range(3)], axis=1)
+    X[7, 1] = 1.25  # outside the (non-periodic) domain
+    ib.setPositions(X)
+    with pytest.raises(api.IBKError) as e:
+        ib.beginDataRedistribution()
+    assert e.value.code == api.IBK_ERR_ESCAPED
+    assert np.array_equal(ib.getLData("X"), X)
+    ib.error_if_points_leave_domain = False
+    ib.beginDataRedistribution()
+    Xc = ib.getLData("X")
+    assert Xc[7, 1] < 1.0 and np.array_equal(np.delete(Xc, 7, axis=0), np.delete(X, 7, axis=0))
+    owned = C.c_int(-1)
+    ib.ctx.check(ib.ctx.lib.ibk_markers_owned_count(ib.ctx.h, C.byref(owned)))
+    assert owned.value == int(np.sum(np.floor(Xc[:, 0] * n) < n // 2))
+    ib.close()
