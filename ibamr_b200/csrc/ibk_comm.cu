@@ -333,6 +333,14 @@ struct Comm
     cudaEvent_t ev_packed[2] = { nullptr, nullptr }, ev_arrived[2] = { nullptr, nullptr };
     ibk_halo_plan* plan = nullptr;
     std::vector<Message> send[2], recv[2]; // per table
+    // all messages of a table and direction share ONE buffer (a message is a slice of it) and ONE item list, so that an
+    // exchange packs with one launch and unpacks with one launch however many neighbours there are ([table][0 send / 1 receive])
+    double* all_buf[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };
+    struct Merged
+    {
+        std::vector<int> patch, axis, lo, hi;
+        std::vector<long long> offs;
+    } merged[2][2];
     bool posted[2] = { false, false };
     long long n_posted[2] = { 0, 0 }; // exchanges posted so far (loopback: a peer must not be behind when this rank finishes)
     // the global box list (migration)
@@ -374,11 +382,17 @@ void free_messages(Comm* c)
         {
             for (Message& m : *v)
             {
-                if (m.d_buf) cudaFree(m.d_buf);
                 if (m.ev_ready) cudaEventDestroy(m.ev_ready);
                 if (m.ev_consumed) cudaEventDestroy(m.ev_consumed);
             }
             v->clear();
+        }
+    for (int t = 0; t < 2; ++t)
+        for (int dir = 0; dir < 2; ++dir)
+        {
+            if (c->all_buf[t][dir]) cudaFree(c->all_buf[t][dir]);
+            c->all_buf[t][dir] = nullptr;
+            c->merged[t][dir] = Comm::Merged();
         }
     if (c->plan) ibk_halo_plan_destroy(c->plan);
     c->plan = nullptr;
@@ -528,13 +542,32 @@ extern "C" int ibk_comm_set_patches(ibk_ctx* ctx, int n_patches, const int* lowe
                 m.offs.push_back(off);
                 off += it.count;
             }
-            CCK(cudaMalloc(&m.d_buf, sizeof(double) * (size_t)std::max<long long>(m.count, 1)));
             if (c->transport == 2)
             {
                 CCK(cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
                 CCK(cudaEventCreateWithFlags(&m.ev_consumed, cudaEventDisableTiming));
             }
             (sending ? c->send[t] : c->recv[t]).push_back(m);
+        }
+    for (int t = 0; t < 2; ++t)
+        for (int dir = 0; dir < 2; ++dir)
+        {
+            std::vector<Message>& v = dir == 0 ? c->send[t] : c->recv[t];
+            long long total = 0;
+            for (Message& m : v) total += (m.count + 15) & ~15ll; // (slices start on 128-byte boundaries)
+            CCK(cudaMalloc(&c->all_buf[t][dir], sizeof(double) * (size_t)std::max<long long>(total, 1)));
+            Comm::Merged& mg = c->merged[t][dir];
+            long long base = 0;
+            for (Message& m : v) // (receive side: ascending source rank = the order of the additions)
+            {
+                m.d_buf = c->all_buf[t][dir] + base;
+                mg.patch.insert(mg.patch.end(), m.patch.begin(), m.patch.end());
+                mg.axis.insert(mg.axis.end(), m.axis.begin(), m.axis.end());
+                mg.lo.insert(mg.lo.end(), m.lo.begin(), m.lo.end());
+                mg.hi.insert(mg.hi.end(), m.hi.begin(), m.hi.end());
+                for (long long o : m.offs) mg.offs.push_back(base + o);
+                base += (m.count + 15) & ~15ll;
+            }
         }
     return IBK_OK;
 }
@@ -551,17 +584,20 @@ int halo_post(ibk_ctx* ctx, int t)
     if (t == 1) // what lies beyond a physical boundary is folded back before any ghost value leaves
         if (int rc = ibk_spread_fold_walls(ctx)) return rc;
     for (Message& m : c->send[t])
-    {
         if (c->transport == 2 && m.consumed_pending) // the peer must have copied the previous content
         {
             CCK(cudaStreamWaitEvent(ctx->L.stream, m.ev_consumed, 0));
             m.consumed_pending = false;
         }
-        if (int rc = ibk_halo_pack_many(ctx, t, (int)m.patch.size(), m.patch.data(), m.axis.data(), m.lo.data(), m.hi.data(), m.offs.data(),
-                                        m.d_buf))
-            return rc;
-        if (c->transport == 2) CCK(cudaEventRecord(m.ev_ready, ctx->L.stream));
+    {
+        const Comm::Merged& mg = c->merged[t][0]; // every message of the exchange in one launch
+        if (!mg.patch.empty())
+            if (int rc = ibk_halo_pack_many(ctx, t, (int)mg.patch.size(), mg.patch.data(), mg.axis.data(), mg.lo.data(), mg.hi.data(),
+                                            mg.offs.data(), c->all_buf[t][0]))
+                return rc;
     }
+    if (c->transport == 2)
+        for (Message& m : c->send[t]) CCK(cudaEventRecord(m.ev_ready, ctx->L.stream));
     if (c->transport == 1)
     {
         // the messages start when the packing is done and run on the communication stream
@@ -602,9 +638,13 @@ int halo_finish(ibk_ctx* ctx, int t)
             CCK(cudaEventRecord(src->ev_consumed, ctx->L.stream));
             src->consumed_pending = true;
         }
-        if (int rc = ibk_halo_unpack_many(ctx, t, (int)m.patch.size(), m.patch.data(), m.axis.data(), m.lo.data(), m.hi.data(), m.offs.data(),
-                                          m.d_buf, t == 0 ? 0 : 1))
-            return rc;
+    }
+    {
+        const Comm::Merged& mg = c->merged[t][1]; // all received messages in one launch, items in ascending source-rank order
+        if (!mg.patch.empty())
+            if (int rc = ibk_halo_unpack_many(ctx, t, (int)mg.patch.size(), mg.patch.data(), mg.axis.data(), mg.lo.data(), mg.hi.data(),
+                                              mg.offs.data(), c->all_buf[t][1], t == 0 ? 0 : 1))
+                return rc;
     }
     c->posted[t] = false;
     return IBK_OK;
