@@ -113,7 +113,8 @@ class ClockSampler(threading.Thread):
 # CPU baseline / reference arm
 # --------------------------------------------------------------------------------------------------
 def cpu_baseline(steps=2, warmup=1, n=256, log2_markers=20):
-    """The reference's CPU path (oracle port) on all host cores, on a density-preserving sample."""
+    """The reference's CPU path (oracle port) on all host cores: uniform markers on an n^3 periodic grid, a few passes (bounded:
+    a pass over the 512^3 / 2^23 workload takes about a second on 16 threads)."""
     from oracle import oracle as orc
     threads = orc.Baseline.threads()
     # one patch per worker, SAMRAI-style box decomposition of the n^3 sample
@@ -624,7 +625,7 @@ def run_gpu(args):
                 "each operation's exchange overlaps its own interior tiles (boundary tiles first)"))
         line["check"] = check
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline()
+            cb = cpu_baseline(n=args.cells, log2_markers=args.log2_markers)  # the N = 1 workload itself (what --impl reference runs)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if world == 1 and not args.no_sample_parity:
             line["check"]["sample_vs_oracle"] = sample_parity(local_rank)
