@@ -303,8 +303,117 @@ static int run_restart(const char* tmp_path)
     return 0;
 }
 
+// N3 through the C++ seam: two levels resident on one device, LDataManagerB200 of the finer one with setCoarserLevel.
+// spread: the coarse level's f is a constant, the fine markers carry no force, the prolongation schedule of level 1 is set
+// -> the fine f must be that constant on every patch interior (a constant has no slope).  interp: the fine u is linear in x,
+// the synchronisation schedule of level 1 is set -> the coarse u under the fine patch must be the same linear field (the
+// area mean of a linear field is its value at the centre).
+static int run_amr()
+{
+    try
+    {
+        const int nc = 16, ratio = 2, g = 3, N = 2000;
+        IBAMR_B200::IBMethodB200::LevelSpec lc, lf;
+        lc.domain_box = Box(Index(0), Index(nc - 1));
+        lf.domain_box = Box(Index(0), Index(nc * ratio - 1));
+        for (int d = 0; d < 3; ++d)
+        {
+            lc.x_lower[d] = lf.x_lower[d] = 0.0;
+            lc.x_upper[d] = lf.x_upper[d] = 1.0;
+            lc.periodic[d] = lf.periodic[d] = 1;
+        }
+        lc.patch_boxes.push_back(lc.domain_box);
+        const Box fine_box(Index(8), Index(23));
+        lf.patch_boxes.push_back(fine_box);
+        IBAMR_B200::IBMethodB200 ibc(lc, "IB_4", 0, g), ibf(lf, "IB_4", 0, g);
+        std::vector<double> X((size_t)N * 3), F((size_t)N * 3, 0.0);
+        unsigned long long sd = 99;
+        for (auto& v : X)
+        {
+            sd = sd * 6364136223846793005ull + 1442695040888963407ull;
+            v = 0.4 + 0.2 * (double)(sd >> 11) * (1.0 / 9007199254740992.0); // well inside the fine patch
+        }
+        ibf.setPositions(X);
+        ibf.setForce(F);
+        ibf.beginDataRedistribution();
+        const int r3[3] = { ratio, ratio, ratio };
+        IBTK_B200::LDataManagerB200 mgr(ibf, 1);
+        mgr.setCoarserLevel(&ibc, r3);
+        std::vector<Pointer<IBTK_B200::LDataB200>> Xd(2), Fd(2), Ud(2);
+        Xd[1] = std::make_shared<IBTK_B200::LDataB200>("X", ibf.ctx(), IBK_COL_X, 3);
+        Fd[1] = std::make_shared<IBTK_B200::LDataB200>("F", ibf.ctx(), IBK_COL_F, 3);
+        Ud[1] = std::make_shared<IBTK_B200::LDataB200>("U", ibf.ctx(), IBK_COL_U, 3);
+        // ---- spread with prolongation
+        if (ibk_grid_fill(ibc.ctx(), 1, 2.5) != IBK_OK || ibk_grid_fill(ibf.ctx(), 1, -1.0) != IBK_OK) return 1;
+        std::vector<Pointer<RefineSchedule>> prolong(2);
+        prolong[1] = std::make_shared<RefineSchedule>();
+        mgr.spread(-1, Fd, Xd, "IB_4", nullptr, prolong, 0.0);
+        const int nf = 16 + 2 * g;
+        for (int a = 0; a < 3; ++a)
+        {
+            const int n0 = nf + (a == 0), n1 = nf + (a == 1), n2 = nf + (a == 2);
+            std::vector<double> f((size_t)n0 * n1 * n2);
+            if (ibk_grid_download(ibf.ctx(), 1, 0, a, f.data()) != IBK_OK) return 1;
+            for (int k = g; k < n2 - g; ++k)
+                for (int j = g; j < n1 - g; ++j)
+                    for (int i = g; i < n0 - g; ++i)
+                        if (f[((size_t)k * n1 + j) * n0 + i] != 2.5)
+                        {
+                            std::printf("amr: prolonged f is %.17g at (%d,%d,%d) of axis %d\n", f[((size_t)k * n1 + j) * n0 + i], i, j, k, a);
+                            return 1;
+                        }
+        }
+        // ---- interp with synchronisation
+        const double hf = 1.0 / (nc * ratio), hc = 1.0 / nc;
+        for (int a = 0; a < 3; ++a)
+        {
+            const int n0 = nf + (a == 0), n1 = nf + (a == 1), n2 = nf + (a == 2);
+            std::vector<double> u((size_t)n0 * n1 * n2);
+            for (int k = 0; k < n2; ++k)
+                for (int j = 0; j < n1; ++j)
+                    for (int i = 0; i < n0; ++i) u[((size_t)k * n1 + j) * n0 + i] = 1.0 + 2.0 * ((8 - g + i) + (a == 0 ? 0.0 : 0.5)) * hf;
+            if (ibk_grid_upload(ibf.ctx(), 0, 0, a, u.data()) != IBK_OK) return 1;
+        }
+        if (ibk_grid_fill(ibc.ctx(), 0, 0.0) != IBK_OK) return 1;
+        std::vector<Pointer<CoarsenSchedule>> synch(2);
+        synch[1] = std::make_shared<CoarsenSchedule>();
+        mgr.interp(-1, Ud, Xd, synch, {}, 0.0);
+        const int ncg = nc + 2 * g;
+        double worst = 0.0;
+        long long covered = 0;
+        for (int a = 0; a < 3; ++a)
+        {
+            const int n0 = ncg + (a == 0), n1 = ncg + (a == 1), n2 = ncg + (a == 2);
+            std::vector<double> u((size_t)n0 * n1 * n2);
+            if (ibk_grid_download(ibc.ctx(), 0, 0, a, u.data()) != IBK_OK) return 1;
+            const int hi[3] = { 11 + (a == 0), 11 + (a == 1), 11 + (a == 2) }; // coarse sides tiled by the fine patch [8, 23]
+            for (int k = 4; k <= hi[2]; ++k)
+                for (int j = 4; j <= hi[1]; ++j)
+                    for (int i = 4; i <= hi[0]; ++i)
+                    {
+                        const double want = 1.0 + 2.0 * (i + (a == 0 ? 0.0 : 0.5)) * hc;
+                        worst = std::max(worst, std::fabs(u[((size_t)(k + g) * n1 + (j + g)) * n0 + (i + g)] - want));
+                        ++covered;
+                    }
+        }
+        if (worst > 1e-13 || covered == 0)
+        {
+            std::printf("amr: coarsened u off by %.3e\n", worst);
+            return 1;
+        }
+        std::printf("amr ok\n");
+    }
+    catch (const std::exception& e)
+    {
+        std::printf("amr error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc >= 2 && !std::strcmp(argv[1], "--amr")) return run_amr();
     if (argc >= 3 && !std::strcmp(argv[1], "--restart")) return run_restart(argv[2]);
     if (argc >= 2 && !std::strcmp(argv[1], "--static")) return run_static();
     if (argc >= 4 && !std::strcmp(argv[1], "--two-ranks")) return run_two_ranks(argv[2], argv[3]);

@@ -228,3 +228,11 @@ def test_cpp_ldata_restart_round_trip(driver, tmp_path):
     back bit for bit and the spread after the restart equals the spread before it bit for bit."""
     r = subprocess.run([driver, "--restart", str(tmp_path / "ldata")], capture_output=True, text=True)
     assert r.returncode == 0 and "restart ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_two_level_prolong_and_coarsen(driver):
+    """N3 through the C++ seam: LDataManagerB200::setCoarserLevel + the schedule arguments of spread / interp
+    (LDataManager.cpp:611-614, 728-734) over two levels resident on one device."""
+    r = subprocess.run([driver, "--amr"], capture_output=True, text=True)
+    assert r.returncode == 0 and "amr ok" in r.stdout, r.stdout + r.stderr
