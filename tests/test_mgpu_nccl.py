@@ -37,3 +37,9 @@ def test_multi_gpu_parity_two_ranks():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MGPU_PARITY" in r.stdout and "overlap=1" in r.stdout
+    # the pipelined sequence of bench.py (each exchange behind the other operation's kernel)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29520", os.path.join(root, "tests", "mgpu_worker.py"), "IB_4", "pipelined"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MGPU_PARITY" in r.stdout and "pipelined=1" in r.stdout
