@@ -181,6 +181,7 @@ extern "C" int ibk_ctx_destroy(ibk_ctx* ctx)
     for (auto& b : ctx->b_io) b.release();
     for (auto& b : ctx->b_stage) b.release();
     for (auto& b : ctx->b_mig) b.release();
+    for (auto& b : ctx->b_user) b.release();
     if (ctx->ev_created)
         for (int i = 0; i < 3; ++i)
         {

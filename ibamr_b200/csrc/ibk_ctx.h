@@ -118,4 +118,5 @@ struct ibk_ctx
     bool pend_in[2] = { false, false }, pend_out[2] = { false, false };
     ibk::DevBuf b_mig[10];  // marker migration scratch (keys/vals ping-pong, sort temp, box list, offsets; [8], [9]: send / receive rows of ibk_migrate)
     ibk::DevBuf b_stage[3]; // staging blocks of the grid transfers: compute stream, copy-in stream, copy-out stream
+    ibk::DevBuf b_user[10]; // USER_DEFINED kernel (ibk_user.cu): ranges, weights, rows; contribution keys / values of the spread
 };

@@ -200,10 +200,10 @@ extern "C" int ibk_construct_sc_interp_op(ibk_ctx* ctx, int interp_fcn, const in
     int npts = 1;
     for (int d = 0; d < ndim; ++d) npts *= S;
     const size_t rows = (size_t)ndim * n;
-    CK(ctx->b_io[5].reserve(sizeof(int) * total));
-    CK(ctx->b_io[6].reserve(sizeof(int) * (rows * npts + 1)));
-    CK(ctx->b_io[7].reserve(sizeof(double) * rows * npts));
-    int* d_dof = ctx->b_io[5].as<int>();
+    CK(ctx->b_user[0].reserve(sizeof(int) * total));
+    CK(ctx->b_user[1].reserve(sizeof(int) * (rows * npts + 1)));
+    CK(ctx->b_user[2].reserve(sizeof(double) * rows * npts));
+    int* d_dof = ctx->b_user[0].as<int>();
     size_t off = 0;
     for (size_t p = 0; p < lv.patches.size(); ++p)
     {
@@ -224,9 +224,9 @@ extern "C" int ibk_construct_sc_interp_op(ibk_ctx* ctx, int interp_fcn, const in
             off += cnt;
         }
     }
-    int* d_cols = ctx->b_io[6].as<int>();
+    int* d_cols = ctx->b_user[1].as<int>();
     int* d_count = d_cols + rows * npts;
-    double* d_vals = ctx->b_io[7].as<double>();
+    double* d_vals = ctx->b_user[2].as<double>();
     CK(cudaMemsetAsync(d_count, 0, sizeof(int), ctx->L.stream));
     const unsigned blocks = (unsigned)((rows + 127) / 128);
     if (S == 4)

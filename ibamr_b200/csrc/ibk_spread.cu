@@ -38,7 +38,6 @@
 namespace ibk
 {
 constexpr int SPREAD_THREADS = 256;
-constexpr int SPREAD_WARPS = SPREAD_THREADS / 32;
 
 struct SpreadArgs
 {

@@ -285,7 +285,7 @@ int user_entries_op(ibk_ctx* ctx, int op, const TileParams& tp, const CellGeom& 
             }
     }
     // ---- device
-    DevBuf &b_lo = ctx->b_io[5], &b_cnt = ctx->b_io[6], &b_w = ctx->b_io[7], &b_rows = ctx->b_mig[0];
+    DevBuf &b_lo = ctx->b_user[0], &b_cnt = ctx->b_user[1], &b_w = ctx->b_user[2], &b_rows = ctx->b_user[3];
     CK(b_lo.reserve(sizeof(int) * lo.size()));
     CK(b_cnt.reserve(sizeof(int) * cnt.size()));
     CK(b_w.reserve(sizeof(double) * w.size()));
@@ -308,7 +308,7 @@ int user_entries_op(ibk_ctx* ctx, int op, const TileParams& tp, const CellGeom& 
     for (int d = 0; d < ndim; ++d) npts *= S;
     const long long n_pairs = (long long)nl * ncomp * npts;
     if (n_pairs > (1ll << 30)) return fail(ctx, IBK_ERR_INVALID, "USER_DEFINED spread: too many contributions for one call (split the index list)");
-    DevBuf &b_ka = ctx->b_mig[1], &b_kb = ctx->b_mig[2], &b_va = ctx->b_mig[3], &b_vb = ctx->b_mig[4], &b_val = ctx->b_mig[5], &b_tmp = ctx->b_mig[6];
+    DevBuf &b_ka = ctx->b_user[4], &b_kb = ctx->b_user[5], &b_va = ctx->b_user[6], &b_vb = ctx->b_user[7], &b_val = ctx->b_user[8], &b_tmp = ctx->b_user[9];
     CK(b_ka.reserve(sizeof(uint64_t) * n_pairs));
     CK(b_kb.reserve(sizeof(uint64_t) * n_pairs));
     CK(b_va.reserve(sizeof(uint32_t) * n_pairs));
