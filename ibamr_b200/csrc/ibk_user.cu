@@ -31,22 +31,14 @@ int cuda_fail(ibk_ctx* ctx, cudaError_t e, const char* what);
 
 namespace
 {
-double default_kernel_fcn(double r) // ib4_kernel_fcn, LEInteractor.cpp:1526-1546
+// the reference's default for s_kernel_fcn: the 4-point function (ib4_kernel_fcn, LEInteractor.cpp:1526-1546), same operations
+double default_kernel_fcn(double r)
 {
-    r = std::abs(r);
-    if (r < 1.0)
-    {
-        const double t2 = r * r;
-        const double t6 = std::sqrt(-0.4e1 * t2 + 0.4e1 * r + 0.1e1);
-        return -r / 0.4e1 + 0.3e1 / 0.8e1 + t6 / 0.8e1;
-    }
-    else if (r < 2.0)
-    {
-        const double t2 = r * r;
-        const double t6 = std::sqrt(0.12e2 * r - 0.7e1 - 0.4e1 * t2);
-        return -r / 0.4e1 + 0.5e1 / 0.8e1 - t6 / 0.8e1;
-    }
-    return 0.0;
+    const double a = std::abs(r);
+    if (a >= 2.0) return 0.0;
+    const double a2 = a * a;
+    if (a < 1.0) return -a / 4.0 + 3.0 / 8.0 + std::sqrt(-4.0 * a2 + 4.0 * a + 1.0) / 8.0;
+    return -a / 4.0 + 5.0 / 8.0 - std::sqrt(12.0 * a - 7.0 - 4.0 * a2) / 8.0;
 }
 ibk_kernel_fcn g_user_fcn = &default_kernel_fcn;
 int g_user_stencil = 4;

@@ -116,17 +116,14 @@ def spread_raw(kernel, ndim, dx, x_lower, depth, indices, Xshift, X, V, ilower, 
 
 
 def ib4_kernel_fcn(r):
-    """LEInteractor.cpp:1526-1546, the default of LEInteractor::s_kernel_fcn (scalar)"""
-    r = abs(r)
-    if r < 1.0:
-        t2 = r * r
-        t6 = np.sqrt(-0.4e1 * t2 + 0.4e1 * r + 0.1e1)
-        return -r / 0.4e1 + 0.3e1 / 0.8e1 + t6 / 0.8e1
-    if r < 2.0:
-        t2 = r * r
-        t6 = np.sqrt(0.12e2 * r - 0.7e1 - 0.4e1 * t2)
-        return -r / 0.4e1 + 0.5e1 / 0.8e1 - t6 / 0.8e1
-    return 0.0
+    """the default of LEInteractor::s_kernel_fcn (the 4-point function, LEInteractor.cpp:1526-1546), scalar"""
+    a = abs(r)
+    if a >= 2.0:
+        return 0.0
+    a2 = a * a
+    if a < 1.0:
+        return -a / 4.0 + 3.0 / 8.0 + np.sqrt(-4.0 * a2 + 4.0 * a + 1.0) / 8.0
+    return -a / 4.0 + 5.0 / 8.0 - np.sqrt(12.0 * a - 7.0 - 4.0 * a2) / 8.0
 
 
 def _user_stencils(kernel_fcn, stencil, ndim, dx, x_lower, ilower, iupper, nugc, X, Xshift, l, s):
