@@ -317,7 +317,7 @@ int user_entries_op(ibk_ctx* ctx, int op, const TileParams& tp, const CellGeom& 
 // and Xr (raw) of stride `stride`; values are addressed through d_indices (nullable).
 int run_entries_op(ibk_ctx* ctx, int op, int kernel, TileParams& tp, const CellGeom& cg, PatchBin& pb, const double* d_Xe,
                    const double* d_Xr, long long stride, int n_entries, const int* d_indices, double* d_V, long long v_cstride,
-                   long long v_istride, bool zero_unreached = true)
+                   long long v_istride, bool zero_unreached = true, const int* box_lo = nullptr, const int* box_hi = nullptr)
 {
     if (n_entries <= 0) return IBK_OK;
     if (kernel == IBK_USER_DEFINED) // host callback: its own path (ibk_user.cu); position-only forms list by the box
@@ -354,6 +354,9 @@ int run_entries_op(ibk_ctx* ctx, int op, int kernel, TileParams& tp, const CellG
     if (op == 0 && zero_unreached)
         CK(zero_discarded(ctx->L, ctx->sbins.brick_start, ctx->sbins.total_bricks, n_entries, mv.src, d_V, v_cstride, v_istride,
                           tp.ncomp));
+    else if (op == 0 && box_lo && box_hi) // position-only: the markers of the caller's box that the binning did not accept
+        CK(zero_discarded_in_box(ctx->L, ctx->sbins.brick_start, ctx->sbins.total_bricks, n_entries, mv.X, mv.x_stride, cg, box_lo, box_hi,
+                                 mv.src, d_V, v_cstride, v_istride, tp.ncomp));
     cudaError_t e = (op == 0) ? launch_interp(ctx->L, kernel, tp, ctx->sbins, mv, err) :
                                 launch_spread(ctx->L, kernel, tp, ctx->sbins, mv, err);
     if (e != cudaSuccess) return cuda_fail(ctx, e, err.empty() ? "tile kernel launch" : err.c_str());
@@ -638,7 +641,8 @@ static int patch_host_op(ibk_ctx* ctx, int op, const char* fcn, const ibk_patch_
     CK(build_entries(ctx->L, ctx->b_io[3].as<double>(), d_idx, d_shift, n_entries, ndim, ctx->b_Xe.as<double>(),
                      ctx->b_Xr.as<double>(), n_entries));
     int rc = run_entries_op(ctx, op, kernel, tp, cg, pb, ctx->b_Xe.as<double>(), d_shift ? ctx->b_Xr.as<double>() : nullptr,
-                            n_entries, n_entries, d_idx, ctx->b_io[4].as<double>(), 1, Q_depth, /*zero_unreached*/ indexed);
+                            n_entries, n_entries, d_idx, ctx->b_io[4].as<double>(), 1, Q_depth, /*zero_unreached*/ indexed,
+                            indexed ? nullptr : box_lower, indexed ? nullptr : box_upper);
     if (rc != IBK_OK) return rc;
     if (op == 0)
     {

@@ -309,7 +309,7 @@ NcclApi& nccl()
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
     return api;
 }
-constexpr int NCCL_FLOAT64 = 8, NCCL_INT32 = 2; // ncclDataType_t values (nccl.h)
+constexpr int NCCL_FLOAT64 = 8; // ncclDataType_t values (nccl.h)
 
 struct Message
 {

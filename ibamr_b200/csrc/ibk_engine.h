@@ -248,6 +248,10 @@ cudaError_t build_entries(Launcher& L, const double* d_X_aos, const int* d_idx, 
                           double* d_Xe, double* d_Xr, long long stride);
 cudaError_t zero_discarded(Launcher& L, const int* brick_start, int total_bricks, int n, const uint32_t* src, double* V,
                            long long v_cstride, long long v_istride, int ncol);
+// the same for the entries whose cell lies in [box_lo, box_hi] only (Xs: the entries' positions in sorted order)
+cudaError_t zero_discarded_in_box(Launcher& L, const int* brick_start, int total_bricks, int n, const double* Xs, long long stride,
+                                  const CellGeom& cg, const int* box_lo, const int* box_hi, const uint32_t* src, double* V,
+                                  long long v_cstride, long long v_istride, int ncol);
 cudaError_t compose_index(Launcher& L, const int* d_idx, const uint32_t* d_perm, uint32_t* d_out, int n);
 
 } // namespace ibk

@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "ibk_engine.h"
+#include "ibk_device.cuh"
 
 namespace ibk
 {
@@ -342,6 +343,51 @@ cudaError_t zero_discarded(Launcher& L, const int* brick_start, int total_bricks
 {
     if (n <= 0) return cudaSuccess;
     zero_discarded_kernel<<<64, 256, 0, L.stream>>>(brick_start, total_bricks, n, src, V, v_cstride, v_istride, ncol);
+    L.launches++;
+    return cudaGetLastError();
+}
+
+// Position-only interpolation: a marker whose cell lies in the caller's box but outside the range the binning accepts
+// (farther than gcw + 4 cells from the patch) has no array point under its stencil: the reference lists it
+// (LEInteractor::buildLocalIndices), interpolates a fully clipped stencil and writes 0 (LEInteractor.cpp:3117-3120).
+struct BoxTest
+{
+    CellGeom cg;
+    int lo[3], hi[3];
+};
+__global__ void zero_discarded_in_box_kernel(const int* __restrict__ brick_start, int total_bricks, int n, const double* __restrict__ Xs,
+                                             long long stride, BoxTest bt, const uint32_t* __restrict__ src, double* __restrict__ V,
+                                             long long v_cstride, long long v_istride, int ncol)
+{
+    const int first = brick_start[total_bricks];
+    for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        bool in = true;
+        for (int d = 0; d < bt.cg.ndim; ++d)
+        {
+            const double x = Xs[d * stride + i];
+            const int c = bt.cg.two_branch ? cell_index_1d(x, bt.cg.x_lower[d], bt.cg.x_upper[d], bt.cg.dx[d], bt.cg.ilower[d], bt.cg.iupper[d]) :
+                                             bt.cg.ilower[d] + (int)floor(__ddiv_rn(__dsub_rn(x, bt.cg.x_lower[d]), bt.cg.dx[d]));
+            in = in && c >= bt.lo[d] && c <= bt.hi[d];
+        }
+        if (!in) continue;
+        const long long row = src ? (long long)src[i] : (long long)i;
+        for (int c = 0; c < ncol; ++c) V[c * v_cstride + row * v_istride] = 0.0;
+    }
+}
+cudaError_t zero_discarded_in_box(Launcher& L, const int* brick_start, int total_bricks, int n, const double* Xs, long long stride,
+                                  const CellGeom& cg, const int* box_lo, const int* box_hi, const uint32_t* src, double* V,
+                                  long long v_cstride, long long v_istride, int ncol)
+{
+    if (n <= 0) return cudaSuccess;
+    BoxTest bt;
+    bt.cg = cg;
+    for (int d = 0; d < 3; ++d)
+    {
+        bt.lo[d] = d < cg.ndim ? box_lo[d] : 0;
+        bt.hi[d] = d < cg.ndim ? box_hi[d] : 0;
+    }
+    zero_discarded_in_box_kernel<<<64, 256, 0, L.stream>>>(brick_start, total_bricks, n, Xs, stride, bt, src, V, v_cstride, v_istride, ncol);
     L.launches++;
     return cudaGetLastError();
 }

@@ -930,3 +930,33 @@ def test_rebin_escape_check_leaves_positions_untouched_and_owned_count(api):
     ib.ctx.check(ib.ctx.lib.ibk_markers_owned_count(ib.ctx.h, C.byref(owned)))
     assert owned.value == int(np.sum(np.floor(Xc[:, 0] * n) < n // 2))
     ib.close()
+
+
+@pytest.mark.parametrize("kernel", ["IB_4", "PIECEWISE_LINEAR"])
+def test_position_only_interpolate_far_box(api, kernel):
+    """a position-only interpolate whose box reaches farther from the patch than the binning accepts (gcw + 4 cells).
+    The reference lists every marker of the box (LEInteractor::buildLocalIndices, LEInteractor.cpp:6088-6126); one whose stencil
+    finds no array point gets 0 (:3117-3120); markers outside the box keep the caller's values."""
+    ndim, n = 2, 8
+    g = orc.min_ghost_width(kernel)
+    lo, hi = (0, 0), (n - 1, n - 1)
+    dx = (1.0 / n,) * 2
+    pg = orc.PatchGeom(lo, hi, (0.0, 0.0), (1.0, 1.0), dx, (g,) * 2)
+    box = api.Box(lo, hi)
+    patch = api.Patch(box, (0.0, 0.0), (1.0, 1.0), dx)
+    u = _side_fields(pg, 100)
+    N = 4000
+    X = np.stack([_uniform(3 + d, N, -2.5, 3.5) for d in range(2)], axis=1)  # up to 20 cells away from the patch
+    far = api.Box((-14, -14), (n - 1 + 14, n - 1 + 14))
+    Q0 = np.full((N, 2), 5.0)
+    idx = orc.indices_in_box(X, pg, far.lower, far.upper)
+    Qo = orc.side_interp(kernel, pg, u, X, idx, None, Q0.copy())
+    q = api.SideData(box, 1, g, u)
+    Q = Q0.copy()
+    api.LEInteractor.interpolate(Q, 2, X, 2, q, patch, far, kernel)
+    listed = np.zeros(N, bool)
+    listed[idx] = True
+    assert listed.sum() > 100 and (~listed).sum() > 100
+    assert np.array_equal(Q[~listed], Q0[~listed])
+    assert np.count_nonzero(Qo[listed].any(axis=1) == 0) > 50  # the far ones interpolate to exactly 0
+    assert np.max(np.abs(Q - Qo)) <= TOL * np.max(np.abs(Qo))
