@@ -47,6 +47,14 @@ def test_kernel_queries_match_leinteractor(lib):
         assert lib.ibk_is_known_kernel(name.encode()) == 1
         assert lib.ibk_get_stencil_size(name.encode()) == sz
         assert lib.ibk_get_minimum_ghost_width(name.encode()) == g
+    # "USER_DEFINED": the statics of LEInteractor (defaults LEInteractor.cpp:2019-2020: the 4-point function, stencil 4)
+    assert lib.ibk_is_known_kernel(b"USER_DEFINED") == 1 and lib.ibk_get_stencil_size(b"USER_DEFINED") == 4
+    cb = C.CFUNCTYPE(C.c_double, C.c_double)(lambda r: max(0.0, 1.0 - abs(r)))
+    assert lib.ibk_set_user_kernel(cb, 2) == 0 and lib.ibk_get_stencil_size(b"USER_DEFINED") == 2
+    assert lib.ibk_get_minimum_ghost_width(b"USER_DEFINED") == 2
+    assert lib.ibk_set_user_kernel(cb, 0) == -1  # IBK_ERR_INVALID
+    assert lib.ibk_set_user_kernel(C.cast(None, C.CFUNCTYPE(C.c_double, C.c_double)), 0) == 0  # back to the default
+    assert lib.ibk_get_stencil_size(b"USER_DEFINED") == 4
     assert lib.ibk_is_known_kernel(b"IB_7") == 0
     assert lib.ibk_get_stencil_size(b"NOPE") == -3  # IBK_ERR_UNKNOWN_KERNEL
     assert lib.ibk_kernel_from_string(b"IB_4") == 1
